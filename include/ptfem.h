@@ -1,0 +1,189 @@
+/*
+ * ptfem.h — C-ABI of libptfem.so, the B200-native steady-current-conduction FEM engine.
+ *
+ * Drop-in boundary.  The reference (alisabryantseva/pelvistim-fem) has no in-process
+ * solver API: it shells out to `ElmerGrid 14 2 mesh.msh -out elmer_mesh` and
+ * `ElmerSolver case.sif` (step03_ankle_layers/run_layered_sweep.py:1077,1099;
+ * step04_pressure/run_pressure_sweep.py:696,727; step02_electrodes/run_sweep.py:315,327;
+ * step01_box/test_step01_baseline.py:49,52) and reads results/case_t0001.vtu back.
+ * Everything ElmerSolver does between "mesh directory + case.sif" and "nodal potential +
+ * nodal volume current" is replaced by the entry points below; each one names the Elmer
+ * stage / SIF keyword it stands in for.  Host code (Python, ctypes) parses the files and
+ * calls these with plain pointers and sizes.
+ *
+ * Conventions: every function returns 0 on success, <0 on error (ptfem_last_error() gives the
+ * message, thread-local).  Host buffers are caller-owned; device buffers are library-owned and
+ * live behind the opaque handles.  Node / element indices are 0-based.  One context per GPU;
+ * a handle is not thread-safe, different handles may be used from different threads.
+ * All floating point is IEEE double.  There is no CPU fallback: without a CUDA device
+ * ptfem_ctx_create fails.
+ */
+#ifndef PTFEM_H
+#define PTFEM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ptfem_ctx ptfem_ctx;
+typedef struct ptfem_mesh ptfem_mesh;
+
+#define PTFEM_OK 0
+#define PTFEM_ERR_ARG (-1)
+#define PTFEM_ERR_CUDA (-2)
+#define PTFEM_ERR_STATE (-3)
+#define PTFEM_ERR_NOCONV (-4)
+#define PTFEM_ERR_NCCL (-5)
+
+/* preconditioners (replaces `Linear System Direct Method = UMFPACK`, step01_box/case.sif:41-42) */
+#define PTFEM_PRECOND_JACOBI 0
+#define PTFEM_PRECOND_CHEBYSHEV 1
+
+/* nodal current recovery (replaces `Calculate Volume Current = True`, step01_box/case.sif:39) */
+#define PTFEM_RECOVER_L2 0      /* Galerkin L2 projection, consistent mass matrix (PCG on the same pattern) */
+#define PTFEM_RECOVER_LUMPED 1  /* volume-weighted nodal mean (row-sum lumped mass) */
+#define PTFEM_RECOVER_AVERAGE 2 /* unweighted mean over the tets touching a node */
+
+/* SpMV kernel variants for ptfem_spmv / ptfem_spmv_bench */
+#define PTFEM_SPMV_AUTO 0
+#define PTFEM_SPMV_VECTOR 1  /* sub-warp per row, direct global loads */
+#define PTFEM_SPMV_STREAM 2  /* persistent CTAs, val/col staged into shared memory by bulk async copies */
+
+typedef struct ptfem_solve_opts {
+  int32_t precond;      /* PTFEM_PRECOND_* */
+  int32_t maxit;        /* iteration cap (per system) */
+  int32_t check_every;  /* residual is copied to the host every this many iterations */
+  int32_t cheb_degree;  /* polynomial degree for PTFEM_PRECOND_CHEBYSHEV */
+  double rtol;          /* stop when ||r||_2 <= rtol * ||b||_2 for every system */
+  double cheb_ratio;    /* lambda_max / lambda_min assumed by the Chebyshev polynomial */
+  int32_t spmv_variant; /* PTFEM_SPMV_* */
+  int32_t use_graph;    /* capture check_every iterations in a CUDA graph */
+} ptfem_solve_opts;
+
+typedef struct ptfem_solve_stats {
+  int32_t iterations;   /* CG iterations executed (same for every system of the batch) */
+  int32_t converged;    /* 1 if every system met rtol */
+  int32_t nsys;         /* systems solved at once */
+  int32_t spmv_calls;   /* sparse matrix-vector products launched (all systems count as one) */
+  double rel_residual;  /* max over systems of recurrence ||r|| / ||b|| at exit */
+  double true_rel_residual; /* max over systems of ||b - A x|| / ||b|| recomputed at exit */
+  double solve_ms;      /* device time of the iteration loop (CUDA events) */
+  double spmv_ms;       /* device time of one SpMV launch, sampled with events after the solve */
+} ptfem_solve_stats;
+
+const char* ptfem_last_error(void);
+int ptfem_version(void);
+int ptfem_device_count(int* n);
+
+/* -- context: one per GPU ------------------------------------------------------------------ */
+int ptfem_ctx_create(int device, ptfem_ctx** out);
+int ptfem_ctx_destroy(ptfem_ctx* ctx);
+int ptfem_ctx_sync(ptfem_ctx* ctx);
+/* kernels launched by this context since creation (for bench.py's gpu_launches) */
+int ptfem_ctx_launch_count(ptfem_ctx* ctx, int64_t* n);
+
+/* -- mesh: replaces ElmerSolver's reading of elmer_mesh/{mesh.nodes,mesh.elements,mesh.boundary}
+ *    (formats: step01_box/find_boundaries.py:16-40,87-90).  Copies host arrays to the device. */
+int ptfem_mesh_create(ptfem_ctx* ctx, int64_t nn, const double* xyz /*[nn*3]*/, int64_t nt,
+                      const int32_t* tets /*[nt*4]*/, const int32_t* region /*[nt]*/, int64_t nb,
+                      const int32_t* tris /*[nb*3]*/, const int32_t* bcid /*[nb]*/, ptfem_mesh** out);
+int ptfem_mesh_destroy(ptfem_mesh* m);
+/* geometry change on fixed topology (node displacement; reference example:
+ * run_layered_sweep.py:329-340): keeps the pattern, recomputes element geometry factors. */
+int ptfem_mesh_set_coords(ptfem_mesh* m, const double* xyz /*[nn*3]*/);
+
+/* -- K1: CSR pattern + element->nnz map (Elmer's matrix-structure creation). Idempotent. ----- */
+int ptfem_pattern(ptfem_mesh* m, int64_t* nnz);
+int ptfem_pattern_get(ptfem_mesh* m, int32_t* rowptr /*[nn+1]*/, int32_t* col /*[nnz]*/);
+int ptfem_e2nnz_get(ptfem_mesh* m, int32_t* e2nnz /*[nt*16]*/);
+
+/* -- K2+K3: bulk assembly of StatCurrentSolve (sum_e sigma_e V_e gradNi.gradNj).
+ *    nsys > 1 assembles nsys matrices on the one pattern (batched-values mode): sigma is
+ *    [nsys][nreg].  nsys == 1 and a later solve with nrhs > 1 is the multi-RHS mode. -------- */
+int ptfem_assemble(ptfem_mesh* m, int32_t nreg, const int32_t* reg_ids /*[nreg]*/,
+                   const double* sigma /*[nsys*nreg]*/, int32_t nsys);
+int ptfem_values_get(ptfem_mesh* m, int32_t sys, int32_t with_bc, double* val /*[nnz]*/);
+
+/* -- K4: boundary conditions (SIF `Boundary Condition` blocks).  rhs = -1 means every column. -- */
+int ptfem_bc_reset(ptfem_mesh* m, int32_t nrhs);
+/* `Potential = value` on every node of boundary elements with id bcid (step01_box/case.sif:61-71) */
+int ptfem_bc_dirichlet(ptfem_mesh* m, int32_t rhs, int32_t bcid, double value);
+/* `Current Density = g` on boundary elements with id bcid (run_layered_sweep.py:608-611);
+ * positive g drives current into the domain */
+int ptfem_bc_neumann(ptfem_mesh* m, int32_t rhs, int32_t bcid, double g);
+/* same, for an explicit list of boundary-triangle indices (electrode patches of a sweep) */
+int ptfem_bc_neumann_tris(ptfem_mesh* m, int32_t rhs, int64_t n, const int32_t* tri_idx, double g);
+int ptfem_rhs_get(ptfem_mesh* m, int32_t rhs, double* b /*[nn]*/);
+
+/* -- K5-K9: PCG solve (replaces the UMFPACK solve).  Systems solved at once =
+ *    max(nsys of ptfem_assemble, nrhs of ptfem_bc_reset).  phi is [nsys_total][nn]. ---------- */
+void ptfem_solve_opts_default(ptfem_solve_opts* o);
+int ptfem_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* phi, ptfem_solve_stats* stats);
+/* device-resident variant: same work, no host copies (phi stays on the device for post-processing) */
+int ptfem_solve_device(ptfem_mesh* m, const ptfem_solve_opts* opts, ptfem_solve_stats* stats);
+int ptfem_phi_get(ptfem_mesh* m, int32_t sys, double* phi /*[nn]*/);
+int ptfem_phi_set(ptfem_mesh* m, int32_t sys, const double* phi /*[nn]*/);
+
+/* y = A x with the assembled matrix of system sys (with_bc selects the eliminated matrix) */
+int ptfem_spmv(ptfem_mesh* m, int32_t sys, int32_t with_bc, int32_t variant, const double* x, double* y);
+/* time `iters` back-to-back SpMV launches of the given variant with CUDA events; nvec > 1 times
+ * the multi-RHS / batched kernel on the current system layout */
+int ptfem_spmv_bench(ptfem_mesh* m, int32_t variant, int32_t iters, double* ms_per_launch);
+
+/* -- K10/K11: E = -grad phi, J = sigma E per element; nodal `volume current` ---------------- */
+int ptfem_element_fields(ptfem_mesh* m, int32_t sys, double* E /*[nt*3] or NULL*/, double* J /*[nt*3] or NULL*/);
+int ptfem_recover_current(ptfem_mesh* m, int32_t sys, int32_t method, double* J /*[nn*3] or NULL*/);
+
+/* -- K12: metric reductions on the device fields of system sys (reference layer L5) ---------- */
+typedef struct ptfem_footprint {
+  double cx, cy, r;  /* centre and radius / half-side */
+  int32_t square;    /* 0 disk, 1 square */
+  int32_t pad_;
+} ptfem_footprint;
+
+/* over nodes with z > zmin, inside (mode 1) / outside both (mode 2) / ignoring (mode 0) the
+ * footprints: out = {count, sum, max, min} of field: 0 |J|, 1 phi, 2 |J_z|, 3 J_z  */
+int ptfem_metric_nodes(ptfem_mesh* m, int32_t sys, int32_t field, double zmin, double zmax, int32_t mode,
+                       const ptfem_footprint* fp, int32_t nfp, double scale_r, double out[4]);
+/* run_layered_sweep.py:704-761: sum J_z*area over boundary triangles whose centroid has
+ * z > zmin and lies within scale_r * r of the footprint; out = {I_signed, area, count} */
+int ptfem_metric_pad_current(ptfem_mesh* m, int32_t sys, double zmin, const ptfem_footprint* fp, double scale_r,
+                             double out[3]);
+/* run_layered_sweep.py:765-822,948-959: ROI sphere means over cells (tets then boundary tris) with the
+ * VTK cell-data semantics; for each radius r0*mult[i]: out[i] = {n, sum|J_c|, sum|E_c|, n_z>z1, n_z in (z0,z1], n_z<=z0} */
+int ptfem_metric_roi(ptfem_mesh* m, int32_t sys, const double cen[3], double r0, const double* mult, int32_t nmult,
+                     double z0, double z1, int32_t include_tris, double* out /*[nmult*6]*/);
+/* step01 (test_step01_baseline.py:59-104): centre-column least squares of phi(z):
+ * out = {n, sum z, sum phi, sum z^2, sum z phi, sum phi^2} over nodes with hypot(x-cx,y-cy) < rad */
+int ptfem_metric_column_fit(ptfem_mesh* m, int32_t sys, double cx, double cy, double rad, double out[6]);
+/* sum and sum of squares of |J| over all nodes: out = {n, sum, sumsq} */
+int ptfem_metric_jstats(ptfem_mesh* m, int32_t sys, double out[3]);
+/* weak-form reaction current: sum over nodes on boundary bcid of (K_raw phi - b_neumann)_i (exact KCL) */
+int ptfem_metric_reaction(ptfem_mesh* m, int32_t sys, int32_t bcid, double* current);
+/* K13 (not in the reference; north_star): phi sampled at points along a nerve-fibre polyline and the
+ * activating function (second difference / h^2) at the interior points. */
+int ptfem_sample_polyline(ptfem_mesh* m, int32_t sys, int64_t npts, const double* pts /*[npts*3]*/,
+                          double* phi_out /*[npts]*/, double* af_out /*[npts]*/);
+int ptfem_current_get(ptfem_mesh* m, double* J /*[nn*3]*/);
+
+/* -- multi-GPU: row-partitioned single solve (config #5).  The caller passes an ncclUniqueId
+ *    (128 bytes) obtained on rank 0 via ptfem_dist_unique_id and broadcast by the launcher. ---- */
+int ptfem_dist_unique_id(const char* libnccl_path, void* id128);
+int ptfem_dist_init(ptfem_ctx* ctx, const char* libnccl_path, const void* id128, int32_t rank, int32_t nranks);
+int ptfem_dist_finalize(ptfem_ctx* ctx);
+/* local block of a row-partitioned system: rows [row0,row0+nloc) of the global matrix with columns
+ * renumbered [0,nloc) = owned, [nloc,nloc+nhalo) = halo; for each neighbour rank the list of owned
+ * rows to send and the halo slots to receive into. */
+int ptfem_dist_system_create(ptfem_ctx* ctx, int64_t nloc, int64_t nhalo, const int32_t* rowptr, const int32_t* col,
+                             const double* val, const double* b, int32_t nnbr, const int32_t* nbr_rank,
+                             const int32_t* send_ptr, const int32_t* send_idx, const int32_t* recv_ptr,
+                             ptfem_mesh** out);
+int ptfem_dist_solve(ptfem_mesh* sys, const ptfem_solve_opts* opts, double* x_local, ptfem_solve_stats* stats,
+                     double* ms_spmv, double* ms_halo, double* ms_allreduce);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTFEM_H */

@@ -1,0 +1,205 @@
+// common.cuh — shared host/device plumbing of libptfem (contexts, buffers, error handling).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ptfem.h"
+
+namespace ptfem {
+
+extern thread_local std::string g_err;
+
+int set_err(int code, const char* fmt, ...);
+
+#define PT_CK(expr)                                                                              \
+  do {                                                                                           \
+    cudaError_t e__ = (expr);                                                                    \
+    if (e__ != cudaSuccess)                                                                      \
+      return ptfem::set_err(PTFEM_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,        \
+                            cudaGetErrorString(e__));                                            \
+  } while (0)
+
+#define PT_TRY(expr)              \
+  do {                            \
+    int r__ = (expr);             \
+    if (r__ != PTFEM_OK) return r__; \
+  } while (0)
+
+#define PT_ARG(cond, msg)                                               \
+  do {                                                                  \
+    if (!(cond)) return ptfem::set_err(PTFEM_ERR_ARG, "%s: %s", __func__, msg); \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    if (count <= n && p) return PTFEM_OK;
+    release();
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return set_err(PTFEM_ERR_CUDA, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+    }
+    n = count;
+    return PTFEM_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace ptfem
+
+// Supported padded system counts (vectors are stored interleaved [nn][S]).
+static inline int ptfem_pad_nsys(int s) {
+  if (s <= 1) return 1;
+  if (s <= 2) return 2;
+  if (s <= 4) return 4;
+  if (s <= 8) return 8;
+  if (s <= 16) return 16;
+  return -1;
+}
+
+struct NcclApi;  // dist.cu
+
+struct ptfem_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // copies / halo
+  int64_t launches = 0;
+  double* h_pinned = nullptr;  // small pinned scratch (scalars)
+  size_t h_pinned_n = 0;
+  // NCCL (row-partitioned solves)
+  NcclApi* nccl = nullptr;
+  void* comm = nullptr;
+  int rank = 0, nranks = 1;
+};
+
+// One CG workspace per (mesh, S).
+struct PcgWork {
+  int S = 0;  // padded systems
+  ptfem::DevBuf<double> x, r, p, q, z, dinv, bb;
+  ptfem::DevBuf<double> partial;   // [3][maxblocks][S] block partials (pq | rz | rr)
+  ptfem::DevBuf<double> scal;      // device scalars: alpha[S] beta[S] rho[S] rr[S] pq[S] bnorm2[S]
+  ptfem::DevBuf<unsigned int> ticket;
+  cudaGraphExec_t graph = nullptr;
+  int graph_iters = 0;
+  int graph_variant = -1;
+  int graph_precond = -1;
+  int graph_cheb = 0;
+};
+
+struct ptfem_mesh {
+  ptfem_ctx* ctx = nullptr;
+  int64_t nn = 0, nt = 0, nb = 0, nnz = 0;
+  // mesh
+  ptfem::DevBuf<double> xyz;     // [nn][3]
+  ptfem::DevBuf<int32_t> tets;   // [nt][4]
+  ptfem::DevBuf<int32_t> region; // [nt]
+  ptfem::DevBuf<int32_t> tris;   // [nb][3]
+  ptfem::DevBuf<int32_t> bcid;   // [nb]
+  // pattern
+  bool has_pattern = false;
+  ptfem::DevBuf<int32_t> n2t_ptr, n2t;   // node -> tets (sorted)
+  ptfem::DevBuf<int32_t> n2b_ptr, n2b;   // node -> boundary tris (sorted)
+  ptfem::DevBuf<int32_t> rowptr, col, diag;
+  ptfem::DevBuf<int32_t> e2nnz;          // [nt][16]
+  ptfem::DevBuf<int32_t> gptr, gsrc;     // nnz -> (tet*16 + ij) contributions, sorted
+  // stream-SpMV row blocks
+  ptfem::DevBuf<int32_t> blk_row;        // [nblk+1] first row of each row block
+  int32_t nblk = 0;
+  int32_t max_row = 0;            // longest row of the pattern
+  // geometry factors
+  bool has_geom = false;
+  ptfem::DevBuf<double> G;        // [nt][10]  |V| gradNi.gradNj (i<=j)
+  ptfem::DevBuf<double> vol;      // [nt]      |V|
+  ptfem::DevBuf<double> tri_area; // [nb]
+  ptfem::DevBuf<double> mlump;    // [nn] lumped mass (sum V/4)
+  ptfem::DevBuf<int32_t> valence; // [nn] tets touching the node
+  // assembled systems
+  int nval = 0;                   // value sets assembled (1 or nsys), padded: nvalp
+  int nvalp = 0;
+  int nreg = 0;
+  ptfem::DevBuf<uint8_t> regidx;  // [nt] dense region index
+  ptfem::DevBuf<double> sigma_tab;// [nvalp][nreg]
+  ptfem::DevBuf<double> val_raw;  // [nnz][nvalp]
+  ptfem::DevBuf<double> val_bc;   // [nnz][nvalp]
+  // boundary conditions
+  int nrhs = 0, nrhsp = 0;        // right-hand sides (padded)
+  ptfem::DevBuf<uint8_t> isdir;   // [nn]
+  ptfem::DevBuf<double> dirval;   // [nn][nrhsp]
+  ptfem::DevBuf<double> tri_load; // [nrhsp][nb]
+  ptfem::DevBuf<double> b_neu;    // [nn][nrhsp]  Neumann load vector
+  ptfem::DevBuf<double> b;        // [nn][S]      rhs after elimination
+  bool bc_dirty = true;
+  // solution / fields
+  int S = 0;                      // systems of the last solve (padded)
+  int nsys_user = 0;
+  ptfem::DevBuf<double> phi;      // [nn][S]
+  ptfem::DevBuf<double> Jnode;    // [nn][3] last recovered nodal current
+  ptfem::DevBuf<double> Eelem, Jelem; // [nt][3]
+  ptfem::DevBuf<double> mval;     // [nnz] consistent mass values (L2 recovery)
+  ptfem::DevBuf<double> scratch_d;
+  ptfem::DevBuf<int32_t> scratch_i;
+  PcgWork work;
+  PcgWork work3;                  // mass-matrix solves (S=4)
+  // distributed system (row block)
+  bool is_dist = false;
+  int64_t nloc = 0, nhalo = 0;
+  int nnbr = 0;
+  std::vector<int32_t> nbr_rank, send_ptr, recv_ptr;
+  ptfem::DevBuf<int32_t> send_idx;
+  ptfem::DevBuf<double> send_buf;
+};
+
+// ---- helpers implemented in util.cu ---------------------------------------------------------
+namespace ptfem {
+int exclusive_scan_i32(ptfem_ctx* ctx, const int32_t* in, int32_t* out, int64_t n, int64_t* total);
+int fill_i32(ptfem_ctx* ctx, int32_t* p, int32_t v, int64_t n);
+int fill_f64(ptfem_ctx* ctx, double* p, double v, int64_t n);
+}  // namespace ptfem
+
+#define PT_LAUNCH_CHECK(ctx)                                                                     \
+  do {                                                                                           \
+    (ctx)->launches++;                                                                           \
+    cudaError_t e__ = cudaGetLastError();                                                        \
+    if (e__ != cudaSuccess)                                                                      \
+      return ptfem::set_err(PTFEM_ERR_CUDA, "%s:%d: kernel launch -> %s", __FILE__, __LINE__,    \
+                            cudaGetErrorString(e__));                                            \
+  } while (0)
+
+// ---- device helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}

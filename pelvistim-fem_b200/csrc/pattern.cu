@@ -1,0 +1,255 @@
+// pattern.cu — K1: CSR sparsity pattern of the P1 stiffness matrix and the deterministic
+// element -> nnz map (plus its inverse, used by the atomics-free gather assembly).
+//
+// Replaces ElmerSolver's matrix-structure creation for `StatCurrentSolve`
+// (step01_box/case.sif:33-45).  Canonical pattern: rows in mesh node order, columns sorted
+// ascending, diagonal always present -> bit-exact comparable with oracle/fem_oracle.csr_pattern.
+//
+// All integer work; atomics are used only for counting / slot claiming and every list is sorted
+// afterwards, so the result does not depend on thread scheduling.
+#include "common.cuh"
+
+using namespace ptfem;
+
+namespace {
+
+// ---- incidence lists: vertex -> elements (elements have NV vertices) ---------------------------
+template <int NV>
+__global__ void count_incidence(const int32_t* __restrict__ elems, int64_t ne, int32_t* __restrict__ cnt) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+#pragma unroll
+  for (int a = 0; a < NV; ++a) atomicAdd(&cnt[elems[e * NV + a]], 1);
+}
+
+template <int NV>
+__global__ void fill_incidence(const int32_t* __restrict__ elems, int64_t ne, const int32_t* __restrict__ ptr,
+                               int32_t* __restrict__ cursor, int32_t* __restrict__ list) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+#pragma unroll
+  for (int a = 0; a < NV; ++a) {
+    int32_t v = elems[e * NV + a];
+    int32_t pos = atomicAdd(&cursor[v], 1);
+    list[ptr[v] + pos] = (int32_t)e;
+  }
+}
+
+// insertion sort of each (short) list: thread per list
+__global__ void sort_lists(const int32_t* __restrict__ ptr, int32_t* __restrict__ list, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t b = ptr[i], e = ptr[i + 1];
+  for (int32_t k = b + 1; k < e; ++k) {
+    int32_t v = list[k];
+    int32_t j = k - 1;
+    while (j >= b && list[j] > v) {
+      list[j + 1] = list[j];
+      --j;
+    }
+    list[j + 1] = v;
+  }
+}
+
+// ---- rows: sorted unique neighbour list of every node ------------------------------------------
+// scratch region of node i: [4*n2t_ptr[i] + i, 4*n2t_ptr[i+1] + i + 1)  (room for 4*cnt + 1 entries)
+__global__ void row_unique(const int32_t* __restrict__ tets, const int32_t* __restrict__ n2t_ptr,
+                           const int32_t* __restrict__ n2t, int64_t nn, int32_t* __restrict__ scratch,
+                           int32_t* __restrict__ rowlen) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nn) return;
+  const int32_t tb = n2t_ptr[i], te = n2t_ptr[i + 1];
+  int32_t* row = scratch + ((int64_t)4 * tb + i);
+  int32_t u = 1;
+  row[0] = (int32_t)i;  // the diagonal is always present
+  for (int32_t t = tb; t < te; ++t) {
+    const int32_t e = n2t[t];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int32_t c = tets[(int64_t)e * 4 + a];
+      // lower bound in row[0..u)
+      int32_t lo = 0, hi = u;
+      while (lo < hi) {
+        int32_t mid = (lo + hi) >> 1;
+        if (row[mid] < c) lo = mid + 1; else hi = mid;
+      }
+      if (lo < u && row[lo] == c) continue;
+      for (int32_t k = u; k > lo; --k) row[k] = row[k - 1];
+      row[lo] = c;
+      ++u;
+    }
+  }
+  rowlen[i] = u;
+}
+
+__global__ void row_copy(const int32_t* __restrict__ n2t_ptr, const int32_t* __restrict__ scratch,
+                         const int32_t* __restrict__ rowptr, int64_t nn, int32_t* __restrict__ col,
+                         int32_t* __restrict__ diag) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nn) return;
+  const int32_t* row = scratch + ((int64_t)4 * n2t_ptr[i] + i);
+  const int32_t b = rowptr[i], e = rowptr[i + 1];
+  for (int32_t k = b; k < e; ++k) {
+    int32_t c = row[k - b];
+    col[k] = c;
+    if (c == (int32_t)i) diag[i] = k;
+  }
+}
+
+// ---- element -> nnz map ---------------------------------------------------------------------------
+__global__ void build_e2nnz(const int32_t* __restrict__ tets, int64_t nt, const int32_t* __restrict__ rowptr,
+                            const int32_t* __restrict__ col, int32_t* __restrict__ e2nnz) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (tet, local row)
+  if (t >= nt * 4) return;
+  const int64_t e = t >> 2;
+  const int a = (int)(t & 3);
+  const int32_t r = tets[e * 4 + a];
+  const int32_t b = rowptr[r], en = rowptr[r + 1];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int32_t target = tets[e * 4 + c];
+    int32_t lo = b, hi = en;
+    while (lo < hi) {
+      int32_t mid = (lo + hi) >> 1;
+      if (col[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    e2nnz[e * 16 + a * 4 + c] = lo;
+  }
+}
+
+__global__ void count_contrib(const int32_t* __restrict__ e2nnz, int64_t n, int32_t* __restrict__ cnt) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  atomicAdd(&cnt[e2nnz[i]], 1);
+}
+
+__global__ void fill_contrib(const int32_t* __restrict__ e2nnz, int64_t n, const int32_t* __restrict__ gptr,
+                             int32_t* __restrict__ cursor, int32_t* __restrict__ gsrc) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t k = e2nnz[i];
+  const int32_t pos = atomicAdd(&cursor[k], 1);
+  gsrc[gptr[k] + pos] = (int32_t)i;  // = tet*16 + local ij
+}
+
+// row blocks for the streaming SpMV: block k starts at the first row whose first non-zero is at or
+// beyond k*tile_nnz, so every block owns whole rows and at most tile_nnz + (longest row) - 1 entries.
+__global__ void build_row_blocks(const int32_t* __restrict__ rowptr, int64_t nn, int32_t tile_nnz, int32_t nblk,
+                                 int32_t* __restrict__ blk_row) {
+  int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > nblk) return;
+  if (k == nblk) { blk_row[k] = (int32_t)nn; return; }
+  const int64_t target = (int64_t)k * tile_nnz;
+  int64_t lo = 0, hi = nn;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (rowptr[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  blk_row[k] = (int32_t)lo;
+}
+
+__global__ void max_row_len(const int32_t* __restrict__ rowptr, int64_t nn, int32_t* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int32_t v = 0;
+  if (i < nn) v = rowptr[i + 1] - rowptr[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
+}
+
+template <int NV>
+int build_incidence(ptfem_ctx* ctx, const int32_t* elems, int64_t ne, int64_t nn, DevBuf<int32_t>& ptr,
+                    DevBuf<int32_t>& list) {
+  PT_TRY(ptr.alloc(nn + 1));
+  DevBuf<int32_t> cursor;
+  PT_TRY(cursor.alloc(nn + 1));
+  PT_TRY(fill_i32(ctx, ptr.p, 0, nn + 1));
+  if (ne > 0) {
+    count_incidence<NV><<<ceil_div(ne, 256), 256, 0, ctx->stream>>>(elems, ne, ptr.p);
+    PT_LAUNCH_CHECK(ctx);
+  }
+  int64_t total = 0;
+  PT_TRY(exclusive_scan_i32(ctx, ptr.p, ptr.p, nn, &total));
+  PT_TRY(list.alloc(total > 0 ? total : 1));
+  if (ne > 0) {
+    PT_TRY(fill_i32(ctx, cursor.p, 0, nn + 1));
+    fill_incidence<NV><<<ceil_div(ne, 256), 256, 0, ctx->stream>>>(elems, ne, ptr.p, cursor.p, list.p);
+    PT_LAUNCH_CHECK(ctx);
+    sort_lists<<<ceil_div(nn, 128), 128, 0, ctx->stream>>>(ptr.p, list.p, nn);
+    PT_LAUNCH_CHECK(ctx);
+  }
+  PT_CK(cudaStreamSynchronize(ctx->stream));  // cursor goes out of scope
+  return PTFEM_OK;
+}
+
+}  // namespace
+
+// max non-zeros / rows per streaming row block (must match spmv.cu)
+int ptfem_stream_tile_nnz();
+
+int ptfem_build_pattern(ptfem_mesh* m) {
+  ptfem_ctx* ctx = m->ctx;
+  const int64_t nn = m->nn, nt = m->nt, nb = m->nb;
+  PT_TRY(build_incidence<4>(ctx, m->tets.p, nt, nn, m->n2t_ptr, m->n2t));
+  PT_TRY(build_incidence<3>(ctx, m->tris.p, nb, nn, m->n2b_ptr, m->n2b));
+
+  // sorted unique neighbour lists into scratch, then compact into CSR
+  DevBuf<int32_t> scratch, rowlen;
+  PT_TRY(scratch.alloc((size_t)16 * nt + nn + 1));
+  PT_TRY(rowlen.alloc(nn + 1));
+  PT_TRY(m->rowptr.alloc(nn + 1));
+  row_unique<<<ceil_div(nn, 128), 128, 0, ctx->stream>>>(m->tets.p, m->n2t_ptr.p, m->n2t.p, nn, scratch.p, rowlen.p);
+  PT_LAUNCH_CHECK(ctx);
+  int64_t nnz = 0;
+  PT_TRY(exclusive_scan_i32(ctx, rowlen.p, m->rowptr.p, nn, &nnz));
+  m->nnz = nnz;
+  PT_TRY(m->col.alloc(nnz + 8));   // +8: streaming SpMV over-reads up to one 16-byte granule
+  PT_TRY(m->diag.alloc(nn));
+  PT_CK(cudaMemsetAsync(m->col.p, 0, (nnz + 8) * sizeof(int32_t), ctx->stream));
+  row_copy<<<ceil_div(nn, 128), 128, 0, ctx->stream>>>(m->n2t_ptr.p, scratch.p, m->rowptr.p, nn, m->col.p, m->diag.p);
+  PT_LAUNCH_CHECK(ctx);
+
+  // element -> nnz and its inverse (nnz -> sorted list of tet*16+ij)
+  PT_TRY(m->e2nnz.alloc((size_t)16 * nt));
+  if (nt > 0) {
+    build_e2nnz<<<ceil_div(nt * 4, 256), 256, 0, ctx->stream>>>(m->tets.p, nt, m->rowptr.p, m->col.p, m->e2nnz.p);
+    PT_LAUNCH_CHECK(ctx);
+  }
+  PT_TRY(m->gptr.alloc(nnz + 1));
+  PT_TRY(fill_i32(ctx, m->gptr.p, 0, nnz + 1));
+  if (nt > 0) {
+    count_contrib<<<ceil_div(nt * 16, 256), 256, 0, ctx->stream>>>(m->e2nnz.p, nt * 16, m->gptr.p);
+    PT_LAUNCH_CHECK(ctx);
+  }
+  int64_t total = 0;
+  PT_TRY(exclusive_scan_i32(ctx, m->gptr.p, m->gptr.p, nnz, &total));
+  if (total != 16 * nt) return set_err(PTFEM_ERR_STATE, "pattern: contribution count %lld != 16*nt", (long long)total);
+  PT_TRY(m->gsrc.alloc((size_t)16 * nt));
+  if (nt > 0) {
+    // reuse rowlen-sized cursor over nnz
+    DevBuf<int32_t> cursor;
+    PT_TRY(cursor.alloc(nnz + 1));
+    PT_TRY(fill_i32(ctx, cursor.p, 0, nnz + 1));
+    fill_contrib<<<ceil_div(nt * 16, 256), 256, 0, ctx->stream>>>(m->e2nnz.p, nt * 16, m->gptr.p, cursor.p, m->gsrc.p);
+    PT_LAUNCH_CHECK(ctx);
+    sort_lists<<<ceil_div(nnz, 128), 128, 0, ctx->stream>>>(m->gptr.p, m->gsrc.p, nnz);
+    PT_LAUNCH_CHECK(ctx);
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+  }
+
+  // streaming row blocks
+  const int tile_nnz = ptfem_stream_tile_nnz();
+  m->nblk = (int32_t)((nnz + tile_nnz - 1) / tile_nnz);
+  PT_TRY(m->blk_row.alloc((size_t)m->nblk + 1));
+  build_row_blocks<<<ceil_div(m->nblk + 1, 128), 128, 0, ctx->stream>>>(m->rowptr.p, nn, tile_nnz, m->nblk, m->blk_row.p);
+  PT_LAUNCH_CHECK(ctx);
+  DevBuf<int32_t> mrl;
+  PT_TRY(mrl.alloc(1));
+  PT_TRY(fill_i32(ctx, mrl.p, 0, 1));
+  max_row_len<<<ceil_div(nn, 256), 256, 0, ctx->stream>>>(m->rowptr.p, nn, mrl.p);
+  PT_LAUNCH_CHECK(ctx);
+  PT_CK(cudaMemcpyAsync(&m->max_row, mrl.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  PT_CK(cudaStreamSynchronize(ctx->stream));
+  m->has_pattern = true;
+  return PTFEM_OK;
+}

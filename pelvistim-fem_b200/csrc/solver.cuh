@@ -1,0 +1,29 @@
+// solver.cuh — internal interface of the SpMV / PCG layer (solver.cu).
+#pragma once
+#include "common.cuh"
+
+// A (batch of) linear system(s) on one CSR pattern, all device pointers.
+struct LinSys {
+  int64_t nn = 0, nnz = 0;
+  const int32_t* rowptr = nullptr;
+  const int32_t* col = nullptr;
+  const double* val = nullptr;   // [nnz][VS]
+  int VS = 1;                    // value sets: 1 (shared matrix) or S
+  int S = 1;                     // systems (padded to 1,2,4,8,16); vectors are [nn][S]
+  const double* dinv = nullptr;  // [nn][VS] inverse diagonal
+  const double* b = nullptr;     // [nn][S]
+  const int32_t* blk_row = nullptr;  // streaming row blocks (may be null -> vector kernel only)
+  int32_t nblk = 0;
+  int32_t max_row = 0;
+};
+
+namespace ptfem {
+// y = A x for all S systems; if dot_with != nullptr also leaves sum_i y_i*dot_with_i per system in
+// work.scal (slot pq) and alpha = rho/pq (CG use).  variant: PTFEM_SPMV_*.
+int spmv_launch(ptfem_ctx* ctx, const LinSys& A, int variant, const double* x, double* y, PcgWork* work, bool cg_dot);
+int pcg_solve(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_opts& o, double* x /*[nn][S] device*/,
+              ptfem_solve_stats* stats);
+int pcg_work_alloc(ptfem_ctx* ctx, PcgWork& w, int64_t nn, int S, int VS);
+void pcg_work_drop_graph(PcgWork& w);
+int resolve_variant(const LinSys& A, int variant);
+}  // namespace ptfem

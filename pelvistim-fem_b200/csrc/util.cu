@@ -1,0 +1,162 @@
+// util.cu — error string, exclusive scan, fills.
+#include <cstdarg>
+
+#include "common.cuh"
+
+namespace ptfem {
+
+thread_local std::string g_err;
+
+int set_err(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+// ---- exclusive scan (int32 in, int32 out, int64 carries) ------------------------------------
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ long long block_exclusive_scan(long long v, long long* total, long long* smem) {
+  // inclusive warp scan
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  long long inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    long long t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) smem[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    long long w = (lane < (blockDim.x >> 5)) ? smem[lane] : 0;
+    long long winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      long long t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    smem[32 + lane] = winc - w;  // exclusive offsets of warps
+    if (lane == 31) smem[64] = winc;
+  }
+  __syncthreads();
+  long long excl = inc - v + smem[32 + wid];
+  *total = smem[64];
+  __syncthreads();
+  return excl;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums(const int32_t* __restrict__ in, int64_t n,
+                                                              long long* __restrict__ sums) {
+  __shared__ long long smem[72];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  long long s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    int64_t i = base + k;
+    if (i < n) s += in[i];
+  }
+  long long tot;
+  block_exclusive_scan(s, &tot, smem);
+  if (threadIdx.x == 0) sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_sums_inplace(long long* sums, int64_t nb, long long* total) {
+  __shared__ long long smem[72];
+  long long carry = 0;
+  for (int64_t base = 0; base < nb; base += SCAN_THREADS) {
+    int64_t i = base + threadIdx.x;
+    long long v = (i < nb) ? sums[i] : 0;
+    long long tot;
+    long long ex = block_exclusive_scan(v, &tot, smem);
+    if (i < nb) sums[i] = ex + carry;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply(const int32_t* __restrict__ in, int32_t* __restrict__ out,
+                                                          int64_t n, const long long* __restrict__ sums) {
+  __shared__ long long smem[72];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int32_t v[SCAN_ITEMS];
+  long long s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    int64_t i = base + k;
+    v[k] = (i < n) ? in[i] : 0;
+    s += v[k];
+  }
+  long long tot;
+  long long ex = block_exclusive_scan(s, &tot, smem) + sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    int64_t i = base + k;
+    if (i < n) out[i] = (int32_t)ex;
+    ex += v[k];
+  }
+}
+
+// out has n+1 entries: out[n] = total.  in and out may alias.
+int exclusive_scan_i32(ptfem_ctx* ctx, const int32_t* in, int32_t* out, int64_t n, int64_t* total) {
+  if (n <= 0) {
+    if (total) *total = 0;
+    int32_t z = 0;
+    PT_CK(cudaMemcpyAsync(out, &z, sizeof z, cudaMemcpyHostToDevice, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    return PTFEM_OK;
+  }
+  const int64_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+  DevBuf<long long> sums;
+  PT_TRY(sums.alloc(nb + 1));
+  scan_tile_sums<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(in, n, sums.p);
+  PT_LAUNCH_CHECK(ctx);
+  scan_sums_inplace<<<1, SCAN_THREADS, 0, ctx->stream>>>(sums.p, nb, sums.p + nb);
+  PT_LAUNCH_CHECK(ctx);
+  scan_apply<<<(unsigned)nb, SCAN_THREADS, 0, ctx->stream>>>(in, out, n, sums.p);
+  PT_LAUNCH_CHECK(ctx);
+  long long tot = 0;
+  PT_CK(cudaMemcpyAsync(&tot, sums.p + nb, sizeof tot, cudaMemcpyDeviceToHost, ctx->stream));
+  PT_CK(cudaStreamSynchronize(ctx->stream));
+  if (tot > 2147483647LL) return set_err(PTFEM_ERR_ARG, "scan total %lld exceeds int32 indexing", tot);
+  int32_t t32 = (int32_t)tot;
+  PT_CK(cudaMemcpyAsync(out + n, &t32, sizeof t32, cudaMemcpyHostToDevice, ctx->stream));
+  PT_CK(cudaStreamSynchronize(ctx->stream));
+  if (total) *total = tot;
+  return PTFEM_OK;
+}
+
+__global__ void fill_i32_k(int32_t* p, int32_t v, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+__global__ void fill_f64_k(double* p, double v, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+int fill_i32(ptfem_ctx* ctx, int32_t* p, int32_t v, int64_t n) {
+  if (n <= 0) return PTFEM_OK;
+  int grid = (int)((n + 255) / 256);
+  if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+  fill_i32_k<<<grid, 256, 0, ctx->stream>>>(p, v, n);
+  PT_LAUNCH_CHECK(ctx);
+  return PTFEM_OK;
+}
+int fill_f64(ptfem_ctx* ctx, double* p, double v, int64_t n) {
+  if (n <= 0) return PTFEM_OK;
+  int grid = (int)((n + 255) / 256);
+  if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+  fill_f64_k<<<grid, 256, 0, ctx->stream>>>(p, v, n);
+  PT_LAUNCH_CHECK(ctx);
+  return PTFEM_OK;
+}
+
+}  // namespace ptfem
