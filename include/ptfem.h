@@ -49,7 +49,8 @@ typedef struct ptfem_mesh ptfem_mesh;
 /* SpMV kernel variants for ptfem_spmv / ptfem_spmv_bench */
 #define PTFEM_SPMV_AUTO 0
 #define PTFEM_SPMV_VECTOR 1  /* sub-warp per row, direct global loads */
-#define PTFEM_SPMV_STREAM 2  /* persistent CTAs, val/col staged into shared memory by bulk async copies */
+#define PTFEM_SPMV_STREAM 2  /* persistent CTAs, val/col staged into shared memory by bulk async copies, 2 stages */
+#define PTFEM_SPMV_STREAM1 3 /* same, single stage (overlap across CTAs only) */
 
 typedef struct ptfem_solve_opts {
   int32_t precond;      /* PTFEM_PRECOND_* */
@@ -83,6 +84,8 @@ int ptfem_ctx_destroy(ptfem_ctx* ctx);
 int ptfem_ctx_sync(ptfem_ctx* ctx);
 /* kernels launched by this context since creation (for bench.py's gpu_launches) */
 int ptfem_ctx_launch_count(ptfem_ctx* ctx, int64_t* n);
+/* the cudaStream_t every kernel of this context is launched on (for external CUDA-event timing) */
+int ptfem_ctx_stream(ptfem_ctx* ctx, void** stream);
 
 /* -- mesh: replaces ElmerSolver's reading of elmer_mesh/{mesh.nodes,mesh.elements,mesh.boundary}
  *    (formats: step01_box/find_boundaries.py:16-40,87-90).  Copies host arrays to the device. */

@@ -1,0 +1,508 @@
+// api.cu — the extern "C" surface of libptfem.so (include/ptfem.h): argument checking, host<->device
+// copies, and sequencing of the kernels in pattern.cu / assembly.cu / solver.cu / post.cu.
+#include <algorithm>
+
+#include "solver.cuh"
+
+using namespace ptfem;
+
+// internal entry points (other translation units)
+int ptfem_build_pattern(ptfem_mesh* m);
+int ptfem_build_geometry(ptfem_mesh* m);
+int ptfem_do_assemble(ptfem_mesh* m, int32_t nreg, const int32_t* reg_ids, const double* sigma, int32_t nsys);
+int ptfem_do_bc_reset(ptfem_mesh* m, int32_t nrhs);
+int ptfem_do_bc_dirichlet(ptfem_mesh* m, int32_t rhs, int32_t bcid, double value);
+int ptfem_do_bc_neumann(ptfem_mesh* m, int32_t rhs, int32_t bcid, double g);
+int ptfem_do_bc_neumann_tris(ptfem_mesh* m, int32_t rhs, int64_t n, const int32_t* tri_idx, double g);
+int ptfem_apply_bc(ptfem_mesh* m, double* dinv_out, int* S_out);
+int ptfem_do_element_fields(ptfem_mesh* m, int sys);
+int ptfem_do_recover(ptfem_mesh* m, int sys, int method);
+int ptfem_do_metric_nodes(ptfem_mesh* m, int sys, int field, double zmin, double zmax, int mode, const ptfem_footprint* fp,
+                          int nfp, double scale_r, double out[4]);
+int ptfem_do_metric_pad_current(ptfem_mesh* m, int sys, double zmin, const ptfem_footprint* fp, double scale_r, double out[3]);
+int ptfem_do_metric_roi(ptfem_mesh* m, int sys, const double cen[3], double r0, const double* mult, int nmult, double z0,
+                        double z1, int include_tris, double* out);
+int ptfem_do_metric_column_fit(ptfem_mesh* m, int sys, double cx, double cy, double rad, double out[6]);
+int ptfem_do_metric_jstats(ptfem_mesh* m, int sys, double out[3]);
+int ptfem_do_metric_reaction(ptfem_mesh* m, int sys, int32_t bcid, double* current);
+int ptfem_do_sample_polyline(ptfem_mesh* m, int sys, int64_t npts, const double* pts, double* phi_out, double* af_out);
+void ptfem_dist_ctx_release(ptfem_ctx* ctx);
+
+namespace {
+
+// strided gather/scatter between a [nn][S] interleaved device array and a dense [nn] host-bound staging vector
+__global__ void gather_sys_kernel(const double* __restrict__ in, int64_t nn, int S, int sys, double* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nn) out[i] = in[i * S + sys];
+}
+__global__ void scatter_sys_kernel(const double* __restrict__ in, int64_t nn, int S, int sys, double* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nn) out[i * S + sys] = in[i];
+}
+// [nn][S] -> [nsys][nn] (system-major, what the host API hands back)
+__global__ void transpose_out_kernel(const double* __restrict__ in, int64_t nn, int S, int nsys, double* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nn) return;
+  for (int s = 0; s < nsys; ++s) out[(int64_t)s * nn + i] = in[i * S + s];
+}
+
+int make_linsys(ptfem_mesh* m, LinSys& A) {
+  A.nn = m->nn;
+  A.nnz = m->nnz;
+  A.rowptr = m->rowptr.p;
+  A.col = m->col.p;
+  A.val = m->val_bc.p;
+  A.VS = m->nvalp;
+  A.S = m->S;
+  A.dinv = m->dinv.p;
+  A.b = m->b.p;
+  A.blk_row = m->blk_row.p;
+  A.nblk = m->nblk;
+  A.max_row = m->max_row;
+  return PTFEM_OK;
+}
+
+int prepare_systems(ptfem_mesh* m) {
+  if (!m->has_pattern) return set_err(PTFEM_ERR_STATE, "ptfem_pattern has not been called");
+  if (m->bc_dirty || !m->b.p) {
+    PT_TRY(m->dinv.alloc((size_t)m->nn * (m->nvalp > 0 ? m->nvalp : 1)));
+    int S = 0;
+    PT_TRY(ptfem_apply_bc(m, m->dinv.p, &S));
+    if (S != m->S || !m->phi.p) {
+      m->S = S;
+      PT_TRY(m->phi.alloc((size_t)m->nn * S));
+      PT_CK(cudaMemsetAsync(m->phi.p, 0, (size_t)m->nn * S * sizeof(double), m->ctx->stream));
+    }
+    m->nsys_user = std::max(m->nval, m->nrhs);
+  }
+  return PTFEM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ptfem_last_error(void) { return g_err.c_str(); }
+int ptfem_version(void) { return 100; }
+
+int ptfem_device_count(int* n) {
+  PT_ARG(n, "null pointer");
+  cudaError_t e = cudaGetDeviceCount(n);
+  if (e != cudaSuccess) {
+    *n = 0;
+    return set_err(PTFEM_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  }
+  return PTFEM_OK;
+}
+
+int ptfem_ctx_create(int device, ptfem_ctx** out) {
+  PT_ARG(out, "null pointer");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return set_err(PTFEM_ERR_CUDA, "no CUDA device available (%s); libptfem has no CPU fallback",
+                   e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0 || device >= n) return set_err(PTFEM_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+  PT_CK(cudaSetDevice(device));
+  ptfem_ctx* c = new ptfem_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  PT_CK(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  PT_CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  PT_CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  c->h_pinned_n = 4096;
+  PT_CK(cudaMallocHost((void**)&c->h_pinned, c->h_pinned_n * sizeof(double)));
+  *out = c;
+  return PTFEM_OK;
+}
+
+int ptfem_ctx_destroy(ptfem_ctx* ctx) {
+  if (!ctx) return PTFEM_OK;
+  cudaSetDevice(ctx->device);
+  ptfem_dist_ctx_release(ctx);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  delete ctx;
+  return PTFEM_OK;
+}
+
+int ptfem_ctx_sync(ptfem_ctx* ctx) {
+  PT_ARG(ctx, "null context");
+  PT_CK(cudaSetDevice(ctx->device));
+  PT_CK(cudaStreamSynchronize(ctx->stream));
+  return PTFEM_OK;
+}
+
+int ptfem_ctx_launch_count(ptfem_ctx* ctx, int64_t* n) {
+  PT_ARG(ctx && n, "null pointer");
+  *n = ctx->launches;
+  return PTFEM_OK;
+}
+
+int ptfem_ctx_stream(ptfem_ctx* ctx, void** stream) {
+  PT_ARG(ctx && stream, "null pointer");
+  *stream = (void*)ctx->stream;
+  return PTFEM_OK;
+}
+
+int ptfem_mesh_create(ptfem_ctx* ctx, int64_t nn, const double* xyz, int64_t nt, const int32_t* tets, const int32_t* region,
+                      int64_t nb, const int32_t* tris, const int32_t* bcid, ptfem_mesh** out) {
+  PT_ARG(ctx && out, "null pointer");
+  *out = nullptr;
+  PT_ARG(nn > 0 && nt >= 0 && nb >= 0, "negative or zero sizes");
+  PT_ARG(xyz && (nt == 0 || (tets && region)) && (nb == 0 || (tris && bcid)), "null array");
+  PT_ARG(nn < 2147483647LL && nt * 16 < 2147483647LL * 4, "mesh too large for 32-bit indexing");
+  for (int64_t i = 0; i < nt * 4; ++i)
+    if (tets[i] < 0 || tets[i] >= nn) return set_err(PTFEM_ERR_ARG, "tet %lld refers to node %d (nn = %lld)", (long long)(i / 4), tets[i], (long long)nn);
+  for (int64_t i = 0; i < nb * 3; ++i)
+    if (tris[i] < 0 || tris[i] >= nn) return set_err(PTFEM_ERR_ARG, "boundary triangle %lld refers to node %d", (long long)(i / 3), tris[i]);
+  PT_CK(cudaSetDevice(ctx->device));
+  ptfem_mesh* m = new ptfem_mesh();
+  m->ctx = ctx;
+  m->nn = nn;
+  m->nt = nt;
+  m->nb = nb;
+  int rc = PTFEM_OK;
+  auto up = [&](auto& buf, const auto* src, size_t count) {
+    if (rc) return;
+    rc = buf.alloc(count);
+    if (rc || count == 0) return;
+    cudaError_t e = cudaMemcpyAsync(buf.p, src, count * sizeof(*src), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) rc = set_err(PTFEM_ERR_CUDA, "mesh upload: %s", cudaGetErrorString(e));
+  };
+  up(m->xyz, xyz, (size_t)nn * 3);
+  up(m->tets, tets, (size_t)nt * 4);
+  up(m->region, region, (size_t)nt);
+  up(m->tris, tris, (size_t)nb * 3);
+  up(m->bcid, bcid, (size_t)nb);
+  if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = set_err(PTFEM_ERR_CUDA, "mesh upload failed");
+  if (rc) {
+    delete m;
+    return rc;
+  }
+  *out = m;
+  return PTFEM_OK;
+}
+
+int ptfem_mesh_destroy(ptfem_mesh* m) {
+  if (!m) return PTFEM_OK;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  pcg_work_drop_graph(m->work);
+  pcg_work_drop_graph(m->work3);
+  delete m;
+  return PTFEM_OK;
+}
+
+int ptfem_mesh_set_coords(ptfem_mesh* m, const double* xyz) {
+  PT_ARG(m && xyz, "null pointer");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  PT_CK(cudaMemcpyAsync(m->xyz.p, xyz, (size_t)m->nn * 3 * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
+  PT_CK(cudaStreamSynchronize(m->ctx->stream));
+  m->has_geom = false;
+  if (m->has_pattern) PT_TRY(ptfem_build_geometry(m));
+  m->nval = 0;  // values must be re-assembled
+  m->bc_dirty = true;
+  return PTFEM_OK;
+}
+
+int ptfem_pattern(ptfem_mesh* m, int64_t* nnz) {
+  PT_ARG(m, "null mesh");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  if (!m->has_pattern) PT_TRY(ptfem_build_pattern(m));
+  if (!m->has_geom) PT_TRY(ptfem_build_geometry(m));
+  if (nnz) *nnz = m->nnz;
+  return PTFEM_OK;
+}
+
+int ptfem_pattern_get(ptfem_mesh* m, int32_t* rowptr, int32_t* col) {
+  PT_ARG(m, "null mesh");
+  if (!m->has_pattern) return set_err(PTFEM_ERR_STATE, "ptfem_pattern has not been called");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  if (rowptr) PT_CK(cudaMemcpyAsync(rowptr, m->rowptr.p, (size_t)(m->nn + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, m->ctx->stream));
+  if (col) PT_CK(cudaMemcpyAsync(col, m->col.p, (size_t)m->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, m->ctx->stream));
+  PT_CK(cudaStreamSynchronize(m->ctx->stream));
+  return PTFEM_OK;
+}
+
+int ptfem_e2nnz_get(ptfem_mesh* m, int32_t* e2nnz) {
+  PT_ARG(m && e2nnz, "null pointer");
+  if (!m->has_pattern) return set_err(PTFEM_ERR_STATE, "ptfem_pattern has not been called");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  PT_CK(cudaMemcpyAsync(e2nnz, m->e2nnz.p, (size_t)m->nt * 16 * sizeof(int32_t), cudaMemcpyDeviceToHost, m->ctx->stream));
+  PT_CK(cudaStreamSynchronize(m->ctx->stream));
+  return PTFEM_OK;
+}
+
+int ptfem_assemble(ptfem_mesh* m, int32_t nreg, const int32_t* reg_ids, const double* sigma, int32_t nsys) {
+  PT_ARG(m && reg_ids && sigma, "null pointer");
+  PT_ARG(nsys >= 1, "nsys must be >= 1");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  PT_TRY(ptfem_pattern(m, nullptr));
+  return ptfem_do_assemble(m, nreg, reg_ids, sigma, nsys);
+}
+
+int ptfem_values_get(ptfem_mesh* m, int32_t sys, int32_t with_bc, double* val) {
+  PT_ARG(m && val, "null pointer");
+  if (m->nval < 1) return set_err(PTFEM_ERR_STATE, "ptfem_assemble has not been called");
+  PT_ARG(sys >= 0 && sys < m->nval, "system index out of range");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  if (with_bc) PT_TRY(prepare_systems(m));
+  const double* src = with_bc ? m->val_bc.p : m->val_raw.p;
+  DevBuf<double> tmp;
+  PT_TRY(tmp.alloc(m->nnz));
+  gather_sys_kernel<<<ceil_div(m->nnz, 256), 256, 0, m->ctx->stream>>>(src, m->nnz, m->nvalp, sys, tmp.p);
+  PT_LAUNCH_CHECK(m->ctx);
+  PT_CK(cudaMemcpyAsync(val, tmp.p, (size_t)m->nnz * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
+  PT_CK(cudaStreamSynchronize(m->ctx->stream));
+  return PTFEM_OK;
+}
+
+int ptfem_bc_reset(ptfem_mesh* m, int32_t nrhs) {
+  PT_ARG(m, "null mesh");
+  PT_ARG(nrhs >= 1, "nrhs must be >= 1");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  PT_TRY(ptfem_pattern(m, nullptr));
+  return ptfem_do_bc_reset(m, nrhs);
+}
+
+#define PT_RHS_CHECK()                                                              \
+  PT_ARG(m, "null mesh");                                                           \
+  if (m->nrhs < 1) return set_err(PTFEM_ERR_STATE, "ptfem_bc_reset has not been called"); \
+  PT_ARG(rhs >= -1 && rhs < m->nrhs, "right-hand-side index out of range");         \
+  PT_CK(cudaSetDevice(m->ctx->device))
+
+int ptfem_bc_dirichlet(ptfem_mesh* m, int32_t rhs, int32_t bcid, double value) {
+  PT_RHS_CHECK();
+  return ptfem_do_bc_dirichlet(m, rhs, bcid, value);
+}
+int ptfem_bc_neumann(ptfem_mesh* m, int32_t rhs, int32_t bcid, double g) {
+  PT_RHS_CHECK();
+  return ptfem_do_bc_neumann(m, rhs, bcid, g);
+}
+int ptfem_bc_neumann_tris(ptfem_mesh* m, int32_t rhs, int64_t n, const int32_t* tri_idx, double g) {
+  PT_RHS_CHECK();
+  PT_ARG(n == 0 || tri_idx, "null pointer");
+  return ptfem_do_bc_neumann_tris(m, rhs, n, tri_idx, g);
+}
+
+int ptfem_rhs_get(ptfem_mesh* m, int32_t rhs, double* b) {
+  PT_ARG(m && b, "null pointer");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  PT_TRY(prepare_systems(m));
+  PT_ARG(rhs >= 0 && rhs < m->nsys_user, "right-hand-side index out of range");
+  DevBuf<double> tmp;
+  PT_TRY(tmp.alloc(m->nn));
+  gather_sys_kernel<<<ceil_div(m->nn, 256), 256, 0, m->ctx->stream>>>(m->b.p, m->nn, m->S, rhs, tmp.p);
+  PT_LAUNCH_CHECK(m->ctx);
+  PT_CK(cudaMemcpyAsync(b, tmp.p, (size_t)m->nn * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
+  PT_CK(cudaStreamSynchronize(m->ctx->stream));
+  return PTFEM_OK;
+}
+
+void ptfem_solve_opts_default(ptfem_solve_opts* o) {
+  if (!o) return;
+  o->precond = PTFEM_PRECOND_JACOBI;
+  o->maxit = 200000;
+  o->check_every = 50;
+  o->cheb_degree = 4;
+  o->rtol = 1e-12;
+  o->cheb_ratio = 30.0;
+  o->spmv_variant = PTFEM_SPMV_AUTO;
+  o->use_graph = 1;
+}
+
+int ptfem_solve_device(ptfem_mesh* m, const ptfem_solve_opts* opts, ptfem_solve_stats* stats) {
+  PT_ARG(m, "null mesh");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  ptfem_solve_opts o;
+  if (opts) o = *opts; else ptfem_solve_opts_default(&o);
+  PT_ARG(o.rtol > 0.0 && o.maxit > 0, "rtol and maxit must be positive");
+  PT_ARG(o.precond == PTFEM_PRECOND_JACOBI || o.precond == PTFEM_PRECOND_CHEBYSHEV, "unknown preconditioner");
+  PT_TRY(prepare_systems(m));
+  LinSys A;
+  make_linsys(m, A);
+  m->J_sys = -1;
+  int rc = pcg_solve(m->ctx, A, m->work, o, m->phi.p, stats);
+  if (stats) stats->nsys = m->nsys_user;
+  return rc;
+}
+
+int ptfem_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* phi, ptfem_solve_stats* stats) {
+  PT_ARG(m && phi, "null pointer");
+  int rc = ptfem_solve_device(m, opts, stats);
+  if (rc != PTFEM_OK && rc != PTFEM_ERR_NOCONV) return rc;
+  // hand the (possibly unconverged) iterate back, system-major
+  ptfem_ctx* ctx = m->ctx;
+  const std::string keep = g_err;
+  if (m->S == 1) {
+    PT_CK(cudaMemcpyAsync(phi, m->phi.p, (size_t)m->nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    PT_TRY(m->scratch_d.alloc((size_t)m->nn * m->nsys_user));
+    transpose_out_kernel<<<ceil_div(m->nn, 256), 256, 0, ctx->stream>>>(m->phi.p, m->nn, m->S, m->nsys_user, m->scratch_d.p);
+    PT_LAUNCH_CHECK(ctx);
+    PT_CK(cudaMemcpyAsync(phi, m->scratch_d.p, (size_t)m->nn * m->nsys_user * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  PT_CK(cudaStreamSynchronize(ctx->stream));
+  g_err = keep;
+  return rc;
+}
+
+int ptfem_phi_get(ptfem_mesh* m, int32_t sys, double* phi) {
+  PT_ARG(m && phi, "null pointer");
+  if (!m->phi.p) return set_err(PTFEM_ERR_STATE, "no solution on the device");
+  PT_ARG(sys >= 0 && sys < m->nsys_user, "system index out of range");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  DevBuf<double> tmp;
+  PT_TRY(tmp.alloc(m->nn));
+  gather_sys_kernel<<<ceil_div(m->nn, 256), 256, 0, m->ctx->stream>>>(m->phi.p, m->nn, m->S, sys, tmp.p);
+  PT_LAUNCH_CHECK(m->ctx);
+  PT_CK(cudaMemcpyAsync(phi, tmp.p, (size_t)m->nn * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
+  PT_CK(cudaStreamSynchronize(m->ctx->stream));
+  return PTFEM_OK;
+}
+
+int ptfem_phi_set(ptfem_mesh* m, int32_t sys, const double* phi) {
+  PT_ARG(m && phi, "null pointer");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  PT_TRY(prepare_systems(m));
+  PT_ARG(sys >= 0 && sys < m->nsys_user, "system index out of range");
+  DevBuf<double> tmp;
+  PT_TRY(tmp.alloc(m->nn));
+  PT_CK(cudaMemcpyAsync(tmp.p, phi, (size_t)m->nn * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
+  scatter_sys_kernel<<<ceil_div(m->nn, 256), 256, 0, m->ctx->stream>>>(tmp.p, m->nn, m->S, sys, m->phi.p);
+  PT_LAUNCH_CHECK(m->ctx);
+  PT_CK(cudaStreamSynchronize(m->ctx->stream));
+  m->J_sys = -1;
+  return PTFEM_OK;
+}
+
+int ptfem_spmv(ptfem_mesh* m, int32_t sys, int32_t with_bc, int32_t variant, const double* x, double* y) {
+  PT_ARG(m && x && y, "null pointer");
+  if (m->nval < 1) return set_err(PTFEM_ERR_STATE, "ptfem_assemble has not been called");
+  PT_ARG(sys >= 0 && sys < m->nval, "system index out of range");
+  ptfem_ctx* ctx = m->ctx;
+  PT_CK(cudaSetDevice(ctx->device));
+  if (with_bc) PT_TRY(prepare_systems(m));
+  // single-system view of the chosen value set
+  DevBuf<double> v1, dx, dy;
+  const double* vals = with_bc ? m->val_bc.p : m->val_raw.p;
+  if (m->nvalp != 1) {
+    PT_TRY(v1.alloc(m->nnz + 8));
+    PT_CK(cudaMemsetAsync(v1.p + m->nnz, 0, 8 * sizeof(double), ctx->stream));
+    gather_sys_kernel<<<ceil_div(m->nnz, 256), 256, 0, ctx->stream>>>(vals, m->nnz, m->nvalp, sys, v1.p);
+    PT_LAUNCH_CHECK(ctx);
+    vals = v1.p;
+  }
+  PT_TRY(dx.alloc(m->nn));
+  PT_TRY(dy.alloc(m->nn));
+  PT_CK(cudaMemcpyAsync(dx.p, x, (size_t)m->nn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  LinSys A;
+  A.nn = m->nn; A.nnz = m->nnz; A.rowptr = m->rowptr.p; A.col = m->col.p; A.val = vals; A.VS = 1; A.S = 1;
+  A.blk_row = m->blk_row.p; A.nblk = m->nblk; A.max_row = m->max_row;
+  PT_TRY(spmv_launch(ctx, A, variant, dx.p, dy.p, nullptr, false));
+  PT_CK(cudaMemcpyAsync(y, dy.p, (size_t)m->nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  PT_CK(cudaStreamSynchronize(ctx->stream));
+  return PTFEM_OK;
+}
+
+int ptfem_spmv_bench(ptfem_mesh* m, int32_t variant, int32_t iters, double* ms_per_launch) {
+  PT_ARG(m && ms_per_launch && iters > 0, "bad arguments");
+  ptfem_ctx* ctx = m->ctx;
+  PT_CK(cudaSetDevice(ctx->device));
+  PT_TRY(prepare_systems(m));
+  LinSys A;
+  make_linsys(m, A);
+  PT_TRY(pcg_work_alloc(ctx, m->work, A.nn, A.S, A.VS));
+  // x = b (any non-trivial vector), y = work.q
+  PT_CK(cudaMemcpyAsync(m->work.p.p, m->b.p, (size_t)m->nn * m->S * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  for (int k = 0; k < 3; ++k) PT_TRY(spmv_launch(ctx, A, variant, m->work.p.p, m->work.q.p, &m->work, false));
+  cudaEvent_t e0, e1;
+  PT_CK(cudaEventCreate(&e0));
+  PT_CK(cudaEventCreate(&e1));
+  PT_CK(cudaEventRecord(e0, ctx->stream));
+  for (int k = 0; k < iters; ++k) PT_TRY(spmv_launch(ctx, A, variant, m->work.p.p, m->work.q.p, &m->work, false));
+  PT_CK(cudaEventRecord(e1, ctx->stream));
+  PT_CK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  PT_CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_launch = (double)ms / iters;
+  return PTFEM_OK;
+}
+
+int ptfem_element_fields(ptfem_mesh* m, int32_t sys, double* E, double* J) {
+  PT_ARG(m, "null mesh");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  PT_TRY(ptfem_do_element_fields(m, sys));
+  if (E) PT_CK(cudaMemcpyAsync(E, m->Eelem.p, (size_t)m->nt * 3 * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
+  if (J) PT_CK(cudaMemcpyAsync(J, m->Jelem.p, (size_t)m->nt * 3 * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
+  PT_CK(cudaStreamSynchronize(m->ctx->stream));
+  return PTFEM_OK;
+}
+
+int ptfem_recover_current(ptfem_mesh* m, int32_t sys, int32_t method, double* J) {
+  PT_ARG(m, "null mesh");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  PT_TRY(ptfem_do_recover(m, sys, method));
+  if (J) {
+    PT_CK(cudaMemcpyAsync(J, m->Jnode.p, (size_t)m->nn * 3 * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
+    PT_CK(cudaStreamSynchronize(m->ctx->stream));
+  }
+  return PTFEM_OK;
+}
+
+int ptfem_current_get(ptfem_mesh* m, double* J) {
+  PT_ARG(m && J, "null pointer");
+  if (!m->Jnode.p || m->J_sys < 0) return set_err(PTFEM_ERR_STATE, "no recovered current on the device");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  PT_CK(cudaMemcpyAsync(J, m->Jnode.p, (size_t)m->nn * 3 * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
+  PT_CK(cudaStreamSynchronize(m->ctx->stream));
+  return PTFEM_OK;
+}
+
+int ptfem_metric_nodes(ptfem_mesh* m, int32_t sys, int32_t field, double zmin, double zmax, int32_t mode,
+                       const ptfem_footprint* fp, int32_t nfp, double scale_r, double out[4]) {
+  PT_ARG(m && out, "null pointer");
+  PT_ARG(field >= 0 && field <= 3 && mode >= 0 && mode <= 2, "bad field / mode");
+  PT_ARG(mode == 0 || (fp && nfp > 0), "footprints required for mode 1/2");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  return ptfem_do_metric_nodes(m, sys, field, zmin, zmax, mode, fp, mode == 0 ? 0 : nfp, scale_r, out);
+}
+int ptfem_metric_pad_current(ptfem_mesh* m, int32_t sys, double zmin, const ptfem_footprint* fp, double scale_r, double out[3]) {
+  PT_ARG(m && fp && out, "null pointer");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  return ptfem_do_metric_pad_current(m, sys, zmin, fp, scale_r, out);
+}
+int ptfem_metric_roi(ptfem_mesh* m, int32_t sys, const double cen[3], double r0, const double* mult, int32_t nmult, double z0,
+                     double z1, int32_t include_tris, double* out) {
+  PT_ARG(m && cen && mult && out, "null pointer");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  return ptfem_do_metric_roi(m, sys, cen, r0, mult, nmult, z0, z1, include_tris, out);
+}
+int ptfem_metric_column_fit(ptfem_mesh* m, int32_t sys, double cx, double cy, double rad, double out[6]) {
+  PT_ARG(m && out, "null pointer");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  return ptfem_do_metric_column_fit(m, sys, cx, cy, rad, out);
+}
+int ptfem_metric_jstats(ptfem_mesh* m, int32_t sys, double out[3]) {
+  PT_ARG(m && out, "null pointer");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  return ptfem_do_metric_jstats(m, sys, out);
+}
+int ptfem_metric_reaction(ptfem_mesh* m, int32_t sys, int32_t bcid, double* current) {
+  PT_ARG(m && current, "null pointer");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  return ptfem_do_metric_reaction(m, sys, bcid, current);
+}
+int ptfem_sample_polyline(ptfem_mesh* m, int32_t sys, int64_t npts, const double* pts, double* phi_out, double* af_out) {
+  PT_ARG(m && (npts == 0 || pts), "null pointer");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  return ptfem_do_sample_polyline(m, sys, npts, pts, phi_out, af_out);
+}
+
+}  // extern "C"

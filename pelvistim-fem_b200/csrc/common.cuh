@@ -88,6 +88,7 @@ struct ptfem_ctx {
   int64_t launches = 0;
   double* h_pinned = nullptr;  // small pinned scratch (scalars)
   size_t h_pinned_n = 0;
+  uint32_t func_attr_done = 0;     // kernels whose dynamic shared memory limit has been raised
   // NCCL (row-partitioned solves)
   NcclApi* nccl = nullptr;
   void* comm = nullptr;
@@ -97,15 +98,22 @@ struct ptfem_ctx {
 // One CG workspace per (mesh, S).
 struct PcgWork {
   int S = 0;  // padded systems
-  ptfem::DevBuf<double> x, r, p, q, z, dinv, bb;
-  ptfem::DevBuf<double> partial;   // [3][maxblocks][S] block partials (pq | rz | rr)
-  ptfem::DevBuf<double> scal;      // device scalars: alpha[S] beta[S] rho[S] rr[S] pq[S] bnorm2[S]
-  ptfem::DevBuf<unsigned int> ticket;
-  cudaGraphExec_t graph = nullptr;
+  ptfem::DevBuf<double> r, p, q;       // CG vectors [nn][S]
+  ptfem::DevBuf<double> z, rt, d;      // Chebyshev preconditioner vectors
+  ptfem::DevBuf<double> coef;          // Chebyshev coefficients [(deg+1)][S][2]
+  ptfem::DevBuf<double> partial;       // per-CTA partial sums
+  ptfem::DevBuf<double> scal;          // device scalars, see solver.cu (SC_*), each [16]
+  ptfem::DevBuf<unsigned int> ticket;  // last-CTA-done counter
+  cudaGraphExec_t graph = nullptr;     // check_every captured iterations
   int graph_iters = 0;
   int graph_variant = -1;
   int graph_precond = -1;
   int graph_cheb = 0;
+  int64_t graph_launches = 0;
+  const void* graph_x = nullptr;
+  const void* graph_val = nullptr;
+  const void* graph_b = nullptr;
+  const void* graph_dinv = nullptr;
 };
 
 struct ptfem_mesh {
@@ -150,6 +158,7 @@ struct ptfem_mesh {
   ptfem::DevBuf<double> tri_load; // [nrhsp][nb]
   ptfem::DevBuf<double> b_neu;    // [nn][nrhsp]  Neumann load vector
   ptfem::DevBuf<double> b;        // [nn][S]      rhs after elimination
+  ptfem::DevBuf<double> dinv;     // [nn][nvalp]  inverse diagonal of the eliminated matrix
   bool bc_dirty = true;
   // solution / fields
   int S = 0;                      // systems of the last solve (padded)
@@ -158,6 +167,10 @@ struct ptfem_mesh {
   ptfem::DevBuf<double> Jnode;    // [nn][3] last recovered nodal current
   ptfem::DevBuf<double> Eelem, Jelem; // [nt][3]
   ptfem::DevBuf<double> mval;     // [nnz] consistent mass values (L2 recovery)
+  ptfem::DevBuf<double> mdinv, mrhs, mx; // mass-matrix Jacobi, rhs [nn][4], solution [nn][4]
+  ptfem::DevBuf<double> phis;     // [nn] VTK-smoothed potential (ROI metric)
+  int J_sys = -1;                 // system whose nodal current is in Jnode
+  int mass_iters = 0;
   ptfem::DevBuf<double> scratch_d;
   ptfem::DevBuf<int32_t> scratch_i;
   PcgWork work;

@@ -1,0 +1,960 @@
+// solver.cu — K5 CSR SpMV (sub-warp-per-row "vector" kernel and bulk-copy staged "stream" kernel),
+// K6 fused CG vector updates, K7 Chebyshev polynomial preconditioner, K8/K9 multi-RHS and
+// batched-values variants (all kernels are templated on the number of interleaved systems).
+//
+// Replaces the linear solve of the reference's ElmerSolver run (`Linear System Solver = Direct`,
+// `Linear System Direct Method = UMFPACK`, step01_box/case.sif:41-42;
+// step03_ankle_layers/run_layered_sweep.py:492,629).  The matrix is SPD after symmetric Dirichlet
+// elimination, so preconditioned CG converges to the same solution; tolerance is on the true residual.
+//
+// Layout: vectors are [nn][S] (system index fastest), values are [nnz][VS] with VS == 1 (one matrix,
+// S right-hand sides) or VS == S (S matrices on one pattern).  All reductions are done as
+// per-CTA partials summed in a fixed order by the last CTA to finish (ticket counter), so results
+// are bit-reproducible run to run and no scalar ever visits the host inside the iteration.
+#include <cmath>
+
+#include "solver.cuh"
+
+using namespace ptfem;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kCtasPerSm = 8;
+constexpr int kMaxSys = 16;
+
+// ---- streaming SpMV geometry --------------------------------------------------------------------
+constexpr int kStreamTile = 2048;    // target non-zeros per row block
+constexpr int kStreamMaxRow = 240;   // longer rows -> vector kernel
+constexpr int kStreamCap = kStreamTile + kStreamMaxRow + 16;  // staged entries (incl. alignment slack)
+
+// scalar slots in PcgWork::scal, each [kMaxSys]
+enum { SC_ALPHA = 0, SC_BETA, SC_RHO, SC_RR, SC_PQ, SC_BN2, SC_LMAX, SC_COUNT };
+
+template <int S>
+__device__ __forceinline__ void load_sys(const double* __restrict__ p, double (&v)[S]) {
+  if constexpr (S == 1) {
+    v[0] = __ldg(p);
+  } else {
+    const double2* q = reinterpret_cast<const double2*>(p);
+#pragma unroll
+    for (int s = 0; s < S / 2; ++s) {
+      const double2 t = __ldg(q + s);
+      v[2 * s] = t.x;
+      v[2 * s + 1] = t.y;
+    }
+  }
+}
+template <int S>
+__device__ __forceinline__ void store_sys(double* __restrict__ p, const double (&v)[S]) {
+  if constexpr (S == 1) {
+    p[0] = v[0];
+  } else {
+    double2* q = reinterpret_cast<double2*>(p);
+#pragma unroll
+    for (int s = 0; s < S / 2; ++s) q[s] = make_double2(v[2 * s], v[2 * s + 1]);
+  }
+}
+
+// Sum over the CTA of NV values per thread, result valid in thread 0 .. written to out[NV].
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* s_red /*[32*NV]*/, double* out /*[NV] smem or gmem*/) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) s_red[wid * NV + k] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double acc = 0.0;
+    for (int w = 0; w < nw; ++w) acc += s_red[w * NV + threadIdx.x];
+    out[threadIdx.x] = acc;
+  }
+  __syncthreads();
+}
+
+// true in every thread of the last CTA of the grid to get here (and resets the ticket)
+__device__ __forceinline__ bool is_last_block(unsigned int* ticket) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicInc(ticket, gridDim.x - 1);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
+// last CTA: total[k] = sum_b partial[b*NV + k], fixed order; valid for threadIdx.x < NV after return
+template <int NV>
+__device__ __forceinline__ double sum_partials(const double* __restrict__ partial, int nblocks, double* s_red) {
+  // thread t owns component (t % NV) of blocks t/NV, t/NV + T/NV, ...
+  static_assert(kThreads % NV == 0, "NV must divide the CTA size");
+  constexpr int G = kThreads / NV;  // groups
+  const int k = threadIdx.x % NV, g = threadIdx.x / NV;
+  double acc = 0.0;
+  for (int b = g; b < nblocks; b += G) acc += __ldcg(partial + (size_t)b * NV + k);
+  s_red[g * NV + k] = acc;
+  __syncthreads();
+  double tot = 0.0;
+  if (threadIdx.x < NV) {
+    for (int gg = 0; gg < G; ++gg) tot += s_red[gg * NV + threadIdx.x];
+  }
+  __syncthreads();
+  return tot;
+}
+
+// ---- K5a: vector SpMV, TPR lanes per row -----------------------------------------------------------
+// DOT: also accumulates sum_i y_i x_i per system, and the last CTA turns it into pq and alpha = rho/pq.
+template <int S, int VS, int TPR, bool DOT>
+__global__ void __launch_bounds__(kThreads) spmv_vector_kernel(int64_t nn, const int32_t* __restrict__ rowptr,
+                                                               const int32_t* __restrict__ col,
+                                                               const double* __restrict__ val,
+                                                               const double* __restrict__ x, double* __restrict__ y,
+                                                               double* __restrict__ partial, double* __restrict__ scal,
+                                                               unsigned int* __restrict__ ticket) {
+  __shared__ double s_red[kThreads];
+  const int lane = threadIdx.x % TPR;
+  const int64_t rows_per_pass = (int64_t)gridDim.x * (kThreads / TPR);
+  double dot[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) dot[s] = 0.0;
+  for (int64_t base = (int64_t)blockIdx.x * (kThreads / TPR); base < nn; base += rows_per_pass) {
+    const int64_t row = base + threadIdx.x / TPR;
+    // the trip count is uniform over the CTA (shuffles below use the full mask); rows past nn idle
+    const bool live = row < nn;
+    double acc[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) acc[s] = 0.0;
+    if (live) {
+      const int32_t b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
+      for (int32_t k = b + lane; k < e; k += TPR) {
+        const int64_t c = __ldg(col + k);
+        double xv[S];
+        load_sys<S>(x + c * S, xv);
+        if constexpr (VS == 1) {
+          const double a = __ldg(val + k);
+#pragma unroll
+          for (int s = 0; s < S; ++s) acc[s] = fma(a, xv[s], acc[s]);
+        } else {
+          double av[S];
+          load_sys<S>(val + (int64_t)k * S, av);
+#pragma unroll
+          for (int s = 0; s < S; ++s) acc[s] = fma(av[s], xv[s], acc[s]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], o);
+    }
+    if (live && lane == 0) {
+      store_sys<S>(y + row * S, acc);
+      if constexpr (DOT) {
+        double xr[S];
+        load_sys<S>(x + row * S, xr);
+#pragma unroll
+        for (int s = 0; s < S; ++s) dot[s] = fma(acc[s], xr[s], dot[s]);
+      }
+    }
+  }
+  if constexpr (DOT) {
+    block_sum<S>(dot, s_red, partial + (size_t)blockIdx.x * S);
+    if (is_last_block(ticket)) {
+      const double pq = sum_partials<S>(partial, gridDim.x, s_red);
+      if (threadIdx.x < S) {
+        const double rho = scal[SC_RHO * kMaxSys + threadIdx.x];
+        scal[SC_PQ * kMaxSys + threadIdx.x] = pq;
+        scal[SC_ALPHA * kMaxSys + threadIdx.x] = pq > 0.0 ? rho / pq : 0.0;
+      }
+    }
+  }
+}
+
+// ---- K5b: streaming SpMV (S == 1) ----------------------------------------------------------------
+// Each CTA walks row blocks of ~kStreamTile non-zeros.  The block's val/col slices are brought into
+// shared memory with two bulk async copies (cp.async.bulk -> UBLKCP, completion on an mbarrier), so
+// HBM sees only long, perfectly coalesced bursts; products val*x[col] are formed in place, one entry
+// per thread (x gathered through L1/L2), and a thread per row sums its segment from shared memory.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int STAGES>
+struct StreamSmem {
+  alignas(128) double val[STAGES][kStreamCap];
+  alignas(128) int32_t col[STAGES][kStreamCap];
+  alignas(8) uint64_t bar[STAGES];
+};
+
+template <int STAGES, bool DOT>
+__global__ void __launch_bounds__(kThreads) spmv_stream_kernel(const int32_t* __restrict__ rowptr,
+                                                               const int32_t* __restrict__ col,
+                                                               const double* __restrict__ val,
+                                                               const int32_t* __restrict__ blk_row, int32_t nblk,
+                                                               const double* __restrict__ x, double* __restrict__ y,
+                                                               double* __restrict__ partial, double* __restrict__ scal,
+                                                               unsigned int* __restrict__ ticket) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  StreamSmem<STAGES>& sm = *reinterpret_cast<StreamSmem<STAGES>*>(smem_raw);
+  __shared__ double s_red[kThreads];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&sm.bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // issue the loads of the row block `blk` into stage `st` (thread 0 only)
+  auto issue = [&](int32_t blk, int st) {
+    const int32_t r0 = __ldg(blk_row + blk), r1 = __ldg(blk_row + blk + 1);
+    const int32_t k0 = __ldg(rowptr + r0), k1 = __ldg(rowptr + r1);
+    const int32_t a0 = k0 & ~3, a1 = (k1 + 3) & ~3;
+    const uint32_t n = (uint32_t)(a1 - a0);
+    if (n == 0) {
+      mbar_expect_tx(&sm.bar[st], 0);
+      return;
+    }
+    mbar_expect_tx(&sm.bar[st], n * 12u);
+    bulk_g2s(sm.val[st], val + a0, n * 8u, &sm.bar[st]);
+    bulk_g2s(sm.col[st], col + a0, n * 4u, &sm.bar[st]);
+  };
+
+  double dot = 0.0;
+  uint32_t phase_bits = 0;  // bit s = parity to wait for on stage s
+  // prologue: fill STAGES-1 stages
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+      const int64_t b = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+      if (b < nblk) issue((int32_t)b, s);
+    }
+  }
+  int st = 0;
+  for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    // prefetch the block STAGES-1 ahead into the stage freed at the end of the previous iteration
+    if (tid == 0) {
+      const int64_t nb = blk + (int64_t)(STAGES - 1) * gridDim.x;
+      if (nb < nblk) {
+        fence_proxy_async();
+        issue((int32_t)nb, (st + STAGES - 1) % STAGES);
+      }
+    }
+    const int32_t r0 = __ldg(blk_row + blk), r1 = __ldg(blk_row + blk + 1);
+    const int32_t k0 = __ldg(rowptr + r0), k1 = __ldg(rowptr + r1);
+    const int32_t a0 = k0 & ~3;
+    const int32_t n = ((k1 + 3) & ~3) - a0;
+    mbar_wait(&sm.bar[st], (phase_bits >> st) & 1u);
+    phase_bits ^= 1u << st;
+    double* sv = sm.val[st];
+    const int32_t* sc = sm.col[st];
+#pragma unroll 4
+    for (int32_t k = tid; k < n; k += kThreads) sv[k] *= __ldg(x + sc[k]);
+    __syncthreads();
+    for (int32_t r = r0 + tid; r < r1; r += kThreads) {
+      const int32_t b = __ldg(rowptr + r) - a0, e = __ldg(rowptr + r + 1) - a0;
+      double acc = 0.0;
+      for (int32_t k = b; k < e; ++k) acc += sv[k];
+      y[r] = acc;
+      if constexpr (DOT) dot = fma(acc, __ldg(x + r), dot);
+    }
+    __syncthreads();  // stage st is free again
+    st = (st + 1) % STAGES;
+  }
+  if constexpr (DOT) {
+    double d1[1] = {dot};
+    block_sum<1>(d1, s_red, partial + blockIdx.x);
+    if (is_last_block(ticket)) {
+      const double pq = sum_partials<1>(partial, gridDim.x, s_red);
+      if (tid == 0) {
+        const double rho = scal[SC_RHO * kMaxSys];
+        scal[SC_PQ * kMaxSys] = pq;
+        scal[SC_ALPHA * kMaxSys] = pq > 0.0 ? rho / pq : 0.0;
+      }
+    }
+  }
+}
+
+// ---- K6: fused CG updates ----------------------------------------------------------------------
+// x += alpha p ; r -= alpha q ; partial sums of r.z (z = dinv r, or handed in for Chebyshev later) and r.r.
+// Last CTA: rho_new, rr, beta = rho_new / rho_old.   JAC: z = dinv*r folded in (z never stored).
+template <int S, int VS, bool JAC>
+__global__ void __launch_bounds__(kThreads) cg_update_kernel(int64_t nn, const double* __restrict__ p,
+                                                             const double* __restrict__ q,
+                                                             const double* __restrict__ dinv, double* __restrict__ x,
+                                                             double* __restrict__ r, double* __restrict__ partial,
+                                                             double* __restrict__ scal,
+                                                             unsigned int* __restrict__ ticket) {
+  __shared__ double s_red[kThreads];
+  double alpha[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) alpha[s] = scal[SC_ALPHA * kMaxSys + s];
+  double acc[2 * S];
+#pragma unroll
+  for (int s = 0; s < 2 * S; ++s) acc[s] = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nn; i += stride) {
+    double pv[S], qv[S], xv[S], rv[S];
+    load_sys<S>(p + i * S, pv);
+    load_sys<S>(q + i * S, qv);
+    load_sys<S>(x + i * S, xv);
+    load_sys<S>(r + i * S, rv);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      xv[s] = fma(alpha[s], pv[s], xv[s]);
+      rv[s] = fma(-alpha[s], qv[s], rv[s]);
+    }
+    store_sys<S>(x + i * S, xv);
+    store_sys<S>(r + i * S, rv);
+    if constexpr (JAC) {
+      if constexpr (VS == 1) {
+        const double d = __ldg(dinv + i);
+#pragma unroll
+        for (int s = 0; s < S; ++s) acc[s] = fma(rv[s] * d, rv[s], acc[s]);
+      } else {
+        double dv[S];
+        load_sys<S>(dinv + i * S, dv);
+#pragma unroll
+        for (int s = 0; s < S; ++s) acc[s] = fma(rv[s] * dv[s], rv[s], acc[s]);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) acc[S + s] = fma(rv[s], rv[s], acc[S + s]);
+  }
+  block_sum<2 * S>(acc, s_red, partial + (size_t)blockIdx.x * 2 * S);
+  if (is_last_block(ticket)) {
+    const double tot = sum_partials<2 * S>(partial, gridDim.x, s_red);
+    if (threadIdx.x < 2 * S) {
+      if (threadIdx.x >= S) {
+        scal[SC_RR * kMaxSys + threadIdx.x - S] = tot;
+      } else if (JAC) {
+        const double rho_old = scal[SC_RHO * kMaxSys + threadIdx.x];
+        scal[SC_RHO * kMaxSys + threadIdx.x] = tot;
+        scal[SC_BETA * kMaxSys + threadIdx.x] = rho_old > 0.0 ? tot / rho_old : 0.0;
+      }
+    }
+  }
+}
+
+// p = z + beta p   with z = dinv * r (JAC) or z given
+template <int S, int VS, bool JAC>
+__global__ void __launch_bounds__(kThreads) cg_pupdate_kernel(int64_t nn, const double* __restrict__ r,
+                                                              const double* __restrict__ zin,
+                                                              const double* __restrict__ dinv, double* __restrict__ p,
+                                                              const double* __restrict__ scal, int first) {
+  double beta[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) beta[s] = first ? 0.0 : scal[SC_BETA * kMaxSys + s];
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nn; i += stride) {
+    double zv[S], pv[S];
+    if constexpr (JAC) {
+      load_sys<S>(r + i * S, zv);
+      if constexpr (VS == 1) {
+        const double d = __ldg(dinv + i);
+#pragma unroll
+        for (int s = 0; s < S; ++s) zv[s] *= d;
+      } else {
+        double dv[S];
+        load_sys<S>(dinv + i * S, dv);
+#pragma unroll
+        for (int s = 0; s < S; ++s) zv[s] *= dv[s];
+      }
+    } else {
+      load_sys<S>(zin + i * S, zv);
+    }
+    if (first) {
+      store_sys<S>(p + i * S, zv);
+    } else {
+      load_sys<S>(p + i * S, pv);
+#pragma unroll
+      for (int s = 0; s < S; ++s) pv[s] = fma(beta[s], pv[s], zv[s]);
+      store_sys<S>(p + i * S, pv);
+    }
+  }
+}
+
+// generic per-system dots: out slots (a.b) -> slotA, (c.c) -> slotB (either may be -1 via null pointers).
+// mode 0: slotA = sum a*b*(w or 1) ; used for rho0 = r.(dinv r), rr0 = r.r, bnorm2 = b.b, r.z
+template <int S, int VS>
+__global__ void __launch_bounds__(kThreads) dots_kernel(int64_t nn, const double* __restrict__ a,
+                                                        const double* __restrict__ b, const double* __restrict__ w,
+                                                        double* __restrict__ partial, double* __restrict__ scal,
+                                                        int slot_ab, int slot_aa, int beta_from_rho,
+                                                        unsigned int* __restrict__ ticket) {
+  __shared__ double s_red[kThreads];
+  double acc[2 * S];
+#pragma unroll
+  for (int s = 0; s < 2 * S; ++s) acc[s] = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nn; i += stride) {
+    double av[S], bv[S];
+    load_sys<S>(a + i * S, av);
+    load_sys<S>(b + i * S, bv);
+    if (w) {
+      if constexpr (VS == 1) {
+        const double d = __ldg(w + i);
+#pragma unroll
+        for (int s = 0; s < S; ++s) bv[s] *= d;
+      } else {
+        double dv[S];
+        load_sys<S>(w + i * S, dv);
+#pragma unroll
+        for (int s = 0; s < S; ++s) bv[s] *= dv[s];
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      acc[s] = fma(av[s], bv[s], acc[s]);
+      acc[S + s] = fma(av[s], av[s], acc[S + s]);
+    }
+  }
+  block_sum<2 * S>(acc, s_red, partial + (size_t)blockIdx.x * 2 * S);
+  if (is_last_block(ticket)) {
+    const double tot = sum_partials<2 * S>(partial, gridDim.x, s_red);
+    if (threadIdx.x < 2 * S) {
+      if (threadIdx.x < S) {
+        if (slot_ab >= 0) {
+          if (beta_from_rho) {
+            const double rho_old = scal[slot_ab * kMaxSys + threadIdx.x];
+            scal[SC_BETA * kMaxSys + threadIdx.x] = rho_old > 0.0 ? tot / rho_old : 0.0;
+          }
+          scal[slot_ab * kMaxSys + threadIdx.x] = tot;
+        }
+      } else if (slot_aa >= 0) {
+        scal[slot_aa * kMaxSys + threadIdx.x - S] = tot;
+      }
+    }
+  }
+}
+
+// r = b - q
+template <int S>
+__global__ void __launch_bounds__(kThreads) residual_kernel(int64_t n, const double* __restrict__ b,
+                                                            const double* __restrict__ q, double* __restrict__ r) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n * S; i += stride) r[i] = b[i] - q[i];
+}
+
+// ---- K7: Chebyshev polynomial preconditioner -------------------------------------------------------
+// Gershgorin bound of D^-1 A per system: lmax[s] = max_i sum_j |a_ij| * dinv_i
+template <int VS>
+__global__ void __launch_bounds__(kThreads) gershgorin_kernel(int64_t nn, const int32_t* __restrict__ rowptr,
+                                                              const double* __restrict__ val,
+                                                              const double* __restrict__ dinv,
+                                                              double* __restrict__ partial, double* __restrict__ scal,
+                                                              unsigned int* __restrict__ ticket) {
+  __shared__ double s_red[kThreads];
+  double mx[VS];
+#pragma unroll
+  for (int s = 0; s < VS; ++s) mx[s] = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nn; i += stride) {
+    const int32_t b = rowptr[i], e = rowptr[i + 1];
+    double sum[VS];
+#pragma unroll
+    for (int s = 0; s < VS; ++s) sum[s] = 0.0;
+    for (int32_t k = b; k < e; ++k) {
+#pragma unroll
+      for (int s = 0; s < VS; ++s) sum[s] += fabs(val[(int64_t)k * VS + s]);
+    }
+#pragma unroll
+    for (int s = 0; s < VS; ++s) mx[s] = fmax(mx[s], sum[s] * dinv[i * VS + s]);
+  }
+#pragma unroll
+  for (int s = 0; s < VS; ++s) mx[s] = warp_max(mx[s]);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < VS; ++s) s_red[wid * VS + s] = mx[s];
+  }
+  __syncthreads();
+  if (threadIdx.x < VS) {
+    double m = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) m = fmax(m, s_red[w * VS + threadIdx.x]);
+    partial[(size_t)blockIdx.x * VS + threadIdx.x] = m;
+  }
+  if (is_last_block(ticket)) {
+    if (threadIdx.x < VS) {
+      double m = 0.0;
+      for (int b = 0; b < (int)gridDim.x; ++b) m = fmax(m, __ldcg(partial + (size_t)b * VS + threadIdx.x));
+      scal[SC_LMAX * kMaxSys + threadIdx.x] = m;
+    }
+  }
+}
+
+// Chebyshev step kernels.  State: z (accumulated correction), rt = D^-1 (r - A z) (scaled residual),
+// d (direction).  coef is [deg+1][S][2] on the device.
+//   init : rt = dinv*r ; d = rt*c0 ; z = d
+//   step : (after q = A d)  rt -= dinv*q ; d = c1*d + c2*rt ; z += d
+template <int S, int VS>
+__global__ void __launch_bounds__(kThreads) cheb_init_kernel(int64_t nn, const double* __restrict__ r,
+                                                             const double* __restrict__ dinv,
+                                                             const double* __restrict__ coef, double* __restrict__ rt,
+                                                             double* __restrict__ d, double* __restrict__ z) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nn; i += stride) {
+    double rv[S], dv[S];
+    load_sys<S>(r + i * S, rv);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      rv[s] *= dinv[i * VS + (VS == 1 ? 0 : s)];
+      dv[s] = rv[s] * coef[s * 2];
+    }
+    store_sys<S>(rt + i * S, rv);
+    store_sys<S>(d + i * S, dv);
+    store_sys<S>(z + i * S, dv);
+  }
+}
+template <int S, int VS>
+__global__ void __launch_bounds__(kThreads) cheb_step_kernel(int64_t nn, const double* __restrict__ q,
+                                                             const double* __restrict__ dinv,
+                                                             const double* __restrict__ coef /*[S][2] of this step*/,
+                                                             double* __restrict__ rt, double* __restrict__ d,
+                                                             double* __restrict__ z) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nn; i += stride) {
+    double qv[S], rv[S], dv[S], zv[S];
+    load_sys<S>(q + i * S, qv);
+    load_sys<S>(rt + i * S, rv);
+    load_sys<S>(d + i * S, dv);
+    load_sys<S>(z + i * S, zv);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      rv[s] = fma(-dinv[i * VS + (VS == 1 ? 0 : s)], qv[s], rv[s]);
+      dv[s] = coef[s * 2] * dv[s] + coef[s * 2 + 1] * rv[s];
+      zv[s] += dv[s];
+    }
+    store_sys<S>(rt + i * S, rv);
+    store_sys<S>(d + i * S, dv);
+    store_sys<S>(z + i * S, zv);
+  }
+}
+
+int grid_for(ptfem_ctx* ctx, int64_t work_items, int per_block) {
+  int64_t g = (work_items + per_block - 1) / per_block;
+  const int64_t cap = (int64_t)ctx->sm_count * kCtasPerSm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+int pick_tpr(const LinSys& A) {
+  const double avg = A.nn > 0 ? (double)A.nnz / (double)A.nn : 1.0;
+  if (avg <= 3.0) return 2;
+  if (avg <= 6.0) return 4;
+  if (avg <= 24.0) return 8;
+  if (avg <= 48.0) return 16;
+  return 32;
+}
+
+template <int S, int VS, bool DOT>
+int launch_vector(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y, PcgWork* w) {
+  const int tpr = pick_tpr(A);
+  double* partial = w ? w->partial.p : nullptr;
+  double* scal = w ? w->scal.p : nullptr;
+  unsigned int* ticket = w ? w->ticket.p : nullptr;
+#define PT_VEC(TPR)                                                                                             \
+  {                                                                                                             \
+    const int grid = grid_for(ctx, A.nn, kThreads / TPR);                                                       \
+    spmv_vector_kernel<S, VS, TPR, DOT><<<grid, kThreads, 0, ctx->stream>>>(A.nn, A.rowptr, A.col, A.val, x, y, \
+                                                                           partial, scal, ticket);             \
+  }
+  switch (tpr) {
+    case 2: PT_VEC(2); break;
+    case 4: PT_VEC(4); break;
+    case 8: PT_VEC(8); break;
+    case 16: PT_VEC(16); break;
+    default: PT_VEC(32); break;
+  }
+#undef PT_VEC
+  PT_LAUNCH_CHECK(ctx);
+  return PTFEM_OK;
+}
+
+template <int STAGES, bool DOT>
+int launch_stream_t(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y, PcgWork* w) {
+  const size_t smem = sizeof(StreamSmem<STAGES>);
+  const uint32_t bit = 1u << (STAGES * 2 + (DOT ? 1 : 0));
+  if (!(ctx->func_attr_done & bit)) {
+    PT_CK(cudaFuncSetAttribute(spmv_stream_kernel<STAGES, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctx->func_attr_done |= bit;
+  }
+  int per_sm = (int)((size_t)(220 * 1024) / (smem + 2304));
+  if (per_sm > kCtasPerSm) per_sm = kCtasPerSm;
+  if (per_sm < 1) per_sm = 1;
+  int64_t grid = (int64_t)ctx->sm_count * per_sm;
+  if (grid > A.nblk) grid = A.nblk;
+  if (grid < 1) grid = 1;
+  spmv_stream_kernel<STAGES, DOT><<<(int)grid, kThreads, smem, ctx->stream>>>(
+      A.rowptr, A.col, A.val, A.blk_row, A.nblk, x, y, w ? w->partial.p : nullptr, w ? w->scal.p : nullptr,
+      w ? w->ticket.p : nullptr);
+  PT_LAUNCH_CHECK(ctx);
+  return PTFEM_OK;
+}
+
+template <int S, int VS>
+int spmv_sv(ptfem_ctx* ctx, const LinSys& A, int variant, const double* x, double* y, PcgWork* w, bool dot) {
+  if constexpr (S == 1) {
+    if (variant == PTFEM_SPMV_STREAM)
+      return dot ? launch_stream_t<2, true>(ctx, A, x, y, w) : launch_stream_t<2, false>(ctx, A, x, y, w);
+    if (variant == PTFEM_SPMV_STREAM1)
+      return dot ? launch_stream_t<1, true>(ctx, A, x, y, w) : launch_stream_t<1, false>(ctx, A, x, y, w);
+  }
+  return dot ? launch_vector<S, VS, true>(ctx, A, x, y, w) : launch_vector<S, VS, false>(ctx, A, x, y, w);
+}
+
+// dispatch on (S, VS) with VS in {1, S}
+#define PT_DISPATCH_S(S_, VS_, CALL)                                            \
+  switch (S_) {                                                                 \
+    case 1: { constexpr int S = 1; constexpr int VS = 1; CALL; } break;         \
+    case 2: if ((VS_) == 1) { constexpr int S = 2; constexpr int VS = 1; CALL; } else { constexpr int S = 2; constexpr int VS = 2; CALL; } break;   \
+    case 4: if ((VS_) == 1) { constexpr int S = 4; constexpr int VS = 1; CALL; } else { constexpr int S = 4; constexpr int VS = 4; CALL; } break;   \
+    case 8: if ((VS_) == 1) { constexpr int S = 8; constexpr int VS = 1; CALL; } else { constexpr int S = 8; constexpr int VS = 8; CALL; } break;   \
+    case 16: if ((VS_) == 1) { constexpr int S = 16; constexpr int VS = 1; CALL; } else { constexpr int S = 16; constexpr int VS = 16; CALL; } break; \
+    default: return set_err(PTFEM_ERR_ARG, "unsupported system count %d", (int)(S_)); \
+  }
+
+}  // namespace
+
+int ptfem_stream_tile_nnz() { return kStreamTile; }
+
+namespace ptfem {
+
+int resolve_variant(const LinSys& A, int variant) {
+  const bool stream_ok = A.S == 1 && A.blk_row != nullptr && A.nblk > 0 && A.max_row <= kStreamMaxRow;
+  if (variant == PTFEM_SPMV_AUTO) return stream_ok && A.nnz >= (int64_t)1 << 20 ? PTFEM_SPMV_STREAM : PTFEM_SPMV_VECTOR;
+  if ((variant == PTFEM_SPMV_STREAM || variant == PTFEM_SPMV_STREAM1) && !stream_ok) return PTFEM_SPMV_VECTOR;
+  return variant;
+}
+
+int spmv_launch(ptfem_ctx* ctx, const LinSys& A, int variant, const double* x, double* y, PcgWork* work, bool cg_dot) {
+  variant = resolve_variant(A, variant);
+  if (cg_dot && !work) return set_err(PTFEM_ERR_STATE, "spmv with fused dot needs a workspace");
+  PT_DISPATCH_S(A.S, A.VS, return (spmv_sv<S, VS>(ctx, A, variant, x, y, work, cg_dot)));
+  return PTFEM_OK;
+}
+
+void pcg_work_drop_graph(PcgWork& w) {
+  if (w.graph) cudaGraphExecDestroy(w.graph);
+  w.graph = nullptr;
+  w.graph_iters = 0;
+}
+
+int pcg_work_alloc(ptfem_ctx* ctx, PcgWork& w, int64_t nn, int S, int VS) {
+  (void)VS;
+  if (w.S != S || w.r.n < (size_t)nn * S) pcg_work_drop_graph(w);
+  w.S = S;
+  const size_t n = (size_t)nn * S;
+  PT_TRY(w.r.alloc(n));
+  PT_TRY(w.p.alloc(n));
+  PT_TRY(w.q.alloc(n));
+  const size_t maxblocks = (size_t)ctx->sm_count * kCtasPerSm;
+  PT_TRY(w.partial.alloc(maxblocks * 2 * kMaxSys));
+  PT_TRY(w.scal.alloc((size_t)SC_COUNT * kMaxSys));
+  if (!w.ticket.p) {
+    PT_TRY(w.ticket.alloc(4));
+    PT_CK(cudaMemsetAsync(w.ticket.p, 0, 4 * sizeof(unsigned int), ctx->stream));
+  }
+  return PTFEM_OK;
+}
+
+namespace detail {
+
+
+// one preconditioner application z = M^-1 r (Chebyshev); uses w.q as SpMV output, w.z / w.rt / w.d
+template <int S, int VS>
+int cheb_apply(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int degree) {
+  const int grid = grid_for(ctx, A.nn, kThreads);
+  double* rt = w.rt.p;
+  double* d = w.d.p;
+  cheb_init_kernel<S, VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.coef.p, rt, d, w.z.p);
+  PT_LAUNCH_CHECK(ctx);
+  for (int k = 1; k <= degree; ++k) {
+    PT_TRY((spmv_sv<S, VS>(ctx, A, variant, d, w.q.p, &w, false)));
+    cheb_step_kernel<S, VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.q.p, A.dinv, w.coef.p + (size_t)k * S * 2, rt, d,
+                                                                w.z.p);
+    PT_LAUNCH_CHECK(ctx);
+  }
+  return PTFEM_OK;
+}
+
+template <int S, int VS>
+int pcg_iteration(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int precond, int degree, double* x) {
+  const int grid = grid_for(ctx, A.nn, kThreads);
+  // q = A p, pq, alpha
+  PT_TRY((spmv_sv<S, VS>(ctx, A, variant, w.p.p, w.q.p, &w, true)));
+  if (precond == PTFEM_PRECOND_JACOBI) {
+    cg_update_kernel<S, VS, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.p.p, w.q.p, A.dinv, x, w.r.p, w.partial.p,
+                                                                      w.scal.p, w.ticket.p);
+    PT_LAUNCH_CHECK(ctx);
+    cg_pupdate_kernel<S, VS, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, nullptr, A.dinv, w.p.p, w.scal.p, 0);
+    PT_LAUNCH_CHECK(ctx);
+  } else {
+    cg_update_kernel<S, VS, false><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.p.p, w.q.p, A.dinv, x, w.r.p,
+                                                                       w.partial.p, w.scal.p, w.ticket.p);
+    PT_LAUNCH_CHECK(ctx);
+    PT_TRY((cheb_apply<S, VS>(ctx, A, w, variant, degree)));
+    // rho_new = r.z, beta = rho_new/rho_old
+    dots_kernel<S, VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.z.p, nullptr, w.partial.p, w.scal.p, SC_RHO, -1,
+                                                           1, w.ticket.p);
+    PT_LAUNCH_CHECK(ctx);
+    cg_pupdate_kernel<S, VS, false><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.z.p, A.dinv, w.p.p, w.scal.p, 0);
+    PT_LAUNCH_CHECK(ctx);
+  }
+  return PTFEM_OK;
+}
+
+// r = b - A x ; z ; p = z ; rho = r.z ; rr = r.r
+template <int S, int VS>
+int pcg_start(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int precond, int degree, double* x) {
+  const int grid = grid_for(ctx, A.nn, kThreads);
+  PT_TRY((spmv_sv<S, VS>(ctx, A, variant, x, w.q.p, &w, false)));
+  residual_kernel<S><<<grid, kThreads, 0, ctx->stream>>>(A.nn, A.b, w.q.p, w.r.p);
+  PT_LAUNCH_CHECK(ctx);
+  if (precond == PTFEM_PRECOND_JACOBI) {
+    dots_kernel<S, VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.r.p, A.dinv, w.partial.p, w.scal.p, SC_RHO, SC_RR,
+                                                           0, w.ticket.p);
+    PT_LAUNCH_CHECK(ctx);
+    cg_pupdate_kernel<S, VS, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, nullptr, A.dinv, w.p.p, w.scal.p, 1);
+    PT_LAUNCH_CHECK(ctx);
+  } else {
+    PT_TRY((cheb_apply<S, VS>(ctx, A, w, variant, degree)));
+    dots_kernel<S, VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.z.p, nullptr, w.partial.p, w.scal.p, SC_RHO, SC_RR,
+                                                           0, w.ticket.p);
+    PT_LAUNCH_CHECK(ctx);
+    cg_pupdate_kernel<S, VS, false><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.z.p, A.dinv, w.p.p, w.scal.p, 1);
+    PT_LAUNCH_CHECK(ctx);
+  }
+  return PTFEM_OK;
+}
+
+template <int S, int VS>
+int pcg_solve_t(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_opts& o, double* x, ptfem_solve_stats* st) {
+  const int variant = resolve_variant(A, o.spmv_variant);
+  const int precond = o.precond;
+  const int degree = precond == PTFEM_PRECOND_CHEBYSHEV ? (o.cheb_degree > 0 ? o.cheb_degree : 4) : 0;
+  const int grid = grid_for(ctx, A.nn, kThreads);
+  const int check = o.check_every > 0 ? o.check_every : 50;
+  double* h = ctx->h_pinned;  // >= SC_COUNT*kMaxSys doubles
+  int spmv_calls = 0;
+
+  if (precond == PTFEM_PRECOND_CHEBYSHEV) {
+    const size_t n = (size_t)A.nn * S;
+    PT_TRY(w.z.alloc(n));
+    PT_TRY(w.rt.alloc(n));
+    PT_TRY(w.d.alloc(n));
+    PT_TRY(w.coef.alloc((size_t)(degree + 1) * S * 2));
+    gershgorin_kernel<VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, A.rowptr, A.val, A.dinv, w.partial.p, w.scal.p,
+                                                              w.ticket.p);
+    PT_LAUNCH_CHECK(ctx);
+    PT_CK(cudaMemcpyAsync(h, w.scal.p + SC_LMAX * kMaxSys, kMaxSys * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    const double ratio = o.cheb_ratio > 1.0 ? o.cheb_ratio : 30.0;
+    std::vector<double> coef((size_t)(degree + 1) * S * 2);
+    for (int s = 0; s < S; ++s) {
+      const double lmax = 1.05 * (h[VS == 1 ? 0 : s] > 0.0 ? h[VS == 1 ? 0 : s] : 2.0);
+      const double lmin = lmax / ratio;
+      const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma1 = theta / delta;
+      double rho = 1.0 / sigma1;
+      coef[(size_t)s * 2] = 1.0 / theta;
+      coef[(size_t)s * 2 + 1] = 0.0;
+      for (int k = 1; k <= degree; ++k) {
+        const double rho_new = 1.0 / (2.0 * sigma1 - rho);
+        coef[((size_t)k * S + s) * 2] = rho_new * rho;
+        coef[((size_t)k * S + s) * 2 + 1] = 2.0 * rho_new / delta;
+        rho = rho_new;
+      }
+    }
+    PT_CK(cudaMemcpyAsync(w.coef.p, coef.data(), coef.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+  }
+
+  // ||b||^2
+  dots_kernel<S, VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, A.b, A.b, nullptr, w.partial.p, w.scal.p, -1, SC_BN2, 0,
+                                                         w.ticket.p);
+  PT_LAUNCH_CHECK(ctx);
+
+  cudaEvent_t ev0, ev1;
+  PT_CK(cudaEventCreate(&ev0));
+  PT_CK(cudaEventCreate(&ev1));
+  PT_CK(cudaEventRecord(ev0, ctx->stream));
+
+  const double rtol2 = o.rtol * o.rtol;
+  int it = 0;
+  bool converged = false;
+  double rel = 0.0;
+  const int max_restarts = 3;
+  int restarts = 0;
+  int rc = PTFEM_OK;
+
+  auto read_scal = [&]() -> int {
+    PT_CK(cudaMemcpyAsync(h, w.scal.p, (size_t)SC_COUNT * kMaxSys * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    return PTFEM_OK;
+  };
+  auto worst_rel2 = [&]() {
+    double worst = 0.0;
+    for (int s = 0; s < S; ++s) {
+      const double bn2 = h[SC_BN2 * kMaxSys + s], rr = h[SC_RR * kMaxSys + s];
+      if (bn2 > 0.0) {
+        if (!(rr == rr)) return (double)INFINITY;
+        worst = rr / bn2 > worst ? rr / bn2 : worst;
+      }
+    }
+    return worst;
+  };
+
+  while (true) {
+    rc = pcg_start<S, VS>(ctx, A, w, variant, precond, degree, x);
+    if (rc) break;
+    spmv_calls += 1 + degree;
+    rc = read_scal();
+    if (rc) break;
+    double w2 = worst_rel2();
+    rel = sqrt(w2);
+    if (w2 <= rtol2) {
+      converged = true;
+      break;
+    }
+    // iterate in chunks of `check`
+    bool chunk_conv = false;
+    while (it < o.maxit) {
+      const int n_it = (o.maxit - it) < check ? (o.maxit - it) : check;
+      const bool use_graph = o.use_graph && n_it == check;
+      if (use_graph) {
+        if (!w.graph || w.graph_iters != check || w.graph_variant != variant || w.graph_precond != precond ||
+            w.graph_cheb != degree || w.graph_x != x || w.graph_val != A.val || w.graph_b != A.b || w.graph_dinv != A.dinv) {
+          pcg_work_drop_graph(w);
+          cudaGraph_t g = nullptr;
+          PT_CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+          const int64_t l0 = ctx->launches;
+          for (int k = 0; k < check && rc == PTFEM_OK; ++k) rc = pcg_iteration<S, VS>(ctx, A, w, variant, precond, degree, x);
+          w.graph_launches = ctx->launches - l0;
+          ctx->launches = l0;
+          cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+          if (rc) break;
+          if (ce != cudaSuccess) {
+            rc = set_err(PTFEM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+            break;
+          }
+          ce = cudaGraphInstantiate(&w.graph, g, 0);
+          cudaGraphDestroy(g);
+          if (ce != cudaSuccess) {
+            rc = set_err(PTFEM_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+            break;
+          }
+          w.graph_iters = check;
+          w.graph_variant = variant;
+          w.graph_precond = precond;
+          w.graph_cheb = degree;
+          w.graph_x = x;
+          w.graph_val = A.val;
+          w.graph_b = A.b;
+          w.graph_dinv = A.dinv;
+        }
+        cudaError_t ce = cudaGraphLaunch(w.graph, ctx->stream);
+        if (ce != cudaSuccess) {
+          rc = set_err(PTFEM_ERR_CUDA, "graph launch failed: %s", cudaGetErrorString(ce));
+          break;
+        }
+        ctx->launches += w.graph_launches;
+      } else {
+        for (int k = 0; k < n_it && rc == PTFEM_OK; ++k) rc = pcg_iteration<S, VS>(ctx, A, w, variant, precond, degree, x);
+        if (rc) break;
+      }
+      it += n_it;
+      spmv_calls += n_it * (1 + degree);
+      rc = read_scal();
+      if (rc) break;
+      w2 = worst_rel2();
+      rel = sqrt(w2);
+      if (!(w2 == w2) || w2 > 1e300) {
+        rc = set_err(PTFEM_ERR_NOCONV, "PCG diverged (residual is not finite) after %d iterations", it);
+        break;
+      }
+      if (w2 <= rtol2) {
+        chunk_conv = true;
+        break;
+      }
+    }
+    if (rc) break;
+    if (!chunk_conv) break;  // maxit
+    // recurrence says converged: confirm on the true residual (restart replaces the residual)
+    if (restarts >= max_restarts) break;
+    ++restarts;
+  }
+  cudaEventRecord(ev1, ctx->stream);
+  cudaEventSynchronize(ev1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ev0, ev1);
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  if (rc) return rc;
+
+  // final true residual
+  PT_TRY((spmv_sv<S, VS>(ctx, A, variant, x, w.q.p, &w, false)));
+  residual_kernel<S><<<grid, kThreads, 0, ctx->stream>>>(A.nn, A.b, w.q.p, w.r.p);
+  PT_LAUNCH_CHECK(ctx);
+  dots_kernel<S, VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.r.p, nullptr, w.partial.p, w.scal.p, -1, SC_RR, 0,
+                                                         w.ticket.p);
+  PT_LAUNCH_CHECK(ctx);
+  PT_TRY(read_scal());
+  const double true_rel = sqrt(worst_rel2());
+  if (!converged && it < o.maxit && true_rel <= 10.0 * o.rtol) converged = true;  // stagnated at round-off
+  if (st) {
+    st->iterations = it;
+    st->converged = converged ? 1 : 0;
+    st->nsys = S;
+    st->spmv_calls = spmv_calls + 1;
+    st->rel_residual = rel;
+    st->true_rel_residual = true_rel;
+    st->solve_ms = ms;
+    st->spmv_ms = 0.0;
+  }
+  if (!converged)
+    return set_err(PTFEM_ERR_NOCONV, "PCG did not reach rtol=%g in %d iterations (rel. residual %.3e)", o.rtol, it, true_rel);
+  return PTFEM_OK;
+}
+
+}  // namespace detail
+
+int pcg_solve(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_opts& o, double* x, ptfem_solve_stats* stats) {
+  PT_TRY(pcg_work_alloc(ctx, w, A.nn, A.S, A.VS));
+  PT_DISPATCH_S(A.S, A.VS, return (detail::pcg_solve_t<S, VS>(ctx, A, w, o, x, stats)));
+  return PTFEM_OK;
+}
+
+}  // namespace ptfem

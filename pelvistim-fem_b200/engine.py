@@ -1,0 +1,433 @@
+"""ctypes binding of ``libptfem.so`` (``include/ptfem.h``) — the only way host code reaches the
+solver.  There is no CPU fallback: if the shared library is missing or no CUDA device is
+present, construction fails loudly.
+
+The classes mirror the stages of the ElmerSolver run the library replaces
+(``step03_ankle_layers/run_layered_sweep.py:1099``): mesh upload -> pattern -> assembly ->
+boundary conditions -> solve -> current recovery -> metric reductions.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_LIB = None
+_LIB_PATH = Path(__file__).resolve().parent / "libptfem.so"
+
+PRECOND_JACOBI, PRECOND_CHEBYSHEV = 0, 1
+RECOVER_L2, RECOVER_LUMPED, RECOVER_AVERAGE = 0, 1, 2
+SPMV_AUTO, SPMV_VECTOR, SPMV_STREAM, SPMV_STREAM1 = 0, 1, 2, 3
+ERR_NOCONV = -4
+_RECOVER = {"l2": RECOVER_L2, "lumped": RECOVER_LUMPED, "average": RECOVER_AVERAGE}
+
+
+class PtfemError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libptfem error {code}: {msg}")
+        self.code = code
+
+
+class SolveOpts(C.Structure):
+    _fields_ = [("precond", C.c_int32), ("maxit", C.c_int32), ("check_every", C.c_int32),
+                ("cheb_degree", C.c_int32), ("rtol", C.c_double), ("cheb_ratio", C.c_double),
+                ("spmv_variant", C.c_int32), ("use_graph", C.c_int32)]
+
+
+class SolveStats(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("converged", C.c_int32), ("nsys", C.c_int32),
+                ("spmv_calls", C.c_int32), ("rel_residual", C.c_double), ("true_rel_residual", C.c_double),
+                ("solve_ms", C.c_double), ("spmv_ms", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Footprint(C.Structure):
+    _fields_ = [("cx", C.c_double), ("cy", C.c_double), ("r", C.c_double), ("square", C.c_int32), ("pad_", C.c_int32)]
+
+
+def lib_path():
+    return Path(os.environ.get("PTFEM_LIB", _LIB_PATH))
+
+
+def load_library():
+    """Load libptfem.so and declare the argument types of every entry point of ptfem.h."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not p.exists():
+        raise PtfemError(-100, f"{p} not found — build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+    L = C.CDLL(str(p))
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    P = C.POINTER
+    sig = {
+        "ptfem_last_error": (C.c_char_p, []),
+        "ptfem_version": (C.c_int, []),
+        "ptfem_device_count": (C.c_int, [P(C.c_int)]),
+        "ptfem_ctx_create": (C.c_int, [C.c_int, P(vp)]),
+        "ptfem_ctx_destroy": (C.c_int, [vp]),
+        "ptfem_ctx_sync": (C.c_int, [vp]),
+        "ptfem_ctx_launch_count": (C.c_int, [vp, P(i64)]),
+        "ptfem_ctx_stream": (C.c_int, [vp, P(vp)]),
+        "ptfem_mesh_create": (C.c_int, [vp, i64, vp, i64, vp, vp, i64, vp, vp, P(vp)]),
+        "ptfem_mesh_destroy": (C.c_int, [vp]),
+        "ptfem_mesh_set_coords": (C.c_int, [vp, vp]),
+        "ptfem_pattern": (C.c_int, [vp, P(i64)]),
+        "ptfem_pattern_get": (C.c_int, [vp, vp, vp]),
+        "ptfem_e2nnz_get": (C.c_int, [vp, vp]),
+        "ptfem_assemble": (C.c_int, [vp, i32, vp, vp, i32]),
+        "ptfem_values_get": (C.c_int, [vp, i32, i32, vp]),
+        "ptfem_bc_reset": (C.c_int, [vp, i32]),
+        "ptfem_bc_dirichlet": (C.c_int, [vp, i32, i32, dbl]),
+        "ptfem_bc_neumann": (C.c_int, [vp, i32, i32, dbl]),
+        "ptfem_bc_neumann_tris": (C.c_int, [vp, i32, i64, vp, dbl]),
+        "ptfem_rhs_get": (C.c_int, [vp, i32, vp]),
+        "ptfem_solve_opts_default": (None, [P(SolveOpts)]),
+        "ptfem_solve": (C.c_int, [vp, P(SolveOpts), vp, P(SolveStats)]),
+        "ptfem_solve_device": (C.c_int, [vp, P(SolveOpts), P(SolveStats)]),
+        "ptfem_phi_get": (C.c_int, [vp, i32, vp]),
+        "ptfem_phi_set": (C.c_int, [vp, i32, vp]),
+        "ptfem_spmv": (C.c_int, [vp, i32, i32, i32, vp, vp]),
+        "ptfem_spmv_bench": (C.c_int, [vp, i32, i32, P(dbl)]),
+        "ptfem_element_fields": (C.c_int, [vp, i32, vp, vp]),
+        "ptfem_recover_current": (C.c_int, [vp, i32, i32, vp]),
+        "ptfem_current_get": (C.c_int, [vp, vp]),
+        "ptfem_metric_nodes": (C.c_int, [vp, i32, i32, dbl, dbl, i32, vp, i32, dbl, P(dbl)]),
+        "ptfem_metric_pad_current": (C.c_int, [vp, i32, dbl, P(Footprint), dbl, P(dbl)]),
+        "ptfem_metric_roi": (C.c_int, [vp, i32, P(dbl), dbl, P(dbl), i32, dbl, dbl, i32, P(dbl)]),
+        "ptfem_metric_column_fit": (C.c_int, [vp, i32, dbl, dbl, dbl, P(dbl)]),
+        "ptfem_metric_jstats": (C.c_int, [vp, i32, P(dbl)]),
+        "ptfem_metric_reaction": (C.c_int, [vp, i32, i32, P(dbl)]),
+        "ptfem_sample_polyline": (C.c_int, [vp, i32, i64, vp, vp, vp]),
+        "ptfem_dist_unique_id": (C.c_int, [C.c_char_p, vp]),
+        "ptfem_dist_init": (C.c_int, [vp, C.c_char_p, vp, i32, i32]),
+        "ptfem_dist_finalize": (C.c_int, [vp]),
+        "ptfem_dist_system_create": (C.c_int, [vp, i64, i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, P(vp)]),
+        "ptfem_dist_solve": (C.c_int, [vp, P(SolveOpts), vp, P(SolveStats), P(dbl), P(dbl), P(dbl)]),
+    }
+    for name, (res, args) in sig.items():
+        if name.startswith("ptfem_dist_") and not hasattr(L, name):
+            continue                   # TEMP until dist.cu lands
+        f = getattr(L, name)          # AttributeError here = header and library out of sync
+        f.restype = res
+        f.argtypes = args
+    _LIB = L
+    return L
+
+
+EXPORTED_SYMBOLS = None  # filled lazily by exported_symbols()
+
+
+def exported_symbols():
+    """Names declared in include/ptfem.h (parsed from the header)."""
+    import re
+    hdr = Path(__file__).resolve().parent.parent / "include" / "ptfem.h"
+    txt = hdr.read_text()
+    return sorted(set(re.findall(r"\b(ptfem_[a-z0-9_]+)\s*\(", txt)))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Context:
+    """One per GPU (``ptfem_ctx``)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.device = device
+        h = C.c_void_p()
+        self._h = None
+        self._ck(self.lib.ptfem_ctx_create(device, C.byref(h)))
+        self._h = h
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise PtfemError(rc, self.lib.ptfem_last_error().decode(errors="replace"))
+
+    def sync(self):
+        self._ck(self.lib.ptfem_ctx_sync(self._h))
+
+    @property
+    def launches(self):
+        n = C.c_int64()
+        self._ck(self.lib.ptfem_ctx_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    @property
+    def stream(self):
+        s = C.c_void_p()
+        self._ck(self.lib.ptfem_ctx_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    def mesh(self, nodes, tets, region, tris, bcid):
+        return DeviceMesh(self, nodes, tets, region, tris, bcid)
+
+    def close(self):
+        if self._h is not None:
+            self.lib.ptfem_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def device_count():
+    n = C.c_int(0)
+    load_library().ptfem_device_count(C.byref(n))
+    return n.value
+
+
+class DeviceMesh:
+    """A mesh resident on the GPU together with its pattern, matrices, right-hand sides and
+    solution (``ptfem_mesh``)."""
+
+    def __init__(self, ctx: Context, nodes, tets, region, tris, bcid):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        nodes, tets, region = _f64(nodes), _i32(tets), _i32(region)
+        tris, bcid = _i32(tris), _i32(bcid)
+        self.nn, self.nt, self.nb = nodes.shape[0], tets.shape[0], tris.shape[0]
+        h = C.c_void_p()
+        self._h = None
+        self._ck(self.lib.ptfem_mesh_create(ctx._h, self.nn, _ptr(nodes), self.nt, _ptr(tets), _ptr(region),
+                                            self.nb, _ptr(tris), _ptr(bcid), C.byref(h)))
+        self._h = h
+        self.nnz = None
+        self.nsys = 1
+        self.last_stats = None
+
+    _ck = Context._ck
+
+    def close(self):
+        if self._h is not None and self.ctx._h is not None:
+            self.lib.ptfem_mesh_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- K1 -------------------------------------------------------------------
+    def pattern(self):
+        n = C.c_int64()
+        self._ck(self.lib.ptfem_pattern(self._h, C.byref(n)))
+        self.nnz = n.value
+        return self.nnz
+
+    def get_pattern(self):
+        nnz = self.pattern()
+        rowptr = np.empty(self.nn + 1, dtype=np.int32)
+        col = np.empty(nnz, dtype=np.int32)
+        self._ck(self.lib.ptfem_pattern_get(self._h, _ptr(rowptr), _ptr(col)))
+        return rowptr, col
+
+    def get_e2nnz(self):
+        self.pattern()
+        out = np.empty((self.nt, 16), dtype=np.int32)
+        self._ck(self.lib.ptfem_e2nnz_get(self._h, _ptr(out)))
+        return out
+
+    def set_coords(self, nodes):
+        nodes = _f64(nodes)
+        assert nodes.shape == (self.nn, 3)
+        self._ck(self.lib.ptfem_mesh_set_coords(self._h, _ptr(nodes)))
+
+    # -- K2/K3 -----------------------------------------------------------------
+    def assemble(self, sigma_by_body):
+        """``sigma_by_body``: dict body id -> conductivity, or a list of such dicts (batched
+        matrices on one pattern; all dicts must have the same keys)."""
+        batch = sigma_by_body if isinstance(sigma_by_body, (list, tuple)) else [sigma_by_body]
+        ids = sorted(batch[0].keys())
+        for d in batch:
+            if sorted(d.keys()) != ids:
+                raise ValueError("all conductivity sets of a batch must name the same bodies")
+        reg = _i32(ids)
+        sig = _f64([[d[i] for i in ids] for d in batch])
+        self._ck(self.lib.ptfem_assemble(self._h, len(ids), _ptr(reg), _ptr(sig), len(batch)))
+        self.nmat = len(batch)
+        return self
+
+    def get_values(self, sys=0, with_bc=False):
+        if self.nnz is None:
+            self.pattern()
+        out = np.empty(self.nnz, dtype=np.float64)
+        self._ck(self.lib.ptfem_values_get(self._h, sys, 1 if with_bc else 0, _ptr(out)))
+        return out
+
+    # -- K4 ----------------------------------------------------------------------
+    def bc_reset(self, nrhs=1):
+        self._ck(self.lib.ptfem_bc_reset(self._h, nrhs))
+        self.nrhs = nrhs
+        return self
+
+    def dirichlet(self, bcid, value, rhs=-1):
+        self._ck(self.lib.ptfem_bc_dirichlet(self._h, rhs, int(bcid), float(value)))
+        return self
+
+    def neumann(self, bcid, g, rhs=-1):
+        self._ck(self.lib.ptfem_bc_neumann(self._h, rhs, int(bcid), float(g)))
+        return self
+
+    def neumann_tris(self, tri_idx, g, rhs=-1):
+        idx = _i32(tri_idx)
+        self._ck(self.lib.ptfem_bc_neumann_tris(self._h, rhs, idx.shape[0], _ptr(idx), float(g)))
+        return self
+
+    def get_rhs(self, rhs=0):
+        out = np.empty(self.nn, dtype=np.float64)
+        self._ck(self.lib.ptfem_rhs_get(self._h, rhs, _ptr(out)))
+        return out
+
+    # -- solve -------------------------------------------------------------------
+    def _opts(self, **kw):
+        o = SolveOpts()
+        self.lib.ptfem_solve_opts_default(C.byref(o))
+        names = {k for k, _ in SolveOpts._fields_}
+        for k, v in kw.items():
+            if k not in names:
+                raise TypeError(f"unknown solver option {k!r}")
+            setattr(o, k, v)
+        return o
+
+    def solve(self, to_host=True, raise_on_noconv=True, **opts):
+        """PCG solve of every assembled system.  Returns phi [nsys, nn] (host) when
+        ``to_host`` else ``None`` (solution stays on the device for post-processing)."""
+        o = self._opts(**opts)
+        st = SolveStats()
+        nsys = max(getattr(self, "nmat", 1), getattr(self, "nrhs", 1))
+        self.nsys = nsys
+        if to_host:
+            phi = np.empty((nsys, self.nn), dtype=np.float64)
+            rc = self.lib.ptfem_solve(self._h, C.byref(o), _ptr(phi), C.byref(st))
+        else:
+            phi = None
+            rc = self.lib.ptfem_solve_device(self._h, C.byref(o), C.byref(st))
+        self.last_stats = st.as_dict()
+        if rc == ERR_NOCONV and not raise_on_noconv:
+            return phi
+        self._ck(rc)
+        return phi
+
+    def get_phi(self, sys=0):
+        out = np.empty(self.nn, dtype=np.float64)
+        self._ck(self.lib.ptfem_phi_get(self._h, sys, _ptr(out)))
+        return out
+
+    def set_phi(self, phi, sys=0):
+        phi = _f64(phi)
+        self._ck(self.lib.ptfem_phi_set(self._h, sys, _ptr(phi)))
+
+    def spmv(self, x, sys=0, with_bc=False, variant=SPMV_AUTO):
+        x = _f64(x)
+        y = np.empty(self.nn, dtype=np.float64)
+        self._ck(self.lib.ptfem_spmv(self._h, sys, 1 if with_bc else 0, variant, _ptr(x), _ptr(y)))
+        return y
+
+    def spmv_bench(self, variant=SPMV_AUTO, iters=20):
+        ms = C.c_double()
+        self._ck(self.lib.ptfem_spmv_bench(self._h, variant, iters, C.byref(ms)))
+        return ms.value
+
+    # -- K10/K11 ---------------------------------------------------------------------
+    def element_fields(self, sys=0):
+        E = np.empty((self.nt, 3), dtype=np.float64)
+        J = np.empty((self.nt, 3), dtype=np.float64)
+        self._ck(self.lib.ptfem_element_fields(self._h, sys, _ptr(E), _ptr(J)))
+        return E, J
+
+    def recover_current(self, sys=0, method="l2", to_host=True):
+        J = np.empty((self.nn, 3), dtype=np.float64) if to_host else None
+        self._ck(self.lib.ptfem_recover_current(self._h, sys, _RECOVER[method], _ptr(J)))
+        return J
+
+    # -- K12 -------------------------------------------------------------------------
+    @staticmethod
+    def _fps(fps):
+        arr = (Footprint * max(1, len(fps)))()
+        for k, (cx, cy, r, square) in enumerate(fps):
+            arr[k] = Footprint(cx, cy, r, 1 if square else 0, 0)
+        return arr
+
+    def metric_nodes(self, field, zmin, zmax=float("nan"), mode=0, footprints=(), scale_r=1.0, sys=0):
+        """{count, sum, max, min} of field (0 |J|, 1 phi, 2 |J_z|, 3 J_z) over nodes with
+        zmin < z (< zmax) and inside (mode 1) / outside all (mode 2) footprints."""
+        out = (C.c_double * 4)()
+        fps = self._fps(footprints)
+        self._ck(self.lib.ptfem_metric_nodes(self._h, sys, field, zmin, zmax, mode, C.cast(fps, C.c_void_p),
+                                             len(footprints), scale_r, out))
+        return dict(count=int(out[0]), sum=out[1], max=out[2], min=out[3])
+
+    def metric_pad_current(self, zmin, footprint, scale_r=1.2, sys=0):
+        out = (C.c_double * 3)()
+        fp = self._fps([footprint])
+        self._ck(self.lib.ptfem_metric_pad_current(self._h, sys, zmin, fp, scale_r, out))
+        return dict(I_signed=out[0], area=out[1], count=int(out[2]))
+
+    def metric_roi(self, cen, r0, mults=(1.0, 1.5, 2.0, 3.0), z0=0.0, z1=0.0, include_tris=True, sys=0):
+        n = len(mults)
+        out = (C.c_double * (6 * n))()
+        cen_a = (C.c_double * 3)(*cen)
+        mul_a = (C.c_double * n)(*mults)
+        self._ck(self.lib.ptfem_metric_roi(self._h, sys, cen_a, r0, mul_a, n, z0, z1, 1 if include_tris else 0, out))
+        return [dict(n=int(out[6 * k]), sum_J=out[6 * k + 1], sum_E=out[6 * k + 2], n_above=int(out[6 * k + 3]),
+                     n_mid=int(out[6 * k + 4]), n_below=int(out[6 * k + 5])) for k in range(n)]
+
+    def metric_column_fit(self, cx, cy, rad, sys=0):
+        out = (C.c_double * 6)()
+        self._ck(self.lib.ptfem_metric_column_fit(self._h, sys, cx, cy, rad, out))
+        return list(out)
+
+    def metric_jstats(self, sys=0):
+        out = (C.c_double * 3)()
+        self._ck(self.lib.ptfem_metric_jstats(self._h, sys, out))
+        return list(out)
+
+    def metric_reaction(self, bcid, sys=0):
+        out = C.c_double()
+        self._ck(self.lib.ptfem_metric_reaction(self._h, sys, int(bcid), C.byref(out)))
+        return out.value
+
+    # -- K13 ---------------------------------------------------------------------------
+    def sample_polyline(self, pts, sys=0):
+        pts = _f64(pts)
+        n = pts.shape[0]
+        phi = np.empty(n, dtype=np.float64)
+        af = np.empty(n, dtype=np.float64)
+        self._ck(self.lib.ptfem_sample_polyline(self._h, sys, n, _ptr(pts), _ptr(phi), _ptr(af)))
+        return phi, af
+
+
+def solve_case(ctx: Context, mesh, sigma_by_body, dirichlet, neumann, recover="l2", **opts):
+    """One full solve step on the GPU with the call shape of ``oracle.fem_oracle.solve_case``
+    (used by the drivers and by the parity tests).  Returns dict(phi, J, stats, dmesh)."""
+    dm = ctx.mesh(mesh.nodes, mesh.tets, mesh.region, mesh.tris, mesh.bcid)
+    dm.assemble(sigma_by_body)
+    dm.bc_reset(1)
+    if not dirichlet:
+        raise ValueError("pure Neumann problem (no Potential BC) is singular")
+    for bid, g in neumann:
+        dm.neumann(bid, g)
+    for bid, v in dirichlet:
+        dm.dirichlet(bid, v)
+    phi = dm.solve(**opts)[0]
+    J = dm.recover_current(0, recover) if recover else None
+    return dict(phi=phi, J=J, stats=dm.last_stats, dmesh=dm)
