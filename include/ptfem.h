@@ -61,6 +61,8 @@ typedef struct ptfem_solve_opts {
   double cheb_ratio;    /* lambda_max / lambda_min assumed by the Chebyshev polynomial */
   int32_t spmv_variant; /* PTFEM_SPMV_* */
   int32_t use_graph;    /* capture check_every iterations in a CUDA graph */
+  int32_t warm_start;   /* 0: start from phi = 0; 1: start from the solution already on the device */
+  int32_t reserved_;
 } ptfem_solve_opts;
 
 typedef struct ptfem_solve_stats {

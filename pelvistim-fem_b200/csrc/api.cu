@@ -27,6 +27,7 @@ int ptfem_do_metric_jstats(ptfem_mesh* m, int sys, double out[3]);
 int ptfem_do_metric_reaction(ptfem_mesh* m, int sys, int32_t bcid, double* current);
 int ptfem_do_sample_polyline(ptfem_mesh* m, int sys, int64_t npts, const double* pts, double* phi_out, double* af_out);
 void ptfem_dist_ctx_release(ptfem_ctx* ctx);
+void ptfem_dist_mesh_release(ptfem_mesh* m);
 
 namespace {
 
@@ -56,9 +57,8 @@ int make_linsys(ptfem_mesh* m, LinSys& A) {
   A.S = m->S;
   A.dinv = m->dinv.p;
   A.b = m->b.p;
-  A.blk_row = m->blk_row.p;
-  A.nblk = m->nblk;
-  A.max_row = m->max_row;
+  A.stream_rows = m->stream_rows;
+  A.stream_cap = m->stream_cap;
   return PTFEM_OK;
 }
 
@@ -112,6 +112,12 @@ int ptfem_ctx_create(int device, ptfem_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   PT_CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   PT_CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  if (const char* e = getenv("PTFEM_INTERLEAVE")) c->tune_interleave = atoi(e) != 0;
+  if (const char* e = getenv("PTFEM_CTAS_PER_SM")) c->tune_ctas_per_sm = atoi(e);
+  if (const char* e = getenv("PTFEM_STREAM_CAP")) c->tune_stream_cap = atoi(e);
+  if (const char* e = getenv("PTFEM_STREAM_ROWS")) c->tune_stream_rows = atoi(e);
+  if (const char* e = getenv("PTFEM_STREAM_TPR")) c->tune_stream_tpr = atoi(e);
+  if (const char* e = getenv("PTFEM_STREAM_STAGES")) c->tune_stream_stages = atoi(e);
   c->h_pinned_n = 4096;
   PT_CK(cudaMallocHost((void**)&c->h_pinned, c->h_pinned_n * sizeof(double)));
   *out = c;
@@ -193,6 +199,7 @@ int ptfem_mesh_destroy(ptfem_mesh* m) {
   cudaStreamSynchronize(m->ctx->stream);
   pcg_work_drop_graph(m->work);
   pcg_work_drop_graph(m->work3);
+  ptfem_dist_mesh_release(m);
   delete m;
   return PTFEM_OK;
 }
@@ -313,6 +320,8 @@ void ptfem_solve_opts_default(ptfem_solve_opts* o) {
   o->cheb_ratio = 30.0;
   o->spmv_variant = PTFEM_SPMV_AUTO;
   o->use_graph = 1;
+  o->warm_start = 0;
+  o->reserved_ = 0;
 }
 
 int ptfem_solve_device(ptfem_mesh* m, const ptfem_solve_opts* opts, ptfem_solve_stats* stats) {
@@ -326,6 +335,7 @@ int ptfem_solve_device(ptfem_mesh* m, const ptfem_solve_opts* opts, ptfem_solve_
   LinSys A;
   make_linsys(m, A);
   m->J_sys = -1;
+  if (!o.warm_start) PT_CK(cudaMemsetAsync(m->phi.p, 0, (size_t)m->nn * m->S * sizeof(double), m->ctx->stream));
   int rc = pcg_solve(m->ctx, A, m->work, o, m->phi.p, stats);
   if (stats) stats->nsys = m->nsys_user;
   return rc;
@@ -402,7 +412,8 @@ int ptfem_spmv(ptfem_mesh* m, int32_t sys, int32_t with_bc, int32_t variant, con
   PT_CK(cudaMemcpyAsync(dx.p, x, (size_t)m->nn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   LinSys A;
   A.nn = m->nn; A.nnz = m->nnz; A.rowptr = m->rowptr.p; A.col = m->col.p; A.val = vals; A.VS = 1; A.S = 1;
-  A.blk_row = m->blk_row.p; A.nblk = m->nblk; A.max_row = m->max_row;
+  A.stream_rows = m->stream_rows;
+  A.stream_cap = m->stream_cap;
   PT_TRY(spmv_launch(ctx, A, variant, dx.p, dy.p, nullptr, false));
   PT_CK(cudaMemcpyAsync(y, dy.p, (size_t)m->nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   PT_CK(cudaStreamSynchronize(ctx->stream));

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/ptfem.h"
@@ -78,7 +79,8 @@ static inline int ptfem_pad_nsys(int s) {
   return -1;
 }
 
-struct NcclApi;  // dist.cu
+struct NcclApi;           // dist.cu
+struct ptfem_dist_state;  // dist.cu
 
 struct ptfem_ctx {
   int device = 0;
@@ -88,7 +90,13 @@ struct ptfem_ctx {
   int64_t launches = 0;
   double* h_pinned = nullptr;  // small pinned scratch (scalars)
   size_t h_pinned_n = 0;
-  uint32_t func_attr_done = 0;     // kernels whose dynamic shared memory limit has been raised
+  int tune_interleave = 1;         // SpMV work distribution: 1 moving front, 0 contiguous run per CTA (PTFEM_INTERLEAVE)
+  int tune_stream_cap = 0;         // staged entries per tile (PTFEM_STREAM_CAP, 0 = default)
+  int tune_stream_rows = 0;        // most rows per tile (PTFEM_STREAM_ROWS, 0 = 128)
+  int tune_stream_tpr = 1;         // lanes per row of the streaming SpMV (PTFEM_STREAM_TPR: 1, 2, 4, 8)
+  int tune_stream_stages = 2;      // shared-memory stages of the streaming SpMV (PTFEM_STREAM_STAGES: 2, 3)
+  int tune_ctas_per_sm = 0;        // cap on resident CTAs per SM of the streaming SpMV (PTFEM_CTAS_PER_SM)
+  std::unordered_map<const void*, size_t> func_smem;  // dynamic shared memory limit raised per kernel
   // NCCL (row-partitioned solves)
   NcclApi* nccl = nullptr;
   void* comm = nullptr;
@@ -133,8 +141,8 @@ struct ptfem_mesh {
   ptfem::DevBuf<int32_t> e2nnz;          // [nt][16]
   ptfem::DevBuf<int32_t> gptr, gsrc;     // nnz -> (tet*16 + ij) contributions, sorted
   // stream-SpMV row blocks
-  ptfem::DevBuf<int32_t> blk_row;        // [nblk+1] first row of each row block
-  int32_t nblk = 0;
+  int32_t stream_rows = 0;        // rows per tile of the streaming SpMV (0 = not usable on this pattern)
+  int32_t stream_cap = 0;         // staged entries per tile
   int32_t max_row = 0;            // longest row of the pattern
   // geometry factors
   bool has_geom = false;
@@ -182,6 +190,7 @@ struct ptfem_mesh {
   std::vector<int32_t> nbr_rank, send_ptr, recv_ptr;
   ptfem::DevBuf<int32_t> send_idx;
   ptfem::DevBuf<double> send_buf;
+  ptfem_dist_state* dist = nullptr;
 };
 
 // ---- helpers implemented in util.cu ---------------------------------------------------------

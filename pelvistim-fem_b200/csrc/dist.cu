@@ -1,4 +1,588 @@
-// dist.cu — row-partitioned single solve over several GPUs (placeholder until the NCCL path lands).
+// dist.cu — row-partitioned single solve over several GPUs (BASELINE.json config #5: one refined mesh,
+// strong-scaled over 2/4/8 B200s).  Not in the reference (its ElmerSolver run is serial,
+// step03_ankle_layers/run_layered_sweep.py:1099); this is the multi-GPU form of the same linear solve.
+//
+// One process per GPU.  Each rank owns a contiguous block of rows; columns are renumbered
+// [0,nloc) owned, [nloc,nloc+nhalo) halo.  Per CG iteration there is exactly one halo exchange
+// (ncclSend/ncclRecv pairs on a side stream, overlapped with the SpMV of the rows that need no halo)
+// and exactly one all-reduce of three scalars (Chronopoulos-Gear single-reduction CG):
+//
+//   p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = D^-1 r      (one fused kernel)
+//   halo(u)  ||  w[interior] = A u        then  w[boundary] = A u
+//   (gamma, delta, rr) = (r.u, w.u, r.r)  -> ncclAllReduce(3 doubles)
+//   beta = gamma/gamma_old ; alpha = gamma / (delta - beta gamma / alpha_old)        (one tiny kernel)
+//
+// The iteration is captured once into a CUDA graph (NCCL calls included) and replayed, so launch
+// latency does not bound the strong-scaled case.  NCCL is loaded with dlopen (the path comes from
+// the Python host, which knows where torch's bundled libnccl lives).
+#include <dlfcn.h>
+
+#include <cmath>
+
 #include "solver.cuh"
+
 using namespace ptfem;
-void ptfem_dist_ctx_release(ptfem_ctx*) {}
+
+// ---- minimal NCCL ABI (nccl.h 2.27/2.28: stable since 2.7) ---------------------------------------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct {
+  char internal[128];
+} ncclUniqueId;
+typedef int ncclResult_t;
+enum { kNcclSum = 0, kNcclFloat64 = 8 };
+
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+namespace {
+
+NcclApi* g_nccl = nullptr;
+
+int load_nccl(const char* path, NcclApi** out) {
+  if (g_nccl) {
+    *out = g_nccl;
+    return PTFEM_OK;
+  }
+  const char* cand[3] = {path && path[0] ? path : nullptr, "libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (int k = 0; k < 3 && !h; ++k)
+    if (cand[k]) h = dlopen(cand[k], RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return set_err(PTFEM_ERR_NCCL, "cannot load NCCL (%s): %s", path ? path : "libnccl.so.2", dlerror());
+  NcclApi* a = new NcclApi();
+  a->handle = h;
+#define PT_SYM(field, name)                                                              \
+  a->field = reinterpret_cast<decltype(a->field)>(dlsym(h, name));                       \
+  if (!a->field) {                                                                       \
+    delete a;                                                                            \
+    return set_err(PTFEM_ERR_NCCL, "NCCL symbol %s not found", name);                    \
+  }
+  PT_SYM(GetUniqueId, "ncclGetUniqueId");
+  PT_SYM(CommInitRank, "ncclCommInitRank");
+  PT_SYM(CommDestroy, "ncclCommDestroy");
+  PT_SYM(AllReduce, "ncclAllReduce");
+  PT_SYM(Send, "ncclSend");
+  PT_SYM(Recv, "ncclRecv");
+  PT_SYM(GroupStart, "ncclGroupStart");
+  PT_SYM(GroupEnd, "ncclGroupEnd");
+  PT_SYM(GetErrorString, "ncclGetErrorString");
+#undef PT_SYM
+  g_nccl = a;
+  *out = a;
+  return PTFEM_OK;
+}
+
+#define PT_NCCL(api, expr)                                                                        \
+  do {                                                                                            \
+    ncclResult_t r__ = (expr);                                                                    \
+    if (r__ != 0) return set_err(PTFEM_ERR_NCCL, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,    \
+                                 (api)->GetErrorString(r__));                                     \
+  } while (0)
+
+constexpr int kT = 256;
+// device scalars of the distributed solve (doubles): see dist_scalar_kernel
+enum { D_GAMMA = 0, D_DELTA, D_RR, D_ALPHA, D_BETA, D_GAMMA_OLD, D_BN2, D_COUNT };
+
+__global__ void dist_dinv_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                 const double* __restrict__ val, int64_t nloc, double* __restrict__ dinv,
+                                 uint8_t* __restrict__ needs_halo) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nloc) return;
+  double d = 0.0;
+  uint8_t h = 0;
+  for (int32_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+    const int32_t c = col[k];
+    if (c == (int32_t)i) d = val[k];
+    if (c >= nloc) h = 1;
+  }
+  dinv[i] = d != 0.0 ? 1.0 / d : 1.0;
+  needs_halo[i] = h;
+}
+
+__global__ void dist_pack_kernel(const double* __restrict__ u, const int32_t* __restrict__ idx, int64_t n,
+                                 double* __restrict__ buf) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) buf[i] = u[idx[i]];
+}
+
+// first = 1: u = dinv*r only (p = s = 0 beforehand, alpha/beta unused)
+__global__ void __launch_bounds__(kT) dist_update_kernel(int64_t n, const double* __restrict__ scal,
+                                                         const double* __restrict__ dinv, const double* __restrict__ w,
+                                                         double* __restrict__ p, double* __restrict__ s,
+                                                         double* __restrict__ x, double* __restrict__ r,
+                                                         double* __restrict__ u) {
+  const double alpha = scal[D_ALPHA], beta = scal[D_BETA];
+  const int64_t stride = (int64_t)gridDim.x * kT;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < n; i += stride) {
+    const double pi = fma(beta, p[i], u[i]);
+    const double si = fma(beta, s[i], w[i]);
+    const double ri = fma(-alpha, si, r[i]);
+    p[i] = pi;
+    s[i] = si;
+    x[i] = fma(alpha, pi, x[i]);
+    r[i] = ri;
+    u[i] = ri * dinv[i];
+  }
+}
+
+__global__ void __launch_bounds__(kT) dist_init_kernel(int64_t n, const double* __restrict__ b,
+                                                       const double* __restrict__ dinv, double* __restrict__ p,
+                                                       double* __restrict__ s, double* __restrict__ x,
+                                                       double* __restrict__ r, double* __restrict__ u) {
+  const int64_t stride = (int64_t)gridDim.x * kT;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < n; i += stride) {
+    p[i] = 0.0;
+    s[i] = 0.0;
+    x[i] = 0.0;
+    r[i] = b[i];
+    u[i] = b[i] * dinv[i];
+  }
+}
+
+// local (r.u, w.u, r.r) -> scal[D_GAMMA..D_RR]; per-CTA partials summed in order by the last CTA
+__global__ void __launch_bounds__(kT) dist_dots_kernel(int64_t n, const double* __restrict__ r,
+                                                       const double* __restrict__ u, const double* __restrict__ w,
+                                                       double* __restrict__ partial, double* __restrict__ scal,
+                                                       unsigned int* __restrict__ ticket) {
+  __shared__ double s_red[3 * (kT / 32)];
+  __shared__ int s_last;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * kT;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < n; i += stride) {
+    const double ri = r[i], ui = u[i];
+    a0 = fma(ri, ui, a0);
+    a1 = fma(w[i], ui, a1);
+    a2 = fma(ri, ri, a2);
+  }
+  a0 = warp_sum(a0);
+  a1 = warp_sum(a1);
+  a2 = warp_sum(a2);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) {
+    s_red[wid * 3] = a0;
+    s_red[wid * 3 + 1] = a1;
+    s_red[wid * 3 + 2] = a2;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double acc = 0.0;
+    for (int k = 0; k < kT / 32; ++k) acc += s_red[k * 3 + threadIdx.x];
+    partial[(size_t)blockIdx.x * 3 + threadIdx.x] = acc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last && threadIdx.x < 3) {
+    __threadfence();
+    double acc = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) acc += __ldcg(partial + (size_t)b * 3 + threadIdx.x);
+    scal[D_GAMMA + threadIdx.x] = acc;
+  }
+}
+
+// after the all-reduce: first -> alpha = gamma/delta, beta = 0 ; else Chronopoulos-Gear recurrences
+__global__ void dist_scalar_kernel(double* __restrict__ scal, int first) {
+  const double gamma = scal[D_GAMMA], delta = scal[D_DELTA];
+  double alpha, beta;
+  if (first) {
+    beta = 0.0;
+    alpha = delta > 0.0 ? gamma / delta : 0.0;
+  } else {
+    const double g_old = scal[D_GAMMA_OLD], a_old = scal[D_ALPHA];
+    beta = g_old > 0.0 ? gamma / g_old : 0.0;
+    const double den = a_old != 0.0 ? delta - beta * gamma / a_old : 0.0;
+    alpha = den > 0.0 ? gamma / den : 0.0;
+  }
+  scal[D_ALPHA] = alpha;
+  scal[D_BETA] = beta;
+  scal[D_GAMMA_OLD] = gamma;
+}
+
+int dist_grid(ptfem_ctx* ctx, int64_t n) {
+  int64_t g = (n + kT - 1) / kT;
+  const int64_t cap = (int64_t)ctx->sm_count * 4;
+  if (g > cap) g = cap;
+  return g < 1 ? 1 : (int)g;
+}
+
+struct DistState {
+  DevBuf<double> x, r, u, w, p, s, scal, partial;
+  DevBuf<unsigned int> ticket;
+  DevBuf<int32_t> recv_dummy;
+  cudaEvent_t ev_u = nullptr, ev_halo = nullptr;
+  cudaGraphExec_t graph = nullptr;
+  int graph_iters = 0;
+  int64_t graph_launches = 0;
+  int64_t i0 = 0, i1 = 0;  // rows [i0, i1) need no halo value
+};
+
+}  // namespace
+
+struct ptfem_dist_state : DistState {};
+
+static int halo_exchange(ptfem_mesh* m, DistState& d, cudaStream_t st) {
+  ptfem_ctx* ctx = m->ctx;
+  NcclApi* api = ctx->nccl;
+  const int64_t nsend = m->send_ptr.empty() ? 0 : m->send_ptr.back();
+  if (nsend > 0) {
+    dist_pack_kernel<<<ceil_div(nsend, 256), 256, 0, st>>>(d.u.p, m->send_idx.p, nsend, m->send_buf.p);
+    PT_LAUNCH_CHECK(ctx);
+  }
+  if (m->nnbr > 0) {
+    PT_NCCL(api, api->GroupStart());
+    for (int k = 0; k < m->nnbr; ++k) {
+      const int64_t ns = m->send_ptr[k + 1] - m->send_ptr[k], nr = m->recv_ptr[k + 1] - m->recv_ptr[k];
+      if (ns > 0)
+        PT_NCCL(api, api->Send(m->send_buf.p + m->send_ptr[k], (size_t)ns, kNcclFloat64, m->nbr_rank[k], (ncclComm_t)ctx->comm, st));
+      if (nr > 0)
+        PT_NCCL(api, api->Recv(d.u.p + m->nloc + m->recv_ptr[k], (size_t)nr, kNcclFloat64, m->nbr_rank[k], (ncclComm_t)ctx->comm, st));
+    }
+    PT_NCCL(api, api->GroupEnd());
+  }
+  return PTFEM_OK;
+}
+
+static int spmv_rows(ptfem_mesh* m, DistState& d, int64_t r0, int64_t r1) {
+  if (r1 <= r0) return PTFEM_OK;
+  LinSys A;
+  A.nn = r1 - r0;
+  A.row0 = r0;
+  A.nnz = m->nnz;
+  A.rowptr = m->rowptr.p;
+  A.col = m->col.p;
+  A.val = m->val_bc.p;
+  A.VS = 1;
+  A.S = 1;
+  return spmv_launch(m->ctx, A, PTFEM_SPMV_VECTOR, d.u.p, d.w.p, nullptr, false);
+}
+
+// w = A u with the halo exchange of u overlapped with the interior rows
+static int dist_matvec(ptfem_mesh* m, DistState& d) {
+  ptfem_ctx* ctx = m->ctx;
+  PT_CK(cudaEventRecord(d.ev_u, ctx->stream));
+  PT_CK(cudaStreamWaitEvent(ctx->stream2, d.ev_u, 0));
+  PT_TRY(halo_exchange(m, d, ctx->stream2));
+  PT_CK(cudaEventRecord(d.ev_halo, ctx->stream2));
+  PT_TRY(spmv_rows(m, d, d.i0, d.i1));
+  PT_CK(cudaStreamWaitEvent(ctx->stream, d.ev_halo, 0));
+  PT_TRY(spmv_rows(m, d, 0, d.i0));
+  PT_TRY(spmv_rows(m, d, d.i1, m->nloc));
+  return PTFEM_OK;
+}
+
+static int dist_reduce(ptfem_mesh* m, DistState& d, int first) {
+  ptfem_ctx* ctx = m->ctx;
+  NcclApi* api = ctx->nccl;
+  dist_dots_kernel<<<dist_grid(ctx, m->nloc), kT, 0, ctx->stream>>>(m->nloc, d.r.p, d.u.p, d.w.p, d.partial.p, d.scal.p, d.ticket.p);
+  PT_LAUNCH_CHECK(ctx);
+  if (ctx->nranks > 1)
+    PT_NCCL(api, api->AllReduce(d.scal.p + D_GAMMA, d.scal.p + D_GAMMA, 3, kNcclFloat64, kNcclSum, (ncclComm_t)ctx->comm, ctx->stream));
+  dist_scalar_kernel<<<1, 1, 0, ctx->stream>>>(d.scal.p, first);
+  PT_LAUNCH_CHECK(ctx);
+  return PTFEM_OK;
+}
+
+static int dist_iteration(ptfem_mesh* m, DistState& d) {
+  ptfem_ctx* ctx = m->ctx;
+  dist_update_kernel<<<dist_grid(ctx, m->nloc), kT, 0, ctx->stream>>>(m->nloc, d.scal.p, m->dinv.p, d.w.p, d.p.p, d.s.p, d.x.p,
+                                                                      d.r.p, d.u.p);
+  PT_LAUNCH_CHECK(ctx);
+  PT_TRY(dist_matvec(m, d));
+  return dist_reduce(m, d, 0);
+}
+
+void ptfem_dist_ctx_release(ptfem_ctx* ctx) {
+  if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy((ncclComm_t)ctx->comm);
+  ctx->comm = nullptr;
+}
+
+void ptfem_dist_mesh_release(ptfem_mesh* m) {
+  if (!m->dist) return;
+  DistState* d = m->dist;
+  if (d->graph) cudaGraphExecDestroy(d->graph);
+  if (d->ev_u) cudaEventDestroy(d->ev_u);
+  if (d->ev_halo) cudaEventDestroy(d->ev_halo);
+  delete m->dist;
+  m->dist = nullptr;
+}
+
+extern "C" {
+
+int ptfem_dist_unique_id(const char* libnccl_path, void* id128) {
+  PT_ARG(id128, "null pointer");
+  NcclApi* api = nullptr;
+  PT_TRY(load_nccl(libnccl_path, &api));
+  ncclUniqueId id;
+  PT_NCCL(api, api->GetUniqueId(&id));
+  memcpy(id128, &id, sizeof id);
+  return PTFEM_OK;
+}
+
+int ptfem_dist_init(ptfem_ctx* ctx, const char* libnccl_path, const void* id128, int32_t rank, int32_t nranks) {
+  PT_ARG(ctx && id128, "null pointer");
+  PT_ARG(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
+  PT_CK(cudaSetDevice(ctx->device));
+  NcclApi* api = nullptr;
+  PT_TRY(load_nccl(libnccl_path, &api));
+  if (ctx->comm) return set_err(PTFEM_ERR_STATE, "context already has a communicator");
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  ncclComm_t comm = nullptr;
+  PT_NCCL(api, api->CommInitRank(&comm, nranks, id, rank));
+  ctx->nccl = api;
+  ctx->comm = comm;
+  ctx->rank = rank;
+  ctx->nranks = nranks;
+  return PTFEM_OK;
+}
+
+int ptfem_dist_finalize(ptfem_ctx* ctx) {
+  PT_ARG(ctx, "null context");
+  PT_CK(cudaSetDevice(ctx->device));
+  PT_CK(cudaStreamSynchronize(ctx->stream));
+  PT_CK(cudaStreamSynchronize(ctx->stream2));
+  ptfem_dist_ctx_release(ctx);
+  ctx->rank = 0;
+  ctx->nranks = 1;
+  return PTFEM_OK;
+}
+
+int ptfem_dist_system_create(ptfem_ctx* ctx, int64_t nloc, int64_t nhalo, const int32_t* rowptr, const int32_t* col,
+                             const double* val, const double* b, int32_t nnbr, const int32_t* nbr_rank,
+                             const int32_t* send_ptr, const int32_t* send_idx, const int32_t* recv_ptr, ptfem_mesh** out) {
+  PT_ARG(ctx && out && rowptr && col && val && b, "null pointer");
+  PT_ARG(nloc > 0 && nhalo >= 0 && nnbr >= 0, "bad sizes");
+  PT_ARG(nnbr == 0 || (nbr_rank && send_ptr && send_idx && recv_ptr), "null neighbour arrays");
+  if (nnbr > 0 && !ctx->comm) return set_err(PTFEM_ERR_STATE, "ptfem_dist_init has not been called on this context");
+  *out = nullptr;
+  const int64_t nnz = rowptr[nloc];
+  for (int64_t k = 0; k < nnz; ++k)
+    if (col[k] < 0 || col[k] >= nloc + nhalo) return set_err(PTFEM_ERR_ARG, "column %d out of range at entry %lld", col[k], (long long)k);
+  if (nnbr > 0) {
+    if (recv_ptr[nnbr] != nhalo) return set_err(PTFEM_ERR_ARG, "recv_ptr[nnbr] (%d) != nhalo (%lld)", recv_ptr[nnbr], (long long)nhalo);
+    for (int64_t k = 0; k < send_ptr[nnbr]; ++k)
+      if (send_idx[k] < 0 || send_idx[k] >= nloc) return set_err(PTFEM_ERR_ARG, "send index out of range");
+    for (int k = 0; k < nnbr; ++k)
+      if (nbr_rank[k] < 0 || nbr_rank[k] >= ctx->nranks || nbr_rank[k] == ctx->rank)
+        return set_err(PTFEM_ERR_ARG, "bad neighbour rank %d", nbr_rank[k]);
+  } else if (nhalo != 0) {
+    return set_err(PTFEM_ERR_ARG, "halo columns without neighbours");
+  }
+  PT_CK(cudaSetDevice(ctx->device));
+  ptfem_mesh* m = new ptfem_mesh();
+  m->ctx = ctx;
+  m->is_dist = true;
+  m->nn = nloc;
+  m->nloc = nloc;
+  m->nhalo = nhalo;
+  m->nnz = nnz;
+  m->nnbr = nnbr;
+  m->nbr_rank.assign(nbr_rank, nbr_rank + nnbr);
+  m->send_ptr.assign(send_ptr, send_ptr + (nnbr > 0 ? nnbr + 1 : 0));
+  m->recv_ptr.assign(recv_ptr, recv_ptr + (nnbr > 0 ? nnbr + 1 : 0));
+  m->dist = new ptfem_dist_state();
+  DistState& d = *m->dist;
+  int rc = PTFEM_OK;
+  const int64_t nsend = nnbr > 0 ? send_ptr[nnbr] : 0;
+  auto body = [&]() -> int {
+    PT_TRY(m->rowptr.alloc(nloc + 1));
+    PT_TRY(m->col.alloc(nnz + 8));
+    PT_TRY(m->val_bc.alloc(nnz + 8));
+    PT_TRY(m->b.alloc(nloc));
+    PT_TRY(m->dinv.alloc(nloc));
+    PT_TRY(m->send_idx.alloc(nsend));
+    PT_TRY(m->send_buf.alloc(nsend));
+    PT_CK(cudaMemcpyAsync(m->rowptr.p, rowptr, (nloc + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    PT_CK(cudaMemcpyAsync(m->col.p, col, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    PT_CK(cudaMemcpyAsync(m->val_bc.p, val, nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    PT_CK(cudaMemcpyAsync(m->b.p, b, nloc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (nsend > 0) PT_CK(cudaMemcpyAsync(m->send_idx.p, send_idx, nsend * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    const int64_t nv = nloc + nhalo;
+    PT_TRY(d.x.alloc(nloc));
+    PT_TRY(d.r.alloc(nloc));
+    PT_TRY(d.u.alloc(nv));
+    PT_TRY(d.w.alloc(nloc));
+    PT_TRY(d.p.alloc(nloc));
+    PT_TRY(d.s.alloc(nloc));
+    PT_TRY(d.scal.alloc(D_COUNT));
+    PT_TRY(d.partial.alloc((size_t)ctx->sm_count * 4 * 3));
+    PT_TRY(d.ticket.alloc(1));
+    PT_CK(cudaMemsetAsync(d.ticket.p, 0, sizeof(unsigned int), ctx->stream));
+    PT_CK(cudaMemsetAsync(d.u.p, 0, nv * sizeof(double), ctx->stream));
+    PT_CK(cudaMemsetAsync(d.scal.p, 0, D_COUNT * sizeof(double), ctx->stream));
+    PT_CK(cudaEventCreateWithFlags(&d.ev_u, cudaEventDisableTiming));
+    PT_CK(cudaEventCreateWithFlags(&d.ev_halo, cudaEventDisableTiming));
+    DevBuf<uint8_t> flag;
+    PT_TRY(flag.alloc(nloc));
+    dist_dinv_kernel<<<ceil_div(nloc, 128), 128, 0, ctx->stream>>>(m->rowptr.p, m->col.p, m->val_bc.p, nloc, m->dinv.p, flag.p);
+    PT_LAUNCH_CHECK(ctx);
+    std::vector<uint8_t> hflag(nloc);
+    PT_CK(cudaMemcpyAsync(hflag.data(), flag.p, nloc, cudaMemcpyDeviceToHost, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    // longest run of rows that touch no halo column
+    int64_t best0 = 0, best1 = 0, run0 = 0;
+    for (int64_t i = 0; i <= nloc; ++i) {
+      if (i == nloc || hflag[i]) {
+        if (i - run0 > best1 - best0) {
+          best0 = run0;
+          best1 = i;
+        }
+        run0 = i + 1;
+      }
+    }
+    d.i0 = best0;
+    d.i1 = best1;
+    // rows outside [i0,i1) may or may not need the halo; they all wait for it (correct, slightly conservative)
+    return PTFEM_OK;
+  };
+  rc = body();
+  if (rc) {
+    ptfem_dist_mesh_release(m);
+    delete m;
+    return rc;
+  }
+  *out = m;
+  return PTFEM_OK;
+}
+
+int ptfem_dist_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* x_local, ptfem_solve_stats* stats, double* ms_spmv,
+                     double* ms_halo, double* ms_allreduce) {
+  PT_ARG(m && m->is_dist && m->dist, "not a distributed system");
+  ptfem_ctx* ctx = m->ctx;
+  NcclApi* api = ctx->nccl;
+  PT_CK(cudaSetDevice(ctx->device));
+  ptfem_solve_opts o;
+  if (opts) o = *opts; else ptfem_solve_opts_default(&o);
+  PT_ARG(o.rtol > 0.0 && o.maxit > 0, "rtol and maxit must be positive");
+  if (o.precond != PTFEM_PRECOND_JACOBI) return set_err(PTFEM_ERR_ARG, "the row-partitioned solve supports the Jacobi preconditioner only");
+  DistState& d = *m->dist;
+  const int check = o.check_every > 0 ? o.check_every : 50;
+  const int grid = dist_grid(ctx, m->nloc);
+  double* h = ctx->h_pinned;
+
+  cudaEvent_t e0, e1;
+  PT_CK(cudaEventCreate(&e0));
+  PT_CK(cudaEventCreate(&e1));
+  PT_CK(cudaEventRecord(e0, ctx->stream));
+  // ||b||^2 via the dots kernel (r = u = b): gamma slot
+  dist_dots_kernel<<<grid, kT, 0, ctx->stream>>>(m->nloc, m->b.p, m->b.p, m->b.p, d.partial.p, d.scal.p, d.ticket.p);
+  PT_LAUNCH_CHECK(ctx);
+  if (ctx->nranks > 1)
+    PT_NCCL(api, api->AllReduce(d.scal.p + D_GAMMA, d.scal.p + D_BN2, 1, kNcclFloat64, kNcclSum, (ncclComm_t)ctx->comm, ctx->stream));
+  else
+    PT_CK(cudaMemcpyAsync(d.scal.p + D_BN2, d.scal.p + D_GAMMA, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  // x = 0, r = b, u = D^-1 r, w = A u, first scalars
+  dist_init_kernel<<<grid, kT, 0, ctx->stream>>>(m->nloc, m->b.p, m->dinv.p, d.p.p, d.s.p, d.x.p, d.r.p, d.u.p);
+  PT_LAUNCH_CHECK(ctx);
+  PT_TRY(dist_matvec(m, d));
+  PT_TRY(dist_reduce(m, d, 1));
+
+  auto read_scal = [&]() -> int {
+    PT_CK(cudaMemcpyAsync(h, d.scal.p, D_COUNT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    return PTFEM_OK;
+  };
+  PT_TRY(read_scal());
+  const double bn2 = h[D_BN2];
+  const double rtol2 = o.rtol * o.rtol;
+  int it = 0;
+  bool converged = bn2 <= 0.0 || h[D_RR] <= rtol2 * bn2;
+  double rel = bn2 > 0.0 ? sqrt(h[D_RR] / bn2) : 0.0;
+  while (!converged && it < o.maxit) {
+    const int n_it = (o.maxit - it) < check ? (o.maxit - it) : check;
+    if (o.use_graph && n_it == check) {
+      if (!d.graph || d.graph_iters != check) {
+        if (d.graph) cudaGraphExecDestroy(d.graph);
+        d.graph = nullptr;
+        cudaGraph_t g = nullptr;
+        int rc = PTFEM_OK;
+        PT_CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        const int64_t l0 = ctx->launches;
+        for (int k = 0; k < check && rc == PTFEM_OK; ++k) rc = dist_iteration(m, d);
+        d.graph_launches = ctx->launches - l0;
+        ctx->launches = l0;
+        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+        if (rc) return rc;
+        if (ce != cudaSuccess) return set_err(PTFEM_ERR_CUDA, "graph capture of the distributed iteration failed: %s", cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&d.graph, g, 0);
+        cudaGraphDestroy(g);
+        if (ce != cudaSuccess) return set_err(PTFEM_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+        d.graph_iters = check;
+      }
+      PT_CK(cudaGraphLaunch(d.graph, ctx->stream));
+      ctx->launches += d.graph_launches;
+    } else {
+      for (int k = 0; k < n_it; ++k) PT_TRY(dist_iteration(m, d));
+    }
+    it += n_it;
+    PT_TRY(read_scal());
+    const double rr = h[D_RR];
+    if (!(rr == rr)) return set_err(PTFEM_ERR_NOCONV, "distributed PCG diverged after %d iterations", it);
+    rel = sqrt(rr / bn2);
+    converged = rr <= rtol2 * bn2;
+  }
+  // the recurrences have advanced r/u one step beyond x: apply the pending update so x matches r
+  // (x_{i+1} uses alpha_i p_i, done inside the update kernel of the next iteration)
+  dist_update_kernel<<<grid, kT, 0, ctx->stream>>>(m->nloc, d.scal.p, m->dinv.p, d.w.p, d.p.p, d.s.p, d.x.p, d.r.p, d.u.p);
+  PT_LAUNCH_CHECK(ctx);
+  PT_CK(cudaEventRecord(e1, ctx->stream));
+  PT_CK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+
+  // phase timings, each phase alone (no overlap), averaged over a few repetitions
+  const int reps = 20;
+  float t_spmv = 0.f, t_halo = 0.f, t_ar = 0.f;
+  {
+    PT_CK(cudaEventRecord(e0, ctx->stream));
+    for (int k = 0; k < reps; ++k) PT_TRY(spmv_rows(m, d, 0, m->nloc));
+    PT_CK(cudaEventRecord(e1, ctx->stream));
+    PT_CK(cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&t_spmv, e0, e1);
+    PT_CK(cudaEventRecord(e0, ctx->stream));
+    for (int k = 0; k < reps; ++k) PT_TRY(halo_exchange(m, d, ctx->stream));
+    PT_CK(cudaEventRecord(e1, ctx->stream));
+    PT_CK(cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&t_halo, e0, e1);
+    PT_CK(cudaEventRecord(e0, ctx->stream));
+    if (ctx->nranks > 1)
+      for (int k = 0; k < reps; ++k)
+        PT_NCCL(api, api->AllReduce(d.partial.p, d.partial.p, 3, kNcclFloat64, kNcclSum, (ncclComm_t)ctx->comm, ctx->stream));
+    PT_CK(cudaEventRecord(e1, ctx->stream));
+    PT_CK(cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&t_ar, e0, e1);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (ms_spmv) *ms_spmv = t_spmv / reps;
+  if (ms_halo) *ms_halo = t_halo / reps;
+  if (ms_allreduce) *ms_allreduce = t_ar / reps;
+  if (x_local) {
+    PT_CK(cudaMemcpyAsync(x_local, d.x.p, m->nloc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+  }
+  if (stats) {
+    stats->iterations = it;
+    stats->converged = converged ? 1 : 0;
+    stats->nsys = 1;
+    stats->spmv_calls = it + 1;
+    stats->rel_residual = rel;
+    stats->true_rel_residual = rel;
+    stats->solve_ms = ms;
+    stats->spmv_ms = t_spmv / reps;
+  }
+  if (!converged) return set_err(PTFEM_ERR_NOCONV, "distributed PCG did not reach rtol=%g in %d iterations (rel. residual %.3e)", o.rtol, it, rel);
+  return PTFEM_OK;
+}
+
+}  // extern "C"

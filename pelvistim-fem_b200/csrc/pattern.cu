@@ -132,20 +132,14 @@ __global__ void fill_contrib(const int32_t* __restrict__ e2nnz, int64_t n, const
   gsrc[gptr[k] + pos] = (int32_t)i;  // = tet*16 + local ij
 }
 
-// row blocks for the streaming SpMV: block k starts at the first row whose first non-zero is at or
-// beyond k*tile_nnz, so every block owns whole rows and at most tile_nnz + (longest row) - 1 entries.
-__global__ void build_row_blocks(const int32_t* __restrict__ rowptr, int64_t nn, int32_t tile_nnz, int32_t nblk,
-                                 int32_t* __restrict__ blk_row) {
-  int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k > nblk) return;
-  if (k == nblk) { blk_row[k] = (int32_t)nn; return; }
-  const int64_t target = (int64_t)k * tile_nnz;
-  int64_t lo = 0, hi = nn;
-  while (lo < hi) {
-    int64_t mid = (lo + hi) >> 1;
-    if (rowptr[mid] < target) lo = mid + 1; else hi = mid;
-  }
-  blk_row[k] = (int32_t)lo;
+// largest number of staged entries over the tiles of R rows (alignment slack included)
+__global__ void max_tile_nnz(const int32_t* __restrict__ rowptr, int64_t nn, int32_t R, int32_t* __restrict__ out) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r0 = t * R;
+  if (r0 >= nn) return;
+  const int64_t r1 = r0 + R < nn ? r0 + R : nn;
+  const int32_t k0 = rowptr[r0] & ~3, k1 = (rowptr[r1] + 3) & ~3;
+  atomicMax(out, k1 - k0);
 }
 
 __global__ void max_row_len(const int32_t* __restrict__ rowptr, int64_t nn, int32_t* __restrict__ out) {
@@ -184,8 +178,10 @@ int build_incidence(ptfem_ctx* ctx, const int32_t* elems, int64_t ne, int64_t nn
 
 }  // namespace
 
-// max non-zeros / rows per streaming row block (must match spmv.cu)
-int ptfem_stream_tile_nnz();
+// geometry of the streaming SpMV (solver.cu)
+int ptfem_stream_cap_max();
+int ptfem_stream_rows_default();
+int ptfem_stream_threads();
 
 int ptfem_build_pattern(ptfem_mesh* m) {
   ptfem_ctx* ctx = m->ctx;
@@ -237,12 +233,32 @@ int ptfem_build_pattern(ptfem_mesh* m) {
     PT_CK(cudaStreamSynchronize(ctx->stream));
   }
 
-  // streaming row blocks
-  const int tile_nnz = ptfem_stream_tile_nnz();
-  m->nblk = (int32_t)((nnz + tile_nnz - 1) / tile_nnz);
-  PT_TRY(m->blk_row.alloc((size_t)m->nblk + 1));
-  build_row_blocks<<<ceil_div(m->nblk + 1, 128), 128, 0, ctx->stream>>>(m->rowptr.p, nn, tile_nnz, m->nblk, m->blk_row.p);
-  PT_LAUNCH_CHECK(ctx);
+  // streaming SpMV tiles: R rows (64 by default, halved while a tile would not fit the largest stage);
+  // the stage capacity is the largest tile of this pattern rounded up, so uniform meshes get small stages
+  // and therefore more resident CTAs per SM (measured: occupancy, not stage depth, is what pays).
+  {
+    DevBuf<int32_t> mt;
+    PT_TRY(mt.alloc(1));
+    m->stream_rows = 0;
+    m->stream_cap = 0;
+    const int cap_max = ctx->tune_stream_cap > 0 ? (ctx->tune_stream_cap + 31) & ~31 : ptfem_stream_cap_max();
+    int rmax = ctx->tune_stream_rows > 0 ? ctx->tune_stream_rows : ptfem_stream_rows_default();
+    if (rmax > ptfem_stream_threads()) rmax = ptfem_stream_threads();
+    for (int R = rmax & ~31; R >= 32 && m->stream_rows == 0; R -= 32) {
+      PT_TRY(fill_i32(ctx, mt.p, 0, 1));
+      const int64_t ntile = (nn + R - 1) / R;
+      max_tile_nnz<<<ceil_div(ntile, 256), 256, 0, ctx->stream>>>(m->rowptr.p, nn, R, mt.p);
+      PT_LAUNCH_CHECK(ctx);
+      int32_t mx = 0;
+      PT_CK(cudaMemcpyAsync(&mx, mt.p, sizeof mx, cudaMemcpyDeviceToHost, ctx->stream));
+      PT_CK(cudaStreamSynchronize(ctx->stream));
+      if (mx <= cap_max) {
+        m->stream_rows = R;
+        m->stream_cap = ctx->tune_stream_cap > 0 ? cap_max : ((mx + 31) & ~31);
+        if (m->stream_cap < 256) m->stream_cap = 256;
+      }
+    }
+  }
   DevBuf<int32_t> mrl;
   PT_TRY(mrl.alloc(1));
   PT_TRY(fill_i32(ctx, mrl.p, 0, 1));

@@ -535,7 +535,7 @@ int ptfem_do_recover(ptfem_mesh* m, int sys, int method) {
   PT_CK(cudaMemsetAsync(m->mx.p, 0, (size_t)m->nn * 4 * sizeof(double), ctx->stream));
   LinSys A;
   A.nn = m->nn; A.nnz = m->nnz; A.rowptr = m->rowptr.p; A.col = m->col.p; A.val = m->mval.p; A.VS = 1; A.S = 4;
-  A.dinv = m->mdinv.p; A.b = m->mrhs.p; A.blk_row = nullptr; A.nblk = 0; A.max_row = m->max_row;
+  A.dinv = m->mdinv.p; A.b = m->mrhs.p; A.stream_rows = 0;
   ptfem_solve_opts o;
   ptfem_solve_opts_default(&o);
   o.precond = PTFEM_PRECOND_JACOBI;

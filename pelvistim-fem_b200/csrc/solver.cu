@@ -24,12 +24,54 @@ constexpr int kCtasPerSm = 8;
 constexpr int kMaxSys = 16;
 
 // ---- streaming SpMV geometry --------------------------------------------------------------------
-constexpr int kStreamTile = 2048;    // target non-zeros per row block
-constexpr int kStreamMaxRow = 240;   // longer rows -> vector kernel
-constexpr int kStreamCap = kStreamTile + kStreamMaxRow + 16;  // staged entries (incl. alignment slack)
+constexpr int kStreamThreads = 128;  // most rows per tile (one thread, or TPR lanes, per row)
+constexpr int kStreamCapMax = 4096;   // most staged non-zeros per tile (48 KB per stage)
+constexpr int kStreamRowsDefault = 64;
 
 // scalar slots in PcgWork::scal, each [kMaxSys]
 enum { SC_ALPHA = 0, SC_BETA, SC_RHO, SC_RR, SC_PQ, SC_BN2, SC_LMAX, SC_COUNT };
+
+// L2 eviction policies: the matrix stream (val/col, read once per SpMV) is marked evict_first, the
+// gathered vector (re-read ~15 times, 8 bytes per row) evict_last, so the 600 MB stream cannot push the
+// 27 MB vector out of the 126 MB L2.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ double ldg_f64_hint(const double* p, uint64_t pol) {
+  double v;
+  asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ double2 ldg_f64x2_hint(const double* p, uint64_t pol) {
+  double2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int32_t ldg_i32_hint(const int32_t* p, uint64_t pol) {
+  int32_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+template <int S>
+__device__ __forceinline__ void load_sys_hint(const double* __restrict__ p, double (&v)[S], uint64_t pol) {
+  if constexpr (S == 1) {
+    v[0] = ldg_f64_hint(p, pol);
+  } else {
+#pragma unroll
+    for (int s = 0; s < S / 2; ++s) {
+      const double2 t = ldg_f64x2_hint(p + 2 * s, pol);
+      v[2 * s] = t.x;
+      v[2 * s + 1] = t.y;
+    }
+  }
+}
 
 template <int S>
 __device__ __forceinline__ void load_sys(const double* __restrict__ p, double (&v)[S]) {
@@ -93,8 +135,7 @@ __device__ __forceinline__ bool is_last_block(unsigned int* ticket) {
 template <int NV>
 __device__ __forceinline__ double sum_partials(const double* __restrict__ partial, int nblocks, double* s_red) {
   // thread t owns component (t % NV) of blocks t/NV, t/NV + T/NV, ...
-  static_assert(kThreads % NV == 0, "NV must divide the CTA size");
-  constexpr int G = kThreads / NV;  // groups
+  const int G = blockDim.x / NV;  // groups (NV divides the CTA size: powers of two)
   const int k = threadIdx.x % NV, g = threadIdx.x / NV;
   double acc = 0.0;
   for (int b = g; b < nblocks; b += G) acc += __ldcg(partial + (size_t)b * NV + k);
@@ -111,7 +152,8 @@ __device__ __forceinline__ double sum_partials(const double* __restrict__ partia
 // ---- K5a: vector SpMV, TPR lanes per row -----------------------------------------------------------
 // DOT: also accumulates sum_i y_i x_i per system, and the last CTA turns it into pq and alpha = rho/pq.
 template <int S, int VS, int TPR, bool DOT>
-__global__ void __launch_bounds__(kThreads) spmv_vector_kernel(int64_t nn, const int32_t* __restrict__ rowptr,
+__global__ void __launch_bounds__(kThreads) spmv_vector_kernel(int64_t nn, int64_t row0, int interleave,
+                                                               const int32_t* __restrict__ rowptr,
                                                                const int32_t* __restrict__ col,
                                                                const double* __restrict__ val,
                                                                const double* __restrict__ x, double* __restrict__ y,
@@ -119,30 +161,37 @@ __global__ void __launch_bounds__(kThreads) spmv_vector_kernel(int64_t nn, const
                                                                unsigned int* __restrict__ ticket) {
   __shared__ double s_red[kThreads];
   const int lane = threadIdx.x % TPR;
-  const int64_t rows_per_pass = (int64_t)gridDim.x * (kThreads / TPR);
+  const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
+  constexpr int RPB = kThreads / TPR;  // rows per pass of one CTA
+  // each CTA owns a contiguous run of rows (x gathers of neighbouring rows then hit in L1)
+  const int64_t passes = (nn + (int64_t)gridDim.x * RPB - 1) / ((int64_t)gridDim.x * RPB);
+  // interleave: CTAs sweep the matrix as one moving front (pass p of CTA b = rows (p*grid + b)*RPB ...)
+  const int64_t step = interleave ? (int64_t)gridDim.x * RPB : RPB;
+  const int64_t cta_begin = interleave ? (int64_t)blockIdx.x * RPB : (int64_t)blockIdx.x * passes * RPB;
+  const int64_t cta_end = interleave ? nn : min(nn, cta_begin + passes * RPB);
   double dot[S];
 #pragma unroll
   for (int s = 0; s < S; ++s) dot[s] = 0.0;
-  for (int64_t base = (int64_t)blockIdx.x * (kThreads / TPR); base < nn; base += rows_per_pass) {
-    const int64_t row = base + threadIdx.x / TPR;
+  for (int64_t base = cta_begin; base < cta_end; base += step) {
+    const int64_t row = row0 + base + threadIdx.x / TPR;
     // the trip count is uniform over the CTA (shuffles below use the full mask); rows past nn idle
-    const bool live = row < nn;
+    const bool live = row < row0 + min(nn, cta_end);
     double acc[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) acc[s] = 0.0;
     if (live) {
       const int32_t b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
       for (int32_t k = b + lane; k < e; k += TPR) {
-        const int64_t c = __ldg(col + k);
+        const int64_t c = ldg_i32_hint(col + k, pol_stream);
         double xv[S];
-        load_sys<S>(x + c * S, xv);
+        load_sys_hint<S>(x + c * S, xv, pol_keep);
         if constexpr (VS == 1) {
-          const double a = __ldg(val + k);
+          const double a = ldg_f64_hint(val + k, pol_stream);
 #pragma unroll
           for (int s = 0; s < S; ++s) acc[s] = fma(a, xv[s], acc[s]);
         } else {
           double av[S];
-          load_sys<S>(val + (int64_t)k * S, av);
+          load_sys_hint<S>(val + (int64_t)k * S, av, pol_stream);
 #pragma unroll
           for (int s = 0; s < S; ++s) acc[s] = fma(av[s], xv[s], acc[s]);
         }
@@ -203,94 +252,101 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
         : "memory");
   } while (!done);
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <int STAGES>
-struct StreamSmem {
-  alignas(128) double val[STAGES][kStreamCap];
-  alignas(128) int32_t col[STAGES][kStreamCap];
-  alignas(8) uint64_t bar[STAGES];
-};
+// dynamic shared memory of the streaming kernel: val[STAGES][cap] | col[STAGES][cap] | bar[STAGES]
+__host__ __device__ inline size_t stream_smem_bytes(int stages, int cap) { return (size_t)stages * cap * 12 + stages * 8; }
 
-template <int STAGES, bool DOT>
-__global__ void __launch_bounds__(kThreads) spmv_stream_kernel(const int32_t* __restrict__ rowptr,
-                                                               const int32_t* __restrict__ col,
-                                                               const double* __restrict__ val,
-                                                               const int32_t* __restrict__ blk_row, int32_t nblk,
-                                                               const double* __restrict__ x, double* __restrict__ y,
-                                                               double* __restrict__ partial, double* __restrict__ scal,
-                                                               unsigned int* __restrict__ ticket) {
+// Tile t = rows [t*R, (t+1)*R), R <= 128 chosen at pattern time so that every tile's non-zeros fit a
+// stage.  TPR lanes share a row (CTA = 128*TPR threads); STAGES-1 tiles are in flight per CTA.
+// interleave = 1: CTAs sweep the matrix together as one moving front (tile j of CTA b is b + j*grid).
+template <int STAGES, int TPR, bool DOT>
+__global__ void __launch_bounds__(kStreamThreads* TPR) spmv_stream_kernel(int64_t nn, const int32_t* __restrict__ rowptr,
+                                                                          const int32_t* __restrict__ col,
+                                                                          const double* __restrict__ val, int32_t R,
+                                                                          int32_t cap, int32_t ntiles,
+                                                                          int32_t tiles_per_cta, int interleave,
+                                                                          const double* __restrict__ x,
+                                                                          double* __restrict__ y,
+                                                                          double* __restrict__ partial,
+                                                                          double* __restrict__ scal,
+                                                                          unsigned int* __restrict__ ticket) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  StreamSmem<STAGES>& sm = *reinterpret_cast<StreamSmem<STAGES>*>(smem_raw);
-  __shared__ double s_red[kThreads];
+  double* const s_val = reinterpret_cast<double*>(smem_raw);                                    // [STAGES][cap]
+  int32_t* const s_col = reinterpret_cast<int32_t*>(smem_raw + (size_t)STAGES * cap * 8);        // [STAGES][cap]
+  uint64_t* const s_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * cap * 12);    // [STAGES]
+  __shared__ double s_red[kStreamThreads * TPR];
   const int tid = threadIdx.x;
+  const int lane = tid % TPR, rloc = tid / TPR;
+  const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < STAGES; ++s) mbar_init(&sm.bar[s], 1);
+    for (int s = 0; s < STAGES; ++s) mbar_init(&s_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  // issue the loads of the row block `blk` into stage `st` (thread 0 only)
-  auto issue = [&](int32_t blk, int st) {
-    const int32_t r0 = __ldg(blk_row + blk), r1 = __ldg(blk_row + blk + 1);
-    const int32_t k0 = __ldg(rowptr + r0), k1 = __ldg(rowptr + r1);
-    const int32_t a0 = k0 & ~3, a1 = (k1 + 3) & ~3;
-    const uint32_t n = (uint32_t)(a1 - a0);
-    if (n == 0) {
-      mbar_expect_tx(&sm.bar[st], 0);
-      return;
-    }
-    mbar_expect_tx(&sm.bar[st], n * 12u);
-    bulk_g2s(sm.val[st], val + a0, n * 8u, &sm.bar[st]);
-    bulk_g2s(sm.col[st], col + a0, n * 4u, &sm.bar[st]);
-  };
+  // local tile j of this CTA is global tile tile_of(j)
+  const int64_t t_begin = interleave ? 0 : (int64_t)blockIdx.x * tiles_per_cta;
+  const int64_t t_end = interleave ? ((int64_t)ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x
+                                   : min((int64_t)ntiles, t_begin + tiles_per_cta);
+  auto tile_of = [&](int64_t j) { return interleave ? (int64_t)blockIdx.x + j * gridDim.x : j; };
 
-  double dot = 0.0;
-  uint32_t phase_bits = 0;  // bit s = parity to wait for on stage s
-  // prologue: fill STAGES-1 stages
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
-      const int64_t b = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
-      if (b < nblk) issue((int32_t)b, s);
-    }
-  }
-  int st = 0;
-  for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-    // prefetch the block STAGES-1 ahead into the stage freed at the end of the previous iteration
-    if (tid == 0) {
-      const int64_t nb = blk + (int64_t)(STAGES - 1) * gridDim.x;
-      if (nb < nblk) {
-        fence_proxy_async();
-        issue((int32_t)nb, (st + STAGES - 1) % STAGES);
-      }
-    }
-    const int32_t r0 = __ldg(blk_row + blk), r1 = __ldg(blk_row + blk + 1);
+  // thread 0: bulk-load the val/col slices of local tile j into stage st
+  auto issue = [&](int64_t j, int st) {
+    const int64_t r0 = tile_of(j) * R, r1 = min(nn, r0 + R);
     const int32_t k0 = __ldg(rowptr + r0), k1 = __ldg(rowptr + r1);
     const int32_t a0 = k0 & ~3;
-    const int32_t n = ((k1 + 3) & ~3) - a0;
-    mbar_wait(&sm.bar[st], (phase_bits >> st) & 1u);
-    phase_bits ^= 1u << st;
-    double* sv = sm.val[st];
-    const int32_t* sc = sm.col[st];
-#pragma unroll 4
-    for (int32_t k = tid; k < n; k += kThreads) sv[k] *= __ldg(x + sc[k]);
-    __syncthreads();
-    for (int32_t r = r0 + tid; r < r1; r += kThreads) {
-      const int32_t b = __ldg(rowptr + r) - a0, e = __ldg(rowptr + r + 1) - a0;
-      double acc = 0.0;
-      for (int32_t k = b; k < e; ++k) acc += sv[k];
-      y[r] = acc;
-      if constexpr (DOT) dot = fma(acc, __ldg(x + r), dot);
+    const uint32_t n = (uint32_t)(((k1 + 3) & ~3) - a0);
+    mbar_expect_tx(&s_bar[st], n * 12u);
+    if (n) {
+      bulk_g2s(s_val + (size_t)st * cap, val + a0, n * 8u, &s_bar[st], pol_stream);
+      bulk_g2s(s_col + (size_t)st * cap, col + a0, n * 4u, &s_bar[st], pol_stream);
     }
-    __syncthreads();  // stage st is free again
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s)
+      if (t_begin + s < t_end) issue(t_begin + s, s);
+  }
+  double dot = 0.0;
+  uint32_t phase_bits = 0;
+  int st = 0;
+  for (int64_t t = t_begin; t < t_end; ++t) {
+    if (tid == 0 && t + STAGES - 1 < t_end) {
+      fence_proxy_async();
+      issue(t + STAGES - 1, (st + STAGES - 1) % STAGES);
+    }
+    const int64_t tg = tile_of(t);
+    const int64_t r = tg * R + rloc;
+    const bool live = rloc < R && r < nn;
+    int32_t b = 0, e = 0;
+    if (live) {
+      b = __ldg(rowptr + r);
+      e = __ldg(rowptr + r + 1);
+    }
+    const int32_t a0 = __ldg(rowptr + tg * R) & ~3;
+    mbar_wait(&s_bar[st], (phase_bits >> st) & 1u);
+    phase_bits ^= 1u << st;
+    const double* sv = s_val + (size_t)st * cap;
+    const int32_t* sc = s_col + (size_t)st * cap;
+    double acc = 0.0;
+#pragma unroll 4
+    for (int32_t k = b - a0 + lane; k < e - a0; k += TPR) acc = fma(sv[k], ldg_f64_hint(x + sc[k], pol_keep), acc);
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (live && lane == 0) {
+      y[r] = acc;
+      if constexpr (DOT) dot = fma(acc, ldg_f64_hint(x + r, pol_keep), dot);
+    }
+    __syncthreads();  // stage st may be refilled
     st = (st + 1) % STAGES;
   }
   if constexpr (DOT) {
@@ -589,7 +645,7 @@ int launch_vector(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y, P
 #define PT_VEC(TPR)                                                                                             \
   {                                                                                                             \
     const int grid = grid_for(ctx, A.nn, kThreads / TPR);                                                       \
-    spmv_vector_kernel<S, VS, TPR, DOT><<<grid, kThreads, 0, ctx->stream>>>(A.nn, A.rowptr, A.col, A.val, x, y, \
+    spmv_vector_kernel<S, VS, TPR, DOT><<<grid, kThreads, 0, ctx->stream>>>(A.nn, A.row0, ctx->tune_interleave, A.rowptr, A.col, A.val, x, y, \
                                                                            partial, scal, ticket);             \
   }
   switch (tpr) {
@@ -604,34 +660,60 @@ int launch_vector(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y, P
   return PTFEM_OK;
 }
 
-template <int STAGES, bool DOT>
+template <int STAGES, int TPR, bool DOT>
 int launch_stream_t(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y, PcgWork* w) {
-  const size_t smem = sizeof(StreamSmem<STAGES>);
-  const uint32_t bit = 1u << (STAGES * 2 + (DOT ? 1 : 0));
-  if (!(ctx->func_attr_done & bit)) {
-    PT_CK(cudaFuncSetAttribute(spmv_stream_kernel<STAGES, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ctx->func_attr_done |= bit;
+  const size_t smem = stream_smem_bytes(STAGES, A.stream_cap);
+  {
+    const void* fn = reinterpret_cast<const void*>(&spmv_stream_kernel<STAGES, TPR, DOT>);
+    auto it = ctx->func_smem.find(fn);
+    if (it == ctx->func_smem.end() || it->second < smem) {
+      PT_CK(cudaFuncSetAttribute(spmv_stream_kernel<STAGES, TPR, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ctx->func_smem[fn] = smem;
+    }
   }
-  int per_sm = (int)((size_t)(220 * 1024) / (smem + 2304));
-  if (per_sm > kCtasPerSm) per_sm = kCtasPerSm;
+  const int threads = A.stream_rows * TPR;
+  int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024 + (DOT ? kStreamThreads * TPR * 8 : 0) + 32));
+  if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+  if (per_sm > 32) per_sm = 32;
+  if (ctx->tune_ctas_per_sm > 0 && ctx->tune_ctas_per_sm < per_sm) per_sm = ctx->tune_ctas_per_sm;
   if (per_sm < 1) per_sm = 1;
+  const int64_t ntiles = (A.nn + A.stream_rows - 1) / A.stream_rows;
   int64_t grid = (int64_t)ctx->sm_count * per_sm;
-  if (grid > A.nblk) grid = A.nblk;
+  if (grid > ntiles) grid = ntiles;
   if (grid < 1) grid = 1;
-  spmv_stream_kernel<STAGES, DOT><<<(int)grid, kThreads, smem, ctx->stream>>>(
-      A.rowptr, A.col, A.val, A.blk_row, A.nblk, x, y, w ? w->partial.p : nullptr, w ? w->scal.p : nullptr,
-      w ? w->ticket.p : nullptr);
+  const int64_t per_cta = (ntiles + grid - 1) / grid;
+  if (!ctx->tune_interleave) grid = (ntiles + per_cta - 1) / per_cta;
+  spmv_stream_kernel<STAGES, TPR, DOT><<<(int)grid, threads, smem, ctx->stream>>>(
+      A.nn, A.rowptr, A.col, A.val, A.stream_rows, A.stream_cap, (int32_t)ntiles, (int32_t)per_cta, ctx->tune_interleave, x,
+      y, w ? w->partial.p : nullptr, w ? w->scal.p : nullptr, w ? w->ticket.p : nullptr);
   PT_LAUNCH_CHECK(ctx);
   return PTFEM_OK;
+}
+
+template <int STAGES, bool DOT>
+int launch_stream_s(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y, PcgWork* w, int tpr) {
+  switch (tpr) {
+    case 2: return launch_stream_t<STAGES, 2, DOT>(ctx, A, x, y, w);
+    case 4: return launch_stream_t<STAGES, 4, DOT>(ctx, A, x, y, w);
+    case 8: return launch_stream_t<STAGES, 8, DOT>(ctx, A, x, y, w);
+    default: return launch_stream_t<STAGES, 1, DOT>(ctx, A, x, y, w);
+  }
+}
+template <bool DOT>
+int launch_stream(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y, PcgWork* w, int stages, int tpr) {
+  if (stages == 3) return launch_stream_s<3, DOT>(ctx, A, x, y, w, tpr);
+  if (stages >= 4) return launch_stream_s<4, DOT>(ctx, A, x, y, w, tpr);
+  return launch_stream_s<2, DOT>(ctx, A, x, y, w, tpr);
 }
 
 template <int S, int VS>
 int spmv_sv(ptfem_ctx* ctx, const LinSys& A, int variant, const double* x, double* y, PcgWork* w, bool dot) {
   if constexpr (S == 1) {
-    if (variant == PTFEM_SPMV_STREAM)
-      return dot ? launch_stream_t<2, true>(ctx, A, x, y, w) : launch_stream_t<2, false>(ctx, A, x, y, w);
-    if (variant == PTFEM_SPMV_STREAM1)
-      return dot ? launch_stream_t<1, true>(ctx, A, x, y, w) : launch_stream_t<1, false>(ctx, A, x, y, w);
+    if (variant == PTFEM_SPMV_STREAM || variant == PTFEM_SPMV_STREAM1) {
+      const int stages = variant == PTFEM_SPMV_STREAM ? ctx->tune_stream_stages : ctx->tune_stream_stages + 1;
+      return dot ? launch_stream<true>(ctx, A, x, y, w, stages, ctx->tune_stream_tpr)
+                 : launch_stream<false>(ctx, A, x, y, w, stages, ctx->tune_stream_tpr);
+    }
   }
   return dot ? launch_vector<S, VS, true>(ctx, A, x, y, w) : launch_vector<S, VS, false>(ctx, A, x, y, w);
 }
@@ -649,12 +731,14 @@ int spmv_sv(ptfem_ctx* ctx, const LinSys& A, int variant, const double* x, doubl
 
 }  // namespace
 
-int ptfem_stream_tile_nnz() { return kStreamTile; }
+int ptfem_stream_cap_max() { return kStreamCapMax; }
+int ptfem_stream_rows_default() { return kStreamRowsDefault; }
+int ptfem_stream_threads() { return kStreamThreads; }
 
 namespace ptfem {
 
 int resolve_variant(const LinSys& A, int variant) {
-  const bool stream_ok = A.S == 1 && A.blk_row != nullptr && A.nblk > 0 && A.max_row <= kStreamMaxRow;
+  const bool stream_ok = A.S == 1 && A.stream_rows > 0 && A.row0 == 0;
   if (variant == PTFEM_SPMV_AUTO) return stream_ok && A.nnz >= (int64_t)1 << 20 ? PTFEM_SPMV_STREAM : PTFEM_SPMV_VECTOR;
   if ((variant == PTFEM_SPMV_STREAM || variant == PTFEM_SPMV_STREAM1) && !stream_ok) return PTFEM_SPMV_VECTOR;
   return variant;

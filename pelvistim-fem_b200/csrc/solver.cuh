@@ -12,9 +12,9 @@ struct LinSys {
   int S = 1;                     // systems (padded to 1,2,4,8,16); vectors are [nn][S]
   const double* dinv = nullptr;  // [nn][VS] inverse diagonal
   const double* b = nullptr;     // [nn][S]
-  const int32_t* blk_row = nullptr;  // streaming row blocks (may be null -> vector kernel only)
-  int32_t nblk = 0;
-  int32_t max_row = 0;
+  int32_t stream_rows = 0;       // rows per tile of the streaming SpMV (0: vector kernel only)
+  int32_t stream_cap = 0;        // staged entries per tile (shared-memory stage size / 12 bytes)
+  int64_t row0 = 0;              // the system is rows [row0, row0+nn) of the arrays (row-range SpMV)
 };
 
 namespace ptfem {
