@@ -1,0 +1,196 @@
+#!/usr/bin/env python3
+"""step03: layered ankle slab sweep (fat thickness x electrode radius) — drop-in for the reference's
+``step03_ankle_layers/run_layered_sweep.py``: same CLI (``--smoke``), ``params.yaml`` schema, case labels
+(``:1063-1064``), per-case files (``elmer_mesh/``, ``case.sif``, ``bc_debug_report.txt``,
+``results/case_t0001.vtu``) and ``results/summary.csv|json`` columns (``:991-1030``).
+
+What changed: ``gmsh`` meshing falls back to the built-in structured mesher, and the two subprocess
+boundaries (``ElmerGrid`` ``:1077``, ``ElmerSolver`` ``:1099``) plus the pyvista metric extraction are
+served by the GPU engine in-process.  Extra flags: ``--gpus N`` shards the independent sweep points
+over N GPUs (one worker process per GPU; rows are gathered in sweep order)."""
+import argparse
+import csv
+import json
+import math
+import sys
+from pathlib import Path
+
+import numpy as np
+import yaml
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import _common  # noqa: F401,E402
+from pelvistim_fem_b200 import elmer_io, meshgen, pipeline, sif, sweep  # noqa: E402
+
+HERE = Path(__file__).resolve().parent
+RESULTS_DIR = HERE / "results"
+PARAMS_FILE = HERE / "params.yaml"
+
+
+def load_params(path=PARAMS_FILE):
+    with open(path) as f:
+        return yaml.safe_load(f)
+
+
+def _pl(p):
+    return p.get("placement", p.get("electrodes", {}))
+
+
+def _stim(p):
+    return p.get("stim", p.get("control", {}))
+
+
+def build_mesh(p, t_fat, elec_r, run_dir, coarse=False):
+    """Layered slab + contact pads (``run_layered_sweep.py:122-362``, rect cross-section).
+    Returns ``(mesh, e1_pos3d, e2_pos3d, body_info)``; writes ``run_dir/elmer_mesh``."""
+    run_dir = Path(run_dir)
+    run_dir.mkdir(parents=True, exist_ok=True)
+    g, ls, pl = p["geometry"], p["layers"], _pl(p)
+    Lx, Ly, Lz = g["Lx"], g["Ly"], g["Lz"]
+    if g.get("cross_section", "rect") != "rect":
+        raise NotImplementedError("only cross_section: rect (the configured default) is built in")
+    shape = pl.get("electrode_shape", pl.get("shape", "circle"))
+    active_xy = pl.get("active_xy", [pl.get("medial_offset", 0.025), Ly / 2])
+    return_xy = pl.get("return_xy", [Lx - pl.get("lateral_offset", 0.025), Ly / 2])
+    ct = p.get("contact", {})
+    contact = bool(ct.get("enabled", False))
+    t_contact = ct.get("t_contact_mm", 0.5) * 1e-3 if contact else 0.0
+    mm = p.get("mesh", {})
+    scale = 2.0 if coarse else 1.0
+    lc_elec = mm.get("lc_electrode_mm", elec_r * 300) * 1e-3 * scale
+    lc_bulk = mm.get("lc_global_mm", 3.0) * 1e-3 * scale
+    t_muscle = Lz - ls["t_skin"] - t_fat
+    n_m = max(3, int(round(t_muscle / lc_bulk)))
+    n_f = max(2, int(round(t_fat / lc_elec)))
+    mesh = meshgen.layered_slab_mesh(Lx, Ly, Lz, ls["t_skin"], t_fat, t_contact or 0.0005, active_xy, return_xy, elec_r,
+                                     shape, n_muscle=n_m, n_fat=n_f, n_skin=2, n_contact=1, h_bulk=lc_bulk,
+                                     h_elec=lc_elec, contact_enabled=contact)
+    elmer_io.write_elmer_mesh(run_dir / "elmer_mesh", mesh)
+    z_top = Lz + t_contact
+    body_info = dict(contact_enabled=contact, z_skin_top=Lz, z_elec_top=z_top, z_e1_skin=Lz, z_e2_skin=Lz,
+                     z_e1_elec_top=z_top, z_e2_elec_top=z_top, c1_body_id=4 if contact else None,
+                     c2_body_id=5 if contact else None, elec_shape=shape)
+    e1 = np.array([float(active_xy[0]), float(active_xy[1]), z_top])
+    e2 = np.array([float(return_xy[0]), float(return_xy[1]), z_top])
+    return mesh, e1, e2, body_info
+
+
+def write_sif(run_dir, e1_id, e2_id, p, elec_r, body_info, sigma_skin_override=None, elec_area_mesh=None,
+              sigma_contact_override=None, dialect="step03"):
+    c, sv, st, ct = p["conductivities"], p["solver"], _stim(p), p.get("contact", {})
+    sigma_skin = sigma_skin_override if sigma_skin_override is not None else c["sigma_skin"]
+    sigma_c = sigma_contact_override if sigma_contact_override is not None else ct.get("sigma_contact_Spm", 0.005)
+    secs, jn_used, warning = sif.layered_case(
+        e1_id, e2_id, c["sigma_muscle"], c["sigma_fat"], sigma_skin, sigma_c,
+        contact=body_info.get("contact_enabled", False), c1_body=body_info.get("c1_body_id") or 4,
+        c2_body=body_info.get("c2_body_id") or 5, mode=st.get("control_mode", "voltage"),
+        injected_current_mA=st.get("injected_current_mA", 5.0), elec_r=elec_r, shape=body_info.get("elec_shape", "circle"),
+        elec_area_mesh=elec_area_mesh, tol=sv.get("tolerance", 1e-8), lin_solver=sv.get("linear_solver", "UMFPACK"),
+        dialect=dialect)
+    if warning:
+        print(f"    WARNING: {warning}")
+    (Path(run_dir) / "case.sif").write_text(sif.serialize(secs))
+    return jn_used
+
+
+def case_label(t_fat, elec_r):
+    return f"tfat{int(t_fat*1000):04d}um_r{int(elec_r*1000):04d}um"
+
+
+def run_case(p, t_fat, elec_r, coarse=False, sigma_skin_override=None, ctx=None, results_dir=None, quiet=False):
+    """One sweep point, end to end (the loop body of ``run_layered_sweep.py:1061-1124``)."""
+    say = (lambda *a, **k: None) if quiet else print
+    results_dir = Path(results_dir) if results_dir else RESULTS_DIR
+    sigma_skin = sigma_skin_override if sigma_skin_override is not None else p["conductivities"]["sigma_skin"]
+    label = case_label(t_fat, elec_r)
+    run_dir = results_dir / label
+    say(f"\n[{label}]  t_fat={t_fat*1000:.1f}mm  r={elec_r*1000:.1f}mm  sigma_skin={sigma_skin}")
+    say("  meshing ...")
+    mesh, e1_pos, e2_pos, body_info = build_mesh(p, t_fat, elec_r, run_dir, coarse=coarse)
+    say(f"    {mesh.nn} nodes")
+    say("  detecting electrode BCs + computing mesh areas ...")
+    e1_id, e2_id, A_act, A_ret = pipeline.detect_elec_bc_ids(mesh, e1_pos, e2_pos, e1_pos[2], e2_pos[2])
+    shape = body_info["elec_shape"]
+    area_an = math.pi * elec_r ** 2 if shape == "circle" else (2 * elec_r) ** 2
+    say(f"    active={e1_id}  return={e2_id}  A_active={A_act*1e4:.4f}cm²  A_analytic={area_an*1e4:.4f}cm²")
+    jn_used = write_sif(run_dir, e1_id, e2_id, p, elec_r, body_info, sigma_skin_override=sigma_skin_override,
+                        elec_area_mesh=A_act)
+    pipeline.save_bc_debug_report(run_dir, label, e1_id, e2_id, A_act, A_ret, jn_used, p, body_info)
+    (run_dir / "results").mkdir(exist_ok=True)
+    say("  solver (GPU engine) ...")
+    case = pipeline.run_elmer_solver(run_dir, ctx=ctx, mesh=mesh)
+    say("  extracting metrics ...")
+    res = pipeline.extract_layered(case, p, t_fat, elec_r, e1_pos, e2_pos, body_info, sigma_skin_used=sigma_skin,
+                                   jn_used=jn_used, elec_area_mesh=A_act, return_area_mesh=A_ret, e1_id=e1_id,
+                                   e2_id=e2_id, warn=say)
+    case.close()
+    say(f"    peak_J_no_elec={res['peak_J_skin_no_elec']:.4f}  roi_mean_E={res['roi_mean_E']:.4f}  "
+        f"efficiency={res['efficiency']:.4e}  flux_err={res['flux_err']:.3e}")
+    if res.get("control_mode") == "current":
+        say(f"    compliance_V={res['compliance_V']:.2f} V  I_active={res['total_current_A']:.4e} A  "
+            f"I_return={res['I_return_A']:.4e} A")
+    return res
+
+
+def _point(args):
+    p, t_fat, elec_r, coarse, override, results_dir = args
+    return run_case(p, t_fat, elec_r, coarse, override, ctx=sweep.worker_context(), results_dir=results_dir,
+                    quiet=sweep.worker_rank() is not None)
+
+
+def run_sweep(p, t_fat_list, elec_r_list, coarse=False, sigma_skin_override=None, gpus=1):
+    RESULTS_DIR.mkdir(exist_ok=True)
+    st = _stim(p)
+    mode = st.get("control_mode", "voltage")
+    print(f"\n{'='*60}")
+    if mode == "current":
+        print("  CONTROL MODE : current")
+        print(f"  Injected I   : {st.get('injected_current_mA', 5.0):.1f} mA  (per-case Neumann BC at active electrode)")
+        print(f"  Compliance   : warn if V_active > {st.get('compliance_voltage_V', 100.0):.0f} V")
+    else:
+        print("  CONTROL MODE : voltage")
+        print("  V_active = 1.0 V  |  V_return = 0 V  (Dirichlet BCs)")
+    print(f"{'='*60}\n")
+    points = [(p, t_fat, r * 1e-3, coarse, sigma_skin_override, str(RESULTS_DIR)) for t_fat in t_fat_list for r in elec_r_list]
+    return sweep.map_points(_point, points, gpus=gpus)
+
+
+def save_results(all_results, results_dir=None):
+    if not all_results:
+        return
+    results_dir = Path(results_dir) if results_dir else RESULTS_DIR
+    keys = list(all_results[0].keys())
+    with open(results_dir / "summary.csv", "w", newline="") as f:
+        w = csv.DictWriter(f, fieldnames=keys)
+        w.writeheader()
+        w.writerows(all_results)
+    print(f"\nSaved → {results_dir / 'summary.csv'}")
+    with open(results_dir / "summary.json", "w") as f:
+        json.dump(all_results, f, indent=2, default=lambda x: None if isinstance(x, float) and np.isnan(x) else x)
+    print(f"Saved → {results_dir / 'summary.json'}")
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description="Ankle layered slab sweep")
+    ap.add_argument("--smoke", action="store_true", help="Single coarse case for quick pipeline check")
+    ap.add_argument("--gpus", type=int, default=1, help="shard sweep points over this many GPUs")
+    args = ap.parse_args(argv)
+    p = load_params()
+    pl = _pl(p)
+    if args.smoke:
+        t_fat_list = [p["layers"]["t_fat"]]
+        r_list = [pl.get("electrode_r_mm_list", pl.get("size_list", [10]))[1]]
+        print("=== SMOKE TEST (1 coarse case) ===")
+    else:
+        t_fat_list = p["layers"]["t_fat_sweep"]
+        r_list = pl.get("electrode_r_mm_list", pl.get("size_list", [5, 10, 15]))
+        print(f"=== FULL SWEEP: {len(t_fat_list)} fat thicknesses × {len(r_list)} electrode sizes = "
+              f"{len(t_fat_list)*len(r_list)} cases ===")
+    results = run_sweep(p, t_fat_list, r_list, coarse=args.smoke, gpus=args.gpus)
+    save_results(results)
+    print(f"\n  {len(results)} case(s) computed → results/summary.csv, results/summary.json")
+    return results
+
+
+if __name__ == "__main__":
+    main()

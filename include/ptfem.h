@@ -163,8 +163,9 @@ int ptfem_metric_roi(ptfem_mesh* m, int32_t sys, const double cen[3], double r0,
 /* step01 (test_step01_baseline.py:59-104): centre-column least squares of phi(z):
  * out = {n, sum z, sum phi, sum z^2, sum z phi, sum phi^2} over nodes with hypot(x-cx,y-cy) < rad */
 int ptfem_metric_column_fit(ptfem_mesh* m, int32_t sys, double cx, double cy, double rad, double out[6]);
-/* sum and sum of squares of |J| over all nodes: out = {n, sum, sumsq} */
-int ptfem_metric_jstats(ptfem_mesh* m, int32_t sys, double out[3]);
+/* moments of |J| over all nodes about `shift`: out = {n, sum(|J|-shift), sum((|J|-shift)^2)}
+ * (two calls, shift = 0 then shift = mean, give mean and an accurate sample variance) */
+int ptfem_metric_jstats(ptfem_mesh* m, int32_t sys, double shift, double out[3]);
 /* weak-form reaction current: sum over nodes on boundary bcid of (K_raw phi - b_neumann)_i (exact KCL) */
 int ptfem_metric_reaction(ptfem_mesh* m, int32_t sys, int32_t bcid, double* current);
 /* K13 (not in the reference; north_star): phi sampled at points along a nerve-fibre polyline and the

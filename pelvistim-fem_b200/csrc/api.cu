@@ -23,7 +23,7 @@ int ptfem_do_metric_pad_current(ptfem_mesh* m, int sys, double zmin, const ptfem
 int ptfem_do_metric_roi(ptfem_mesh* m, int sys, const double cen[3], double r0, const double* mult, int nmult, double z0,
                         double z1, int include_tris, double* out);
 int ptfem_do_metric_column_fit(ptfem_mesh* m, int sys, double cx, double cy, double rad, double out[6]);
-int ptfem_do_metric_jstats(ptfem_mesh* m, int sys, double out[3]);
+int ptfem_do_metric_jstats(ptfem_mesh* m, int sys, double shift, double out[3]);
 int ptfem_do_metric_reaction(ptfem_mesh* m, int sys, int32_t bcid, double* current);
 int ptfem_do_sample_polyline(ptfem_mesh* m, int sys, int64_t npts, const double* pts, double* phi_out, double* af_out);
 void ptfem_dist_ctx_release(ptfem_ctx* ctx);
@@ -500,10 +500,10 @@ int ptfem_metric_column_fit(ptfem_mesh* m, int32_t sys, double cx, double cy, do
   PT_CK(cudaSetDevice(m->ctx->device));
   return ptfem_do_metric_column_fit(m, sys, cx, cy, rad, out);
 }
-int ptfem_metric_jstats(ptfem_mesh* m, int32_t sys, double out[3]) {
+int ptfem_metric_jstats(ptfem_mesh* m, int32_t sys, double shift, double out[3]) {
   PT_ARG(m && out, "null pointer");
   PT_CK(cudaSetDevice(m->ctx->device));
-  return ptfem_do_metric_jstats(m, sys, out);
+  return ptfem_do_metric_jstats(m, sys, shift, out);
 }
 int ptfem_metric_reaction(ptfem_mesh* m, int32_t sys, int32_t bcid, double* current) {
   PT_ARG(m && current, "null pointer");

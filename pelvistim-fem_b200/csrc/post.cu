@@ -326,13 +326,14 @@ __global__ void __launch_bounds__(kT) column_fit_kernel(const double* __restrict
   block_reduce_ops<6>(v, op, partial);
 }
 
-__global__ void __launch_bounds__(kT) jstats_kernel(const double* __restrict__ Jn, int64_t nn, double* __restrict__ partial) {
+__global__ void __launch_bounds__(kT) jstats_kernel(const double* __restrict__ Jn, int64_t nn, double shift,
+                                                    double* __restrict__ partial) {
   double v[3] = {0, 0, 0};
   const int64_t stride = (int64_t)gridDim.x * kT;
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < nn; i += stride) {
     const double jx = Jn[i * 3], jy = Jn[i * 3 + 1], jz = Jn[i * 3 + 2];
-    const double m2 = jx * jx + jy * jy + jz * jz;
-    v[0] += 1.0; v[1] += sqrt(m2); v[2] += m2;
+    const double d = sqrt(jx * jx + jy * jy + jz * jz) - shift;
+    v[0] += 1.0; v[1] += d; v[2] += d * d;
   }
   const int op[3] = {0, 0, 0};
   block_reduce_ops<3>(v, op, partial);
@@ -634,12 +635,12 @@ int ptfem_do_metric_column_fit(ptfem_mesh* m, int sys, double cx, double cy, dou
   return finish_reduce(m, grid, 6, ops, out);
 }
 
-int ptfem_do_metric_jstats(ptfem_mesh* m, int sys, double out[3]) {
+int ptfem_do_metric_jstats(ptfem_mesh* m, int sys, double shift, double out[3]) {
   ptfem_ctx* ctx = m->ctx;
   PT_TRY(need_J(m, sys));
   const int grid = red_grid(ctx, m->nn);
   PT_TRY(need_partials(m, grid, 3));
-  jstats_kernel<<<grid, kT, 0, ctx->stream>>>(m->Jnode.p, m->nn, m->scratch_d.p);
+  jstats_kernel<<<grid, kT, 0, ctx->stream>>>(m->Jnode.p, m->nn, shift, m->scratch_d.p);
   PT_LAUNCH_CHECK(ctx);
   const int ops[3] = {0, 0, 0};
   return finish_reduce(m, grid, 3, ops, out);

@@ -101,7 +101,7 @@ def load_library():
         "ptfem_metric_pad_current": (C.c_int, [vp, i32, dbl, P(Footprint), dbl, P(dbl)]),
         "ptfem_metric_roi": (C.c_int, [vp, i32, P(dbl), dbl, P(dbl), i32, dbl, dbl, i32, P(dbl)]),
         "ptfem_metric_column_fit": (C.c_int, [vp, i32, dbl, dbl, dbl, P(dbl)]),
-        "ptfem_metric_jstats": (C.c_int, [vp, i32, P(dbl)]),
+        "ptfem_metric_jstats": (C.c_int, [vp, i32, dbl, P(dbl)]),
         "ptfem_metric_reaction": (C.c_int, [vp, i32, i32, P(dbl)]),
         "ptfem_sample_polyline": (C.c_int, [vp, i32, i64, vp, vp, vp]),
         "ptfem_dist_unique_id": (C.c_int, [C.c_char_p, vp]),
@@ -111,8 +111,6 @@ def load_library():
         "ptfem_dist_solve": (C.c_int, [vp, P(SolveOpts), vp, P(SolveStats), P(dbl), P(dbl), P(dbl)]),
     }
     for name, (res, args) in sig.items():
-        if name.startswith("ptfem_dist_") and not hasattr(L, name):
-            continue                   # TEMP until dist.cu lands
         f = getattr(L, name)          # AttributeError here = header and library out of sync
         f.restype = res
         f.argtypes = args
@@ -396,9 +394,9 @@ class DeviceMesh:
         self._ck(self.lib.ptfem_metric_column_fit(self._h, sys, cx, cy, rad, out))
         return list(out)
 
-    def metric_jstats(self, sys=0):
+    def metric_jstats(self, shift=0.0, sys=0):
         out = (C.c_double * 3)()
-        self._ck(self.lib.ptfem_metric_jstats(self._h, sys, out))
+        self._ck(self.lib.ptfem_metric_jstats(self._h, sys, float(shift), out))
         return list(out)
 
     def metric_reaction(self, bcid, sys=0):

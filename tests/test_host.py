@@ -1,0 +1,161 @@
+"""Host-side logic on CPU: SIF writer/parser against the reference's committed case.sif files, Elmer mesh
+and VTU I/O, boundary-id detection, labels, sweep sharding, and the C-ABI library surface."""
+import ctypes
+import re
+
+import numpy as np
+import pytest
+
+import pelvistim_fem_b200  # noqa: F401
+from oracle import metrics_oracle as mo
+from pelvistim_fem_b200 import elmer_io, engine, meshgen, pipeline, sif, sweep, vtu
+
+
+# -- SIF -------------------------------------------------------------------------------------------
+def test_sif_step01_step02_byte_exact(golden):
+    assert sif.serialize(sif.box_case([2], [1])) == (golden / "step01_case.sif").read_text()
+    assert sif.serialize(sif.electrode_case(101, 102)) == (golden / "step02_circle_r05mm_case.sif").read_text()
+
+
+@pytest.mark.parametrize("name,r_mm", [("tfat0003um_r0005um", 5), ("tfat0005um_r0010um", 10), ("tfat0008um_r0015um", 15)])
+def test_sif_step03_byte_exact(golden, name, r_mm):
+    ref = (golden / f"step03_{name}_case.sif").read_text()
+    rep = (golden / f"step03_{name}_bc_debug_report.txt").read_text()
+    jn = float(re.search(r"Current Density = (\S+)", ref).group(1))
+    area = 5e-3 / jn
+    secs, jn_used, _ = sif.layered_case(101, 102, 0.35, 0.04, 0.001, 0.005, elec_r=r_mm * 1e-3, elec_area_mesh=area)
+    # the comment carries the mesh area to 4 decimals: take it from the golden report
+    a_txt = re.search(r"Mesh area — active electrode : (\S+) cm²", rep).group(1)
+    out = sif.serialize(secs)
+    assert f"A_mesh={a_txt}cm²" in ref
+    assert out == ref
+
+
+@pytest.mark.parametrize("lvl", ["p01", "p08", "p15"])
+def test_sif_step04_byte_exact(golden, lvl):
+    import yaml
+    ref = (golden / f"step04_{lvl}_case.sif").read_text()
+    p = yaml.safe_load((golden / "step04_params.yaml").read_text())
+    k = p["pressure_sweep"]["labels"].index(lvl)
+    sigma_c = p["pressure_sweep"]["sigma_contact_Spm"][k]
+    jn = float(re.search(r"Current Density = (\S+)", ref).group(1))
+    secs, _, _ = sif.layered_case(101, 102, 0.35, 0.04, 0.001, sigma_c, elec_r=0.010, elec_area_mesh=5e-3 / jn, dialect="step04")
+    assert sif.serialize(secs) == ref
+
+
+def test_sif_parse_problem(golden):
+    pr = sif.problem_from_sif((golden / "step03_tfat0005um_r0010um_case.sif").read_text())
+    assert pr.sigma_by_body == {1: 0.35, 2: 0.04, 3: 0.001, 4: 0.005, 5: 0.005}
+    assert pr.dirichlet == [(102, 0.0)] and pr.neumann == [(101, 15.97501)] and pr.calc_current
+    assert (pr.mesh_db, pr.results_dir, pr.output_name) == ("elmer_mesh", "results", "case")
+    p1 = sif.problem_from_sif((golden / "step01_case.sif").read_text())
+    assert p1.sigma_by_body == {1: 0.2} and p1.dirichlet == [(2, 1.0), (1, 0.0)] and p1.neumann == []
+    multi = sif.serialize(sif.box_case([2, 7], [1]))
+    assert "Target Boundaries(2) = 2 7" in multi
+    assert sif.problem_from_sif(multi).dirichlet == [(2, 1.0), (7, 1.0), (1, 0.0)]
+    with pytest.raises(ValueError):
+        sif.problem_from_sif("Header\n  Mesh DB \".\" \"m\"\n")          # missing End
+    with pytest.raises(ValueError):
+        sif.problem_from_sif("Body 1\n  Target Bodies(1) = 1\n  Material = 3\nEnd\n")   # no conductivity
+
+
+# -- mesh / VTU I/O ----------------------------------------------------------------------------------
+def test_elmer_mesh_roundtrip(tmp_path):
+    m = meshgen.synth_slab("XS")
+    elmer_io.write_elmer_mesh(tmp_path / "elmer_mesh", m)
+    hdr = (tmp_path / "elmer_mesh" / "mesh.header").read_text().split()
+    assert [int(hdr[0]), int(hdr[1]), int(hdr[2])] == [m.nn, m.nt, m.nb]
+    first = (tmp_path / "elmer_mesh" / "mesh.elements").read_text().splitlines()[0].split()
+    assert first[2] == "504" and len(first) == 7                  # find_boundaries.py:31-40
+    b = (tmp_path / "elmer_mesh" / "mesh.boundary").read_text().splitlines()[0].split()
+    assert b[4] == "303" and len(b) == 8                          # find_boundaries.py:87-90
+    r = elmer_io.read_elmer_mesh(tmp_path / "elmer_mesh")
+    assert np.array_equal(r.nodes, m.nodes) and np.array_equal(r.tets, m.tets) and np.array_equal(r.region, m.region)
+    assert np.array_equal(r.tris, m.tris) and np.array_equal(r.bcid, m.bcid)
+    with pytest.raises(FileNotFoundError):
+        elmer_io.read_elmer_mesh(tmp_path / "nope")
+
+
+def test_vtu_roundtrip(tmp_path):
+    m = meshgen.box_mesh(nx=3, ny=3, nz=2)
+    phi = np.arange(m.nn, dtype=np.float64)
+    J = np.random.default_rng(0).standard_normal((m.nn, 3))
+    pipeline.write_case_vtu(tmp_path / "case_t0001.vtu", m, phi, J)
+    v = vtu.read_vtu(tmp_path / "case_t0001.vtu")
+    tets, tris = vtu.split_cells(v)
+    assert np.array_equal(v["points"], m.nodes) and np.array_equal(tets, m.tets) and np.array_equal(tris, m.tris)
+    assert np.array_equal(v["point_data"]["potential"], phi) and np.array_equal(v["point_data"]["volume current"], J)
+    assert list(v["cell_types"][:m.nt]) == [10] * m.nt and list(v["cell_types"][m.nt:]) == [5] * m.nb
+    assert v["cell_data"]["GeometryIds"].shape[0] == m.nt + m.nb
+
+
+# -- pre-solve host logic -----------------------------------------------------------------------------
+def test_detect_elec_bc_ids_matches_loop_restatement():
+    m = meshgen.layered_slab_mesh(elec_r=0.010, n_muscle=4, n_fat=2, h_bulk=0.006, h_elec=0.003)
+    e1, e2 = [0.015, 0.045, 0.0405], [0.065, 0.045, 0.0405]
+    got = pipeline.detect_elec_bc_ids(m, e1, e2, 0.0405, 0.0405)
+    want = mo.detect_elec_bc_ids_loops(m.nodes, m.tris, m.bcid, e1, e2, 0.0405, 0.0405)
+    assert got[:2] == want[:2] == (101, 102)
+    assert np.isclose(got[2], want[2], rtol=1e-12) and np.isclose(got[3], want[3], rtol=1e-12)
+    assert abs(got[2] - np.pi * 0.010 ** 2) / (np.pi * 0.010 ** 2) < 0.05     # golden: 3.1299 vs 3.1416 cm2
+    # swapped positions pick swapped ids
+    assert pipeline.detect_elec_bc_ids(m, e2, e1, 0.0405, 0.0405)[:2] == (102, 101)
+
+
+def test_step01_boundary_classification_and_labels():
+    m = meshgen.box_mesh(ids=(2, 1, 3))
+    assert pipeline.classify_flat_boundaries(m) == ([2], [1])
+    import run_layered_sweep as s3
+    assert s3.case_label(0.005, 0.010) == "tfat0005um_r0010um"        # run_layered_sweep.py:1063-1064
+    assert s3.case_label(0.003, 0.005) == "tfat0003um_r0005um"
+    assert f"{'circle'}_r{int(0.005*1000):02d}mm" == "circle_r05mm"   # run_sweep.py:303
+
+
+def test_bc_debug_report_byte_exact(golden, tmp_path):
+    import yaml
+    p = yaml.safe_load((golden / "step03_params.yaml").read_text())
+    ref = (golden / "step03_tfat0005um_r0010um_bc_debug_report.txt").read_text()
+    jn = float(re.search(r"\(Jn\) : (\S+) A", ref).group(1))
+    bi = dict(contact_enabled=True, z_skin_top=0.040, z_elec_top=0.0405, z_e1_skin=0.040, z_e2_skin=0.040,
+              z_e1_elec_top=0.0405, z_e2_elec_top=0.0405)
+    out = pipeline.save_bc_debug_report(tmp_path, "tfat0005um_r0010um", 101, 102, 5e-3 / jn, 5e-3 / jn, jn, p, bi)
+    assert out.read_text() == ref
+
+
+def test_sweep_assignment():
+    assert sweep.assign(9, 4) == [[0, 4, 8], [1, 5], [2, 6], [3, 7]]
+    assert sweep.assign(2, 8)[:3] == [[0], [1], []]
+    assert sweep.map_points(lambda x: x * x, [1, 2, 3], gpus=1) == [1, 4, 9]
+
+
+def test_meshers_are_valid():
+    for m in (meshgen.box_mesh(jitter=0.3), meshgen.synth_slab("XS"), meshgen.electrode_box_mesh(0.15, 0.15, 0.05, (0.045, 0.075), (0.105, 0.075), 0.01, "square", nz=4)):
+        assert (meshgen.tet_volumes(m.nodes, m.tets) > 0).all()
+        ext, _ = meshgen.external_faces(m.tets)
+        # every external face carries exactly one boundary triangle
+        key = lambda t: set(map(tuple, np.sort(t, axis=1).tolist()))
+        assert key(ext) <= key(m.tris)
+    slab = meshgen.synth_slab("XS")
+    assert sorted(np.unique(slab.region).tolist()) == [1, 2, 3, 4, 5] and sorted(np.unique(slab.bcid).tolist()) == [101, 102, 103]
+    with pytest.raises(ValueError):
+        meshgen.layered_slab_mesh(t_fat=0.0385)
+
+
+# -- C-ABI surface ---------------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    lib = engine.load_library()
+    names = engine.exported_symbols()
+    assert len(names) >= 43
+    for n in names:
+        assert hasattr(lib, n), f"libptfem.so does not export {n}"
+    assert lib.ptfem_version() >= 100
+
+
+def test_no_cpu_fallback_without_device():
+    n = ctypes.c_int(-1)
+    engine.load_library().ptfem_device_count(ctypes.byref(n))
+    if n.value > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(engine.PtfemError) as ei:
+        engine.Context(0)
+    assert "no CPU fallback" in str(ei.value)

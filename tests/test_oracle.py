@@ -1,0 +1,152 @@
+"""The CPU oracle against the reference's known answers: the analytic step01 case
+(exact for P1), physical laws (KCL, series resistance of the contact layer as in step04's table), the
+golden step03/step04 tables to discretisation accuracy, and the C oracle against the numpy oracle."""
+import json
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import pelvistim_fem_b200  # noqa: F401
+from conftest import SIGMA5
+from oracle import c_oracle as co
+from oracle import fem_oracle as fo
+from oracle import metrics_oracle as mo
+from pelvistim_fem_b200 import meshgen
+
+
+@pytest.mark.parametrize("jitter", [0.0, 0.3])
+def test_step01_analytic_exact(jitter):
+    # test_step01_baseline.py:59-104: phi = z/Lz, J = (0,0,-sigma/Lz) at every node; published:
+    # mean|J| 10.000000, CV 8.5e-16, R^2 1.0000000, slope 50.0000 (step01_summary.png)
+    m = meshgen.box_mesh(0.04, 0.04, 0.02, 10, 10, 5, jitter=jitter, seed=3, ids=(2, 1, 3))
+    res = fo.solve_case(m, {1: 0.2}, [(2, 1.0), (1, 0.0)], [], recover="l2")
+    assert np.abs(res["phi"] - m.nodes[:, 2] / 0.02).max() < 1e-12
+    assert np.abs(res["J"] - np.array([0, 0, -10.0])).max() < 1e-9
+    met = mo.step01_metrics(m.nodes, res["phi"], res["J"])
+    assert met["rel_J"] < 1e-3 and met["cv_J"] < 1e-2 and met["r2"] > 0.9999 and met["flux_err"] < 1e-2   # :22-25
+    assert abs(met["slope"] - 50.0) < 1e-9 and abs(met["mean_J"] - 10.0) < 1e-9
+
+
+def test_pattern_and_matrix_properties():
+    m = meshgen.synth_slab("XS")
+    rowptr, col = fo.csr_pattern(m.nn, m.tets)
+    K = fo.assemble_stiffness(m.nodes, m.tets, m.region, SIGMA5)
+    assert np.array_equal(K.indptr, rowptr) and np.array_equal(K.indices, col)
+    for i in range(m.nn):                                     # sorted, diagonal present
+        c = col[rowptr[i]:rowptr[i + 1]]
+        assert np.all(np.diff(c) > 0) and i in c
+    assert abs(K - K.T).max() < 1e-15 * abs(K).max() * 10
+    assert np.abs(K @ np.ones(m.nn)).max() < 1e-12 * abs(K).max()   # constants are in the null space
+    M = fo.assemble_mass(m.nodes, m.tets)
+    vol, _ = fo.tet_geometry(m.nodes, m.tets)
+    assert abs(M.sum() - vol.sum()) < 1e-15 * m.nn
+
+
+def test_kcl_and_series_resistance_law():
+    # weak-form reaction at the Dirichlet electrode = injected current (exact KCL); and the step04 law
+    # compliance(sigma_c) ~ c0 + 2 t_c I / (sigma_c A) extracted from step04 summary.csv
+    m = meshgen.synth_slab("XS")
+    areas = meshgen.tri_areas(m.nodes, m.tris)
+    A = areas[m.bcid == 101].sum()
+    I = 5e-3
+    comp = []
+    for sc in (5e-5, 5e-3):
+        sig = dict(SIGMA5)
+        sig[4] = sig[5] = sc
+        r = fo.solve_case(m, sig, [(102, 0.0)], [(101, I / A)], recover=None)
+        react = (r["K_raw"] @ r["phi"] - r["b_neumann"])
+        nodes102 = np.unique(m.tris[m.bcid == 102])
+        assert abs(react[nodes102].sum() + I) < 1e-9 * I * 100
+        top = np.unique(m.tris[m.bcid == 101])
+        comp.append(r["phi"][top].mean())
+    slope = (comp[0] - comp[1]) / (1 / 5e-5 - 1 / 5e-3)
+    assert abs(slope - 2 * 0.0005 * I / A) / (2 * 0.0005 * I / A) < 0.05
+
+
+def test_c_oracle_matches_numpy_oracle():
+    m = meshgen.synth_slab("XS")
+    ref = fo.solve_case(m, SIGMA5, [(102, 0.0)], [(101, 15.975)], recover=None)
+    cs = co.CSystem(m, SIGMA5, [(102, 0.0)], [(101, 15.975)])
+    rp, col = fo.csr_pattern(m.nn, m.tets)
+    assert np.array_equal(cs.rowptr, rp) and np.array_equal(cs.col, col)
+    assert np.abs(cs.val_raw - ref["K_raw"].data).max() <= 4e-15 * np.abs(ref["K_raw"].data).max()
+    Kc = sp.csr_matrix((cs.val, cs.col, cs.rowptr), shape=(m.nn, m.nn))
+    assert abs(Kc - ref["K"]).max() <= 1e-14 * abs(ref["K"]).max()
+    assert np.abs(cs.b - ref["b"]).max() <= 1e-15
+    x, it, rel = cs.pcg(1e-12)
+    assert rel <= 1e-12 and np.abs(x - ref["phi"]).max() <= 1e-9 * np.abs(ref["phi"]).max()
+    v = np.random.default_rng(0).standard_normal(m.nn)
+    assert np.abs(cs.spmv(v) - ref["K"] @ v).max() <= 1e-13 * np.abs(ref["K"] @ v).max()
+
+
+def test_numpy_pcg_matches_direct():
+    m = meshgen.synth_slab("XS")
+    ref = fo.solve_case(m, SIGMA5, [(102, 0.0)], [(101, 15.975)], recover=None)
+    x, it = fo.jacobi_pcg(ref["K"], ref["b"], rtol=1e-12)
+    assert np.abs(x - ref["phi"]).max() < 1e-9 * np.abs(ref["phi"]).max()
+
+
+def test_recovery_variants_on_linear_field():
+    # every recovery must reproduce a constant J exactly
+    m = meshgen.box_mesh(0.04, 0.04, 0.02, 6, 6, 4, jitter=0.25, seed=1)
+    phi = 3.0 * m.nodes[:, 0] - 2.0 * m.nodes[:, 1] + 5.0 * m.nodes[:, 2]
+    for method in ("l2", "lumped", "average"):
+        J = fo.recover_nodal_current(m.nodes, m.tets, m.region, {1: 0.5}, phi, method)
+        assert np.abs(J - (-0.5) * np.array([3.0, -2.0, 5.0])).max() < 1e-11
+
+
+def test_metrics_hand_cases():
+    # one tet + one boundary triangle: VTK-style cell averaging and centre gradients by hand
+    pts = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1.0]])
+    tets = np.array([[0, 1, 2, 3]], dtype=np.int32)
+    tris = np.array([[0, 1, 2]], dtype=np.int32)
+    phi = np.array([0.0, 1.0, 2.0, 3.0])
+    J = np.tile(np.array([0.0, 0.0, -2.0]), (4, 1))
+    Jm, Em, cen = mo.cell_fields(pts, tets, tris, phi, J)
+    assert np.allclose(Jm, 2.0) and np.allclose(cen[0], [0.25, 0.25, 0.25]) and np.allclose(cen[1], [1 / 3, 1 / 3, 0])
+    # smoothed point values: nodes 0..2 belong to tet (mean 1.5) and tri (mean 1.0) -> 1.25 ; node 3 -> 1.5
+    ps = np.array([1.25, 1.25, 1.25, 1.5])
+    assert np.isclose(Em[0], abs(ps[3] - ps[0])) and np.isclose(Em[1], 0.0)
+    Ia, Ir, ferr, Ias, Irs = mo.injected_current(pts, tris, J, (1 / 3, 1 / 3), (1 / 3, 1 / 3), 1.0, 0.0, 0.0)
+    assert np.isclose(Ias, -2.0 * 0.5)
+
+
+def test_layered_oracle_vs_golden_table(golden):
+    # step03 summary row (t_fat 5 mm, r 10 mm): mesh-dependent golden; the built-in mesh must agree
+    # to discretisation accuracy on the mesh-insensitive columns (few %)
+    import run_layered_sweep as s3
+    import tempfile
+    from pathlib import Path
+    from pelvistim_fem_b200 import pipeline, sif
+    p = s3.load_params()
+    with tempfile.TemporaryDirectory() as d:
+        mesh, e1, e2, bi = s3.build_mesh(p, 0.005, 0.010, Path(d) / "c", coarse=False)
+        e1id, e2id, Aa, Ar = pipeline.detect_elec_bc_ids(mesh, e1, e2, e1[2], e2[2])
+        jn = s3.write_sif(Path(d) / "c", e1id, e2id, p, 0.010, bi, elec_area_mesh=Aa)
+        prob = sif.problem_from_sif((Path(d) / "c" / "case.sif").read_text())
+    assert (e1id, e2id) == (101, 102)
+    ref = fo.solve_case(mesh, prob.sigma_by_body, prob.dirichlet, prob.neumann, recover="l2")
+    row = mo.layered_row(mesh.nodes, mesh.tets, mesh.tris, ref["phi"], ref["J"], p, 0.005, 0.010, e1, e2, bi, jn_used=jn,
+                         elec_area_mesh=Aa, return_area_mesh=Ar, e1_id=e1id, e2_id=e2id)
+    gold = [r for r in json.load(open(golden / "step03_summary.json")) if r["t_fat_mm"] == 5.0 and r["elec_r_mm"] == 10.0][0]
+    assert list(row.keys()) == list(gold.keys())                       # 36 columns, same order
+    for k, tol in (("compliance_V", 0.08), ("roi_mean_J", 0.08), ("roi_mean_E", 0.08), ("elec_area_mesh_cm2", 0.03)):
+        assert abs(row[k] - gold[k]) / abs(gold[k]) < tol, (k, row[k], gold[k])
+    for k in ("elec_shape", "contact_enabled", "control_mode", "roi_layer", "roi_center_z_mm", "dist_fat_muscle_mm",
+              "active_boundary_id_used", "return_boundary_id_used", "elec_area_cm2", "t_fat_mm", "elec_r_mm"):
+        assert row[k] == gold[k], k
+    # weak-form KCL is exact even though the nodal-J pad integral is not (run_layered_sweep.py README note)
+    react = ref["K_raw"] @ ref["phi"] - ref["b_neumann"]
+    I_in = prob.neumann[0][1] * Aa            # the SIF holds Jn with 7 significant digits
+    assert abs(react[np.unique(mesh.tris[mesh.bcid == 102])].sum() + I_in) < 1e-12
+
+
+def test_step04_series_law_from_golden(golden):
+    # the law extracted from the reference's own table: compliance_V(sigma_c) - compliance_V(p15) ~ 2 t_c I/(sigma_c A)
+    rows = json.load(open(golden / "step04_summary.json"))
+    A, I, tc = 3.1299e-4, 5e-3, 0.5e-3
+    base = rows[-1]["compliance_V"] - 2 * tc * I / (rows[-1]["sigma_contact_Spm"] * A)
+    for r in rows:
+        pred = base + 2 * tc * I / (r["sigma_contact_Spm"] * A)
+        assert -0.04 < (pred - r["compliance_V"]) / r["compliance_V"] < 0.005
