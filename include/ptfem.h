@@ -57,12 +57,13 @@ typedef struct ptfem_solve_opts {
   int32_t maxit;        /* iteration cap (per system) */
   int32_t check_every;  /* residual is copied to the host every this many iterations */
   int32_t cheb_degree;  /* polynomial degree for PTFEM_PRECOND_CHEBYSHEV */
-  double rtol;          /* stop when ||r||_2 <= rtol * ||b||_2 for every system */
+  double rtol;          /* stop when ||b - A x||_2 <= rtol * ||b||_2 for every system (default 1e-10), or when
+                           residual replacement shows the round-off floor has been reached (still < 1e-8) */
   double cheb_ratio;    /* lambda_max / lambda_min assumed by the Chebyshev polynomial */
   int32_t spmv_variant; /* PTFEM_SPMV_* */
   int32_t use_graph;    /* capture check_every iterations in a CUDA graph */
   int32_t warm_start;   /* 0: start from phi = 0; 1: start from the solution already on the device */
-  int32_t reserved_;
+  int32_t sample_spmv;  /* >0: after the solve, time this many launches of the solve's SpMV kernel (stats.spmv_ms) */
 } ptfem_solve_opts;
 
 typedef struct ptfem_solve_stats {

@@ -316,12 +316,12 @@ void ptfem_solve_opts_default(ptfem_solve_opts* o) {
   o->maxit = 200000;
   o->check_every = 50;
   o->cheb_degree = 4;
-  o->rtol = 1e-12;
+  o->rtol = 1e-10;
   o->cheb_ratio = 30.0;
   o->spmv_variant = PTFEM_SPMV_AUTO;
   o->use_graph = 1;
   o->warm_start = 0;
-  o->reserved_ = 0;
+  o->sample_spmv = 0;
 }
 
 int ptfem_solve_device(ptfem_mesh* m, const ptfem_solve_opts* opts, ptfem_solve_stats* stats) {

@@ -267,7 +267,7 @@ __host__ __device__ inline size_t stream_smem_bytes(int stages, int cap) { retur
 // Tile t = rows [t*R, (t+1)*R), R <= 128 chosen at pattern time so that every tile's non-zeros fit a
 // stage.  TPR lanes share a row (CTA = 128*TPR threads); STAGES-1 tiles are in flight per CTA.
 // interleave = 1: CTAs sweep the matrix together as one moving front (tile j of CTA b is b + j*grid).
-template <int STAGES, int TPR, bool DOT>
+template <int S, int STAGES, int TPR, bool DOT>
 __global__ void __launch_bounds__(kStreamThreads* TPR) spmv_stream_kernel(int64_t nn, const int32_t* __restrict__ rowptr,
                                                                           const int32_t* __restrict__ col,
                                                                           const double* __restrict__ val, int32_t R,
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(kStreamThreads* TPR) spmv_stream_kernel(int64_
   double* const s_val = reinterpret_cast<double*>(smem_raw);                                    // [STAGES][cap]
   int32_t* const s_col = reinterpret_cast<int32_t*>(smem_raw + (size_t)STAGES * cap * 8);        // [STAGES][cap]
   uint64_t* const s_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * cap * 12);    // [STAGES]
-  __shared__ double s_red[kStreamThreads * TPR];
+  __shared__ double s_red[DOT ? kStreamThreads * TPR : 1];
   const int tid = threadIdx.x;
   const int lane = tid % TPR, rloc = tid / TPR;
   const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
@@ -316,7 +316,9 @@ __global__ void __launch_bounds__(kStreamThreads* TPR) spmv_stream_kernel(int64_
     for (int s = 0; s < STAGES - 1; ++s)
       if (t_begin + s < t_end) issue(t_begin + s, s);
   }
-  double dot = 0.0;
+  double dot[S];
+#pragma unroll
+  for (int s = 0; s < S; ++s) dot[s] = 0.0;
   uint32_t phase_bits = 0;
   int st = 0;
   for (int64_t t = t_begin; t < t_end; ++t) {
@@ -337,27 +339,42 @@ __global__ void __launch_bounds__(kStreamThreads* TPR) spmv_stream_kernel(int64_
     phase_bits ^= 1u << st;
     const double* sv = s_val + (size_t)st * cap;
     const int32_t* sc = s_col + (size_t)st * cap;
-    double acc = 0.0;
-#pragma unroll 4
-    for (int32_t k = b - a0 + lane; k < e - a0; k += TPR) acc = fma(sv[k], ldg_f64_hint(x + sc[k], pol_keep), acc);
+    double acc[S];
 #pragma unroll
-    for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    for (int s = 0; s < S; ++s) acc[s] = 0.0;
+#pragma unroll 4
+    for (int32_t k = b - a0 + lane; k < e - a0; k += TPR) {
+      const double a = sv[k];
+      double xv[S];
+      load_sys_hint<S>(x + (int64_t)sc[k] * S, xv, pol_keep);
+#pragma unroll
+      for (int s = 0; s < S; ++s) acc[s] = fma(a, xv[s], acc[s]);
+    }
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], o);
+    }
     if (live && lane == 0) {
-      y[r] = acc;
-      if constexpr (DOT) dot = fma(acc, ldg_f64_hint(x + r, pol_keep), dot);
+      store_sys<S>(y + r * S, acc);
+      if constexpr (DOT) {
+        double xr[S];
+        load_sys_hint<S>(x + r * S, xr, pol_keep);
+#pragma unroll
+        for (int s = 0; s < S; ++s) dot[s] = fma(acc[s], xr[s], dot[s]);
+      }
     }
     __syncthreads();  // stage st may be refilled
     st = (st + 1) % STAGES;
   }
   if constexpr (DOT) {
-    double d1[1] = {dot};
-    block_sum<1>(d1, s_red, partial + blockIdx.x);
+    block_sum<S>(dot, s_red, partial + (size_t)blockIdx.x * S);
     if (is_last_block(ticket)) {
-      const double pq = sum_partials<1>(partial, gridDim.x, s_red);
-      if (tid == 0) {
-        const double rho = scal[SC_RHO * kMaxSys];
-        scal[SC_PQ * kMaxSys] = pq;
-        scal[SC_ALPHA * kMaxSys] = pq > 0.0 ? rho / pq : 0.0;
+      const double pq = sum_partials<S>(partial, gridDim.x, s_red);
+      if (tid < S) {
+        const double rho = scal[SC_RHO * kMaxSys + tid];
+        scal[SC_PQ * kMaxSys + tid] = pq;
+        scal[SC_ALPHA * kMaxSys + tid] = pq > 0.0 ? rho / pq : 0.0;
       }
     }
   }
@@ -660,14 +677,14 @@ int launch_vector(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y, P
   return PTFEM_OK;
 }
 
-template <int STAGES, int TPR, bool DOT>
+template <int S, int STAGES, int TPR, bool DOT>
 int launch_stream_t(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y, PcgWork* w) {
   const size_t smem = stream_smem_bytes(STAGES, A.stream_cap);
   {
-    const void* fn = reinterpret_cast<const void*>(&spmv_stream_kernel<STAGES, TPR, DOT>);
+    const void* fn = reinterpret_cast<const void*>(&spmv_stream_kernel<S, STAGES, TPR, DOT>);
     auto it = ctx->func_smem.find(fn);
     if (it == ctx->func_smem.end() || it->second < smem) {
-      PT_CK(cudaFuncSetAttribute(spmv_stream_kernel<STAGES, TPR, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PT_CK(cudaFuncSetAttribute(spmv_stream_kernel<S, STAGES, TPR, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       ctx->func_smem[fn] = smem;
     }
   }
@@ -683,36 +700,31 @@ int launch_stream_t(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y,
   if (grid < 1) grid = 1;
   const int64_t per_cta = (ntiles + grid - 1) / grid;
   if (!ctx->tune_interleave) grid = (ntiles + per_cta - 1) / per_cta;
-  spmv_stream_kernel<STAGES, TPR, DOT><<<(int)grid, threads, smem, ctx->stream>>>(
+  spmv_stream_kernel<S, STAGES, TPR, DOT><<<(int)grid, threads, smem, ctx->stream>>>(
       A.nn, A.rowptr, A.col, A.val, A.stream_rows, A.stream_cap, (int32_t)ntiles, (int32_t)per_cta, ctx->tune_interleave, x,
       y, w ? w->partial.p : nullptr, w ? w->scal.p : nullptr, w ? w->ticket.p : nullptr);
   PT_LAUNCH_CHECK(ctx);
   return PTFEM_OK;
 }
 
-template <int STAGES, bool DOT>
-int launch_stream_s(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y, PcgWork* w, int tpr) {
-  switch (tpr) {
-    case 2: return launch_stream_t<STAGES, 2, DOT>(ctx, A, x, y, w);
-    case 4: return launch_stream_t<STAGES, 4, DOT>(ctx, A, x, y, w);
-    case 8: return launch_stream_t<STAGES, 8, DOT>(ctx, A, x, y, w);
-    default: return launch_stream_t<STAGES, 1, DOT>(ctx, A, x, y, w);
-  }
-}
-template <bool DOT>
+// S == 1 exposes the tuning knobs (stages 2/3, 1 or 2 lanes per row); multi-RHS uses the measured best
+template <int S, bool DOT>
 int launch_stream(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y, PcgWork* w, int stages, int tpr) {
-  if (stages == 3) return launch_stream_s<3, DOT>(ctx, A, x, y, w, tpr);
-  if (stages >= 4) return launch_stream_s<4, DOT>(ctx, A, x, y, w, tpr);
-  return launch_stream_s<2, DOT>(ctx, A, x, y, w, tpr);
+  if constexpr (S == 1) {
+    if (stages >= 3) return tpr == 2 ? launch_stream_t<1, 3, 2, DOT>(ctx, A, x, y, w) : launch_stream_t<1, 3, 1, DOT>(ctx, A, x, y, w);
+    return tpr == 2 ? launch_stream_t<1, 2, 2, DOT>(ctx, A, x, y, w) : launch_stream_t<1, 2, 1, DOT>(ctx, A, x, y, w);
+  } else {
+    return launch_stream_t<S, 2, 1, DOT>(ctx, A, x, y, w);
+  }
 }
 
 template <int S, int VS>
 int spmv_sv(ptfem_ctx* ctx, const LinSys& A, int variant, const double* x, double* y, PcgWork* w, bool dot) {
-  if constexpr (S == 1) {
+  if constexpr (VS == 1) {
     if (variant == PTFEM_SPMV_STREAM || variant == PTFEM_SPMV_STREAM1) {
       const int stages = variant == PTFEM_SPMV_STREAM ? ctx->tune_stream_stages : ctx->tune_stream_stages + 1;
-      return dot ? launch_stream<true>(ctx, A, x, y, w, stages, ctx->tune_stream_tpr)
-                 : launch_stream<false>(ctx, A, x, y, w, stages, ctx->tune_stream_tpr);
+      return dot ? launch_stream<S, true>(ctx, A, x, y, w, stages, ctx->tune_stream_tpr)
+                 : launch_stream<S, false>(ctx, A, x, y, w, stages, ctx->tune_stream_tpr);
     }
   }
   return dot ? launch_vector<S, VS, true>(ctx, A, x, y, w) : launch_vector<S, VS, false>(ctx, A, x, y, w);
@@ -738,7 +750,7 @@ int ptfem_stream_threads() { return kStreamThreads; }
 namespace ptfem {
 
 int resolve_variant(const LinSys& A, int variant) {
-  const bool stream_ok = A.S == 1 && A.stream_rows > 0 && A.row0 == 0;
+  const bool stream_ok = A.VS == 1 && A.stream_rows > 0 && A.row0 == 0;
   if (variant == PTFEM_SPMV_AUTO) return stream_ok && A.nnz >= (int64_t)1 << 20 ? PTFEM_SPMV_STREAM : PTFEM_SPMV_VECTOR;
   if ((variant == PTFEM_SPMV_STREAM || variant == PTFEM_SPMV_STREAM1) && !stream_ok) return PTFEM_SPMV_VECTOR;
   return variant;
@@ -900,8 +912,10 @@ int pcg_solve_t(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_o
   int it = 0;
   bool converged = false;
   double rel = 0.0;
-  const int max_restarts = 3;
+  const int max_restarts = 5;
   int restarts = 0;
+  bool stagnated = false;
+  double prev_true2 = INFINITY;
   int rc = PTFEM_OK;
 
   auto read_scal = [&]() -> int {
@@ -933,6 +947,11 @@ int pcg_solve_t(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_o
       converged = true;
       break;
     }
+    if (restarts > 0 && w2 >= 0.25 * prev_true2) {
+      stagnated = true;
+      break;
+    }
+    prev_true2 = w2;
     // iterate in chunks of `check`
     bool chunk_conv = false;
     while (it < o.maxit) {
@@ -996,7 +1015,8 @@ int pcg_solve_t(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_o
     }
     if (rc) break;
     if (!chunk_conv) break;  // maxit
-    // recurrence says converged: confirm on the true residual (restart replaces the residual)
+    // recurrence says converged: confirm on the true residual (the restart replaces the residual);
+    // if a restart no longer lowers the true residual the attainable accuracy has been reached
     if (restarts >= max_restarts) break;
     ++restarts;
   }
@@ -1017,7 +1037,26 @@ int pcg_solve_t(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_o
   PT_LAUNCH_CHECK(ctx);
   PT_TRY(read_scal());
   const double true_rel = sqrt(worst_rel2());
-  if (!converged && it < o.maxit && true_rel <= 10.0 * o.rtol) converged = true;  // stagnated at round-off
+  // optional: device time of the SpMV kernel this solve used (same variant, fused dot), for roofline reports
+  double spmv_ms = 0.0;
+  if (o.sample_spmv > 0) {
+    cudaEvent_t s0, s1;
+    PT_CK(cudaEventCreate(&s0));
+    PT_CK(cudaEventCreate(&s1));
+    PT_CK(cudaEventRecord(s0, ctx->stream));
+    for (int k = 0; k < o.sample_spmv; ++k) PT_TRY((spmv_sv<S, VS>(ctx, A, variant, w.p.p, w.q.p, &w, true)));
+    PT_CK(cudaEventRecord(s1, ctx->stream));
+    PT_CK(cudaEventSynchronize(s1));
+    float t = 0.f;
+    cudaEventElapsedTime(&t, s0, s1);
+    cudaEventDestroy(s0);
+    cudaEventDestroy(s1);
+    spmv_ms = (double)t / o.sample_spmv;
+    spmv_calls += o.sample_spmv;
+  }
+  // attainable accuracy: the true residual stopped improving under residual replacement (round-off floor of
+  // ||A|| ||x|| eps / ||b||); accepted when it is still small in absolute terms
+  if (!converged && stagnated && true_rel <= 1e-8) converged = true;
   if (st) {
     st->iterations = it;
     st->converged = converged ? 1 : 0;
@@ -1026,7 +1065,7 @@ int pcg_solve_t(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_o
     st->rel_residual = rel;
     st->true_rel_residual = true_rel;
     st->solve_ms = ms;
-    st->spmv_ms = 0.0;
+    st->spmv_ms = spmv_ms;
   }
   if (!converged)
     return set_err(PTFEM_ERR_NOCONV, "PCG did not reach rtol=%g in %d iterations (rel. residual %.3e)", o.rtol, it, true_rel);

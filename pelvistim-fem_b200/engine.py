@@ -33,7 +33,7 @@ class PtfemError(RuntimeError):
 class SolveOpts(C.Structure):
     _fields_ = [("precond", C.c_int32), ("maxit", C.c_int32), ("check_every", C.c_int32),
                 ("cheb_degree", C.c_int32), ("rtol", C.c_double), ("cheb_ratio", C.c_double),
-                ("spmv_variant", C.c_int32), ("use_graph", C.c_int32), ("warm_start", C.c_int32), ("reserved_", C.c_int32)]
+                ("spmv_variant", C.c_int32), ("use_graph", C.c_int32), ("warm_start", C.c_int32), ("sample_spmv", C.c_int32)]
 
 
 class SolveStats(C.Structure):

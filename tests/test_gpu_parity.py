@@ -1,0 +1,367 @@
+"""GPU parity tests (run on the B200 with ``-m gpu``): everything goes through the C-ABI of libptfem.so
+(via ``engine``) and is compared with the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): CSR pattern bit-exact; node potentials within 1e-6 relative; field /
+current / metric values within 1e-4 relative.  The tolerances are written where they are used."""
+import json
+import math
+
+import numpy as np
+import pytest
+
+import pelvistim_fem_b200  # noqa: F401
+from conftest import SIGMA5
+from oracle import fem_oracle as fo
+from oracle import metrics_oracle as mo
+from pelvistim_fem_b200 import engine, meshgen, pipeline, sif
+
+pytestmark = pytest.mark.gpu
+
+TOL_PHI = 1e-6      # node potentials, relative to max |phi|
+TOL_FIELD = 1e-4    # E, J, metrics
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300))
+
+
+def dm_for(ctx, m):
+    return ctx.mesh(m.nodes, m.tets, m.region, m.tris, m.bcid)
+
+
+# -- K1 ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mesh_fn", [lambda: meshgen.box_mesh(nx=4, ny=3, nz=2), lambda: meshgen.synth_slab("XS"),
+                                     lambda: meshgen.synth_slab("S"),
+                                     lambda: meshgen.electrode_box_mesh(0.15, 0.15, 0.05, (0.045, 0.075), (0.105, 0.075), 0.01, "circle", nz=4)])
+def test_pattern_bit_exact(gpu_ctx, mesh_fn):
+    m = mesh_fn()
+    # shuffle node numbering: the canonical pattern must not rely on structured ordering
+    perm = np.random.default_rng(5).permutation(m.nn)
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(m.nn)
+    nodes, tets, tris = m.nodes[perm], inv[m.tets].astype(np.int32), inv[m.tris].astype(np.int32)
+    dm = gpu_ctx.mesh(nodes, tets, m.region, tris, m.bcid)
+    rowptr, col = dm.get_pattern()
+    rp, cc = fo.csr_pattern(m.nn, tets)
+    assert rowptr.dtype == np.int32 and col.dtype == np.int32
+    assert np.array_equal(rowptr, rp) and np.array_equal(col, cc)           # bit-exact
+    e2 = dm.get_e2nnz()
+    i = np.repeat(tets, 4, axis=1).ravel()
+    j = np.tile(tets, (1, 4)).ravel()
+    k = e2.ravel()
+    assert np.array_equal(col[k], j) and np.all((rowptr[i] <= k) & (k < rowptr[i + 1]))
+    dm.close()
+
+
+def test_pattern_with_unreferenced_node_and_no_boundary(gpu_ctx):
+    m = meshgen.box_mesh(nx=2, ny=2, nz=2)
+    nodes = np.vstack([m.nodes, [[9.0, 9.0, 9.0]]])                     # node without tets
+    dm = gpu_ctx.mesh(nodes, m.tets, m.region, np.zeros((0, 3), np.int32), np.zeros(0, np.int32))
+    rowptr, col = dm.get_pattern()
+    rp, cc = fo.csr_pattern(nodes.shape[0], m.tets)
+    assert np.array_equal(rowptr, rp) and np.array_equal(col, cc)
+    dm.close()
+
+
+def test_bad_inputs_raise(gpu_ctx):
+    m = meshgen.box_mesh(nx=2, ny=2, nz=2)
+    bad = m.tets.copy()
+    bad[0, 0] = m.nn + 3
+    with pytest.raises(engine.PtfemError):
+        gpu_ctx.mesh(m.nodes, bad, m.region, m.tris, m.bcid)
+    dm = dm_for(gpu_ctx, m)
+    with pytest.raises(engine.PtfemError):          # body 1 has no conductivity
+        dm.assemble({7: 1.0})
+    with pytest.raises(engine.PtfemError):          # non-positive conductivity
+        dm.assemble({1: 0.0})
+    dm.assemble({1: 0.2})
+    with pytest.raises(engine.PtfemError):          # solve before BCs
+        dm.solve()
+    flat = m.nodes.copy()
+    flat[:, 2] = 0.0
+    with pytest.raises(engine.PtfemError):          # degenerate tets
+        gpu_ctx.mesh(flat, m.tets, m.region, m.tris, m.bcid).pattern()
+    dm.close()
+
+
+# -- K2-K4 ---------------------------------------------------------------------------------------------
+def test_assembly_and_bc_match_oracle(gpu_ctx):
+    m = meshgen.synth_slab("S")
+    ref = fo.solve_case(m, SIGMA5, [(102, 0.0)], [(101, 15.975)], recover=None)
+    dm = dm_for(gpu_ctx, m)
+    dm.assemble(SIGMA5).bc_reset(1).neumann(101, 15.975).dirichlet(102, 0.0)
+    val = dm.get_values(0, False)
+    scale = np.abs(ref["K_raw"].data).max()
+    assert np.abs(val - ref["K_raw"].data).max() <= 1e-14 * scale
+    import scipy.sparse as sp
+    rowptr, col = dm.get_pattern()
+    Kbc = sp.csr_matrix((dm.get_values(0, True), col, rowptr), shape=(m.nn, m.nn))
+    assert abs(Kbc - ref["K"]).max() <= 1e-14 * scale
+    assert np.abs(dm.get_rhs(0) - ref["b"]).max() <= 1e-14 * np.abs(ref["b"]).max()
+    # run-to-run bit reproducibility of the atomics-free assembly
+    dm.assemble(SIGMA5)
+    assert np.array_equal(dm.get_values(0, False), val)
+    dm.close()
+
+
+# -- step01: analytic known answer (test_step01_baseline.py:59-104) --------------------------------------
+@pytest.mark.parametrize("precond", [engine.PRECOND_JACOBI, engine.PRECOND_CHEBYSHEV])
+def test_step01_analytic(gpu_ctx, precond):
+    m = meshgen.box_mesh(0.04, 0.04, 0.02, 10, 10, 5, jitter=0.3, seed=3, ids=(2, 1, 3))
+    res = engine.solve_case(gpu_ctx, m, {1: 0.2}, [(2, 1.0), (1, 0.0)], [], recover="l2", precond=precond, rtol=1e-13)
+    assert np.abs(res["phi"] - m.nodes[:, 2] / 0.02).max() < 1e-10
+    assert np.abs(res["J"] - np.array([0.0, 0.0, -10.0])).max() < 1e-8
+    case = pipeline.SolvedCase(m, res["dmesh"], res["phi"], res["J"], res["stats"])
+    got = pipeline.step01_metrics(case)
+    want = mo.step01_metrics(m.nodes, res["phi"], res["J"])
+    assert got["rel_J"] < 1e-3 and got["cv_J"] < 1e-2 and got["r2"] > 0.9999 and got["flux_err"] < 1e-2   # :22-25
+    for k in ("mean_J", "slope", "flux_top", "flux_bot", "phi_min", "phi_max"):
+        assert abs(got[k] - want[k]) <= TOL_FIELD * max(abs(want[k]), 1e-12), k
+    res["dmesh"].close()
+
+
+# -- step02/03/04-like solves ---------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", [engine.SPMV_VECTOR, engine.SPMV_STREAM, engine.SPMV_STREAM1])
+@pytest.mark.parametrize("size", ["XS", "S"])
+def test_layered_solve_matches_oracle(gpu_ctx, size, variant):
+    m = meshgen.synth_slab(size)
+    ref = fo.solve_case(m, SIGMA5, [(102, 0.0)], [(101, 15.975)], recover="l2")
+    res = engine.solve_case(gpu_ctx, m, SIGMA5, [(102, 0.0)], [(101, 15.975)], recover="l2", spmv_variant=variant)
+    assert res["stats"]["converged"] == 1 and res["stats"]["true_rel_residual"] < 1e-9
+    assert rel(res["phi"], ref["phi"]) < TOL_PHI
+    assert rel(res["J"], ref["J"]) < TOL_FIELD
+    E, Je = res["dmesh"].element_fields(0)
+    Er, Jr, _ = fo.element_fields(m.nodes, m.tets, m.region, SIGMA5, ref["phi"])
+    assert rel(E, Er) < TOL_FIELD and rel(Je, Jr) < TOL_FIELD
+    for method in ("lumped", "average"):
+        Jm = res["dmesh"].recover_current(0, method)
+        assert rel(Jm, fo.recover_nodal_current(m.nodes, m.tets, m.region, SIGMA5, ref["phi"], method)) < TOL_FIELD
+    # weak-form KCL (exact): reaction at the return electrode = -injected current
+    A = meshgen.tri_areas(m.nodes, m.tris)[m.bcid == 101].sum()
+    assert abs(res["dmesh"].metric_reaction(102) + 15.975 * A) < 1e-8 * 15.975 * A
+    res["dmesh"].close()
+
+
+def test_voltage_mode_electrode_box(gpu_ctx):
+    # step02: two Dirichlet patches on the top face, sigma 0.2 (run_sweep.py:39-45,197-272)
+    m = meshgen.electrode_box_mesh(0.15, 0.15, 0.05, (0.045, 0.075), (0.105, 0.075), 0.010, "circle", h_elec=0.006, h_bulk=0.02)
+    ref = fo.solve_case(m, {1: 0.2}, [(101, 1.0), (102, 0.0)], [], recover="l2")
+    res = engine.solve_case(gpu_ctx, m, {1: 0.2}, [(101, 1.0), (102, 0.0)], [], recover="l2")
+    assert rel(res["phi"], ref["phi"]) < TOL_PHI and rel(res["J"], ref["J"]) < TOL_FIELD
+    assert res["phi"].min() > -1e-9 and res["phi"].max() < 1 + 1e-9          # smoke_test.py:104
+    case = pipeline.SolvedCase(m, res["dmesh"], res["phi"], res["J"], res["stats"])
+    peak, mean, n = pipeline.extract_top_J(case, 0.05)
+    wp, wm, wn = mo.top_face_J(m.nodes, ref["J"], 0.05)
+    assert n == wn and abs(peak - wp) < TOL_FIELD * wp and abs(mean - wm) < TOL_FIELD * wm
+    res["dmesh"].close()
+
+
+def test_multi_rhs_matches_single_solves(gpu_ctx):
+    # electrode-position sweep on one matrix: Neumann patches as triangle lists, one Dirichlet return pad
+    m = meshgen.synth_slab("XS", interfaces_as_103=False)
+    cen = m.nodes[m.tris].mean(axis=1)
+    top = np.nonzero(np.isclose(cen[:, 2], 0.040) | (m.bcid == 101))[0]
+    dm = dm_for(gpu_ctx, m)
+    dm.assemble(SIGMA5).bc_reset(5)
+    patches = []
+    for k in range(5):
+        xc = 0.02 + 0.006 * k
+        sel = top[np.hypot(cen[top, 0] - xc, cen[top, 1] - 0.02) < 0.008].astype(np.int32)
+        assert sel.size > 0
+        patches.append(sel)
+        dm.neumann_tris(sel, 10.0 + k, rhs=k)
+    dm.dirichlet(102, 0.0)
+    phi = dm.solve()
+    assert phi.shape == (5, m.nn)
+    K_raw = fo.assemble_stiffness(m.nodes, m.tets, m.region, SIGMA5)
+    is_dir, val = fo.dirichlet_nodes(m.tris, m.bcid, [(102, 0.0)], m.nn)
+    area = meshgen.tri_areas(m.nodes, m.tris)
+    for k in range(5):
+        b = np.zeros(m.nn)
+        np.add.at(b, m.tris[patches[k]].ravel(), np.repeat((10.0 + k) * area[patches[k]] / 3.0, 3))
+        K, b2 = fo.apply_dirichlet_symmetric(K_raw, b, is_dir, val)
+        assert rel(phi[k], fo.solve_direct(K, b2)) < TOL_PHI
+        assert np.array_equal(dm.get_phi(k), phi[k])
+    dm.close()
+
+
+def test_batched_matrices_match_single_solves(gpu_ctx, golden):
+    # step04: 15 sigma_contact levels on one pattern (run_pressure_sweep.py:709-738)
+    import yaml
+    p = yaml.safe_load((golden / "step04_params.yaml").read_text())
+    levels = p["pressure_sweep"]["sigma_contact_Spm"]
+    assert len(levels) == 15
+    m = meshgen.synth_slab("XS")
+    dm = dm_for(gpu_ctx, m)
+    sigs = [{**SIGMA5, 4: s, 5: s} for s in levels]
+    dm.assemble(sigs).bc_reset(1).neumann(101, 15.975015).dirichlet(102, 0.0)
+    phi = dm.solve()
+    assert phi.shape == (15, m.nn) and dm.last_stats["converged"] == 1
+    for k in (0, 7, 14):
+        ref = fo.solve_case(m, sigs[k], [(102, 0.0)], [(101, 15.975015)], recover="l2")
+        assert rel(phi[k], ref["phi"]) < TOL_PHI
+        assert rel(dm.recover_current(k, "l2"), ref["J"]) < TOL_FIELD
+        assert np.abs(dm.get_values(k, False) - ref["K_raw"].data).max() <= 1e-14 * np.abs(ref["K_raw"].data).max()
+    dm.close()
+
+
+def test_warm_start_and_noconv(gpu_ctx):
+    m = meshgen.synth_slab("XS")
+    dm = dm_for(gpu_ctx, m)
+    dm.assemble(SIGMA5).bc_reset(1).neumann(101, 15.975).dirichlet(102, 0.0)
+    phi = dm.solve()[0]
+    it0 = dm.last_stats["iterations"]
+    dm.solve(warm_start=1)
+    assert dm.last_stats["iterations"] <= 50 < it0
+    with pytest.raises(engine.PtfemError) as ei:
+        dm.solve(maxit=5, check_every=5)
+    assert ei.value.code == engine.ERR_NOCONV
+    part = dm.solve(maxit=5, check_every=5, raise_on_noconv=False)[0]
+    assert np.isfinite(part).all() and rel(part, phi) > 1e-3
+    dm.close()
+
+
+def test_geometry_change_on_fixed_topology(gpu_ctx):
+    # node displacement keeps the pattern, re-values the matrix (compressed tissue: run_layered_sweep.py:329-340)
+    m = meshgen.synth_slab("XS")
+    dm = dm_for(gpu_ctx, m)
+    rp0, c0 = dm.get_pattern()
+    nodes2 = m.nodes.copy()
+    nodes2[:, 2] *= 0.9
+    dm.set_coords(nodes2)
+    dm.assemble(SIGMA5).bc_reset(1).neumann(101, 15.975).dirichlet(102, 0.0)
+    phi = dm.solve()[0]
+    rp1, c1 = dm.get_pattern()
+    assert np.array_equal(rp0, rp1) and np.array_equal(c0, c1)
+    m2 = meshgen.TetMesh(nodes2, m.tets, m.region, m.tris, m.bcid)
+    ref = fo.solve_case(m2, SIGMA5, [(102, 0.0)], [(101, 15.975)], recover=None)
+    assert rel(phi, ref["phi"]) < TOL_PHI
+    dm.close()
+
+
+# -- metrics rows (A9-A11) ---------------------------------------------------------------------------------
+def _layered_case(gpu_ctx, coarse=True):
+    import tempfile
+    from pathlib import Path
+    import run_layered_sweep as s3
+    p = s3.load_params()
+    with tempfile.TemporaryDirectory() as d:
+        mesh, e1, e2, bi = s3.build_mesh(p, 0.005, 0.010, Path(d) / "c", coarse=coarse)
+        e1id, e2id, Aa, Ar = pipeline.detect_elec_bc_ids(mesh, e1, e2, e1[2], e2[2])
+        jn = s3.write_sif(Path(d) / "c", e1id, e2id, p, 0.010, bi, elec_area_mesh=Aa)
+        (Path(d) / "c" / "results").mkdir()
+        case = pipeline.run_elmer_solver(Path(d) / "c", ctx=gpu_ctx, mesh=mesh)
+        from pelvistim_fem_b200 import vtu
+        v = vtu.read_vtu(Path(d) / "c" / "results" / "case_t0001.vtu")
+    return p, mesh, e1, e2, bi, (e1id, e2id, Aa, Ar), jn, case, v
+
+
+def test_step03_row_matches_oracle(gpu_ctx, golden):
+    p, mesh, e1, e2, bi, (e1id, e2id, Aa, Ar), jn, case, v = _layered_case(gpu_ctx)
+    assert np.array_equal(v["point_data"]["potential"], case.phi) and "volume current" in v["point_data"]
+    ref = fo.solve_case(mesh, case.problem.sigma_by_body, case.problem.dirichlet, case.problem.neumann, recover="l2")
+    assert rel(case.phi, ref["phi"]) < TOL_PHI and rel(case.J, ref["J"]) < TOL_FIELD
+    got = pipeline.extract_layered(case, p, 0.005, 0.010, e1, e2, bi, jn_used=jn, elec_area_mesh=Aa, return_area_mesh=Ar,
+                                   e1_id=e1id, e2_id=e2id, warn=lambda *a: None)
+    want = mo.layered_row(mesh.nodes, mesh.tets, mesh.tris, ref["phi"], ref["J"], p, 0.005, 0.010, e1, e2, bi, jn_used=jn,
+                          elec_area_mesh=Aa, return_area_mesh=Ar, e1_id=e1id, e2_id=e2id)
+    gold = json.load(open(golden / "step03_summary.json"))[0]
+    assert list(got.keys()) == list(want.keys()) == list(gold.keys())
+    for k in got:
+        a, b = got[k], want[k]
+        if isinstance(b, float) and not isinstance(b, bool):
+            assert (math.isnan(a) and math.isnan(b)) or abs(a - b) <= TOL_FIELD * max(abs(b), 1e-9) + 1e-8, (k, a, b)
+        else:
+            assert a == b, (k, a, b)
+    case.close()
+
+
+def test_step04_row_matches_oracle(gpu_ctx, golden):
+    import yaml
+    p4 = yaml.safe_load((golden / "step04_params.yaml").read_text())
+    _, mesh, e1, e2, bi, ids, jn, case, _ = _layered_case(gpu_ctx)
+    ref = fo.solve_case(mesh, case.problem.sigma_by_body, case.problem.dirichlet, case.problem.neumann, recover="l2")
+    got = pipeline.extract_pressure(case, p4, 0.005, "p08", e1, e2, bi, jn, warn=lambda *a: None)
+    want = mo.pressure_row(mesh.nodes, mesh.tets, mesh.tris, ref["phi"], ref["J"], p4, 0.005, "p08", e1, e2, bi, jn)
+    gold = json.load(open(golden / "step04_summary.json"))[0]
+    assert list(got.keys()) == list(want.keys()) == list(gold.keys())
+    for k in got:
+        a, b = got[k], want[k]
+        if isinstance(b, float) and not isinstance(b, bool):
+            assert abs(a - b) <= TOL_FIELD * max(abs(b), 1e-9) + 1e-8, (k, a, b)
+        else:
+            assert a == b, (k, a, b)
+    case.close()
+
+
+def test_roi_expansion_and_empty(gpu_ctx):
+    m = meshgen.synth_slab("XS")
+    res = engine.solve_case(gpu_ctx, m, SIGMA5, [(102, 0.0)], [(101, 15.975)], recover="l2")
+    dm = res["dmesh"]
+    for cen, r0 in (([0.015, 0.045, 0.03], 0.005), ([0.015, 0.045, 0.03], 0.0009), ([1.0, 1.0, 1.0], 0.001)):
+        mJ, mE, n, used, warn, _ = pipeline.eval_roi(dm, cen, r0)
+        wJ, wE, wn, wused, _, _ = mo.eval_roi(m.nodes, m.tets, m.tris, res["phi"], res["J"], cen, r0)
+        assert n == wn and abs(used - wused) < 1e-15
+        if wn:
+            assert abs(mJ - wJ) <= TOL_FIELD * wJ and abs(mE - wE) <= TOL_FIELD * wE
+        else:
+            assert math.isnan(mJ) and math.isnan(mE)
+    dm.close()
+
+
+# -- K13: polyline sampling + activating function (not in the reference; analytic checks) ---------------------
+def test_polyline_sampling(gpu_ctx):
+    m = meshgen.box_mesh(0.04, 0.04, 0.02, 8, 8, 4, jitter=0.2, seed=2, ids=(2, 1, 3))
+    res = engine.solve_case(gpu_ctx, m, {1: 0.2}, [(2, 1.0), (1, 0.0)], [], recover=None)
+    dm = res["dmesh"]
+    t = np.linspace(0.05, 0.95, 41)
+    pts = np.stack([0.005 + 0.03 * t, 0.01 + 0.02 * t, 0.02 * t], axis=1)
+    phi, af = dm.sample_polyline(pts)
+    assert np.abs(phi - pts[:, 2] / 0.02).max() < 1e-9            # linear field is interpolated exactly
+    assert np.abs(af[1:-1]).max() < 1e-3 and af[0] == 0.0 and af[-1] == 0.0
+    # a quadratic nodal field sampled along a mesh line of an unjittered grid: nodal values at the grid
+    # planes, and the second difference of q(z) = (z/Lz)^2 is 2/Lz^2 at the interior nodes
+    m2 = meshgen.box_mesh(0.04, 0.04, 0.02, 8, 8, 4, ids=(2, 1, 3))
+    dm2 = engine.solve_case(gpu_ctx, m2, {1: 0.2}, [(2, 1.0), (1, 0.0)], [], recover=None)["dmesh"]
+    dm2.set_phi((m2.nodes[:, 2] / 0.02) ** 2)
+    zline = np.stack([np.full(5, 0.02), np.full(5, 0.02), np.linspace(0.0, 0.02, 5)], axis=1)
+    phi2, af2 = dm2.sample_polyline(zline)
+    assert np.abs(phi2 - (zline[:, 2] / 0.02) ** 2).max() < 1e-12
+    assert np.abs(af2[1:-1] - 2.0 / 0.02 ** 2).max() < 1e-6 * (2.0 / 0.02 ** 2)
+    dm2.close()
+    out, _ = dm.sample_polyline(np.array([[1.0, 1.0, 1.0], [0.02, 0.02, 0.01]]))
+    assert math.isnan(out[0]) and math.isfinite(out[1])
+    dm.close()
+
+
+# -- full-size properties (BASELINE.json config: synthetic refined mesh) ----------------------------------------
+def test_large_mesh_properties(gpu_ctx):
+    m = meshgen.synth_slab("M")
+    dm = dm_for(gpu_ctx, m)
+    nnz = dm.pattern()
+    rowptr, col = dm.get_pattern()
+    assert rowptr[-1] == nnz and np.all(np.diff(rowptr) >= 1)
+    # sorted columns in every row, diagonal present, symmetric pattern (checksum of index pairs)
+    rows = np.repeat(np.arange(m.nn, dtype=np.int64), np.diff(rowptr))
+    same_row = rows[1:] == rows[:-1]
+    assert np.all(col[1:][same_row] > col[:-1][same_row])
+    assert int((col == rows).sum()) == m.nn
+    assert int((rows * 1000003 + col).sum()) == int((col.astype(np.int64) * 1000003 + rows).sum())
+    dm.assemble(SIGMA5).bc_reset(1).neumann(101, 15.975).dirichlet(102, 0.0)
+    rng = np.random.default_rng(1)
+    x, y = rng.standard_normal(m.nn), rng.standard_normal(m.nn)
+    outs = {}
+    for variant in (engine.SPMV_VECTOR, engine.SPMV_STREAM, engine.SPMV_STREAM1):
+        Ax, Ay, Axy = dm.spmv(x, 0, True, variant), dm.spmv(y, 0, True, variant), dm.spmv(2.0 * x - 3.0 * y, 0, True, variant)
+        assert rel(Axy, 2.0 * Ax - 3.0 * Ay) < 1e-12                      # linearity
+        assert abs(y @ Ax - x @ Ay) < 1e-10 * abs(y @ Ax)                 # symmetry
+        outs[variant] = Ax
+    assert rel(outs[engine.SPMV_STREAM], outs[engine.SPMV_VECTOR]) < 1e-13
+    raw = dm.spmv(np.ones(m.nn), 0, False, engine.SPMV_STREAM)
+    assert np.abs(raw).max() < 1e-12 * np.abs(dm.get_values(0)).max() * 30   # constants in the null space of K_raw
+    phi = dm.solve(rtol=1e-10)[0]
+    assert dm.last_stats["converged"] == 1 and dm.last_stats["true_rel_residual"] < 1e-9
+    A = meshgen.tri_areas(m.nodes, m.tris)[m.bcid == 101].sum()
+    assert abs(dm.metric_reaction(102) + 15.975 * A) < 1e-6 * 15.975 * A      # global current balance
+    assert phi.min() > -1e-6 * phi.max()                                        # discrete maximum principle (to solver tol)
+    dm.close()
