@@ -1,0 +1,368 @@
+#!/usr/bin/env python3
+"""bench.py — electrode-sweep solves/s and CG SpMV HBM GB/s on synthetic refined layered meshes.
+
+    python bench.py --gpus N --steps K --warmup W            # this engine (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference's solve path
+
+A *step* is one electrode sweep: ``--nconf`` (8) electrode configurations (Neumann patches at different
+positions on the skin of ONE mesh, one Dirichlet return pad => one matrix, 8 right-hand sides) taken
+through the whole solve step the reference delegates to ElmerSolver + pyvista per sweep point
+(step02_electrodes/run_sweep.py:301-341): assemble, boundary conditions, multi-RHS PCG to the
+tolerance, nodal current recovery and the metric reductions.  ``value`` = solves / s with the mesh
+already resident in HBM; ``e2e`` = the same from host buffers through the public API (mesh upload,
+pattern, ..., potentials and currents copied back), every step.  N > 1: every rank sweeps its own set
+of configurations (independent units, no data-path collective) => weak scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+SIGMA = {1: 0.35, 2: 0.04, 3: 0.001}
+I_INJECT = 5e-3
+RTOL = 1e-10
+METRIC = "electrode_sweep_solves_per_s"
+
+
+# ---------------------------------------------------------------------------------------------------
+def sweep_definition(mesh, nconf, rank=0):
+    """Electrode configurations of one sweep: active patch (disk r = 8 mm) at x = 12 + 4k mm on the skin
+    top face; ranks use different y so that no two ranks solve the same configuration."""
+    Lz = mesh.meta["Lz"]
+    tz = mesh.nodes[mesh.tris][:, :, 2]
+    top = np.nonzero(np.all(np.abs(tz - Lz) < 1e-12, axis=1) & (mesh.bcid != 102))[0]
+    cen = mesh.nodes[mesh.tris[top]].mean(axis=1)
+    p = mesh.nodes[mesh.tris[top]]
+    area = 0.5 * np.linalg.norm(np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0]), axis=1)
+    confs = []
+    y0 = 0.045 - 0.004 * (rank % 8)
+    for k in range(nconf):
+        xc = 0.012 + 0.004 * k
+        sel = np.hypot(cen[:, 0] - xc, cen[:, 1] - y0) < 0.008
+        confs.append(dict(center=(xc, y0), r=0.008, tris=top[sel].astype(np.int32), area=float(area[sel].sum())))
+    return confs
+
+
+def run_sweep_step(dm, mesh, confs, step, phi_out=None, J_out=None, sample_spmv=0):
+    """One electrode sweep on a device-resident mesh; returns the per-configuration metric rows."""
+    sig = dict(SIGMA)
+    sig[3] = SIGMA[3] * (1.0 + 0.01 * step)           # a fresh matrix every step (nothing can be cached)
+    dm.assemble(sig)
+    dm.bc_reset(len(confs))
+    for k, c in enumerate(confs):
+        dm.neumann_tris(c["tris"], I_INJECT / c["area"], rhs=k)
+    dm.dirichlet(102, 0.0)
+    phi = dm.solve(to_host=phi_out is not None, out=phi_out, rtol=RTOL, sample_spmv=sample_spmv, spmv_variant=0)
+    stats = dm.last_stats
+    Lz, t_skin = mesh.meta["Lz"], mesh.meta["t_skin"]
+    rows = []
+    for k, c in enumerate(confs):
+        dm.recover_current(k, "l2", to_host=J_out is not None, out=None if J_out is None else J_out[k])
+        fp = (c["center"][0], c["center"][1], c["r"], False)
+        pk = dm.metric_nodes(0, Lz - 0.2 * t_skin, sys=k)
+        ph = dm.metric_nodes(1, Lz - 1e-5, mode=1, footprints=[fp], scale_r=1.0, sys=k)
+        roi = dm.metric_roi([c["center"][0], c["center"][1], Lz - 0.010], 0.005, (1.0, 1.5, 2.0, 3.0), include_tris=False, sys=k)[0]
+        rows.append(dict(peak_J=pk["max"], V_active=ph["sum"] / max(ph["count"], 1), roi_mean_E=roi["sum_E"] / max(roi["n"], 1)))
+    return rows, stats, phi
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    f = ROOT / "profiles" / "traffic.json"
+    if f.exists():
+        return json.loads(f.read_text())
+    return None
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_sample(mesh, conf, n_iter_sample, threads=None):
+    """Bounded CPU sample of one solve with the C/OpenMP oracle: assembly + BCs timed in full, PCG for
+    ``n_iter_sample`` iterations.  Returns (t_setup, t_per_iter, cores)."""
+    from oracle import c_oracle as co
+    if threads:
+        co.set_threads(threads)
+    t0 = time.perf_counter()
+    # Neumann patch as a temporary boundary id (the oracle applies `Current Density` per boundary id)
+    bcid = mesh.bcid.copy()
+    bcid[conf["tris"]] = 9001
+    m2 = type(mesh)(mesh.nodes, mesh.tets, mesh.region, mesh.tris, bcid)
+    cs = co.CSystem(m2, SIGMA, [(102, 0.0)], [(9001, I_INJECT / conf["area"])])
+    t_setup = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    _, it, _ = cs.pcg(rtol=1e-30, maxit=n_iter_sample)
+    t_iter = (time.perf_counter() - t0) / max(it, 1)
+    return cs, t_setup, t_iter, co.threads()
+
+
+def reference_arm(args, rank):
+    """The reference's CPU path for the same workload (ElmerSolver itself cannot be installed here: Fortran,
+    un-vendored), restated by oracle/fem_c.c with all host threads.  Only rank 0 works."""
+    if rank != 0:
+        return
+    import pelvistim_fem_b200  # noqa: F401
+    from pelvistim_fem_b200 import meshgen
+    mesh = meshgen.synth_slab(args.size, contact_enabled=False)
+    confs = sweep_definition(mesh, args.nconf, 0)
+    n_sample = args.cpu_iters
+    # warm-up: assemble once and find the iteration count a full solve needs (first configuration)
+    cs, t_setup, t_iter, cores = cpu_sample(mesh, confs[0], n_sample)
+    n_full = None
+    if not args.cpu_quick:
+        _, n_full, _ = cs.pcg(rtol=RTOL, maxit=200000)
+    else:
+        n_full = args.cpu_assumed_iters or int(round(11.2 * max(meshgen.SYNTH_SIZES[args.size])))
+    for _ in range(max(args.warmup - 1, 0)):
+        cs.pcg(rtol=1e-30, maxit=max(n_sample // 4, 1))
+    t_steps = []
+    for s in range(args.steps):
+        t0 = time.perf_counter()
+        _, it, _ = cs.pcg(rtol=1e-30, maxit=n_sample)
+        t_steps.append((time.perf_counter() - t0) / it)
+    t_it = statistics.mean(t_steps)
+    per_solve = t_setup + n_full * t_it                      # recovery + metrics not counted (favours the CPU arm)
+    value = 1.0 / per_solve
+    sample = (f"size {args.size}: assembly+BC of 1 of {args.nconf} configurations timed in full ({t_setup:.2f} s), "
+              f"{n_sample} Jacobi-PCG iterations per step timed ({t_it*1e3:.2f} ms/it), extrapolated to the "
+              f"{n_full} iterations a solve to rtol {RTOL:g} needs ({'measured by a full CPU solve' if not args.cpu_quick else 'iteration count of the same algorithm on this mesh'}); "
+              "nodal current recovery and metrics not included")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": per_solve * args.nconf * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, mesh, None),
+            "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, mesh, nnz):
+    return {"workload": f"synth_slab {args.size} ({mesh.nt} tets, {mesh.nn} nodes{'' if nnz is None else f', {nnz} nnz'}): electrode sweep of "
+                        f"{args.nconf} Neumann-patch configurations on one matrix (multi-RHS Jacobi-PCG, rtol {RTOL:g}) + L2 current "
+                        "recovery + metric reductions per configuration",
+            "mesh": f"synth_slab_{args.size}", "nconf": args.nconf, "rtol": RTOL, "sweep_points_per_gpu_per_step": args.nconf,
+            "l2": "inputs larger than L2 (matrix + vectors > 126 MB)" if mesh.nt > 4_000_000 else "flushed between steps"}
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ptfem", choices=["ptfem", "reference"])
+    ap.add_argument("--size", default="L", help="synthetic mesh size (XS, S, M, L)")
+    ap.add_argument("--nconf", type=int, default=8)
+    ap.add_argument("--cpu-iters", type=int, default=150, help="PCG iterations per CPU sample")
+    ap.add_argument("--cpu-quick", action="store_true", help="reference arm: skip the full CPU solve that measures the iteration count")
+    ap.add_argument("--cpu-assumed-iters", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+
+    import torch
+    import pelvistim_fem_b200  # noqa: F401
+    from pelvistim_fem_b200 import engine, meshgen
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    mesh = meshgen.synth_slab(args.size, contact_enabled=False)
+    confs = sweep_definition(mesh, args.nconf, rank)
+    ctx = engine.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+    flush = None
+    if mesh.nt <= 4_000_000:
+        flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+
+    def l2_flush():
+        if flush is not None:
+            flush.fill_(1.0)
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput -------------------------------------------------------------------
+    dm = ctx.mesh(mesh.nodes, mesh.tets, mesh.region, mesh.tris, mesh.bcid)
+    nnz = dm.pattern()
+    for s in range(args.warmup):
+        run_sweep_step(dm, mesh, confs, s)
+    ctx.sync(); torch.cuda.synchronize(); barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ctx.launches
+    spmv_ms, iters, rows = [], [], None
+    with ClockSampler(local_rank) as clocks:
+        ev0.record(stream)
+        for s in range(args.steps):
+            l2_flush()
+            rows, st, _ = run_sweep_step(dm, mesh, confs, args.warmup + s, sample_spmv=4)
+            spmv_ms.append(st["spmv_ms"]); iters.append(st["iterations"])
+        ev1.record(stream)
+        ctx.sync(); torch.cuda.synchronize()
+    launches = ctx.launches - launches0
+    t_dev = ev0.elapsed_time(ev1) * 1e-3
+    barrier()
+    if dist is not None:
+        t = torch.tensor([t_dev], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev = float(t.item())
+    value = world * args.nconf * args.steps / t_dev
+    # single right-hand-side streaming SpMV of the CG (the north-star roofline kernel), timed alone
+    dm.bc_reset(1); dm.neumann_tris(confs[0]["tris"], I_INJECT / confs[0]["area"]); dm.dirichlet(102, 0.0)
+    spmv1_ms = dm.spmv_bench(engine.SPMV_STREAM, 30)
+    dm.close()
+
+    # ---- end to end from host buffers -------------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+        h = dict(nodes=pin(mesh.nodes), tets=pin(mesh.tets), region=pin(mesh.region), tris=pin(mesh.tris), bcid=pin(mesh.bcid))
+        phi_out = torch.empty((args.nconf, mesh.nn), dtype=torch.float64).pin_memory().numpy()
+        J_out = torch.empty((args.nconf, mesh.nn, 3), dtype=torch.float64).pin_memory().numpy()
+        h2d = sum(a.nbytes for a in h.values()) + sum(c["tris"].nbytes for c in confs)
+        d2h = phi_out.nbytes + J_out.nbytes
+
+        def e2e_step(s):
+            d = ctx.mesh(h["nodes"], h["tets"], h["region"], h["tris"], h["bcid"])
+            r, _, _ = run_sweep_step(d, mesh, confs, s, phi_out=phi_out, J_out=J_out)
+            d.close()
+            return r
+        e2e_step(0)
+        ctx.sync(); torch.cuda.synchronize(); barrier()
+        n_e2e = max(1, min(args.steps, 3))
+        ev0.record(stream)
+        for s in range(n_e2e):
+            l2_flush()
+            e2e_step(100 + s)
+        ev1.record(stream)
+        ctx.sync(); torch.cuda.synchronize()
+        t_e2e = ev0.elapsed_time(ev1) * 1e-3
+        barrier()
+        if dist is not None:
+            t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e = float(t.item())
+        e2e = {"value": world * args.nconf * n_e2e / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "steps": n_e2e}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the multi-RHS streaming SpMV inside the PCG) ---------------------
+    S = 1
+    while S < args.nconf:
+        S *= 2
+    peak, peak_src = measured_peaks()
+    alg_bytes = 12 * nnz + 4 * (mesh.nn + 1) + 16 * S * mesh.nn
+    t_spmv = statistics.mean(spmv_ms) * 1e-3
+    achieved = alg_bytes / t_spmv / 1e9
+    traffic = ncu_traffic()
+    alg1 = 12 * nnz + 20 * mesh.nn
+    spmv1_gbs = alg1 / (spmv1_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": f"spmv_stream_kernel<S={S}> (multi-RHS CSR SpMV with fused p.Ap)", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": t_spmv * 1e3,
+                "share_of_step": statistics.mean(iters) * t_spmv * args.steps / t_dev,
+                "traffic": None if traffic is None else traffic.get("spmm_bytes_per_launch"),
+                "frac_of_nominal_8TBs": achieved / 8000.0}
+    line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, mesh, nnz),
+            "clocks": clocks.summary(), "gpu_launches": int(launches), "pcg_iterations_per_step": statistics.mean(iters),
+            "roofline": roofline,
+            "cg_spmv_1rhs": {"achieved": spmv1_gbs, "unit": "GB/s", "frac": spmv1_gbs / peak, "frac_of_nominal_8TBs": spmv1_gbs / 8000.0,
+                             "ms_per_launch": spmv1_ms, "algorithmic_bytes_per_launch": alg1,
+                             "traffic": None if traffic is None else traffic.get("spmv_bytes_per_launch")},
+            "sample_metrics": rows[0] if rows else None}
+    if e2e is not None:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu:
+        _, t_setup, t_it, cores = cpu_sample(mesh, confs[0], args.cpu_iters)
+        n_full = statistics.mean(iters)
+        per_solve = t_setup + n_full * t_it
+        line["cpu_baseline"] = {"value": 1.0 / per_solve, "unit": "solves/s", "cores": cores, "kind": "port",
+                                "sample": f"C/OpenMP oracle on the same mesh: assembly+BC of 1 configuration in full ({t_setup:.2f} s), "
+                                          f"{args.cpu_iters} Jacobi-PCG iterations timed ({t_it*1e3:.2f} ms/it), extrapolated to the "
+                                          f"{n_full:.0f} iterations the GPU solve needed at the same tolerance; recovery and metrics not included"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

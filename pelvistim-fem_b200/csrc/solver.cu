@@ -149,6 +149,61 @@ __device__ __forceinline__ double sum_partials(const double* __restrict__ partia
   return tot;
 }
 
+// ---- helpers of the flat (two doubles per thread) kernels ---------------------------------------------------
+template <int S>
+struct FlatPairs {
+  int64_t npairs, stride, j0;
+  int s0, s1;
+  bool has_tail;  // odd element count (S == 1, odd nn): element n-1 is handled by thread 0 of CTA 0
+  int64_t tail;
+  __device__ __forceinline__ FlatPairs(int64_t nn) {
+    const int64_t n = nn * S;
+    npairs = n >> 1;
+    stride = (int64_t)gridDim.x * blockDim.x;
+    j0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    s0 = S == 1 ? 0 : (int)((2 * j0) % S);
+    s1 = S == 1 ? 0 : s0 + 1;
+    has_tail = (n & 1) && blockIdx.x == 0 && threadIdx.x == 0;
+    tail = n - 1;
+  }
+};
+
+// per-element weight (Jacobi inverse diagonal) of the pair starting at flat element e
+template <int S, int VS>
+__device__ __forceinline__ double2 pair_weight(const double* __restrict__ dinv, int64_t e) {
+  if constexpr (VS == S) {
+    return __ldg(reinterpret_cast<const double2*>(dinv + e));
+  } else {
+    const double d = __ldg(dinv + e / S);
+    return make_double2(d, d);
+  }
+}
+template <int S, int VS>
+__device__ __forceinline__ double elem_weight(const double* __restrict__ dinv, int64_t e) {
+  return __ldg(dinv + (VS == S ? e : e / S));
+}
+
+// CTA-level sums per system of NQ quantities held as (value for s0, value for s1) per thread:
+// partial[blockIdx.x][q][sys].  Fixed order -> deterministic.
+template <int S, int NQ>
+__device__ __forceinline__ void block_sum_by_sys(const double (&acc)[NQ][2], double* s_red /*[NQ][2*blockDim.x]*/,
+                                                 double* __restrict__ partial) {
+  const int n2 = 2 * blockDim.x;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    s_red[q * n2 + 2 * threadIdx.x] = acc[q][0];
+    s_red[q * n2 + 2 * threadIdx.x + 1] = acc[q][1];
+  }
+  __syncthreads();
+  if (threadIdx.x < NQ * S) {
+    const int q = threadIdx.x / S, sys = threadIdx.x % S;
+    double t = 0.0;
+    for (int k = sys; k < n2; k += S) t += s_red[q * n2 + k];
+    partial[(size_t)blockIdx.x * NQ * S + threadIdx.x] = t;
+  }
+  __syncthreads();
+}
+
 // ---- K5a: vector SpMV, TPR lanes per row -----------------------------------------------------------
 // DOT: also accumulates sum_i y_i x_i per system, and the last CTA turns it into pq and alpha = rho/pq.
 template <int S, int VS, int TPR, bool DOT>
@@ -225,6 +280,67 @@ __global__ void __launch_bounds__(kThreads) spmv_vector_kernel(int64_t nn, int64
   }
 }
 
+// ---- K5a': vector SpMV for S >= 2: one lane per (row, pair of systems) -------------------------------------
+// S/2 adjacent lanes share a row and each owns two systems, so the x gather (and the val load when every
+// system has its own matrix) of a row is one contiguous 8*S-byte access per non-zero.
+template <int S, int VS, bool DOT>
+__global__ void __launch_bounds__(kThreads) spmv_vector_multi_kernel(int64_t nn, int64_t row0, int interleave,
+                                                                     const int32_t* __restrict__ rowptr,
+                                                                     const int32_t* __restrict__ col,
+                                                                     const double* __restrict__ val,
+                                                                     const double* __restrict__ x, double* __restrict__ y,
+                                                                     double* __restrict__ partial,
+                                                                     double* __restrict__ scal,
+                                                                     unsigned int* __restrict__ ticket) {
+  __shared__ double s_red[DOT ? 2 * kThreads : 1];
+  constexpr int LPR = S / 2;
+  constexpr int RPB = kThreads / LPR;
+  const int lane = threadIdx.x % LPR;
+  const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
+  const int64_t passes = (nn + (int64_t)gridDim.x * RPB - 1) / ((int64_t)gridDim.x * RPB);
+  const int64_t step = interleave ? (int64_t)gridDim.x * RPB : RPB;
+  const int64_t cta_begin = interleave ? (int64_t)blockIdx.x * RPB : (int64_t)blockIdx.x * passes * RPB;
+  const int64_t cta_end = interleave ? nn : min(nn, cta_begin + passes * RPB);
+  double dot[1][2] = {{0.0, 0.0}};
+  for (int64_t base = cta_begin; base < cta_end; base += step) {
+    const int64_t row = row0 + base + threadIdx.x / LPR;
+    if (row >= row0 + min(nn, cta_end)) continue;
+    const int32_t b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
+    double2 acc = make_double2(0.0, 0.0);
+#pragma unroll 4
+    for (int32_t k = b; k < e; ++k) {
+      const int64_t c = ldg_i32_hint(col + k, pol_stream);
+      const double2 xv = ldg_f64x2_hint(x + c * S + 2 * lane, pol_keep);
+      if constexpr (VS == 1) {
+        const double a = ldg_f64_hint(val + k, pol_stream);
+        acc.x = fma(a, xv.x, acc.x);
+        acc.y = fma(a, xv.y, acc.y);
+      } else {
+        const double2 av = ldg_f64x2_hint(val + (int64_t)k * S + 2 * lane, pol_stream);
+        acc.x = fma(av.x, xv.x, acc.x);
+        acc.y = fma(av.y, xv.y, acc.y);
+      }
+    }
+    *reinterpret_cast<double2*>(y + row * S + 2 * lane) = acc;
+    if constexpr (DOT) {
+      const double2 xr = ldg_f64x2_hint(x + row * S + 2 * lane, pol_keep);
+      dot[0][0] = fma(acc.x, xr.x, dot[0][0]);
+      dot[0][1] = fma(acc.y, xr.y, dot[0][1]);
+    }
+  }
+  if constexpr (DOT) {
+    block_sum_by_sys<S, 1>(dot, s_red, partial);
+    if (is_last_block(ticket)) {
+      const double pq = sum_partials<S>(partial, gridDim.x, s_red);
+      if (threadIdx.x < S) {
+        const double rho = scal[SC_RHO * kMaxSys + threadIdx.x];
+        scal[SC_PQ * kMaxSys + threadIdx.x] = pq;
+        scal[SC_ALPHA * kMaxSys + threadIdx.x] = pq > 0.0 ? rho / pq : 0.0;
+      }
+    }
+  }
+}
+
 // ---- K5b: streaming SpMV (S == 1) ----------------------------------------------------------------
 // Each CTA walks row blocks of ~kStreamTile non-zeros.  The block's val/col slices are brought into
 // shared memory with two bulk async copies (cp.async.bulk -> UBLKCP, completion on an mbarrier), so
@@ -259,6 +375,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
       : "memory");
 }
+// bring [src, src+bytes) into L2 ahead of use (16-byte aligned, multiple of 16)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // dynamic shared memory of the streaming kernel: val[STAGES][cap] | col[STAGES][cap] | bar[STAGES]
@@ -267,24 +387,22 @@ __host__ __device__ inline size_t stream_smem_bytes(int stages, int cap) { retur
 // Tile t = rows [t*R, (t+1)*R), R <= 128 chosen at pattern time so that every tile's non-zeros fit a
 // stage.  TPR lanes share a row (CTA = 128*TPR threads); STAGES-1 tiles are in flight per CTA.
 // interleave = 1: CTAs sweep the matrix together as one moving front (tile j of CTA b is b + j*grid).
+// LPR lanes share a row: for S == 1 they split the row's non-zeros (TPR), for S >= 2 each of the S/2
+// lanes owns two systems (one 16-byte access per lane, 8*S contiguous bytes per row and non-zero).
 template <int S, int STAGES, int TPR, bool DOT>
-__global__ void __launch_bounds__(kStreamThreads* TPR) spmv_stream_kernel(int64_t nn, const int32_t* __restrict__ rowptr,
-                                                                          const int32_t* __restrict__ col,
-                                                                          const double* __restrict__ val, int32_t R,
-                                                                          int32_t cap, int32_t ntiles,
-                                                                          int32_t tiles_per_cta, int interleave,
-                                                                          const double* __restrict__ x,
-                                                                          double* __restrict__ y,
-                                                                          double* __restrict__ partial,
-                                                                          double* __restrict__ scal,
-                                                                          unsigned int* __restrict__ ticket) {
+__global__ void __launch_bounds__(kStreamThreads*(S == 1 ? TPR : S / 2))
+    spmv_stream_kernel(int64_t nn, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                       const double* __restrict__ val, int32_t R, int32_t cap, int32_t ntiles, int32_t tiles_per_cta,
+                       int interleave, int xprefetch, const double* __restrict__ x, double* __restrict__ y,
+                       double* __restrict__ partial, double* __restrict__ scal, unsigned int* __restrict__ ticket) {
+  constexpr int LPR = S == 1 ? TPR : S / 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* const s_val = reinterpret_cast<double*>(smem_raw);                                    // [STAGES][cap]
   int32_t* const s_col = reinterpret_cast<int32_t*>(smem_raw + (size_t)STAGES * cap * 8);        // [STAGES][cap]
   uint64_t* const s_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * cap * 12);    // [STAGES]
-  __shared__ double s_red[DOT ? kStreamThreads * TPR : 1];
+  __shared__ double s_red[DOT ? 2 * kStreamThreads * LPR : 1];
   const int tid = threadIdx.x;
-  const int lane = tid % TPR, rloc = tid / TPR;
+  const int lane = tid % LPR, rloc = tid / LPR;
   const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
   if (tid == 0) {
 #pragma unroll
@@ -309,6 +427,16 @@ __global__ void __launch_bounds__(kStreamThreads* TPR) spmv_stream_kernel(int64_
     if (n) {
       bulk_g2s(s_val + (size_t)st * cap, val + a0, n * 8u, &s_bar[st], pol_stream);
       bulk_g2s(s_col + (size_t)st * cap, col + a0, n * 4u, &s_bar[st], pol_stream);
+      if (xprefetch) {
+        // the vector entries this tile touches for the first time sit just below its largest column
+        // (banded matrix): pull them into L2 now, STAGES-1 tiles before the gathers need them
+        const int64_t cmax = __ldg(col + k1 - 1);
+        int64_t lo = (cmax + 1 - R) & ~(int64_t)1;
+        if (lo < 0) lo = 0;
+        const int64_t hi = min(nn, cmax + 1);
+        const uint32_t bytes = (uint32_t)(((hi - lo) * S * 8) & ~(int64_t)15);
+        if (bytes) bulk_prefetch_l2(x + lo * S, bytes, pol_keep);
+      }
     }
   };
   if (tid == 0) {
@@ -316,9 +444,7 @@ __global__ void __launch_bounds__(kStreamThreads* TPR) spmv_stream_kernel(int64_
     for (int s = 0; s < STAGES - 1; ++s)
       if (t_begin + s < t_end) issue(t_begin + s, s);
   }
-  double dot[S];
-#pragma unroll
-  for (int s = 0; s < S; ++s) dot[s] = 0.0;
+  double dot[1][2] = {{0.0, 0.0}};
   uint32_t phase_bits = 0;
   int st = 0;
   for (int64_t t = t_begin; t < t_end; ++t) {
@@ -339,36 +465,40 @@ __global__ void __launch_bounds__(kStreamThreads* TPR) spmv_stream_kernel(int64_
     phase_bits ^= 1u << st;
     const double* sv = s_val + (size_t)st * cap;
     const int32_t* sc = s_col + (size_t)st * cap;
-    double acc[S];
-#pragma unroll
-    for (int s = 0; s < S; ++s) acc[s] = 0.0;
+    if constexpr (S == 1) {
+      double acc = 0.0;
 #pragma unroll 4
-    for (int32_t k = b - a0 + lane; k < e - a0; k += TPR) {
-      const double a = sv[k];
-      double xv[S];
-      load_sys_hint<S>(x + (int64_t)sc[k] * S, xv, pol_keep);
+      for (int32_t k = b - a0 + lane; k < e - a0; k += TPR) acc = fma(sv[k], ldg_f64_hint(x + sc[k], pol_keep), acc);
 #pragma unroll
-      for (int s = 0; s < S; ++s) acc[s] = fma(a, xv[s], acc[s]);
-    }
-#pragma unroll
-    for (int o = TPR / 2; o > 0; o >>= 1) {
-#pragma unroll
-      for (int s = 0; s < S; ++s) acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], o);
-    }
-    if (live && lane == 0) {
-      store_sys<S>(y + r * S, acc);
-      if constexpr (DOT) {
-        double xr[S];
-        load_sys_hint<S>(x + r * S, xr, pol_keep);
-#pragma unroll
-        for (int s = 0; s < S; ++s) dot[s] = fma(acc[s], xr[s], dot[s]);
+      for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (live && lane == 0) {
+        y[r] = acc;
+        if constexpr (DOT) dot[0][0] = fma(acc, ldg_f64_hint(x + r, pol_keep), dot[0][0]);
+      }
+    } else {
+      double2 acc = make_double2(0.0, 0.0);
+#pragma unroll 4
+      for (int32_t k = b - a0; k < e - a0; ++k) {
+        const double a = sv[k];
+        const double2 xv = ldg_f64x2_hint(x + (int64_t)sc[k] * S + 2 * lane, pol_keep);
+        acc.x = fma(a, xv.x, acc.x);
+        acc.y = fma(a, xv.y, acc.y);
+      }
+      if (live) {
+        *reinterpret_cast<double2*>(y + r * S + 2 * lane) = acc;
+        if constexpr (DOT) {
+          const double2 xr = ldg_f64x2_hint(x + r * S + 2 * lane, pol_keep);
+          dot[0][0] = fma(acc.x, xr.x, dot[0][0]);
+          dot[0][1] = fma(acc.y, xr.y, dot[0][1]);
+        }
       }
     }
     __syncthreads();  // stage st may be refilled
     st = (st + 1) % STAGES;
   }
   if constexpr (DOT) {
-    block_sum<S>(dot, s_red, partial + (size_t)blockIdx.x * S);
+    // S == 1: every slot belongs to system 0; S >= 2: slot (2*tid + j) mod S = 2*lane + j
+    block_sum_by_sys<S, 1>(dot, s_red, partial);
     if (is_last_block(ticket)) {
       const double pq = sum_partials<S>(partial, gridDim.x, s_red);
       if (tid < S) {
@@ -381,8 +511,12 @@ __global__ void __launch_bounds__(kStreamThreads* TPR) spmv_stream_kernel(int64_
 }
 
 // ---- K6: fused CG updates ----------------------------------------------------------------------
-// x += alpha p ; r -= alpha q ; partial sums of r.z (z = dinv r, or handed in for Chebyshev later) and r.r.
-// Last CTA: rho_new, rr, beta = rho_new / rho_old.   JAC: z = dinv*r folded in (z never stored).
+// All element-wise kernels walk the [nn][S] vectors as FLAT arrays, two doubles (one 16-byte access) per
+// thread and pass, so every load/store instruction of a warp covers 512 contiguous bytes whatever S is.
+// Because the grid stride is a multiple of S, a thread always sees the same pair of systems
+// (s0 = 2 j mod S, s1 = s0 + 1; both 0 when S == 1), which is what lets it keep per-system partial sums.
+// x += alpha p ; r -= alpha q ; partial sums of r.z (z = dinv r when JAC) and r.r.
+// Last CTA: rr, and when JAC rho_new and beta = rho_new / rho_old (z is never stored for Jacobi).
 template <int S, int VS, bool JAC>
 __global__ void __launch_bounds__(kThreads) cg_update_kernel(int64_t nn, const double* __restrict__ p,
                                                              const double* __restrict__ q,
@@ -390,43 +524,39 @@ __global__ void __launch_bounds__(kThreads) cg_update_kernel(int64_t nn, const d
                                                              double* __restrict__ r, double* __restrict__ partial,
                                                              double* __restrict__ scal,
                                                              unsigned int* __restrict__ ticket) {
-  __shared__ double s_red[kThreads];
-  double alpha[S];
-#pragma unroll
-  for (int s = 0; s < S; ++s) alpha[s] = scal[SC_ALPHA * kMaxSys + s];
-  double acc[2 * S];
-#pragma unroll
-  for (int s = 0; s < 2 * S; ++s) acc[s] = 0.0;
-  const int64_t stride = (int64_t)gridDim.x * kThreads;
-  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nn; i += stride) {
-    double pv[S], qv[S], xv[S], rv[S];
-    load_sys<S>(p + i * S, pv);
-    load_sys<S>(q + i * S, qv);
-    load_sys<S>(x + i * S, xv);
-    load_sys<S>(r + i * S, rv);
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      xv[s] = fma(alpha[s], pv[s], xv[s]);
-      rv[s] = fma(-alpha[s], qv[s], rv[s]);
-    }
-    store_sys<S>(x + i * S, xv);
-    store_sys<S>(r + i * S, rv);
+  __shared__ double s_red[4 * kThreads];
+  const FlatPairs<S> fp(nn);
+  const double a0 = scal[SC_ALPHA * kMaxSys + fp.s0], a1 = scal[SC_ALPHA * kMaxSys + fp.s1];
+  double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};  // [rz | rr][s0 | s1]
+  for (int64_t j = fp.j0; j < fp.npairs; j += fp.stride) {
+    const int64_t e = 2 * j;
+    const double2 pv = __ldg(reinterpret_cast<const double2*>(p + e));
+    const double2 qv = __ldg(reinterpret_cast<const double2*>(q + e));
+    double2 xv = *reinterpret_cast<const double2*>(x + e);
+    double2 rv = *reinterpret_cast<const double2*>(r + e);
+    xv.x = fma(a0, pv.x, xv.x);
+    xv.y = fma(a1, pv.y, xv.y);
+    rv.x = fma(-a0, qv.x, rv.x);
+    rv.y = fma(-a1, qv.y, rv.y);
+    *reinterpret_cast<double2*>(x + e) = xv;
+    *reinterpret_cast<double2*>(r + e) = rv;
     if constexpr (JAC) {
-      if constexpr (VS == 1) {
-        const double d = __ldg(dinv + i);
-#pragma unroll
-        for (int s = 0; s < S; ++s) acc[s] = fma(rv[s] * d, rv[s], acc[s]);
-      } else {
-        double dv[S];
-        load_sys<S>(dinv + i * S, dv);
-#pragma unroll
-        for (int s = 0; s < S; ++s) acc[s] = fma(rv[s] * dv[s], rv[s], acc[s]);
-      }
+      const double2 d = pair_weight<S, VS>(dinv, e);
+      acc[0][0] = fma(rv.x * d.x, rv.x, acc[0][0]);
+      acc[0][1] = fma(rv.y * d.y, rv.y, acc[0][1]);
     }
-#pragma unroll
-    for (int s = 0; s < S; ++s) acc[S + s] = fma(rv[s], rv[s], acc[S + s]);
+    acc[1][0] = fma(rv.x, rv.x, acc[1][0]);
+    acc[1][1] = fma(rv.y, rv.y, acc[1][1]);
   }
-  block_sum<2 * S>(acc, s_red, partial + (size_t)blockIdx.x * 2 * S);
+  if (fp.has_tail) {
+    const int64_t e = fp.tail;
+    const double xv = fma(a0, p[e], x[e]), rv = fma(-a0, q[e], r[e]);
+    x[e] = xv;
+    r[e] = rv;
+    if constexpr (JAC) acc[0][0] = fma(rv * elem_weight<S, VS>(dinv, e), rv, acc[0][0]);
+    acc[1][0] = fma(rv, rv, acc[1][0]);
+  }
+  block_sum_by_sys<S, 2>(acc, s_red, partial);
   if (is_last_block(ticket)) {
     const double tot = sum_partials<2 * S>(partial, gridDim.x, s_red);
     if (threadIdx.x < 2 * S) {
@@ -441,80 +571,71 @@ __global__ void __launch_bounds__(kThreads) cg_update_kernel(int64_t nn, const d
   }
 }
 
-// p = z + beta p   with z = dinv * r (JAC) or z given
+// p = z + beta p   with z = dinv * r (JAC) or z given; first: p = z
 template <int S, int VS, bool JAC>
 __global__ void __launch_bounds__(kThreads) cg_pupdate_kernel(int64_t nn, const double* __restrict__ r,
                                                               const double* __restrict__ zin,
                                                               const double* __restrict__ dinv, double* __restrict__ p,
                                                               const double* __restrict__ scal, int first) {
-  double beta[S];
-#pragma unroll
-  for (int s = 0; s < S; ++s) beta[s] = first ? 0.0 : scal[SC_BETA * kMaxSys + s];
-  const int64_t stride = (int64_t)gridDim.x * kThreads;
-  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nn; i += stride) {
-    double zv[S], pv[S];
+  const FlatPairs<S> fp(nn);
+  const double b0 = first ? 0.0 : scal[SC_BETA * kMaxSys + fp.s0], b1 = first ? 0.0 : scal[SC_BETA * kMaxSys + fp.s1];
+  for (int64_t j = fp.j0; j < fp.npairs; j += fp.stride) {
+    const int64_t e = 2 * j;
+    double2 zv;
     if constexpr (JAC) {
-      load_sys<S>(r + i * S, zv);
-      if constexpr (VS == 1) {
-        const double d = __ldg(dinv + i);
-#pragma unroll
-        for (int s = 0; s < S; ++s) zv[s] *= d;
-      } else {
-        double dv[S];
-        load_sys<S>(dinv + i * S, dv);
-#pragma unroll
-        for (int s = 0; s < S; ++s) zv[s] *= dv[s];
-      }
+      zv = __ldg(reinterpret_cast<const double2*>(r + e));
+      const double2 d = pair_weight<S, VS>(dinv, e);
+      zv.x *= d.x;
+      zv.y *= d.y;
     } else {
-      load_sys<S>(zin + i * S, zv);
+      zv = __ldg(reinterpret_cast<const double2*>(zin + e));
     }
-    if (first) {
-      store_sys<S>(p + i * S, zv);
-    } else {
-      load_sys<S>(p + i * S, pv);
-#pragma unroll
-      for (int s = 0; s < S; ++s) pv[s] = fma(beta[s], pv[s], zv[s]);
-      store_sys<S>(p + i * S, pv);
+    if (!first) {
+      const double2 pv = *reinterpret_cast<const double2*>(p + e);
+      zv.x = fma(b0, pv.x, zv.x);
+      zv.y = fma(b1, pv.y, zv.y);
     }
+    *reinterpret_cast<double2*>(p + e) = zv;
+  }
+  if (fp.has_tail) {
+    const int64_t e = fp.tail;
+    const double z = JAC ? r[e] * elem_weight<S, VS>(dinv, e) : zin[e];
+    p[e] = first ? z : fma(b0, p[e], z);
   }
 }
 
-// generic per-system dots: out slots (a.b) -> slotA, (c.c) -> slotB (either may be -1 via null pointers).
-// mode 0: slotA = sum a*b*(w or 1) ; used for rho0 = r.(dinv r), rr0 = r.r, bnorm2 = b.b, r.z
+// per-system dots: (a . (w b)) -> slot_ab and (a . a) -> slot_aa (either may be -1); w may be null.
+// beta_from_rho: also beta = new/old for slot_ab (Chebyshev path: rho = r.z)
 template <int S, int VS>
 __global__ void __launch_bounds__(kThreads) dots_kernel(int64_t nn, const double* __restrict__ a,
                                                         const double* __restrict__ b, const double* __restrict__ w,
                                                         double* __restrict__ partial, double* __restrict__ scal,
                                                         int slot_ab, int slot_aa, int beta_from_rho,
                                                         unsigned int* __restrict__ ticket) {
-  __shared__ double s_red[kThreads];
-  double acc[2 * S];
-#pragma unroll
-  for (int s = 0; s < 2 * S; ++s) acc[s] = 0.0;
-  const int64_t stride = (int64_t)gridDim.x * kThreads;
-  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nn; i += stride) {
-    double av[S], bv[S];
-    load_sys<S>(a + i * S, av);
-    load_sys<S>(b + i * S, bv);
+  __shared__ double s_red[4 * kThreads];
+  const FlatPairs<S> fp(nn);
+  double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  for (int64_t j = fp.j0; j < fp.npairs; j += fp.stride) {
+    const int64_t e = 2 * j;
+    const double2 av = __ldg(reinterpret_cast<const double2*>(a + e));
+    double2 bv = __ldg(reinterpret_cast<const double2*>(b + e));
     if (w) {
-      if constexpr (VS == 1) {
-        const double d = __ldg(w + i);
-#pragma unroll
-        for (int s = 0; s < S; ++s) bv[s] *= d;
-      } else {
-        double dv[S];
-        load_sys<S>(w + i * S, dv);
-#pragma unroll
-        for (int s = 0; s < S; ++s) bv[s] *= dv[s];
-      }
+      const double2 d = pair_weight<S, VS>(w, e);
+      bv.x *= d.x;
+      bv.y *= d.y;
     }
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      acc[s] = fma(av[s], bv[s], acc[s]);
-      acc[S + s] = fma(av[s], av[s], acc[S + s]);
-    }
+    acc[0][0] = fma(av.x, bv.x, acc[0][0]);
+    acc[0][1] = fma(av.y, bv.y, acc[0][1]);
+    acc[1][0] = fma(av.x, av.x, acc[1][0]);
+    acc[1][1] = fma(av.y, av.y, acc[1][1]);
   }
-  block_sum<2 * S>(acc, s_red, partial + (size_t)blockIdx.x * 2 * S);
+  if (fp.has_tail) {
+    const int64_t e = fp.tail;
+    const double bv = w ? b[e] * elem_weight<S, VS>(w, e) : b[e];
+    acc[0][0] = fma(a[e], bv, acc[0][0]);
+    acc[1][0] = fma(a[e], a[e], acc[1][0]);
+  }
+  block_sum_by_sys<S, 2>(acc, s_red, partial);
   if (is_last_block(ticket)) {
     const double tot = sum_partials<2 * S>(partial, gridDim.x, s_red);
     if (threadIdx.x < 2 * S) {
@@ -597,18 +718,25 @@ __global__ void __launch_bounds__(kThreads) cheb_init_kernel(int64_t nn, const d
                                                              const double* __restrict__ dinv,
                                                              const double* __restrict__ coef, double* __restrict__ rt,
                                                              double* __restrict__ d, double* __restrict__ z) {
-  const int64_t stride = (int64_t)gridDim.x * kThreads;
-  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nn; i += stride) {
-    double rv[S], dv[S];
-    load_sys<S>(r + i * S, rv);
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      rv[s] *= dinv[i * VS + (VS == 1 ? 0 : s)];
-      dv[s] = rv[s] * coef[s * 2];
-    }
-    store_sys<S>(rt + i * S, rv);
-    store_sys<S>(d + i * S, dv);
-    store_sys<S>(z + i * S, dv);
+  const FlatPairs<S> fp(nn);
+  const double c0 = coef[fp.s0 * 2], c1 = coef[fp.s1 * 2];
+  for (int64_t j = fp.j0; j < fp.npairs; j += fp.stride) {
+    const int64_t e = 2 * j;
+    double2 rv = __ldg(reinterpret_cast<const double2*>(r + e));
+    const double2 w = pair_weight<S, VS>(dinv, e);
+    rv.x *= w.x;
+    rv.y *= w.y;
+    const double2 dv = make_double2(rv.x * c0, rv.y * c1);
+    *reinterpret_cast<double2*>(rt + e) = rv;
+    *reinterpret_cast<double2*>(d + e) = dv;
+    *reinterpret_cast<double2*>(z + e) = dv;
+  }
+  if (fp.has_tail) {
+    const int64_t e = fp.tail;
+    const double rv = r[e] * elem_weight<S, VS>(dinv, e);
+    rt[e] = rv;
+    d[e] = rv * c0;
+    z[e] = rv * c0;
   }
 }
 template <int S, int VS>
@@ -617,22 +745,32 @@ __global__ void __launch_bounds__(kThreads) cheb_step_kernel(int64_t nn, const d
                                                              const double* __restrict__ coef /*[S][2] of this step*/,
                                                              double* __restrict__ rt, double* __restrict__ d,
                                                              double* __restrict__ z) {
-  const int64_t stride = (int64_t)gridDim.x * kThreads;
-  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nn; i += stride) {
-    double qv[S], rv[S], dv[S], zv[S];
-    load_sys<S>(q + i * S, qv);
-    load_sys<S>(rt + i * S, rv);
-    load_sys<S>(d + i * S, dv);
-    load_sys<S>(z + i * S, zv);
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      rv[s] = fma(-dinv[i * VS + (VS == 1 ? 0 : s)], qv[s], rv[s]);
-      dv[s] = coef[s * 2] * dv[s] + coef[s * 2 + 1] * rv[s];
-      zv[s] += dv[s];
-    }
-    store_sys<S>(rt + i * S, rv);
-    store_sys<S>(d + i * S, dv);
-    store_sys<S>(z + i * S, zv);
+  const FlatPairs<S> fp(nn);
+  const double c10 = coef[fp.s0 * 2], c20 = coef[fp.s0 * 2 + 1], c11 = coef[fp.s1 * 2], c21 = coef[fp.s1 * 2 + 1];
+  for (int64_t j = fp.j0; j < fp.npairs; j += fp.stride) {
+    const int64_t e = 2 * j;
+    const double2 qv = __ldg(reinterpret_cast<const double2*>(q + e));
+    const double2 w = pair_weight<S, VS>(dinv, e);
+    double2 rv = *reinterpret_cast<const double2*>(rt + e);
+    double2 dv = *reinterpret_cast<const double2*>(d + e);
+    double2 zv = *reinterpret_cast<const double2*>(z + e);
+    rv.x = fma(-w.x, qv.x, rv.x);
+    rv.y = fma(-w.y, qv.y, rv.y);
+    dv.x = c10 * dv.x + c20 * rv.x;
+    dv.y = c11 * dv.y + c21 * rv.y;
+    zv.x += dv.x;
+    zv.y += dv.y;
+    *reinterpret_cast<double2*>(rt + e) = rv;
+    *reinterpret_cast<double2*>(d + e) = dv;
+    *reinterpret_cast<double2*>(z + e) = zv;
+  }
+  if (fp.has_tail) {
+    const int64_t e = fp.tail;
+    const double rv = fma(-elem_weight<S, VS>(dinv, e), q[e], rt[e]);
+    const double dv = c10 * d[e] + c20 * rv;
+    rt[e] = rv;
+    d[e] = dv;
+    z[e] += dv;
   }
 }
 
@@ -659,6 +797,13 @@ int launch_vector(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y, P
   double* partial = w ? w->partial.p : nullptr;
   double* scal = w ? w->scal.p : nullptr;
   unsigned int* ticket = w ? w->ticket.p : nullptr;
+  if constexpr (S >= 2) {
+    const int grid = grid_for(ctx, A.nn, kThreads / (S / 2));
+    spmv_vector_multi_kernel<S, VS, DOT><<<grid, kThreads, 0, ctx->stream>>>(A.nn, A.row0, ctx->tune_interleave, A.rowptr,
+                                                                             A.col, A.val, x, y, partial, scal, ticket);
+    PT_LAUNCH_CHECK(ctx);
+    return PTFEM_OK;
+  }
 #define PT_VEC(TPR)                                                                                             \
   {                                                                                                             \
     const int grid = grid_for(ctx, A.nn, kThreads / TPR);                                                       \
@@ -688,8 +833,9 @@ int launch_stream_t(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y,
       ctx->func_smem[fn] = smem;
     }
   }
-  const int threads = A.stream_rows * TPR;
-  int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024 + (DOT ? kStreamThreads * TPR * 8 : 0) + 32));
+  constexpr int LPR = S == 1 ? TPR : S / 2;
+  const int threads = A.stream_rows * LPR;
+  int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024 + (DOT ? 2 * kStreamThreads * LPR * 8 : 0) + 32));
   if (per_sm > 2048 / threads) per_sm = 2048 / threads;
   if (per_sm > 32) per_sm = 32;
   if (ctx->tune_ctas_per_sm > 0 && ctx->tune_ctas_per_sm < per_sm) per_sm = ctx->tune_ctas_per_sm;
@@ -701,8 +847,8 @@ int launch_stream_t(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y,
   const int64_t per_cta = (ntiles + grid - 1) / grid;
   if (!ctx->tune_interleave) grid = (ntiles + per_cta - 1) / per_cta;
   spmv_stream_kernel<S, STAGES, TPR, DOT><<<(int)grid, threads, smem, ctx->stream>>>(
-      A.nn, A.rowptr, A.col, A.val, A.stream_rows, A.stream_cap, (int32_t)ntiles, (int32_t)per_cta, ctx->tune_interleave, x,
-      y, w ? w->partial.p : nullptr, w ? w->scal.p : nullptr, w ? w->ticket.p : nullptr);
+      A.nn, A.rowptr, A.col, A.val, A.stream_rows, A.stream_cap, (int32_t)ntiles, (int32_t)per_cta, ctx->tune_interleave,
+      ctx->tune_xprefetch, x, y, w ? w->partial.p : nullptr, w ? w->scal.p : nullptr, w ? w->ticket.p : nullptr);
   PT_LAUNCH_CHECK(ctx);
   return PTFEM_OK;
 }
@@ -793,7 +939,7 @@ namespace detail {
 // one preconditioner application z = M^-1 r (Chebyshev); uses w.q as SpMV output, w.z / w.rt / w.d
 template <int S, int VS>
 int cheb_apply(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int degree) {
-  const int grid = grid_for(ctx, A.nn, kThreads);
+  const int grid = grid_for(ctx, (A.nn * A.S + 1) / 2, kThreads);
   double* rt = w.rt.p;
   double* d = w.d.p;
   cheb_init_kernel<S, VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.coef.p, rt, d, w.z.p);
@@ -809,7 +955,7 @@ int cheb_apply(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int deg
 
 template <int S, int VS>
 int pcg_iteration(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int precond, int degree, double* x) {
-  const int grid = grid_for(ctx, A.nn, kThreads);
+  const int grid = grid_for(ctx, (A.nn * A.S + 1) / 2, kThreads);
   // q = A p, pq, alpha
   PT_TRY((spmv_sv<S, VS>(ctx, A, variant, w.p.p, w.q.p, &w, true)));
   if (precond == PTFEM_PRECOND_JACOBI) {
@@ -836,7 +982,7 @@ int pcg_iteration(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int 
 // r = b - A x ; z ; p = z ; rho = r.z ; rr = r.r
 template <int S, int VS>
 int pcg_start(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int precond, int degree, double* x) {
-  const int grid = grid_for(ctx, A.nn, kThreads);
+  const int grid = grid_for(ctx, (A.nn * A.S + 1) / 2, kThreads);
   PT_TRY((spmv_sv<S, VS>(ctx, A, variant, x, w.q.p, &w, false)));
   residual_kernel<S><<<grid, kThreads, 0, ctx->stream>>>(A.nn, A.b, w.q.p, w.r.p);
   PT_LAUNCH_CHECK(ctx);
@@ -862,7 +1008,7 @@ int pcg_solve_t(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_o
   const int variant = resolve_variant(A, o.spmv_variant);
   const int precond = o.precond;
   const int degree = precond == PTFEM_PRECOND_CHEBYSHEV ? (o.cheb_degree > 0 ? o.cheb_degree : 4) : 0;
-  const int grid = grid_for(ctx, A.nn, kThreads);
+  const int grid = grid_for(ctx, (A.nn * A.S + 1) / 2, kThreads);
   const int check = o.check_every > 0 ? o.check_every : 50;
   double* h = ctx->h_pinned;  // >= SC_COUNT*kMaxSys doubles
   int spmv_calls = 0;

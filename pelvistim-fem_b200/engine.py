@@ -306,15 +306,18 @@ class DeviceMesh:
             setattr(o, k, v)
         return o
 
-    def solve(self, to_host=True, raise_on_noconv=True, **opts):
+    def solve(self, to_host=True, raise_on_noconv=True, out=None, **opts):
         """PCG solve of every assembled system.  Returns phi [nsys, nn] (host) when
-        ``to_host`` else ``None`` (solution stays on the device for post-processing)."""
+        ``to_host`` else ``None`` (solution stays on the device for post-processing).
+        ``out``: optional preallocated (e.g. pinned) float64 array [nsys, nn] to receive phi."""
         o = self._opts(**opts)
         st = SolveStats()
         nsys = max(getattr(self, "nmat", 1), getattr(self, "nrhs", 1))
         self.nsys = nsys
         if to_host:
-            phi = np.empty((nsys, self.nn), dtype=np.float64)
+            phi = out if out is not None else np.empty((nsys, self.nn), dtype=np.float64)
+            if phi.shape != (nsys, self.nn) or phi.dtype != np.float64 or not phi.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous float64 array of shape [nsys, nn]")
             rc = self.lib.ptfem_solve(self._h, C.byref(o), _ptr(phi), C.byref(st))
         else:
             phi = None
@@ -352,8 +355,8 @@ class DeviceMesh:
         self._ck(self.lib.ptfem_element_fields(self._h, sys, _ptr(E), _ptr(J)))
         return E, J
 
-    def recover_current(self, sys=0, method="l2", to_host=True):
-        J = np.empty((self.nn, 3), dtype=np.float64) if to_host else None
+    def recover_current(self, sys=0, method="l2", to_host=True, out=None):
+        J = (out if out is not None else np.empty((self.nn, 3), dtype=np.float64)) if to_host else None
         self._ck(self.lib.ptfem_recover_current(self._h, sys, _RECOVER[method], _ptr(J)))
         return J
 

@@ -488,7 +488,8 @@ SYNTH_SIZES = {
 }
 
 
-def synth_slab(size="S", seed=0, jitter=0.2, elec_r=0.010, with_parents=False, interfaces_as_103=False):
+def synth_slab(size="S", seed=0, jitter=0.2, elec_r=0.010, with_parents=False, interfaces_as_103=False,
+               contact_enabled=True):
     """Synthetic refined layered slab of SURVEY.md section 8(d): 80x60x40.5 mm, nx*ny*nz
     hexes -> 6 Kuhn tets each, regions 1-5, pads r = 10 mm at (15,45)/(65,45) mm."""
     nx, ny, nz = SYNTH_SIZES[size] if isinstance(size, str) else size
@@ -504,7 +505,7 @@ def synth_slab(size="S", seed=0, jitter=0.2, elec_r=0.010, with_parents=False, i
     return layered_slab_mesh(Lx, Ly, Lz, t_skin, t_fat, t_c, (0.015, 0.045), (0.065, 0.045), elec_r, "circle",
                              xs=xs, ys=ys, n_muscle=n_m, n_fat=n_f, n_skin=n_s, n_contact=n_c,
                              jitter=jitter, seed=seed, interfaces_as_103=interfaces_as_103,
-                             with_parents=with_parents)
+                             with_parents=with_parents, contact_enabled=contact_enabled)
 
 
 def tri_areas(nodes, tris):
