@@ -219,6 +219,7 @@ def main():
     ap.add_argument("--cpu-assumed-iters", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-partitioned", action="store_true", help="N > 1: skip the row-partitioned single-solve extra")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -318,6 +319,23 @@ def main():
         e2e = {"value": world * args.nconf * n_e2e / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": n_e2e}
 
+    # ---- N > 1 extra: the same mesh as ONE row-partitioned solve over all ranks (config #5, strong scaling) -------
+    part = None
+    if world > 1 and not args.no_partitioned:
+        from pelvistim_fem_b200 import distsolve
+        pmesh = meshgen.synth_slab(args.size)
+        res = distsolve.partitioned_solve(ctx, pmesh, {1: 0.35, 2: 0.04, 3: 0.001, 4: 0.005, 5: 0.005}, [(102, 0.0)],
+                                          [(101, 15.975)], rank, world, check=True, rtol=RTOL)
+        t = torch.tensor([res["stats"]["solve_ms"], res["timings"]["spmv_ms"], res["timings"]["halo_ms"],
+                          res["timings"]["allreduce_ms"], res["rel_err_vs_single"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = t.tolist()
+        part = {"workload": f"synth_slab {args.size} with contact pads, one Jacobi-PCG solve row-partitioned over {world} GPUs "
+                            "(NCCL halo exchange + 3-scalar all-reduce per iteration, single-reduction CG)",
+                "iterations": res["stats"]["iterations"], "solve_ms": t[0], "ms_per_iteration": t[0] / max(res["stats"]["iterations"], 1),
+                "spmv_ms": t[1], "halo_ms": t[2], "allreduce_ms": t[3], "rows_per_rank": res["nloc"], "halo_rows": res["nhalo"],
+                "single_gpu_solve_ms": res["single_gpu_ms"], "single_gpu_iterations": res["single_gpu_iterations"],
+                "speedup_vs_1gpu": res["single_gpu_ms"] / t[0], "max_rel_err_vs_single_gpu": t[4]}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -351,6 +369,8 @@ def main():
             "sample_metrics": rows[0] if rows else None}
     if e2e is not None:
         line["e2e"] = e2e
+    if part is not None:
+        line["partitioned_solve"] = part
     if world == 1 and not args.no_cpu:
         _, t_setup, t_it, cores = cpu_sample(mesh, confs[0], args.cpu_iters)
         n_full = statistics.mean(iters)

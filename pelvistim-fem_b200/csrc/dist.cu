@@ -108,6 +108,11 @@ __global__ void dist_dinv_kernel(const int32_t* __restrict__ rowptr, const int32
   needs_halo[i] = h;
 }
 
+__global__ void dist_max_row_kernel(const int32_t* __restrict__ rowptr, int64_t n, int32_t* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicMax(out, rowptr[i + 1] - rowptr[i]);
+}
+
 __global__ void dist_pack_kernel(const double* __restrict__ u, const int32_t* __restrict__ idx, int64_t n,
                                  double* __restrict__ buf) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -223,7 +228,9 @@ struct DistState {
   cudaGraphExec_t graph = nullptr;
   int graph_iters = 0;
   int64_t graph_launches = 0;
+  bool warmed = false;
   int64_t i0 = 0, i1 = 0;  // rows [i0, i1) need no halo value
+  int32_t stream_rows = 0, stream_cap = 0;  // streaming SpMV tile geometry valid for any row range
 };
 
 }  // namespace
@@ -263,7 +270,11 @@ static int spmv_rows(ptfem_mesh* m, DistState& d, int64_t r0, int64_t r1) {
   A.val = m->val_bc.p;
   A.VS = 1;
   A.S = 1;
-  return spmv_launch(m->ctx, A, PTFEM_SPMV_VECTOR, d.u.p, d.w.p, nullptr, false);
+  A.stream_rows = d.stream_rows;
+  A.stream_cap = d.stream_cap;
+  // short ranges (the few boundary rows) are not worth a persistent launch
+  const int variant = (d.stream_rows > 0 && r1 - r0 >= 16384) ? PTFEM_SPMV_STREAM : PTFEM_SPMV_VECTOR;
+  return spmv_launch(m->ctx, A, variant, d.u.p, d.w.p, nullptr, false);
 }
 
 // w = A u with the halo exchange of u overlapped with the interior rows
@@ -442,6 +453,22 @@ int ptfem_dist_system_create(ptfem_ctx* ctx, int64_t nloc, int64_t nhalo, const 
     }
     d.i0 = best0;
     d.i1 = best1;
+    // streaming SpMV on arbitrary row ranges: a stage must hold any 64 consecutive rows
+    {
+      DevBuf<int32_t> mr;
+      PT_TRY(mr.alloc(1));
+      PT_CK(cudaMemsetAsync(mr.p, 0, sizeof(int32_t), ctx->stream));
+      dist_max_row_kernel<<<ceil_div(nloc, 256), 256, 0, ctx->stream>>>(m->rowptr.p, nloc, mr.p);
+      PT_LAUNCH_CHECK(ctx);
+      int32_t mx = 0;
+      PT_CK(cudaMemcpyAsync(&mx, mr.p, sizeof mx, cudaMemcpyDeviceToHost, ctx->stream));
+      PT_CK(cudaStreamSynchronize(ctx->stream));
+      const int cap = ((64 * mx + 8) + 31) & ~31;
+      if (mx > 0 && cap <= 4096) {
+        d.stream_rows = 64;
+        d.stream_cap = cap;
+      }
+    }
     // rows outside [i0,i1) may or may not need the halo; they all wait for it (correct, slightly conservative)
     return PTFEM_OK;
   };
@@ -470,6 +497,13 @@ int ptfem_dist_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* x_loca
   const int grid = dist_grid(ctx, m->nloc);
   double* h = ctx->h_pinned;
 
+  // first use of a peer connection / collective sets up NCCL channels (seconds): keep it out of the timing
+  if (ctx->nranks > 1 && !d.warmed) {
+    PT_TRY(halo_exchange(m, d, ctx->stream));
+    PT_NCCL(api, api->AllReduce(d.partial.p, d.partial.p, 3, kNcclFloat64, kNcclSum, (ncclComm_t)ctx->comm, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    d.warmed = true;
+  }
   cudaEvent_t e0, e1;
   PT_CK(cudaEventCreate(&e0));
   PT_CK(cudaEventCreate(&e1));

@@ -391,7 +391,7 @@ __host__ __device__ inline size_t stream_smem_bytes(int stages, int cap) { retur
 // lanes owns two systems (one 16-byte access per lane, 8*S contiguous bytes per row and non-zero).
 template <int S, int STAGES, int TPR, bool DOT>
 __global__ void __launch_bounds__(kStreamThreads*(S == 1 ? TPR : S / 2))
-    spmv_stream_kernel(int64_t nn, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+    spmv_stream_kernel(int64_t nn, int64_t row0, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                        const double* __restrict__ val, int32_t R, int32_t cap, int32_t ntiles, int32_t tiles_per_cta,
                        int interleave, int xprefetch, const double* __restrict__ x, double* __restrict__ y,
                        double* __restrict__ partial, double* __restrict__ scal, unsigned int* __restrict__ ticket) {
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(kStreamThreads*(S == 1 ? TPR : S / 2))
 
   // thread 0: bulk-load the val/col slices of local tile j into stage st
   auto issue = [&](int64_t j, int st) {
-    const int64_t r0 = tile_of(j) * R, r1 = min(nn, r0 + R);
+    const int64_t r0 = row0 + tile_of(j) * R, r1 = min(row0 + nn, r0 + R);
     const int32_t k0 = __ldg(rowptr + r0), k1 = __ldg(rowptr + r1);
     const int32_t a0 = k0 & ~3;
     const uint32_t n = (uint32_t)(((k1 + 3) & ~3) - a0);
@@ -453,14 +453,14 @@ __global__ void __launch_bounds__(kStreamThreads*(S == 1 ? TPR : S / 2))
       issue(t + STAGES - 1, (st + STAGES - 1) % STAGES);
     }
     const int64_t tg = tile_of(t);
-    const int64_t r = tg * R + rloc;
-    const bool live = rloc < R && r < nn;
+    const int64_t r = row0 + tg * R + rloc;
+    const bool live = rloc < R && r < row0 + nn;
     int32_t b = 0, e = 0;
     if (live) {
       b = __ldg(rowptr + r);
       e = __ldg(rowptr + r + 1);
     }
-    const int32_t a0 = __ldg(rowptr + tg * R) & ~3;
+    const int32_t a0 = __ldg(rowptr + row0 + tg * R) & ~3;
     mbar_wait(&s_bar[st], (phase_bits >> st) & 1u);
     phase_bits ^= 1u << st;
     const double* sv = s_val + (size_t)st * cap;
@@ -847,7 +847,7 @@ int launch_stream_t(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y,
   const int64_t per_cta = (ntiles + grid - 1) / grid;
   if (!ctx->tune_interleave) grid = (ntiles + per_cta - 1) / per_cta;
   spmv_stream_kernel<S, STAGES, TPR, DOT><<<(int)grid, threads, smem, ctx->stream>>>(
-      A.nn, A.rowptr, A.col, A.val, A.stream_rows, A.stream_cap, (int32_t)ntiles, (int32_t)per_cta, ctx->tune_interleave,
+      A.nn, A.row0, A.rowptr, A.col, A.val, A.stream_rows, A.stream_cap, (int32_t)ntiles, (int32_t)per_cta, ctx->tune_interleave,
       ctx->tune_xprefetch, x, y, w ? w->partial.p : nullptr, w ? w->scal.p : nullptr, w ? w->ticket.p : nullptr);
   PT_LAUNCH_CHECK(ctx);
   return PTFEM_OK;
@@ -896,7 +896,7 @@ int ptfem_stream_threads() { return kStreamThreads; }
 namespace ptfem {
 
 int resolve_variant(const LinSys& A, int variant) {
-  const bool stream_ok = A.VS == 1 && A.stream_rows > 0 && A.row0 == 0;
+  const bool stream_ok = A.VS == 1 && A.stream_rows > 0;
   if (variant == PTFEM_SPMV_AUTO) return stream_ok && A.nnz >= (int64_t)1 << 20 ? PTFEM_SPMV_STREAM : PTFEM_SPMV_VECTOR;
   if ((variant == PTFEM_SPMV_STREAM || variant == PTFEM_SPMV_STREAM1) && !stream_ok) return PTFEM_SPMV_VECTOR;
   return variant;

@@ -1,0 +1,49 @@
+"""Launcher-side helper for the row-partitioned multi-GPU solve: every rank assembles the case on its own
+GPU (mesh and pattern are replicated, as in a sweep), keeps the rows it owns, and the ranks then iterate
+together over NCCL (``ptfem_dist_solve``).  Needs ``torch.distributed`` to be initialised (any backend)
+for the one-off broadcast of the NCCL id."""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import engine, partition
+
+
+def partitioned_solve(ctx, mesh, sigma_by_body, dirichlet, neumann, rank, world, check=True, **opts):
+    """Returns dict(x_local, row0, stats, timings, nloc, nhalo, rel_err_vs_single)."""
+    import torch.distributed as dist
+    dm = ctx.mesh(mesh.nodes, mesh.tets, mesh.region, mesh.tris, mesh.bcid)
+    dm.assemble(sigma_by_body).bc_reset(1)
+    for bid, g in neumann:
+        dm.neumann(bid, g)
+    for bid, v in dirichlet:
+        dm.dirichlet(bid, v)
+    rowptr, col = dm.get_pattern()
+    val = dm.get_values(0, True)
+    b = dm.get_rhs(0)
+    phi_single = None
+    if check:
+        phi_single = dm.solve(rtol=opts.get("rtol", 1e-10))[0]
+        single_stats = dm.last_stats
+    dm.close()
+    blk = partition.local_block(rowptr, col, val, b, rank, world)
+    if world > 1:
+        ids = [engine.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        engine.dist_init(ctx, ids[0], rank, world)
+    ds = engine.DistSystem(ctx, blk)
+    t0 = time.perf_counter()
+    x = ds.solve(**opts)
+    wall = time.perf_counter() - t0
+    out = dict(x_local=x, row0=blk.row0, nloc=blk.nloc, nhalo=blk.nhalo, stats=ds.last_stats, timings=ds.timings, wall_s=wall)
+    if check:
+        ref = phi_single[blk.row0:blk.row0 + blk.nloc]
+        out["rel_err_vs_single"] = float(np.abs(x - ref).max() / max(np.abs(phi_single).max(), 1e-300))
+        out["single_gpu_ms"] = single_stats["solve_ms"]
+        out["single_gpu_iterations"] = single_stats["iterations"]
+    ds.close()
+    if world > 1:
+        engine.dist_finalize(ctx)
+    return out

@@ -432,3 +432,78 @@ def solve_case(ctx: Context, mesh, sigma_by_body, dirichlet, neumann, recover="l
     phi = dm.solve(**opts)[0]
     J = dm.recover_current(0, recover) if recover else None
     return dict(phi=phi, J=J, stats=dm.last_stats, dmesh=dm)
+
+
+# -- multi-GPU: row-partitioned single solve ------------------------------------------------------------
+def nccl_library_path():
+    """Path of the NCCL shared library torch ships (``nvidia/nccl/lib/libnccl.so.2``), else the soname."""
+    try:
+        import nvidia.nccl as _n
+        base = Path(list(_n.__path__)[0]) / "lib"
+        for name in ("libnccl.so.2", "libnccl.so"):
+            if (base / name).exists():
+                return str(base / name)
+    except Exception:
+        pass
+    return "libnccl.so.2"
+
+
+def dist_unique_id(libnccl=None):
+    """128-byte ncclUniqueId (rank 0 creates it, the launcher broadcasts it)."""
+    buf = C.create_string_buffer(128)
+    L = load_library()
+    rc = L.ptfem_dist_unique_id((libnccl or nccl_library_path()).encode(), buf)
+    if rc != 0:
+        raise PtfemError(rc, L.ptfem_last_error().decode(errors="replace"))
+    return buf.raw
+
+
+def dist_init(ctx: Context, unique_id: bytes, rank, nranks, libnccl=None):
+    buf = C.create_string_buffer(unique_id, 128)
+    ctx._ck(ctx.lib.ptfem_dist_init(ctx._h, (libnccl or nccl_library_path()).encode(), buf, rank, nranks))
+
+
+def dist_finalize(ctx: Context):
+    ctx._ck(ctx.lib.ptfem_dist_finalize(ctx._h))
+
+
+class DistSystem:
+    """One rank's block of a row-partitioned system on its GPU (``ptfem_dist_system_create``)."""
+
+    def __init__(self, ctx: Context, blk):
+        self.ctx, self.lib, self.nloc = ctx, ctx.lib, blk.nloc
+        h = C.c_void_p()
+        self._h = None
+        nnbr = int(blk.nbr_rank.shape[0])
+        arrs = [_i32(blk.rowptr), _i32(blk.col), _f64(blk.val), _f64(blk.b), _i32(blk.nbr_rank), _i32(blk.send_ptr),
+                _i32(blk.send_idx), _i32(blk.recv_ptr)]
+        ctx._ck(self.lib.ptfem_dist_system_create(ctx._h, blk.nloc, blk.nhalo, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]),
+                                                  _ptr(arrs[3]), nnbr, _ptr(arrs[4]) if nnbr else None,
+                                                  _ptr(arrs[5]) if nnbr else None, _ptr(arrs[6]) if nnbr else None,
+                                                  _ptr(arrs[7]) if nnbr else None, C.byref(h)))
+        self._h = h
+
+    def solve(self, **opts):
+        o = SolveOpts()
+        self.lib.ptfem_solve_opts_default(C.byref(o))
+        for k, v in opts.items():
+            setattr(o, k, v)
+        st = SolveStats()
+        x = np.empty(self.nloc, dtype=np.float64)
+        t = [C.c_double(), C.c_double(), C.c_double()]
+        rc = self.lib.ptfem_dist_solve(self._h, C.byref(o), _ptr(x), C.byref(st), C.byref(t[0]), C.byref(t[1]), C.byref(t[2]))
+        self.last_stats = st.as_dict()
+        self.timings = dict(spmv_ms=t[0].value, halo_ms=t[1].value, allreduce_ms=t[2].value)
+        self.ctx._ck(rc)
+        return x
+
+    def close(self):
+        if self._h is not None and self.ctx._h is not None:
+            self.lib.ptfem_mesh_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,145 @@
+"""Row partitioning of one assembled system for the multi-GPU solve (BASELINE.json config #5; not in
+the reference, whose ElmerSolver run is serial: ``step03_ankle_layers/run_layered_sweep.py:1099``).
+
+Rank *r* owns the contiguous rows ``[bounds[r], bounds[r+1])``.  Columns of its block are renumbered
+``[0, nloc)`` = owned (global - row0) and ``[nloc, nloc+nhalo)`` = halo, the halo being the sorted
+global ids of the non-owned columns (so it is automatically grouped by owner rank).  Because the
+stiffness pattern is symmetric, the rows a neighbour needs from this rank are exactly this rank's
+rows that have a column owned by that neighbour, in ascending order — no communication is needed to
+build the send lists.
+
+``cg_single_reduction`` is the host (numpy) statement of the iteration ``ptfem_dist_solve`` runs on
+the GPUs (Chronopoulos-Gear: one halo exchange + one all-reduce of three scalars per iteration); the
+CPU tests drive it over ``torch.distributed`` (gloo) to check the partitioning logic.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+
+def row_bounds(n, nranks):
+    """Contiguous, balanced row ownership: int64 [nranks+1]."""
+    return np.array([(n * r) // nranks for r in range(nranks + 1)], dtype=np.int64)
+
+
+@dataclass
+class LocalBlock:
+    rank: int
+    nranks: int
+    row0: int
+    nloc: int
+    nhalo: int
+    rowptr: np.ndarray        # int32 [nloc+1]
+    col: np.ndarray           # int32 [nnz_loc], local numbering
+    val: np.ndarray           # float64 [nnz_loc]
+    b: np.ndarray             # float64 [nloc]
+    halo_global: np.ndarray   # int64 [nhalo] global ids of the halo slots
+    nbr_rank: np.ndarray      # int32 [nnbr]
+    send_ptr: np.ndarray      # int32 [nnbr+1]
+    send_idx: np.ndarray      # int32 [send_ptr[-1]] local rows to send, grouped by neighbour
+    recv_ptr: np.ndarray      # int32 [nnbr+1] halo slots [nloc+recv_ptr[k], nloc+recv_ptr[k+1]) come from nbr k
+
+
+def local_block(rowptr, col, val, b, rank, nranks, bounds=None) -> LocalBlock:
+    n = rowptr.shape[0] - 1
+    bounds = row_bounds(n, nranks) if bounds is None else np.asarray(bounds, dtype=np.int64)
+    r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+    nloc = r1 - r0
+    k0, k1 = int(rowptr[r0]), int(rowptr[r1])
+    lrowptr = (rowptr[r0:r1 + 1].astype(np.int64) - k0).astype(np.int32)
+    c = col[k0:k1].astype(np.int64)
+    owned = (c >= r0) & (c < r1)
+    halo = np.unique(c[~owned])
+    owner = np.searchsorted(bounds, halo, side="right") - 1
+    lcol = np.where(owned, c - r0, nloc + np.searchsorted(halo, c)).astype(np.int32)
+    nbr = np.unique(owner).astype(np.int32)
+    recv_ptr = np.concatenate([[0], np.cumsum([(owner == q).sum() for q in nbr])]).astype(np.int32)
+    # send lists: rows of this block with at least one column owned by q (pattern symmetry)
+    rows = np.repeat(np.arange(nloc, dtype=np.int64), np.diff(lrowptr))
+    col_owner = np.searchsorted(bounds, c, side="right") - 1
+    send = []
+    for q in nbr:
+        send.append(np.unique(rows[col_owner == q]).astype(np.int32))
+    send_ptr = np.concatenate([[0], np.cumsum([s.size for s in send])]).astype(np.int32)
+    send_idx = np.concatenate(send).astype(np.int32) if send else np.zeros(0, np.int32)
+    return LocalBlock(rank, nranks, r0, nloc, int(halo.size), lrowptr, lcol, np.ascontiguousarray(val[k0:k1], dtype=np.float64),
+                      np.ascontiguousarray(b[r0:r1], dtype=np.float64), halo, nbr, send_ptr, send_idx, recv_ptr)
+
+
+class SerialComm:
+    """All ranks in one process (tests): exchange/allreduce over a list of blocks."""
+
+    def __init__(self, blocks):
+        self.blocks = blocks
+
+    def exchange_all(self, us):
+        """us[r]: owned part of rank r's vector -> list of halo arrays."""
+        out = []
+        for blk in self.blocks:
+            h = np.empty(blk.nhalo)
+            for k, q in enumerate(blk.nbr_rank):
+                peer = self.blocks[q]
+                kk = int(np.nonzero(peer.nbr_rank == blk.rank)[0][0])
+                h[blk.recv_ptr[k]:blk.recv_ptr[k + 1]] = us[q][peer.send_idx[peer.send_ptr[kk]:peer.send_ptr[kk + 1]]]
+            out.append(h)
+        return out
+
+
+def check_consistency(blocks):
+    """Send list of p towards q must be exactly q's halo slots owned by p, in order."""
+    for blk in blocks:
+        for k, q in enumerate(blk.nbr_rank):
+            peer = blocks[q]
+            kk = np.nonzero(peer.nbr_rank == blk.rank)[0]
+            if kk.size != 1:
+                return False
+            kk = int(kk[0])
+            want = blk.halo_global[blk.recv_ptr[k]:blk.recv_ptr[k + 1]]
+            got = peer.row0 + peer.send_idx[peer.send_ptr[kk]:peer.send_ptr[kk + 1]].astype(np.int64)
+            if not np.array_equal(want, got):
+                return False
+    return True
+
+
+def local_spmv(blk: LocalBlock, u_full):
+    """y_loc = A_loc [u_owned ; u_halo]."""
+    import scipy.sparse as sp
+    A = sp.csr_matrix((blk.val, blk.col, blk.rowptr), shape=(blk.nloc, blk.nloc + blk.nhalo))
+    return A @ u_full
+
+
+def cg_single_reduction(blk: LocalBlock, exchange, allreduce, rtol=1e-10, maxit=100000):
+    """Chronopoulos-Gear Jacobi-PCG on one rank's block.  ``exchange(u_owned) -> u_halo`` and
+    ``allreduce(vec3) -> vec3`` are the only communication.  Returns (x_owned, iterations, rel)."""
+    nloc = blk.nloc
+    diag = np.ones(nloc)
+    rows = np.repeat(np.arange(nloc), np.diff(blk.rowptr))
+    on_diag = blk.col == rows
+    diag[rows[on_diag]] = blk.val[on_diag]
+    dinv = 1.0 / diag
+    x = np.zeros(nloc)
+    r = blk.b.copy()
+    u = r * dinv
+    bn2 = allreduce(np.array([blk.b @ blk.b, 0.0, 0.0]))[0]
+    w = local_spmv(blk, np.concatenate([u, exchange(u)]))
+    g, d, rr = allreduce(np.array([r @ u, w @ u, r @ r]))
+    alpha, beta, g_old = (g / d if d > 0 else 0.0), 0.0, g
+    p = np.zeros(nloc)
+    s = np.zeros(nloc)
+    it = 0
+    while it < maxit and rr > rtol * rtol * bn2:
+        p = u + beta * p
+        s = w + beta * s
+        x += alpha * p
+        r -= alpha * s
+        u = r * dinv
+        w = local_spmv(blk, np.concatenate([u, exchange(u)]))
+        g, d, rr = allreduce(np.array([r @ u, w @ u, r @ r]))
+        beta = g / g_old if g_old > 0 else 0.0
+        den = d - beta * g / alpha if alpha != 0 else 0.0
+        alpha = g / den if den > 0 else 0.0
+        g_old = g
+        it += 1
+    return x, it, float(np.sqrt(rr / bn2)) if bn2 > 0 else 0.0
