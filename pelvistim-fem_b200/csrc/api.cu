@@ -133,6 +133,7 @@ int ptfem_ctx_destroy(ptfem_ctx* ctx) {
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   delete ctx;
+  dev_cache_flush();
   return PTFEM_OK;
 }
 

@@ -38,6 +38,14 @@ int set_err(int code, const char* fmt, ...);
     if (!(cond)) return ptfem::set_err(PTFEM_ERR_ARG, "%s: %s", __func__, msg); \
   } while (0)
 
+// Device allocations go through a small caching allocator (util.cu): cudaFree synchronises the device and
+// costs ~0.3 s per mesh of the size-L working set, which an end-to-end sweep step would pay every time.
+// Freed blocks are kept and handed out again (best fit within 25 %); the cache is flushed when cudaMalloc
+// runs out of memory and when the last context is destroyed.
+int dev_alloc(void** p, size_t bytes);
+void dev_free(void* p);
+void dev_cache_flush();
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -46,16 +54,16 @@ struct DevBuf {
     if (count <= n && p) return PTFEM_OK;
     release();
     if (count == 0) count = 1;
-    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
-    if (e != cudaSuccess) {
+    const int rc = dev_alloc((void**)&p, count * sizeof(T));
+    if (rc != PTFEM_OK) {
       p = nullptr;
-      return set_err(PTFEM_ERR_CUDA, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+      return rc;
     }
     n = count;
     return PTFEM_OK;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) dev_free(p);
     p = nullptr;
     n = 0;
   }

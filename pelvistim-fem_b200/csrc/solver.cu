@@ -515,14 +515,13 @@ __global__ void __launch_bounds__(kStreamThreads*(S == 1 ? TPR : S / 2))
 // thread and pass, so every load/store instruction of a warp covers 512 contiguous bytes whatever S is.
 // Because the grid stride is a multiple of S, a thread always sees the same pair of systems
 // (s0 = 2 j mod S, s1 = s0 + 1; both 0 when S == 1), which is what lets it keep per-system partial sums.
-// x += alpha p ; r -= alpha q ; partial sums of r.z (z = dinv r when JAC) and r.r.
+// r -= alpha q ; partial sums of r.z (z = dinv r when JAC) and r.r.  (x += alpha p is folded into the p-update
+// kernel, which reads p anyway: p is then read once per iteration instead of twice.)
 // Last CTA: rr, and when JAC rho_new and beta = rho_new / rho_old (z is never stored for Jacobi).
 template <int S, int VS, bool JAC>
-__global__ void __launch_bounds__(kThreads) cg_update_kernel(int64_t nn, const double* __restrict__ p,
-                                                             const double* __restrict__ q,
-                                                             const double* __restrict__ dinv, double* __restrict__ x,
-                                                             double* __restrict__ r, double* __restrict__ partial,
-                                                             double* __restrict__ scal,
+__global__ void __launch_bounds__(kThreads) cg_update_kernel(int64_t nn, const double* __restrict__ q,
+                                                             const double* __restrict__ dinv, double* __restrict__ r,
+                                                             double* __restrict__ partial, double* __restrict__ scal,
                                                              unsigned int* __restrict__ ticket) {
   __shared__ double s_red[4 * kThreads];
   const FlatPairs<S> fp(nn);
@@ -530,15 +529,10 @@ __global__ void __launch_bounds__(kThreads) cg_update_kernel(int64_t nn, const d
   double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};  // [rz | rr][s0 | s1]
   for (int64_t j = fp.j0; j < fp.npairs; j += fp.stride) {
     const int64_t e = 2 * j;
-    const double2 pv = __ldg(reinterpret_cast<const double2*>(p + e));
     const double2 qv = __ldg(reinterpret_cast<const double2*>(q + e));
-    double2 xv = *reinterpret_cast<const double2*>(x + e);
     double2 rv = *reinterpret_cast<const double2*>(r + e);
-    xv.x = fma(a0, pv.x, xv.x);
-    xv.y = fma(a1, pv.y, xv.y);
     rv.x = fma(-a0, qv.x, rv.x);
     rv.y = fma(-a1, qv.y, rv.y);
-    *reinterpret_cast<double2*>(x + e) = xv;
     *reinterpret_cast<double2*>(r + e) = rv;
     if constexpr (JAC) {
       const double2 d = pair_weight<S, VS>(dinv, e);
@@ -550,8 +544,7 @@ __global__ void __launch_bounds__(kThreads) cg_update_kernel(int64_t nn, const d
   }
   if (fp.has_tail) {
     const int64_t e = fp.tail;
-    const double xv = fma(a0, p[e], x[e]), rv = fma(-a0, q[e], r[e]);
-    x[e] = xv;
+    const double rv = fma(-a0, q[e], r[e]);
     r[e] = rv;
     if constexpr (JAC) acc[0][0] = fma(rv * elem_weight<S, VS>(dinv, e), rv, acc[0][0]);
     acc[1][0] = fma(rv, rv, acc[1][0]);
@@ -571,14 +564,16 @@ __global__ void __launch_bounds__(kThreads) cg_update_kernel(int64_t nn, const d
   }
 }
 
-// p = z + beta p   with z = dinv * r (JAC) or z given; first: p = z
+// x += alpha p_old ; p = z + beta p_old   with z = dinv * r (JAC) or z given.   first: p = z only.
 template <int S, int VS, bool JAC>
 __global__ void __launch_bounds__(kThreads) cg_pupdate_kernel(int64_t nn, const double* __restrict__ r,
                                                               const double* __restrict__ zin,
                                                               const double* __restrict__ dinv, double* __restrict__ p,
-                                                              const double* __restrict__ scal, int first) {
+                                                              double* __restrict__ x, const double* __restrict__ scal,
+                                                              int first) {
   const FlatPairs<S> fp(nn);
   const double b0 = first ? 0.0 : scal[SC_BETA * kMaxSys + fp.s0], b1 = first ? 0.0 : scal[SC_BETA * kMaxSys + fp.s1];
+  const double a0 = first ? 0.0 : scal[SC_ALPHA * kMaxSys + fp.s0], a1 = first ? 0.0 : scal[SC_ALPHA * kMaxSys + fp.s1];
   for (int64_t j = fp.j0; j < fp.npairs; j += fp.stride) {
     const int64_t e = 2 * j;
     double2 zv;
@@ -592,6 +587,10 @@ __global__ void __launch_bounds__(kThreads) cg_pupdate_kernel(int64_t nn, const 
     }
     if (!first) {
       const double2 pv = *reinterpret_cast<const double2*>(p + e);
+      double2 xv = *reinterpret_cast<const double2*>(x + e);
+      xv.x = fma(a0, pv.x, xv.x);
+      xv.y = fma(a1, pv.y, xv.y);
+      *reinterpret_cast<double2*>(x + e) = xv;
       zv.x = fma(b0, pv.x, zv.x);
       zv.y = fma(b1, pv.y, zv.y);
     }
@@ -600,7 +599,12 @@ __global__ void __launch_bounds__(kThreads) cg_pupdate_kernel(int64_t nn, const 
   if (fp.has_tail) {
     const int64_t e = fp.tail;
     const double z = JAC ? r[e] * elem_weight<S, VS>(dinv, e) : zin[e];
-    p[e] = first ? z : fma(b0, p[e], z);
+    if (first) {
+      p[e] = z;
+    } else {
+      x[e] = fma(a0, p[e], x[e]);
+      p[e] = fma(b0, p[e], z);
+    }
   }
 }
 
@@ -959,21 +963,21 @@ int pcg_iteration(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int 
   // q = A p, pq, alpha
   PT_TRY((spmv_sv<S, VS>(ctx, A, variant, w.p.p, w.q.p, &w, true)));
   if (precond == PTFEM_PRECOND_JACOBI) {
-    cg_update_kernel<S, VS, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.p.p, w.q.p, A.dinv, x, w.r.p, w.partial.p,
-                                                                      w.scal.p, w.ticket.p);
+    cg_update_kernel<S, VS, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.q.p, A.dinv, w.r.p, w.partial.p, w.scal.p,
+                                                                      w.ticket.p);
     PT_LAUNCH_CHECK(ctx);
-    cg_pupdate_kernel<S, VS, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, nullptr, A.dinv, w.p.p, w.scal.p, 0);
+    cg_pupdate_kernel<S, VS, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, nullptr, A.dinv, w.p.p, x, w.scal.p, 0);
     PT_LAUNCH_CHECK(ctx);
   } else {
-    cg_update_kernel<S, VS, false><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.p.p, w.q.p, A.dinv, x, w.r.p,
-                                                                       w.partial.p, w.scal.p, w.ticket.p);
+    cg_update_kernel<S, VS, false><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.q.p, A.dinv, w.r.p, w.partial.p, w.scal.p,
+                                                                       w.ticket.p);
     PT_LAUNCH_CHECK(ctx);
     PT_TRY((cheb_apply<S, VS>(ctx, A, w, variant, degree)));
     // rho_new = r.z, beta = rho_new/rho_old
     dots_kernel<S, VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.z.p, nullptr, w.partial.p, w.scal.p, SC_RHO, -1,
                                                            1, w.ticket.p);
     PT_LAUNCH_CHECK(ctx);
-    cg_pupdate_kernel<S, VS, false><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.z.p, A.dinv, w.p.p, w.scal.p, 0);
+    cg_pupdate_kernel<S, VS, false><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.z.p, A.dinv, w.p.p, x, w.scal.p, 0);
     PT_LAUNCH_CHECK(ctx);
   }
   return PTFEM_OK;
@@ -990,14 +994,14 @@ int pcg_start(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int prec
     dots_kernel<S, VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.r.p, A.dinv, w.partial.p, w.scal.p, SC_RHO, SC_RR,
                                                            0, w.ticket.p);
     PT_LAUNCH_CHECK(ctx);
-    cg_pupdate_kernel<S, VS, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, nullptr, A.dinv, w.p.p, w.scal.p, 1);
+    cg_pupdate_kernel<S, VS, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, nullptr, A.dinv, w.p.p, x, w.scal.p, 1);
     PT_LAUNCH_CHECK(ctx);
   } else {
     PT_TRY((cheb_apply<S, VS>(ctx, A, w, variant, degree)));
     dots_kernel<S, VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.z.p, nullptr, w.partial.p, w.scal.p, SC_RHO, SC_RR,
                                                            0, w.ticket.p);
     PT_LAUNCH_CHECK(ctx);
-    cg_pupdate_kernel<S, VS, false><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.z.p, A.dinv, w.p.p, w.scal.p, 1);
+    cg_pupdate_kernel<S, VS, false><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.z.p, A.dinv, w.p.p, x, w.scal.p, 1);
     PT_LAUNCH_CHECK(ctx);
   }
   return PTFEM_OK;

@@ -1,5 +1,9 @@
 // util.cu — error string, exclusive scan, fills.
 #include <cstdarg>
+#include <map>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
 
 #include "common.cuh"
 
@@ -15,6 +19,80 @@ int set_err(int code, const char* fmt, ...) {
   va_end(ap);
   g_err = buf;
   return code;
+}
+
+// ---- caching device allocator ---------------------------------------------------------------------
+// One cache per process, keyed by device.  Blocks are only reused after the owning buffer was released
+// on the host, and every kernel that touched a buffer was launched on the context's stream before that
+// release; callers synchronise that stream before dropping buffers that may still be in use
+// (ptfem_mesh_destroy does), so a recycled block is never in flight.
+namespace {
+struct CacheBlock {
+  void* p;
+  size_t bytes;
+  int device;
+};
+std::mutex g_cache_mu;
+std::multimap<size_t, CacheBlock> g_free;                 // by size
+std::unordered_map<void*, CacheBlock> g_live;
+}  // namespace
+
+int dev_alloc(void** out, size_t bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bytes = (bytes + 511) & ~(size_t)511;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (auto it = g_free.lower_bound(bytes); it != g_free.end() && it->first <= bytes + bytes / 4 + 4096; ++it) {
+      if (it->second.device == dev) {
+        CacheBlock b = it->second;
+        g_free.erase(it);
+        g_live[b.p] = b;
+        *out = b.p;
+        return PTFEM_OK;
+      }
+    }
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    dev_cache_flush();
+    e = cudaMalloc(&p, bytes);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_err(PTFEM_ERR_CUDA, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+  }
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  g_live[p] = CacheBlock{p, bytes, dev};
+  *out = p;
+  return PTFEM_OK;
+}
+
+void dev_free(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  auto it = g_live.find(p);
+  if (it == g_live.end()) return;
+  g_free.emplace(it->second.bytes, it->second);
+  g_live.erase(it);
+}
+
+void dev_cache_flush() {
+  std::vector<CacheBlock> blocks;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (auto& kv : g_free) blocks.push_back(kv.second);
+    g_free.clear();
+  }
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (auto& b : blocks) {
+    cudaSetDevice(b.device);
+    cudaFree(b.p);
+  }
+  cudaSetDevice(cur);
 }
 
 // ---- exclusive scan (int32 in, int32 out, int64 carries) ------------------------------------

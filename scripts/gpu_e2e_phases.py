@@ -1,0 +1,40 @@
+"""Wall-clock phases of one end-to-end sweep step (host buffers -> results) on the L mesh."""
+import sys, time
+sys.path.insert(0, ".")
+import numpy as np, torch
+import pelvistim_fem_b200
+from pelvistim_fem_b200 import engine, meshgen
+import bench
+size = sys.argv[1] if len(sys.argv) > 1 else "L"
+mesh = meshgen.synth_slab(size, contact_enabled=False)
+confs = bench.sweep_definition(mesh, 8, 0)
+ctx = engine.Context(0)
+pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+h = dict(nodes=pin(mesh.nodes), tets=pin(mesh.tets), region=pin(mesh.region), tris=pin(mesh.tris), bcid=pin(mesh.bcid))
+phi_out = torch.empty((8, mesh.nn), dtype=torch.float64).pin_memory().numpy()
+J_out = torch.empty((8, mesh.nn, 3), dtype=torch.float64).pin_memory().numpy()
+for rep in range(2):
+    T = {}
+    def tic(name, t0):
+        ctx.sync(); T[name] = time.perf_counter() - t0; return time.perf_counter()
+    t = time.perf_counter()
+    d = ctx.mesh(h["nodes"], h["tets"], h["region"], h["tris"], h["bcid"]); t = tic("mesh_create", t)
+    d.pattern(); t = tic("pattern+geometry", t)
+    d.assemble(bench.SIGMA); t = tic("assemble", t)
+    d.bc_reset(8)
+    for k, c in enumerate(confs):
+        d.neumann_tris(c["tris"], bench.I_INJECT / c["area"], rhs=k)
+    d.dirichlet(102, 0.0); t = tic("bc", t)
+    d.solve(to_host=True, out=phi_out, rtol=bench.RTOL); t = tic("solve+d2h_phi", t)
+    T["recover+d2h_J x8"] = 0.0; T["metrics x8"] = 0.0
+    for k, c in enumerate(confs):
+        t = time.perf_counter()
+        d.recover_current(k, "l2", to_host=True, out=J_out[k]); ctx.sync()
+        T["recover+d2h_J x8"] += time.perf_counter() - t; t = time.perf_counter()
+        fp = (c["center"][0], c["center"][1], c["r"], False)
+        d.metric_nodes(0, 0.0397, sys=k); d.metric_nodes(1, 0.04 - 1e-5, mode=1, footprints=[fp], sys=k)
+        d.metric_roi([c["center"][0], c["center"][1], 0.03], 0.005, (1.0, 1.5, 2.0, 3.0), include_tris=False, sys=k)
+        ctx.sync(); T["metrics x8"] += time.perf_counter() - t
+    t = time.perf_counter()
+    d.close(); t = tic("close", t)
+    print({k: round(v, 4) for k, v in T.items()}, "iters", d.last_stats["iterations"], "solve_ms", round(d.last_stats["solve_ms"], 1), flush=True)

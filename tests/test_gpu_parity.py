@@ -205,6 +205,26 @@ def test_batched_matrices_match_single_solves(gpu_ctx, golden):
     dm.close()
 
 
+@pytest.mark.parametrize("precond", [engine.PRECOND_JACOBI, engine.PRECOND_CHEBYSHEV])
+def test_odd_node_count_and_chebyshev_batches(gpu_ctx, precond):
+    # odd nn exercises the tail element of the two-doubles-per-thread kernels (S = 1); then 3 matrices
+    # (padded to 4 systems) with the Chebyshev preconditioner's per-system eigenvalue bounds
+    m = meshgen.box_mesh(0.04, 0.04, 0.02, 6, 4, 2, jitter=0.2, seed=7, ids=(2, 1, 3))
+    assert m.nn % 2 == 1
+    ref = fo.solve_case(m, {1: 0.2}, [(2, 1.0), (1, 0.0)], [], recover="l2")
+    res = engine.solve_case(gpu_ctx, m, {1: 0.2}, [(2, 1.0), (1, 0.0)], [], recover="l2", precond=precond, rtol=1e-12)
+    assert rel(res["phi"], ref["phi"]) < TOL_PHI and rel(res["J"], ref["J"]) < TOL_FIELD
+    res["dmesh"].close()
+    ms = meshgen.synth_slab("XS")
+    dm = dm_for(gpu_ctx, ms)
+    sigs = [{**SIGMA5, 4: s, 5: s} for s in (5e-5, 5e-3, 0.5)]
+    dm.assemble(sigs).bc_reset(1).neumann(101, 15.975).dirichlet(102, 0.0)
+    phi = dm.solve(precond=precond, cheb_degree=3)
+    for k, sg in enumerate(sigs):
+        assert rel(phi[k], fo.solve_case(ms, sg, [(102, 0.0)], [(101, 15.975)], recover=None)["phi"]) < TOL_PHI
+    dm.close()
+
+
 def test_warm_start_and_noconv(gpu_ctx):
     m = meshgen.synth_slab("XS")
     dm = dm_for(gpu_ctx, m)
