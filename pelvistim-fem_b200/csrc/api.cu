@@ -59,6 +59,12 @@ int make_linsys(ptfem_mesh* m, LinSys& A) {
   A.b = m->b.p;
   A.stream_rows = m->stream_rows;
   A.stream_cap = m->stream_cap;
+  if (m->has_rowperm && m->nvalp == 1 && m->pval.p) {
+    A.rowid = m->rowid.p;
+    A.prowptr = m->prowptr.p;
+    A.pcol = m->pcol.p;
+    A.pval = m->pval.p;
+  }
   return PTFEM_OK;
 }
 
@@ -74,6 +80,11 @@ int prepare_systems(ptfem_mesh* m) {
       PT_CK(cudaMemsetAsync(m->phi.p, 0, (size_t)m->nn * S * sizeof(double), m->ctx->stream));
     }
     m->nsys_user = std::max(m->nval, m->nrhs);
+    if (m->has_rowperm && m->nvalp == 1) {   // the streaming kernel's private copy of the eliminated matrix
+      PT_TRY(m->pval.alloc(m->nnz + 8));
+      PT_CK(cudaMemsetAsync(m->pval.p + m->nnz, 0, 8 * sizeof(double), m->ctx->stream));
+      PT_TRY(permute_values(m->ctx, m->nn, m->rowptr.p, m->rowid.p, m->prowptr.p, m->val_bc.p, m->pval.p));
+    }
   }
   return PTFEM_OK;
 }
@@ -113,6 +124,7 @@ int ptfem_ctx_create(int device, ptfem_ctx** out) {
   PT_CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   PT_CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
   if (const char* e = getenv("PTFEM_INTERLEAVE")) c->tune_interleave = atoi(e) != 0;
+  if (const char* e = getenv("PTFEM_MORTON")) c->tune_morton = atoi(e);
   if (const char* e = getenv("PTFEM_XPREFETCH")) c->tune_xprefetch = atoi(e) != 0;
   if (const char* e = getenv("PTFEM_CTAS_PER_SM")) c->tune_ctas_per_sm = atoi(e);
   if (const char* e = getenv("PTFEM_STREAM_CAP")) c->tune_stream_cap = atoi(e);
@@ -173,6 +185,13 @@ int ptfem_mesh_create(ptfem_ctx* ctx, int64_t nn, const double* xyz, int64_t nt,
   m->nn = nn;
   m->nt = nt;
   m->nb = nb;
+  for (int d = 0; d < 3; ++d) m->bb_lo[d] = m->bb_hi[d] = xyz[d];
+  for (int64_t i = 0; i < nn; ++i)
+    for (int d = 0; d < 3; ++d) {
+      const double v = xyz[i * 3 + d];
+      if (v < m->bb_lo[d]) m->bb_lo[d] = v;
+      if (v > m->bb_hi[d]) m->bb_hi[d] = v;
+    }
   int rc = PTFEM_OK;
   auto up = [&](auto& buf, const auto* src, size_t count) {
     if (rc) return;
@@ -416,6 +435,16 @@ int ptfem_spmv(ptfem_mesh* m, int32_t sys, int32_t with_bc, int32_t variant, con
   A.nn = m->nn; A.nnz = m->nnz; A.rowptr = m->rowptr.p; A.col = m->col.p; A.val = vals; A.VS = 1; A.S = 1;
   A.stream_rows = m->stream_rows;
   A.stream_cap = m->stream_cap;
+  DevBuf<double> pv;
+  if (m->has_rowperm) {
+    PT_TRY(pv.alloc(m->nnz + 8));
+    PT_CK(cudaMemsetAsync(pv.p + m->nnz, 0, 8 * sizeof(double), ctx->stream));
+    PT_TRY(permute_values(ctx, m->nn, m->rowptr.p, m->rowid.p, m->prowptr.p, vals, pv.p));
+    A.rowid = m->rowid.p;
+    A.prowptr = m->prowptr.p;
+    A.pcol = m->pcol.p;
+    A.pval = pv.p;
+  }
   PT_TRY(spmv_launch(ctx, A, variant, dx.p, dy.p, nullptr, false));
   PT_CK(cudaMemcpyAsync(y, dy.p, (size_t)m->nn * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   PT_CK(cudaStreamSynchronize(ctx->stream));

@@ -103,6 +103,7 @@ struct ptfem_ctx {
   int tune_stream_rows = 0;        // most rows per tile (PTFEM_STREAM_ROWS, 0 = 128)
   int tune_stream_tpr = 1;         // lanes per row of the streaming SpMV (PTFEM_STREAM_TPR: 1, 2, 4, 8)
   int tune_stream_stages = 2;      // shared-memory stages of the streaming SpMV (PTFEM_STREAM_STAGES: 2, 3)
+  int tune_morton = -1;            // streaming SpMV walks rows along a Morton curve: -1 auto, 0 off, 1 on (PTFEM_MORTON)
   int tune_xprefetch = 0;          // streaming SpMV prefetches the leading edge of x into L2 (PTFEM_XPREFETCH)
   int tune_ctas_per_sm = 0;        // cap on resident CTAs per SM of the streaming SpMV (PTFEM_CTAS_PER_SM)
   std::unordered_map<const void*, size_t> func_smem;  // dynamic shared memory limit raised per kernel
@@ -150,6 +151,12 @@ struct ptfem_mesh {
   ptfem::DevBuf<int32_t> e2nnz;          // [nt][16]
   ptfem::DevBuf<int32_t> gptr, gsrc;     // nnz -> (tet*16 + ij) contributions, sorted
   // stream-SpMV row blocks
+  // streaming SpMV: Morton processing order (rowid[j] = mesh row handled j-th) and the matrix copy in that order
+  bool has_rowperm = false;
+  double row_coherence = 1.0;     // fraction of rows whose columns are the previous row's shifted by one
+  ptfem::DevBuf<int32_t> rowid, prowptr, pcol;
+  ptfem::DevBuf<double> pval;     // [nnz] values of val_bc in processing order (single matrix only)
+  double bb_lo[3] = {0, 0, 0}, bb_hi[3] = {0, 0, 0};
   int32_t stream_rows = 0;        // rows per tile of the streaming SpMV (0 = not usable on this pattern)
   int32_t stream_cap = 0;         // staged entries per tile
   int32_t max_row = 0;            // longest row of the pattern

@@ -393,8 +393,9 @@ template <int S, int STAGES, int TPR, bool DOT>
 __global__ void __launch_bounds__(kStreamThreads*(S == 1 ? TPR : S / 2))
     spmv_stream_kernel(int64_t nn, int64_t row0, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                        const double* __restrict__ val, int32_t R, int32_t cap, int32_t ntiles, int32_t tiles_per_cta,
-                       int interleave, int xprefetch, const double* __restrict__ x, double* __restrict__ y,
-                       double* __restrict__ partial, double* __restrict__ scal, unsigned int* __restrict__ ticket) {
+                       int interleave, int xprefetch, const int32_t* __restrict__ rowid, const double* __restrict__ x,
+                       double* __restrict__ y, double* __restrict__ partial, double* __restrict__ scal,
+                       unsigned int* __restrict__ ticket) {
   constexpr int LPR = S == 1 ? TPR : S / 2;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* const s_val = reinterpret_cast<double*>(smem_raw);                                    // [STAGES][cap]
@@ -461,6 +462,8 @@ __global__ void __launch_bounds__(kStreamThreads*(S == 1 ? TPR : S / 2))
       e = __ldg(rowptr + r + 1);
     }
     const int32_t a0 = __ldg(rowptr + row0 + tg * R) & ~3;
+    // ro: the mesh row this thread's (processing-order) row r stands for
+    const int64_t ro = (live && rowid) ? (int64_t)__ldg(rowid + r) : r;
     mbar_wait(&s_bar[st], (phase_bits >> st) & 1u);
     phase_bits ^= 1u << st;
     const double* sv = s_val + (size_t)st * cap;
@@ -472,8 +475,8 @@ __global__ void __launch_bounds__(kStreamThreads*(S == 1 ? TPR : S / 2))
 #pragma unroll
       for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (live && lane == 0) {
-        y[r] = acc;
-        if constexpr (DOT) dot[0][0] = fma(acc, ldg_f64_hint(x + r, pol_keep), dot[0][0]);
+        y[ro] = acc;
+        if constexpr (DOT) dot[0][0] = fma(acc, ldg_f64_hint(x + ro, pol_keep), dot[0][0]);
       }
     } else {
       double2 acc = make_double2(0.0, 0.0);
@@ -485,9 +488,9 @@ __global__ void __launch_bounds__(kStreamThreads*(S == 1 ? TPR : S / 2))
         acc.y = fma(a, xv.y, acc.y);
       }
       if (live) {
-        *reinterpret_cast<double2*>(y + r * S + 2 * lane) = acc;
+        *reinterpret_cast<double2*>(y + ro * S + 2 * lane) = acc;
         if constexpr (DOT) {
-          const double2 xr = ldg_f64x2_hint(x + r * S + 2 * lane, pol_keep);
+          const double2 xr = ldg_f64x2_hint(x + ro * S + 2 * lane, pol_keep);
           dot[0][0] = fma(acc.x, xr.x, dot[0][0]);
           dot[0][1] = fma(acc.y, xr.y, dot[0][1]);
         }
@@ -850,9 +853,10 @@ int launch_stream_t(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y,
   if (grid < 1) grid = 1;
   const int64_t per_cta = (ntiles + grid - 1) / grid;
   if (!ctx->tune_interleave) grid = (ntiles + per_cta - 1) / per_cta;
+  const bool perm = A.rowid != nullptr && A.row0 == 0;
   spmv_stream_kernel<S, STAGES, TPR, DOT><<<(int)grid, threads, smem, ctx->stream>>>(
-      A.nn, A.row0, A.rowptr, A.col, A.val, A.stream_rows, A.stream_cap, (int32_t)ntiles, (int32_t)per_cta, ctx->tune_interleave,
-      ctx->tune_xprefetch, x, y, w ? w->partial.p : nullptr, w ? w->scal.p : nullptr, w ? w->ticket.p : nullptr);
+      A.nn, A.row0, perm ? A.prowptr : A.rowptr, perm ? A.pcol : A.col, perm ? A.pval : A.val, A.stream_rows, A.stream_cap,
+      (int32_t)ntiles, (int32_t)per_cta, ctx->tune_interleave, perm ? 0 : ctx->tune_xprefetch, perm ? A.rowid : nullptr, x, y, w ? w->partial.p : nullptr, w ? w->scal.p : nullptr, w ? w->ticket.p : nullptr);
   PT_LAUNCH_CHECK(ctx);
   return PTFEM_OK;
 }
@@ -893,6 +897,19 @@ int spmv_sv(ptfem_ctx* ctx, const LinSys& A, int variant, const double* x, doubl
 
 }  // namespace
 
+namespace {
+__global__ void permute_values_kernel(int64_t nn, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rowid,
+                                      const int32_t* __restrict__ prowptr, const double* __restrict__ val,
+                                      double* __restrict__ pval) {
+  // 8 lanes per row: short rows, coalesced within a row segment
+  const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int lane = threadIdx.x & 7;
+  if (j >= nn) return;
+  const int32_t src = rowptr[rowid[j]], dst = prowptr[j], n = prowptr[j + 1] - dst;
+  for (int32_t t = lane; t < n; t += 8) pval[dst + t] = val[src + t];
+}
+}  // namespace
+
 int ptfem_stream_cap_max() { return kStreamCapMax; }
 int ptfem_stream_rows_default() { return kStreamRowsDefault; }
 int ptfem_stream_threads() { return kStreamThreads; }
@@ -904,6 +921,13 @@ int resolve_variant(const LinSys& A, int variant) {
   if (variant == PTFEM_SPMV_AUTO) return stream_ok && A.nnz >= (int64_t)1 << 20 ? PTFEM_SPMV_STREAM : PTFEM_SPMV_VECTOR;
   if ((variant == PTFEM_SPMV_STREAM || variant == PTFEM_SPMV_STREAM1) && !stream_ok) return PTFEM_SPMV_VECTOR;
   return variant;
+}
+
+int permute_values(ptfem_ctx* ctx, int64_t nn, const int32_t* rowptr, const int32_t* rowid, const int32_t* prowptr,
+                   const double* val, double* pval) {
+  permute_values_kernel<<<ceil_div(nn * 8, 256), 256, 0, ctx->stream>>>(nn, rowptr, rowid, prowptr, val, pval);
+  PT_LAUNCH_CHECK(ctx);
+  return PTFEM_OK;
 }
 
 int spmv_launch(ptfem_ctx* ctx, const LinSys& A, int variant, const double* x, double* y, PcgWork* work, bool cg_dot) {

@@ -14,6 +14,11 @@ struct LinSys {
   const double* b = nullptr;     // [nn][S]
   int32_t stream_rows = 0;       // rows per tile of the streaming SpMV (0: vector kernel only)
   int32_t stream_cap = 0;        // staged entries per tile (shared-memory stage size / 12 bytes)
+  // optional processing-order view for the streaming kernel: row j of (prowptr, pcol, pval) is mesh row rowid[j]
+  const int32_t* rowid = nullptr;
+  const int32_t* prowptr = nullptr;
+  const int32_t* pcol = nullptr;
+  const double* pval = nullptr;
   int64_t row0 = 0;              // the system is rows [row0, row0+nn) of the arrays (row-range SpMV)
 };
 
@@ -26,4 +31,7 @@ int pcg_solve(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_opt
 int pcg_work_alloc(ptfem_ctx* ctx, PcgWork& w, int64_t nn, int S, int VS);
 void pcg_work_drop_graph(PcgWork& w);
 int resolve_variant(const LinSys& A, int variant);
+// pval = val gathered into processing order (one matrix): pval[prowptr[j]+t] = val[rowptr[rowid[j]]+t]
+int permute_values(ptfem_ctx* ctx, int64_t nn, const int32_t* rowptr, const int32_t* rowid, const int32_t* prowptr,
+                   const double* val, double* pval);
 }  // namespace ptfem

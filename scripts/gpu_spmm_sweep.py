@@ -8,9 +8,11 @@ import bench
 size = sys.argv[1] if len(sys.argv) > 1 else "L"
 mesh = meshgen.synth_slab(size, contact_enabled=False)
 confs = bench.sweep_definition(mesh, 8, 0)
-configs = [dict(XPREFETCH=0), dict(XPREFETCH=1), dict(XPREFETCH=1, STREAM_ROWS=32), dict(XPREFETCH=1, STREAM_ROWS=128), dict(XPREFETCH=0, STREAM_ROWS=32)]
+configs = [dict(MORTON=0), dict(MORTON=1), dict(MORTON=1, STREAM_ROWS=32), dict(MORTON=1, STREAM_ROWS=128), dict(MORTON=1, INTERLEAVE=0)]
+if len(sys.argv) > 2:
+    configs = [eval("dict(" + a + ")") for a in sys.argv[2:]]
 for c in configs:
-    for k in ("XPREFETCH", "STREAM_ROWS", "INTERLEAVE", "STREAM_STAGES"):
+    for k in ("XPREFETCH", "STREAM_ROWS", "INTERLEAVE", "STREAM_STAGES", "MORTON", "STREAM_CAP", "CTAS_PER_SM"):
         os.environ.pop("PTFEM_" + k, None)
     for k, v in c.items():
         os.environ["PTFEM_" + k] = str(v)
