@@ -220,6 +220,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-partitioned", action="store_true", help="N > 1: skip the row-partitioned single-solve extra")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="transport of the row-partitioned solve")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -325,13 +326,16 @@ def main():
         from pelvistim_fem_b200 import distsolve
         pmesh = meshgen.synth_slab(args.size)
         res = distsolve.partitioned_solve(ctx, pmesh, {1: 0.35, 2: 0.04, 3: 0.001, 4: 0.005, 5: 0.005}, [(102, 0.0)],
-                                          [(101, 15.975)], rank, world, check=True, rtol=RTOL)
+                                          [(101, 15.975)], rank, world, check=True, transport=args.transport, rtol=RTOL)
         t = torch.tensor([res["stats"]["solve_ms"], res["timings"]["spmv_ms"], res["timings"]["halo_ms"],
                           res["timings"]["allreduce_ms"], res["rel_err_vs_single"]], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t = t.tolist()
         part = {"workload": f"synth_slab {args.size} with contact pads, one Jacobi-PCG solve row-partitioned over {world} GPUs "
-                            "(NCCL halo exchange + 3-scalar all-reduce per iteration, single-reduction CG)",
+                            + ("(peer-memory transport: halo rows pulled with direct NVLink loads, 3-scalar all-reduce through "
+                               "mailboxes, no NCCL call in the iteration; single-reduction CG)" if args.transport == "p2p" else
+                               "(NCCL halo exchange + 3-scalar all-reduce per iteration, single-reduction CG)"),
+                "transport": args.transport,
                 "iterations": res["stats"]["iterations"], "solve_ms": t[0], "ms_per_iteration": t[0] / max(res["stats"]["iterations"], 1),
                 "spmv_ms": t[1], "halo_ms": t[2], "allreduce_ms": t[3], "rows_per_rank": res["nloc"], "halo_rows": res["nhalo"],
                 "single_gpu_solve_ms": res["single_gpu_ms"], "single_gpu_iterations": res["single_gpu_iterations"],

@@ -189,6 +189,14 @@ int ptfem_dist_system_create(ptfem_ctx* ctx, int64_t nloc, int64_t nhalo, const 
                              ptfem_mesh** out);
 int ptfem_dist_solve(ptfem_mesh* sys, const ptfem_solve_opts* opts, double* x_local, ptfem_solve_stats* stats,
                      double* ms_spmv, double* ms_halo, double* ms_allreduce);
+/* Peer-memory transport (NVLink P2P through CUDA IPC) instead of NCCL calls inside the iteration: every rank
+ * exports two IPC handles (its vector and its mailbox, 2 x 64 bytes), the launcher all-gathers them, and each
+ * rank connects.  halo_src[h] = index, in the owner's local numbering, of the row halo slot h mirrors.
+ * After a successful connect ptfem_dist_solve pulls halos with direct peer loads and reduces the three CG
+ * scalars through the mailboxes (ptfem_dist_init may then be called with id128 == NULL: no NCCL at all). */
+int ptfem_dist_p2p_export(ptfem_mesh* sys, void* handles128);
+int ptfem_dist_p2p_connect(ptfem_mesh* sys, int32_t nranks, const void* all_handles /*[nranks*128]*/,
+                           const int32_t* halo_src /*[nhalo]*/);
 
 #ifdef __cplusplus
 }

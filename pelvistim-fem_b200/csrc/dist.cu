@@ -119,6 +119,25 @@ __global__ void dist_pack_kernel(const double* __restrict__ u, const int32_t* __
   if (i < n) buf[i] = u[idx[i]];
 }
 
+// last CTA: tot[c] = sum_b partial[b*3 + c] with all threads (fixed order: strided per thread, then serial over
+// the 85 thread groups) - the single-thread version of this loop was ~40 % of an iteration at 592 CTAs
+__device__ __forceinline__ void sum3_partials(const double* __restrict__ partial, unsigned nblocks, double* s_part /*[255]*/,
+                                              double tot[3]) {
+  const int t = threadIdx.x;
+  if (t < 255) {
+    const int c = t % 3, g = t / 3;
+    double acc = 0.0;
+    for (unsigned b = g; b < nblocks; b += 85) acc += __ldcg(partial + (size_t)b * 3 + c);
+    s_part[t] = acc;
+  }
+  __syncthreads();
+  for (int c = 0; c < 3; ++c) {
+    double a = 0.0;
+    for (int g = 0; g < 85; ++g) a += s_part[g * 3 + c];
+    tot[c] = a;
+  }
+}
+
 // first = 1: u = dinv*r only (p = s = 0 beforehand, alpha/beta unused)
 __global__ void __launch_bounds__(kT) dist_update_kernel(int64_t n, const double* __restrict__ scal,
                                                          const double* __restrict__ dinv, const double* __restrict__ w,
@@ -187,11 +206,12 @@ __global__ void __launch_bounds__(kT) dist_dots_kernel(int64_t n, const double* 
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
   __syncthreads();
-  if (s_last && threadIdx.x < 3) {
+  if (s_last) {
+    __shared__ double s_part[255];
     __threadfence();
-    double acc = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) acc += __ldcg(partial + (size_t)b * 3 + threadIdx.x);
-    scal[D_GAMMA + threadIdx.x] = acc;
+    double tot[3];
+    sum3_partials(partial, gridDim.x, s_part, tot);
+    if (threadIdx.x < 3) scal[D_GAMMA + threadIdx.x] = tot[threadIdx.x];
   }
 }
 
@@ -213,6 +233,191 @@ __global__ void dist_scalar_kernel(double* __restrict__ scal, int first) {
   scal[D_GAMMA_OLD] = gamma;
 }
 
+// ---- peer-memory path (NVLink P2P through CUDA IPC): no NCCL call inside the iteration ----------------------
+// Every rank exports its u vector and a small mailbox.  Per iteration:
+//   update kernel   -> last CTA bumps the local iteration counter and PUSHES "u of iteration k is ready" into each
+//                      neighbour's mailbox (remote store, release at system scope)
+//   pull kernel     -> waits (acquire) for the neighbour's ready flag in the LOCAL mailbox, then loads the halo
+//                      entries straight out of the neighbour's u (ld.volatile over NVLink) - no pack, no send/recv
+//   SpMV            -> one launch over all rows
+//   dots kernel     -> last CTA pushes (gamma, delta, rr, seq) into the mailbox of EVERY rank, waits until its own
+//                      mailbox holds all nranks contributions of this iteration, sums them in rank order (identical
+//                      on all ranks, deterministic) and computes alpha / beta: all-reduce + scalar kernel in one
+// The all-reduce of iteration k is also the barrier that protects u: a neighbour contributes to it only after its
+// pull of iteration k, and this rank overwrites u (update k+1) only after the all-reduce completed.
+// Mailboxes are double-buffered by iteration parity.  Every wait is bounded; a timeout raises err in the mailbox.
+constexpr int kMaxRanks = 16;
+constexpr unsigned long long kSpinLimit = 1ull << 23;   // bounded waits: a few seconds, then err is raised
+struct alignas(16) MailBox {
+  double v[3];
+  unsigned long long seq;
+};
+struct Mail {
+  unsigned long long iter;                    // local: iterations started (written by the update kernel)
+  unsigned long long err;                     // local: a bounded wait timed out
+  unsigned long long nred;                    // local: reductions started (sequence number of the mailbox protocol)
+  unsigned long long pad[5];
+  unsigned long long ready_from[kMaxRanks];   // ready_from[q] = k : rank q's u of iteration k is complete (pushed by q)
+  MailBox box[2][kMaxRanks];                  // box[k & 1][q] : rank q's partial sums of iteration k (pushed by q)
+};
+struct PeerTable {
+  Mail* mail[kMaxRanks];       // every rank's mailbox (own entry = local pointer)
+  const double* u[kMaxRanks];  // neighbours' u vectors, indexed by rank (null when not a neighbour)
+  int32_t nbr_rank[kMaxRanks];
+  int32_t nnbr, rank, nranks;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_volatile_f64(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_f64(double* p, double v) {
+  asm volatile("st.volatile.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+// spin until *p >= want (bounded); returns false on timeout
+__device__ __forceinline__ bool wait_ge(const unsigned long long* p, unsigned long long want, unsigned long long* err) {
+  for (unsigned long long n = 0; n < kSpinLimit; ++n) {
+    if (ld_acquire_sys(p) >= want) return true;
+    __nanosleep(64);
+  }
+  atomicExch(err, 1ull);
+  return false;
+}
+
+// update + "u is ready" signal.  first: x = 0, r = b, u = D^-1 b, p = s = 0.
+__global__ void __launch_bounds__(kT) p2p_update_kernel(int64_t n, int first, const double* __restrict__ b,
+                                                        const double* __restrict__ scal, const double* __restrict__ dinv,
+                                                        const double* __restrict__ w, double* __restrict__ p,
+                                                        double* __restrict__ s, double* __restrict__ x,
+                                                        double* __restrict__ r, double* __restrict__ u, PeerTable pt,
+                                                        unsigned int* __restrict__ ticket) {
+  __shared__ int s_last;
+  const double alpha = scal[D_ALPHA], beta = scal[D_BETA];
+  const int64_t stride = (int64_t)gridDim.x * kT;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < n; i += stride) {
+    if (first) {
+      p[i] = 0.0; s[i] = 0.0; x[i] = 0.0;
+      r[i] = b[i];
+      u[i] = b[i] * dinv[i];
+    } else {
+      const double pi = fma(beta, p[i], u[i]);
+      const double si = fma(beta, s[i], w[i]);
+      const double ri = fma(-alpha, si, r[i]);
+      p[i] = pi; s[i] = si;
+      x[i] = fma(alpha, pi, x[i]);
+      r[i] = ri;
+      u[i] = ri * dinv[i];
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence_system();
+    Mail* me = pt.mail[pt.rank];
+    const unsigned long long k = me->iter + 1;
+    me->iter = k;
+    for (int j = 0; j < pt.nnbr; ++j) st_release_sys(&pt.mail[pt.nbr_rank[j]]->ready_from[pt.rank], k);
+  }
+}
+
+// halo pull: slot h of neighbour j (recv_ptr ranges) = peer u[src[h]]
+__global__ void __launch_bounds__(kT) p2p_pull_kernel(int64_t nloc, const int32_t* __restrict__ recv_ptr,
+                                                      const int32_t* __restrict__ src, double* __restrict__ u, PeerTable pt) {
+  Mail* me = pt.mail[pt.rank];
+  const unsigned long long k = me->iter;
+  const int64_t stride = (int64_t)gridDim.x * kT;
+  for (int j = 0; j < pt.nnbr; ++j) {
+    const int q = pt.nbr_rank[j];
+    if (threadIdx.x == 0) wait_ge(&me->ready_from[q], k, &me->err);
+    __syncthreads();
+    const double* pu = pt.u[q];
+    for (int64_t h = recv_ptr[j] + (int64_t)blockIdx.x * kT + threadIdx.x; h < recv_ptr[j + 1]; h += stride)
+      u[nloc + h] = ld_volatile_f64(pu + src[h]);
+  }
+}
+
+// local (r.u, w.u, r.r); last CTA: all-reduce through the mailboxes + Chronopoulos-Gear scalars
+__global__ void __launch_bounds__(kT) p2p_dots_kernel(int64_t n, const double* __restrict__ r, const double* __restrict__ u,
+                                                      const double* __restrict__ w, double* __restrict__ partial,
+                                                      double* __restrict__ scal, unsigned int* __restrict__ ticket,
+                                                      PeerTable pt, int first, int bnorm) {
+  __shared__ double s_red[3 * (kT / 32)];
+  __shared__ int s_last;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * kT;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < n; i += stride) {
+    const double ri = r[i], ui = u[i];
+    a0 = fma(ri, ui, a0);
+    a1 = fma(w[i], ui, a1);
+    a2 = fma(ri, ri, a2);
+  }
+  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { s_red[wid * 3] = a0; s_red[wid * 3 + 1] = a1; s_red[wid * 3 + 2] = a2; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double acc = 0.0;
+    for (int k = 0; k < kT / 32; ++k) acc += s_red[k * 3 + threadIdx.x];
+    partial[(size_t)blockIdx.x * 3 + threadIdx.x] = acc;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __shared__ double s_part[255];
+  __threadfence();
+  double loc[3];
+  sum3_partials(partial, gridDim.x, s_part, loc);
+  if (threadIdx.x != 0) return;
+  Mail* me = pt.mail[pt.rank];
+  // every rank runs the same sequence of reductions, so a local counter numbers them consistently
+  const unsigned long long seq = me->nred + 1;
+  me->nred = seq;
+  const int par = (int)(seq & 1);
+  for (int q = 0; q < pt.nranks; ++q) {
+    MailBox* bx = &pt.mail[q]->box[par][pt.rank];
+    st_volatile_f64(&bx->v[0], loc[0]);
+    st_volatile_f64(&bx->v[1], loc[1]);
+    st_volatile_f64(&bx->v[2], loc[2]);
+    st_release_sys(&bx->seq, seq);
+  }
+  double tot[3] = {0.0, 0.0, 0.0};
+  for (int q = 0; q < pt.nranks; ++q) {
+    MailBox* bx = &me->box[par][q];
+    if (!wait_ge(&bx->seq, seq, &me->err)) break;
+    for (int c = 0; c < 3; ++c) tot[c] += ld_volatile_f64(&bx->v[c]);
+  }
+  if (bnorm) {
+    scal[D_BN2] = tot[0];
+    return;
+  }
+  const double gamma = tot[0], delta = tot[1];
+  double alpha, beta;
+  if (first) {
+    beta = 0.0;
+    alpha = delta > 0.0 ? gamma / delta : 0.0;
+  } else {
+    const double g_old = scal[D_GAMMA_OLD], a_old = scal[D_ALPHA];
+    beta = g_old > 0.0 ? gamma / g_old : 0.0;
+    const double den = a_old != 0.0 ? delta - beta * gamma / a_old : 0.0;
+    alpha = den > 0.0 ? gamma / den : 0.0;
+  }
+  scal[D_GAMMA] = gamma; scal[D_DELTA] = delta; scal[D_RR] = tot[2];
+  scal[D_ALPHA] = alpha; scal[D_BETA] = beta; scal[D_GAMMA_OLD] = gamma;
+}
+
 int dist_grid(ptfem_ctx* ctx, int64_t n) {
   int64_t g = (n + kT - 1) / kT;
   const int64_t cap = (int64_t)ctx->sm_count * 4;
@@ -231,6 +436,12 @@ struct DistState {
   bool warmed = false;
   int64_t i0 = 0, i1 = 0;  // rows [i0, i1) need no halo value
   int32_t stream_rows = 0, stream_cap = 0;  // streaming SpMV tile geometry valid for any row range
+  // peer-memory path
+  bool p2p = false;
+  DevBuf<Mail> mail;
+  DevBuf<int32_t> halo_src, recv_ptr_dev;
+  PeerTable pt;
+  std::vector<void*> opened;   // cudaIpcOpenMemHandle mappings to close
 };
 
 }  // namespace
@@ -312,6 +523,29 @@ static int dist_iteration(ptfem_mesh* m, DistState& d) {
   return dist_reduce(m, d, 0);
 }
 
+// ---- peer-memory iteration --------------------------------------------------------------------------------
+static int p2p_matvec_reduce(ptfem_mesh* m, DistState& d, int first) {
+  ptfem_ctx* ctx = m->ctx;
+  if (m->nhalo > 0) {
+    int g = ceil_div(m->nhalo / (m->nnbr > 0 ? m->nnbr : 1) + 1, kT);
+    if (g > 64) g = 64;
+    p2p_pull_kernel<<<g, kT, 0, ctx->stream>>>(m->nloc, d.recv_ptr_dev.p, d.halo_src.p, d.u.p, d.pt);
+    PT_LAUNCH_CHECK(ctx);
+  }
+  PT_TRY(spmv_rows(m, d, 0, m->nloc));
+  p2p_dots_kernel<<<dist_grid(ctx, m->nloc), kT, 0, ctx->stream>>>(m->nloc, d.r.p, d.u.p, d.w.p, d.partial.p, d.scal.p,
+                                                                   d.ticket.p, d.pt, first, 0);
+  PT_LAUNCH_CHECK(ctx);
+  return PTFEM_OK;
+}
+static int p2p_iteration(ptfem_mesh* m, DistState& d, int first) {
+  ptfem_ctx* ctx = m->ctx;
+  p2p_update_kernel<<<dist_grid(ctx, m->nloc), kT, 0, ctx->stream>>>(m->nloc, first, m->b.p, d.scal.p, m->dinv.p, d.w.p, d.p.p,
+                                                                     d.s.p, d.x.p, d.r.p, d.u.p, d.pt, d.ticket.p);
+  PT_LAUNCH_CHECK(ctx);
+  return p2p_matvec_reduce(m, d, first);
+}
+
 void ptfem_dist_ctx_release(ptfem_ctx* ctx) {
   if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy((ncclComm_t)ctx->comm);
   ctx->comm = nullptr;
@@ -323,6 +557,7 @@ void ptfem_dist_mesh_release(ptfem_mesh* m) {
   if (d->graph) cudaGraphExecDestroy(d->graph);
   if (d->ev_u) cudaEventDestroy(d->ev_u);
   if (d->ev_halo) cudaEventDestroy(d->ev_halo);
+  for (void* p : d->opened) cudaIpcCloseMemHandle(p);
   delete m->dist;
   m->dist = nullptr;
 }
@@ -340,9 +575,14 @@ int ptfem_dist_unique_id(const char* libnccl_path, void* id128) {
 }
 
 int ptfem_dist_init(ptfem_ctx* ctx, const char* libnccl_path, const void* id128, int32_t rank, int32_t nranks) {
-  PT_ARG(ctx && id128, "null pointer");
+  PT_ARG(ctx, "null pointer");
   PT_ARG(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
   PT_CK(cudaSetDevice(ctx->device));
+  if (!id128) {  // peer-memory only: no NCCL communicator
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    return PTFEM_OK;
+  }
   NcclApi* api = nullptr;
   PT_TRY(load_nccl(libnccl_path, &api));
   if (ctx->comm) return set_err(PTFEM_ERR_STATE, "context already has a communicator");
@@ -374,7 +614,7 @@ int ptfem_dist_system_create(ptfem_ctx* ctx, int64_t nloc, int64_t nhalo, const 
   PT_ARG(ctx && out && rowptr && col && val && b, "null pointer");
   PT_ARG(nloc > 0 && nhalo >= 0 && nnbr >= 0, "bad sizes");
   PT_ARG(nnbr == 0 || (nbr_rank && send_ptr && send_idx && recv_ptr), "null neighbour arrays");
-  if (nnbr > 0 && !ctx->comm) return set_err(PTFEM_ERR_STATE, "ptfem_dist_init has not been called on this context");
+  if (nnbr > 0 && ctx->nranks < 2) return set_err(PTFEM_ERR_STATE, "ptfem_dist_init has not been called on this context");
   *out = nullptr;
   const int64_t nnz = rowptr[nloc];
   for (int64_t k = 0; k < nnz; ++k)
@@ -497,8 +737,11 @@ int ptfem_dist_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* x_loca
   const int grid = dist_grid(ctx, m->nloc);
   double* h = ctx->h_pinned;
 
+  const bool p2p = d.p2p;
+  if (ctx->nranks > 1 && !p2p && !ctx->comm)
+    return set_err(PTFEM_ERR_STATE, "neither an NCCL communicator (ptfem_dist_init) nor peer memory (ptfem_dist_p2p_connect) is set up");
   // first use of a peer connection / collective sets up NCCL channels (seconds): keep it out of the timing
-  if (ctx->nranks > 1 && !d.warmed) {
+  if (ctx->nranks > 1 && !p2p && !d.warmed) {
     PT_TRY(halo_exchange(m, d, ctx->stream));
     PT_NCCL(api, api->AllReduce(d.partial.p, d.partial.p, 3, kNcclFloat64, kNcclSum, (ncclComm_t)ctx->comm, ctx->stream));
     PT_CK(cudaStreamSynchronize(ctx->stream));
@@ -508,18 +751,25 @@ int ptfem_dist_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* x_loca
   PT_CK(cudaEventCreate(&e0));
   PT_CK(cudaEventCreate(&e1));
   PT_CK(cudaEventRecord(e0, ctx->stream));
-  // ||b||^2 via the dots kernel (r = u = b): gamma slot
-  dist_dots_kernel<<<grid, kT, 0, ctx->stream>>>(m->nloc, m->b.p, m->b.p, m->b.p, d.partial.p, d.scal.p, d.ticket.p);
-  PT_LAUNCH_CHECK(ctx);
-  if (ctx->nranks > 1)
-    PT_NCCL(api, api->AllReduce(d.scal.p + D_GAMMA, d.scal.p + D_BN2, 1, kNcclFloat64, kNcclSum, (ncclComm_t)ctx->comm, ctx->stream));
-  else
-    PT_CK(cudaMemcpyAsync(d.scal.p + D_BN2, d.scal.p + D_GAMMA, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  // x = 0, r = b, u = D^-1 r, w = A u, first scalars
-  dist_init_kernel<<<grid, kT, 0, ctx->stream>>>(m->nloc, m->b.p, m->dinv.p, d.p.p, d.s.p, d.x.p, d.r.p, d.u.p);
-  PT_LAUNCH_CHECK(ctx);
-  PT_TRY(dist_matvec(m, d));
-  PT_TRY(dist_reduce(m, d, 1));
+  if (p2p) {
+    // ||b||^2 through the mailboxes, then iteration 0 (x = 0, r = b, u = D^-1 r, w = A u, first scalars)
+    p2p_dots_kernel<<<grid, kT, 0, ctx->stream>>>(m->nloc, m->b.p, m->b.p, m->b.p, d.partial.p, d.scal.p, d.ticket.p, d.pt, 0, 1);
+    PT_LAUNCH_CHECK(ctx);
+    PT_TRY(p2p_iteration(m, d, 1));
+  } else {
+    // ||b||^2 via the dots kernel (r = u = b): gamma slot
+    dist_dots_kernel<<<grid, kT, 0, ctx->stream>>>(m->nloc, m->b.p, m->b.p, m->b.p, d.partial.p, d.scal.p, d.ticket.p);
+    PT_LAUNCH_CHECK(ctx);
+    if (ctx->nranks > 1)
+      PT_NCCL(api, api->AllReduce(d.scal.p + D_GAMMA, d.scal.p + D_BN2, 1, kNcclFloat64, kNcclSum, (ncclComm_t)ctx->comm, ctx->stream));
+    else
+      PT_CK(cudaMemcpyAsync(d.scal.p + D_BN2, d.scal.p + D_GAMMA, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    // x = 0, r = b, u = D^-1 r, w = A u, first scalars
+    dist_init_kernel<<<grid, kT, 0, ctx->stream>>>(m->nloc, m->b.p, m->dinv.p, d.p.p, d.s.p, d.x.p, d.r.p, d.u.p);
+    PT_LAUNCH_CHECK(ctx);
+    PT_TRY(dist_matvec(m, d));
+    PT_TRY(dist_reduce(m, d, 1));
+  }
 
   auto read_scal = [&]() -> int {
     PT_CK(cudaMemcpyAsync(h, d.scal.p, D_COUNT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -542,7 +792,7 @@ int ptfem_dist_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* x_loca
         int rc = PTFEM_OK;
         PT_CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
         const int64_t l0 = ctx->launches;
-        for (int k = 0; k < check && rc == PTFEM_OK; ++k) rc = dist_iteration(m, d);
+        for (int k = 0; k < check && rc == PTFEM_OK; ++k) rc = p2p ? p2p_iteration(m, d, 0) : dist_iteration(m, d);
         d.graph_launches = ctx->launches - l0;
         ctx->launches = l0;
         cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
@@ -556,7 +806,7 @@ int ptfem_dist_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* x_loca
       PT_CK(cudaGraphLaunch(d.graph, ctx->stream));
       ctx->launches += d.graph_launches;
     } else {
-      for (int k = 0; k < n_it; ++k) PT_TRY(dist_iteration(m, d));
+      for (int k = 0; k < n_it; ++k) PT_TRY(p2p ? p2p_iteration(m, d, 0) : dist_iteration(m, d));
     }
     it += n_it;
     PT_TRY(read_scal());
@@ -583,18 +833,30 @@ int ptfem_dist_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* x_loca
     PT_CK(cudaEventRecord(e1, ctx->stream));
     PT_CK(cudaEventSynchronize(e1));
     cudaEventElapsedTime(&t_spmv, e0, e1);
-    PT_CK(cudaEventRecord(e0, ctx->stream));
-    for (int k = 0; k < reps; ++k) PT_TRY(halo_exchange(m, d, ctx->stream));
-    PT_CK(cudaEventRecord(e1, ctx->stream));
-    PT_CK(cudaEventSynchronize(e1));
-    cudaEventElapsedTime(&t_halo, e0, e1);
-    PT_CK(cudaEventRecord(e0, ctx->stream));
-    if (ctx->nranks > 1)
-      for (int k = 0; k < reps; ++k)
-        PT_NCCL(api, api->AllReduce(d.partial.p, d.partial.p, 3, kNcclFloat64, kNcclSum, (ncclComm_t)ctx->comm, ctx->stream));
-    PT_CK(cudaEventRecord(e1, ctx->stream));
-    PT_CK(cudaEventSynchronize(e1));
-    cudaEventElapsedTime(&t_ar, e0, e1);
+    if (!p2p) {   // (the peer-memory phases are not separate launches; they are part of ms_per_iteration)
+      PT_CK(cudaEventRecord(e0, ctx->stream));
+      for (int k = 0; k < reps; ++k) PT_TRY(halo_exchange(m, d, ctx->stream));
+      PT_CK(cudaEventRecord(e1, ctx->stream));
+      PT_CK(cudaEventSynchronize(e1));
+      cudaEventElapsedTime(&t_halo, e0, e1);
+      PT_CK(cudaEventRecord(e0, ctx->stream));
+      if (ctx->nranks > 1)
+        for (int k = 0; k < reps; ++k)
+          PT_NCCL(api, api->AllReduce(d.partial.p, d.partial.p, 3, kNcclFloat64, kNcclSum, (ncclComm_t)ctx->comm, ctx->stream));
+      PT_CK(cudaEventRecord(e1, ctx->stream));
+      PT_CK(cudaEventSynchronize(e1));
+      cudaEventElapsedTime(&t_ar, e0, e1);
+    }
+  }
+  if (p2p) {
+    Mail hm;
+    PT_CK(cudaMemcpy(&hm, d.mail.p, sizeof(Mail), cudaMemcpyDeviceToHost));
+    if (hm.err) {
+      cudaMemset(&d.mail.p->err, 0, sizeof(unsigned long long));
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      return set_err(PTFEM_ERR_STATE, "peer-memory solve: a wait on another rank timed out (iteration %llu)", hm.iter);
+    }
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
@@ -616,6 +878,74 @@ int ptfem_dist_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* x_loca
     stats->spmv_ms = t_spmv / reps;
   }
   if (!converged) return set_err(PTFEM_ERR_NOCONV, "distributed PCG did not reach rtol=%g in %d iterations (rel. residual %.3e)", o.rtol, it, rel);
+  return PTFEM_OK;
+}
+
+int ptfem_dist_p2p_export(ptfem_mesh* m, void* handles128) {
+  PT_ARG(m && m->is_dist && m->dist && handles128, "not a distributed system");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  DistState& d = *m->dist;
+  if (!d.mail.p) {
+    PT_TRY(d.mail.alloc(1));
+    PT_CK(cudaMemsetAsync(d.mail.p, 0, sizeof(Mail), m->ctx->stream));
+    PT_CK(cudaStreamSynchronize(m->ctx->stream));
+  }
+  cudaIpcMemHandle_t h[2];
+  PT_CK(cudaIpcGetMemHandle(&h[0], d.u.p));
+  PT_CK(cudaIpcGetMemHandle(&h[1], d.mail.p));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(handles128, h, 128);
+  return PTFEM_OK;
+}
+
+int ptfem_dist_p2p_connect(ptfem_mesh* m, int32_t nranks, const void* all_handles, const int32_t* halo_src) {
+  PT_ARG(m && m->is_dist && m->dist && all_handles, "not a distributed system");
+  ptfem_ctx* ctx = m->ctx;
+  PT_ARG(nranks == ctx->nranks && nranks <= kMaxRanks, "rank count mismatch (at most 16 ranks)");
+  PT_ARG(m->nhalo == 0 || halo_src, "null halo source list");
+  PT_CK(cudaSetDevice(ctx->device));
+  DistState& d = *m->dist;
+  if (!d.mail.p) return set_err(PTFEM_ERR_STATE, "ptfem_dist_p2p_export must be called first");
+  PeerTable pt;
+  memset(&pt, 0, sizeof pt);
+  pt.rank = ctx->rank;
+  pt.nranks = nranks;
+  pt.nnbr = m->nnbr;
+  if (m->nnbr > kMaxRanks) return set_err(PTFEM_ERR_ARG, "too many neighbours");
+  for (int k = 0; k < m->nnbr; ++k) pt.nbr_rank[k] = m->nbr_rank[k];
+  const cudaIpcMemHandle_t* hs = reinterpret_cast<const cudaIpcMemHandle_t*>(all_handles);
+  for (int q = 0; q < nranks; ++q) {
+    if (q == ctx->rank) {
+      pt.mail[q] = d.mail.p;
+      pt.u[q] = d.u.p;
+      continue;
+    }
+    void* pm = nullptr;
+    PT_CK(cudaIpcOpenMemHandle(&pm, hs[2 * q + 1], cudaIpcMemLazyEnablePeerAccess));
+    d.opened.push_back(pm);
+    pt.mail[q] = reinterpret_cast<Mail*>(pm);
+    bool is_nbr = false;
+    for (int k = 0; k < m->nnbr; ++k) is_nbr = is_nbr || m->nbr_rank[k] == q;
+    if (is_nbr) {
+      void* pu = nullptr;
+      PT_CK(cudaIpcOpenMemHandle(&pu, hs[2 * q], cudaIpcMemLazyEnablePeerAccess));
+      d.opened.push_back(pu);
+      pt.u[q] = reinterpret_cast<const double*>(pu);
+    }
+  }
+  d.pt = pt;
+  PT_TRY(d.halo_src.alloc(m->nhalo));
+  PT_TRY(d.recv_ptr_dev.alloc(m->nnbr + 1));
+  if (m->nhalo > 0)
+    PT_CK(cudaMemcpyAsync(d.halo_src.p, halo_src, m->nhalo * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (m->nnbr > 0)
+    PT_CK(cudaMemcpyAsync(d.recv_ptr_dev.p, m->recv_ptr.data(), (m->nnbr + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  else
+    PT_CK(cudaMemsetAsync(d.recv_ptr_dev.p, 0, sizeof(int32_t), ctx->stream));
+  PT_CK(cudaStreamSynchronize(ctx->stream));
+  d.p2p = true;
+  if (d.graph) cudaGraphExecDestroy(d.graph);
+  d.graph = nullptr;
   return PTFEM_OK;
 }
 

@@ -480,12 +480,22 @@ __global__ void __launch_bounds__(kStreamThreads*(S == 1 ? TPR : S / 2))
       }
     } else {
       double2 acc = make_double2(0.0, 0.0);
-#pragma unroll 4
-      for (int32_t k = b - a0; k < e - a0; ++k) {
+      // TPR doubles as the unroll selector of the multi-RHS path (tuning knob PTFEM_STREAM_TPR): 1 -> 4, 2 -> 8, 4 -> 2
+      auto body = [&](int32_t k) {
         const double a = sv[k];
         const double2 xv = ldg_f64x2_hint(x + (int64_t)sc[k] * S + 2 * lane, pol_keep);
         acc.x = fma(a, xv.x, acc.x);
         acc.y = fma(a, xv.y, acc.y);
+      };
+      if constexpr (TPR == 2) {
+#pragma unroll 8
+        for (int32_t k = b - a0; k < e - a0; ++k) body(k);
+      } else if constexpr (TPR == 4) {
+#pragma unroll 2
+        for (int32_t k = b - a0; k < e - a0; ++k) body(k);
+      } else {
+#pragma unroll 4
+        for (int32_t k = b - a0; k < e - a0; ++k) body(k);
       }
       if (live) {
         *reinterpret_cast<double2*>(y + ro * S + 2 * lane) = acc;
@@ -868,6 +878,8 @@ int launch_stream(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y, P
     if (stages >= 3) return tpr == 2 ? launch_stream_t<1, 3, 2, DOT>(ctx, A, x, y, w) : launch_stream_t<1, 3, 1, DOT>(ctx, A, x, y, w);
     return tpr == 2 ? launch_stream_t<1, 2, 2, DOT>(ctx, A, x, y, w) : launch_stream_t<1, 2, 1, DOT>(ctx, A, x, y, w);
   } else {
+    if (tpr == 2) return launch_stream_t<S, 2, 2, DOT>(ctx, A, x, y, w);
+    if (tpr == 4) return launch_stream_t<S, 2, 4, DOT>(ctx, A, x, y, w);
     return launch_stream_t<S, 2, 1, DOT>(ctx, A, x, y, w);
   }
 }

@@ -11,7 +11,7 @@ import numpy as np
 from . import engine, partition
 
 
-def partitioned_solve(ctx, mesh, sigma_by_body, dirichlet, neumann, rank, world, check=True, **opts):
+def partitioned_solve(ctx, mesh, sigma_by_body, dirichlet, neumann, rank, world, check=True, transport="p2p", **opts):
     """Returns dict(x_local, row0, stats, timings, nloc, nhalo, rel_err_vs_single)."""
     import torch.distributed as dist
     dm = ctx.mesh(mesh.nodes, mesh.tets, mesh.region, mesh.tris, mesh.bcid)
@@ -30,10 +30,18 @@ def partitioned_solve(ctx, mesh, sigma_by_body, dirichlet, neumann, rank, world,
     dm.close()
     blk = partition.local_block(rowptr, col, val, b, rank, world)
     if world > 1:
-        ids = [engine.dist_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        engine.dist_init(ctx, ids[0], rank, world)
+        if transport == "nccl":
+            ids = [engine.dist_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            engine.dist_init(ctx, ids[0], rank, world)
+        else:
+            engine.dist_init(ctx, None, rank, world)
     ds = engine.DistSystem(ctx, blk)
+    if world > 1 and transport == "p2p":
+        handles = [None] * world
+        dist.all_gather_object(handles, ds.p2p_export())
+        ds.p2p_connect(handles, partition.halo_sources(blk, n=rowptr.shape[0] - 1))
+        dist.barrier()
     t0 = time.perf_counter()
     x = ds.solve(**opts)
     wall = time.perf_counter() - t0
@@ -43,6 +51,8 @@ def partitioned_solve(ctx, mesh, sigma_by_body, dirichlet, neumann, rank, world,
         out["rel_err_vs_single"] = float(np.abs(x - ref).max() / max(np.abs(phi_single).max(), 1e-300))
         out["single_gpu_ms"] = single_stats["solve_ms"]
         out["single_gpu_iterations"] = single_stats["iterations"]
+    if world > 1:
+        dist.barrier()          # nobody unmaps peer memory while a neighbour may still read it
     ds.close()
     if world > 1:
         engine.dist_finalize(ctx)

@@ -109,6 +109,8 @@ def load_library():
         "ptfem_dist_finalize": (C.c_int, [vp]),
         "ptfem_dist_system_create": (C.c_int, [vp, i64, i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, P(vp)]),
         "ptfem_dist_solve": (C.c_int, [vp, P(SolveOpts), vp, P(SolveStats), P(dbl), P(dbl), P(dbl)]),
+        "ptfem_dist_p2p_export": (C.c_int, [vp, vp]),
+        "ptfem_dist_p2p_connect": (C.c_int, [vp, i32, vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)          # AttributeError here = header and library out of sync
@@ -458,7 +460,11 @@ def dist_unique_id(libnccl=None):
     return buf.raw
 
 
-def dist_init(ctx: Context, unique_id: bytes, rank, nranks, libnccl=None):
+def dist_init(ctx: Context, unique_id, rank, nranks, libnccl=None):
+    """``unique_id`` = the 128-byte ncclUniqueId, or ``None`` for the peer-memory-only transport (no NCCL)."""
+    if unique_id is None:
+        ctx._ck(ctx.lib.ptfem_dist_init(ctx._h, None, None, rank, nranks))
+        return
     buf = C.create_string_buffer(unique_id, 128)
     ctx._ck(ctx.lib.ptfem_dist_init(ctx._h, (libnccl or nccl_library_path()).encode(), buf, rank, nranks))
 
@@ -482,6 +488,17 @@ class DistSystem:
                                                   _ptr(arrs[5]) if nnbr else None, _ptr(arrs[6]) if nnbr else None,
                                                   _ptr(arrs[7]) if nnbr else None, C.byref(h)))
         self._h = h
+
+    def p2p_export(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self.ctx._ck(self.lib.ptfem_dist_p2p_export(self._h, buf))
+        return buf.raw
+
+    def p2p_connect(self, all_handles, halo_src):
+        """``all_handles``: list (by rank) of the 128-byte exports; ``halo_src``: owner-local row of every halo slot."""
+        blob = b"".join(all_handles)
+        src = _i32(halo_src)
+        self.ctx._ck(self.lib.ptfem_dist_p2p_connect(self._h, len(all_handles), blob, _ptr(src) if src.size else None))
 
     def solve(self, **opts):
         o = SolveOpts()

@@ -103,6 +103,14 @@ def check_consistency(blocks):
     return True
 
 
+def halo_sources(blk: LocalBlock, bounds=None, n=None):
+    """Owner-local row index mirrored by every halo slot (for the peer-memory pull): global id - owner's row0."""
+    if bounds is None:
+        bounds = row_bounds(n, blk.nranks)
+    owner = np.searchsorted(np.asarray(bounds), blk.halo_global, side="right") - 1
+    return (blk.halo_global - np.asarray(bounds)[owner]).astype(np.int32)
+
+
 def local_spmv(blk: LocalBlock, u_full):
     """y_loc = A_loc [u_owned ; u_halo]."""
     import scipy.sparse as sp

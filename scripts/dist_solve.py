@@ -10,6 +10,7 @@ import pelvistim_fem_b200
 from pelvistim_fem_b200 import engine, meshgen, distsolve
 
 size = sys.argv[1] if len(sys.argv) > 1 else "M"
+transport = sys.argv[2] if len(sys.argv) > 2 else "p2p"
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 if world > 1:
@@ -20,8 +21,8 @@ else:
 mesh = meshgen.synth_slab(size)
 sig = {1: 0.35, 2: 0.04, 3: 0.001, 4: 0.005, 5: 0.005}
 ctx = engine.Context(local)
-res = distsolve.partitioned_solve(ctx, mesh, sig, [(102, 0.0)], [(101, 15.975)], rank, world, check=True, rtol=1e-10)
-line = dict(rank=rank, world=world, size=size, nloc=res["nloc"], nhalo=res["nhalo"], iterations=res["stats"]["iterations"],
+res = distsolve.partitioned_solve(ctx, mesh, sig, [(102, 0.0)], [(101, 15.975)], rank, world, check=True, transport=transport, rtol=1e-10)
+line = dict(rank=rank, world=world, size=size, transport=transport, nloc=res["nloc"], nhalo=res["nhalo"], iterations=res["stats"]["iterations"],
             solve_ms=res["stats"]["solve_ms"], ms_per_iter=res["stats"]["solve_ms"] / max(res["stats"]["iterations"], 1),
             rel_err_vs_single=res["rel_err_vs_single"], single_gpu_ms=res["single_gpu_ms"], single_gpu_iterations=res["single_gpu_iterations"],
             **res["timings"])
