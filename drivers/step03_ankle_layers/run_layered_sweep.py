@@ -20,7 +20,7 @@ import yaml
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import _common  # noqa: F401,E402
-from pelvistim_fem_b200 import elmer_io, meshgen, pipeline, sif, sweep  # noqa: E402
+from pelvistim_fem_b200 import elmer_io, gmsh_io, meshgen, pipeline, sif, sweep  # noqa: E402
 
 HERE = Path(__file__).resolve().parent
 RESULTS_DIR = HERE / "results"
@@ -65,6 +65,10 @@ def build_mesh(p, t_fat, elec_r, run_dir, coarse=False):
     mesh = meshgen.layered_slab_mesh(Lx, Ly, Lz, ls["t_skin"], t_fat, t_contact or 0.0005, active_xy, return_xy, elec_r,
                                      shape, n_muscle=n_m, n_fat=n_f, n_skin=2, n_contact=1, h_bulk=lc_bulk,
                                      h_elec=lc_elec, contact_enabled=contact)
+    # same per-case files as the reference: mesh.msh (gmsh.write, :342-343) then the ElmerGrid 14 2 conversion (:1077)
+    names = {(3, 1): "muscle", (3, 2): "fat", (3, 3): "skin", (3, 4): "contact_active", (3, 5): "contact_return",
+             (2, 101): "active", (2, 102): "return", (2, 103): "other"}
+    gmsh_io.write_msh(run_dir / "mesh.msh", mesh, names)
     elmer_io.write_elmer_mesh(run_dir / "elmer_mesh", mesh)
     z_top = Lz + t_contact
     body_info = dict(contact_enabled=contact, z_skin_top=Lz, z_elec_top=z_top, z_e1_skin=Lz, z_e2_skin=Lz,

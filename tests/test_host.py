@@ -159,3 +159,81 @@ def test_no_cpu_fallback_without_device():
     with pytest.raises(engine.PtfemError) as ei:
         engine.Context(0)
     assert "no CPU fallback" in str(ei.value)
+
+
+# -- Gmsh .msh reader / ElmerGrid 14 2 ---------------------------------------------------------------------
+MSH41 = """$MeshFormat
+4.1 0 8
+$EndMeshFormat
+$PhysicalNames
+2
+2 101 "active"
+3 1 "tissue"
+$EndPhysicalNames
+$Entities
+0 0 2 1
+7 0 0 0 1 1 0 1 101 0
+8 0 0 0 1 0 1 0 0
+1 0 0 0 1 1 1 1 1 2 7 8
+$EndEntities
+$Nodes
+2 5 1 9
+2 7 0 3
+1
+2
+3
+0 0 0
+1 0 0
+0 1 0
+3 1 0 2
+4
+9
+0 0 1
+1 1 1
+$EndNodes
+$Elements
+3 4 1 4
+2 7 2 1
+1 1 2 3
+2 8 2 1
+2 1 2 4
+3 1 4 2
+3 1 2 3 4
+4 2 3 4 9
+$EndElements
+"""
+
+
+def test_msh41_reader(tmp_path):
+    from pelvistim_fem_b200 import gmsh_io
+    (tmp_path / "m.msh").write_text(MSH41)
+    m = gmsh_io.read_msh(tmp_path / "m.msh")
+    assert m.nn == 5 and m.nt == 2 and m.nb == 1             # the triangle on the unnamed surface 8 is dropped
+    assert m.bcid.tolist() == [101] and m.region.tolist() == [1, 1]   # named groups keep their ids
+    assert np.allclose(m.nodes[4], [1, 1, 1])                 # node tag 9 -> compact index 4
+    assert (meshgen.tet_volumes(m.nodes, m.tets) > 0).all()
+    assert m.tri_parent.tolist() == [0]
+
+
+def test_msh22_roundtrip_and_elmergrid_shim(tmp_path):
+    import subprocess, sys
+    from pathlib import Path
+    from pelvistim_fem_b200 import gmsh_io
+    m = meshgen.synth_slab("XS")
+    names = {(3, 1): "muscle", (3, 2): "fat", (3, 3): "skin", (3, 4): "ca", (3, 5): "cr", (2, 101): "active", (2, 102): "return", (2, 103): "other"}
+    gmsh_io.write_msh(tmp_path / "mesh.msh", m, names)
+    r = gmsh_io.read_msh(tmp_path / "mesh.msh")
+    assert np.array_equal(r.nodes, m.nodes) and np.array_equal(r.tets, m.tets) and np.array_equal(r.tris, m.tris)
+    assert np.array_equal(r.region, m.region) and np.array_equal(r.bcid, m.bcid)
+    # unnamed groups are renumbered 1..K (box.geo case: boundaries 101/102/103 -> 1/2/3)
+    b = meshgen.box_mesh(nx=3, ny=3, nz=2)
+    gmsh_io.write_msh(tmp_path / "box.msh", b)
+    rb = gmsh_io.read_msh(tmp_path / "box.msh")
+    assert sorted(np.unique(rb.bcid).tolist()) == [1, 2, 3] and np.unique(rb.region).tolist() == [1]
+    # the shim executable, called exactly as the reference calls ElmerGrid
+    shim = Path(__file__).resolve().parent.parent / "drivers" / "bin" / "ElmerGrid"
+    pr = subprocess.run([sys.executable, str(shim), "14", "2", "mesh.msh", "-out", "elmer_mesh"], cwd=tmp_path, capture_output=True, text=True)
+    assert pr.returncode == 0, pr.stderr
+    e = elmer_io.read_elmer_mesh(tmp_path / "elmer_mesh")
+    assert np.array_equal(e.tets, m.tets) and np.array_equal(e.bcid, m.bcid) and np.array_equal(e.nodes, m.nodes)
+    assert subprocess.run([sys.executable, str(shim), "1", "2", "x.grd"], cwd=tmp_path, capture_output=True).returncode == 1
