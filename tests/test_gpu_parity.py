@@ -385,3 +385,70 @@ def test_large_mesh_properties(gpu_ctx):
     assert abs(dm.metric_reaction(102) + 15.975 * A) < 1e-6 * 15.975 * A      # global current balance
     assert phi.min() > -1e-6 * phi.max()                                        # discrete maximum principle (to solver tol)
     dm.close()
+
+
+# -- the drop-in boundary itself: `ElmerSolver case.sif` in a case directory -----------------------------------------
+def test_elmersolver_shim_subprocess(tmp_path):
+    import subprocess, sys
+    from pathlib import Path
+    from pelvistim_fem_b200 import elmer_io, vtu
+    m = meshgen.synth_slab("XS")
+    elmer_io.write_elmer_mesh(tmp_path / "elmer_mesh", m)
+    secs, jn, _ = sif.layered_case(101, 102, 0.35, 0.04, 0.001, 0.005, elec_r=0.010, elec_area_mesh=3.2e-4)
+    (tmp_path / "case.sif").write_text(sif.serialize(secs))
+    (tmp_path / "results").mkdir()
+    shim = Path(__file__).resolve().parent.parent / "drivers" / "bin" / "ElmerSolver"
+    # exactly the reference's call: subprocess.run(["ElmerSolver", "case.sif"], cwd=run_dir)  (run_layered_sweep.py:1099)
+    pr = subprocess.run([sys.executable, str(shim), "case.sif"], cwd=tmp_path, capture_output=True, text=True)
+    assert pr.returncode == 0, pr.stdout + pr.stderr
+    v = vtu.read_vtu(tmp_path / "results" / "case_t0001.vtu")            # the file every consumer reads (:831-834)
+    prob = sif.problem_from_sif((tmp_path / "case.sif").read_text())
+    ref = fo.solve_case(m, prob.sigma_by_body, prob.dirichlet, prob.neumann, recover="l2")
+    assert rel(v["point_data"]["potential"], ref["phi"]) < TOL_PHI
+    assert rel(v["point_data"]["volume current"], ref["J"]) < TOL_FIELD
+    assert v["cell_types"].tolist().count(10) == m.nt and v["cell_types"].tolist().count(5) == m.nb
+    # error convention: non-zero exit code when the case is broken (missing mesh)
+    bad = tmp_path / "bad"
+    bad.mkdir()
+    (bad / "case.sif").write_text(sif.serialize(secs))
+    assert subprocess.run([sys.executable, str(shim), "case.sif"], cwd=bad, capture_output=True).returncode == 1
+
+
+def test_row_partitioned_path_single_rank(gpu_ctx):
+    # the multi-GPU iteration (single-reduction CG, streaming SpMV on row ranges) with one rank and no halo
+    from pelvistim_fem_b200 import partition
+    m = meshgen.synth_slab("S")
+    ref = fo.solve_case(m, SIGMA5, [(102, 0.0)], [(101, 15.975)], recover=None)
+    dm = dm_for(gpu_ctx, m)
+    dm.assemble(SIGMA5).bc_reset(1).neumann(101, 15.975).dirichlet(102, 0.0)
+    rowptr, col = dm.get_pattern()
+    blk = partition.local_block(rowptr, col, dm.get_values(0, True), dm.get_rhs(0), 0, 1)
+    dm.close()
+    ds = engine.DistSystem(gpu_ctx, blk)
+    x = ds.solve(rtol=1e-11)
+    assert ds.last_stats["converged"] == 1 and rel(x, ref["phi"]) < TOL_PHI
+    x2 = ds.solve(rtol=1e-11, use_graph=0)
+    assert np.array_equal(x, x2)                                  # graph replay == direct launches, bit for bit
+    ds.close()
+
+
+def test_morton_row_order_forced(monkeypatch):
+    # processing-order permutation of the streaming SpMV (auto-enabled only for incoherent numberings)
+    monkeypatch.setenv("PTFEM_MORTON", "1")
+    ctx = engine.Context(0)
+    m = meshgen.synth_slab("S")
+    perm = np.random.default_rng(3).permutation(m.nn)
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(m.nn)
+    ms = meshgen.TetMesh(m.nodes[perm], inv[m.tets].astype(np.int32), m.region, inv[m.tris].astype(np.int32), m.bcid)
+    ref = fo.solve_case(ms, SIGMA5, [(102, 0.0)], [(101, 15.975)], recover=None)
+    res = engine.solve_case(ctx, ms, SIGMA5, [(102, 0.0)], [(101, 15.975)], recover=None, spmv_variant=engine.SPMV_STREAM)
+    assert rel(res["phi"], ref["phi"]) < TOL_PHI
+    x = np.random.default_rng(0).standard_normal(ms.nn)
+    y_s, y_v = res["dmesh"].spmv(x, 0, True, engine.SPMV_STREAM), res["dmesh"].spmv(x, 0, True, engine.SPMV_VECTOR)
+    assert rel(y_s, ref["K"] @ x) < 1e-12 and rel(y_s, y_v) < 1e-13
+    rp, cc = fo.csr_pattern(ms.nn, ms.tets)
+    grp, gcol = res["dmesh"].get_pattern()
+    assert np.array_equal(grp, rp) and np.array_equal(gcol, cc)    # the API pattern stays canonical
+    res["dmesh"].close()
+    ctx.close()
