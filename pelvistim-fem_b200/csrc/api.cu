@@ -125,6 +125,7 @@ int ptfem_ctx_create(int device, ptfem_ctx** out) {
   PT_CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
   if (const char* e = getenv("PTFEM_INTERLEAVE")) c->tune_interleave = atoi(e) != 0;
   if (const char* e = getenv("PTFEM_MORTON")) c->tune_morton = atoi(e);
+  if (const char* e = getenv("PTFEM_P2P_FUSED")) c->tune_p2p_fused = atoi(e) != 0;
   if (const char* e = getenv("PTFEM_XPREFETCH")) c->tune_xprefetch = atoi(e) != 0;
   if (const char* e = getenv("PTFEM_CTAS_PER_SM")) c->tune_ctas_per_sm = atoi(e);
   if (const char* e = getenv("PTFEM_STREAM_CAP")) c->tune_stream_cap = atoi(e);

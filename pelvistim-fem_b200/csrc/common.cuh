@@ -104,6 +104,7 @@ struct ptfem_ctx {
   int tune_stream_tpr = 1;         // lanes per row of the streaming SpMV (PTFEM_STREAM_TPR: 1, 2, 4, 8)
   int tune_stream_stages = 2;      // shared-memory stages of the streaming SpMV (PTFEM_STREAM_STAGES: 2, 3)
   int tune_morton = -1;            // streaming SpMV walks rows along a Morton curve: -1 auto, 0 off, 1 on (PTFEM_MORTON)
+  int tune_p2p_fused = 0;          // row-partitioned solve: SpMV loads halo entries from peer memory itself (PTFEM_P2P_FUSED)
   int tune_xprefetch = 0;          // streaming SpMV prefetches the leading edge of x into L2 (PTFEM_XPREFETCH)
   int tune_ctas_per_sm = 0;        // cap on resident CTAs per SM of the streaming SpMV (PTFEM_CTAS_PER_SM)
   std::unordered_map<const void*, size_t> func_smem;  // dynamic shared memory limit raised per kernel

@@ -90,7 +90,7 @@ int load_nccl(const char* path, NcclApi** out) {
 
 constexpr int kT = 256;
 // device scalars of the distributed solve (doubles): see dist_scalar_kernel
-enum { D_GAMMA = 0, D_DELTA, D_RR, D_ALPHA, D_BETA, D_GAMMA_OLD, D_BN2, D_COUNT };
+enum { D_GAMMA = 0, D_DELTA, D_RR, D_ALPHA, D_BETA, D_GAMMA_OLD, D_BN2, D_LOC_G, D_LOC_RR, D_COUNT };
 
 __global__ void dist_dinv_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                  const double* __restrict__ val, int64_t nloc, double* __restrict__ dinv,
@@ -293,21 +293,66 @@ __device__ __forceinline__ bool wait_ge(const unsigned long long* p, unsigned lo
   return false;
 }
 
+// Thread 0 of one CTA: all-reduce of three local sums through the mailboxes of all ranks, then the
+// Chronopoulos-Gear scalars (or ||b||^2 when bnorm).  Every rank sums in rank order: identical results.
+__device__ void mailbox_allreduce(const double loc[3], const PeerTable& pt, double* __restrict__ scal, int first, int bnorm) {
+  Mail* me = pt.mail[pt.rank];
+  // every rank runs the same sequence of reductions, so a local counter numbers them consistently
+  const unsigned long long seq = me->nred + 1;
+  me->nred = seq;
+  const int par = (int)(seq & 1);
+  for (int q = 0; q < pt.nranks; ++q) {
+    MailBox* bx = &pt.mail[q]->box[par][pt.rank];
+    st_volatile_f64(&bx->v[0], loc[0]);
+    st_volatile_f64(&bx->v[1], loc[1]);
+    st_volatile_f64(&bx->v[2], loc[2]);
+    st_release_sys(&bx->seq, seq);
+  }
+  double tot[3] = {0.0, 0.0, 0.0};
+  for (int q = 0; q < pt.nranks; ++q) {
+    MailBox* bx = &me->box[par][q];
+    if (!wait_ge(&bx->seq, seq, &me->err)) break;
+    for (int c = 0; c < 3; ++c) tot[c] += ld_volatile_f64(&bx->v[c]);
+  }
+  if (bnorm) {
+    scal[D_BN2] = tot[0];
+    return;
+  }
+  const double gamma = tot[0], delta = tot[1];
+  double alpha, beta;
+  if (first) {
+    beta = 0.0;
+    alpha = delta > 0.0 ? gamma / delta : 0.0;
+  } else {
+    const double g_old = scal[D_GAMMA_OLD], a_old = scal[D_ALPHA];
+    beta = g_old > 0.0 ? gamma / g_old : 0.0;
+    const double den = a_old != 0.0 ? delta - beta * gamma / a_old : 0.0;
+    alpha = den > 0.0 ? gamma / den : 0.0;
+  }
+  scal[D_GAMMA] = gamma; scal[D_DELTA] = delta; scal[D_RR] = tot[2];
+  scal[D_ALPHA] = alpha; scal[D_BETA] = beta; scal[D_GAMMA_OLD] = gamma;
+}
+
 // update + "u is ready" signal.  first: x = 0, r = b, u = D^-1 b, p = s = 0.
 __global__ void __launch_bounds__(kT) p2p_update_kernel(int64_t n, int first, const double* __restrict__ b,
-                                                        const double* __restrict__ scal, const double* __restrict__ dinv,
+                                                        const double* scal /* aliases scal_out */, const double* __restrict__ dinv,
                                                         const double* __restrict__ w, double* __restrict__ p,
                                                         double* __restrict__ s, double* __restrict__ x,
                                                         double* __restrict__ r, double* __restrict__ u, PeerTable pt,
-                                                        unsigned int* __restrict__ ticket) {
+                                                        unsigned int* __restrict__ ticket, double* __restrict__ partial,
+                                                        double* scal_out) {
   __shared__ int s_last;
+  __shared__ double s_red[2 * (kT / 32)];
   const double alpha = scal[D_ALPHA], beta = scal[D_BETA];
   const int64_t stride = (int64_t)gridDim.x * kT;
+  double g_acc = 0.0, rr_acc = 0.0;   // r.u and r.r of the updated vectors (consumed by the fused path)
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < n; i += stride) {
     if (first) {
       p[i] = 0.0; s[i] = 0.0; x[i] = 0.0;
       r[i] = b[i];
       u[i] = b[i] * dinv[i];
+      g_acc = fma(b[i], b[i] * dinv[i], g_acc);
+      rr_acc = fma(b[i], b[i], rr_acc);
     } else {
       const double pi = fma(beta, p[i], u[i]);
       const double si = fma(beta, s[i], w[i]);
@@ -316,13 +361,42 @@ __global__ void __launch_bounds__(kT) p2p_update_kernel(int64_t n, int first, co
       x[i] = fma(alpha, pi, x[i]);
       r[i] = ri;
       u[i] = ri * dinv[i];
+      g_acc = fma(ri, ri * dinv[i], g_acc);
+      rr_acc = fma(ri, ri, rr_acc);
     }
+  }
+  g_acc = warp_sum(g_acc);
+  rr_acc = warp_sum(rr_acc);
+  if ((threadIdx.x & 31) == 0) {
+    s_red[(threadIdx.x >> 5) * 2] = g_acc;
+    s_red[(threadIdx.x >> 5) * 2 + 1] = rr_acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double a = 0.0;
+    for (int k = 0; k < kT / 32; ++k) a += s_red[k * 2 + threadIdx.x];
+    partial[(size_t)blockIdx.x * 2 + threadIdx.x] = a;
   }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
   __syncthreads();
-  if (s_last && threadIdx.x == 0) {
+  if (!s_last) return;
+  __threadfence();
+  {  // fixed-order sum of the per-CTA partials (two values), all threads then one
+    __shared__ double s_part[kT];
+    const int c = threadIdx.x & 1, g = threadIdx.x >> 1;
+    double a = 0.0;
+    for (unsigned bk = g; bk < gridDim.x; bk += kT / 2) a += __ldcg(partial + (size_t)bk * 2 + c);
+    s_part[threadIdx.x] = a;
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      double t = 0.0;
+      for (int gg = 0; gg < kT / 2; ++gg) t += s_part[gg * 2 + threadIdx.x];
+      scal_out[D_LOC_G + threadIdx.x] = t;
+    }
+  }
+  if (threadIdx.x == 0) {
     __threadfence_system();
     Mail* me = pt.mail[pt.rank];
     const unsigned long long k = me->iter + 1;
@@ -381,41 +455,14 @@ __global__ void __launch_bounds__(kT) p2p_dots_kernel(int64_t n, const double* _
   double loc[3];
   sum3_partials(partial, gridDim.x, s_part, loc);
   if (threadIdx.x != 0) return;
-  Mail* me = pt.mail[pt.rank];
-  // every rank runs the same sequence of reductions, so a local counter numbers them consistently
-  const unsigned long long seq = me->nred + 1;
-  me->nred = seq;
-  const int par = (int)(seq & 1);
-  for (int q = 0; q < pt.nranks; ++q) {
-    MailBox* bx = &pt.mail[q]->box[par][pt.rank];
-    st_volatile_f64(&bx->v[0], loc[0]);
-    st_volatile_f64(&bx->v[1], loc[1]);
-    st_volatile_f64(&bx->v[2], loc[2]);
-    st_release_sys(&bx->seq, seq);
-  }
-  double tot[3] = {0.0, 0.0, 0.0};
-  for (int q = 0; q < pt.nranks; ++q) {
-    MailBox* bx = &me->box[par][q];
-    if (!wait_ge(&bx->seq, seq, &me->err)) break;
-    for (int c = 0; c < 3; ++c) tot[c] += ld_volatile_f64(&bx->v[c]);
-  }
-  if (bnorm) {
-    scal[D_BN2] = tot[0];
-    return;
-  }
-  const double gamma = tot[0], delta = tot[1];
-  double alpha, beta;
-  if (first) {
-    beta = 0.0;
-    alpha = delta > 0.0 ? gamma / delta : 0.0;
-  } else {
-    const double g_old = scal[D_GAMMA_OLD], a_old = scal[D_ALPHA];
-    beta = g_old > 0.0 ? gamma / g_old : 0.0;
-    const double den = a_old != 0.0 ? delta - beta * gamma / a_old : 0.0;
-    alpha = den > 0.0 ? gamma / den : 0.0;
-  }
-  scal[D_GAMMA] = gamma; scal[D_DELTA] = delta; scal[D_RR] = tot[2];
-  scal[D_ALPHA] = alpha; scal[D_BETA] = beta; scal[D_GAMMA_OLD] = gamma;
+  mailbox_allreduce(loc, pt, scal, first, bnorm);
+}
+
+// fused path: the three local sums already exist (update kernel: r.u, r.r; SpMV epilogue: w.u)
+__global__ void p2p_reduce_kernel(double* __restrict__ scal, const double* __restrict__ spmv_scal, PeerTable pt, int first) {
+  if (threadIdx.x != 0) return;
+  const double loc[3] = {scal[D_LOC_G], spmv_scal[kScalPqOffset], scal[D_LOC_RR]};
+  mailbox_allreduce(loc, pt, scal, first, 0);
 }
 
 int dist_grid(ptfem_ctx* ctx, int64_t n) {
@@ -442,6 +489,12 @@ struct DistState {
   DevBuf<int32_t> halo_src, recv_ptr_dev;
   PeerTable pt;
   std::vector<void*> opened;   // cudaIpcOpenMemHandle mappings to close
+  // fused peer-memory SpMV: per halo slot the neighbour address, per neighbour the local ready flag
+  DevBuf<const double*> halo_ptr;
+  DevBuf<const unsigned long long*> flag_ptr;
+  DevBuf<double> partial2;
+  PcgWork spmv_work;           // partial / scal / ticket of the SpMV's fused dot
+  bool fused = false;
 };
 
 }  // namespace
@@ -541,9 +594,32 @@ static int p2p_matvec_reduce(ptfem_mesh* m, DistState& d, int first) {
 static int p2p_iteration(ptfem_mesh* m, DistState& d, int first) {
   ptfem_ctx* ctx = m->ctx;
   p2p_update_kernel<<<dist_grid(ctx, m->nloc), kT, 0, ctx->stream>>>(m->nloc, first, m->b.p, d.scal.p, m->dinv.p, d.w.p, d.p.p,
-                                                                     d.s.p, d.x.p, d.r.p, d.u.p, d.pt, d.ticket.p);
+                                                                     d.s.p, d.x.p, d.r.p, d.u.p, d.pt, d.ticket.p,
+                                                                     d.partial2.p, d.scal.p);
   PT_LAUNCH_CHECK(ctx);
-  return p2p_matvec_reduce(m, d, first);
+  if (!d.fused) return p2p_matvec_reduce(m, d, first);
+  // one kernel: wait for the neighbours' flags, w = A u with halo entries loaded straight from the neighbours'
+  // memory, local w.u in the epilogue; then the single-thread mailbox all-reduce
+  LinSys A;
+  A.nn = m->nloc;
+  A.nnz = m->nnz;
+  A.rowptr = m->rowptr.p;
+  A.col = m->col.p;
+  A.val = m->val_bc.p;
+  A.VS = 1;
+  A.S = 1;
+  A.stream_rows = d.stream_rows;
+  A.stream_cap = d.stream_cap;
+  A.peer.nloc = m->nloc;
+  A.peer.halo = d.halo_ptr.p;
+  A.peer.flags = d.flag_ptr.p;
+  A.peer.nflags = m->nnbr;
+  A.peer.wait = &d.mail.p->iter;
+  A.peer.err = &d.mail.p->err;
+  PT_TRY(spmv_launch(ctx, A, PTFEM_SPMV_STREAM, d.u.p, d.w.p, &d.spmv_work, true));
+  p2p_reduce_kernel<<<1, 32, 0, ctx->stream>>>(d.scal.p, d.spmv_work.scal.p, d.pt, first);
+  PT_LAUNCH_CHECK(ctx);
+  return PTFEM_OK;
 }
 
 void ptfem_dist_ctx_release(ptfem_ctx* ctx) {
@@ -942,6 +1018,26 @@ int ptfem_dist_p2p_connect(ptfem_mesh* m, int32_t nranks, const void* all_handle
     PT_CK(cudaMemcpyAsync(d.recv_ptr_dev.p, m->recv_ptr.data(), (m->nnbr + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
   else
     PT_CK(cudaMemsetAsync(d.recv_ptr_dev.p, 0, sizeof(int32_t), ctx->stream));
+  // tables of the fused SpMV
+  PT_TRY(d.partial2.alloc((size_t)ctx->sm_count * 4 * 2));
+  PT_TRY(d.spmv_work.partial.alloc((size_t)ctx->sm_count * 32 * 2));
+  PT_TRY(d.spmv_work.scal.alloc(8 * 16));
+  PT_TRY(d.spmv_work.ticket.alloc(4));
+  PT_CK(cudaMemsetAsync(d.spmv_work.ticket.p, 0, 4 * sizeof(unsigned int), ctx->stream));
+  PT_CK(cudaMemsetAsync(d.spmv_work.scal.p, 0, 8 * 16 * sizeof(double), ctx->stream));
+  {
+    std::vector<const double*> hp((size_t)m->nhalo);
+    for (int k = 0; k < m->nnbr; ++k)
+      for (int32_t hh = m->recv_ptr[k]; hh < m->recv_ptr[k + 1]; ++hh) hp[hh] = pt.u[m->nbr_rank[k]] + halo_src[hh];
+    std::vector<const unsigned long long*> fl((size_t)m->nnbr);
+    for (int k = 0; k < m->nnbr; ++k) fl[k] = &d.mail.p->ready_from[m->nbr_rank[k]];
+    PT_TRY(d.halo_ptr.alloc(hp.size()));
+    PT_TRY(d.flag_ptr.alloc(fl.size()));
+    if (!hp.empty()) PT_CK(cudaMemcpyAsync(d.halo_ptr.p, hp.data(), hp.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+    if (!fl.empty()) PT_CK(cudaMemcpyAsync(d.flag_ptr.p, fl.data(), fl.size() * sizeof(void*), cudaMemcpyHostToDevice, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+  }
+  d.fused = d.stream_rows > 0 && ctx->tune_p2p_fused;
   PT_CK(cudaStreamSynchronize(ctx->stream));
   d.p2p = true;
   if (d.graph) cudaGraphExecDestroy(d.graph);

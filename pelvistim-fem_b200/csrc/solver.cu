@@ -30,6 +30,7 @@ constexpr int kStreamRowsDefault = 64;
 
 // scalar slots in PcgWork::scal, each [kMaxSys]
 enum { SC_ALPHA = 0, SC_BETA, SC_RHO, SC_RR, SC_PQ, SC_BN2, SC_LMAX, SC_COUNT };
+static_assert(SC_PQ * kMaxSys == kScalPqOffset, "solver.cuh: kScalPqOffset out of sync");
 
 // L2 eviction policies: the matrix stream (val/col, read once per SpMV) is marked evict_first, the
 // gathered vector (re-read ~15 times, 8 bytes per row) evict_last, so the 600 MB stream cannot push the
@@ -389,14 +390,15 @@ __host__ __device__ inline size_t stream_smem_bytes(int stages, int cap) { retur
 // interleave = 1: CTAs sweep the matrix together as one moving front (tile j of CTA b is b + j*grid).
 // LPR lanes share a row: for S == 1 they split the row's non-zeros (TPR), for S >= 2 each of the S/2
 // lanes owns two systems (one 16-byte access per lane, 8*S contiguous bytes per row and non-zero).
-template <int S, int STAGES, int TPR, bool DOT>
+template <int S, int STAGES, int TPR, bool DOT, bool PEER = false>
 __global__ void __launch_bounds__(kStreamThreads*(S == 1 ? TPR : S / 2))
     spmv_stream_kernel(int64_t nn, int64_t row0, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                        const double* __restrict__ val, int32_t R, int32_t cap, int32_t ntiles, int32_t tiles_per_cta,
                        int interleave, int xprefetch, const int32_t* __restrict__ rowid, const double* __restrict__ x,
                        double* __restrict__ y, double* __restrict__ partial, double* __restrict__ scal,
-                       unsigned int* __restrict__ ticket) {
+                       unsigned int* __restrict__ ticket, PeerGather pg) {
   constexpr int LPR = S == 1 ? TPR : S / 2;
+  static_assert(!PEER || S == 1, "peer gathers are implemented for one right-hand side");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* const s_val = reinterpret_cast<double*>(smem_raw);                                    // [STAGES][cap]
   int32_t* const s_col = reinterpret_cast<int32_t*>(smem_raw + (size_t)STAGES * cap * 8);        // [STAGES][cap]
@@ -409,6 +411,19 @@ __global__ void __launch_bounds__(kStreamThreads*(S == 1 ? TPR : S / 2))
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) mbar_init(&s_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if constexpr (PEER) {
+      // fused halo exchange: the neighbours' vectors are read in place, once their update of this iteration
+      // is complete (flags are pushed into local memory by the neighbours; bounded wait)
+      const unsigned long long want = *reinterpret_cast<const volatile unsigned long long*>(pg.wait);
+      for (int f = 0; f < pg.nflags; ++f) {
+        unsigned long long n = 0, v;
+        do {
+          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(pg.flags[f]) : "memory");
+          if (v < want) __nanosleep(32);
+        } while (v < want && ++n < (1ull << 23));
+        if (v < want) atomicExch(pg.err, 1ull);
+      }
+    }
   }
   __syncthreads();
 
@@ -471,7 +486,16 @@ __global__ void __launch_bounds__(kStreamThreads*(S == 1 ? TPR : S / 2))
     if constexpr (S == 1) {
       double acc = 0.0;
 #pragma unroll 4
-      for (int32_t k = b - a0 + lane; k < e - a0; k += TPR) acc = fma(sv[k], ldg_f64_hint(x + sc[k], pol_keep), acc);
+      for (int32_t k = b - a0 + lane; k < e - a0; k += TPR) {
+        const int32_t c = sc[k];
+        double xv;
+        if (PEER && c >= pg.nloc) {
+          asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(xv) : "l"(pg.halo[c - pg.nloc]));
+        } else {
+          xv = ldg_f64_hint(x + c, pol_keep);
+        }
+        acc = fma(sv[k], xv, acc);
+      }
 #pragma unroll
       for (int o = TPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (live && lane == 0) {
@@ -839,14 +863,14 @@ int launch_vector(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y, P
   return PTFEM_OK;
 }
 
-template <int S, int STAGES, int TPR, bool DOT>
+template <int S, int STAGES, int TPR, bool DOT, bool PEER = false>
 int launch_stream_t(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y, PcgWork* w) {
   const size_t smem = stream_smem_bytes(STAGES, A.stream_cap);
   {
-    const void* fn = reinterpret_cast<const void*>(&spmv_stream_kernel<S, STAGES, TPR, DOT>);
+    const void* fn = reinterpret_cast<const void*>(&spmv_stream_kernel<S, STAGES, TPR, DOT, PEER>);
     auto it = ctx->func_smem.find(fn);
     if (it == ctx->func_smem.end() || it->second < smem) {
-      PT_CK(cudaFuncSetAttribute(spmv_stream_kernel<S, STAGES, TPR, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PT_CK(cudaFuncSetAttribute(spmv_stream_kernel<S, STAGES, TPR, DOT, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       ctx->func_smem[fn] = smem;
     }
   }
@@ -864,9 +888,10 @@ int launch_stream_t(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y,
   const int64_t per_cta = (ntiles + grid - 1) / grid;
   if (!ctx->tune_interleave) grid = (ntiles + per_cta - 1) / per_cta;
   const bool perm = A.rowid != nullptr && A.row0 == 0;
-  spmv_stream_kernel<S, STAGES, TPR, DOT><<<(int)grid, threads, smem, ctx->stream>>>(
+  spmv_stream_kernel<S, STAGES, TPR, DOT, PEER><<<(int)grid, threads, smem, ctx->stream>>>(
       A.nn, A.row0, perm ? A.prowptr : A.rowptr, perm ? A.pcol : A.col, perm ? A.pval : A.val, A.stream_rows, A.stream_cap,
-      (int32_t)ntiles, (int32_t)per_cta, ctx->tune_interleave, perm ? 0 : ctx->tune_xprefetch, perm ? A.rowid : nullptr, x, y, w ? w->partial.p : nullptr, w ? w->scal.p : nullptr, w ? w->ticket.p : nullptr);
+      (int32_t)ntiles, (int32_t)per_cta, ctx->tune_interleave, perm ? 0 : ctx->tune_xprefetch, perm ? A.rowid : nullptr, x, y,
+      w ? w->partial.p : nullptr, w ? w->scal.p : nullptr, w ? w->ticket.p : nullptr, A.peer);
   PT_LAUNCH_CHECK(ctx);
   return PTFEM_OK;
 }
@@ -875,6 +900,10 @@ int launch_stream_t(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y,
 template <int S, bool DOT>
 int launch_stream(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y, PcgWork* w, int stages, int tpr) {
   if constexpr (S == 1) {
+    if (A.peer.nloc > 0) {
+      if constexpr (DOT) return launch_stream_t<1, 2, 1, true, true>(ctx, A, x, y, w);
+      return set_err(PTFEM_ERR_STATE, "peer-memory SpMV is only built with the fused dot product");
+    }
     if (stages >= 3) return tpr == 2 ? launch_stream_t<1, 3, 2, DOT>(ctx, A, x, y, w) : launch_stream_t<1, 3, 1, DOT>(ctx, A, x, y, w);
     return tpr == 2 ? launch_stream_t<1, 2, 2, DOT>(ctx, A, x, y, w) : launch_stream_t<1, 2, 1, DOT>(ctx, A, x, y, w);
   } else {

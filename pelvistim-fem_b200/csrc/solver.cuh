@@ -2,6 +2,16 @@
 #pragma once
 #include "common.cuh"
 
+// Arguments of the fused peer-memory gather of the streaming SpMV (see dist.cu).
+struct PeerGather {
+  int64_t nloc = 0;                                     // 0 = disabled
+  const double* const* halo = nullptr;                  // [nhalo] device pointers (neighbour memory)
+  const unsigned long long* const* flags = nullptr;     // [nflags] local flags written remotely by the neighbours
+  int nflags = 0;
+  const unsigned long long* wait = nullptr;             // value the flags must reach (local iteration counter)
+  unsigned long long* err = nullptr;                    // raised when a wait times out
+};
+
 // A (batch of) linear system(s) on one CSR pattern, all device pointers.
 struct LinSys {
   int64_t nn = 0, nnz = 0;
@@ -19,8 +29,15 @@ struct LinSys {
   const int32_t* prowptr = nullptr;
   const int32_t* pcol = nullptr;
   const double* pval = nullptr;
+  // peer-memory gathers (row-partitioned solve, S == 1): columns >= peer.nloc are not local; entry c is read
+  // through peer.halo[c - nloc] (a pointer into a neighbour GPU's vector) after the neighbours' ready flags
+  // (peer.flags, local memory) have reached *peer.wait
+  PeerGather peer;
   int64_t row0 = 0;              // the system is rows [row0, row0+nn) of the arrays (row-range SpMV)
 };
+
+// where the fused dot of spmv_launch(cg_dot = true) leaves sum_i y_i x_i of system 0 in PcgWork::scal
+constexpr int kScalPqOffset = 4 * 16;
 
 namespace ptfem {
 // y = A x for all S systems; if dot_with != nullptr also leaves sum_i y_i*dot_with_i per system in
