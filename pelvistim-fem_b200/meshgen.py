@@ -478,6 +478,44 @@ def _pad_wall_quads(msk, nxn, nyn, k):
     return np.concatenate(quads, axis=0) if quads else np.zeros((0, 4), dtype=np.int64)
 
 
+def delaunay_box_mesh(npts=2000, Lx=0.04, Ly=0.03, Lz=0.02, seed=0, ids=(101, 102, 103), min_quality=1e-3):
+    """Unstructured tetrahedral mesh of a box: Delaunay triangulation (scipy / Qhull) of random interior points
+    plus a jittered lattice on the faces, the kind of irregular connectivity (3..40 neighbours per node, no
+    row-to-row coherence) a Gmsh mesh has.  Boundary ids = (top z=Lz, bottom z=0, sides).  Test meshes only."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(seed)
+    nface = max(4, int(round((npts / 6) ** (1 / 3) * 2)))
+    g = np.linspace(0.0, 1.0, nface)
+    faces = []
+    for ax in range(3):
+        for v in (0.0, 1.0):
+            a, b = np.meshgrid(g, g, indexing="ij")
+            a = a + rng.uniform(-0.3, 0.3, a.shape) / (nface - 1) * ((a > 0) & (a < 1))
+            b = b + rng.uniform(-0.3, 0.3, b.shape) / (nface - 1) * ((b > 0) & (b < 1))
+            p = np.empty((a.size, 3))
+            p[:, ax] = v
+            p[:, (ax + 1) % 3] = a.ravel()
+            p[:, (ax + 2) % 3] = b.ravel()
+            faces.append(p)
+    surf = np.unique(np.round(np.concatenate(faces), 12), axis=0)
+    inner = rng.uniform(0.03, 0.97, size=(max(npts - surf.shape[0], 8), 3))
+    pts = np.concatenate([surf, inner]) * np.array([Lx, Ly, Lz])
+    tets = Delaunay(pts).simplices.astype(np.int32)
+    vol = tet_volumes(pts, tets)
+    h3 = (Lx * Ly * Lz) / max(tets.shape[0], 1)
+    tets = tets[np.abs(vol) > min_quality * h3]                 # drop slivers on the flat faces
+    orient_positive(pts, tets)
+    used = np.zeros(pts.shape[0], dtype=bool)
+    used[tets.ravel()] = True
+    new_id = np.cumsum(used) - 1
+    pts, tets = pts[used], new_id[tets].astype(np.int32)
+    tris, parent = external_faces(tets)
+    zc = pts[tris][:, :, 2]
+    bcid = np.where(np.all(zc > Lz * (1 - 1e-9), axis=1), ids[0], np.where(np.all(zc < Lz * 1e-9, axis=1), ids[1], ids[2])).astype(np.int32)
+    return TetMesh(np.ascontiguousarray(pts), np.ascontiguousarray(tets), np.ones(tets.shape[0], dtype=np.int32),
+                   np.ascontiguousarray(tris), bcid, tri_parent=parent, meta=dict(kind="delaunay_box", Lx=Lx, Ly=Ly, Lz=Lz))
+
+
 # Synthetic benchmark meshes (SURVEY.md section 8d): uniform tensor grid on the
 # step03 slab, z-levels snapped to the layer interfaces.
 SYNTH_SIZES = {

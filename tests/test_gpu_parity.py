@@ -452,3 +452,39 @@ def test_morton_row_order_forced(monkeypatch):
     assert np.array_equal(grp, rp) and np.array_equal(gcol, cc)    # the API pattern stays canonical
     res["dmesh"].close()
     ctx.close()
+
+
+# -- unstructured connectivity (3..40 neighbours per node, no row-to-row coherence) --------------------------------
+@pytest.mark.parametrize("morton", ["-1", "0", "1"])
+def test_unstructured_delaunay_mesh(monkeypatch, morton):
+    monkeypatch.setenv("PTFEM_MORTON", morton)
+    ctx = engine.Context(0)
+    m = meshgen.delaunay_box_mesh(6000, seed=4)
+    # two materials split at x = Lx/2, Neumann on top, Dirichlet on the bottom
+    reg = np.where(m.nodes[m.tets].mean(axis=1)[:, 0] > 0.02, 2, 1).astype(np.int32)
+    m = meshgen.TetMesh(m.nodes, m.tets, reg, m.tris, m.bcid)
+    sig = {1: 0.3, 2: 0.002}
+    ref = fo.solve_case(m, sig, [(102, 0.0)], [(101, 4.0)], recover="l2")
+    dm = ctx.mesh(m.nodes, m.tets, m.region, m.tris, m.bcid)
+    rp, cc = fo.csr_pattern(m.nn, m.tets)
+    grp, gcol = dm.get_pattern()
+    assert np.array_equal(grp, rp) and np.array_equal(gcol, cc)
+    dm.assemble(sig).bc_reset(1).neumann(101, 4.0).dirichlet(102, 0.0)
+    x = np.random.default_rng(2).standard_normal(m.nn)
+    for variant in (engine.SPMV_VECTOR, engine.SPMV_STREAM, engine.SPMV_STREAM1):
+        assert rel(dm.spmv(x, 0, True, variant), ref["K"] @ x) < 1e-12
+        phi = dm.solve(spmv_variant=variant, rtol=1e-11)[0]
+        assert rel(phi, ref["phi"]) < TOL_PHI
+    assert rel(dm.recover_current(0, "l2"), ref["J"]) < TOL_FIELD
+    dm.close()
+    # multi-RHS on the same irregular pattern through the streaming SpMM
+    dm = ctx.mesh(m.nodes, m.tets, m.region, m.tris, m.bcid)
+    dm.assemble(sig).bc_reset(3)
+    for k in range(3):
+        dm.neumann(101, 1.0 + k, rhs=k)
+    dm.dirichlet(102, 0.0)
+    phi3 = dm.solve(spmv_variant=engine.SPMV_STREAM, rtol=1e-11)
+    for k in range(3):
+        assert rel(phi3[k], ref["phi"] * (1.0 + k) / 4.0) < TOL_PHI          # linearity in the injected current
+    dm.close()
+    ctx.close()

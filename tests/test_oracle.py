@@ -150,3 +150,25 @@ def test_step04_series_law_from_golden(golden):
     for r in rows:
         pred = base + 2 * tc * I / (r["sigma_contact_Spm"] * A)
         assert -0.04 < (pred - r["compliance_V"]) / r["compliance_V"] < 0.005
+
+
+# -- unstructured (Delaunay) meshes: irregular connectivity like a Gmsh mesh ---------------------------------------
+from hypothesis import given, settings, strategies as st
+
+
+@settings(max_examples=6, deadline=None)
+@given(seed=st.integers(0, 10_000), npts=st.integers(150, 600))
+def test_property_unstructured_meshes(seed, npts):
+    m = meshgen.delaunay_box_mesh(npts, seed=seed)
+    vol = meshgen.tet_volumes(m.nodes, m.tets)
+    assert (vol > 0).all() and abs(vol.sum() - 0.04 * 0.03 * 0.02) < 1e-4 * 2.4e-5   # box filled (dropped slivers have ~0 volume)
+    rowptr, col = fo.csr_pattern(m.nn, m.tets)
+    cs = co.CSystem(m, {1: 0.2}, [(101, 1.0), (102, 0.0)], [])
+    assert np.array_equal(cs.rowptr, rowptr) and np.array_equal(cs.col, col)         # C and numpy oracles agree bit for bit
+    ref = fo.solve_case(m, {1: 0.2}, [(101, 1.0), (102, 0.0)], [], recover="l2")
+    assert np.abs(cs.val_raw - ref["K_raw"].data).max() <= 1e-13 * np.abs(ref["K_raw"].data).max()
+    # the analytic solution is exact on ANY tet mesh (test_step01_baseline.py: V = z/Lz, J = -sigma/Lz)
+    assert np.abs(ref["phi"] - m.nodes[:, 2] / 0.02).max() < 1e-11
+    assert np.abs(ref["J"] - np.array([0.0, 0.0, -10.0])).max() < 1e-8
+    x, it, rel = cs.pcg(1e-13)
+    assert np.abs(x - ref["phi"]).max() < 1e-9
