@@ -478,7 +478,7 @@ def _pad_wall_quads(msk, nxn, nyn, k):
     return np.concatenate(quads, axis=0) if quads else np.zeros((0, 4), dtype=np.int64)
 
 
-def delaunay_box_mesh(npts=2000, Lx=0.04, Ly=0.03, Lz=0.02, seed=0, ids=(101, 102, 103), min_quality=1e-3):
+def delaunay_box_mesh(npts=2000, Lx=0.04, Ly=0.03, Lz=0.02, seed=0, ids=(101, 102, 103), min_quality=1e-9):
     """Unstructured tetrahedral mesh of a box: Delaunay triangulation (scipy / Qhull) of random interior points
     plus a jittered lattice on the faces, the kind of irregular connectivity (3..40 neighbours per node, no
     row-to-row coherence) a Gmsh mesh has.  Boundary ids = (top z=Lz, bottom z=0, sides).  Test meshes only."""
@@ -503,7 +503,7 @@ def delaunay_box_mesh(npts=2000, Lx=0.04, Ly=0.03, Lz=0.02, seed=0, ids=(101, 10
     tets = Delaunay(pts).simplices.astype(np.int32)
     vol = tet_volumes(pts, tets)
     h3 = (Lx * Ly * Lz) / max(tets.shape[0], 1)
-    tets = tets[np.abs(vol) > min_quality * h3]                 # drop slivers on the flat faces
+    tets = tets[np.abs(vol) > min_quality * h3]                 # drop the exactly flat tets Qhull leaves on the faces
     orient_positive(pts, tets)
     used = np.zeros(pts.shape[0], dtype=bool)
     used[tets.ravel()] = True
