@@ -19,7 +19,7 @@ import yaml
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import _common  # noqa: F401,E402
-from pelvistim_fem_b200 import elmer_io, pipeline, sif  # noqa: E402
+from pelvistim_fem_b200 import elmer_io, meshgen, pipeline, sif  # noqa: E402
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "step03_ankle_layers"))
 import run_layered_sweep as step03  # noqa: E402
@@ -105,6 +105,48 @@ def run_pressure_sweep(p, sigma_contact_list, pressure_labels, coarse=False, seq
     return all_results
 
 
+def run_compression_sweep(p, sigma_contact_list, pressure_labels, max_compression_mm, coarse=False, ctx=None, results_dir=None):
+    """Pressure as conductivity AND geometry (BASELINE.json config 4; not in the reference, whose step04 changes
+    sigma_contact only: ``run_pressure_sweep.py:12-13``): level k also indents the tissue under both pads by
+    ``max_compression_mm * k/(n-1)``.  Topology is fixed, so the CSR pattern is built once; every level moves the
+    nodes (``ptfem_mesh_set_coords``), re-assembles and solves.  Adds the column ``compression_mm``."""
+    results_dir = Path(results_dir) if results_dir else RESULTS_DIR
+    results_dir.mkdir(exist_ok=True)
+    pl = p.get("placement", p.get("electrodes", {}))
+    elec_r = float(pl["electrode_r_mm"]) * 1e-3
+    mesh, e1_pos, e2_pos, body_info = build_mesh(p, results_dir / "_mesh_base", coarse=coarse)
+    e1_id, e2_id, A_active, _ = pipeline.detect_elec_bc_ids(mesh, e1_pos, e2_pos, e1_pos[2], e2_pos[2])
+    ctx = ctx or pipeline.default_context()
+    dmesh = ctx.mesh(mesh.nodes, mesh.tets, mesh.region, mesh.tris, mesh.bcid)
+    dmesh.pattern()
+    Lz = p["geometry"]["Lz"]
+    rows = []
+    n = len(sigma_contact_list)
+    for k, (sigma_c, label) in enumerate(zip(sigma_contact_list, pressure_labels)):
+        depth = max_compression_mm * 1e-3 * (k / (n - 1) if n > 1 else 1.0)
+        nodes_k = meshgen.compress_under_pads(mesh.nodes, [e1_pos[:2], e2_pos[:2]], elec_r, depth, Lz)
+        mesh_k = type(mesh)(nodes_k, mesh.tets, mesh.region, mesh.tris, mesh.bcid, tri_parent=mesh.tri_parent)
+        run_dir = results_dir / label
+        run_dir.mkdir(exist_ok=True)
+        elmer_io.write_elmer_mesh(run_dir / "elmer_mesh", mesh_k)
+        z1 = float(nodes_k[np.unique(mesh.tris[mesh.bcid == e1_id]), 2].mean())
+        z2 = float(nodes_k[np.unique(mesh.tris[mesh.bcid == e2_id]), 2].mean())
+        bi = dict(body_info, z_e1_elec_top=z1, z_e2_elec_top=z2, z_elec_top=max(z1, z2))
+        # pad areas change slightly with the indentation: Jn follows the deformed mesh, as write_sif does
+        _, _, A_k, _ = pipeline.detect_elec_bc_ids(mesh_k, [*e1_pos[:2], z1], [*e2_pos[:2], z2], z1, z2)
+        jn = step03.write_sif(run_dir, e1_id, e2_id, p, elec_r, bi, elec_area_mesh=A_k, sigma_contact_override=sigma_c,
+                              dialect="step04")
+        (run_dir / "results").mkdir(exist_ok=True)
+        dmesh.set_coords(nodes_k)
+        print(f"\n[{label}]  sigma_contact={sigma_c:.4f} S/m  compression={depth*1e3:.2f} mm")
+        case = pipeline.run_elmer_solver(run_dir, ctx=ctx, mesh=mesh_k, dmesh=dmesh)
+        row = _row(case, p, sigma_c, label, [*e1_pos[:2], z1], [*e2_pos[:2], z2], bi, jn, 0)
+        row["compression_mm"] = round(depth * 1e3, 4)
+        rows.append(row)
+    dmesh.close()
+    return rows
+
+
 def _row(case, p, sigma_c, label, e1_pos, e2_pos, body_info, jn, sys_idx):
     res = pipeline.extract_pressure(case, p, sigma_c, label, e1_pos, e2_pos, body_info, jn, sys=sys_idx)
     print(f"    compliance_V={res['compliance_V']:.1f} V  Z_contact={res['contact_impedance_ohm']:.0f} Ω  "
@@ -120,6 +162,9 @@ def main(argv=None):
     ap = argparse.ArgumentParser(description="Pressure-dependent contact sweep")
     ap.add_argument("--smoke", action="store_true", help="Single coarse case (middle pressure level)")
     ap.add_argument("--sequential", action="store_true", help="solve the levels one by one instead of as a batch")
+    ap.add_argument("--compression-mm", type=float, default=0.0,
+                    help="also indent the tissue under the pads, linearly up to this depth at the last level (geometry change "
+                         "on fixed topology; extension, not in the reference)")
     args = ap.parse_args(argv)
     p = load_params()
     ps = p["pressure_sweep"]
@@ -128,7 +173,10 @@ def main(argv=None):
         mid = len(sig_list) // 2
         sig_list, lbl_list = [sig_list[mid]], [lbl_list[mid]]
         print("=== SMOKE TEST (1 coarse case) ===")
-    results = run_pressure_sweep(p, sig_list, lbl_list, coarse=args.smoke, sequential=args.sequential)
+    if args.compression_mm > 0:
+        results = run_compression_sweep(p, sig_list, lbl_list, args.compression_mm, coarse=args.smoke)
+    else:
+        results = run_pressure_sweep(p, sig_list, lbl_list, coarse=args.smoke, sequential=args.sequential)
     save_results(results)
     print(f"\n  {len(results)} pressure level(s) computed → results/summary.csv, results/summary.json")
     return results

@@ -516,6 +516,22 @@ def delaunay_box_mesh(npts=2000, Lx=0.04, Ly=0.03, Lz=0.02, seed=0, ids=(101, 10
                    np.ascontiguousarray(tris), bcid, tri_parent=parent, meta=dict(kind="delaunay_box", Lx=Lx, Ly=Ly, Lz=Lz))
 
 
+def compress_under_pads(nodes, pads_xy, pad_r, depth, Lz, width_factor=1.5):
+    """Node displacement of tissue compressed by the electrodes: a Gaussian indentation of ``depth`` (m) centred
+    on each pad, growing linearly from 0 at z = 0 to its full value at the skin surface (pads ride down
+    rigidly).  Same idea as the reference's Gaussian skin-height field applied to fixed topology
+    (``step03_ankle_layers/run_layered_sweep.py:93-118,329-340``); used with ``ptfem_mesh_set_coords``.
+    The indentation is clipped to 60 % of the local column height so no element inverts."""
+    out = np.array(nodes, dtype=np.float64, copy=True)
+    sig2 = (width_factor * pad_r) ** 2
+    dz = np.zeros(out.shape[0])
+    for (px, py) in pads_xy:
+        dz += depth * np.exp(-((out[:, 0] - px) ** 2 + (out[:, 1] - py) ** 2) / (2.0 * sig2))
+    dz = np.minimum(dz, 0.6 * Lz)
+    out[:, 2] -= dz * np.clip(out[:, 2] / Lz, 0.0, 1.0)
+    return out
+
+
 # Synthetic benchmark meshes (SURVEY.md section 8d): uniform tensor grid on the
 # step03 slab, z-levels snapped to the layer interfaces.
 SYNTH_SIZES = {

@@ -237,3 +237,12 @@ def test_msh22_roundtrip_and_elmergrid_shim(tmp_path):
     e = elmer_io.read_elmer_mesh(tmp_path / "elmer_mesh")
     assert np.array_equal(e.tets, m.tets) and np.array_equal(e.bcid, m.bcid) and np.array_equal(e.nodes, m.nodes)
     assert subprocess.run([sys.executable, str(shim), "1", "2", "x.grd"], cwd=tmp_path, capture_output=True).returncode == 1
+
+
+def test_compression_field_keeps_mesh_valid():
+    m = meshgen.synth_slab("S")
+    for depth in (0.0005, 0.003):
+        n2 = meshgen.compress_under_pads(m.nodes, [(0.015, 0.045), (0.065, 0.045)], 0.010, depth, 0.040)
+        assert (meshgen.tet_volumes(n2, m.tets) > 0).all()
+        assert np.all(n2[:, 2] <= m.nodes[:, 2] + 1e-15) and np.isclose((m.nodes[:, 2] - n2[:, 2]).max(), depth * 1.0125, rtol=0.02)
+        assert np.array_equal(n2[:, :2], m.nodes[:, :2]) and np.all(n2[m.nodes[:, 2] == 0.0, 2] == 0.0)
