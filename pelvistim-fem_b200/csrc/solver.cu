@@ -342,11 +342,12 @@ __global__ void __launch_bounds__(kThreads) spmv_vector_multi_kernel(int64_t nn,
   }
 }
 
-// ---- K5b: streaming SpMV (S == 1) ----------------------------------------------------------------
-// Each CTA walks row blocks of ~kStreamTile non-zeros.  The block's val/col slices are brought into
-// shared memory with two bulk async copies (cp.async.bulk -> UBLKCP, completion on an mbarrier), so
-// HBM sees only long, perfectly coalesced bursts; products val*x[col] are formed in place, one entry
-// per thread (x gathered through L1/L2), and a thread per row sums its segment from shared memory.
+// ---- K5b: streaming SpMV / SpMM (one matrix, S = 1..16 right-hand sides) ---------------------------------
+// Each CTA walks tiles of R consecutive rows (64 by default).  A tile's val/col slices are brought into
+// shared memory with two bulk async copies (cp.async.bulk -> UBLKCP, completion on an mbarrier, 2 stages),
+// so HBM sees only long, perfectly coalesced bursts and no register is spent on keeping bytes in flight;
+// one thread per row (S == 1) or S/2 lanes per row (S >= 2) then accumulates val * x[col] out of shared
+// memory, x gathered through L1/L2 with an evict_last policy.  DESIGN.md section 3.1 has the measurements.
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -834,7 +835,6 @@ int pick_tpr(const LinSys& A) {
 
 template <int S, int VS, bool DOT>
 int launch_vector(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y, PcgWork* w) {
-  const int tpr = pick_tpr(A);
   double* partial = w ? w->partial.p : nullptr;
   double* scal = w ? w->scal.p : nullptr;
   unsigned int* ticket = w ? w->ticket.p : nullptr;
@@ -842,23 +842,22 @@ int launch_vector(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y, P
     const int grid = grid_for(ctx, A.nn, kThreads / (S / 2));
     spmv_vector_multi_kernel<S, VS, DOT><<<grid, kThreads, 0, ctx->stream>>>(A.nn, A.row0, ctx->tune_interleave, A.rowptr,
                                                                              A.col, A.val, x, y, partial, scal, ticket);
-    PT_LAUNCH_CHECK(ctx);
-    return PTFEM_OK;
-  }
+  } else {
 #define PT_VEC(TPR)                                                                                             \
   {                                                                                                             \
     const int grid = grid_for(ctx, A.nn, kThreads / TPR);                                                       \
-    spmv_vector_kernel<S, VS, TPR, DOT><<<grid, kThreads, 0, ctx->stream>>>(A.nn, A.row0, ctx->tune_interleave, A.rowptr, A.col, A.val, x, y, \
-                                                                           partial, scal, ticket);             \
+    spmv_vector_kernel<1, 1, TPR, DOT><<<grid, kThreads, 0, ctx->stream>>>(A.nn, A.row0, ctx->tune_interleave, A.rowptr, \
+                                                                          A.col, A.val, x, y, partial, scal, ticket); \
   }
-  switch (tpr) {
-    case 2: PT_VEC(2); break;
-    case 4: PT_VEC(4); break;
-    case 8: PT_VEC(8); break;
-    case 16: PT_VEC(16); break;
-    default: PT_VEC(32); break;
-  }
+    switch (pick_tpr(A)) {
+      case 2: PT_VEC(2); break;
+      case 4: PT_VEC(4); break;
+      case 8: PT_VEC(8); break;
+      case 16: PT_VEC(16); break;
+      default: PT_VEC(32); break;
+    }
 #undef PT_VEC
+  }
   PT_LAUNCH_CHECK(ctx);
   return PTFEM_OK;
 }
