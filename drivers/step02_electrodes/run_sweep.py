@@ -33,7 +33,7 @@ e2_pos = np.array([Lx / 2 + SEP / 2, Ly / 2])
 def build_mesh(shape, r, run_dir, coarse=False):
     run_dir.mkdir(parents=True, exist_ok=True)
     s = 2.0 if coarse else 1.0
-    m = meshgen.electrode_box_mesh(Lx, Ly, Lz, e1_pos, e2_pos, r, shape, h_elec=s * r / 3.5, h_bulk=s * min(4 * r, 0.012))
+    m = meshgen.electrode_box_mesh(Lx, Ly, Lz, e1_pos, e2_pos, r, shape, h_elec=s * r / 3.5, h_bulk=s * min(4 * r, 0.012), snap_rim=True)
     gmsh_io.write_msh(run_dir / "mesh.msh", m, {(3, 1): "tissue", (2, 101): "active", (2, 102): "return", (2, 103): "other"})
     elmer_io.write_elmer_mesh(run_dir / "elmer_mesh", m)
     return m, (np.pi * r * r if shape == "circle" else (2 * r) ** 2)

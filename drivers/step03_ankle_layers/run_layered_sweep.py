@@ -64,7 +64,7 @@ def build_mesh(p, t_fat, elec_r, run_dir, coarse=False):
     n_f = max(2, int(round(t_fat / lc_elec)))
     mesh = meshgen.layered_slab_mesh(Lx, Ly, Lz, ls["t_skin"], t_fat, t_contact or 0.0005, active_xy, return_xy, elec_r,
                                      shape, n_muscle=n_m, n_fat=n_f, n_skin=2, n_contact=1, h_bulk=lc_bulk,
-                                     h_elec=lc_elec, contact_enabled=contact)
+                                     h_elec=lc_elec, contact_enabled=contact, snap_rim=True)
     # same per-case files as the reference: mesh.msh (gmsh.write, :342-343) then the ElmerGrid 14 2 conversion (:1077)
     names = {(3, 1): "muscle", (3, 2): "fat", (3, 3): "skin", (3, 4): "contact_active", (3, 5): "contact_return",
              (2, 101): "active", (2, 102): "return", (2, 103): "other"}

@@ -255,6 +255,39 @@ def _footprint_mask(xc, yc, cx, cy, r, shape, match_area=True, cell_area=None):
     return m.reshape(d.shape)
 
 
+def _snap_rim_columns(nodes, nxn, nyn, nzn, xs, ys, masks, centers, r, max_shift=0.42):
+    """Move the grid columns on the rim of each disk footprint radially onto the circle of radius ``r`` (the
+    whole column, all z-levels), by at most ``max_shift`` of the local spacing, so the staircase outline of the
+    structured grid follows the electrode edge.  Returns the displaced copy (topology unchanged)."""
+    out = nodes.copy()
+    hx = np.minimum(np.diff(xs, prepend=xs[0] - (xs[1] - xs[0])), np.diff(xs, append=xs[-1] + (xs[-1] - xs[-2])))
+    hy = np.minimum(np.diff(ys, prepend=ys[0] - (ys[1] - ys[0])), np.diff(ys, append=ys[-1] + (ys[-1] - ys[-2])))
+    for msk, (cx, cy) in zip(masks, centers):
+        pad = np.zeros((nxn + 1, nyn + 1), dtype=bool)
+        pad[1:nxn, 1:nyn] = msk                      # cell (i,j) occupies pad[i+1, j+1]
+        # node (i,j) touches cells (i-1..i, j-1..j)
+        touch_in = pad[0:nxn, 0:nyn] | pad[1:nxn + 1, 0:nyn] | pad[0:nxn, 1:nyn + 1] | pad[1:nxn + 1, 1:nyn + 1]
+        touch_all = pad[0:nxn, 0:nyn] & pad[1:nxn + 1, 0:nyn] & pad[0:nxn, 1:nyn + 1] & pad[1:nxn + 1, 1:nyn + 1]
+        rim = touch_in & ~touch_all
+        ii, jj = np.nonzero(rim)
+        interior = (ii > 0) & (ii < nxn - 1) & (jj > 0) & (jj < nyn - 1)
+        ii, jj = ii[interior], jj[interior]
+        dx, dy = xs[ii] - cx, ys[jj] - cy
+        d = np.hypot(dx, dy)
+        ok = d > 1e-12
+        scale = np.where(ok, r / np.where(ok, d, 1.0), 1.0)
+        sx, sy = dx * (scale - 1.0), dy * (scale - 1.0)
+        lim = max_shift * np.minimum(hx[ii], hy[jj])
+        mag = np.hypot(sx, sy)
+        f = np.where(mag > lim, lim / np.where(mag > 0, mag, 1.0), 1.0)
+        sx, sy = sx * f, sy * f
+        for k in range(nzn):
+            nid = _grid_node_id(ii, jj, k, nxn, nyn)
+            out[nid, 0] += sx
+            out[nid, 1] += sy
+    return out
+
+
 def graded_lines(L, h_far, refine=None):
     """1-D grid lines on [0, L]: spacing ~h_far, refined to ~h_near inside the
     intervals listed in ``refine`` = [(lo, hi, h_near), ...] (merged, clipped)."""
@@ -282,7 +315,7 @@ def graded_lines(L, h_far, refine=None):
 
 
 def electrode_box_mesh(Lx, Ly, Lz, e1_xy, e2_xy, r, shape="circle", h_elec=None, h_bulk=None,
-                       nz=None, with_parents=True):
+                       nz=None, with_parents=True, snap_rim=False):
     """Homogeneous box with two electrode patches on the top face.
 
     Geometry/tags follow ``step02_electrodes/run_sweep.py:39-52,63-103``: box
@@ -315,6 +348,14 @@ def electrode_box_mesh(Lx, Ly, Lz, e1_xy, e2_xy, r, shape="circle", h_elec=None,
     ca = np.diff(xs)[:, None] * np.diff(ys)[None, :]
     m1 = _footprint_mask(xc, yc, e1_xy[0], e1_xy[1], r, shape, cell_area=ca)
     m2 = _footprint_mask(xc, yc, e2_xy[0], e2_xy[1], r, shape, cell_area=ca)
+    if snap_rim and shape == "circle":
+        shift = 0.42
+        while shift > 0.05:
+            cand = _snap_rim_columns(m["nodes"], nxn, nyn, nzn, xs, ys, (m1, m2), (e1_xy, e2_xy), r, shift)
+            if (tet_volumes(cand, m["tets"]) > 0).all():
+                m["nodes"] = cand
+                break
+            shift *= 0.5
     rest = ~(m1 | m2)
     k_top = nzn - 1
     q1 = _plane_quads(nxn, nyn, nzn, 2, k_top, m1)
@@ -340,7 +381,7 @@ def layered_slab_mesh(Lx=0.080, Ly=0.060, Lz=0.040, t_skin=0.0015, t_fat=0.005, 
                       active_xy=(0.015, 0.045), return_xy=(0.065, 0.045), elec_r=0.010, shape="circle",
                       xs=None, ys=None, n_muscle=12, n_fat=3, n_skin=2, n_contact=1,
                       h_bulk=0.003, h_elec=0.0015, jitter=0.0, seed=0,
-                      interfaces_as_103=True, with_parents=True, contact_enabled=True):
+                      interfaces_as_103=True, with_parents=True, contact_enabled=True, snap_rim=False):
     """Layered slab: muscle (body 1) / fat (2) / skin (3) + two contact pads
     (4 active, 5 return) sitting ON TOP of the skin.
 
@@ -401,6 +442,15 @@ def layered_slab_mesh(Lx=0.080, Ly=0.060, Lz=0.040, t_skin=0.0015, t_fat=0.005, 
     region = np.repeat(body, 6).astype(np.int32)
     nodes = m["nodes"]
     orient_positive(nodes, tets)
+    if snap_rim and shape == "circle":
+        # follow the circular electrode edge instead of the grid's staircase (halved until no element inverts)
+        shift = 0.42
+        while shift > 0.05:
+            cand = _snap_rim_columns(nodes, nxn, nyn, nzn, xs, ys, (m1, m2), (active_xy, return_xy), elec_r, shift)
+            if (tet_volumes(cand, tets) > 0).all():
+                nodes = cand
+                break
+            shift *= 0.5
     # boundary triangles
     k_elec = nzn - 1 if nc else k_top
     q101 = _plane_quads(nxn, nyn, nzn, 2, k_elec, m1)
