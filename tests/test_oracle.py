@@ -131,7 +131,7 @@ def test_layered_oracle_vs_golden_table(golden):
                          elec_area_mesh=Aa, return_area_mesh=Ar, e1_id=e1id, e2_id=e2id)
     gold = [r for r in json.load(open(golden / "step03_summary.json")) if r["t_fat_mm"] == 5.0 and r["elec_r_mm"] == 10.0][0]
     assert list(row.keys()) == list(gold.keys())                       # 36 columns, same order
-    for k, tol in (("compliance_V", 0.08), ("roi_mean_J", 0.08), ("roi_mean_E", 0.08), ("elec_area_mesh_cm2", 0.03)):
+    for k, tol in (("compliance_V", 0.02), ("roi_mean_J", 0.04), ("roi_mean_E", 0.06), ("elec_area_mesh_cm2", 0.002)):
         assert abs(row[k] - gold[k]) / abs(gold[k]) < tol, (k, row[k], gold[k])
     for k in ("elec_shape", "contact_enabled", "control_mode", "roi_layer", "roi_center_z_mm", "dist_fat_muscle_mm",
               "active_boundary_id_used", "return_boundary_id_used", "elec_area_cm2", "t_fat_mm", "elec_r_mm"):
