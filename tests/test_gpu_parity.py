@@ -488,3 +488,32 @@ def test_unstructured_delaunay_mesh(monkeypatch, morton):
         assert rel(phi3[k], ref["phi"] * (1.0 + k) / 4.0) < TOL_PHI          # linearity in the injected current
     dm.close()
     ctx.close()
+
+
+def test_hub_node_mesh_falls_back_to_vector_kernel(gpu_ctx):
+    # a star of tets around one centre node: one row with ~5000 entries, which no shared-memory tile can hold,
+    # so the pattern disables the streaming kernel and every SpMV variant request resolves to the vector kernel
+    from scipy.spatial import ConvexHull
+    rng = np.random.default_rng(11)
+    p = rng.standard_normal((5000, 3))
+    p /= np.linalg.norm(p, axis=1)[:, None]
+    hull = ConvexHull(p)
+    nodes = np.vstack([p * 0.01, [[0.0, 0.0, 0.0]]])
+    tets = np.column_stack([hull.simplices, np.full(hull.simplices.shape[0], 5000)]).astype(np.int32)
+    meshgen.orient_positive(nodes, tets)
+    tris = hull.simplices.astype(np.int32)
+    bcid = np.where(nodes[tris][:, :, 2].mean(axis=1) > 0.005, 101, np.where(nodes[tris][:, :, 2].mean(axis=1) < -0.005, 102, 103)).astype(np.int32)
+    m = meshgen.TetMesh(nodes, tets, np.ones(tets.shape[0], np.int32), tris, bcid)
+    ref = fo.solve_case(m, {1: 0.2}, [(101, 1.0), (102, 0.0)], [], recover="l2")
+    dm = dm_for(gpu_ctx, m)
+    rowptr, col = dm.get_pattern()
+    rp, cc = fo.csr_pattern(m.nn, m.tets)
+    assert np.array_equal(rowptr, rp) and np.array_equal(col, cc) and np.diff(rowptr).max() == 5001
+    dm.assemble({1: 0.2}).bc_reset(1).dirichlet(101, 1.0).dirichlet(102, 0.0)
+    x = rng.standard_normal(m.nn)
+    for variant in (engine.SPMV_AUTO, engine.SPMV_STREAM, engine.SPMV_VECTOR):
+        assert rel(dm.spmv(x, 0, True, variant), ref["K"] @ x) < 1e-12
+    phi = dm.solve(spmv_variant=engine.SPMV_STREAM, rtol=1e-12)[0]
+    assert rel(phi, ref["phi"]) < TOL_PHI
+    assert rel(dm.recover_current(0, "l2"), ref["J"]) < TOL_FIELD
+    dm.close()
