@@ -97,6 +97,43 @@ def write_sif(run_dir, e1_id, e2_id, p, elec_r, body_info, sigma_skin_override=N
     return jn_used
 
 
+def nerve_polyline(p, e1_pos, body_info):
+    """Sample points along the (straight) tibial-nerve fibre: by default parallel to x at the ROI depth
+    (``roi.z_target`` below the skin, ``params.yaml:72-74``) under the electrode row, 5 mm clear of the slab ends.
+    Optional ``nerve: {points: [[x,y,z],...], internode_mm: h}`` in params.yaml gives an explicit polyline and
+    sample spacing.  The spacing defaults to 2 mm (node-of-Ranvier scale, and not below the element size: the
+    second difference of a P1 potential sampled finer than the mesh is a train of kinks)."""
+    nv = p.get("nerve", {})
+    h = float(nv.get("internode_mm", 2.0)) * 1e-3
+    if "points" in nv:
+        ctrl = np.asarray(nv["points"], dtype=float)
+    else:
+        g = p["geometry"]
+        z = body_info["z_skin_top"] - p["roi"]["z_target"]
+        ctrl = np.array([[0.005, e1_pos[1], z], [g["Lx"] - 0.005, e1_pos[1], z]])
+    seg = np.linalg.norm(np.diff(ctrl, axis=0), axis=1)
+    s_ctrl = np.concatenate([[0.0], np.cumsum(seg)])
+    n = max(3, int(round(s_ctrl[-1] / h)) + 1)
+    s = np.linspace(0.0, s_ctrl[-1], n)
+    pts = np.stack([np.interp(s, s_ctrl, ctrl[:, k]) for k in range(3)], axis=1)
+    return s, pts
+
+
+def save_activating_function(case, p, e1_pos, body_info, run_dir):
+    """Potential and activating function (second difference of phi along the fibre, V/m^2) sampled on the GPU
+    (K13; BASELINE.json north_star - the reference only has the ROI-mean |E| proxy, ``run_layered_sweep.py:930-936``)."""
+    s, pts = nerve_polyline(p, e1_pos, body_info)
+    phi, af = case.dmesh.sample_polyline(pts)
+    out = Path(run_dir) / "results" / "activating_function.csv"
+    with open(out, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["s_m", "x_m", "y_m", "z_m", "phi_V", "activating_function_V_per_m2"])
+        for k in range(len(s)):
+            w.writerow([f"{s[k]:.6e}", f"{pts[k,0]:.6e}", f"{pts[k,1]:.6e}", f"{pts[k,2]:.6e}", f"{phi[k]:.9e}", f"{af[k]:.9e}"])
+    ok = np.isfinite(af)
+    return float(np.max(af[ok])) if ok.any() else float("nan"), out
+
+
 def case_label(t_fat, elec_r):
     return f"tfat{int(t_fat*1000):04d}um_r{int(elec_r*1000):04d}um"
 
@@ -127,6 +164,8 @@ def run_case(p, t_fat, elec_r, coarse=False, sigma_skin_override=None, ctx=None,
     res = pipeline.extract_layered(case, p, t_fat, elec_r, e1_pos, e2_pos, body_info, sigma_skin_used=sigma_skin,
                                    jn_used=jn_used, elec_area_mesh=A_act, return_area_mesh=A_ret, e1_id=e1_id,
                                    e2_id=e2_id, warn=say)
+    af_peak, af_path = save_activating_function(case, p, e1_pos, body_info, run_dir)
+    say(f"    activating function along the nerve fibre: peak {af_peak:.4e} V/m² → {af_path.name}")
     case.close()
     say(f"    peak_J_no_elec={res['peak_J_skin_no_elec']:.4f}  roi_mean_E={res['roi_mean_E']:.4f}  "
         f"efficiency={res['efficiency']:.4e}  flux_err={res['flux_err']:.3e}")
