@@ -159,7 +159,8 @@ def run_case(p, t_fat, elec_r, coarse=False, sigma_skin_override=None, ctx=None,
     pipeline.save_bc_debug_report(run_dir, label, e1_id, e2_id, A_act, A_ret, jn_used, p, body_info)
     (run_dir / "results").mkdir(exist_ok=True)
     say("  solver (GPU engine) ...")
-    case = pipeline.run_elmer_solver(run_dir, ctx=ctx, mesh=mesh)
+    case = pipeline.run_elmer_solver(run_dir, ctx=ctx, mesh=mesh,
+                                     recover=p.get("solver", {}).get("current_recovery", pipeline.DEFAULT_RECOVER))
     say("  extracting metrics ...")
     res = pipeline.extract_layered(case, p, t_fat, elec_r, e1_pos, e2_pos, body_info, sigma_skin_used=sigma_skin,
                                    jn_used=jn_used, elec_area_mesh=A_act, return_area_mesh=A_ret, e1_id=e1_id,

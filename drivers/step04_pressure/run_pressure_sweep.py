@@ -75,11 +75,12 @@ def run_pressure_sweep(p, sigma_contact_list, pressure_labels, coarse=False, seq
         (run_dir / "results").mkdir(exist_ok=True)
         problems.append(sif.problem_from_sif((run_dir / "case.sif").read_text()))
         jn_list.append(jn)
+    recover = p.get("solver", {}).get("current_recovery", pipeline.DEFAULT_RECOVER)
     all_results = []
     if sequential:
         for k, (sigma_c, label) in enumerate(zip(sigma_contact_list, pressure_labels)):
             print(f"\n[{label}]  sigma_contact={sigma_c:.4f} S/m")
-            case = pipeline.run_elmer_solver(results_dir / label, ctx=ctx, mesh=mesh, dmesh=dmesh)
+            case = pipeline.run_elmer_solver(results_dir / label, ctx=ctx, mesh=mesh, dmesh=dmesh, recover=recover)
             all_results.append(_row(case, p, sigma_c, label, e1_pos, e2_pos, body_info, jn_list[k], 0))
     else:
         for b0 in range(0, len(problems), BATCH):
@@ -96,7 +97,7 @@ def run_pressure_sweep(p, sigma_contact_list, pressure_labels, coarse=False, seq
             phi = dmesh.solve()
             for j, k in enumerate(chunk):
                 label, sigma_c = pressure_labels[k], sigma_contact_list[k]
-                J = dmesh.recover_current(j, "l2")
+                J = dmesh.recover_current(j, recover)
                 case = pipeline.SolvedCase(mesh, dmesh, phi[j], J, dmesh.last_stats, problems[k])
                 pipeline.write_case_vtu(results_dir / label / "results" / "case_t0001.vtu", mesh, phi[j], J)
                 print(f"\n[{label}]  sigma_contact={sigma_c:.4f} S/m")
@@ -139,7 +140,8 @@ def run_compression_sweep(p, sigma_contact_list, pressure_labels, max_compressio
         (run_dir / "results").mkdir(exist_ok=True)
         dmesh.set_coords(nodes_k)
         print(f"\n[{label}]  sigma_contact={sigma_c:.4f} S/m  compression={depth*1e3:.2f} mm")
-        case = pipeline.run_elmer_solver(run_dir, ctx=ctx, mesh=mesh_k, dmesh=dmesh)
+        case = pipeline.run_elmer_solver(run_dir, ctx=ctx, mesh=mesh_k, dmesh=dmesh,
+                                         recover=p.get("solver", {}).get("current_recovery", pipeline.DEFAULT_RECOVER))
         row = _row(case, p, sigma_c, label, [*e1_pos[:2], z1], [*e2_pos[:2], z2], bi, jn, 0)
         row["compression_mm"] = round(depth * 1e3, 4)
         rows.append(row)

@@ -166,7 +166,11 @@ def recover_nodal_current(nodes, tets, region, sigma_by_body, phi, method="l2"):
 
     method "l2"      : Galerkin L2 projection  M J^k = int (-sigma d_k phi) N_i dV  (consistent mass)
            "lumped"  : same right-hand side, row-sum lumped mass (= volume-weighted mean of J_e)
-           "average" : unweighted mean of J_e over the tets touching the node."""
+           "average" : unweighted mean of J_e over the tets touching the node.
+    Which of these Elmer's ``Calculate Volume Current`` implements cannot be read here (no Elmer source); the
+    reference's own step03/step04 tables favour "lumped": the pad current integrated from the nodal field is
+    5.58 / 5.30 / 5.20 mA (r = 5 / 10 / 15 mm) with it and 6.25 / 5.65 / 5.39 mA with "l2", against
+    5.51 / 5.27 / 5.14 mA in ``step03_ankle_layers/results/summary.csv``."""
     nn = nodes.shape[0]
     _, Je, vol = element_fields(nodes, tets, region, sigma_by_body, phi)
     if method == "average":

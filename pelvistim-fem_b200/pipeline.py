@@ -117,6 +117,14 @@ def save_bc_debug_report(run_dir, label, e1_id, e2_id, A_active_mesh, A_return_m
 # ---------------------------------------------------------------------------
 # the solve step (what `ElmerSolver case.sif` does)
 # ---------------------------------------------------------------------------
+# Nodal "volume current" recovery used by the drivers and the ElmerSolver shim.  The reference's tables pin this
+# choice: on the rim-fitted built-in meshes the pad current integrated from the nodal field is 5.58 / 5.30 / 5.20 mA
+# (r = 5 / 10 / 15 mm) with the volume-weighted nodal average ("lumped"), 6.25 / 5.65 / 5.39 mA with the consistent-mass
+# L2 projection, against 5.51 / 5.27 / 5.14 mA in step03_ankle_layers/results/summary.csv - Elmer's field behaves like
+# the former.  ``solver: {current_recovery: l2 | lumped | average}`` in params.yaml overrides it.
+DEFAULT_RECOVER = "lumped"
+
+
 class SolvedCase:
     """Device-resident result of one case: mesh, solution and recovered current stay on the GPU
     for the metric kernels; ``phi`` / ``J`` are host copies (what the VTU holds)."""
@@ -137,7 +145,7 @@ def default_context(device=0) -> Context:
     return _CTX[device]
 
 
-def solve_problem(ctx: Context, mesh, problem: sif.Problem, recover="l2", dmesh=None, **opts) -> SolvedCase:
+def solve_problem(ctx: Context, mesh, problem: sif.Problem, recover=DEFAULT_RECOVER, dmesh=None, **opts) -> SolvedCase:
     """Assemble + BCs + PCG + nodal current recovery for a parsed SIF problem on ``mesh``.
     ``dmesh`` lets a sweep reuse the device mesh/pattern (step04: same mesh, new conductivities)."""
     if not problem.dirichlet:
@@ -162,7 +170,7 @@ def write_case_vtu(path, mesh, phi, J):
     vtu.write_vtu(path, mesh.nodes, mesh.tets, mesh.tris, point_data=pd, cell_data={"GeometryIds": geom})
 
 
-def run_elmer_solver(run_dir, sif_name="case.sif", ctx=None, mesh=None, dmesh=None, recover="l2", keep=True, **opts):
+def run_elmer_solver(run_dir, sif_name="case.sif", ctx=None, mesh=None, dmesh=None, recover=DEFAULT_RECOVER, keep=True, **opts):
     """In-process stand-in for ``subprocess.run(["ElmerSolver", "case.sif"], cwd=run_dir)``.
     Raises on any failure (the reference exits non-zero); returns the ``SolvedCase``."""
     run_dir = Path(run_dir)

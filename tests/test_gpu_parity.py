@@ -279,7 +279,7 @@ def _layered_case(gpu_ctx, coarse=True):
 def test_step03_row_matches_oracle(gpu_ctx, golden):
     p, mesh, e1, e2, bi, (e1id, e2id, Aa, Ar), jn, case, v = _layered_case(gpu_ctx)
     assert np.array_equal(v["point_data"]["potential"], case.phi) and "volume current" in v["point_data"]
-    ref = fo.solve_case(mesh, case.problem.sigma_by_body, case.problem.dirichlet, case.problem.neumann, recover="l2")
+    ref = fo.solve_case(mesh, case.problem.sigma_by_body, case.problem.dirichlet, case.problem.neumann, recover=pipeline.DEFAULT_RECOVER)
     assert rel(case.phi, ref["phi"]) < TOL_PHI and rel(case.J, ref["J"]) < TOL_FIELD
     got = pipeline.extract_layered(case, p, 0.005, 0.010, e1, e2, bi, jn_used=jn, elec_area_mesh=Aa, return_area_mesh=Ar,
                                    e1_id=e1id, e2_id=e2id, warn=lambda *a: None)
@@ -300,7 +300,7 @@ def test_step04_row_matches_oracle(gpu_ctx, golden):
     import yaml
     p4 = yaml.safe_load((golden / "step04_params.yaml").read_text())
     _, mesh, e1, e2, bi, ids, jn, case, _ = _layered_case(gpu_ctx)
-    ref = fo.solve_case(mesh, case.problem.sigma_by_body, case.problem.dirichlet, case.problem.neumann, recover="l2")
+    ref = fo.solve_case(mesh, case.problem.sigma_by_body, case.problem.dirichlet, case.problem.neumann, recover=pipeline.DEFAULT_RECOVER)
     got = pipeline.extract_pressure(case, p4, 0.005, "p08", e1, e2, bi, jn, warn=lambda *a: None)
     want = mo.pressure_row(mesh.nodes, mesh.tets, mesh.tris, ref["phi"], ref["J"], p4, 0.005, "p08", e1, e2, bi, jn)
     gold = json.load(open(golden / "step04_summary.json"))[0]
@@ -403,7 +403,7 @@ def test_elmersolver_shim_subprocess(tmp_path):
     assert pr.returncode == 0, pr.stdout + pr.stderr
     v = vtu.read_vtu(tmp_path / "results" / "case_t0001.vtu")            # the file every consumer reads (:831-834)
     prob = sif.problem_from_sif((tmp_path / "case.sif").read_text())
-    ref = fo.solve_case(m, prob.sigma_by_body, prob.dirichlet, prob.neumann, recover="l2")
+    ref = fo.solve_case(m, prob.sigma_by_body, prob.dirichlet, prob.neumann, recover=pipeline.DEFAULT_RECOVER)
     assert rel(v["point_data"]["potential"], ref["phi"]) < TOL_PHI
     assert rel(v["point_data"]["volume current"], ref["J"]) < TOL_FIELD
     assert v["cell_types"].tolist().count(10) == m.nt and v["cell_types"].tolist().count(5) == m.nb
