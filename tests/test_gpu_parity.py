@@ -517,3 +517,24 @@ def test_hub_node_mesh_falls_back_to_vector_kernel(gpu_ctx):
     assert rel(phi, ref["phi"]) < TOL_PHI
     assert rel(dm.recover_current(0, "l2"), ref["J"]) < TOL_FIELD
     dm.close()
+
+
+# -- the full step04 driver against the reference's committed table (golden fixture, discretisation-level bars) --------
+def test_step04_driver_reproduces_reference_table(gpu_ctx, golden, tmp_path):
+    import run_pressure_sweep as s4
+    p = s4.load_params()
+    ps = p["pressure_sweep"]
+    rows = s4.run_pressure_sweep(p, ps["sigma_contact_Spm"], ps["labels"], ctx=gpu_ctx, results_dir=tmp_path)
+    gold = json.load(open(golden / "step04_summary.json"))
+    assert len(rows) == len(gold) == 15 and [list(r.keys()) for r in rows] == [list(g.keys()) for g in gold]
+    for r, g in zip(rows, gold):
+        assert r["pressure_label"] == g["pressure_label"] and r["sigma_contact_Spm"] == g["sigma_contact_Spm"]
+        assert abs(r["jn_used_A_m2"] - g["jn_used_A_m2"]) / g["jn_used_A_m2"] < 2e-3          # mesh area 3.1307 vs 3.1299 cm2
+        for k, tol in (("compliance_V", 0.02), ("contact_impedance_ohm", 0.035), ("I_active_A", 0.025), ("I_return_A", 0.06),
+                       ("roi_mean_J", 0.05), ("roi_mean_E", 0.06)):
+            assert abs(r[k] - g[k]) / abs(g[k]) < tol, (r["pressure_label"], k, r[k], g[k])
+        assert r["exceeded_compliance"] == g["exceeded_compliance"] and r["exceeds_charge_limit"] == g["exceeds_charge_limit"]
+    # per-case files exist where the reference puts them (run_pressure_sweep.py:709-738)
+    for lbl in ("p01", "p15"):
+        assert (tmp_path / lbl / "case.sif").exists() and (tmp_path / lbl / "results" / "case_t0001.vtu").exists()
+        assert (tmp_path / lbl / "elmer_mesh" / "mesh.nodes").exists()
