@@ -27,6 +27,8 @@ for case in ("tfat0003um_r0005um", "tfat0005um_r0010um", "tfat0008um_r0015um"):
 for lvl in ("p01", "p08", "p15"):
     ITEMS.append((f"step04_pressure/results/{lvl}/case.sif", f"step04_{lvl}_case.sif"))
 
+# step02_png_titles.json is transcribed by hand from step02_electrodes/results/sweep_J_maps.png
+
 if __name__ == "__main__":
     for src, dst in ITEMS:
         shutil.copyfile(REF / src, OUT / dst)

@@ -538,3 +538,19 @@ def test_step04_driver_reproduces_reference_table(gpu_ctx, golden, tmp_path):
     for lbl in ("p01", "p15"):
         assert (tmp_path / lbl / "case.sif").exists() and (tmp_path / lbl / "results" / "case_t0001.vtu").exists()
         assert (tmp_path / lbl / "elmer_mesh" / "mesh.nodes").exists()
+
+
+def test_step02_driver_against_png_title_numbers(golden, tmp_path, monkeypatch):
+    # the only step02 goldens are the peak / mean |J| printed in the reference's PNG titles; both are mesh-density
+    # dependent (node maximum at the electrode edge; unweighted node mean over the whole top face, run_sweep.py:331-333)
+    import run_sweep as s2
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(s2, "RESULTS", tmp_path / "results")
+    rows = s2.main([])
+    gold = json.load(open(golden / "step02_png_titles.json"))
+    assert [r["label"] for r in rows][:2] == ["circle_r05mm", "circle_r10mm"] and len(rows) == 8
+    for r in rows:
+        peak, mean = gold[r["shape"]][str(int(round(r["r"] * 1000)))]
+        assert abs(r["peak_J"] - peak) / peak < 0.16, (r["label"], r["peak_J"], peak)
+        assert abs(r["mean_J"] - mean) / mean < 0.25, (r["label"], r["mean_J"], mean)
+        assert (tmp_path / "results" / r["label"] / "results" / "case_t0001.vtu").exists()
