@@ -554,3 +554,24 @@ def test_step02_driver_against_png_title_numbers(golden, tmp_path, monkeypatch):
         assert abs(r["peak_J"] - peak) / peak < 0.16, (r["label"], r["peak_J"], peak)
         assert abs(r["mean_J"] - mean) / mean < 0.25, (r["label"], r["mean_J"], mean)
         assert (tmp_path / "results" / r["label"] / "results" / "case_t0001.vtu").exists()
+
+
+def test_step03_driver_reproduces_reference_table(gpu_ctx, golden, tmp_path, monkeypatch):
+    import run_layered_sweep as s3
+    monkeypatch.setattr(s3, "RESULTS_DIR", tmp_path)
+    monkeypatch.setattr(s3.sweep, "worker_context", lambda: gpu_ctx)
+    p = s3.load_params()
+    rows = s3.run_sweep(p, p["layers"]["t_fat_sweep"], p["placement"]["electrode_r_mm_list"])
+    gold = json.load(open(golden / "step03_summary.json"))
+    assert len(rows) == len(gold) == 9
+    for r, g in zip(rows, gold):
+        assert list(r.keys()) == list(g.keys()) and (r["t_fat_mm"], r["elec_r_mm"]) == (g["t_fat_mm"], g["elec_r_mm"])
+        for k, tol in (("elec_area_mesh_cm2", 0.025), ("jn_used", 0.025), ("compliance_V", 0.03), ("total_current_A", 0.035),
+                       ("roi_mean_J", 0.10), ("roi_center_z_mm", 1e-12), ("dist_fat_muscle_mm", 1e-12)):
+            assert abs(r[k] - g[k]) <= tol * abs(g[k]), (r["t_fat_mm"], r["elec_r_mm"], k, r[k], g[k])
+        for k in ("elec_shape", "contact_enabled", "control_mode", "roi_layer", "active_boundary_id_used", "return_boundary_id_used",
+                  "exceeded_compliance", "elec_area_cm2"):
+            assert r[k] == g[k], k
+    label = "tfat0005um_r0010um"
+    for f in ("mesh.msh", "case.sif", "bc_debug_report.txt", "elmer_mesh/mesh.boundary", "results/case_t0001.vtu"):
+        assert (tmp_path / label / f).exists(), f                      # per-case layout of README.md:67-86
