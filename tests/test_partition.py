@@ -92,3 +92,24 @@ def test_two_process_gloo_solve():
     assert len(its) == 1                                    # both ranks agree on the iteration count
     for rank, it, rel, err in res:
         assert rel <= 1e-11 and err < 1e-7, (rank, it, rel, err)
+
+
+# -- sweep-level sharding: independent points over worker processes, rows gathered in sweep order ------------------
+def _point_fn(pt):
+    from pelvistim_fem_b200 import sweep
+    return dict(point=pt, square=pt * pt, rank=sweep.worker_rank())
+
+
+def _failing_fn(pt):
+    if pt == 3:
+        raise ValueError("boom")
+    return pt
+
+
+def test_sweep_map_points_two_workers():
+    from pelvistim_fem_b200 import sweep
+    out = sweep.map_points(_point_fn, list(range(7)), gpus=2)
+    assert [r["point"] for r in out] == list(range(7)) and [r["square"] for r in out] == [k * k for k in range(7)]
+    assert [r["rank"] for r in out] == [k % 2 for k in range(7)]            # point i -> GPU i mod G
+    with pytest.raises(RuntimeError, match="boom"):
+        sweep.map_points(_failing_fn, [1, 2, 3, 4], gpus=2)
