@@ -34,6 +34,7 @@ SIGMA = {1: 0.35, 2: 0.04, 3: 0.001}
 I_INJECT = 5e-3
 RTOL = 1e-10
 METRIC = "electrode_sweep_solves_per_s"
+RECOVER = "lumped"   # = pipeline.DEFAULT_RECOVER: the nodal current recovery the drivers use
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -69,7 +70,7 @@ def run_sweep_step(dm, mesh, confs, step, phi_out=None, J_out=None, sample_spmv=
     Lz, t_skin = mesh.meta["Lz"], mesh.meta["t_skin"]
     rows = []
     for k, c in enumerate(confs):
-        dm.recover_current(k, "l2", to_host=J_out is not None, out=None if J_out is None else J_out[k])
+        dm.recover_current(k, RECOVER, to_host=J_out is not None, out=None if J_out is None else J_out[k])
         fp = (c["center"][0], c["center"][1], c["r"], False)
         pk = dm.metric_nodes(0, Lz - 0.2 * t_skin, sys=k)
         ph = dm.metric_nodes(1, Lz - 1e-5, mode=1, footprints=[fp], scale_r=1.0, sys=k)
@@ -199,8 +200,8 @@ def reference_arm(args, rank):
 
 def workload_config(args, mesh, nnz):
     return {"workload": f"synth_slab {args.size} ({mesh.nt} tets, {mesh.nn} nodes{'' if nnz is None else f', {nnz} nnz'}): electrode sweep of "
-                        f"{args.nconf} Neumann-patch configurations on one matrix (multi-RHS Jacobi-PCG, rtol {RTOL:g}) + L2 current "
-                        "recovery + metric reductions per configuration",
+                        f"{args.nconf} Neumann-patch configurations on one matrix (multi-RHS Jacobi-PCG, rtol {RTOL:g}) + nodal current "
+                        f"recovery ({RECOVER}) + metric reductions per configuration",
             "mesh": f"synth_slab_{args.size}", "nconf": args.nconf, "rtol": RTOL, "sweep_points_per_gpu_per_step": args.nconf,
             "l2": "inputs larger than L2 (matrix + vectors > 126 MB)" if mesh.nt > 4_000_000 else "flushed between steps"}
 
