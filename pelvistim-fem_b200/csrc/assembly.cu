@@ -154,6 +154,12 @@ __global__ void set_tri_load_list(const int32_t* __restrict__ idx, int64_t n, in
   }
 }
 
+__global__ void any_dirichlet_kernel(const uint8_t* __restrict__ isdir, int64_t nn, int32_t* __restrict__ flag) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int has = i < nn && isdir[i];
+  if (__any_sync(0xffffffffu, has) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
 // Neumann load vector, gather over the node's boundary triangles in ascending triangle order.
 __global__ void neumann_load_kernel(const int32_t* __restrict__ n2b_ptr, const int32_t* __restrict__ n2b,
                                     const double* __restrict__ tri_area, const double* __restrict__ tri_load,
@@ -380,6 +386,19 @@ int ptfem_apply_bc(ptfem_mesh* m, double* dinv_out /*[nn][VS]*/, int* S_out) {
   if (VS != 1 && m->nrhsp != 1 && VS != m->nrhsp)
     return set_err(PTFEM_ERR_ARG, "batched matrices (%d) and right-hand sides (%d) must match or one of them be 1", m->nval,
                    m->nrhs);
+  {  // a problem without any `Potential` node is singular (pure Neumann): refuse instead of iterating forever
+    DevBuf<int32_t> flag;
+    PT_TRY(flag.alloc(1));
+    PT_TRY(fill_i32(ctx, flag.p, 0, 1));
+    any_dirichlet_kernel<<<ceil_div(m->nn, 256), 256, 0, ctx->stream>>>(m->isdir.p, m->nn, flag.p);
+    PT_LAUNCH_CHECK(ctx);
+    int32_t h = 0;
+    PT_CK(cudaMemcpyAsync(&h, flag.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    if (!h)
+      return set_err(PTFEM_ERR_ARG, "no mesh node carries a Potential (Dirichlet) condition: the boundary ids given to "
+                                    "ptfem_bc_dirichlet do not occur in the mesh, or none was set (pure Neumann problem is singular)");
+  }
   neumann_load_kernel<<<ceil_div(m->nn, 128), 128, 0, ctx->stream>>>(m->n2b_ptr.p, m->n2b.p, m->tri_area.p, m->tri_load.p,
                                                                       m->nn, m->nb, m->nrhsp, m->b_neu.p);
   PT_LAUNCH_CHECK(ctx);

@@ -77,6 +77,9 @@ def test_bad_inputs_raise(gpu_ctx):
     dm.assemble({1: 0.2})
     with pytest.raises(engine.PtfemError):          # solve before BCs
         dm.solve()
+    dm.bc_reset(1).neumann(101, 1.0).dirichlet(999, 0.0)          # boundary id 999 does not exist -> pure Neumann
+    with pytest.raises(engine.PtfemError, match="Dirichlet"):
+        dm.solve()
     flat = m.nodes.copy()
     flat[:, 2] = 0.0
     with pytest.raises(engine.PtfemError):          # degenerate tets
