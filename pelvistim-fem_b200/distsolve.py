@@ -29,23 +29,43 @@ def partitioned_solve(ctx, mesh, sigma_by_body, dirichlet, neumann, rank, world,
         single_stats = dm.last_stats
     dm.close()
     blk = partition.local_block(rowptr, col, val, b, rank, world)
-    if world > 1:
-        if transport == "nccl":
-            ids = [engine.dist_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(ids, src=0)
-            engine.dist_init(ctx, ids[0], rank, world)
-        else:
-            engine.dist_init(ctx, None, rank, world)
-    ds = engine.DistSystem(ctx, blk)
+    used = transport if world > 1 else "single"
+    ds = None
     if world > 1 and transport == "p2p":
-        handles = [None] * world
-        dist.all_gather_object(handles, ds.p2p_export())
-        ds.p2p_connect(handles, partition.halo_sources(blk, n=rowptr.shape[0] - 1))
-        dist.barrier()
+        # peer memory needs CUDA IPC between the ranks' processes; every rank must agree on whether it works
+        ok = 1
+        try:
+            engine.dist_init(ctx, None, rank, world)
+            ds = engine.DistSystem(ctx, blk)
+            handles = [None] * world
+            dist.all_gather_object(handles, ds.p2p_export())
+            ds.p2p_connect(handles, partition.halo_sources(blk, n=rowptr.shape[0] - 1))
+        except engine.PtfemError as e:
+            ok = 0
+            p2p_error = str(e)
+        flags = [None] * world
+        dist.all_gather_object(flags, ok)
+        if not all(flags):
+            if ds is not None:
+                ds.close()
+                ds = None
+            engine.dist_finalize(ctx)
+            used = "nccl"
+            if rank == 0:
+                print(f"distsolve: peer-memory transport unavailable ({p2p_error if not ok else 'on another rank'}); using NCCL", flush=True)
+        else:
+            dist.barrier()
+    if world > 1 and used == "nccl":
+        ids = [engine.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        engine.dist_init(ctx, ids[0], rank, world)
+    if ds is None:
+        ds = engine.DistSystem(ctx, blk)
     t0 = time.perf_counter()
     x = ds.solve(**opts)
     wall = time.perf_counter() - t0
-    out = dict(x_local=x, row0=blk.row0, nloc=blk.nloc, nhalo=blk.nhalo, stats=ds.last_stats, timings=ds.timings, wall_s=wall)
+    out = dict(x_local=x, row0=blk.row0, nloc=blk.nloc, nhalo=blk.nhalo, stats=ds.last_stats, timings=ds.timings, wall_s=wall,
+               transport=used)
     if check:
         ref = phi_single[blk.row0:blk.row0 + blk.nloc]
         out["rel_err_vs_single"] = float(np.abs(x - ref).max() / max(np.abs(phi_single).max(), 1e-300))
