@@ -34,6 +34,7 @@ SIGMA = {1: 0.35, 2: 0.04, 3: 0.001}
 I_INJECT = 5e-3
 RTOL = 1e-10
 METRIC = "electrode_sweep_solves_per_s"
+PRECOND = -1         # engine.PRECOND_AUTO: Jacobi + geometric coarse grids on this size; --precond jacobi for plain Jacobi
 RECOVER = "lumped"   # = pipeline.DEFAULT_RECOVER: the nodal current recovery the drivers use
 
 
@@ -65,7 +66,7 @@ def run_sweep_step(dm, mesh, confs, step, phi_out=None, J_out=None, sample_spmv=
     for k, c in enumerate(confs):
         dm.neumann_tris(c["tris"], I_INJECT / c["area"], rhs=k)
     dm.dirichlet(102, 0.0)
-    phi = dm.solve(to_host=phi_out is not None, out=phi_out, rtol=RTOL, sample_spmv=sample_spmv, spmv_variant=0)
+    phi = dm.solve(to_host=phi_out is not None, out=phi_out, rtol=RTOL, sample_spmv=sample_spmv, spmv_variant=0, precond=PRECOND)
     stats = dm.last_stats
     Lz, t_skin = mesh.meta["Lz"], mesh.meta["t_skin"]
     rows = []
@@ -200,7 +201,7 @@ def reference_arm(args, rank):
 
 def workload_config(args, mesh, nnz):
     return {"workload": f"synth_slab {args.size} ({mesh.nt} tets, {mesh.nn} nodes{'' if nnz is None else f', {nnz} nnz'}): electrode sweep of "
-                        f"{args.nconf} Neumann-patch configurations on one matrix (multi-RHS Jacobi-PCG, rtol {RTOL:g}) + nodal current "
+                        f"{args.nconf} Neumann-patch configurations on one matrix (multi-RHS PCG to rtol {RTOL:g}; the GPU arm preconditions with Jacobi + geometric coarse grids, the CPU arm with Jacobi) + nodal current "
                         f"recovery ({RECOVER}) + metric reductions per configuration",
             "mesh": f"synth_slab_{args.size}", "nconf": args.nconf, "rtol": RTOL, "sweep_points_per_gpu_per_step": args.nconf,
             "l2": "inputs larger than L2 (matrix + vectors > 126 MB)" if mesh.nt > 4_000_000 else "flushed between steps"}
@@ -216,6 +217,8 @@ def main():
     ap.add_argument("--size", default="L", help="synthetic mesh size (XS, S, M, L)")
     ap.add_argument("--nconf", type=int, default=8)
     ap.add_argument("--cpu-iters", type=int, default=150, help="PCG iterations per CPU sample")
+    ap.add_argument("--precond", choices=["auto", "jacobi", "chebyshev", "twolevel"], default="auto",
+                    help="PCG preconditioner of the GPU arm (auto = Jacobi + coarse grids on meshes >= 100k nodes)")
     ap.add_argument("--cpu-quick", action="store_true", help="reference arm: skip the full CPU solve that measures the iteration count")
     ap.add_argument("--cpu-assumed-iters", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -229,6 +232,8 @@ def main():
     if args.impl == "reference":
         reference_arm(args, rank)
         return
+    global PRECOND
+    PRECOND = {"auto": -1, "jacobi": 0, "chebyshev": 1, "twolevel": 2}[args.precond]
 
     import torch
     import pelvistim_fem_b200  # noqa: F401
@@ -266,13 +271,13 @@ def main():
     ctx.sync(); torch.cuda.synchronize(); barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = ctx.launches
-    spmv_ms, iters, rows = [], [], None
+    spmv_ms, iters, rows, last_st = [], [], None, None
     with ClockSampler(local_rank) as clocks:
         ev0.record(stream)
         for s in range(args.steps):
             l2_flush()
             rows, st, _ = run_sweep_step(dm, mesh, confs, args.warmup + s, sample_spmv=4)
-            spmv_ms.append(st["spmv_ms"]); iters.append(st["iterations"])
+            spmv_ms.append(st["spmv_ms"]); iters.append(st["iterations"]); last_st = st
         ev1.record(stream)
         ctx.sync(); torch.cuda.synchronize()
     launches = ctx.launches - launches0
@@ -286,6 +291,13 @@ def main():
     # single right-hand-side streaming SpMV of the CG (the north-star roofline kernel), timed alone
     dm.bc_reset(1); dm.neumann_tris(confs[0]["tris"], I_INJECT / confs[0]["area"]); dm.dirichlet(102, 0.0)
     spmv1_ms = dm.spmv_bench(engine.SPMV_STREAM, 30)
+    # iterations plain Jacobi-PCG needs on this system (what the CPU arm runs): one untimed solve
+    dm.bc_reset(args.nconf)
+    for k, c in enumerate(confs):
+        dm.neumann_tris(c["tris"], I_INJECT / c["area"], rhs=k)
+    dm.dirichlet(102, 0.0)
+    dm.solve(to_host=False, rtol=RTOL, precond=engine.PRECOND_JACOBI)
+    jacobi_iters, jacobi_ms = dm.last_stats["iterations"], dm.last_stats["solve_ms"]
     dm.close()
 
     # ---- end to end from host buffers -------------------------------------------------------------------
@@ -378,6 +390,9 @@ def main():
             "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, mesh, nnz),
             "clocks": clocks.summary(), "gpu_launches": int(launches), "pcg_iterations_per_step": statistics.mean(iters),
+            "pcg": {"precond": {0: "jacobi", 1: "chebyshev", 2: "jacobi+coarse-grids"}[last_st["precond"]],
+                    "iterations": statistics.mean(iters), "solve_ms": last_st["solve_ms"], "setup_ms": last_st["setup_ms"],
+                    "coarse_unknowns": last_st["coarse_unknowns"], "jacobi_iterations": jacobi_iters, "jacobi_solve_ms": jacobi_ms},
             "roofline": roofline,
             "cg_spmv_1rhs": {"achieved": spmv1_gbs, "unit": "GB/s", "frac": spmv1_gbs / peak, "frac_of_nominal_8TBs": spmv1_gbs / 8000.0,
                              "ms_per_launch": spmv1_ms, "algorithmic_bytes_per_launch": alg1,
@@ -389,12 +404,12 @@ def main():
         line["partitioned_solve"] = part
     if world == 1 and not args.no_cpu:
         _, t_setup, t_it, cores = cpu_sample(mesh, confs[0], args.cpu_iters)
-        n_full = statistics.mean(iters)
+        n_full = jacobi_iters
         per_solve = t_setup + n_full * t_it
         line["cpu_baseline"] = {"value": 1.0 / per_solve, "unit": "solves/s", "cores": cores, "kind": "port",
                                 "sample": f"C/OpenMP oracle on the same mesh: assembly+BC of 1 configuration in full ({t_setup:.2f} s), "
                                           f"{args.cpu_iters} Jacobi-PCG iterations timed ({t_it*1e3:.2f} ms/it), extrapolated to the "
-                                          f"{n_full:.0f} iterations the GPU solve needed at the same tolerance; recovery and metrics not included"}
+                                          f"{n_full:.0f} iterations Jacobi-PCG needs at the same tolerance (counted by a GPU run of the same algorithm); recovery and metrics not included"}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -40,6 +40,10 @@ typedef struct ptfem_mesh ptfem_mesh;
 /* preconditioners (replaces `Linear System Direct Method = UMFPACK`, step01_box/case.sif:41-42) */
 #define PTFEM_PRECOND_JACOBI 0
 #define PTFEM_PRECOND_CHEBYSHEV 1
+#define PTFEM_PRECOND_TWOLEVEL 2 /* Jacobi + geometric coarse-grid correction: trilinear interpolation from regular grids over the
+                                    bounding box, exact Galerkin inverse on the coarsest, diagonal (BPX) on finer ones; one shared
+                                    matrix (multi-RHS) only */
+#define PTFEM_PRECOND_AUTO (-1)  /* TWOLEVEL for one shared matrix with >= 100000 rows, else JACOBI */
 
 /* nodal current recovery (replaces `Calculate Volume Current = True`, step01_box/case.sif:39) */
 #define PTFEM_RECOVER_L2 0      /* Galerkin L2 projection, consistent mass matrix (PCG on the same pattern) */
@@ -55,7 +59,7 @@ typedef struct ptfem_mesh ptfem_mesh;
 typedef struct ptfem_solve_opts {
   int32_t precond;      /* PTFEM_PRECOND_* */
   int32_t maxit;        /* iteration cap (per system) */
-  int32_t check_every;  /* residual is copied to the host every this many iterations */
+  int32_t check_every;  /* residual is copied to the host every this many iterations (0 = 50, or 10 with TWOLEVEL) */
   int32_t cheb_degree;  /* polynomial degree for PTFEM_PRECOND_CHEBYSHEV */
   double rtol;          /* stop when ||b - A x||_2 <= rtol * ||b||_2 for every system (default 1e-10), or when
                            residual replacement shows the round-off floor has been reached (still < 1e-8) */
@@ -64,6 +68,9 @@ typedef struct ptfem_solve_opts {
   int32_t use_graph;    /* capture check_every iterations in a CUDA graph */
   int32_t warm_start;   /* 0: start from phi = 0; 1: start from the solution already on the device */
   int32_t sample_spmv;  /* >0: after the solve, time this many launches of the solve's SpMV kernel (stats.spmv_ms) */
+  int32_t coarse_nodes; /* PTFEM_PRECOND_TWOLEVEL: unknowns of the coarsest (exactly inverted) grid, 0 = default (2000) */
+  int32_t coarse_levels;/* PTFEM_PRECOND_TWOLEVEL: extra finer diagonal-only grids (0..3), each halves the cell size;
+                           -1 (default) = as many as keep >= 16 mesh nodes per cell of the finest grid */
 } ptfem_solve_opts;
 
 typedef struct ptfem_solve_stats {
@@ -75,6 +82,9 @@ typedef struct ptfem_solve_stats {
   double true_rel_residual; /* max over systems of ||b - A x|| / ||b|| recomputed at exit */
   double solve_ms;      /* device time of the iteration loop (CUDA events) */
   double spmv_ms;       /* device time of one SpMV launch, sampled with events after the solve */
+  double setup_ms;      /* device time of the preconditioner set-up this solve paid (coarse grids, Galerkin inverse); 0 if reused */
+  int32_t precond;      /* preconditioner actually used (PTFEM_PRECOND_AUTO resolved) */
+  int32_t coarse_unknowns; /* unknowns of the exactly inverted coarse grid (0 without coarse space) */
 } ptfem_solve_stats;
 
 const char* ptfem_last_error(void);

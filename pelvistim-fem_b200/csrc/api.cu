@@ -222,6 +222,8 @@ int ptfem_mesh_destroy(ptfem_mesh* m) {
   pcg_work_drop_graph(m->work);
   pcg_work_drop_graph(m->work3);
   ptfem_dist_mesh_release(m);
+  if (m->coarse) coarse_free(m->coarse);
+  m->coarse = nullptr;
   delete m;
   return PTFEM_OK;
 }
@@ -231,6 +233,14 @@ int ptfem_mesh_set_coords(ptfem_mesh* m, const double* xyz) {
   PT_CK(cudaSetDevice(m->ctx->device));
   PT_CK(cudaMemcpyAsync(m->xyz.p, xyz, (size_t)m->nn * 3 * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
   PT_CK(cudaStreamSynchronize(m->ctx->stream));
+  for (int d = 0; d < 3; ++d) m->bb_lo[d] = m->bb_hi[d] = xyz[d];
+  for (int64_t i = 0; i < m->nn; ++i)
+    for (int d = 0; d < 3; ++d) {
+      const double v = xyz[3 * i + d];
+      if (v < m->bb_lo[d]) m->bb_lo[d] = v;
+      if (v > m->bb_hi[d]) m->bb_hi[d] = v;
+    }
+  if (m->coarse) m->coarse->geom_ok = false;
   m->has_geom = false;
   if (m->has_pattern) PT_TRY(ptfem_build_geometry(m));
   m->nval = 0;  // values must be re-assembled
@@ -334,9 +344,9 @@ int ptfem_rhs_get(ptfem_mesh* m, int32_t rhs, double* b) {
 
 void ptfem_solve_opts_default(ptfem_solve_opts* o) {
   if (!o) return;
-  o->precond = PTFEM_PRECOND_JACOBI;
+  o->precond = PTFEM_PRECOND_AUTO;
   o->maxit = 200000;
-  o->check_every = 50;
+  o->check_every = 0;
   o->cheb_degree = 4;
   o->rtol = 1e-10;
   o->cheb_ratio = 30.0;
@@ -344,6 +354,8 @@ void ptfem_solve_opts_default(ptfem_solve_opts* o) {
   o->use_graph = 1;
   o->warm_start = 0;
   o->sample_spmv = 0;
+  o->coarse_nodes = 0;
+  o->coarse_levels = -1;
 }
 
 int ptfem_solve_device(ptfem_mesh* m, const ptfem_solve_opts* opts, ptfem_solve_stats* stats) {
@@ -352,14 +364,28 @@ int ptfem_solve_device(ptfem_mesh* m, const ptfem_solve_opts* opts, ptfem_solve_
   ptfem_solve_opts o;
   if (opts) o = *opts; else ptfem_solve_opts_default(&o);
   PT_ARG(o.rtol > 0.0 && o.maxit > 0, "rtol and maxit must be positive");
-  PT_ARG(o.precond == PTFEM_PRECOND_JACOBI || o.precond == PTFEM_PRECOND_CHEBYSHEV, "unknown preconditioner");
+  PT_ARG(o.precond >= PTFEM_PRECOND_AUTO && o.precond <= PTFEM_PRECOND_TWOLEVEL, "unknown preconditioner");
   PT_TRY(prepare_systems(m));
+  if (o.precond == PTFEM_PRECOND_AUTO)
+    o.precond = (m->nvalp == 1 && m->nn >= 100000) ? PTFEM_PRECOND_TWOLEVEL : PTFEM_PRECOND_JACOBI;
   LinSys A;
   make_linsys(m, A);
+  double setup_ms = 0.0;
+  if (o.precond == PTFEM_PRECOND_TWOLEVEL) {
+    const int64_t epoch_before = m->coarse ? m->coarse->matrix_epoch : -1;
+    PT_TRY(coarse_prepare(m, o.coarse_nodes, o.coarse_levels, m->S));
+    if (m->coarse->matrix_epoch != epoch_before) setup_ms = m->coarse->setup_ms;
+    A.coarse = m->coarse;
+  }
   m->J_sys = -1;
   if (!o.warm_start) PT_CK(cudaMemsetAsync(m->phi.p, 0, (size_t)m->nn * m->S * sizeof(double), m->ctx->stream));
   int rc = pcg_solve(m->ctx, A, m->work, o, m->phi.p, stats);
-  if (stats) stats->nsys = m->nsys_user;
+  if (stats) {
+    stats->nsys = m->nsys_user;
+    stats->setup_ms = setup_ms;
+    stats->precond = o.precond;
+    stats->coarse_unknowns = (o.precond == PTFEM_PRECOND_TWOLEVEL) ? (int32_t)m->coarse->lev[m->coarse->nlev - 1].k : 0;
+  }
   return rc;
 }
 

@@ -409,5 +409,6 @@ int ptfem_apply_bc(ptfem_mesh* m, double* dinv_out /*[nn][VS]*/, int* S_out) {
   PT_LAUNCH_CHECK(ctx);
   *S_out = S;
   m->bc_dirty = false;
+  m->matrix_epoch++;
   return PTFEM_OK;
 }

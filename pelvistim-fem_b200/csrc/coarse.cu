@@ -1,0 +1,858 @@
+// coarse.cu — geometric coarse spaces for the PCG preconditioner: grids, Galerkin operators, dense inverse,
+// restriction / coarse solve kernels.  See coarse.cuh for the operator; solver.cu adds Z y_c to z in its p-update.
+//
+// Everything is deterministic: restriction sums per coarse cell in a fixed order, a grid node then adds the
+// partials of its (up to) eight cells in a fixed order; the Galerkin matrix is built the same way.  The only
+// atomics are the shared-memory accumulations inside one CTA of the Galerkin build (their order changes the
+// preconditioner in the last bits, never the solution the iteration converges to) and the rarely taken slow path.
+#include <cub/cub.cuh>
+
+#include "coarse.cuh"
+
+namespace ptfem {
+namespace {
+
+constexpr int kGjNb = 32;     // pivot block of the Gauss-Jordan inverse
+constexpr int kGjTile = 64;   // update tile (kp is a multiple of it)
+
+// ---- grids ------------------------------------------------------------------------------------------------
+constexpr long long kDirBit = (long long)(1ull << 63);
+
+// table row = position of the mesh node in the coarsest grid (see CoarseSpace::ctab)
+__global__ void coarse_table_kernel(CoarseGrid g, const double* __restrict__ xyz, int64_t nn, double* __restrict__ ctab) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nn) return;
+  int c[3];
+  double t[3];
+  coarse_locate(g, xyz, i, c, t);
+  ctab[4 * i] = t[0];
+  ctab[4 * i + 1] = t[1];
+  ctab[4 * i + 2] = t[2];
+  ctab[4 * i + 3] = __longlong_as_double((long long)c[0] | ((long long)c[1] << 21) | ((long long)c[2] << 42));
+}
+// Dirichlet rows carry the sign bit: coarse_row() then reports them as outside every coarse space
+__global__ void coarse_table_flag_kernel(const uint8_t* __restrict__ isdir, int64_t nn, double* __restrict__ ctab) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nn) return;
+  const long long cell = __double_as_longlong(ctab[4 * i + 3]) & ~kDirBit;
+  ctab[4 * i + 3] = __longlong_as_double(isdir[i] ? (cell | kDirBit) : cell);
+}
+
+// (called before the Dirichlet flags are set: every row has a cell)
+__global__ void cell_key_kernel(int n0, int n1, int shift, const double* __restrict__ ctab, int64_t nn, int32_t* __restrict__ key,
+                                int32_t* __restrict__ id) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nn) return;
+  int c[3];
+  double t[3];
+  coarse_row(ctab, i, shift, c, t);
+  key[i] = c[0] + n0 * (c[1] + n1 * c[2]);
+  id[i] = (int32_t)i;
+}
+
+// cellptr[c] = first position of the sorted keys holding a key >= c
+__global__ void cell_ptr_kernel(const int32_t* __restrict__ key, int64_t nn, int64_t ncell, int32_t* __restrict__ cellptr) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > nn) return;
+  const int64_t hi = p < nn ? key[p] : ncell;
+  const int64_t lo = p == 0 ? -1 : key[p - 1];
+  for (int64_t c = lo + 1; c <= hi; ++c) cellptr[c] = (int32_t)p;
+}
+
+// ---- restriction: per-cell partials -------------------------------------------------------------------------
+// One warp per task = (cell, split index); lane = (row slot, system pair).  part[task][corner][s] = sum over the
+// task's rows of w_corner(row) r[row][s]: registers and shuffles only, fixed order, no atomics.
+template <int S>
+__global__ void __launch_bounds__(256) restrict_cell_kernel(int64_t ntask, int split, int shift, const int32_t* __restrict__ cellptr,
+                                                            const int32_t* __restrict__ rows, const double* __restrict__ ctab,
+                                                            const double* __restrict__ r, double* __restrict__ part) {
+  constexpr int NP = S >= 2 ? S / 2 : 1;  // lanes per row
+  constexpr int NV = S >= 2 ? 2 : 1;      // systems per lane
+  constexpr int RPW = 32 / NP;            // rows per warp trip
+  const int lane = threadIdx.x & 31;
+  const int pr = lane % NP, slot = lane / NP;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = warp0; w < ntask; w += nwarp) {
+    const int64_t c = w / split;
+    const int sp = (int)(w % split);
+    double acc[8][NV];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int v = 0; v < NV; ++v) acc[a][v] = 0.0;
+    const int32_t p1 = cellptr[c + 1];
+    for (int32_t p = cellptr[c] + sp * RPW + slot; p < p1; p += 2 * split * RPW) {
+      // two rows per trip so that both index -> value chains are in flight together
+      const int32_t pb = p + split * RPW;
+      const int32_t ia = __ldg(rows + p), ib = pb < p1 ? __ldg(rows + pb) : -1;
+      double va[NV], vb[NV];
+      if constexpr (NV == 2) {
+        const double2 x = __ldg(reinterpret_cast<const double2*>(r + (size_t)ia * S + 2 * pr));
+        va[0] = x.x;
+        va[1] = x.y;
+        const double2 y = ib >= 0 ? __ldg(reinterpret_cast<const double2*>(r + (size_t)ib * S + 2 * pr)) : make_double2(0.0, 0.0);
+        vb[0] = y.x;
+        vb[1] = y.y;
+      } else {
+        va[0] = __ldg(r + ia);
+        vb[0] = ib >= 0 ? __ldg(r + ib) : 0.0;
+      }
+      int cc[3];
+      double t[3], wgt[8];
+      if (coarse_row(ctab, ia, shift, cc, t)) {
+        coarse_weights(t, wgt);
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+          for (int v = 0; v < NV; ++v) acc[a][v] = fma(wgt[a], va[v], acc[a][v]);
+      }
+      if (ib >= 0 && coarse_row(ctab, ib, shift, cc, t)) {
+        coarse_weights(t, wgt);
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+          for (int v = 0; v < NV; ++v) acc[a][v] = fma(wgt[a], vb[v], acc[a][v]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+#pragma unroll
+        for (int o = NP; o < 32; o <<= 1) acc[a][v] += __shfl_xor_sync(0xffffffffu, acc[a][v], o);
+      }
+    if (slot == 0) {
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) part[((size_t)w * 8 + a) * S + NV * pr + v] = acc[a][v];
+    }
+  }
+}
+
+// last CTA of the grid (ticket) — same protocol as solver.cu
+__device__ __forceinline__ bool last_block(unsigned int* ticket) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicInc(ticket, gridDim.x - 1);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
+// CTA sum per system of one value per thread whose system is threadIdx.x % S; result -> dpart[blockIdx.x][S];
+// last CTA adds the CTAs up in order -> cdot[S]
+template <int S>
+__device__ __forceinline__ void dot_by_sys(double v, double* s_buf /*[blockDim]*/, double* __restrict__ dpart,
+                                           double* __restrict__ cdot, unsigned int* ticket) {
+  s_buf[threadIdx.x] = v;
+  __syncthreads();
+  if (threadIdx.x < S) {
+    double tot = 0.0;
+    for (int k = threadIdx.x; k < (int)blockDim.x; k += S) tot += s_buf[k];
+    dpart[(size_t)blockIdx.x * S + threadIdx.x] = tot;
+  }
+  if (last_block(ticket)) {
+    // thread t adds the partials of CTAs t/S, t/S + G, ... for system t % S; then G group sums in order
+    const int G = (int)blockDim.x / S, sys = threadIdx.x % S, g = threadIdx.x / S;
+    double tot = 0.0;
+    for (unsigned int b = g; b < gridDim.x; b += G) tot += __ldcg(dpart + (size_t)b * S + sys);
+    __syncthreads();
+    s_buf[threadIdx.x] = tot;
+    __syncthreads();
+    if (threadIdx.x < S) {
+      double t2 = 0.0;
+      for (int gg = 0; gg < G; ++gg) t2 += s_buf[gg * S + threadIdx.x];
+      cdot[threadIdx.x] = t2;
+    }
+  }
+}
+
+// grid node I gathers the partials of the cells around it (fixed order).  DIAG: y = r_c * binv, dot.
+template <int S, bool DIAG>
+__global__ void __launch_bounds__(256) coarse_node_kernel(CoarseGrid g, int64_t k, int split, const double* __restrict__ part,
+                                                          const double* __restrict__ binv, double* __restrict__ rc,
+                                                          double* __restrict__ yc, double* __restrict__ dpart,
+                                                          double* __restrict__ cdot, unsigned int* ticket) {
+  __shared__ double s_buf[256];
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t I = e / S;
+  const int s = (int)(e % S);
+  double v = 0.0, dot = 0.0;
+  if (I < k) {
+    const int nx1 = g.n[0] + 1, ny1 = g.n[1] + 1;
+    const int ix = (int)(I % nx1), iy = (int)((I / nx1) % ny1), iz = (int)(I / ((int64_t)nx1 * ny1));
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const int cx = ix - (a & 1), cy = iy - ((a >> 1) & 1), cz = iz - (a >> 2);
+      if (cx < 0 || cy < 0 || cz < 0 || cx >= g.n[0] || cy >= g.n[1] || cz >= g.n[2]) continue;
+      const int64_t c = cx + (int64_t)g.n[0] * (cy + (int64_t)g.n[1] * cz);
+      for (int sp = 0; sp < split; ++sp) v += __ldcg(part + (((size_t)c * split + sp) * 8 + a) * S + s);
+    }
+    rc[I * S + s] = v;
+    if (DIAG) {
+      const double y = v * __ldg(binv + I);
+      yc[I * S + s] = y;
+      dot = v * y;
+    }
+  }
+  if (DIAG) dot_by_sys<S>(dot, s_buf, dpart, cdot, ticket);
+}
+
+// ---- grid-to-grid transfers (nested grids, cells halve from level l to l-1) -------------------------------------
+// Trilinear interpolation from the coarser grid reproduces itself on the finer one, so Z_coarse = Z_fine P: the mesh
+// is touched once (finest level) and the other levels are reached through these small kernels.
+// r_c[I] = sum_f P[f][I] r_f[f] (27 fine nodes around 2I);  DIAG: y = binv r_c and the level's dot
+template <int S, bool DIAG>
+__global__ void __launch_bounds__(256) grid_restrict_kernel(CoarseGrid gc, int64_t k, const double* __restrict__ rf,
+                                                            const double* __restrict__ binv, double* __restrict__ rc,
+                                                            double* __restrict__ yc, double* __restrict__ dpart,
+                                                            double* __restrict__ cdot, unsigned int* ticket) {
+  __shared__ double s_buf[256];
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t I = e / S;
+  const int s = (int)(e % S);
+  double v = 0.0, dot = 0.0;
+  if (I < k) {
+    const int nx1 = gc.n[0] + 1, ny1 = gc.n[1] + 1;
+    const int ix = (int)(I % nx1), iy = (int)((I / nx1) % ny1), iz = (int)(I / ((int64_t)nx1 * ny1));
+    const int fx1 = 2 * gc.n[0] + 1, fy1 = 2 * gc.n[1] + 1, fz1 = 2 * gc.n[2] + 1;
+    for (int dz = -1; dz <= 1; ++dz) {
+      const int fz = 2 * iz + dz;
+      if (fz < 0 || fz >= fz1) continue;
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int fy = 2 * iy + dy;
+        if (fy < 0 || fy >= fy1) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int fx = 2 * ix + dx;
+          if (fx < 0 || fx >= fx1) continue;
+          const double w = (dx ? 0.5 : 1.0) * (dy ? 0.5 : 1.0) * (dz ? 0.5 : 1.0);
+          v = fma(w, __ldcg(rf + ((size_t)fx + (size_t)fx1 * (fy + (size_t)fy1 * fz)) * S + s), v);
+        }
+      }
+    }
+    rc[I * S + s] = v;
+    if (DIAG) {
+      const double y = v * __ldg(binv + I);
+      yc[I * S + s] = y;
+      dot = v * y;
+    }
+  }
+  if (DIAG) dot_by_sys<S>(dot, s_buf, dpart, cdot, ticket);
+}
+
+// yt_f[f] = y_f[f] + (P yt_c)[f]
+template <int S>
+__global__ void __launch_bounds__(256) grid_prolong_kernel(CoarseGrid gc, int64_t kf, const double* __restrict__ yf,
+                                                           const double* __restrict__ ytc, double* __restrict__ ytf) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t F = e / S;
+  const int s = (int)(e % S);
+  if (F >= kf) return;
+  const int fx1 = 2 * gc.n[0] + 1, fy1 = 2 * gc.n[1] + 1;
+  const int nx1 = gc.n[0] + 1, ny1 = gc.n[1] + 1;
+  const int fx = (int)(F % fx1), fy = (int)((F / fx1) % fy1), fz = (int)(F / ((int64_t)fx1 * fy1));
+  double v = yf[F * S + s];
+  for (int az = 0; az <= (fz & 1); ++az)
+    for (int ay = 0; ay <= (fy & 1); ++ay)
+      for (int ax = 0; ax <= (fx & 1); ++ax) {
+        const double w = ((fx & 1) ? 0.5 : 1.0) * ((fy & 1) ? 0.5 : 1.0) * ((fz & 1) ? 0.5 : 1.0);
+        const size_t c = (size_t)(fx / 2 + ax) + (size_t)nx1 * ((fy / 2 + ay) + (size_t)ny1 * (fz / 2 + az));
+        v = fma(w, __ldcg(ytc + c * S + s), v);
+      }
+  ytf[F * S + s] = v;
+}
+
+// exact level: y_c = B r_c (dense), dot r_c . y_c.  CTA = 4 rows of B; warp w takes the w-th eighth of the columns;
+// lane = (column within a group of 32/S, system), so the r_c loads of a warp are one contiguous 256-byte run.
+constexpr int kDenseRows = 4;
+template <int S>
+__global__ void __launch_bounds__(256) coarse_dense_kernel(int kp, const double* __restrict__ binv, const double* __restrict__ rc,
+                                                           double* __restrict__ yc, double* __restrict__ dpart,
+                                                           double* __restrict__ cdot, unsigned int* ticket) {
+  __shared__ double s_buf[256];
+  __shared__ double s_part[8][kDenseRows][S];
+  constexpr int JPW = 32 / S;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int jj = lane / S, s = lane % S;
+  const int I0 = blockIdx.x * kDenseRows;
+  const int chunk = kp / 8;  // kp is a multiple of 64
+  const int j0 = wid * chunk, j1 = j0 + chunk;
+  double acc[kDenseRows];
+#pragma unroll
+  for (int r = 0; r < kDenseRows; ++r) acc[r] = 0.0;
+#pragma unroll 4
+  for (int J = j0 + jj; J < j1; J += JPW) {
+    const double v = __ldcg(rc + (size_t)J * S + s);
+#pragma unroll
+    for (int r = 0; r < kDenseRows; ++r) acc[r] = fma(__ldg(binv + (size_t)(I0 + r) * kp + J), v, acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < kDenseRows; ++r) {
+#pragma unroll
+    for (int o = S; o < 32; o <<= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+  }
+  if (lane < S) {
+#pragma unroll
+    for (int r = 0; r < kDenseRows; ++r) s_part[wid][r][lane] = acc[r];
+  }
+  __syncthreads();
+  double dot = 0.0;
+  if (threadIdx.x < kDenseRows * S) {
+    const int r = threadIdx.x / S, ss = threadIdx.x % S;
+    double y = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) y += s_part[w][r][ss];
+    yc[(size_t)(I0 + r) * S + ss] = y;
+    dot = y * __ldcg(rc + (size_t)(I0 + r) * S + ss);
+  }
+  dot_by_sys<S>(dot, s_buf, dpart, cdot, ticket);
+}
+
+// ---- Galerkin operator of the exact level ----------------------------------------------------------------------
+// CTA per cell.  For the rows i of the cell: Y[i][slot] = sum_j K_ij w_j(slot), slot = position of the grid node in
+// the 4x4x4 block of nodes around the cell (columns in the 27 neighbouring cells); then the cell's 8 x 64 block
+// sum_i w_i(I) Y[i][slot].  Columns further away (mesh edge longer than a coarse cell) take the slow path.
+constexpr int kGalRows = 64;
+__global__ void __launch_bounds__(256) galerkin_cell_kernel(CoarseGrid g, const int32_t* __restrict__ cellptr,
+                                                            const int32_t* __restrict__ rows, const double* __restrict__ ctab,
+                                                            const int32_t* __restrict__ rowptr,
+                                                            const int32_t* __restrict__ col, const double* __restrict__ val,
+                                                            double* __restrict__ blockE /*[ncell][8][64]*/,
+                                                            double* __restrict__ E, int kp, int32_t* __restrict__ flag) {
+  __shared__ double Y[kGalRows][65];
+  __shared__ double W[kGalRows][8];
+  const int64_t c = blockIdx.x;
+  int cc[3];
+  cc[0] = (int)(c % g.n[0]);
+  cc[1] = (int)((c / g.n[0]) % g.n[1]);
+  cc[2] = (int)(c / ((int64_t)g.n[0] * g.n[1]));
+  double acc[2] = {0.0, 0.0};
+  const int rloc = threadIdx.x >> 2, l4 = threadIdx.x & 3;
+  const int32_t p0 = cellptr[c], p1 = cellptr[c + 1];
+  for (int32_t base = p0; base < p1; base += kGalRows) {
+    for (int k = threadIdx.x; k < kGalRows * 65; k += 256) (&Y[0][0])[k] = 0.0;
+    __syncthreads();
+    const int32_t p = base + rloc;
+    bool live = false;
+    int32_t i = 0;
+    double ti[3] = {0, 0, 0};
+    if (p < p1) {
+      i = rows[p];
+      int ci[3];
+      live = coarse_row(ctab, i, 0, ci, ti);
+    }
+    if (l4 == 0) {
+#pragma unroll
+      for (int a = 0; a < 8; ++a) W[rloc][a] = live ? coarse_weight(ti, a) : 0.0;
+    }
+    if (live) {
+      for (int32_t e = rowptr[i] + l4; e < rowptr[i + 1]; e += 4) {
+        const double v = val[e];
+        const int32_t j = col[e];
+        if (v == 0.0) continue;
+        int cj[3];
+        double tj[3];
+        if (!coarse_row(ctab, j, 0, cj, tj)) continue;
+        const int d0 = cj[0] - cc[0], d1 = cj[1] - cc[1], d2 = cj[2] - cc[2];
+        if (d0 >= -1 && d0 <= 1 && d1 >= -1 && d1 <= 1 && d2 >= -1 && d2 <= 1) {
+#pragma unroll
+          for (int a = 0; a < 8; ++a) {
+            const int slot = (d0 + (a & 1) + 1) + 4 * (d1 + ((a >> 1) & 1) + 1) + 16 * (d2 + (a >> 2) + 1);
+            atomicAdd(&Y[rloc][slot], v * coarse_weight(tj, a));
+          }
+        } else {
+          flag[1] = 1;
+          int ci[3] = {cc[0], cc[1], cc[2]};
+          for (int a = 0; a < 8; ++a) {
+            const double wi = coarse_weight(ti, a);
+            const int64_t I = coarse_node(g, ci, a);
+            for (int b = 0; b < 8; ++b) atomicAdd(E + (size_t)I * kp + coarse_node(g, cj, b), wi * v * coarse_weight(tj, b));
+          }
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int o = threadIdx.x + 256 * h, I = o >> 6, slot = o & 63;
+      double t = acc[h];
+      for (int rr = 0; rr < kGalRows; ++rr) t = fma(W[rr][I], Y[rr][slot], t);
+      acc[h] = t;
+    }
+    __syncthreads();
+  }
+  blockE[(size_t)c * 512 + threadIdx.x] = acc[0];
+  blockE[(size_t)c * 512 + 256 + threadIdx.x] = acc[1];
+}
+
+// E[I][J] += sum over the cells around I of their block entry for (I, J); padding / empty nodes -> identity
+__global__ void __launch_bounds__(256) galerkin_gather_kernel(CoarseGrid g, int64_t k, int kp, const double* __restrict__ blockE,
+                                                              double* __restrict__ E) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)kp * kp) return;
+  const int64_t I = e / kp, J = e % kp;
+  if (I >= k || J >= k) {
+    E[e] = I == J ? 1.0 : 0.0;
+    return;
+  }
+  const int nx1 = g.n[0] + 1, ny1 = g.n[1] + 1;
+  const int ix = (int)(I % nx1), iy = (int)((I / nx1) % ny1), iz = (int)(I / ((int64_t)nx1 * ny1));
+  const int jx = (int)(J % nx1), jy = (int)((J / nx1) % ny1), jz = (int)(J / ((int64_t)nx1 * ny1));
+  double v = E[e];
+  if (abs(jx - ix) <= 2 && abs(jy - iy) <= 2 && abs(jz - iz) <= 2) {
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const int cx = ix - (a & 1), cy = iy - ((a >> 1) & 1), cz = iz - (a >> 2);
+      if (cx < 0 || cy < 0 || cz < 0 || cx >= g.n[0] || cy >= g.n[1] || cz >= g.n[2]) continue;
+      const int sx = jx - cx + 1, sy = jy - cy + 1, sz = jz - cz + 1;
+      if (sx < 0 || sx > 3 || sy < 0 || sy > 3 || sz < 0 || sz > 3) continue;
+      const int64_t c = cx + (int64_t)g.n[0] * (cy + (int64_t)g.n[1] * cz);
+      v += blockE[(size_t)c * 512 + a * 64 + (sx + 4 * sy + 16 * sz)];
+    }
+  }
+  if (I == J && !(v > 0.0)) v = 1.0;  // grid node without a free mesh node in its support
+  E[e] = v;
+}
+
+// ---- Galerkin diagonal of a finer (BPX) level -----------------------------------------------------------------
+// diag_I = sum_i sum_j w_i(I) K_ij hat_I(x_j); CTA per cell, 4 lanes per row, per-cell partials [ncell][8]
+__global__ void __launch_bounds__(256) galerkin_diag_cell_kernel(int shift, int64_t ncell, const int32_t* __restrict__ cellptr,
+                                                                 const int32_t* __restrict__ rows, const double* __restrict__ ctab,
+                                                                 const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                                 const double* __restrict__ val, double* __restrict__ dpartc) {
+  __shared__ double s_red[8 * 256];
+  for (int64_t c = blockIdx.x; c < ncell; c += gridDim.x) {
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int32_t p1 = cellptr[c + 1];
+    for (int32_t p = cellptr[c] + (threadIdx.x >> 2); p < p1; p += 64) {
+      const int32_t i = rows[p];
+      int ci[3];
+      double ti[3];
+      if (!coarse_row(ctab, i, shift, ci, ti)) continue;
+      double h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int32_t e = rowptr[i] + (threadIdx.x & 3); e < rowptr[i + 1]; e += 4) {
+        const double v = val[e];
+        const int32_t j = col[e];
+        if (v == 0.0) continue;
+        int cj[3];
+        double u[3];
+        if (!coarse_row(ctab, j, shift, cj, u)) continue;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) u[d] += (double)cj[d];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          const double hx = 1.0 - fabs(u[0] - (double)(ci[0] + (a & 1)));
+          const double hy = 1.0 - fabs(u[1] - (double)(ci[1] + ((a >> 1) & 1)));
+          const double hz = 1.0 - fabs(u[2] - (double)(ci[2] + (a >> 2)));
+          if (hx > 0.0 && hy > 0.0 && hz > 0.0) h[a] = fma(v, hx * hy * hz, h[a]);
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 8; ++a) acc[a] = fma(coarse_weight(ti, a), h[a], acc[a]);
+    }
+#pragma unroll
+    for (int a = 0; a < 8; ++a) s_red[a * 256 + threadIdx.x] = acc[a];
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      double tot = 0.0;
+      for (int k = 0; k < 256; ++k) tot += s_red[threadIdx.x * 256 + k];
+      dpartc[(size_t)c * 8 + threadIdx.x] = tot;
+    }
+    __syncthreads();
+  }
+}
+__global__ void galerkin_diag_node_kernel(CoarseGrid g, int64_t k, const double* __restrict__ dpartc, double* __restrict__ binv) {
+  const int64_t I = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (I >= k) return;
+  const int nx1 = g.n[0] + 1, ny1 = g.n[1] + 1;
+  const int ix = (int)(I % nx1), iy = (int)((I / nx1) % ny1), iz = (int)(I / ((int64_t)nx1 * ny1));
+  double v = 0.0;
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int cx = ix - (a & 1), cy = iy - ((a >> 1) & 1), cz = iz - (a >> 2);
+    if (cx < 0 || cy < 0 || cz < 0 || cx >= g.n[0] || cy >= g.n[1] || cz >= g.n[2]) continue;
+    const int64_t c = cx + (int64_t)g.n[0] * (cy + (int64_t)g.n[1] * cz);
+    v += dpartc[(size_t)c * 8 + a];
+  }
+  binv[I] = v > 0.0 ? 1.0 / v : 0.0;
+}
+
+// ---- dense inverse: blocked Gauss-Jordan without pivoting (the matrix is SPD) ---------------------------------
+// step t: P = A[t,t]; R = P^-1 [A[t,:] with block column t replaced by I]; C = A[:,t];
+//         A[i,:] = A[i,:](block column t zeroed) - C[i] R  (i != t),  A[t,:] = R
+__global__ void __launch_bounds__(1024) gj_pivot_kernel(const double* __restrict__ A, int kp, int t, double* __restrict__ Pinv,
+                                                        int32_t* __restrict__ flag) {
+  __shared__ double P[kGjNb][kGjNb + 1], Q[kGjNb][kGjNb + 1];
+  const int r = threadIdx.x / kGjNb, c = threadIdx.x % kGjNb;
+  P[r][c] = A[(size_t)(t * kGjNb + r) * kp + t * kGjNb + c];
+  Q[r][c] = r == c ? 1.0 : 0.0;
+  __syncthreads();
+  for (int s = 0; s < kGjNb; ++s) {
+    const double piv = P[s][s], f = P[r][s];
+    if (threadIdx.x == 0 && !(piv > 0.0)) flag[0] = 1;
+    __syncthreads();
+    if (r == s) {
+      P[r][c] /= piv;
+      Q[r][c] /= piv;
+    }
+    __syncthreads();
+    if (r != s) {
+      P[r][c] -= f * P[s][c];
+      Q[r][c] -= f * Q[s][c];
+    }
+    __syncthreads();
+  }
+  Pinv[r * kGjNb + c] = Q[r][c];
+}
+
+__global__ void __launch_bounds__(256) gj_panel_kernel(const double* __restrict__ A, int kp, int t, const double* __restrict__ Pinv,
+                                                       double* __restrict__ Rbuf /*[nb][kp]*/, double* __restrict__ Cbuf /*[kp][nb]*/) {
+  __shared__ double Ps[kGjNb][kGjNb + 1];
+  __shared__ double As[kGjNb][kGjTile];
+  const int j0 = blockIdx.x * kGjTile;
+  for (int k = threadIdx.x; k < kGjNb * kGjNb; k += 256) Ps[k / kGjNb][k % kGjNb] = Pinv[k];
+  for (int k = threadIdx.x; k < kGjNb * kGjTile; k += 256) {
+    const int c = k / kGjTile, j = j0 + k % kGjTile;
+    const int jt = j - t * kGjNb;
+    As[c][k % kGjTile] = (jt >= 0 && jt < kGjNb) ? (jt == c ? 1.0 : 0.0) : A[(size_t)(t * kGjNb + c) * kp + j];
+  }
+  // column panel copy: rows j0 .. j0+63
+  for (int k = threadIdx.x; k < kGjTile * kGjNb; k += 256) {
+    const int i = j0 + k / kGjNb, c = k % kGjNb;
+    Cbuf[(size_t)i * kGjNb + c] = A[(size_t)i * kp + t * kGjNb + c];
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < kGjNb * kGjTile; k += 256) {
+    const int r = k / kGjTile, jj = k % kGjTile;
+    double acc = 0.0;
+#pragma unroll 8
+    for (int c = 0; c < kGjNb; ++c) acc = fma(Ps[r][c], As[c][jj], acc);
+    Rbuf[(size_t)r * kp + j0 + jj] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) gj_update_kernel(double* __restrict__ A, int kp, int t, const double* __restrict__ Rbuf,
+                                                        const double* __restrict__ Cbuf) {
+  __shared__ double Cs[kGjTile][kGjNb + 1];
+  __shared__ double Rs[kGjNb][kGjTile];
+  const int i0 = blockIdx.y * kGjTile, j0 = blockIdx.x * kGjTile;
+  for (int k = threadIdx.x; k < kGjTile * kGjNb; k += 256) Cs[k / kGjNb][k % kGjNb] = Cbuf[(size_t)(i0 + k / kGjNb) * kGjNb + k % kGjNb];
+  for (int k = threadIdx.x; k < kGjNb * kGjTile; k += 256) Rs[k / kGjTile][k % kGjTile] = Rbuf[(size_t)(k / kGjTile) * kp + j0 + k % kGjTile];
+  __syncthreads();
+  const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+#pragma unroll 4
+  for (int k = 0; k < kGjNb; ++k) {
+    double cv[4], rv[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) cv[a] = Cs[ty * 4 + a][k];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) rv[b] = Rs[k][tx * 4 + b];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = fma(cv[a], rv[b], acc[a][b]);
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int i = i0 + ty * 4 + a;
+    const int it = i - t * kGjNb;
+    const bool pivot_row = it >= 0 && it < kGjNb;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int jj = tx * 4 + b, j = j0 + jj;
+      const int jt = j - t * kGjNb;
+      double out;
+      if (pivot_row) {
+        out = Rs[it][jj];
+      } else {
+        const double old = (jt >= 0 && jt < kGjNb) ? 0.0 : A[(size_t)i * kp + j];
+        out = old - acc[a][b];
+      }
+      A[(size_t)i * kp + j] = out;
+    }
+  }
+}
+
+int dense_inverse(ptfem_ctx* ctx, double* A, int kp, int32_t* flag) {
+  DevBuf<double> Pinv, Rbuf, Cbuf;
+  PT_TRY(Pinv.alloc(kGjNb * kGjNb));
+  PT_TRY(Rbuf.alloc((size_t)kGjNb * kp));
+  PT_TRY(Cbuf.alloc((size_t)kp * kGjNb));
+  const int steps = kp / kGjNb, tiles = kp / kGjTile;
+  for (int t = 0; t < steps; ++t) {
+    gj_pivot_kernel<<<1, kGjNb * kGjNb, 0, ctx->stream>>>(A, kp, t, Pinv.p, flag);
+    PT_LAUNCH_CHECK(ctx);
+    gj_panel_kernel<<<tiles, 256, 0, ctx->stream>>>(A, kp, t, Pinv.p, Rbuf.p, Cbuf.p);
+    PT_LAUNCH_CHECK(ctx);
+    gj_update_kernel<<<dim3(tiles, tiles), 256, 0, ctx->stream>>>(A, kp, t, Rbuf.p, Cbuf.p);
+    PT_LAUNCH_CHECK(ctx);
+  }
+  PT_CK(cudaStreamSynchronize(ctx->stream));  // the scratch buffers go back to the allocator here
+  return PTFEM_OK;
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+int build_level_geometry(ptfem_mesh* m, CoarseLevel& L) {
+  ptfem_ctx* ctx = m->ctx;
+  const int64_t nn = m->nn;
+  L.ncell = (int64_t)L.g.n[0] * L.g.n[1] * L.g.n[2];
+  L.k = (int64_t)(L.g.n[0] + 1) * (L.g.n[1] + 1) * (L.g.n[2] + 1);
+  DevBuf<int32_t> key, key2, id;
+  PT_TRY(key.alloc(nn));
+  PT_TRY(key2.alloc(nn));
+  PT_TRY(id.alloc(nn));
+  PT_TRY(L.rows.alloc(nn));
+  PT_TRY(L.cellptr.alloc(L.ncell + 1));
+  cell_key_kernel<<<ceil_div(nn, 256), 256, 0, ctx->stream>>>(L.g.n[0], L.g.n[1], L.shift, m->coarse->ctab.p, nn, key.p, id.p);
+  PT_LAUNCH_CHECK(ctx);
+  int bits = 1;
+  while (((int64_t)1 << bits) < L.ncell) ++bits;
+  size_t tmp_bytes = 0;
+  PT_CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key.p, key2.p, id.p, L.rows.p, (int)nn, 0, bits, ctx->stream));
+  DevBuf<uint8_t> tmp;
+  PT_TRY(tmp.alloc(tmp_bytes));
+  PT_CK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key.p, key2.p, id.p, L.rows.p, (int)nn, 0, bits, ctx->stream));
+  ctx->launches += 2;
+  cell_ptr_kernel<<<ceil_div(nn + 1, 256), 256, 0, ctx->stream>>>(key2.p, nn, L.ncell, L.cellptr.p);
+  PT_LAUNCH_CHECK(ctx);
+  PT_CK(cudaStreamSynchronize(ctx->stream));
+  return PTFEM_OK;
+}
+
+void choose_grid(const ptfem_mesh* m, double target_nodes, CoarseGrid& g) {
+  double ext[3], vol = 1.0;
+  for (int d = 0; d < 3; ++d) {
+    ext[d] = m->bb_hi[d] - m->bb_lo[d];
+    if (!(ext[d] > 0.0)) ext[d] = 1.0;
+    vol *= ext[d];
+  }
+  // about `target_nodes` grid nodes with near-cubic cells, at least 2 cells per axis
+  double h = cbrt(vol / target_nodes);
+  for (int it = 0; it < 8; ++it) {
+    double nodes = 1.0;
+    for (int d = 0; d < 3; ++d) nodes *= std::max(2.0, std::round(ext[d] / h)) + 1.0;
+    h *= cbrt(nodes / target_nodes);
+  }
+  for (int d = 0; d < 3; ++d) {
+    g.n[d] = (int)std::max(2.0, std::round(ext[d] / h));
+    // the box is widened by a hair so that nodes on the upper faces fall inside the last cell
+    g.lo[d] = m->bb_lo[d];
+    g.inv_h[d] = (double)g.n[d] / (ext[d] * (1.0 + 1e-12));
+  }
+}
+
+template <int S>
+int apply_t(ptfem_ctx* ctx, CoarseSpace& cs, const double* r) {
+  // mesh -> finest grid
+  CoarseLevel& L0 = cs.lev[0];
+  {
+    const int64_t ntask = L0.ncell * L0.split;
+    const int grid = (int)std::min<int64_t>((ntask + 7) / 8, (int64_t)ctx->sm_count * 32);
+    restrict_cell_kernel<S><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab.p, r,
+                                                           L0.part.p);
+    PT_LAUNCH_CHECK(ctx);
+  }
+  for (int l = 0; l < cs.nlev; ++l) {
+    CoarseLevel& L = cs.lev[l];
+    double* cdot = cs.cdot.p + (size_t)l * 16;
+    const int ngrid = ceil_div(L.k * S, 256);
+    if (l == 0) {
+      if (L.exact)
+        coarse_node_kernel<S, false><<<ngrid, 256, 0, ctx->stream>>>(L.g, L.k, L.split, L.part.p, nullptr, L.rc.p, L.yc.p, cs.dpart.p,
+                                                                     cdot, cs.ticket.p);
+      else
+        coarse_node_kernel<S, true><<<ngrid, 256, 0, ctx->stream>>>(L.g, L.k, L.split, L.part.p, L.binv.p, L.rc.p, L.yc.p, cs.dpart.p,
+                                                                    cdot, cs.ticket.p);
+    } else {
+      if (L.exact)
+        grid_restrict_kernel<S, false><<<ngrid, 256, 0, ctx->stream>>>(L.g, L.k, cs.lev[l - 1].rc.p, nullptr, L.rc.p, L.yc.p,
+                                                                       cs.dpart.p, cdot, cs.ticket.p);
+      else
+        grid_restrict_kernel<S, true><<<ngrid, 256, 0, ctx->stream>>>(L.g, L.k, cs.lev[l - 1].rc.p, L.binv.p, L.rc.p, L.yc.p,
+                                                                      cs.dpart.p, cdot, cs.ticket.p);
+    }
+    PT_LAUNCH_CHECK(ctx);
+    if (L.exact) {
+      coarse_dense_kernel<S><<<L.kp / kDenseRows, 256, 0, ctx->stream>>>(L.kp, L.binv.p, L.rc.p, L.yc.p, cs.dpart.p, cdot,
+                                                                        cs.ticket.p);
+      PT_LAUNCH_CHECK(ctx);
+    }
+  }
+  // coarsest -> finest grid: yt_l = y_l + P yt_{l+1}
+  for (int l = cs.nlev - 2; l >= 0; --l) {
+    CoarseLevel& L = cs.lev[l];
+    const double* ytc = (l + 1 == cs.nlev - 1) ? cs.lev[l + 1].yc.p : cs.lev[l + 1].yt.p;
+    grid_prolong_kernel<S><<<ceil_div(L.k * S, 256), 256, 0, ctx->stream>>>(cs.lev[l + 1].g, L.k, L.yc.p, ytc, L.yt.p);
+    PT_LAUNCH_CHECK(ctx);
+  }
+  return PTFEM_OK;
+}
+
+}  // namespace
+
+int coarse_apply(ptfem_ctx* ctx, CoarseSpace& cs, int S, const double* r) {
+  switch (S) {
+    case 1: return apply_t<1>(ctx, cs, r);
+    case 2: return apply_t<2>(ctx, cs, r);
+    case 4: return apply_t<4>(ctx, cs, r);
+    case 8: return apply_t<8>(ctx, cs, r);
+    case 16: return apply_t<16>(ctx, cs, r);
+  }
+  return set_err(PTFEM_ERR_ARG, "unsupported system count %d", S);
+}
+
+CoarseDev coarse_dev(const CoarseSpace& cs) {
+  // the CG p-update interpolates from the finest grid only (it carries the sum of all levels)
+  CoarseDev d;
+  d.nx1 = cs.lev[0].g.n[0] + 1;
+  d.ny1 = cs.lev[0].g.n[1] + 1;
+  d.shift = cs.lev[0].shift;
+  d.y = cs.nlev > 1 ? cs.lev[0].yt.p : cs.lev[0].yc.p;
+  d.ctab = cs.ctab.p;
+  return d;
+}
+
+void coarse_free(CoarseSpace* cs) { delete cs; }
+
+int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
+  ptfem_ctx* ctx = m->ctx;
+  if (m->nvalp != 1) return set_err(PTFEM_ERR_ARG, "the two-level preconditioner needs one shared matrix (multi-RHS), not %d", m->nval);
+  if (!m->coarse) m->coarse = new CoarseSpace();
+  CoarseSpace& cs = *m->coarse;
+  if (target_nodes <= 0) target_nodes = 2000;
+  if (extra_levels > kMaxCoarseLevels - 1) extra_levels = kMaxCoarseLevels - 1;
+  cudaEvent_t e0, e1;
+  PT_CK(cudaEventCreate(&e0));
+  PT_CK(cudaEventCreate(&e1));
+  PT_CK(cudaEventRecord(e0, ctx->stream));
+  bool rebuilt = false;
+  if (!cs.geom_ok || cs.req_nodes != target_nodes || cs.req_levels != extra_levels) {
+    {  // extra_levels < 0: as many finer grids as keep >= 16 mesh nodes per finest cell; a request is honoured down to 8
+      CoarseGrid b0;
+      choose_grid(m, (double)target_nodes, b0);
+      const double cells = (double)b0.n[0] * b0.n[1] * b0.n[2];
+      const double min_rows = extra_levels < 0 ? 16.0 : 8.0;
+      cs.nlev = extra_levels < 0 ? kMaxCoarseLevels : extra_levels + 1;
+      while (cs.nlev > 1 && cells * pow(8.0, cs.nlev - 1) * min_rows > (double)m->nn) --cs.nlev;
+    }
+    CoarseGrid base;
+    choose_grid(m, (double)target_nodes, base);
+    PT_TRY(cs.ctab.alloc((size_t)m->nn * 4));
+    coarse_table_kernel<<<ceil_div(m->nn, 256), 256, 0, ctx->stream>>>(base, m->xyz.p, m->nn, cs.ctab.p);
+    PT_LAUNCH_CHECK(ctx);
+    for (int l = 0; l < cs.nlev; ++l) {
+      CoarseLevel& L = cs.lev[l];
+      L.shift = cs.nlev - 1 - l;
+      const int f = 1 << L.shift;
+      L.g = base;
+      for (int d = 0; d < 3; ++d) {
+        L.g.n[d] = base.n[d] * f;
+        L.g.inv_h[d] = base.inv_h[d] * f;
+      }
+      L.exact = (l == cs.nlev - 1);
+      PT_TRY(build_level_geometry(m, L));
+      L.kp = L.exact ? (int)((L.k + kGjTile - 1) / kGjTile) * kGjTile : 0;
+      // restriction tasks (one warp each) of at most ~96 rows
+      L.split = 1;
+      while (m->nn / (L.ncell * L.split) > 96 && L.split < 64) L.split *= 2;
+    }
+    cs.geom_ok = true;
+    cs.req_nodes = target_nodes;
+    cs.req_levels = extra_levels;
+    cs.matrix_epoch = -1;
+    cs.S = 0;
+    rebuilt = true;
+    cs.generation++;
+  }
+  if (cs.S != S) {
+    size_t maxgrid = 1;
+    for (int l = 0; l < cs.nlev; ++l) {
+      CoarseLevel& L = cs.lev[l];
+      const size_t kk = L.exact ? (size_t)L.kp : (size_t)L.k;
+      if (l == 0) PT_TRY(L.part.alloc((size_t)L.ncell * L.split * 8 * S));
+      if (l < cs.nlev - 1) PT_TRY(L.yt.alloc(kk * S));
+      PT_TRY(L.rc.alloc(kk * S));
+      PT_TRY(L.yc.alloc(kk * S));
+      PT_CK(cudaMemsetAsync(L.rc.p, 0, kk * S * sizeof(double), ctx->stream));
+      PT_CK(cudaMemsetAsync(L.yc.p, 0, kk * S * sizeof(double), ctx->stream));
+      maxgrid = std::max(maxgrid, (size_t)ceil_div(kk * S, 256) + 1);
+      maxgrid = std::max(maxgrid, (size_t)kk / kDenseRows + 1);
+    }
+    PT_TRY(cs.dpart.alloc(maxgrid * 16));
+    PT_TRY(cs.cdot.alloc((size_t)kMaxCoarseLevels * 16));
+    PT_CK(cudaMemsetAsync(cs.cdot.p, 0, (size_t)kMaxCoarseLevels * 16 * sizeof(double), ctx->stream));
+    if (!cs.ticket.p) {
+      PT_TRY(cs.ticket.alloc(4));
+      PT_CK(cudaMemsetAsync(cs.ticket.p, 0, 4 * sizeof(unsigned int), ctx->stream));
+    }
+    cs.S = S;
+    rebuilt = true;
+    cs.generation++;
+  }
+  if (cs.matrix_epoch != m->matrix_epoch) {
+    PT_TRY(cs.flag.alloc(2));
+    PT_CK(cudaMemsetAsync(cs.flag.p, 0, 2 * sizeof(int32_t), ctx->stream));
+    coarse_table_flag_kernel<<<ceil_div(m->nn, 256), 256, 0, ctx->stream>>>(m->isdir.p, m->nn, cs.ctab.p);
+    PT_LAUNCH_CHECK(ctx);
+    for (int l = 0; l < cs.nlev; ++l) {
+      CoarseLevel& L = cs.lev[l];
+      if (L.exact) {
+        const size_t n2 = (size_t)L.kp * L.kp;
+        const double* before = L.binv.p;
+        PT_TRY(L.binv.alloc(n2));
+        if (L.binv.p != before) cs.generation++;
+        PT_CK(cudaMemsetAsync(L.binv.p, 0, n2 * sizeof(double), ctx->stream));
+        DevBuf<double> blockE;
+        PT_TRY(blockE.alloc((size_t)L.ncell * 512));
+        galerkin_cell_kernel<<<(unsigned)L.ncell, 256, 0, ctx->stream>>>(L.g, L.cellptr.p, L.rows.p, cs.ctab.p,
+                                                                          m->rowptr.p, m->col.p, m->val_bc.p, blockE.p, L.binv.p,
+                                                                          L.kp, cs.flag.p);
+        PT_LAUNCH_CHECK(ctx);
+        galerkin_gather_kernel<<<ceil_div((int64_t)n2, 256), 256, 0, ctx->stream>>>(L.g, L.k, L.kp, blockE.p, L.binv.p);
+        PT_LAUNCH_CHECK(ctx);
+        PT_TRY(dense_inverse(ctx, L.binv.p, L.kp, cs.flag.p));
+      } else {
+        const double* before = L.binv.p;
+        PT_TRY(L.binv.alloc(L.k));
+        if (L.binv.p != before) cs.generation++;
+        DevBuf<double> dpartc;
+        PT_TRY(dpartc.alloc((size_t)L.ncell * 8));
+        const int grid = (int)std::min<int64_t>(L.ncell, (int64_t)ctx->sm_count * 16);
+        galerkin_diag_cell_kernel<<<grid, 256, 0, ctx->stream>>>(L.shift, L.ncell, L.cellptr.p, L.rows.p, cs.ctab.p,
+                                                                 m->rowptr.p, m->col.p, m->val_bc.p, dpartc.p);
+        PT_LAUNCH_CHECK(ctx);
+        galerkin_diag_node_kernel<<<ceil_div(L.k, 256), 256, 0, ctx->stream>>>(L.g, L.k, dpartc.p, L.binv.p);
+        PT_LAUNCH_CHECK(ctx);
+        PT_CK(cudaStreamSynchronize(ctx->stream));
+      }
+    }
+    int32_t hflag[2] = {0, 0};
+    PT_CK(cudaMemcpyAsync(hflag, cs.flag.p, sizeof hflag, cudaMemcpyDeviceToHost, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    if (hflag[0])
+      return set_err(PTFEM_ERR_STATE, "coarse Galerkin matrix is not positive definite (grid %dx%dx%d too fine for this mesh?)",
+                     cs.lev[cs.nlev - 1].g.n[0], cs.lev[cs.nlev - 1].g.n[1], cs.lev[cs.nlev - 1].g.n[2]);
+    cs.matrix_epoch = m->matrix_epoch;
+    rebuilt = true;
+  }
+  PT_CK(cudaEventRecord(e1, ctx->stream));
+  PT_CK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (rebuilt) cs.setup_ms = ms;
+  return PTFEM_OK;
+}
+
+}  // namespace ptfem

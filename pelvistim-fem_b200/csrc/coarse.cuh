@@ -1,0 +1,123 @@
+// coarse.cuh — geometric coarse spaces of the two-level / multilevel-additive PCG preconditioner (coarse.cu).
+//
+//   M^-1 r = D^-1 r + sum_l Z_l B_l Z_l^T r
+//
+// Z_l interpolates trilinearly from a regular grid laid over the mesh bounding box to the mesh nodes (rows of
+// Dirichlet nodes are zero).  The coarsest grid carries the exact Galerkin inverse B = (Z^T K Z)^-1 (dense, a few
+// thousand unknowns), the finer ones only the inverse diagonal of their Galerkin operator (BPX).  The reference
+// solves with a direct method (UMFPACK, step01_box/case.sif:41-42), so any SPD preconditioner gives the same
+// answer; this one cuts the Jacobi-PCG iteration count of the refined layered slab by about an order of magnitude.
+#pragma once
+#include "common.cuh"
+
+constexpr int kMaxCoarseLevels = 4;
+
+struct CoarseGrid {  // passed by value to kernels
+  int n[3];          // cells per axis
+  double lo[3], inv_h[3];
+};
+
+// what the CG kernels need to add the coarse correction to z (by value)
+struct CoarseDev {
+  int nx1 = 1, ny1 = 1;         // grid nodes per axis (x, y) of the finest level
+  int shift = 0;                // its cells are 2^shift smaller than the table's
+  const double* y = nullptr;    // [k_0][S] sum over the levels, on the finest grid
+  const double* ctab = nullptr; // [nn][4] see CoarseSpace::ctab
+};
+
+struct CoarseLevel {
+  CoarseGrid g;
+  int64_t k = 0, ncell = 0;   // grid nodes, cells
+  bool exact = false;
+  int kp = 0;                 // k padded to the tile of the dense inverse (exact level)
+  ptfem::DevBuf<int32_t> rows, cellptr;   // mesh rows sorted by cell, [ncell+1]
+  ptfem::DevBuf<double> binv;             // exact: [kp][kp] inverse; else [k] inverse diagonal
+  int split = 1;                          // CTAs sharing one cell in the restriction
+  int shift = 0;                          // cells are 2^shift smaller than the coarsest level's
+  ptfem::DevBuf<double> part;             // [ncell][split][8][S] restriction partials
+  ptfem::DevBuf<double> rc, yc;           // [kp or k][S]
+  ptfem::DevBuf<double> yt;               // [k][S] y of this level + interpolated coarser levels
+};
+
+struct CoarseSpace {
+  int nlev = 0;
+  CoarseLevel lev[kMaxCoarseLevels];
+  bool geom_ok = false;
+  int64_t matrix_epoch = -1;  // ptfem_mesh::matrix_epoch the Galerkin operators were built for
+  int64_t generation = 0;     // bumped whenever buffers or grids change (CUDA-graph key)
+  int S = 0;
+  int req_nodes = 0, req_levels = 0;
+  ptfem::DevBuf<double> cdot;             // [nlev][16] r_c . y_c per level and system
+  ptfem::DevBuf<double> dpart;            // per-CTA partials of those dots
+  ptfem::DevBuf<unsigned int> ticket;
+  // per mesh row: position in the coarsest grid {t_x, t_y, t_z, packed cell (21 bits per axis) or -1 for a
+  // Dirichlet row}; finer levels derive theirs by doubling.  Rebuilt with the matrix (Dirichlet flags live here).
+  ptfem::DevBuf<double> ctab;
+  ptfem::DevBuf<int32_t> flag;            // [0] non-positive pivot seen, [1] slow-path entries
+  double setup_ms = 0.0;
+};
+
+__device__ __forceinline__ void coarse_locate(const CoarseGrid& g, const double* __restrict__ xyz, int64_t i, int (&c)[3],
+                                              double (&t)[3]) {
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double u = (__ldg(xyz + 3 * i + d) - g.lo[d]) * g.inv_h[d];
+    int ci = (int)floor(u);
+    ci = ci < 0 ? 0 : (ci > g.n[d] - 1 ? g.n[d] - 1 : ci);
+    double tt = u - (double)ci;
+    t[d] = tt < 0.0 ? 0.0 : (tt > 1.0 ? 1.0 : tt);
+    c[d] = ci;
+  }
+}
+// table row -> cell and local coordinates on the level whose cells are 2^shift smaller; false for Dirichlet rows
+__device__ __forceinline__ bool coarse_row(const double* __restrict__ ctab, int64_t i, int shift, int (&c)[3], double (&t)[3]) {
+  const double2 a = __ldg(reinterpret_cast<const double2*>(ctab + 4 * i));
+  const double2 b = __ldg(reinterpret_cast<const double2*>(ctab + 4 * i + 2));
+  const long long cell = __double_as_longlong(b.y);
+  if (cell < 0) return false;
+  c[0] = (int)(cell & 0x1fffff);
+  c[1] = (int)((cell >> 21) & 0x1fffff);
+  c[2] = (int)(cell >> 42);
+  t[0] = a.x;
+  t[1] = a.y;
+  t[2] = b.x;
+  if (shift > 0) {
+    const int f = 1 << shift;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double u = t[d] * (double)f;
+      int k = (int)u;
+      k = k > f - 1 ? f - 1 : k;
+      t[d] = u - (double)k;
+      c[d] = c[d] * f + k;
+    }
+  }
+  return true;
+}
+// the eight trilinear weights from three subtractions and twelve products
+__device__ __forceinline__ void coarse_weights(const double (&t)[3], double (&w)[8]) {
+  const double x0 = 1.0 - t[0], y0 = 1.0 - t[1], z0 = 1.0 - t[2];
+  const double xy[4] = {x0 * y0, t[0] * y0, x0 * t[1], t[0] * t[1]};
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    w[a] = xy[a] * z0;
+    w[a + 4] = xy[a] * t[2];
+  }
+}
+__device__ __forceinline__ double coarse_weight(const double (&t)[3], int a) {
+  return ((a & 1) ? t[0] : 1.0 - t[0]) * ((a & 2) ? t[1] : 1.0 - t[1]) * ((a & 4) ? t[2] : 1.0 - t[2]);
+}
+__device__ __forceinline__ int64_t coarse_node(const CoarseGrid& g, const int (&c)[3], int a) {
+  return (int64_t)(c[0] + (a & 1)) + (int64_t)(g.n[0] + 1) * ((c[1] + ((a >> 1) & 1)) + (int64_t)(g.n[1] + 1) * (c[2] + (a >> 2)));
+}
+
+namespace ptfem {
+// (re)builds what is stale: grids + sorted row lists (mesh coordinates / requested size changed) and the Galerkin
+// operators (matrix changed).  target_nodes: unknowns of the exact level (0 = default); extra_levels: finer
+// diagonal-only levels (each halves the cell size).
+int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S);
+// y_c = B_l Z_l^T r for every level; leaves r_c.y_c per level/system in cs.cdot
+int coarse_apply(ptfem_ctx* ctx, CoarseSpace& cs, int S, const double* r);
+CoarseDev coarse_dev(const CoarseSpace& cs);
+void coarse_free(CoarseSpace* cs);
+}  // namespace ptfem

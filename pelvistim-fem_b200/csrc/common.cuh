@@ -88,6 +88,7 @@ static inline int ptfem_pad_nsys(int s) {
 }
 
 struct NcclApi;           // dist.cu
+struct CoarseSpace;       // coarse.cuh
 struct ptfem_dist_state;  // dist.cu
 
 struct ptfem_ctx {
@@ -128,6 +129,7 @@ struct PcgWork {
   int graph_variant = -1;
   int graph_precond = -1;
   int graph_cheb = 0;
+  int64_t graph_coarse = -1;
   int64_t graph_launches = 0;
   const void* graph_x = nullptr;
   const void* graph_val = nullptr;
@@ -185,6 +187,8 @@ struct ptfem_mesh {
   ptfem::DevBuf<double> b;        // [nn][S]      rhs after elimination
   ptfem::DevBuf<double> dinv;     // [nn][nvalp]  inverse diagonal of the eliminated matrix
   bool bc_dirty = true;
+  int64_t matrix_epoch = 0;       // bumped whenever val_bc is rewritten (coarse Galerkin operators follow it)
+  CoarseSpace* coarse = nullptr;  // geometric coarse spaces of the two-level preconditioner (coarse.cu)
   // solution / fields
   int S = 0;                      // systems of the last solve (padded)
   int nsys_user = 0;

@@ -807,6 +807,7 @@ int ptfem_dist_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* x_loca
   ptfem_solve_opts o;
   if (opts) o = *opts; else ptfem_solve_opts_default(&o);
   PT_ARG(o.rtol > 0.0 && o.maxit > 0, "rtol and maxit must be positive");
+  if (o.precond == PTFEM_PRECOND_AUTO) o.precond = PTFEM_PRECOND_JACOBI;
   if (o.precond != PTFEM_PRECOND_JACOBI) return set_err(PTFEM_ERR_ARG, "the row-partitioned solve supports the Jacobi preconditioner only");
   DistState& d = *m->dist;
   const int check = o.check_every > 0 ? o.check_every : 50;

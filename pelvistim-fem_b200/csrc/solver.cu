@@ -29,7 +29,7 @@ constexpr int kStreamCapMax = 4096;   // most staged non-zeros per tile (48 KB p
 constexpr int kStreamRowsDefault = 64;
 
 // scalar slots in PcgWork::scal, each [kMaxSys]
-enum { SC_ALPHA = 0, SC_BETA, SC_RHO, SC_RR, SC_PQ, SC_BN2, SC_LMAX, SC_COUNT };
+enum { SC_ALPHA = 0, SC_BETA, SC_RHO, SC_RR, SC_PQ, SC_BN2, SC_LMAX, SC_RHOL, SC_COUNT };
 static_assert(SC_PQ * kMaxSys == kScalPqOffset, "solver.cuh: kScalPqOffset out of sync");
 
 // L2 eviction policies: the matrix stream (val/col, read once per SpMV) is marked evict_first, the
@@ -560,7 +560,7 @@ template <int S, int VS, bool JAC>
 __global__ void __launch_bounds__(kThreads) cg_update_kernel(int64_t nn, const double* __restrict__ q,
                                                              const double* __restrict__ dinv, double* __restrict__ r,
                                                              double* __restrict__ partial, double* __restrict__ scal,
-                                                             unsigned int* __restrict__ ticket) {
+                                                             unsigned int* __restrict__ ticket, int coarse) {
   __shared__ double s_red[4 * kThreads];
   const FlatPairs<S> fp(nn);
   const double a0 = scal[SC_ALPHA * kMaxSys + fp.s0], a1 = scal[SC_ALPHA * kMaxSys + fp.s1];
@@ -614,10 +614,114 @@ __global__ void __launch_bounds__(kThreads) cg_update_kernel(int64_t nn, const d
       if (threadIdx.x >= S) {
         scal[SC_RR * kMaxSys + threadIdx.x - S] = tot;
       } else if (JAC) {
-        const double rho_old = scal[SC_RHO * kMaxSys + threadIdx.x];
-        scal[SC_RHO * kMaxSys + threadIdx.x] = tot;
-        scal[SC_BETA * kMaxSys + threadIdx.x] = rho_old > 0.0 ? tot / rho_old : 0.0;
+        if (coarse) {  // only the Jacobi part of r.z: rho_finalize_kernel adds the coarse levels and forms beta
+          scal[SC_RHOL * kMaxSys + threadIdx.x] = tot;
+        } else {
+          const double rho_old = scal[SC_RHO * kMaxSys + threadIdx.x];
+          scal[SC_RHO * kMaxSys + threadIdx.x] = tot;
+          scal[SC_BETA * kMaxSys + threadIdx.x] = rho_old > 0.0 ? tot / rho_old : 0.0;
+        }
       }
+    }
+  }
+}
+
+// two-level preconditioner: rho = r.D^-1 r + sum_l r_c.y_c ; beta = rho / rho_old
+__global__ void rho_finalize_kernel(double* __restrict__ scal, const double* __restrict__ cdot, int nlev, int S) {
+  const int s = threadIdx.x;
+  if (s >= S) return;
+  double rho = scal[SC_RHOL * kMaxSys + s];
+  for (int l = 0; l < nlev; ++l) rho += cdot[l * kMaxSys + s];
+  const double rho_old = scal[SC_RHO * kMaxSys + s];
+  scal[SC_RHO * kMaxSys + s] = rho;
+  scal[SC_BETA * kMaxSys + s] = rho_old > 0.0 ? rho / rho_old : 0.0;
+}
+
+// (Z y)[row i], systems s .. s+NS-1 (y = sum of all levels on the finest grid)
+template <int S, int NS>
+__device__ __forceinline__ void coarse_prolong(const CoarseDev& cd, int64_t i, int s, double (&out)[NS]) {
+#pragma unroll
+  for (int k = 0; k < NS; ++k) out[k] = 0.0;
+  int c[3];
+  double t[3], w[8];
+  if (!coarse_row(cd.ctab, i, cd.shift, c, t)) return;
+  coarse_weights(t, w);
+  const int64_t n0 = c[0] + (int64_t)cd.nx1 * (c[1] + (int64_t)cd.ny1 * c[2]);
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int64_t node = n0 + (a & 1) + (int64_t)cd.nx1 * (((a >> 1) & 1) + (int64_t)cd.ny1 * (a >> 2));
+    const double* y = cd.y + (size_t)node * S + s;
+    if constexpr (NS == 2) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(y));
+      out[0] = fma(w[a], v.x, out[0]);
+      out[1] = fma(w[a], v.y, out[1]);
+    } else {
+      out[0] = fma(w[a], __ldg(y), out[0]);
+    }
+  }
+}
+
+// p-update of the two-level preconditioner (one shared matrix): z = dinv r + Z y.  Two pairs per trip: the
+// table row -> grid node -> y chain of one pair overlaps the vector loads of the other.
+template <int S>
+__global__ void __launch_bounds__(kThreads) cg_pupdate_coarse_kernel(int64_t nn, const double* __restrict__ r,
+                                                                     const double* __restrict__ dinv, double* __restrict__ p,
+                                                                     double* __restrict__ x, const double* __restrict__ scal,
+                                                                     int first, CoarseDev cd) {
+  const FlatPairs<S> fp(nn);
+  const double b0 = first ? 0.0 : scal[SC_BETA * kMaxSys + fp.s0], b1 = first ? 0.0 : scal[SC_BETA * kMaxSys + fp.s1];
+  const double a0 = first ? 0.0 : scal[SC_ALPHA * kMaxSys + fp.s0], a1 = first ? 0.0 : scal[SC_ALPHA * kMaxSys + fp.s1];
+  for (int64_t j = fp.j0; j < fp.npairs; j += 2 * fp.stride) {
+    int64_t e[2] = {2 * j, 2 * (j + fp.stride)};
+    const bool on[2] = {true, j + fp.stride < fp.npairs};
+    double2 zv[2], d[2], pv[2], xv[2];
+    double cz[2][2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!on[u]) e[u] = e[0];
+      zv[u] = __ldg(reinterpret_cast<const double2*>(r + e[u]));
+      d[u] = pair_weight<S, 1>(dinv, e[u]);
+      if (!first) {
+        pv[u] = *reinterpret_cast<const double2*>(p + e[u]);
+        xv[u] = *reinterpret_cast<const double2*>(x + e[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if constexpr (S == 1) {
+        double c0[1], c1[1];
+        coarse_prolong<1, 1>(cd, e[u], 0, c0);
+        coarse_prolong<1, 1>(cd, e[u] + 1, 0, c1);
+        cz[u][0] = c0[0];
+        cz[u][1] = c1[0];
+      } else {
+        coarse_prolong<S, 2>(cd, e[u] / S, fp.s0, cz[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!on[u]) continue;
+      double2 z = make_double2(fma(zv[u].x, d[u].x, cz[u][0]), fma(zv[u].y, d[u].y, cz[u][1]));
+      if (!first) {
+        xv[u].x = fma(a0, pv[u].x, xv[u].x);
+        xv[u].y = fma(a1, pv[u].y, xv[u].y);
+        *reinterpret_cast<double2*>(x + e[u]) = xv[u];
+        z.x = fma(b0, pv[u].x, z.x);
+        z.y = fma(b1, pv[u].y, z.y);
+      }
+      *reinterpret_cast<double2*>(p + e[u]) = z;
+    }
+  }
+  if (fp.has_tail) {
+    const int64_t e = fp.tail;
+    double c0[1];
+    coarse_prolong<1, 1>(cd, e, 0, c0);
+    const double z = fma(r[e], __ldg(dinv + e), c0[0]);
+    if (first) {
+      p[e] = z;
+    } else {
+      x[e] = fma(a0, p[e], x[e]);
+      p[e] = fma(b0, p[e], z);
     }
   }
 }
@@ -1048,13 +1152,25 @@ int pcg_iteration(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int 
   PT_TRY((spmv_sv<S, VS>(ctx, A, variant, w.p.p, w.q.p, &w, true)));
   if (precond == PTFEM_PRECOND_JACOBI) {
     cg_update_kernel<S, VS, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.q.p, A.dinv, w.r.p, w.partial.p, w.scal.p,
-                                                                      w.ticket.p);
+                                                                      w.ticket.p, 0);
     PT_LAUNCH_CHECK(ctx);
     cg_pupdate_kernel<S, VS, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, nullptr, A.dinv, w.p.p, x, w.scal.p, 0);
     PT_LAUNCH_CHECK(ctx);
+  } else if (precond == PTFEM_PRECOND_TWOLEVEL) {
+    if constexpr (VS == 1) {
+      cg_update_kernel<S, 1, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.q.p, A.dinv, w.r.p, w.partial.p, w.scal.p,
+                                                                       w.ticket.p, 1);
+      PT_LAUNCH_CHECK(ctx);
+      PT_TRY(coarse_apply(ctx, *A.coarse, S, w.r.p));
+      rho_finalize_kernel<<<1, 32, 0, ctx->stream>>>(w.scal.p, A.coarse->cdot.p, A.coarse->nlev, S);
+      PT_LAUNCH_CHECK(ctx);
+      cg_pupdate_coarse_kernel<S><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
+                                                                      coarse_dev(*A.coarse));
+      PT_LAUNCH_CHECK(ctx);
+    }
   } else {
     cg_update_kernel<S, VS, false><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.q.p, A.dinv, w.r.p, w.partial.p, w.scal.p,
-                                                                       w.ticket.p);
+                                                                       w.ticket.p, 0);
     PT_LAUNCH_CHECK(ctx);
     PT_TRY((cheb_apply<S, VS>(ctx, A, w, variant, degree)));
     // rho_new = r.z, beta = rho_new/rho_old
@@ -1080,6 +1196,18 @@ int pcg_start(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int prec
     PT_LAUNCH_CHECK(ctx);
     cg_pupdate_kernel<S, VS, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, nullptr, A.dinv, w.p.p, x, w.scal.p, 1);
     PT_LAUNCH_CHECK(ctx);
+  } else if (precond == PTFEM_PRECOND_TWOLEVEL) {
+    if constexpr (VS == 1) {
+      dots_kernel<S, 1><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.r.p, A.dinv, w.partial.p, w.scal.p, SC_RHOL, SC_RR, 0,
+                                                            w.ticket.p);
+      PT_LAUNCH_CHECK(ctx);
+      PT_TRY(coarse_apply(ctx, *A.coarse, S, w.r.p));
+      rho_finalize_kernel<<<1, 32, 0, ctx->stream>>>(w.scal.p, A.coarse->cdot.p, A.coarse->nlev, S);
+      PT_LAUNCH_CHECK(ctx);
+      cg_pupdate_coarse_kernel<S><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 1,
+                                                                      coarse_dev(*A.coarse));
+      PT_LAUNCH_CHECK(ctx);
+    }
   } else {
     PT_TRY((cheb_apply<S, VS>(ctx, A, w, variant, degree)));
     dots_kernel<S, VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.z.p, nullptr, w.partial.p, w.scal.p, SC_RHO, SC_RR,
@@ -1097,9 +1225,11 @@ int pcg_solve_t(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_o
   const int precond = o.precond;
   const int degree = precond == PTFEM_PRECOND_CHEBYSHEV ? (o.cheb_degree > 0 ? o.cheb_degree : 4) : 0;
   const int grid = grid_for(ctx, (A.nn * A.S + 1) / 2, kThreads);
-  const int check = o.check_every > 0 ? o.check_every : 50;
+  const int check = o.check_every > 0 ? o.check_every : (precond == PTFEM_PRECOND_TWOLEVEL ? 10 : 50);
   double* h = ctx->h_pinned;  // >= SC_COUNT*kMaxSys doubles
   int spmv_calls = 0;
+  if (precond == PTFEM_PRECOND_TWOLEVEL && (VS != 1 || !A.coarse))
+    return set_err(PTFEM_ERR_STATE, "two-level preconditioner: coarse spaces not prepared (needs one shared matrix)");
 
   if (precond == PTFEM_PRECOND_CHEBYSHEV) {
     const size_t n = (size_t)A.nn * S;
@@ -1193,7 +1323,7 @@ int pcg_solve_t(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_o
       const bool use_graph = o.use_graph && n_it == check;
       if (use_graph) {
         if (!w.graph || w.graph_iters != check || w.graph_variant != variant || w.graph_precond != precond ||
-            w.graph_cheb != degree || w.graph_x != x || w.graph_val != A.val || w.graph_b != A.b || w.graph_dinv != A.dinv) {
+            w.graph_cheb != degree || w.graph_coarse != (A.coarse ? A.coarse->generation : -1) || w.graph_x != x || w.graph_val != A.val || w.graph_b != A.b || w.graph_dinv != A.dinv) {
           pcg_work_drop_graph(w);
           cudaGraph_t g = nullptr;
           PT_CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
@@ -1217,6 +1347,7 @@ int pcg_solve_t(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_o
           w.graph_variant = variant;
           w.graph_precond = precond;
           w.graph_cheb = degree;
+          w.graph_coarse = A.coarse ? A.coarse->generation : -1;
           w.graph_x = x;
           w.graph_val = A.val;
           w.graph_b = A.b;
@@ -1300,6 +1431,9 @@ int pcg_solve_t(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_o
     st->true_rel_residual = true_rel;
     st->solve_ms = ms;
     st->spmv_ms = spmv_ms;
+    st->setup_ms = 0.0;
+    st->precond = precond;
+    st->coarse_unknowns = 0;
   }
   if (!converged)
     return set_err(PTFEM_ERR_NOCONV, "PCG did not reach rtol=%g in %d iterations (rel. residual %.3e)", o.rtol, it, true_rel);

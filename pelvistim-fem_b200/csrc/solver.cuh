@@ -1,6 +1,7 @@
 // solver.cuh — internal interface of the SpMV / PCG layer (solver.cu).
 #pragma once
 #include "common.cuh"
+#include "coarse.cuh"
 
 // Arguments of the fused peer-memory gather of the streaming SpMV (see dist.cu).
 struct PeerGather {
@@ -33,6 +34,8 @@ struct LinSys {
   // through peer.halo[c - nloc] (a pointer into a neighbour GPU's vector) after the neighbours' ready flags
   // (peer.flags, local memory) have reached *peer.wait
   PeerGather peer;
+  // two-level preconditioner (PTFEM_PRECOND_TWOLEVEL): prepared coarse spaces + what their kernels read
+  CoarseSpace* coarse = nullptr;
   int64_t row0 = 0;              // the system is rows [row0, row0+nn) of the arrays (row-range SpMV)
 };
 

@@ -17,7 +17,7 @@ import numpy as np
 _LIB = None
 _LIB_PATH = Path(__file__).resolve().parent / "libptfem.so"
 
-PRECOND_JACOBI, PRECOND_CHEBYSHEV = 0, 1
+PRECOND_JACOBI, PRECOND_CHEBYSHEV, PRECOND_TWOLEVEL, PRECOND_AUTO = 0, 1, 2, -1
 RECOVER_L2, RECOVER_LUMPED, RECOVER_AVERAGE = 0, 1, 2
 SPMV_AUTO, SPMV_VECTOR, SPMV_STREAM, SPMV_STREAM1 = 0, 1, 2, 3
 ERR_NOCONV = -4
@@ -33,13 +33,15 @@ class PtfemError(RuntimeError):
 class SolveOpts(C.Structure):
     _fields_ = [("precond", C.c_int32), ("maxit", C.c_int32), ("check_every", C.c_int32),
                 ("cheb_degree", C.c_int32), ("rtol", C.c_double), ("cheb_ratio", C.c_double),
-                ("spmv_variant", C.c_int32), ("use_graph", C.c_int32), ("warm_start", C.c_int32), ("sample_spmv", C.c_int32)]
+                ("spmv_variant", C.c_int32), ("use_graph", C.c_int32), ("warm_start", C.c_int32), ("sample_spmv", C.c_int32),
+                ("coarse_nodes", C.c_int32), ("coarse_levels", C.c_int32)]
 
 
 class SolveStats(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("converged", C.c_int32), ("nsys", C.c_int32),
                 ("spmv_calls", C.c_int32), ("rel_residual", C.c_double), ("true_rel_residual", C.c_double),
-                ("solve_ms", C.c_double), ("spmv_ms", C.c_double)]
+                ("solve_ms", C.c_double), ("spmv_ms", C.c_double), ("setup_ms", C.c_double),
+                ("precond", C.c_int32), ("coarse_unknowns", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -262,6 +262,78 @@ def test_geometry_change_on_fixed_topology(gpu_ctx):
     dm.close()
 
 
+# -- coarse-grid preconditioner ---------------------------------------------------------------------------
+@pytest.mark.parametrize("levels", [0, 1, -1])
+@pytest.mark.parametrize("nrhs", [1, 2, 3, 8, 16])
+def test_twolevel_preconditioner_matches_oracle(gpu_ctx, nrhs, levels):
+    # same systems, same answers, fewer iterations: Jacobi + trilinear coarse grids (exact coarsest, BPX finer)
+    m = meshgen.synth_slab("S", interfaces_as_103=False)
+    dm = dm_for(gpu_ctx, m)
+    dm.assemble(SIGMA5).bc_reset(nrhs)
+    for k in range(nrhs):
+        dm.neumann(101, 10.0 + k, rhs=k)
+    dm.dirichlet(102, 0.0)
+    phi_j = dm.solve(precond=engine.PRECOND_JACOBI)
+    it_j = dm.last_stats["iterations"]
+    phi_t = dm.solve(precond=engine.PRECOND_TWOLEVEL, coarse_nodes=300, coarse_levels=levels)
+    st = dm.last_stats
+    assert st["converged"] == 1 and st["precond"] == engine.PRECOND_TWOLEVEL and 200 <= st["coarse_unknowns"] <= 450
+    assert st["iterations"] * 3 < it_j
+    ref = fo.solve_case(m, SIGMA5, [(102, 0.0)], [(101, 10.0)], recover=None)["phi"]
+    for k in range(nrhs):
+        assert rel(phi_t[k], ref * (10.0 + k) / 10.0) < TOL_PHI
+        assert rel(phi_t[k], phi_j[k]) < 1e-8
+    # second solve on the same matrix reuses the coarse operators
+    dm.solve(precond=engine.PRECOND_TWOLEVEL, coarse_nodes=300, coarse_levels=levels)
+    assert dm.last_stats["setup_ms"] == 0.0
+    dm.close()
+
+
+def test_twolevel_odd_rows_unstructured_and_moved_mesh(gpu_ctx):
+    # odd node count (tail element of the pair kernels), Delaunay mesh (cells with few or no nodes, long edges
+    # taking the slow path of the Galerkin build), then new coordinates (grids and tables are rebuilt)
+    m = meshgen.box_mesh(0.04, 0.04, 0.02, 14, 10, 6, jitter=0.2, seed=7, ids=(2, 1, 3))
+    assert m.nn % 2 == 1
+    ref = fo.solve_case(m, {1: 0.2}, [(2, 1.0), (1, 0.0)], [], recover=None)
+    res = engine.solve_case(gpu_ctx, m, {1: 0.2}, [(2, 1.0), (1, 0.0)], [], recover=None, precond=engine.PRECOND_TWOLEVEL,
+                            coarse_nodes=100, rtol=1e-12)
+    assert rel(res["phi"], ref["phi"]) < TOL_PHI
+    res["dmesh"].close()
+    md = meshgen.delaunay_box_mesh(6000, seed=4)
+    reg = np.where(md.nodes[md.tets].mean(axis=1)[:, 0] > 0.02, 2, 1).astype(np.int32)
+    md = meshgen.TetMesh(md.nodes, md.tets, reg, md.tris, md.bcid)
+    sig = {1: 0.3, 2: 0.002}
+    refd = fo.solve_case(md, sig, [(102, 0.0)], [(101, 4.0)], recover=None)
+    dm = dm_for(gpu_ctx, md)
+    dm.assemble(sig).bc_reset(1).neumann(101, 4.0).dirichlet(102, 0.0)
+    for nodes_c, lev in ((60, 0), (400, 0), (60, 2)):
+        phi = dm.solve(precond=engine.PRECOND_TWOLEVEL, coarse_nodes=nodes_c, coarse_levels=lev, rtol=1e-11)[0]
+        assert rel(phi, refd["phi"]) < TOL_PHI
+    it_t = dm.last_stats["iterations"]
+    dm.solve(precond=engine.PRECOND_JACOBI, rtol=1e-11)
+    assert it_t < dm.last_stats["iterations"]
+    nodes2 = md.nodes.copy()
+    nodes2[:, 2] *= 0.8
+    dm.set_coords(nodes2)
+    dm.assemble(sig).bc_reset(1).neumann(101, 4.0).dirichlet(102, 0.0)
+    phi = dm.solve(precond=engine.PRECOND_TWOLEVEL, coarse_nodes=400, rtol=1e-11)[0]
+    md2 = meshgen.TetMesh(nodes2, md.tets, md.region, md.tris, md.bcid)
+    assert rel(phi, fo.solve_case(md2, sig, [(102, 0.0)], [(101, 4.0)], recover=None)["phi"]) < TOL_PHI
+    dm.close()
+
+
+def test_twolevel_needs_shared_matrix_and_auto_choice(gpu_ctx):
+    m = meshgen.synth_slab("XS")
+    dm = dm_for(gpu_ctx, m)
+    sigs = [{**SIGMA5, 4: s, 5: s} for s in (5e-3, 0.5)]
+    dm.assemble(sigs).bc_reset(1).neumann(101, 15.975).dirichlet(102, 0.0)
+    with pytest.raises(engine.PtfemError):
+        dm.solve(precond=engine.PRECOND_TWOLEVEL)
+    dm.solve(precond=engine.PRECOND_AUTO)                       # batched matrices / small mesh -> Jacobi
+    assert dm.last_stats["precond"] == engine.PRECOND_JACOBI and dm.last_stats["converged"] == 1
+    dm.close()
+
+
 # -- metrics rows (A9-A11) ---------------------------------------------------------------------------------
 def _layered_case(gpu_ctx, coarse=True):
     import tempfile
