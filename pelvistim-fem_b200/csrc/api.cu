@@ -47,6 +47,55 @@ __global__ void transpose_out_kernel(const double* __restrict__ in, int64_t nn, 
   for (int s = 0; s < nsys; ++s) out[(int64_t)s * nn + i] = in[i * S + s];
 }
 
+// first out-of-range entry of an index array (position, or INT64_MAX) — mesh validation on the device
+__global__ void index_check_kernel(const int32_t* __restrict__ idx, int64_t n, int64_t nn, unsigned long long* __restrict__ first_bad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && (idx[i] < 0 || idx[i] >= nn)) atomicMin(first_bad, (unsigned long long)i);
+}
+// per-CTA bounding box partials [grid][6] (lo xyz, hi xyz); the host folds the few hundred partials
+__global__ void __launch_bounds__(256) bbox_kernel(const double* __restrict__ xyz, int64_t nn, double* __restrict__ part) {
+  __shared__ double s[6][256];
+  double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < nn; i += (int64_t)gridDim.x * 256)
+    for (int d = 0; d < 3; ++d) {
+      const double v = xyz[3 * i + d];
+      lo[d] = fmin(lo[d], v);
+      hi[d] = fmax(hi[d], v);
+    }
+  for (int d = 0; d < 3; ++d) {
+    s[d][threadIdx.x] = lo[d];
+    s[3 + d][threadIdx.x] = hi[d];
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double v = s[threadIdx.x][0];
+    for (int k = 1; k < 256; ++k) v = threadIdx.x < 3 ? fmin(v, s[threadIdx.x][k]) : fmax(v, s[threadIdx.x][k]);
+    part[(size_t)blockIdx.x * 6 + threadIdx.x] = v;
+  }
+}
+
+int device_bbox(ptfem_mesh* m) {
+  ptfem_ctx* ctx = m->ctx;
+  const int grid = std::min<int64_t>(ceil_div(m->nn, 256), 4 * ctx->sm_count);
+  DevBuf<double> part;
+  PT_TRY(part.alloc((size_t)grid * 6));
+  bbox_kernel<<<grid, 256, 0, ctx->stream>>>(m->xyz.p, m->nn, part.p);
+  PT_LAUNCH_CHECK(ctx);
+  std::vector<double> h((size_t)grid * 6);
+  PT_CK(cudaMemcpyAsync(h.data(), part.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  PT_CK(cudaStreamSynchronize(ctx->stream));
+  for (int d = 0; d < 3; ++d) {
+    m->bb_lo[d] = h[d];
+    m->bb_hi[d] = h[3 + d];
+  }
+  for (int b = 1; b < grid; ++b)
+    for (int d = 0; d < 3; ++d) {
+      m->bb_lo[d] = std::min(m->bb_lo[d], h[(size_t)b * 6 + d]);
+      m->bb_hi[d] = std::max(m->bb_hi[d], h[(size_t)b * 6 + 3 + d]);
+    }
+  return PTFEM_OK;
+}
+
 int make_linsys(ptfem_mesh* m, LinSys& A) {
   A.nn = m->nn;
   A.nnz = m->nnz;
@@ -176,23 +225,12 @@ int ptfem_mesh_create(ptfem_ctx* ctx, int64_t nn, const double* xyz, int64_t nt,
   PT_ARG(nn > 0 && nt >= 0 && nb >= 0, "negative or zero sizes");
   PT_ARG(xyz && (nt == 0 || (tets && region)) && (nb == 0 || (tris && bcid)), "null array");
   PT_ARG(nn < 2147483647LL && nt * 16 < 2147483647LL * 4, "mesh too large for 32-bit indexing");
-  for (int64_t i = 0; i < nt * 4; ++i)
-    if (tets[i] < 0 || tets[i] >= nn) return set_err(PTFEM_ERR_ARG, "tet %lld refers to node %d (nn = %lld)", (long long)(i / 4), tets[i], (long long)nn);
-  for (int64_t i = 0; i < nb * 3; ++i)
-    if (tris[i] < 0 || tris[i] >= nn) return set_err(PTFEM_ERR_ARG, "boundary triangle %lld refers to node %d", (long long)(i / 3), tris[i]);
   PT_CK(cudaSetDevice(ctx->device));
   ptfem_mesh* m = new ptfem_mesh();
   m->ctx = ctx;
   m->nn = nn;
   m->nt = nt;
   m->nb = nb;
-  for (int d = 0; d < 3; ++d) m->bb_lo[d] = m->bb_hi[d] = xyz[d];
-  for (int64_t i = 0; i < nn; ++i)
-    for (int d = 0; d < 3; ++d) {
-      const double v = xyz[i * 3 + d];
-      if (v < m->bb_lo[d]) m->bb_lo[d] = v;
-      if (v > m->bb_hi[d]) m->bb_hi[d] = v;
-    }
   int rc = PTFEM_OK;
   auto up = [&](auto& buf, const auto* src, size_t count) {
     if (rc) return;
@@ -207,6 +245,27 @@ int ptfem_mesh_create(ptfem_ctx* ctx, int64_t nn, const double* xyz, int64_t nt,
   up(m->tris, tris, (size_t)nb * 3);
   up(m->bcid, bcid, (size_t)nb);
   if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = set_err(PTFEM_ERR_CUDA, "mesh upload failed");
+  // validation and bounding box on the device (a host pass over 80 M indices cost more than the upload itself)
+  if (!rc) {
+    DevBuf<unsigned long long> bad;
+    rc = bad.alloc(2);
+    if (!rc && cudaMemsetAsync(bad.p, 0xff, 2 * sizeof(unsigned long long), ctx->stream) != cudaSuccess)
+      rc = set_err(PTFEM_ERR_CUDA, "mesh validation failed");
+    if (!rc) {
+      if (nt > 0) index_check_kernel<<<ceil_div(nt * 4, 256), 256, 0, ctx->stream>>>(m->tets.p, nt * 4, nn, bad.p);
+      if (nb > 0) index_check_kernel<<<ceil_div(nb * 3, 256), 256, 0, ctx->stream>>>(m->tris.p, nb * 3, nn, bad.p + 1);
+      ctx->launches += (nt > 0) + (nb > 0);
+      unsigned long long hb[2];
+      if (cudaMemcpyAsync(hb, bad.p, sizeof hb, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+          cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        rc = set_err(PTFEM_ERR_CUDA, "mesh validation failed: %s", cudaGetErrorString(cudaGetLastError()));
+      else if (hb[0] != ~0ull)
+        rc = set_err(PTFEM_ERR_ARG, "tet %llu refers to node %d (nn = %lld)", hb[0] / 4, tets[hb[0]], (long long)nn);
+      else if (hb[1] != ~0ull)
+        rc = set_err(PTFEM_ERR_ARG, "boundary triangle %llu refers to node %d", hb[1] / 3, tris[hb[1]]);
+    }
+  }
+  if (!rc) rc = device_bbox(m);
   if (rc) {
     delete m;
     return rc;
@@ -233,13 +292,7 @@ int ptfem_mesh_set_coords(ptfem_mesh* m, const double* xyz) {
   PT_CK(cudaSetDevice(m->ctx->device));
   PT_CK(cudaMemcpyAsync(m->xyz.p, xyz, (size_t)m->nn * 3 * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
   PT_CK(cudaStreamSynchronize(m->ctx->stream));
-  for (int d = 0; d < 3; ++d) m->bb_lo[d] = m->bb_hi[d] = xyz[d];
-  for (int64_t i = 0; i < m->nn; ++i)
-    for (int d = 0; d < 3; ++d) {
-      const double v = xyz[3 * i + d];
-      if (v < m->bb_lo[d]) m->bb_lo[d] = v;
-      if (v > m->bb_hi[d]) m->bb_hi[d] = v;
-    }
+  PT_TRY(device_bbox(m));
   if (m->coarse) m->coarse->geom_ok = false;
   m->has_geom = false;
   if (m->has_pattern) PT_TRY(ptfem_build_geometry(m));

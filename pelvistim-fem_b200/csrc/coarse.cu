@@ -179,11 +179,11 @@ __global__ void __launch_bounds__(256) coarse_node_kernel(CoarseGrid g, int64_t 
                                                           double* __restrict__ yc, double* __restrict__ dpart,
                                                           double* __restrict__ cdot, unsigned int* ticket) {
   __shared__ double s_buf[256];
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t I = e / S;
-  const int s = (int)(e % S);
-  double v = 0.0, dot = 0.0;
-  if (I < k) {
+  const int s = threadIdx.x % S;  // the stride is a multiple of S: a thread stays with one system
+  double dot = 0.0;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < k * S; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t I = e / S;
+    double v = 0.0;
     const int nx1 = g.n[0] + 1, ny1 = g.n[1] + 1;
     const int ix = (int)(I % nx1), iy = (int)((I / nx1) % ny1), iz = (int)(I / ((int64_t)nx1 * ny1));
 #pragma unroll
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(256) coarse_node_kernel(CoarseGrid g, int64_t 
     if (DIAG) {
       const double y = v * __ldg(binv + I);
       yc[I * S + s] = y;
-      dot = v * y;
+      dot = fma(v, y, dot);
     }
   }
   if (DIAG) dot_by_sys<S>(dot, s_buf, dpart, cdot, ticket);
@@ -213,11 +213,11 @@ __global__ void __launch_bounds__(256) grid_restrict_kernel(CoarseGrid gc, int64
                                                             double* __restrict__ yc, double* __restrict__ dpart,
                                                             double* __restrict__ cdot, unsigned int* ticket) {
   __shared__ double s_buf[256];
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t I = e / S;
-  const int s = (int)(e % S);
-  double v = 0.0, dot = 0.0;
-  if (I < k) {
+  const int s = threadIdx.x % S;
+  double dot = 0.0;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < k * S; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t I = e / S;
+    double v = 0.0;
     const int nx1 = gc.n[0] + 1, ny1 = gc.n[1] + 1;
     const int ix = (int)(I % nx1), iy = (int)((I / nx1) % ny1), iz = (int)(I / ((int64_t)nx1 * ny1));
     const int fx1 = 2 * gc.n[0] + 1, fy1 = 2 * gc.n[1] + 1, fz1 = 2 * gc.n[2] + 1;
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(256) grid_restrict_kernel(CoarseGrid gc, int64
     if (DIAG) {
       const double y = v * __ldg(binv + I);
       yc[I * S + s] = y;
-      dot = v * y;
+      dot = fma(v, y, dot);
     }
   }
   if (DIAG) dot_by_sys<S>(dot, s_buf, dpart, cdot, ticket);
@@ -665,7 +665,7 @@ int apply_t(ptfem_ctx* ctx, CoarseSpace& cs, const double* r) {
   for (int l = 0; l < cs.nlev; ++l) {
     CoarseLevel& L = cs.lev[l];
     double* cdot = cs.cdot.p + (size_t)l * 16;
-    const int ngrid = ceil_div(L.k * S, 256);
+    const int ngrid = std::min(ceil_div(L.k * S, 256), 4 * ctx->sm_count);
     if (l == 0) {
       if (L.exact)
         coarse_node_kernel<S, false><<<ngrid, 256, 0, ctx->stream>>>(L.g, L.k, L.split, L.part.p, nullptr, L.rc.p, L.yc.p, cs.dpart.p,

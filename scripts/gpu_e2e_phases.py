@@ -13,7 +13,7 @@ pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
 h = dict(nodes=pin(mesh.nodes), tets=pin(mesh.tets), region=pin(mesh.region), tris=pin(mesh.tris), bcid=pin(mesh.bcid))
 phi_out = torch.empty((8, mesh.nn), dtype=torch.float64).pin_memory().numpy()
 J_out = torch.empty((8, mesh.nn, 3), dtype=torch.float64).pin_memory().numpy()
-for rep in range(2):
+for rep in range(3):
     T = {}
     def tic(name, t0):
         ctx.sync(); T[name] = time.perf_counter() - t0; return time.perf_counter()
@@ -29,7 +29,7 @@ for rep in range(2):
     T["recover+d2h_J x8"] = 0.0; T["metrics x8"] = 0.0
     for k, c in enumerate(confs):
         t = time.perf_counter()
-        d.recover_current(k, "l2", to_host=True, out=J_out[k]); ctx.sync()
+        d.recover_current(k, bench.RECOVER, to_host=True, out=J_out[k]); ctx.sync()
         T["recover+d2h_J x8"] += time.perf_counter() - t; t = time.perf_counter()
         fp = (c["center"][0], c["center"][1], c["r"], False)
         d.metric_nodes(0, 0.0397, sys=k); d.metric_nodes(1, 0.04 - 1e-5, mode=1, footprints=[fp], sys=k)
