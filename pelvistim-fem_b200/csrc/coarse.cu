@@ -38,6 +38,17 @@ __global__ void coarse_table_flag_kernel(const uint8_t* __restrict__ isdir, int6
   ctab[4 * i + 3] = __longlong_as_double(isdir[i] ? (cell | kDirBit) : cell);
 }
 
+// table rows in the order of a row list
+__global__ void gather_table_kernel(const double* __restrict__ ctab, const int32_t* __restrict__ rows, int64_t nn,
+                                    double* __restrict__ out) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nn) return;
+  const int64_t i = rows[p];
+  const double2 a = *reinterpret_cast<const double2*>(ctab + 4 * i), b = *reinterpret_cast<const double2*>(ctab + 4 * i + 2);
+  *reinterpret_cast<double2*>(out + 4 * p) = a;
+  *reinterpret_cast<double2*>(out + 4 * p + 2) = b;
+}
+
 // (called before the Dirichlet flags are set: every row has a cell)
 __global__ void cell_key_kernel(int n0, int n1, int shift, const double* __restrict__ ctab, int64_t nn, int32_t* __restrict__ key,
                                 int32_t* __restrict__ id) {
@@ -62,9 +73,9 @@ __global__ void cell_ptr_kernel(const int32_t* __restrict__ key, int64_t nn, int
 // ---- restriction: per-cell partials -------------------------------------------------------------------------
 // One warp per task = (cell, split index); lane = (row slot, system pair).  part[task][corner][s] = sum over the
 // task's rows of w_corner(row) r[row][s]: registers and shuffles only, fixed order, no atomics.
-template <int S>
-__global__ void __launch_bounds__(256) restrict_cell_kernel(int64_t ntask, int split, int shift, const int32_t* __restrict__ cellptr,
-                                                            const int32_t* __restrict__ rows, const double* __restrict__ ctab,
+template <int S, bool OCC>
+__global__ void __launch_bounds__(256, OCC ? 4 : 2) restrict_cell_kernel(int64_t ntask, int split, int shift, const int32_t* __restrict__ cellptr,
+                                                            const int32_t* __restrict__ rows, const double* __restrict__ ctab0,
                                                             const double* __restrict__ r, double* __restrict__ part) {
   constexpr int NP = S >= 2 ? S / 2 : 1;  // lanes per row
   constexpr int NV = S >= 2 ? 2 : 1;      // systems per lane
@@ -85,6 +96,7 @@ __global__ void __launch_bounds__(256) restrict_cell_kernel(int64_t ntask, int s
       // two rows per trip so that both index -> value chains are in flight together
       const int32_t pb = p + split * RPW;
       const int32_t ia = __ldg(rows + p), ib = pb < p1 ? __ldg(rows + pb) : -1;
+      const CoarseRaw ra = coarse_row_load(ctab0, p), rb = coarse_row_load(ctab0, pb < p1 ? pb : p);
       double va[NV], vb[NV];
       if constexpr (NV == 2) {
         const double2 x = __ldg(reinterpret_cast<const double2*>(r + (size_t)ia * S + 2 * pr));
@@ -99,15 +111,21 @@ __global__ void __launch_bounds__(256) restrict_cell_kernel(int64_t ntask, int s
       }
       int cc[3];
       double t[3], wgt[8];
-      if (coarse_row(ctab, ia, shift, cc, t)) {
+      {
+        const double live = coarse_row_decode(ra, shift, cc, t) ? 1.0 : 0.0;
         coarse_weights(t, wgt);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) va[v] *= live;
 #pragma unroll
         for (int a = 0; a < 8; ++a)
 #pragma unroll
           for (int v = 0; v < NV; ++v) acc[a][v] = fma(wgt[a], va[v], acc[a][v]);
       }
-      if (ib >= 0 && coarse_row(ctab, ib, shift, cc, t)) {
+      if (ib >= 0) {
+        const double live = coarse_row_decode(rb, shift, cc, t) ? 1.0 : 0.0;
         coarse_weights(t, wgt);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) vb[v] *= live;
 #pragma unroll
         for (int a = 0; a < 8; ++a)
 #pragma unroll
@@ -658,8 +676,12 @@ int apply_t(ptfem_ctx* ctx, CoarseSpace& cs, const double* r) {
   {
     const int64_t ntask = L0.ncell * L0.split;
     const int grid = (int)std::min<int64_t>((ntask + 7) / 8, (int64_t)ctx->sm_count * 32);
-    restrict_cell_kernel<S><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab.p, r,
-                                                           L0.part.p);
+    if (ctx->tune_restrict_occ)
+      restrict_cell_kernel<S, true><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p, r,
+                                                                   L0.part.p);
+    else
+      restrict_cell_kernel<S, false><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p,
+                                                                    r, L0.part.p);
     PT_LAUNCH_CHECK(ctx);
   }
   for (int l = 0; l < cs.nlev; ++l) {
@@ -803,6 +825,9 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
     PT_TRY(cs.flag.alloc(2));
     PT_CK(cudaMemsetAsync(cs.flag.p, 0, 2 * sizeof(int32_t), ctx->stream));
     coarse_table_flag_kernel<<<ceil_div(m->nn, 256), 256, 0, ctx->stream>>>(m->isdir.p, m->nn, cs.ctab.p);
+    PT_LAUNCH_CHECK(ctx);
+    PT_TRY(cs.ctab0.alloc((size_t)m->nn * 4));
+    gather_table_kernel<<<ceil_div(m->nn, 256), 256, 0, ctx->stream>>>(cs.ctab.p, cs.lev[0].rows.p, m->nn, cs.ctab0.p);
     PT_LAUNCH_CHECK(ctx);
     for (int l = 0; l < cs.nlev; ++l) {
       CoarseLevel& L = cs.lev[l];

@@ -53,6 +53,7 @@ struct CoarseSpace {
   // per mesh row: position in the coarsest grid {t_x, t_y, t_z, packed cell (21 bits per axis) or -1 for a
   // Dirichlet row}; finer levels derive theirs by doubling.  Rebuilt with the matrix (Dirichlet flags live here).
   ptfem::DevBuf<double> ctab;
+  ptfem::DevBuf<double> ctab0;            // the same rows in the order of level 0's row list (restriction reads it in step with the list)
   ptfem::DevBuf<int32_t> flag;            // [0] non-positive pivot seen, [1] slow-path entries
   double setup_ms = 0.0;
 };
@@ -69,18 +70,28 @@ __device__ __forceinline__ void coarse_locate(const CoarseGrid& g, const double*
     c[d] = ci;
   }
 }
-// table row -> cell and local coordinates on the level whose cells are 2^shift smaller; false for Dirichlet rows
-__device__ __forceinline__ bool coarse_row(const double* __restrict__ ctab, int64_t i, int shift, int (&c)[3], double (&t)[3]) {
-  const double2 a = __ldg(reinterpret_cast<const double2*>(ctab + 4 * i));
-  const double2 b = __ldg(reinterpret_cast<const double2*>(ctab + 4 * i + 2));
-  const long long cell = __double_as_longlong(b.y);
-  if (cell < 0) return false;
+// table row -> cell and local coordinates on the level whose cells are 2^shift smaller; false for Dirichlet rows.
+// Split in load + decode so that callers can issue the loads of several rows before any of them is used; the decode
+// is branch-free (a Dirichlet row decodes to cell 0 and live = false).
+struct CoarseRaw {
+  double2 a, b;
+};
+__device__ __forceinline__ CoarseRaw coarse_row_load(const double* __restrict__ ctab, int64_t i) {
+  CoarseRaw r;
+  r.a = __ldg(reinterpret_cast<const double2*>(ctab + 4 * i));
+  r.b = __ldg(reinterpret_cast<const double2*>(ctab + 4 * i + 2));
+  return r;
+}
+__device__ __forceinline__ bool coarse_row_decode(const CoarseRaw& r, int shift, int (&c)[3], double (&t)[3]) {
+  long long cell = __double_as_longlong(r.b.y);
+  const bool live = cell >= 0;
+  cell = live ? cell : 0;
   c[0] = (int)(cell & 0x1fffff);
   c[1] = (int)((cell >> 21) & 0x1fffff);
   c[2] = (int)(cell >> 42);
-  t[0] = a.x;
-  t[1] = a.y;
-  t[2] = b.x;
+  t[0] = r.a.x;
+  t[1] = r.a.y;
+  t[2] = r.b.x;
   if (shift > 0) {
     const int f = 1 << shift;
 #pragma unroll
@@ -92,7 +103,10 @@ __device__ __forceinline__ bool coarse_row(const double* __restrict__ ctab, int6
       c[d] = c[d] * f + k;
     }
   }
-  return true;
+  return live;
+}
+__device__ __forceinline__ bool coarse_row(const double* __restrict__ ctab, int64_t i, int shift, int (&c)[3], double (&t)[3]) {
+  return coarse_row_decode(coarse_row_load(ctab, i), shift, c, t);
 }
 // the eight trilinear weights from three subtractions and twelve products
 __device__ __forceinline__ void coarse_weights(const double (&t)[3], double (&w)[8]) {

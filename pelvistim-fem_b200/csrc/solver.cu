@@ -637,69 +637,96 @@ __global__ void rho_finalize_kernel(double* __restrict__ scal, const double* __r
   scal[SC_BETA * kMaxSys + s] = rho_old > 0.0 ? rho / rho_old : 0.0;
 }
 
-// (Z y)[row i], systems s .. s+NS-1 (y = sum of all levels on the finest grid)
+// (Z y)[row], systems s .. s+NS-1 (y = sum of all levels on the finest grid); raw = the row's table entry
 template <int S, int NS>
-__device__ __forceinline__ void coarse_prolong(const CoarseDev& cd, int64_t i, int s, double (&out)[NS]) {
-#pragma unroll
-  for (int k = 0; k < NS; ++k) out[k] = 0.0;
+__device__ __forceinline__ void coarse_prolong(const CoarseDev& cd, const CoarseRaw& raw, int s, double (&out)[NS]) {
   int c[3];
   double t[3], w[8];
-  if (!coarse_row(cd.ctab, i, cd.shift, c, t)) return;
+  const double live = coarse_row_decode(raw, cd.shift, c, t) ? 1.0 : 0.0;
   coarse_weights(t, w);
   const int64_t n0 = c[0] + (int64_t)cd.nx1 * (c[1] + (int64_t)cd.ny1 * c[2]);
+  double acc[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) acc[k] = 0.0;
 #pragma unroll
   for (int a = 0; a < 8; ++a) {
     const int64_t node = n0 + (a & 1) + (int64_t)cd.nx1 * (((a >> 1) & 1) + (int64_t)cd.ny1 * (a >> 2));
     const double* y = cd.y + (size_t)node * S + s;
     if constexpr (NS == 2) {
       const double2 v = __ldg(reinterpret_cast<const double2*>(y));
-      out[0] = fma(w[a], v.x, out[0]);
-      out[1] = fma(w[a], v.y, out[1]);
+      acc[0] = fma(w[a], v.x, acc[0]);
+      acc[1] = fma(w[a], v.y, acc[1]);
     } else {
-      out[0] = fma(w[a], __ldg(y), out[0]);
+      acc[0] = fma(w[a], __ldg(y), acc[0]);
     }
   }
+#pragma unroll
+  for (int k = 0; k < NS; ++k) out[k] = acc[k] * live;
 }
 
-// p-update of the two-level preconditioner (one shared matrix): z = dinv r + Z y.  Two pairs per trip: the
-// table row -> grid node -> y chain of one pair overlaps the vector loads of the other.
-template <int S>
-__global__ void __launch_bounds__(kThreads) cg_pupdate_coarse_kernel(int64_t nn, const double* __restrict__ r,
-                                                                     const double* __restrict__ dinv, double* __restrict__ p,
-                                                                     double* __restrict__ x, const double* __restrict__ scal,
-                                                                     int first, CoarseDev cd) {
+// p-update of the two-level preconditioner (one shared matrix): z = dinv r + Z y.  NPT pairs per trip: all table
+// rows are loaded first, so the table -> grid node -> y chains of the pairs overlap each other and the vector loads.
+template <int S, int NPT>
+__global__ void __launch_bounds__(kThreads, NPT == 1 ? 3 : 2) cg_pupdate_coarse_kernel(int64_t nn, const double* __restrict__ r,
+                                                                                     const double* __restrict__ dinv,
+                                                                                     double* __restrict__ p, double* __restrict__ x,
+                                                                                     const double* __restrict__ scal, int first,
+                                                                                     CoarseDev cd) {
   const FlatPairs<S> fp(nn);
   const double b0 = first ? 0.0 : scal[SC_BETA * kMaxSys + fp.s0], b1 = first ? 0.0 : scal[SC_BETA * kMaxSys + fp.s1];
   const double a0 = first ? 0.0 : scal[SC_ALPHA * kMaxSys + fp.s0], a1 = first ? 0.0 : scal[SC_ALPHA * kMaxSys + fp.s1];
-  for (int64_t j = fp.j0; j < fp.npairs; j += 2 * fp.stride) {
-    int64_t e[2] = {2 * j, 2 * (j + fp.stride)};
-    const bool on[2] = {true, j + fp.stride < fp.npairs};
-    double2 zv[2], d[2], pv[2], xv[2];
-    double cz[2][2];
+  for (int64_t j = fp.j0; j < fp.npairs; j += NPT * fp.stride) {
+    int64_t e[NPT];
+    bool on[NPT];
+    double2 zv[NPT], d[NPT], pv[NPT], xv[NPT];
+    double cz[NPT][2];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (!on[u]) e[u] = e[0];
-      zv[u] = __ldg(reinterpret_cast<const double2*>(r + e[u]));
-      d[u] = pair_weight<S, 1>(dinv, e[u]);
-      if (!first) {
-        pv[u] = *reinterpret_cast<const double2*>(p + e[u]);
-        xv[u] = *reinterpret_cast<const double2*>(x + e[u]);
-      }
+    for (int u = 0; u < NPT; ++u) {
+      on[u] = j + u * fp.stride < fp.npairs;
+      e[u] = on[u] ? 2 * (j + u * fp.stride) : 2 * j;
     }
+    if constexpr (S == 1) {
+      CoarseRaw raw[2 * NPT];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if constexpr (S == 1) {
+      for (int u = 0; u < NPT; ++u) {
+        raw[2 * u] = coarse_row_load(cd.ctab, e[u]);
+        raw[2 * u + 1] = coarse_row_load(cd.ctab, e[u] + 1);
+      }
+#pragma unroll
+      for (int u = 0; u < NPT; ++u) {
+        zv[u] = __ldg(reinterpret_cast<const double2*>(r + e[u]));
+        d[u] = pair_weight<S, 1>(dinv, e[u]);
+        if (!first) {
+          pv[u] = *reinterpret_cast<const double2*>(p + e[u]);
+          xv[u] = *reinterpret_cast<const double2*>(x + e[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < NPT; ++u) {
         double c0[1], c1[1];
-        coarse_prolong<1, 1>(cd, e[u], 0, c0);
-        coarse_prolong<1, 1>(cd, e[u] + 1, 0, c1);
+        coarse_prolong<1, 1>(cd, raw[2 * u], 0, c0);
+        coarse_prolong<1, 1>(cd, raw[2 * u + 1], 0, c1);
         cz[u][0] = c0[0];
         cz[u][1] = c1[0];
-      } else {
-        coarse_prolong<S, 2>(cd, e[u] / S, fp.s0, cz[u]);
       }
+    } else {
+      CoarseRaw raw[NPT];
+#pragma unroll
+      for (int u = 0; u < NPT; ++u) raw[u] = coarse_row_load(cd.ctab, e[u] / S);
+#pragma unroll
+      for (int u = 0; u < NPT; ++u) {
+        zv[u] = __ldg(reinterpret_cast<const double2*>(r + e[u]));
+        d[u] = pair_weight<S, 1>(dinv, e[u]);
+        if (!first) {
+          pv[u] = *reinterpret_cast<const double2*>(p + e[u]);
+          xv[u] = *reinterpret_cast<const double2*>(x + e[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < NPT; ++u) coarse_prolong<S, 2>(cd, raw[u], fp.s0, cz[u]);
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < NPT; ++u) {
       if (!on[u]) continue;
       double2 z = make_double2(fma(zv[u].x, d[u].x, cz[u][0]), fma(zv[u].y, d[u].y, cz[u][1]));
       if (!first) {
@@ -715,7 +742,7 @@ __global__ void __launch_bounds__(kThreads) cg_pupdate_coarse_kernel(int64_t nn,
   if (fp.has_tail) {
     const int64_t e = fp.tail;
     double c0[1];
-    coarse_prolong<1, 1>(cd, e, 0, c0);
+    coarse_prolong<1, 1>(cd, coarse_row_load(cd.ctab, e), 0, c0);
     const double z = fma(r[e], __ldg(dinv + e), c0[0]);
     if (first) {
       p[e] = z;
@@ -1164,8 +1191,12 @@ int pcg_iteration(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int 
       PT_TRY(coarse_apply(ctx, *A.coarse, S, w.r.p));
       rho_finalize_kernel<<<1, 32, 0, ctx->stream>>>(w.scal.p, A.coarse->cdot.p, A.coarse->nlev, S);
       PT_LAUNCH_CHECK(ctx);
-      cg_pupdate_coarse_kernel<S><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
-                                                                      coarse_dev(*A.coarse));
+      if (ctx->tune_pup_pairs == 2)
+        cg_pupdate_coarse_kernel<S, 2><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
+                                                                           coarse_dev(*A.coarse));
+      else
+        cg_pupdate_coarse_kernel<S, 1><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
+                                                                           coarse_dev(*A.coarse));
       PT_LAUNCH_CHECK(ctx);
     }
   } else {
@@ -1204,8 +1235,8 @@ int pcg_start(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int prec
       PT_TRY(coarse_apply(ctx, *A.coarse, S, w.r.p));
       rho_finalize_kernel<<<1, 32, 0, ctx->stream>>>(w.scal.p, A.coarse->cdot.p, A.coarse->nlev, S);
       PT_LAUNCH_CHECK(ctx);
-      cg_pupdate_coarse_kernel<S><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 1,
-                                                                      coarse_dev(*A.coarse));
+      cg_pupdate_coarse_kernel<S, 1><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 1,
+                                                                         coarse_dev(*A.coarse));
       PT_LAUNCH_CHECK(ctx);
     }
   } else {

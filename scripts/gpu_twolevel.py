@@ -7,7 +7,7 @@ from pelvistim_fem_b200 import engine, meshgen
 import bench
 
 sizes = sys.argv[1].split(",") if len(sys.argv) > 1 else ["S", "M", "L"]
-variants = [dict(precond=0)] + [dict(precond=2, coarse_nodes=k) for k in (400, 700, 1000, 1500, 2000, 3000)]
+variants = [dict(precond=0), dict(precond=2), dict(precond=2, coarse_levels=0), dict(precond=2, coarse_levels=1), dict(precond=2, coarse_nodes=1000)]
 ctx = engine.Context(0)
 for size in sizes:
     mesh = meshgen.synth_slab(size, contact_enabled=False)
