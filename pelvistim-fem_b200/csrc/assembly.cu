@@ -14,8 +14,25 @@ namespace {
 
 // K2: per tet |V| and G[ij] = |V| gradNi.gradNj (10 unique)
 __global__ void geom_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ tets, int64_t nt,
-                            double* __restrict__ G, double* __restrict__ vol, int32_t* __restrict__ nbad) {
+                            double* __restrict__ G, double* __restrict__ vol, int32_t* __restrict__ nbad,
+                            unsigned long long* __restrict__ hmax2) {
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // longest edge of the mesh (squared, as ordered bits of a non-negative double): bounds how far a node can be
+  // from the centroid of a cell that uses it (lazy smoothing of the ROI metric)
+  double l2 = 0.0;
+  if (e < nt) {
+    const int32_t* t = tets + e * 4;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = a + 1; b < 4; ++b) {
+        const double dx = xyz[3 * (int64_t)t[a]] - xyz[3 * (int64_t)t[b]], dy = xyz[3 * (int64_t)t[a] + 1] - xyz[3 * (int64_t)t[b] + 1],
+                     dz = xyz[3 * (int64_t)t[a] + 2] - xyz[3 * (int64_t)t[b] + 2];
+        l2 = fmax(l2, dx * dx + dy * dy + dz * dz);
+      }
+  }
+  l2 = warp_max(l2);
+  if ((threadIdx.x & 31) == 0 && l2 > 0.0) atomicMax(hmax2, (unsigned long long)__double_as_longlong(l2));
   if (e >= nt) return;
   double g[4][3];
   const double v = fabs(tet_grads(xyz, tets + e * 4, g));
@@ -235,8 +252,11 @@ int ptfem_build_geometry(ptfem_mesh* m) {
   DevBuf<int32_t> nbad;
   PT_TRY(nbad.alloc(1));
   PT_TRY(fill_i32(ctx, nbad.p, 0, 1));
+  DevBuf<unsigned long long> hmax2;
+  PT_TRY(hmax2.alloc(1));
+  PT_CK(cudaMemsetAsync(hmax2.p, 0, sizeof(unsigned long long), ctx->stream));
   if (m->nt > 0) {
-    geom_kernel<<<ceil_div(m->nt, 128), 128, 0, ctx->stream>>>(m->xyz.p, m->tets.p, m->nt, m->G.p, m->vol.p, nbad.p);
+    geom_kernel<<<ceil_div(m->nt, 128), 128, 0, ctx->stream>>>(m->xyz.p, m->tets.p, m->nt, m->G.p, m->vol.p, nbad.p, hmax2.p);
     PT_LAUNCH_CHECK(ctx);
   }
   if (m->nb > 0) {
@@ -247,8 +267,15 @@ int ptfem_build_geometry(ptfem_mesh* m) {
                                                                    m->valence.p);
   PT_LAUNCH_CHECK(ctx);
   int32_t bad = 0;
+  unsigned long long hbits = 0;
   PT_CK(cudaMemcpyAsync(&bad, nbad.p, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+  PT_CK(cudaMemcpyAsync(&hbits, hmax2.p, sizeof hbits, cudaMemcpyDeviceToHost, ctx->stream));
   PT_CK(cudaStreamSynchronize(ctx->stream));
+  {
+    double l2;
+    memcpy(&l2, &hbits, sizeof l2);
+    m->h_max = sqrt(l2);
+  }
   if (bad > 0) return set_err(PTFEM_ERR_ARG, "mesh has %d degenerate (zero-volume) tetrahedra", bad);
   m->has_geom = true;
   m->mval.release();

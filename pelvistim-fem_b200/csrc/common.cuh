@@ -165,6 +165,7 @@ struct ptfem_mesh {
   int32_t stream_rows = 0;        // rows per tile of the streaming SpMV (0 = not usable on this pattern)
   int32_t stream_cap = 0;         // staged entries per tile
   int32_t max_row = 0;            // longest row of the pattern
+  double h_max = 0.0;             // longest tet edge
   // geometry factors
   bool has_geom = false;
   ptfem::DevBuf<double> G;        // [nt][10]  |V| gradNi.gradNj (i<=j)

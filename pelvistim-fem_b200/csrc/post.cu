@@ -200,9 +200,14 @@ __global__ void smooth_phi_kernel(const int32_t* __restrict__ n2t_ptr, const int
                                   const int32_t* __restrict__ n2b_ptr, const int32_t* __restrict__ n2b,
                                   const int32_t* __restrict__ tets, const int32_t* __restrict__ tris,
                                   const double* __restrict__ phi, int S, int sys, int include_tris, int64_t nn,
+                                  const double* __restrict__ xyz, double cx, double cy, double cz, double rad,
                                   double* __restrict__ phis) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nn) return;
+  {  // only nodes that a cell inside the ROI can use are needed (rad = largest ROI radius + longest edge)
+    const double dx = xyz[3 * i] - cx, dy = xyz[3 * i + 1] - cy, dz = xyz[3 * i + 2] - cz;
+    if (dx * dx + dy * dy + dz * dz > rad * rad) return;
+  }
   double acc = 0.0;
   int cnt = 0;
   for (int32_t k = n2t_ptr[i]; k < n2t_ptr[i + 1]; ++k) {
@@ -246,16 +251,20 @@ __global__ void __launch_bounds__(kT) roi_kernel(const double* __restrict__ xyz,
     if (c < nt) {
       const int32_t* t = tets + c * 4;
       cx = cy = cz = 0.0;
-      double jx = 0.0, jy = 0.0, jz = 0.0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int64_t n = t[k];
         cx += xyz[n * 3]; cy += xyz[n * 3 + 1]; cz += xyz[n * 3 + 2];
-        jx += Jn[n * 3]; jy += Jn[n * 3 + 1]; jz += Jn[n * 3 + 2];
       }
       cx *= 0.25; cy *= 0.25; cz *= 0.25;
       const double dx = cx - a.cen[0], dy = cy - a.cen[1], dz = cz - a.cen[2];
       if (!(sqrt(dx * dx + dy * dy + dz * dz) < a.r[a.nmult - 1])) continue;
+      double jx = 0.0, jy = 0.0, jz = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int64_t n = t[k];
+        jx += Jn[n * 3]; jy += Jn[n * 3 + 1]; jz += Jn[n * 3 + 2];
+      }
       jx *= 0.25; jy *= 0.25; jz *= 0.25;
       jm = sqrt(jx * jx + jy * jy + jz * jz);
       double g[4][3];
@@ -607,7 +616,8 @@ int ptfem_do_metric_roi(ptfem_mesh* m, int sys, const double cen[3], double r0, 
   PT_TRY(m->phis.alloc(m->nn));
   smooth_phi_kernel<<<ceil_div(m->nn, 128), 128, 0, ctx->stream>>>(m->n2t_ptr.p, m->n2t.p, m->n2b_ptr.p, m->n2b.p, m->tets.p,
                                                                     m->tris.p, m->phi.p, m->S, sys, include_tris, m->nn,
-                                                                    m->phis.p);
+                                                                    m->xyz.p, cen[0], cen[1], cen[2],
+                                                                    r0 * mult[nmult - 1] + 1.01 * m->h_max, m->phis.p);
   PT_LAUNCH_CHECK(ctx);
   RoiArgs a;
   for (int k = 0; k < 3; ++k) a.cen[k] = cen[k];
