@@ -107,7 +107,6 @@ struct ptfem_ctx {
   int tune_morton = -1;            // streaming SpMV walks rows along a Morton curve: -1 auto, 0 off, 1 on (PTFEM_MORTON)
   int tune_p2p_fused = 0;          // row-partitioned solve: SpMV loads halo entries from peer memory itself (PTFEM_P2P_FUSED)
   int tune_xprefetch = 0;          // streaming SpMV prefetches the leading edge of x into L2 (PTFEM_XPREFETCH)
-  int tune_pup_pairs = 1;          // pairs per trip of the coarse p-update kernel (PTFEM_PUP_PAIRS: 1, 2)
   int tune_restrict_occ = 1;       // PTFEM_RESTRICT_OCC: 1 = register-capped restriction kernel (4 CTAs/SM, measured 7% faster solve), 0 = uncapped
   int tune_ctas_per_sm = 0;        // cap on resident CTAs per SM of the streaming SpMV (PTFEM_CTAS_PER_SM)
   std::unordered_map<const void*, size_t> func_smem;  // dynamic shared memory limit raised per kernel

@@ -664,80 +664,57 @@ __device__ __forceinline__ void coarse_prolong(const CoarseDev& cd, const Coarse
   for (int k = 0; k < NS; ++k) out[k] = acc[k] * live;
 }
 
-// p-update of the two-level preconditioner (one shared matrix): z = dinv r + Z y.  NPT pairs per trip: all table
-// rows are loaded first, so the table -> grid node -> y chains of the pairs overlap each other and the vector loads.
-template <int S, int NPT>
-__global__ void __launch_bounds__(kThreads, NPT == 1 ? 3 : 2) cg_pupdate_coarse_kernel(int64_t nn, const double* __restrict__ r,
-                                                                                     const double* __restrict__ dinv,
-                                                                                     double* __restrict__ p, double* __restrict__ x,
-                                                                                     const double* __restrict__ scal, int first,
-                                                                                     CoarseDev cd) {
+// p-update of the two-level preconditioner (one shared matrix): z = dinv r + Z y.  The table entry of the next trip is
+// loaded one trip ahead: the table -> grid node -> y chain is two dependent loads deep and ncu shows the kernel
+// waiting on exactly that chain (long-scoreboard stalls on the first use of the table entry).
+template <int S>
+__global__ void __launch_bounds__(kThreads, 3) cg_pupdate_coarse_kernel(int64_t nn, const double* __restrict__ r,
+                                                                        const double* __restrict__ dinv, double* __restrict__ p,
+                                                                        double* __restrict__ x, const double* __restrict__ scal,
+                                                                        int first, CoarseDev cd) {
   const FlatPairs<S> fp(nn);
   const double b0 = first ? 0.0 : scal[SC_BETA * kMaxSys + fp.s0], b1 = first ? 0.0 : scal[SC_BETA * kMaxSys + fp.s1];
   const double a0 = first ? 0.0 : scal[SC_ALPHA * kMaxSys + fp.s0], a1 = first ? 0.0 : scal[SC_ALPHA * kMaxSys + fp.s1];
-  for (int64_t j = fp.j0; j < fp.npairs; j += NPT * fp.stride) {
-    int64_t e[NPT];
-    bool on[NPT];
-    double2 zv[NPT], d[NPT], pv[NPT], xv[NPT];
-    double cz[NPT][2];
+  constexpr int NR = S == 1 ? 2 : 1;  // mesh rows per pair
+  CoarseRaw raw[NR], nxt[NR];
+  if (fp.j0 < fp.npairs) {
 #pragma unroll
-    for (int u = 0; u < NPT; ++u) {
-      on[u] = j + u * fp.stride < fp.npairs;
-      e[u] = on[u] ? 2 * (j + u * fp.stride) : 2 * j;
+    for (int k = 0; k < NR; ++k) raw[k] = coarse_row_load(cd.ctab, S == 1 ? 2 * fp.j0 + k : (2 * fp.j0) / S);
+  }
+  for (int64_t j = fp.j0; j < fp.npairs; j += fp.stride) {
+    const int64_t e = 2 * j;
+    const int64_t jn = j + fp.stride < fp.npairs ? j + fp.stride : j;
+#pragma unroll
+    for (int k = 0; k < NR; ++k) nxt[k] = coarse_row_load(cd.ctab, S == 1 ? 2 * jn + k : (2 * jn) / S);
+    double2 zv = __ldg(reinterpret_cast<const double2*>(r + e));
+    const double2 d = pair_weight<S, 1>(dinv, e);
+    double2 pv = make_double2(0.0, 0.0), xv = make_double2(0.0, 0.0);
+    if (!first) {
+      pv = *reinterpret_cast<const double2*>(p + e);
+      xv = *reinterpret_cast<const double2*>(x + e);
     }
+    double cz[2];
     if constexpr (S == 1) {
-      CoarseRaw raw[2 * NPT];
-#pragma unroll
-      for (int u = 0; u < NPT; ++u) {
-        raw[2 * u] = coarse_row_load(cd.ctab, e[u]);
-        raw[2 * u + 1] = coarse_row_load(cd.ctab, e[u] + 1);
-      }
-#pragma unroll
-      for (int u = 0; u < NPT; ++u) {
-        zv[u] = __ldg(reinterpret_cast<const double2*>(r + e[u]));
-        d[u] = pair_weight<S, 1>(dinv, e[u]);
-        if (!first) {
-          pv[u] = *reinterpret_cast<const double2*>(p + e[u]);
-          xv[u] = *reinterpret_cast<const double2*>(x + e[u]);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < NPT; ++u) {
-        double c0[1], c1[1];
-        coarse_prolong<1, 1>(cd, raw[2 * u], 0, c0);
-        coarse_prolong<1, 1>(cd, raw[2 * u + 1], 0, c1);
-        cz[u][0] = c0[0];
-        cz[u][1] = c1[0];
-      }
+      double c0[1], c1[1];
+      coarse_prolong<1, 1>(cd, raw[0], 0, c0);
+      coarse_prolong<1, 1>(cd, raw[1], 0, c1);
+      cz[0] = c0[0];
+      cz[1] = c1[0];
     } else {
-      CoarseRaw raw[NPT];
-#pragma unroll
-      for (int u = 0; u < NPT; ++u) raw[u] = coarse_row_load(cd.ctab, e[u] / S);
-#pragma unroll
-      for (int u = 0; u < NPT; ++u) {
-        zv[u] = __ldg(reinterpret_cast<const double2*>(r + e[u]));
-        d[u] = pair_weight<S, 1>(dinv, e[u]);
-        if (!first) {
-          pv[u] = *reinterpret_cast<const double2*>(p + e[u]);
-          xv[u] = *reinterpret_cast<const double2*>(x + e[u]);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < NPT; ++u) coarse_prolong<S, 2>(cd, raw[u], fp.s0, cz[u]);
+      coarse_prolong<S, 2>(cd, raw[0], fp.s0, cz);
     }
-#pragma unroll
-    for (int u = 0; u < NPT; ++u) {
-      if (!on[u]) continue;
-      double2 z = make_double2(fma(zv[u].x, d[u].x, cz[u][0]), fma(zv[u].y, d[u].y, cz[u][1]));
-      if (!first) {
-        xv[u].x = fma(a0, pv[u].x, xv[u].x);
-        xv[u].y = fma(a1, pv[u].y, xv[u].y);
-        *reinterpret_cast<double2*>(x + e[u]) = xv[u];
-        z.x = fma(b0, pv[u].x, z.x);
-        z.y = fma(b1, pv[u].y, z.y);
-      }
-      *reinterpret_cast<double2*>(p + e[u]) = z;
+    zv.x = fma(zv.x, d.x, cz[0]);
+    zv.y = fma(zv.y, d.y, cz[1]);
+    if (!first) {
+      xv.x = fma(a0, pv.x, xv.x);
+      xv.y = fma(a1, pv.y, xv.y);
+      *reinterpret_cast<double2*>(x + e) = xv;
+      zv.x = fma(b0, pv.x, zv.x);
+      zv.y = fma(b1, pv.y, zv.y);
     }
+    *reinterpret_cast<double2*>(p + e) = zv;
+#pragma unroll
+    for (int k = 0; k < NR; ++k) raw[k] = nxt[k];
   }
   if (fp.has_tail) {
     const int64_t e = fp.tail;
@@ -1191,12 +1168,8 @@ int pcg_iteration(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int 
       PT_TRY(coarse_apply(ctx, *A.coarse, S, w.r.p));
       rho_finalize_kernel<<<1, 32, 0, ctx->stream>>>(w.scal.p, A.coarse->cdot.p, A.coarse->nlev, S);
       PT_LAUNCH_CHECK(ctx);
-      if (ctx->tune_pup_pairs == 2)
-        cg_pupdate_coarse_kernel<S, 2><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
-                                                                           coarse_dev(*A.coarse));
-      else
-        cg_pupdate_coarse_kernel<S, 1><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
-                                                                           coarse_dev(*A.coarse));
+      cg_pupdate_coarse_kernel<S><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
+                                                                      coarse_dev(*A.coarse));
       PT_LAUNCH_CHECK(ctx);
     }
   } else {
@@ -1235,8 +1208,8 @@ int pcg_start(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int prec
       PT_TRY(coarse_apply(ctx, *A.coarse, S, w.r.p));
       rho_finalize_kernel<<<1, 32, 0, ctx->stream>>>(w.scal.p, A.coarse->cdot.p, A.coarse->nlev, S);
       PT_LAUNCH_CHECK(ctx);
-      cg_pupdate_coarse_kernel<S, 1><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 1,
-                                                                         coarse_dev(*A.coarse));
+      cg_pupdate_coarse_kernel<S><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 1,
+                                                                      coarse_dev(*A.coarse));
       PT_LAUNCH_CHECK(ctx);
     }
   } else {

@@ -1,3 +1,5 @@
+"""CPU prototype (scipy) behind csrc/coarse.cu: PCG iteration counts of Jacobi vs Jacobi + trilinear coarse grids on the
+bench workload.  Usage: python scripts/proto_coarse_space.py S|M|NXxNYxNZ   (SKIPJ=1 skips the plain Jacobi solve)."""
 import sys, time, importlib, numpy as np, scipy.sparse as sp, scipy.sparse.linalg as spla
 sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/oracle')
 import fem_oracle as fo
@@ -65,19 +67,14 @@ def coarse_const(ncx, ncy, zlines):
 
 Lz = mesh.meta['Lz']; ts = mesh.meta['t_skin']; tf = 0.005
 zl_layers = lambda nm: np.concatenate([np.linspace(0, Lz-ts-tf, nm+1), [Lz-ts, Lz]])
-
-def run(name, M):
-    t=time.time(); x1, it1 = pcg(K, b, M); print(f'{name}: its {it1} {time.time()-t:.1f}s', flush=True)
-def uz(n): return np.linspace(0, Lz, n+1)
-def bpx(grids, exact):
-    Zs=[coarse_trilinear(*g[:2], uz(g[2])) for g in grids]
-    Ds=[np.asarray((Z.T@K@Z).diagonal()) for Z in Zs]
-    Ze=coarse_trilinear(exact[0],exact[1],uz(exact[2])); lu=spla.splu((Ze.T@K@Ze).tocsc())
-    def M(r):
-        z=r/d + Ze@lu.solve(Ze.T@r)
-        for Z,D in zip(Zs,Ds): z+= Z@((Z.T@r)/D)
-        return z
-    return M, Ze.shape[1]
-for grids, exact in [([], (16,12,6)), ([(32,24,12)], (16,12,6)), ([(64,48,24),(32,24,12)], (16,12,6)), ([(48,36,30),(24,18,15)], (12,9,8)),
-                     ([(64,48,40)], (16,12,10)), ([(64,48,40),(32,24,20)], (16,12,10))]:
-    M,k=bpx(grids, exact); run(f'bpx {grids} exact {exact} k={k}', M)
+for name, Z in [
+    ('tri 12x9x(3+2)', coarse_trilinear(12,9,zl_layers(3))),
+    ('tri 24x18x(6+2)', coarse_trilinear(24,18,zl_layers(6))),
+    ('tri 16x12x(4+2)', coarse_trilinear(16,12,zl_layers(4))),
+    ('tri 32x24x(8+2)', coarse_trilinear(32,24,zl_layers(8))),
+    ('tri 32x24 uniform z 10', coarse_trilinear(32,24,np.linspace(0,Lz,11))),
+]:
+    E = (Z.T @ K @ Z).tocsc(); lu = spla.splu(E)
+    M = lambda r: r/d + Z @ lu.solve(Z.T @ r)
+    t=time.time(); x1, it1 = pcg(K, b, M)
+    print(f'{name}: k={Z.shape[1]} its {it1}    {time.time()-t:.1f}s', flush=True)
