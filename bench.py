@@ -71,7 +71,7 @@ def run_sweep_step(dm, mesh, confs, step, phi_out=None, J_out=None, sample_spmv=
     Lz, t_skin = mesh.meta["Lz"], mesh.meta["t_skin"]
     rows = []
     for k, c in enumerate(confs):
-        dm.recover_current(k, RECOVER, to_host=J_out is not None, out=None if J_out is None else J_out[k])
+        dm.recover_current(k, RECOVER, to_host=J_out is not None, out=None if J_out is None else J_out[k], wait=J_out is None)
         fp = (c["center"][0], c["center"][1], c["r"], False)
         pk = dm.metric_nodes(0, Lz - 0.2 * t_skin, sys=k)
         ph = dm.metric_nodes(1, Lz - 1e-5, mode=1, footprints=[fp], scale_r=1.0, sys=k)

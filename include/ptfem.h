@@ -183,6 +183,10 @@ int ptfem_metric_reaction(ptfem_mesh* m, int32_t sys, int32_t bcid, double* curr
  * activating function (second difference / h^2) at the interior points. */
 int ptfem_sample_polyline(ptfem_mesh* m, int32_t sys, int64_t npts, const double* pts /*[npts*3]*/,
                           double* phi_out /*[npts]*/, double* af_out /*[npts]*/);
+/* same, but the device->host copy of J runs on a side stream and is NOT waited for: J (pinned host memory) is valid
+   after the next ptfem_ctx_sync; the following recovery waits for the copy before it overwrites the device buffer, so
+   the copy overlaps the metric reductions of this system and the element pass of the next one */
+int ptfem_recover_current_async(ptfem_mesh* m, int32_t sys, int32_t method, double* J /*[nn*3], pinned*/);
 int ptfem_current_get(ptfem_mesh* m, double* J /*[nn*3]*/);
 
 /* -- multi-GPU: row-partitioned single solve (config #5).  The caller passes an ncclUniqueId

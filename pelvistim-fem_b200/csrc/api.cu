@@ -172,6 +172,8 @@ int ptfem_ctx_create(int device, ptfem_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   PT_CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   PT_CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  PT_CK(cudaEventCreateWithFlags(&c->ev_j_ready, cudaEventDisableTiming));
+  PT_CK(cudaEventCreateWithFlags(&c->ev_j_copied, cudaEventDisableTiming));
   if (const char* e = getenv("PTFEM_INTERLEAVE")) c->tune_interleave = atoi(e) != 0;
   if (const char* e = getenv("PTFEM_MORTON")) c->tune_morton = atoi(e);
   if (const char* e = getenv("PTFEM_P2P_FUSED")) c->tune_p2p_fused = atoi(e) != 0;
@@ -193,6 +195,8 @@ int ptfem_ctx_destroy(ptfem_ctx* ctx) {
   cudaSetDevice(ctx->device);
   ptfem_dist_ctx_release(ctx);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->ev_j_ready) cudaEventDestroy(ctx->ev_j_ready);
+  if (ctx->ev_j_copied) cudaEventDestroy(ctx->ev_j_copied);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   delete ctx;
@@ -204,6 +208,7 @@ int ptfem_ctx_sync(ptfem_ctx* ctx) {
   PT_ARG(ctx, "null context");
   PT_CK(cudaSetDevice(ctx->device));
   PT_CK(cudaStreamSynchronize(ctx->stream));
+  PT_CK(cudaStreamSynchronize(ctx->stream2));
   return PTFEM_OK;
 }
 
@@ -279,6 +284,7 @@ int ptfem_mesh_destroy(ptfem_mesh* m) {
   if (!m) return PTFEM_OK;
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
+  cudaStreamSynchronize(m->ctx->stream2);
   pcg_work_drop_graph(m->work);
   pcg_work_drop_graph(m->work3);
   ptfem_dist_mesh_release(m);
@@ -576,6 +582,21 @@ int ptfem_recover_current(ptfem_mesh* m, int32_t sys, int32_t method, double* J)
     PT_CK(cudaMemcpyAsync(J, m->Jnode.p, (size_t)m->nn * 3 * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
     PT_CK(cudaStreamSynchronize(m->ctx->stream));
   }
+  return PTFEM_OK;
+}
+
+int ptfem_recover_current_async(ptfem_mesh* m, int32_t sys, int32_t method, double* J) {
+  PT_ARG(m && J, "null pointer");
+  ptfem_ctx* ctx = m->ctx;
+  PT_CK(cudaSetDevice(ctx->device));
+  PT_TRY(ptfem_do_recover(m, sys, method));
+  // copy on the side stream once the recovery kernels are done; the next recovery waits for it before it
+  // overwrites the device buffer, metric kernels of this system only read it and run concurrently
+  PT_CK(cudaEventRecord(ctx->ev_j_ready, ctx->stream));
+  PT_CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_j_ready, 0));
+  PT_CK(cudaMemcpyAsync(J, m->Jnode.p, (size_t)m->nn * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream2));
+  PT_CK(cudaEventRecord(ctx->ev_j_copied, ctx->stream2));
+  m->j_copy_pending = true;
   return PTFEM_OK;
 }
 

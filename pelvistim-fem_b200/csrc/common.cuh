@@ -97,6 +97,7 @@ struct ptfem_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // copies / halo
   int64_t launches = 0;
+  cudaEvent_t ev_j_ready = nullptr, ev_j_copied = nullptr;  // asynchronous read-back of the nodal current (stream2)
   double* h_pinned = nullptr;  // small pinned scratch (scalars)
   size_t h_pinned_n = 0;
   int tune_interleave = 1;         // SpMV work distribution: 1 moving front, 0 contiguous run per CTA (PTFEM_INTERLEAVE)
@@ -201,6 +202,7 @@ struct ptfem_mesh {
   ptfem::DevBuf<double> mdinv, mrhs, mx; // mass-matrix Jacobi, rhs [nn][4], solution [nn][4]
   ptfem::DevBuf<double> phis;     // [nn] VTK-smoothed potential (ROI metric)
   int J_sys = -1;                 // system whose nodal current is in Jnode
+  bool j_copy_pending = false;    // an asynchronous device->host copy of Jnode may still be reading it
   int mass_iters = 0;
   ptfem::DevBuf<double> scratch_d;
   ptfem::DevBuf<int32_t> scratch_i;

@@ -518,12 +518,22 @@ int ptfem_do_element_fields(ptfem_mesh* m, int sys) {
 
 int ptfem_do_assemble_mass(ptfem_mesh* m);
 
+// Jnode is about to be overwritten: an asynchronous read-back issued by ptfem_recover_current_async must finish first
+static int wait_j_copy(ptfem_mesh* m) {
+  if (m->j_copy_pending) {
+    PT_CK(cudaStreamWaitEvent(m->ctx->stream, m->ctx->ev_j_copied, 0));
+    m->j_copy_pending = false;
+  }
+  return PTFEM_OK;
+}
+
 int ptfem_do_recover(ptfem_mesh* m, int sys, int method) {
   ptfem_ctx* ctx = m->ctx;
   PT_TRY(ptfem_do_element_fields(m, sys));
   PT_TRY(m->Jnode.alloc((size_t)m->nn * 3));
   const int grid = ceil_div(m->nn, 128);
   if (method == PTFEM_RECOVER_LUMPED || method == PTFEM_RECOVER_AVERAGE) {
+    PT_TRY(wait_j_copy(m));
     recover_gather_kernel<<<grid, 128, 0, ctx->stream>>>(m->n2t_ptr.p, m->n2t.p, m->vol.p, m->Jelem.p, m->mlump.p, m->nn,
                                                          method == PTFEM_RECOVER_LUMPED ? 1 : 2, m->Jnode.p);
     PT_LAUNCH_CHECK(ctx);
@@ -562,6 +572,7 @@ int ptfem_do_recover(ptfem_mesh* m, int sys, int method) {
   ptfem_solve_stats st;
   PT_TRY(pcg_solve(ctx, A, m->work3, o, m->mx.p, &st));
   m->mass_iters = st.iterations;
+  PT_TRY(wait_j_copy(m));
   pack43_kernel<<<grid, 128, 0, ctx->stream>>>(m->mx.p, m->nn, m->Jnode.p);
   PT_LAUNCH_CHECK(ctx);
   m->J_sys = sys;

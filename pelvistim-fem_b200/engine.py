@@ -98,6 +98,7 @@ def load_library():
         "ptfem_spmv_bench": (C.c_int, [vp, i32, i32, P(dbl)]),
         "ptfem_element_fields": (C.c_int, [vp, i32, vp, vp]),
         "ptfem_recover_current": (C.c_int, [vp, i32, i32, vp]),
+        "ptfem_recover_current_async": (C.c_int, [vp, i32, i32, vp]),
         "ptfem_current_get": (C.c_int, [vp, vp]),
         "ptfem_metric_nodes": (C.c_int, [vp, i32, i32, dbl, dbl, i32, vp, i32, dbl, P(dbl)]),
         "ptfem_metric_pad_current": (C.c_int, [vp, i32, dbl, P(Footprint), dbl, P(dbl)]),
@@ -359,9 +360,16 @@ class DeviceMesh:
         self._ck(self.lib.ptfem_element_fields(self._h, sys, _ptr(E), _ptr(J)))
         return E, J
 
-    def recover_current(self, sys=0, method="l2", to_host=True, out=None):
+    def recover_current(self, sys=0, method="l2", to_host=True, out=None, wait=True):
+        """Nodal current of one system.  ``wait=False`` (needs ``out`` in pinned memory): the read-back runs on a side
+        stream and ``out`` is valid after ``Context.sync()``; it overlaps the metric calls that follow."""
         J = (out if out is not None else np.empty((self.nn, 3), dtype=np.float64)) if to_host else None
-        self._ck(self.lib.ptfem_recover_current(self._h, sys, _RECOVER[method], _ptr(J)))
+        if to_host and not wait:
+            if out is None:
+                raise ValueError("wait=False needs a caller-owned (pinned) out array")
+            self._ck(self.lib.ptfem_recover_current_async(self._h, sys, _RECOVER[method], _ptr(J)))
+        else:
+            self._ck(self.lib.ptfem_recover_current(self._h, sys, _RECOVER[method], _ptr(J)))
         return J
 
     # -- K12 -------------------------------------------------------------------------

@@ -262,6 +262,30 @@ def test_geometry_change_on_fixed_topology(gpu_ctx):
     dm.close()
 
 
+def test_async_current_readback_matches_blocking(gpu_ctx):
+    # ptfem_recover_current_async: the copy runs on a side stream; valid after Context.sync(); the next recovery must
+    # not overwrite the device buffer before the copy has read it
+    import torch
+    m = meshgen.synth_slab("S")
+    dm = dm_for(gpu_ctx, m)
+    dm.assemble(SIGMA5).bc_reset(3)
+    for k in range(3):
+        dm.neumann(101, 5.0 + 3 * k, rhs=k)
+    dm.dirichlet(102, 0.0)
+    dm.solve(to_host=False)
+    ref = [dm.recover_current(k, "lumped").copy() for k in range(3)]
+    out = torch.empty((3, m.nn, 3), dtype=torch.float64).pin_memory().numpy()
+    for k in range(3):
+        dm.recover_current(k, "lumped", out=out[k], wait=False)
+        dm.metric_nodes(0, 0.0, sys=k)
+    gpu_ctx.sync()
+    for k in range(3):
+        assert np.array_equal(out[k], ref[k])
+    with pytest.raises(ValueError):
+        dm.recover_current(0, "lumped", wait=False)
+    dm.close()
+
+
 # -- coarse-grid preconditioner ---------------------------------------------------------------------------
 @pytest.mark.parametrize("levels", [0, 1, -1])
 @pytest.mark.parametrize("nrhs", [1, 2, 3, 8, 16])
