@@ -426,16 +426,29 @@ int ptfem_solve_device(ptfem_mesh* m, const ptfem_solve_opts* opts, ptfem_solve_
   PT_ARG(o.rtol > 0.0 && o.maxit > 0, "rtol and maxit must be positive");
   PT_ARG(o.precond >= PTFEM_PRECOND_AUTO && o.precond <= PTFEM_PRECOND_TWOLEVEL, "unknown preconditioner");
   PT_TRY(prepare_systems(m));
-  if (o.precond == PTFEM_PRECOND_AUTO)
-    o.precond = (m->nvalp == 1 && m->nn >= 100000) ? PTFEM_PRECOND_TWOLEVEL : PTFEM_PRECOND_JACOBI;
+  const bool automatic = o.precond == PTFEM_PRECOND_AUTO;
+  if (automatic) o.precond = (m->nvalp == 1 && m->nn >= 100000) ? PTFEM_PRECOND_TWOLEVEL : PTFEM_PRECOND_JACOBI;
   LinSys A;
   make_linsys(m, A);
   double setup_ms = 0.0;
   if (o.precond == PTFEM_PRECOND_TWOLEVEL) {
     const int64_t epoch_before = m->coarse ? m->coarse->matrix_epoch : -1;
-    PT_TRY(coarse_prepare(m, o.coarse_nodes, o.coarse_levels, m->S));
-    if (m->coarse->matrix_epoch != epoch_before) setup_ms = m->coarse->setup_ms;
-    A.coarse = m->coarse;
+    int rcp = coarse_prepare(m, o.coarse_nodes, o.coarse_levels, m->S);
+    // a strongly graded mesh can leave coarse cells (nearly) empty and the Galerkin matrix singular: the automatic
+    // choice then retries with a 4x coarser grid and finally settles for Jacobi; an explicit request reports the error
+    if (rcp == PTFEM_ERR_STATE && automatic) {
+      const int nodes = (o.coarse_nodes > 0 ? o.coarse_nodes : 2000) / 4;
+      rcp = coarse_prepare(m, nodes < 27 ? 27 : nodes, o.coarse_levels, m->S);
+      if (rcp == PTFEM_ERR_STATE) {
+        o.precond = PTFEM_PRECOND_JACOBI;
+        rcp = PTFEM_OK;
+      }
+    }
+    if (rcp) return rcp;
+    if (o.precond == PTFEM_PRECOND_TWOLEVEL) {
+      if (m->coarse->matrix_epoch != epoch_before) setup_ms = m->coarse->setup_ms;
+      A.coarse = m->coarse;
+    }
   }
   m->J_sys = -1;
   if (!o.warm_start) PT_CK(cudaMemsetAsync(m->phi.p, 0, (size_t)m->nn * m->S * sizeof(double), m->ctx->stream));

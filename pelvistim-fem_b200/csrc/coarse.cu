@@ -503,8 +503,13 @@ __global__ void galerkin_diag_node_kernel(CoarseGrid g, int64_t k, const double*
 // ---- dense inverse: blocked Gauss-Jordan without pivoting (the matrix is SPD) ---------------------------------
 // step t: P = A[t,t]; R = P^-1 [A[t,:] with block column t replaced by I]; C = A[:,t];
 //         A[i,:] = A[i,:](block column t zeroed) - C[i] R  (i != t),  A[t,:] = R
-__global__ void __launch_bounds__(1024) gj_pivot_kernel(const double* __restrict__ A, int kp, int t, double* __restrict__ Pinv,
-                                                        int32_t* __restrict__ flag) {
+__global__ void gj_diag_kernel(const double* __restrict__ A, int kp, double* __restrict__ d0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < kp) d0[i] = A[(size_t)i * kp + i];
+}
+// a pivot that has lost ten digits against the original diagonal means (numerically) dependent coarse functions
+__global__ void __launch_bounds__(1024) gj_pivot_kernel(const double* __restrict__ A, int kp, int t, const double* __restrict__ d0,
+                                                        double* __restrict__ Pinv, int32_t* __restrict__ flag) {
   __shared__ double P[kGjNb][kGjNb + 1], Q[kGjNb][kGjNb + 1];
   const int r = threadIdx.x / kGjNb, c = threadIdx.x % kGjNb;
   P[r][c] = A[(size_t)(t * kGjNb + r) * kp + t * kGjNb + c];
@@ -512,7 +517,7 @@ __global__ void __launch_bounds__(1024) gj_pivot_kernel(const double* __restrict
   __syncthreads();
   for (int s = 0; s < kGjNb; ++s) {
     const double piv = P[s][s], f = P[r][s];
-    if (threadIdx.x == 0 && !(piv > 0.0)) flag[0] = 1;
+    if (threadIdx.x == 0 && !(piv > 1e-10 * d0[t * kGjNb + s])) flag[0] = 1;
     __syncthreads();
     if (r == s) {
       P[r][c] /= piv;
@@ -602,13 +607,16 @@ __global__ void __launch_bounds__(256) gj_update_kernel(double* __restrict__ A, 
 }
 
 int dense_inverse(ptfem_ctx* ctx, double* A, int kp, int32_t* flag) {
-  DevBuf<double> Pinv, Rbuf, Cbuf;
+  DevBuf<double> Pinv, Rbuf, Cbuf, d0;
+  PT_TRY(d0.alloc(kp));
+  gj_diag_kernel<<<ceil_div(kp, 256), 256, 0, ctx->stream>>>(A, kp, d0.p);
+  PT_LAUNCH_CHECK(ctx);
   PT_TRY(Pinv.alloc(kGjNb * kGjNb));
   PT_TRY(Rbuf.alloc((size_t)kGjNb * kp));
   PT_TRY(Cbuf.alloc((size_t)kp * kGjNb));
   const int steps = kp / kGjNb, tiles = kp / kGjTile;
   for (int t = 0; t < steps; ++t) {
-    gj_pivot_kernel<<<1, kGjNb * kGjNb, 0, ctx->stream>>>(A, kp, t, Pinv.p, flag);
+    gj_pivot_kernel<<<1, kGjNb * kGjNb, 0, ctx->stream>>>(A, kp, t, d0.p, Pinv.p, flag);
     PT_LAUNCH_CHECK(ctx);
     gj_panel_kernel<<<tiles, 256, 0, ctx->stream>>>(A, kp, t, Pinv.p, Rbuf.p, Cbuf.p);
     PT_LAUNCH_CHECK(ctx);
@@ -865,7 +873,7 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
     PT_CK(cudaMemcpyAsync(hflag, cs.flag.p, sizeof hflag, cudaMemcpyDeviceToHost, ctx->stream));
     PT_CK(cudaStreamSynchronize(ctx->stream));
     if (hflag[0])
-      return set_err(PTFEM_ERR_STATE, "coarse Galerkin matrix is not positive definite (grid %dx%dx%d too fine for this mesh?)",
+      return set_err(PTFEM_ERR_STATE, "coarse Galerkin matrix is singular or indefinite to working precision (grid %dx%dx%d too fine for this mesh?)",
                      cs.lev[cs.nlev - 1].g.n[0], cs.lev[cs.nlev - 1].g.n[1], cs.lev[cs.nlev - 1].g.n[2]);
     cs.matrix_epoch = m->matrix_epoch;
     rebuilt = true;

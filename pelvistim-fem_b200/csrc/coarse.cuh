@@ -66,7 +66,9 @@ __device__ __forceinline__ void coarse_locate(const CoarseGrid& g, const double*
     int ci = (int)floor(u);
     ci = ci < 0 ? 0 : (ci > g.n[d] - 1 ? g.n[d] - 1 : ci);
     double tt = u - (double)ci;
-    t[d] = tt < 0.0 ? 0.0 : (tt > 1.0 ? 1.0 : tt);
+    // snap onto the grid planes: a mesh node on a plane must give its neighbour across the plane weight 0, not 1e-12
+    // (a coarse function carried only by such weights would make the Galerkin matrix numerically singular)
+    t[d] = tt < 1e-9 ? 0.0 : (tt > 1.0 - 1e-9 ? 1.0 : tt);
     c[d] = ci;
   }
 }

@@ -14,8 +14,14 @@ by = 12 * nnz + 20 * mesh.nn
 for v in (2, 1):
     ms = dm.spmv_bench(v, 20)
     print("variant", v, "%.4f ms  %.0f GB/s (%.2f of measured peak)" % (ms, by / ms / 1e6, by / ms / 1e6 / 6543.7), flush=True)
-dm.solve(to_host=False, raise_on_noconv=False, maxit=200, check_every=50, rtol=1e-10)
+dm.solve(to_host=False, raise_on_noconv=False, maxit=200, check_every=50, rtol=1e-10, precond=engine.PRECOND_JACOBI)
 s = dm.last_stats
-print("200 PCG iterations: %.1f ms (%.3f ms/it)" % (s["solve_ms"], s["solve_ms"] / 200), "host maxrss GB %.1f" % (resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1e6), flush=True)
+print("200 Jacobi-PCG iterations: %.1f ms (%.3f ms/it)" % (s["solve_ms"], s["solve_ms"] / 200), "host maxrss GB %.1f" % (resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1e6), flush=True)
+# full solves to rtol 1e-10: default (Jacobi + coarse grids), then plain Jacobi
+for name, pc in (("auto", engine.PRECOND_AUTO), ("auto again (set-up reused)", engine.PRECOND_AUTO), ("jacobi", engine.PRECOND_JACOBI)):
+    dm.solve(to_host=False, rtol=1e-10, precond=pc)
+    s = dm.last_stats
+    print("full solve %s: precond %d, %d iterations, solve %.1f ms, set-up %.1f ms, coarse unknowns %d, true rel. residual %.1e"
+          % (name, s["precond"], s["iterations"], s["solve_ms"], s["setup_ms"], s["coarse_unknowns"], s["true_rel_residual"]), flush=True)
 import torch
 print("device memory in use GB %.1f" % ((torch.cuda.mem_get_info()[1] - torch.cuda.mem_get_info()[0]) / 1e9))

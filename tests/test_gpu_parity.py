@@ -346,6 +346,19 @@ def test_twolevel_odd_rows_unstructured_and_moved_mesh(gpu_ctx):
     dm.close()
 
 
+def test_twolevel_too_fine_grid_is_reported(gpu_ctx):
+    # more coarse unknowns than mesh nodes: the Galerkin matrix is singular; an explicit request says so
+    m = meshgen.box_mesh(nx=4, ny=3, nz=2)
+    dm = dm_for(gpu_ctx, m)
+    dm.assemble({1: 0.2}).bc_reset(1).neumann(101, 1.0).dirichlet(102, 0.0)
+    with pytest.raises(engine.PtfemError, match="singular"):
+        dm.solve(precond=engine.PRECOND_TWOLEVEL, coarse_nodes=2000, coarse_levels=0)
+    phi = dm.solve(precond=engine.PRECOND_TWOLEVEL, coarse_nodes=27, coarse_levels=0)[0]
+    ref = fo.solve_case(m, {1: 0.2}, [(102, 0.0)], [(101, 1.0)], recover=None)["phi"]
+    assert rel(phi, ref) < TOL_PHI
+    dm.close()
+
+
 def test_twolevel_needs_shared_matrix_and_auto_choice(gpu_ctx):
     m = meshgen.synth_slab("XS")
     dm = dm_for(gpu_ctx, m)
