@@ -246,3 +246,18 @@ def test_compression_field_keeps_mesh_valid():
         assert (meshgen.tet_volumes(n2, m.tets) > 0).all()
         assert np.all(n2[:, 2] <= m.nodes[:, 2] + 1e-15) and np.isclose((m.nodes[:, 2] - n2[:, 2]).max(), depth * 1.0125, rtol=0.02)
         assert np.array_equal(n2[:, :2], m.nodes[:, :2]) and np.all(n2[m.nodes[:, 2] == 0.0, 2] == 0.0)
+
+
+def test_ctypes_structs_follow_the_header():
+    """ptfem_solve_opts / ptfem_solve_stats: field names, order and C types of the ctypes mirrors equal the header's."""
+    import ctypes as C
+    import re
+    from pelvistim_fem_b200 import engine
+    from pathlib import Path
+    hdr = (Path(__file__).resolve().parents[1] / "include" / "ptfem.h").read_text()
+    ctype = {"int32_t": C.c_int32, "double": C.c_double, "int64_t": C.c_int64}
+    for name, cls in (("ptfem_solve_opts", engine.SolveOpts), ("ptfem_solve_stats", engine.SolveStats)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        fields = [(m.group(2), ctype[m.group(1)]) for m in re.finditer(r"(int32_t|int64_t|double)\s+(\w+)\s*;", body)]
+        assert fields == list(cls._fields_), name
