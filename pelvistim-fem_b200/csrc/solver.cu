@@ -1322,8 +1322,10 @@ int pcg_solve_t(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_o
     prev_true2 = w2;
     // iterate in chunks of `check`
     bool chunk_conv = false;
+    double chunk_w2 = w2;   // worst rel^2 at the start of the next chunk
+    int next_it = check;    // length of the next chunk: `check`, or fewer when the end is predicted to be near
     while (it < o.maxit) {
-      const int n_it = (o.maxit - it) < check ? (o.maxit - it) : check;
+      const int n_it = (o.maxit - it) < next_it ? (o.maxit - it) : next_it;
       const bool use_graph = o.use_graph && n_it == check;
       if (use_graph) {
         if (!w.graph || w.graph_iters != check || w.graph_variant != variant || w.graph_precond != precond ||
@@ -1381,6 +1383,21 @@ int pcg_solve_t(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_o
         chunk_conv = true;
         break;
       }
+      // the residual of the last chunk fell by (w2 / chunk_w2) in n_it iterations: when that rate reaches rtol
+      // within less than a chunk, run just that many iterations (plus one) instead of a whole chunk
+      // (CG residuals are not log-linear: if such a short chunk falls short, go on in fifths of a chunk)
+      if (n_it < check) {
+        next_it = check >= 5 ? check / 5 : 1;
+      } else {
+        next_it = check;
+        if (w2 < chunk_w2 && chunk_w2 > 0.0) {
+          const double per_it = log(w2 / chunk_w2) / (double)n_it;   // < 0
+          const double need = log(rtol2 / w2) / per_it;
+          if (need < (double)check - 1.0) next_it = (int)ceil(need) + 1;
+          if (next_it < 1) next_it = 1;
+        }
+      }
+      chunk_w2 = w2;
     }
     if (rc) break;
     if (!chunk_conv) break;  // maxit
