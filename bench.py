@@ -437,7 +437,9 @@ def main():
             "clocks": clocks.summary(), "gpu_launches": int(launches), "pcg_iterations_per_step": statistics.mean(iters),
             "pcg": {"precond": {0: "jacobi", 1: "chebyshev", 2: "jacobi+coarse-grids"}[last_st["precond"]],
                     "iterations": statistics.mean(iters), "solve_ms": last_st["solve_ms"], "setup_ms": last_st["setup_ms"],
-                    "coarse_unknowns": last_st["coarse_unknowns"], "jacobi_iterations": jacobi_iters, "jacobi_solve_ms": jacobi_ms},
+                    "coarse_unknowns": last_st["coarse_unknowns"], "jacobi_iterations": jacobi_iters, "jacobi_solve_ms": jacobi_ms,
+                    # the same step if the GPU arm ran the CPU arm's algorithm (plain Jacobi-PCG), for a like-for-like ratio
+                    "value_with_jacobi_only": world * args.nconf / ((t_dev / args.steps) - (last_st["solve_ms"] + last_st["setup_ms"] - jacobi_ms) * 1e-3)},
             "roofline": roofline,
             "cg_spmv_1rhs": {"achieved": spmv1_gbs, "unit": "GB/s", "frac": spmv1_gbs / peak, "frac_of_nominal_8TBs": spmv1_gbs / 8000.0,
                              "ms_per_launch": spmv1_ms, "algorithmic_bytes_per_launch": alg1,
