@@ -172,9 +172,6 @@ int ptfem_ctx_create(int device, ptfem_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   PT_CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   PT_CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-  PT_CK(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
-  PT_CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-  PT_CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   PT_CK(cudaEventCreateWithFlags(&c->ev_j_ready, cudaEventDisableTiming));
   PT_CK(cudaEventCreateWithFlags(&c->ev_j_copied, cudaEventDisableTiming));
   if (const char* e = getenv("PTFEM_INTERLEAVE")) c->tune_interleave = atoi(e) != 0;
@@ -183,7 +180,6 @@ int ptfem_ctx_create(int device, ptfem_ctx** out) {
   if (const char* e = getenv("PTFEM_XPREFETCH")) c->tune_xprefetch = atoi(e) != 0;
   if (const char* e = getenv("PTFEM_CTAS_PER_SM")) c->tune_ctas_per_sm = atoi(e);
   if (const char* e = getenv("PTFEM_RESTRICT_OCC")) c->tune_restrict_occ = atoi(e);
-  if (const char* e = getenv("PTFEM_XFORK")) c->tune_xfork = atoi(e);
   if (const char* e = getenv("PTFEM_STREAM_CAP")) c->tune_stream_cap = atoi(e);
   if (const char* e = getenv("PTFEM_STREAM_ROWS")) c->tune_stream_rows = atoi(e);
   if (const char* e = getenv("PTFEM_STREAM_TPR")) c->tune_stream_tpr = atoi(e);
@@ -199,9 +195,6 @@ int ptfem_ctx_destroy(ptfem_ctx* ctx) {
   cudaSetDevice(ctx->device);
   ptfem_dist_ctx_release(ctx);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
-  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-  if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
   if (ctx->ev_j_ready) cudaEventDestroy(ctx->ev_j_ready);
   if (ctx->ev_j_copied) cudaEventDestroy(ctx->ev_j_copied);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);

@@ -761,9 +761,16 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
   CoarseSpace& cs = *m->coarse;
   if (target_nodes <= 0) target_nodes = 2000;
   if (extra_levels > kMaxCoarseLevels - 1) extra_levels = kMaxCoarseLevels - 1;
-  cudaEvent_t e0, e1;
-  PT_CK(cudaEventCreate(&e0));
-  PT_CK(cudaEventCreate(&e1));
+  struct Events {  // destroyed on every return path
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~Events() {
+      if (e0) cudaEventDestroy(e0);
+      if (e1) cudaEventDestroy(e1);
+    }
+  } ev;
+  PT_CK(cudaEventCreate(&ev.e0));
+  PT_CK(cudaEventCreate(&ev.e1));
+  cudaEvent_t e0 = ev.e0, e1 = ev.e1;
   PT_CK(cudaEventRecord(e0, ctx->stream));
   bool rebuilt = false;
   if (!cs.geom_ok || cs.req_nodes != target_nodes || cs.req_levels != extra_levels) {
@@ -882,8 +889,6 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
   PT_CK(cudaEventSynchronize(e1));
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   if (rebuilt) cs.setup_ms = ms;
   return PTFEM_OK;
 }

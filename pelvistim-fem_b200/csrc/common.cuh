@@ -96,8 +96,6 @@ struct ptfem_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // copies / halo
-  cudaStream_t stream3 = nullptr;  // PCG side branch (x += alpha p beside the coarse-grid chain)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int64_t launches = 0;
   cudaEvent_t ev_j_ready = nullptr, ev_j_copied = nullptr;  // asynchronous read-back of the nodal current (stream2)
   double* h_pinned = nullptr;  // small pinned scratch (scalars)
@@ -110,7 +108,6 @@ struct ptfem_ctx {
   int tune_morton = -1;            // streaming SpMV walks rows along a Morton curve: -1 auto, 0 off, 1 on (PTFEM_MORTON)
   int tune_p2p_fused = 0;          // row-partitioned solve: SpMV loads halo entries from peer memory itself (PTFEM_P2P_FUSED)
   int tune_xprefetch = 0;          // streaming SpMV prefetches the leading edge of x into L2 (PTFEM_XPREFETCH)
-  int tune_xfork = 0;              // coarse-grid PCG: x += alpha p on a side stream beside restriction + grid chain (PTFEM_XFORK); measured slower (77 vs 71 ms), off
   int tune_restrict_occ = 1;       // PTFEM_RESTRICT_OCC: 1 = register-capped restriction kernel (4 CTAs/SM, measured 7% faster solve), 0 = uncapped
   int tune_ctas_per_sm = 0;        // cap on resident CTAs per SM of the streaming SpMV (PTFEM_CTAS_PER_SM)
   std::unordered_map<const void*, size_t> func_smem;  // dynamic shared memory limit raised per kernel

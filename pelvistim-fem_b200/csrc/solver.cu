@@ -667,24 +667,7 @@ __device__ __forceinline__ void coarse_prolong(const CoarseDev& cd, const Coarse
 // p-update of the two-level preconditioner (one shared matrix): z = dinv r + Z y.  The table entry of the next trip is
 // loaded one trip ahead: the table -> grid node -> y chain is two dependent loads deep and ncu shows the kernel
 // waiting on exactly that chain (long-scoreboard stalls on the first use of the table entry).
-// x += alpha p (the x half of the p-update, run on a side stream beside the coarse-grid chain)
 template <int S>
-__global__ void __launch_bounds__(kThreads) x_axpy_kernel(int64_t nn, const double* __restrict__ p, double* __restrict__ x,
-                                                          const double* __restrict__ scal) {
-  const FlatPairs<S> fp(nn);
-  const double a0 = scal[SC_ALPHA * kMaxSys + fp.s0], a1 = scal[SC_ALPHA * kMaxSys + fp.s1];
-  for (int64_t j = fp.j0; j < fp.npairs; j += fp.stride) {
-    const int64_t e = 2 * j;
-    const double2 pv = __ldg(reinterpret_cast<const double2*>(p + e));
-    double2 xv = *reinterpret_cast<const double2*>(x + e);
-    xv.x = fma(a0, pv.x, xv.x);
-    xv.y = fma(a1, pv.y, xv.y);
-    *reinterpret_cast<double2*>(x + e) = xv;
-  }
-  if (fp.has_tail) x[fp.tail] = fma(a0, p[fp.tail], x[fp.tail]);
-}
-
-template <int S, bool WITH_X>
 __global__ void __launch_bounds__(kThreads, 3) cg_pupdate_coarse_kernel(int64_t nn, const double* __restrict__ r,
                                                                         const double* __restrict__ dinv, double* __restrict__ p,
                                                                         double* __restrict__ x, const double* __restrict__ scal,
@@ -708,7 +691,7 @@ __global__ void __launch_bounds__(kThreads, 3) cg_pupdate_coarse_kernel(int64_t 
     double2 pv = make_double2(0.0, 0.0), xv = make_double2(0.0, 0.0);
     if (!first) {
       pv = *reinterpret_cast<const double2*>(p + e);
-      if constexpr (WITH_X) xv = *reinterpret_cast<const double2*>(x + e);
+      xv = *reinterpret_cast<const double2*>(x + e);
     }
     double cz[2];
     if constexpr (S == 1) {
@@ -723,11 +706,9 @@ __global__ void __launch_bounds__(kThreads, 3) cg_pupdate_coarse_kernel(int64_t 
     zv.x = fma(zv.x, d.x, cz[0]);
     zv.y = fma(zv.y, d.y, cz[1]);
     if (!first) {
-      if constexpr (WITH_X) {
-        xv.x = fma(a0, pv.x, xv.x);
-        xv.y = fma(a1, pv.y, xv.y);
-        *reinterpret_cast<double2*>(x + e) = xv;
-      }
+      xv.x = fma(a0, pv.x, xv.x);
+      xv.y = fma(a1, pv.y, xv.y);
+      *reinterpret_cast<double2*>(x + e) = xv;
       zv.x = fma(b0, pv.x, zv.x);
       zv.y = fma(b1, pv.y, zv.y);
     }
@@ -743,7 +724,7 @@ __global__ void __launch_bounds__(kThreads, 3) cg_pupdate_coarse_kernel(int64_t 
     if (first) {
       p[e] = z;
     } else {
-      if constexpr (WITH_X) x[e] = fma(a0, p[e], x[e]);
+      x[e] = fma(a0, p[e], x[e]);
       p[e] = fma(b0, p[e], z);
     }
   }
@@ -1184,25 +1165,11 @@ int pcg_iteration(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int 
       cg_update_kernel<S, 1, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.q.p, A.dinv, w.r.p, w.partial.p, w.scal.p,
                                                                        w.ticket.p, 1);
       PT_LAUNCH_CHECK(ctx);
-      const bool fork = ctx->tune_xfork != 0;
-      if (fork) {  // x += alpha p needs nothing from the coarse grids: it runs beside the restriction and the grid chain
-        PT_CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
-        PT_CK(cudaStreamWaitEvent(ctx->stream3, ctx->ev_fork, 0));
-        x_axpy_kernel<S><<<grid, kThreads, 0, ctx->stream3>>>(A.nn, w.p.p, x, w.scal.p);
-        PT_LAUNCH_CHECK(ctx);
-        PT_CK(cudaEventRecord(ctx->ev_join, ctx->stream3));
-      }
       PT_TRY(coarse_apply(ctx, *A.coarse, S, w.r.p));
       rho_finalize_kernel<<<1, 32, 0, ctx->stream>>>(w.scal.p, A.coarse->cdot.p, A.coarse->nlev, S);
       PT_LAUNCH_CHECK(ctx);
-      if (fork) {
-        PT_CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-        cg_pupdate_coarse_kernel<S, false><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
-                                                                               coarse_dev(*A.coarse));
-      } else {
-        cg_pupdate_coarse_kernel<S, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
-                                                                              coarse_dev(*A.coarse));
-      }
+      cg_pupdate_coarse_kernel<S><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
+                                                                      coarse_dev(*A.coarse));
       PT_LAUNCH_CHECK(ctx);
     }
   } else {
@@ -1241,8 +1208,8 @@ int pcg_start(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int prec
       PT_TRY(coarse_apply(ctx, *A.coarse, S, w.r.p));
       rho_finalize_kernel<<<1, 32, 0, ctx->stream>>>(w.scal.p, A.coarse->cdot.p, A.coarse->nlev, S);
       PT_LAUNCH_CHECK(ctx);
-      cg_pupdate_coarse_kernel<S, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 1,
-                                                                            coarse_dev(*A.coarse));
+      cg_pupdate_coarse_kernel<S><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 1,
+                                                                      coarse_dev(*A.coarse));
       PT_LAUNCH_CHECK(ctx);
     }
   } else {
