@@ -313,6 +313,28 @@ def test_twolevel_preconditioner_matches_oracle(gpu_ctx, nrhs, levels):
     dm.close()
 
 
+@pytest.mark.parametrize("levels", [0, 1])
+def test_twolevel_iteration_count_matches_restatement(gpu_ctx, levels):
+    # the preconditioner does not change the answer, so the way to check that the device builds the SAME operator as
+    # oracle/coarse_oracle.py (interpolation, Galerkin matrix, its inverse, BPX diagonals) is the iteration count
+    from oracle import coarse_oracle as cz
+    m = meshgen.synth_slab("S", interfaces_as_103=False)
+    K_raw = fo.assemble_stiffness(m.nodes, m.tets, m.region, SIGMA5)
+    is_dir, val = fo.dirichlet_nodes(m.tris, m.bcid, [(102, 0.0)], m.nn)
+    K, b = fo.apply_dirichlet_symmetric(K_raw, fo.neumann_rhs(m.nodes, m.tris, m.bcid, [(101, 10.0)]), is_dir, val)
+    K = K.tocsr()
+    M = cz.CoarsePreconditioner(K, m.nodes, is_dir, coarse_nodes=300, extra_levels=levels)
+    x_ref, it_ref = cz.pcg(K, b, M.apply, rtol=1e-10)
+    dm = dm_for(gpu_ctx, m)
+    dm.assemble(SIGMA5).bc_reset(1).neumann(101, 10.0).dirichlet(102, 0.0)
+    phi = dm.solve(precond=engine.PRECOND_TWOLEVEL, coarse_nodes=300, coarse_levels=levels, check_every=1, use_graph=0, rtol=1e-10)[0]
+    st = dm.last_stats
+    assert st["coarse_unknowns"] == M.coarse_unknowns
+    assert abs(st["iterations"] - it_ref) <= 2, (st["iterations"], it_ref)
+    assert rel(phi, x_ref) < 1e-8
+    dm.close()
+
+
 def test_twolevel_odd_rows_unstructured_and_moved_mesh(gpu_ctx):
     # odd node count (tail element of the pair kernels), Delaunay mesh (cells with few or no nodes, long edges
     # taking the slow path of the Galerkin build), then new coordinates (grids and tables are rebuilt)

@@ -172,3 +172,30 @@ def test_property_unstructured_meshes(seed, npts):
     assert np.abs(ref["J"] - np.array([0.0, 0.0, -10.0])).max() < 1e-8
     x, it, rel = cs.pcg(1e-13)
     assert np.abs(x - ref["phi"]).max() < 1e-9
+
+
+def test_coarse_grid_preconditioner_restatement():
+    """oracle/coarse_oracle.py: same answer as the direct solve, several times fewer iterations than Jacobi, and the
+    multilevel variant no worse than the two-level one (the CUDA solver's iteration counts are compared with these)."""
+    from oracle import coarse_oracle as cz
+    m = meshgen.synth_slab("S", interfaces_as_103=False)
+    K_raw = fo.assemble_stiffness(m.nodes, m.tets, m.region, SIGMA5)
+    is_dir, val = fo.dirichlet_nodes(m.tris, m.bcid, [(102, 0.0)], m.nn)
+    b = fo.neumann_rhs(m.nodes, m.tris, m.bcid, [(101, 10.0)])
+    K, b = fo.apply_dirichlet_symmetric(K_raw, b, is_dir, val)
+    K = K.tocsr()
+    ref = fo.solve_direct(K, b)
+    dinv = 1.0 / K.diagonal()
+    x_j, it_j = cz.pcg(K, b, lambda r: dinv * r)
+    counts = {}
+    for levels in (0, 1):
+        M = cz.CoarsePreconditioner(K, m.nodes, is_dir, coarse_nodes=300, extra_levels=levels)
+        assert 200 <= M.coarse_unknowns <= 450 and M.nlev == levels + 1
+        x, it = cz.pcg(K, b, M.apply)
+        assert np.abs(x - ref).max() <= 1e-8 * np.abs(ref).max()
+        counts[levels] = it
+    assert np.abs(x_j - ref).max() <= 1e-8 * np.abs(ref).max()
+    assert counts[0] * 3 < it_j and counts[1] <= counts[0]
+    # grid choice follows coarse.cu: >= 2 cells per axis, about the requested node count
+    n = cz.choose_grid(np.zeros(3), np.array([0.08, 0.06, 0.0405]), 2000.0)
+    assert (n >= 2).all() and 1500 <= np.prod(n + 1) <= 2600
