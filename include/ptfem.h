@@ -203,6 +203,14 @@ int ptfem_dist_system_create(ptfem_ctx* ctx, int64_t nloc, int64_t nhalo, const 
                              ptfem_mesh** out);
 int ptfem_dist_solve(ptfem_mesh* sys, const ptfem_solve_opts* opts, double* x_local, ptfem_solve_stats* stats,
                      double* ms_spmv, double* ms_halo, double* ms_allreduce);
+/* Coarse-grid preconditioner for the row-partitioned solve.  `replica` is this rank's full mesh on the same context with
+ * the same matrix assembled and boundary conditions set (the ranks build it anyway to cut their row blocks); its coarse
+ * spaces are prepared here if they are not yet and the block [row0, row0+nloc) of them is attached to `sys`: grids and
+ * Galerkin operators replicated, restriction / prolongation on the owned rows, the finest grid vector summed over the
+ * ranks once per iteration.  The replica may be destroyed afterwards.  Call before ptfem_dist_p2p_export.
+ * ptfem_dist_solve then preconditions with Jacobi + coarse grids for PTFEM_PRECOND_AUTO / _TWOLEVEL.
+ * PTFEM_ERR_STATE: the Galerkin matrix is singular on this mesh (keep Jacobi). */
+int ptfem_dist_coarse_attach(ptfem_mesh* sys, ptfem_mesh* replica, int64_t row0);
 /* Peer-memory transport (NVLink P2P through CUDA IPC) instead of NCCL calls inside the iteration: every rank
  * exports two IPC handles (its vector and its mailbox, 2 x 64 bytes), the launcher all-gathers them, and each
  * rank connects.  halo_src[h] = index, in the owner's local numbering, of the row halo slot h mirrors.

@@ -140,6 +140,20 @@ int prepare_systems(ptfem_mesh* m) {
 
 }  // namespace
 
+namespace ptfem {
+// coarse spaces of a rank's replica of the mesh for the row-partitioned solve (dist.cu): the defaults of
+// ptfem_solve's automatic choice, including its retry on a coarser grid
+int coarse_replica_prepare(ptfem_mesh* full) {
+  PT_TRY(prepare_systems(full));
+  if (full->nvalp != 1) return set_err(PTFEM_ERR_ARG, "the replica must hold one matrix");
+  // spaces prepared by an earlier solve of the replica on this matrix are taken as they are (the caller chose them)
+  if (full->coarse && full->coarse->geom_ok && full->coarse->matrix_epoch == full->matrix_epoch) return PTFEM_OK;
+  int rc = coarse_prepare(full, 0, -1, full->S);
+  if (rc == PTFEM_ERR_STATE) rc = coarse_prepare(full, 500, -1, full->S);
+  return rc;
+}
+}  // namespace ptfem
+
 extern "C" {
 
 const char* ptfem_last_error(void) { return g_err.c_str(); }

@@ -627,6 +627,22 @@ int dense_inverse(ptfem_ctx* ctx, double* A, int kp, int32_t* flag) {
   return PTFEM_OK;
 }
 
+// ---- row-partitioned solve (dist.cu): table of a row block, level-0 scaling after the cross-rank sum -----------
+// splits the Dirichlet bit off a copied table (the row lists are built from cells, which Dirichlet rows keep)
+__global__ void coarse_table_split_kernel(int64_t nn, double* __restrict__ ctab, uint8_t* __restrict__ isdir) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nn) return;
+  const long long cell = __double_as_longlong(ctab[4 * i + 3]);
+  isdir[i] = cell < 0 ? 1 : 0;
+  ctab[4 * i + 3] = __longlong_as_double(cell & ~kDirBit);
+}
+// y_c = binv * r_c on a diagonal-only level whose r_c was summed over the ranks by the caller
+__global__ void coarse_scale_kernel(int64_t k, const double* __restrict__ binv, const double* __restrict__ rc,
+                                    double* __restrict__ yc) {
+  const int64_t I = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (I < k) yc[I] = rc[I] * __ldg(binv + I);
+}
+
 // ---- host side ------------------------------------------------------------------------------------------------
 int build_level_geometry(ptfem_mesh* m, CoarseLevel& L) {
   ptfem_ctx* ctx = m->ctx;
@@ -890,6 +906,127 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
   if (rebuilt) cs.setup_ms = ms;
+  return PTFEM_OK;
+}
+
+
+// ---- row-partitioned solve ------------------------------------------------------------------------------------
+// The ranks of a partitioned solve each hold a replica of the mesh (they assembled it, as in a sweep) and a block of
+// rows.  The coarse spaces are those of the replica: grids, Dirichlet flags and Galerkin operators are computed on
+// every rank from the whole matrix (deterministic, hence identical everywhere, no communication) and copied; what is
+// distributed is the work that scales with the mesh - restriction and prolongation touch the owned rows only, the
+// finest grid vector is summed over the ranks (dist.cu), the grid hierarchy above it is replicated.
+int coarse_attach_rows(ptfem_mesh* sys, ptfem_mesh* full, int64_t row0) {
+  ptfem_ctx* ctx = sys->ctx;
+  if (!full->coarse || !full->coarse->geom_ok || full->coarse->matrix_epoch != full->matrix_epoch)
+    return set_err(PTFEM_ERR_STATE, "the replica's coarse spaces are not prepared for its current matrix");
+  const CoarseSpace& F = *full->coarse;
+  const int64_t nloc = sys->nn;
+  if (row0 < 0 || row0 + nloc > full->nn) return set_err(PTFEM_ERR_ARG, "row block [%lld, %lld) outside the replica", (long long)row0, (long long)(row0 + nloc));
+  if (sys->coarse) coarse_free(sys->coarse);
+  sys->coarse = new CoarseSpace();
+  CoarseSpace& cs = *sys->coarse;
+  cs.nlev = F.nlev;
+  PT_TRY(cs.ctab.alloc((size_t)nloc * 4));
+  PT_CK(cudaMemcpyAsync(cs.ctab.p, F.ctab.p + 4 * row0, (size_t)nloc * 4 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  DevBuf<uint8_t> isdir;
+  PT_TRY(isdir.alloc(nloc));
+  coarse_table_split_kernel<<<ceil_div(nloc, 256), 256, 0, ctx->stream>>>(nloc, cs.ctab.p, isdir.p);
+  PT_LAUNCH_CHECK(ctx);
+  size_t maxgrid = 1;
+  for (int l = 0; l < cs.nlev; ++l) {
+    const CoarseLevel& FL = F.lev[l];
+    CoarseLevel& L = cs.lev[l];
+    L.g = FL.g;
+    L.shift = FL.shift;
+    L.exact = FL.exact;
+    L.kp = FL.kp;
+    L.k = FL.k;
+    L.ncell = FL.ncell;
+    L.split = FL.split;     // populated cells are as dense as on the replica
+    if (l == 0) {
+      PT_TRY(build_level_geometry(sys, L));   // row list of the owned rows (most cells of the grid are empty here)
+      PT_TRY(L.part.alloc((size_t)L.ncell * L.split * 8));
+    }
+    const size_t kk = L.exact ? (size_t)L.kp : (size_t)L.k;
+    const size_t nb = L.exact ? (size_t)L.kp * L.kp : (size_t)L.k;
+    PT_TRY(L.binv.alloc(nb));
+    PT_CK(cudaMemcpyAsync(L.binv.p, FL.binv.p, nb * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (l < cs.nlev - 1) PT_TRY(L.yt.alloc(kk));
+    PT_TRY(L.rc.alloc(kk));
+    PT_TRY(L.yc.alloc(kk));
+    PT_CK(cudaMemsetAsync(L.rc.p, 0, kk * sizeof(double), ctx->stream));
+    PT_CK(cudaMemsetAsync(L.yc.p, 0, kk * sizeof(double), ctx->stream));
+    maxgrid = std::max(maxgrid, (size_t)ceil_div(kk, 256) + 1);
+    maxgrid = std::max(maxgrid, (size_t)kk / kDenseRows + 1);
+  }
+  coarse_table_flag_kernel<<<ceil_div(nloc, 256), 256, 0, ctx->stream>>>(isdir.p, nloc, cs.ctab.p);
+  PT_LAUNCH_CHECK(ctx);
+  PT_TRY(cs.ctab0.alloc((size_t)nloc * 4));
+  gather_table_kernel<<<ceil_div(nloc, 256), 256, 0, ctx->stream>>>(cs.ctab.p, cs.lev[0].rows.p, nloc, cs.ctab0.p);
+  PT_LAUNCH_CHECK(ctx);
+  PT_TRY(cs.dpart.alloc(maxgrid * 16));
+  PT_TRY(cs.cdot.alloc((size_t)kMaxCoarseLevels * 16));
+  PT_TRY(cs.ticket.alloc(4));
+  PT_CK(cudaMemsetAsync(cs.cdot.p, 0, (size_t)kMaxCoarseLevels * 16 * sizeof(double), ctx->stream));
+  PT_CK(cudaMemsetAsync(cs.ticket.p, 0, 4 * sizeof(unsigned int), ctx->stream));
+  PT_CK(cudaStreamSynchronize(ctx->stream));
+  cs.S = 1;
+  cs.geom_ok = true;
+  cs.req_nodes = F.req_nodes;
+  cs.req_levels = F.req_levels;
+  cs.setup_ms = F.setup_ms;
+  cs.generation++;
+  return PTFEM_OK;
+}
+
+// owned rows -> finest grid: rc_out[k_0] = this rank's part of Z_0^T r (the caller sums over the ranks)
+int coarse_restrict_rows(ptfem_ctx* ctx, CoarseSpace& cs, const double* r, double* rc_out) {
+  CoarseLevel& L0 = cs.lev[0];
+  const int64_t ntask = L0.ncell * L0.split;
+  const int grid = (int)std::min<int64_t>((ntask + 7) / 8, (int64_t)ctx->sm_count * 32);
+  restrict_cell_kernel<1, true><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p, r,
+                                                                L0.part.p);
+  PT_LAUNCH_CHECK(ctx);
+  const int ngrid = std::min(ceil_div(L0.k, 256), 4 * ctx->sm_count);
+  coarse_node_kernel<1, false><<<ngrid, 256, 0, ctx->stream>>>(L0.g, L0.k, L0.split, L0.part.p, nullptr, rc_out, nullptr, nullptr,
+                                                               nullptr, nullptr);
+  PT_LAUNCH_CHECK(ctx);
+  return PTFEM_OK;
+}
+
+// lev[0].rc holds the summed Z_0^T r (and, when scaled0, lev[0].yc = binv_0 r_c): the replicated grid hierarchy
+int coarse_grids_apply(ptfem_ctx* ctx, CoarseSpace& cs, bool scaled0) {
+  for (int l = 0; l < cs.nlev; ++l) {
+    CoarseLevel& L = cs.lev[l];
+    double* cdot = cs.cdot.p + (size_t)l * 16;
+    const int ngrid = std::min(ceil_div(L.k, 256), 4 * ctx->sm_count);
+    if (l == 0) {
+      if (!L.exact && !scaled0) {
+        coarse_scale_kernel<<<ceil_div(L.k, 256), 256, 0, ctx->stream>>>(L.k, L.binv.p, L.rc.p, L.yc.p);
+        PT_LAUNCH_CHECK(ctx);
+      }
+    } else {
+      if (L.exact)
+        grid_restrict_kernel<1, false><<<ngrid, 256, 0, ctx->stream>>>(L.g, L.k, cs.lev[l - 1].rc.p, nullptr, L.rc.p, L.yc.p,
+                                                                       cs.dpart.p, cdot, cs.ticket.p);
+      else
+        grid_restrict_kernel<1, true><<<ngrid, 256, 0, ctx->stream>>>(L.g, L.k, cs.lev[l - 1].rc.p, L.binv.p, L.rc.p, L.yc.p,
+                                                                      cs.dpart.p, cdot, cs.ticket.p);
+      PT_LAUNCH_CHECK(ctx);
+    }
+    if (L.exact) {
+      coarse_dense_kernel<1><<<L.kp / kDenseRows, 256, 0, ctx->stream>>>(L.kp, L.binv.p, L.rc.p, L.yc.p, cs.dpart.p, cdot,
+                                                                        cs.ticket.p);
+      PT_LAUNCH_CHECK(ctx);
+    }
+  }
+  for (int l = cs.nlev - 2; l >= 0; --l) {
+    CoarseLevel& L = cs.lev[l];
+    const double* ytc = (l + 1 == cs.nlev - 1) ? cs.lev[l + 1].yc.p : cs.lev[l + 1].yt.p;
+    grid_prolong_kernel<1><<<ceil_div(L.k, 256), 256, 0, ctx->stream>>>(cs.lev[l + 1].g, L.k, L.yc.p, ytc, L.yt.p);
+    PT_LAUNCH_CHECK(ctx);
+  }
   return PTFEM_OK;
 }
 

@@ -127,6 +127,33 @@ __device__ __forceinline__ int64_t coarse_node(const CoarseGrid& g, const int (&
   return (int64_t)(c[0] + (a & 1)) + (int64_t)(g.n[0] + 1) * ((c[1] + ((a >> 1) & 1)) + (int64_t)(g.n[1] + 1) * (c[2] + (a >> 2)));
 }
 
+// (Z y)[row], systems s .. s+NS-1 (y = sum of all levels on the finest grid); raw = the row's table entry
+template <int S, int NS>
+__device__ __forceinline__ void coarse_prolong(const CoarseDev& cd, const CoarseRaw& raw, int s, double (&out)[NS]) {
+  int c[3];
+  double t[3], w[8];
+  const double live = coarse_row_decode(raw, cd.shift, c, t) ? 1.0 : 0.0;
+  coarse_weights(t, w);
+  const int64_t n0 = c[0] + (int64_t)cd.nx1 * (c[1] + (int64_t)cd.ny1 * c[2]);
+  double acc[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) acc[k] = 0.0;
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int64_t node = n0 + (a & 1) + (int64_t)cd.nx1 * (((a >> 1) & 1) + (int64_t)cd.ny1 * (a >> 2));
+    const double* y = cd.y + (size_t)node * S + s;
+    if constexpr (NS == 2) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(y));
+      acc[0] = fma(w[a], v.x, acc[0]);
+      acc[1] = fma(w[a], v.y, acc[1]);
+    } else {
+      acc[0] = fma(w[a], __ldg(y), acc[0]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NS; ++k) out[k] = acc[k] * live;
+}
+
 namespace ptfem {
 // (re)builds what is stale: grids + sorted row lists (mesh coordinates / requested size changed) and the Galerkin
 // operators (matrix changed).  target_nodes: unknowns of the exact level (0 = default); extra_levels: finer
@@ -136,4 +163,10 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S);
 int coarse_apply(ptfem_ctx* ctx, CoarseSpace& cs, int S, const double* r);
 CoarseDev coarse_dev(const CoarseSpace& cs);
 void coarse_free(CoarseSpace* cs);
+// row-partitioned solve (dist.cu): coarse spaces of a row block [row0, row0 + sys->nn) taken from the rank's replica
+// of the mesh, restriction of the owned rows, and the replicated grid hierarchy (one right-hand side)
+int coarse_replica_prepare(ptfem_mesh* full);   // api.cu
+int coarse_attach_rows(ptfem_mesh* sys, ptfem_mesh* full, int64_t row0);
+int coarse_restrict_rows(ptfem_ctx* ctx, CoarseSpace& cs, const double* r, double* rc_out);
+int coarse_grids_apply(ptfem_ctx* ctx, CoarseSpace& cs, bool scaled0);
 }  // namespace ptfem

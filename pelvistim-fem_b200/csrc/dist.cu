@@ -12,6 +12,11 @@
 //   (gamma, delta, rr) = (r.u, w.u, r.r)  -> ncclAllReduce(3 doubles)
 //   beta = gamma/gamma_old ; alpha = gamma / (delta - beta gamma / alpha_old)        (one tiny kernel)
 //
+// With the coarse-grid preconditioner attached (ptfem_dist_coarse_attach) u = D^-1 r + sum_l Z_l B_l Z_l^T r: every rank
+// restricts its own rows to the finest grid, the grid vector (k_0 doubles, ~1 MB on the 20 M-tet slab) is summed over
+// the ranks - ncclAllReduce, or with peer memory one kernel in which every rank adds up all ranks' buffers in rank
+// order - the grid hierarchy above it is replicated, and each rank interpolates back to its rows.
+//
 // The iteration is captured once into a CUDA graph (NCCL calls included) and replayed, so launch
 // latency does not bound the strong-scaled case.  NCCL is loaded with dlopen (the path comes from
 // the Python host, which knows where torch's bundled libnccl lives).
@@ -19,6 +24,7 @@
 
 #include <cmath>
 
+#include "coarse.cuh"
 #include "solver.cuh"
 
 using namespace ptfem;
@@ -256,13 +262,17 @@ struct Mail {
   unsigned long long iter;                    // local: iterations started (written by the update kernel)
   unsigned long long err;                     // local: a bounded wait timed out
   unsigned long long nred;                    // local: reductions started (sequence number of the mailbox protocol)
-  unsigned long long pad[5];
+  unsigned long long xred;                    // local: coarse-grid sums started (sequence number of the exchange buffers)
+  unsigned long long pad[4];
   unsigned long long ready_from[kMaxRanks];   // ready_from[q] = k : rank q's u of iteration k is complete (pushed by q)
+  unsigned long long xready_from[kMaxRanks];  // xready_from[q] = n : rank q's exchange buffer of coarse sum n is complete
   MailBox box[2][kMaxRanks];                  // box[k & 1][q] : rank q's partial sums of iteration k (pushed by q)
 };
 struct PeerTable {
   Mail* mail[kMaxRanks];       // every rank's mailbox (own entry = local pointer)
   const double* u[kMaxRanks];  // neighbours' u vectors, indexed by rank (null when not a neighbour)
+  const double* xch[kMaxRanks];// every rank's coarse exchange area [2][xstride] (behind its mailbox; null without coarse grids)
+  int64_t xstride;
   int32_t nbr_rank[kMaxRanks];
   int32_t nnbr, rank, nranks;
 };
@@ -333,8 +343,18 @@ __device__ void mailbox_allreduce(const double loc[3], const PeerTable& pt, doub
   scal[D_ALPHA] = alpha; scal[D_BETA] = beta; scal[D_GAMMA_OLD] = gamma;
 }
 
-// update + "u is ready" signal.  first: x = 0, r = b, u = D^-1 b, p = s = 0.
-__global__ void __launch_bounds__(kT) p2p_update_kernel(int64_t n, int first, const double* __restrict__ b,
+// one thread: "u of the next iteration is complete" into every neighbour's mailbox
+__device__ __forceinline__ void signal_u_ready(const PeerTable& pt) {
+  __threadfence_system();
+  Mail* me = pt.mail[pt.rank];
+  const unsigned long long k = me->iter + 1;
+  me->iter = k;
+  for (int j = 0; j < pt.nnbr; ++j) st_release_sys(&pt.mail[pt.nbr_rank[j]]->ready_from[pt.rank], k);
+}
+
+// update + "u is ready" signal (signal = 0: u is completed by the coarse-grid kernels that follow, which signal).
+// first: x = 0, r = b, u = D^-1 b, p = s = 0.
+__global__ void __launch_bounds__(kT) p2p_update_kernel(int64_t n, int first, int signal, const double* __restrict__ b,
                                                         const double* scal /* aliases scal_out */, const double* __restrict__ dinv,
                                                         const double* __restrict__ w, double* __restrict__ p,
                                                         double* __restrict__ s, double* __restrict__ x,
@@ -396,12 +416,56 @@ __global__ void __launch_bounds__(kT) p2p_update_kernel(int64_t n, int first, co
       scal_out[D_LOC_G + threadIdx.x] = t;
     }
   }
+  if (threadIdx.x == 0 && signal) signal_u_ready(pt);
+}
+
+// ---- coarse grids in the partitioned solve -------------------------------------------------------------------
+// u += Z y on the owned rows (y = sum of all levels on the finest grid); signal: last CTA announces u (peer memory)
+__global__ void __launch_bounds__(kT) dist_zadd_kernel(int64_t n, CoarseDev cd, double* __restrict__ u, PeerTable pt, int signal,
+                                                       unsigned int* __restrict__ ticket) {
+  const int64_t stride = (int64_t)gridDim.x * kT;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < n; i += stride) {
+    double c0[1];
+    coarse_prolong<1, 1>(cd, coarse_row_load(cd.ctab, i), 0, c0);
+    u[i] += c0[0];
+  }
+  if (!signal) return;
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) signal_u_ready(pt);
+}
+
+// one thread: this rank's exchange buffer of the next coarse sum is complete -> every other rank's mailbox
+__global__ void p2p_coarse_signal_kernel(PeerTable pt) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  __threadfence_system();
+  Mail* me = pt.mail[pt.rank];
+  const unsigned long long seq = me->xred + 1;
+  me->xred = seq;
+  for (int q = 0; q < pt.nranks; ++q)
+    if (q != pt.rank) st_release_sys(&pt.mail[q]->xready_from[pt.rank], seq);
+}
+
+// r_c = sum over the ranks (in rank order: identical on all ranks) of their exchange buffers, read straight out of
+// the peers' memory; binv: y_c = binv r_c (diagonal-only finest level)
+__global__ void __launch_bounds__(kT) p2p_coarse_reduce_kernel(int64_t k, int par, const double* __restrict__ binv,
+                                                               double* __restrict__ rc, double* __restrict__ yc, PeerTable pt) {
+  Mail* me = pt.mail[pt.rank];
   if (threadIdx.x == 0) {
-    __threadfence_system();
-    Mail* me = pt.mail[pt.rank];
-    const unsigned long long k = me->iter + 1;
-    me->iter = k;
-    for (int j = 0; j < pt.nnbr; ++j) st_release_sys(&pt.mail[pt.nbr_rank[j]]->ready_from[pt.rank], k);
+    const unsigned long long seq = me->xred;   // bumped by the signal kernel just before this launch
+    for (int q = 0; q < pt.nranks; ++q)
+      if (q != pt.rank && !wait_ge(&me->xready_from[q], seq, &me->err)) break;
+  }
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * kT;
+  for (int64_t I = (int64_t)blockIdx.x * kT + threadIdx.x; I < k; I += stride) {
+    double v = 0.0;
+    for (int q = 0; q < pt.nranks; ++q) v += ld_volatile_f64(pt.xch[q] + (size_t)par * pt.xstride + I);
+    rc[I] = v;
+    if (binv) yc[I] = v * __ldg(binv + I);
   }
 }
 
@@ -487,7 +551,7 @@ struct DistState {
   bool p2p = false;
   DevBuf<Mail> mail;
   DevBuf<int32_t> halo_src, recv_ptr_dev;
-  PeerTable pt;
+  PeerTable pt{};
   std::vector<void*> opened;   // cudaIpcOpenMemHandle mappings to close
   // fused peer-memory SpMV: per halo slot the neighbour address, per neighbour the local ready flag
   DevBuf<const double*> halo_ptr;
@@ -495,6 +559,14 @@ struct DistState {
   DevBuf<double> partial2;
   PcgWork spmv_work;           // partial / scal / ticket of the SpMV's fused dot
   bool fused = false;
+  // coarse-grid preconditioner (ptfem_dist_coarse_attach)
+  bool coarse = false;         // attached
+  bool use_coarse = false;     // this solve applies it
+  bool graph_coarse = false;   // what the captured graph applies
+  int64_t xk = 0;              // unknowns of the finest grid = length of one exchange buffer
+  int64_t xstride = 0;
+  double* xch = nullptr;       // own exchange area [2][xstride] behind the mailbox (peer memory)
+  unsigned long long xseq = 0; // coarse sums enqueued so far (host copy of Mail::xred)
 };
 
 }  // namespace
@@ -567,11 +639,40 @@ static int dist_reduce(ptfem_mesh* m, DistState& d, int first) {
   return PTFEM_OK;
 }
 
+// u (= D^-1 r on entry) += sum_l Z_l B_l Z_l^T r
+static int dist_coarse_add(ptfem_mesh* m, DistState& d) {
+  ptfem_ctx* ctx = m->ctx;
+  CoarseSpace& cs = *m->coarse;
+  CoarseLevel& L0 = cs.lev[0];
+  if (d.p2p) {
+    const int par = (int)((d.xseq + 1) & 1);
+    PT_TRY(coarse_restrict_rows(ctx, cs, d.r.p, d.xch + (size_t)par * d.xstride));
+    p2p_coarse_signal_kernel<<<1, 32, 0, ctx->stream>>>(d.pt);
+    PT_LAUNCH_CHECK(ctx);
+    d.xseq++;
+    const int g = std::min(ceil_div(L0.k, kT), 2 * ctx->sm_count);
+    p2p_coarse_reduce_kernel<<<g, kT, 0, ctx->stream>>>(L0.k, par, L0.exact ? nullptr : L0.binv.p, L0.rc.p, L0.yc.p, d.pt);
+    PT_LAUNCH_CHECK(ctx);
+    PT_TRY(coarse_grids_apply(ctx, cs, !L0.exact));
+  } else {
+    PT_TRY(coarse_restrict_rows(ctx, cs, d.r.p, L0.rc.p));
+    if (ctx->nranks > 1) {
+      NcclApi* api = ctx->nccl;
+      PT_NCCL(api, api->AllReduce(L0.rc.p, L0.rc.p, (size_t)L0.k, kNcclFloat64, kNcclSum, (ncclComm_t)ctx->comm, ctx->stream));
+    }
+    PT_TRY(coarse_grids_apply(ctx, cs, false));
+  }
+  dist_zadd_kernel<<<dist_grid(ctx, m->nloc), kT, 0, ctx->stream>>>(m->nloc, coarse_dev(cs), d.u.p, d.pt, d.p2p ? 1 : 0, d.ticket.p);
+  PT_LAUNCH_CHECK(ctx);
+  return PTFEM_OK;
+}
+
 static int dist_iteration(ptfem_mesh* m, DistState& d) {
   ptfem_ctx* ctx = m->ctx;
   dist_update_kernel<<<dist_grid(ctx, m->nloc), kT, 0, ctx->stream>>>(m->nloc, d.scal.p, m->dinv.p, d.w.p, d.p.p, d.s.p, d.x.p,
                                                                       d.r.p, d.u.p);
   PT_LAUNCH_CHECK(ctx);
+  if (d.use_coarse) PT_TRY(dist_coarse_add(m, d));
   PT_TRY(dist_matvec(m, d));
   return dist_reduce(m, d, 0);
 }
@@ -593,10 +694,14 @@ static int p2p_matvec_reduce(ptfem_mesh* m, DistState& d, int first) {
 }
 static int p2p_iteration(ptfem_mesh* m, DistState& d, int first) {
   ptfem_ctx* ctx = m->ctx;
-  p2p_update_kernel<<<dist_grid(ctx, m->nloc), kT, 0, ctx->stream>>>(m->nloc, first, m->b.p, d.scal.p, m->dinv.p, d.w.p, d.p.p,
-                                                                     d.s.p, d.x.p, d.r.p, d.u.p, d.pt, d.ticket.p,
-                                                                     d.partial2.p, d.scal.p);
+  p2p_update_kernel<<<dist_grid(ctx, m->nloc), kT, 0, ctx->stream>>>(m->nloc, first, d.use_coarse ? 0 : 1, m->b.p, d.scal.p,
+                                                                     m->dinv.p, d.w.p, d.p.p, d.s.p, d.x.p, d.r.p, d.u.p, d.pt,
+                                                                     d.ticket.p, d.partial2.p, d.scal.p);
   PT_LAUNCH_CHECK(ctx);
+  if (d.use_coarse) {
+    PT_TRY(dist_coarse_add(m, d));
+    return p2p_matvec_reduce(m, d, first);
+  }
   if (!d.fused) return p2p_matvec_reduce(m, d, first);
   // one kernel: wait for the neighbours' flags, w = A u with halo entries loaded straight from the neighbours'
   // memory, local w.u in the epilogue; then the single-thread mailbox all-reduce
@@ -807,10 +912,28 @@ int ptfem_dist_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* x_loca
   ptfem_solve_opts o;
   if (opts) o = *opts; else ptfem_solve_opts_default(&o);
   PT_ARG(o.rtol > 0.0 && o.maxit > 0, "rtol and maxit must be positive");
-  if (o.precond == PTFEM_PRECOND_AUTO) o.precond = PTFEM_PRECOND_JACOBI;
-  if (o.precond != PTFEM_PRECOND_JACOBI) return set_err(PTFEM_ERR_ARG, "the row-partitioned solve supports the Jacobi preconditioner only");
   DistState& d = *m->dist;
-  const int check = o.check_every > 0 ? o.check_every : 50;
+  if (o.precond == PTFEM_PRECOND_AUTO) o.precond = d.coarse ? PTFEM_PRECOND_TWOLEVEL : PTFEM_PRECOND_JACOBI;
+  if (o.precond != PTFEM_PRECOND_JACOBI && o.precond != PTFEM_PRECOND_TWOLEVEL)
+    return set_err(PTFEM_ERR_ARG, "the row-partitioned solve supports the Jacobi and the coarse-grid preconditioner only");
+  if (o.precond == PTFEM_PRECOND_TWOLEVEL && !d.coarse)
+    return set_err(PTFEM_ERR_STATE, "coarse-grid preconditioner requested but ptfem_dist_coarse_attach has not been called");
+  d.use_coarse = o.precond == PTFEM_PRECOND_TWOLEVEL;
+  if (d.use_coarse && d.p2p && !d.xch)
+    return set_err(PTFEM_ERR_STATE, "peer memory was exported before the coarse grids were attached (no exchange area)");
+  if (d.graph && d.graph_coarse != d.use_coarse) {
+    cudaGraphExecDestroy(d.graph);
+    d.graph = nullptr;
+  }
+  // the exchange buffers alternate with the parity of the coarse-sum count and the captured graph assumes it starts on
+  // an even count after the initial application: check_every is kept even, every solve starts on an even count
+  int check = o.check_every > 0 ? o.check_every : (d.use_coarse ? 10 : 50);
+  if (d.use_coarse && (check & 1)) ++check;
+  if (d.use_coarse && d.p2p && (d.xseq & 1)) {
+    p2p_coarse_signal_kernel<<<1, 32, 0, ctx->stream>>>(d.pt);
+    PT_LAUNCH_CHECK(ctx);
+    d.xseq++;
+  }
   const int grid = dist_grid(ctx, m->nloc);
   double* h = ctx->h_pinned;
 
@@ -844,6 +967,7 @@ int ptfem_dist_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* x_loca
     // x = 0, r = b, u = D^-1 r, w = A u, first scalars
     dist_init_kernel<<<grid, kT, 0, ctx->stream>>>(m->nloc, m->b.p, m->dinv.p, d.p.p, d.s.p, d.x.p, d.r.p, d.u.p);
     PT_LAUNCH_CHECK(ctx);
+    if (d.use_coarse) PT_TRY(dist_coarse_add(m, d));
     PT_TRY(dist_matvec(m, d));
     PT_TRY(dist_reduce(m, d, 1));
   }
@@ -869,9 +993,12 @@ int ptfem_dist_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* x_loca
         int rc = PTFEM_OK;
         PT_CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
         const int64_t l0 = ctx->launches;
+        const unsigned long long x0 = d.xseq;
         for (int k = 0; k < check && rc == PTFEM_OK; ++k) rc = p2p ? p2p_iteration(m, d, 0) : dist_iteration(m, d);
         d.graph_launches = ctx->launches - l0;
         ctx->launches = l0;
+        d.xseq = x0;            // captured, not run
+        d.graph_coarse = d.use_coarse;
         cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
         if (rc) return rc;
         if (ce != cudaSuccess) return set_err(PTFEM_ERR_CUDA, "graph capture of the distributed iteration failed: %s", cudaGetErrorString(ce));
@@ -882,6 +1009,7 @@ int ptfem_dist_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* x_loca
       }
       PT_CK(cudaGraphLaunch(d.graph, ctx->stream));
       ctx->launches += d.graph_launches;
+      if (d.use_coarse && p2p) d.xseq += (unsigned long long)check;
     } else {
       for (int k = 0; k < n_it; ++k) PT_TRY(p2p ? p2p_iteration(m, d, 0) : dist_iteration(m, d));
     }
@@ -953,8 +1081,26 @@ int ptfem_dist_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* x_loca
     stats->true_rel_residual = rel;
     stats->solve_ms = ms;
     stats->spmv_ms = t_spmv / reps;
+    stats->setup_ms = 0.0;
+    stats->precond = o.precond;
+    stats->coarse_unknowns = d.use_coarse ? (int32_t)m->coarse->lev[m->coarse->nlev - 1].k : 0;
   }
   if (!converged) return set_err(PTFEM_ERR_NOCONV, "distributed PCG did not reach rtol=%g in %d iterations (rel. residual %.3e)", o.rtol, it, rel);
+  return PTFEM_OK;
+}
+
+int ptfem_dist_coarse_attach(ptfem_mesh* m, ptfem_mesh* full, int64_t row0) {
+  PT_ARG(m && m->is_dist && m->dist, "not a distributed system");
+  PT_ARG(full && !full->is_dist && full->ctx == m->ctx, "the replica must be a mesh of the same context");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  DistState& d = *m->dist;
+  if (d.mail.p) return set_err(PTFEM_ERR_STATE, "attach the coarse grids before ptfem_dist_p2p_export (the exchange area is part of the export)");
+  PT_TRY(coarse_replica_prepare(full));
+  PT_TRY(coarse_attach_rows(m, full, row0));
+  d.coarse = true;
+  d.xk = m->coarse->lev[0].k;
+  if (d.graph) cudaGraphExecDestroy(d.graph);
+  d.graph = nullptr;
   return PTFEM_OK;
 }
 
@@ -963,9 +1109,17 @@ int ptfem_dist_p2p_export(ptfem_mesh* m, void* handles128) {
   PT_CK(cudaSetDevice(m->ctx->device));
   DistState& d = *m->dist;
   if (!d.mail.p) {
-    PT_TRY(d.mail.alloc(1));
-    PT_CK(cudaMemsetAsync(d.mail.p, 0, sizeof(Mail), m->ctx->stream));
+    // one allocation = one IPC handle: the coarse exchange area [2][xstride] lives behind the mailbox
+    size_t nmail = 1;
+    if (d.coarse) {
+      d.xstride = (d.xk + 15) & ~(int64_t)15;
+      nmail += (2 * (size_t)d.xstride * sizeof(double) + sizeof(Mail) - 1) / sizeof(Mail);
+    }
+    PT_TRY(d.mail.alloc(nmail));
+    PT_CK(cudaMemsetAsync(d.mail.p, 0, nmail * sizeof(Mail), m->ctx->stream));
     PT_CK(cudaStreamSynchronize(m->ctx->stream));
+    d.xch = d.coarse ? reinterpret_cast<double*>(d.mail.p + 1) : nullptr;
+    d.xseq = 0;
   }
   cudaIpcMemHandle_t h[2];
   PT_CK(cudaIpcGetMemHandle(&h[0], d.u.p));
@@ -988,6 +1142,7 @@ int ptfem_dist_p2p_connect(ptfem_mesh* m, int32_t nranks, const void* all_handle
   pt.rank = ctx->rank;
   pt.nranks = nranks;
   pt.nnbr = m->nnbr;
+  pt.xstride = d.xstride;
   if (m->nnbr > kMaxRanks) return set_err(PTFEM_ERR_ARG, "too many neighbours");
   for (int k = 0; k < m->nnbr; ++k) pt.nbr_rank[k] = m->nbr_rank[k];
   const cudaIpcMemHandle_t* hs = reinterpret_cast<const cudaIpcMemHandle_t*>(all_handles);
@@ -995,12 +1150,14 @@ int ptfem_dist_p2p_connect(ptfem_mesh* m, int32_t nranks, const void* all_handle
     if (q == ctx->rank) {
       pt.mail[q] = d.mail.p;
       pt.u[q] = d.u.p;
+      pt.xch[q] = d.xch;
       continue;
     }
     void* pm = nullptr;
     PT_CK(cudaIpcOpenMemHandle(&pm, hs[2 * q + 1], cudaIpcMemLazyEnablePeerAccess));
     d.opened.push_back(pm);
     pt.mail[q] = reinterpret_cast<Mail*>(pm);
+    pt.xch[q] = d.xch ? reinterpret_cast<const double*>(pt.mail[q] + 1) : nullptr;   // every rank attaches the same grids
     bool is_nbr = false;
     for (int k = 0; k < m->nnbr; ++k) is_nbr = is_nbr || m->nbr_rank[k] == q;
     if (is_nbr) {

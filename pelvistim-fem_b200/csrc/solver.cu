@@ -637,33 +637,6 @@ __global__ void rho_finalize_kernel(double* __restrict__ scal, const double* __r
   scal[SC_BETA * kMaxSys + s] = rho_old > 0.0 ? rho / rho_old : 0.0;
 }
 
-// (Z y)[row], systems s .. s+NS-1 (y = sum of all levels on the finest grid); raw = the row's table entry
-template <int S, int NS>
-__device__ __forceinline__ void coarse_prolong(const CoarseDev& cd, const CoarseRaw& raw, int s, double (&out)[NS]) {
-  int c[3];
-  double t[3], w[8];
-  const double live = coarse_row_decode(raw, cd.shift, c, t) ? 1.0 : 0.0;
-  coarse_weights(t, w);
-  const int64_t n0 = c[0] + (int64_t)cd.nx1 * (c[1] + (int64_t)cd.ny1 * c[2]);
-  double acc[NS];
-#pragma unroll
-  for (int k = 0; k < NS; ++k) acc[k] = 0.0;
-#pragma unroll
-  for (int a = 0; a < 8; ++a) {
-    const int64_t node = n0 + (a & 1) + (int64_t)cd.nx1 * (((a >> 1) & 1) + (int64_t)cd.ny1 * (a >> 2));
-    const double* y = cd.y + (size_t)node * S + s;
-    if constexpr (NS == 2) {
-      const double2 v = __ldg(reinterpret_cast<const double2*>(y));
-      acc[0] = fma(w[a], v.x, acc[0]);
-      acc[1] = fma(w[a], v.y, acc[1]);
-    } else {
-      acc[0] = fma(w[a], __ldg(y), acc[0]);
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < NS; ++k) out[k] = acc[k] * live;
-}
-
 // p-update of the two-level preconditioner (one shared matrix): z = dinv r + Z y.  The table entry of the next trip is
 // loaded one trip ahead: the table -> grid node -> y chain is two dependent loads deep and ncu shows the kernel
 // waiting on exactly that chain (long-scoreboard stalls on the first use of the table entry).

@@ -11,8 +11,14 @@ import numpy as np
 from . import engine, partition
 
 
-def partitioned_solve(ctx, mesh, sigma_by_body, dirichlet, neumann, rank, world, check=True, transport="p2p", **opts):
-    """Returns dict(x_local, row0, stats, timings, nloc, nhalo, rel_err_vs_single)."""
+def partitioned_solve(ctx, mesh, sigma_by_body, dirichlet, neumann, rank, world, check=True, transport="p2p", coarse=True,
+                      force_p2p=False, **opts):
+    """Returns dict(x_local, row0, stats, timings, nloc, nhalo, rel_err_vs_single).
+
+    ``coarse``: precondition with Jacobi + geometric coarse grids (taken from this rank's replica of the mesh; the finest
+    grid vector is summed over the ranks once per iteration) when the mesh is large enough for the single-GPU solver to
+    choose them too (>= 100 k nodes); Jacobi otherwise.  ``force_p2p``: use the peer-memory kernels even with one rank
+    (tests)."""
     import torch.distributed as dist
     dm = ctx.mesh(mesh.nodes, mesh.tets, mesh.region, mesh.tris, mesh.bcid)
     dm.assemble(sigma_by_body).bc_reset(1)
@@ -30,16 +36,31 @@ def partitioned_solve(ctx, mesh, sigma_by_body, dirichlet, neumann, rank, world,
         single_stats = dm.last_stats
         dm.solve(to_host=False, rtol=opts.get("rtol", 1e-10), precond=engine.PRECOND_AUTO)
         single_auto_stats = dm.last_stats
-    dm.close()
     blk = partition.local_block(rowptr, col, val, b, rank, world)
-    used = transport if world > 1 else "single"
+    want_coarse = bool(coarse) and mesh.nn >= 100000
+    state = dict(coarse=False, note=None)
+
+    def make_system():
+        """This rank's block; with the coarse grids attached when asked for and possible (every rank decides alike: the
+        replicas are identical).  Must run before the peer-memory export."""
+        sysm = engine.DistSystem(ctx, blk)
+        state["coarse"] = False
+        if want_coarse:
+            try:
+                sysm.coarse_attach(dm, blk.row0)
+                state["coarse"] = True
+            except engine.PtfemError as e:
+                state["note"] = f"coarse grids not attached ({e}); Jacobi"
+        return sysm
+
+    used = transport if (world > 1 or force_p2p) else "single"
     ds = None
-    if world > 1 and transport == "p2p":
+    if (world > 1 or force_p2p) and transport == "p2p":
         # peer memory needs CUDA IPC between the ranks' processes; every rank must agree on whether it works
         ok = 1
         try:
             engine.dist_init(ctx, None, rank, world)
-            ds = engine.DistSystem(ctx, blk)
+            ds = make_system()
             handles = [None] * world
             dist.all_gather_object(handles, ds.p2p_export())
             ds.p2p_connect(handles, partition.halo_sources(blk, n=rowptr.shape[0] - 1))
@@ -63,18 +84,22 @@ def partitioned_solve(ctx, mesh, sigma_by_body, dirichlet, neumann, rank, world,
         dist.broadcast_object_list(ids, src=0)
         engine.dist_init(ctx, ids[0], rank, world)
     if ds is None:
-        ds = engine.DistSystem(ctx, blk)
+        ds = make_system()
+    dm.close()
     t0 = time.perf_counter()
     x = ds.solve(**opts)
     wall = time.perf_counter() - t0
     out = dict(x_local=x, row0=blk.row0, nloc=blk.nloc, nhalo=blk.nhalo, stats=ds.last_stats, timings=ds.timings, wall_s=wall,
-               transport=used)
+               transport=used, coarse=state["coarse"], coarse_note=state["note"])
     if check:
         ref = phi_single[blk.row0:blk.row0 + blk.nloc]
         out["rel_err_vs_single"] = float(np.abs(x - ref).max() / max(np.abs(phi_single).max(), 1e-300))
         out["single_gpu_ms"] = single_stats["solve_ms"]
         out["single_gpu_iterations"] = single_stats["iterations"]
         out["single_gpu_auto_ms"] = single_auto_stats["solve_ms"] + single_auto_stats["setup_ms"]
+        out["single_gpu_auto_solve_ms"] = single_auto_stats["solve_ms"]
+        out["single_gpu_auto_setup_ms"] = single_auto_stats["setup_ms"]
+        out["single_gpu_auto_precond"] = single_auto_stats["precond"]
         out["single_gpu_auto_iterations"] = single_auto_stats["iterations"]
     if world > 1:
         dist.barrier()          # nobody unmaps peer memory while a neighbour may still read it

@@ -112,6 +112,7 @@ def load_library():
         "ptfem_dist_finalize": (C.c_int, [vp]),
         "ptfem_dist_system_create": (C.c_int, [vp, i64, i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, P(vp)]),
         "ptfem_dist_solve": (C.c_int, [vp, P(SolveOpts), vp, P(SolveStats), P(dbl), P(dbl), P(dbl)]),
+        "ptfem_dist_coarse_attach": (C.c_int, [vp, vp, i64]),
         "ptfem_dist_p2p_export": (C.c_int, [vp, vp]),
         "ptfem_dist_p2p_connect": (C.c_int, [vp, i32, vp, vp]),
     }
@@ -498,6 +499,12 @@ class DistSystem:
                                                   _ptr(arrs[5]) if nnbr else None, _ptr(arrs[6]) if nnbr else None,
                                                   _ptr(arrs[7]) if nnbr else None, C.byref(h)))
         self._h = h
+
+    def coarse_attach(self, replica, row0):
+        """Attach the coarse-grid preconditioner: ``replica`` is this rank's full :class:`DeviceMesh` with the same matrix
+        and boundary conditions; rows ``[row0, row0 + nloc)`` of its coarse spaces are taken (``ptfem_dist_coarse_attach``).
+        Call before :meth:`p2p_export`."""
+        self.ctx._ck(self.lib.ptfem_dist_coarse_attach(self._h, replica._h, int(row0)))
 
     def p2p_export(self) -> bytes:
         buf = C.create_string_buffer(128)

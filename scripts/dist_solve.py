@@ -1,5 +1,8 @@
 """Row-partitioned solve of one synthetic mesh over the ranks of a torchrun launch (or 1 rank).
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/dist_solve.py M
+    ... scripts/dist_solve.py L p2p jacobi          # transport, preconditioner (auto = Jacobi + coarse grids | jacobi)
+    PTFEM_SAME_GPU=1 ... --nproc-per-node 2 scripts/dist_solve.py M p2p   # all ranks on GPU 0 (CUDA IPC between processes of
+                                                    # one device; time-sliced, slow - a protocol check when one GPU is all there is)
 """
 import json, os, sys
 sys.path.insert(0, ".")
@@ -11,20 +14,27 @@ from pelvistim_fem_b200 import engine, meshgen, distsolve
 
 size = sys.argv[1] if len(sys.argv) > 1 else "M"
 transport = sys.argv[2] if len(sys.argv) > 2 else "p2p"
+precond = sys.argv[3] if len(sys.argv) > 3 else "auto"
+same_gpu = os.environ.get("PTFEM_SAME_GPU", "0") == "1"
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+if same_gpu:
+    local = 0
 torch.cuda.set_device(local)
-if world > 1:
+if world > 1 and not same_gpu:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 else:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29512")
-    dist.init_process_group("gloo", rank=0, world_size=1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
 mesh = meshgen.synth_slab(size)
 sig = {1: 0.35, 2: 0.04, 3: 0.001, 4: 0.005, 5: 0.005}
 ctx = engine.Context(local)
-res = distsolve.partitioned_solve(ctx, mesh, sig, [(102, 0.0)], [(101, 15.975)], rank, world, check=True, transport=transport, rtol=1e-10)
-line = dict(rank=rank, world=world, size=size, transport=transport, nloc=res["nloc"], nhalo=res["nhalo"], iterations=res["stats"]["iterations"],
+res = distsolve.partitioned_solve(ctx, mesh, sig, [(102, 0.0)], [(101, 15.975)], rank, world, check=True, transport=transport,
+                                  coarse=precond == "auto", force_p2p=os.environ.get("PTFEM_FORCE_P2P", "0") == "1", rtol=1e-10)
+line = dict(rank=rank, world=world, size=size, transport=res["transport"], coarse=res["coarse"], coarse_note=res["coarse_note"],
+            nloc=res["nloc"], nhalo=res["nhalo"], iterations=res["stats"]["iterations"],
             solve_ms=res["stats"]["solve_ms"], ms_per_iter=res["stats"]["solve_ms"] / max(res["stats"]["iterations"], 1),
             rel_err_vs_single=res["rel_err_vs_single"], single_gpu_ms=res["single_gpu_ms"], single_gpu_iterations=res["single_gpu_iterations"],
+            single_gpu_coarse_solve_ms=res["single_gpu_auto_solve_ms"], single_gpu_coarse_iterations=res["single_gpu_auto_iterations"],
             **res["timings"])
 print(json.dumps(line), flush=True)
 assert res["rel_err_vs_single"] < 1e-6, res["rel_err_vs_single"]

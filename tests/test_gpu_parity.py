@@ -566,6 +566,53 @@ def test_row_partitioned_path_single_rank(gpu_ctx):
     ds.close()
 
 
+@pytest.mark.parametrize("levels", [0, 1])
+def test_row_partitioned_path_coarse_grids_single_rank(gpu_ctx, levels):
+    # the coarse-grid preconditioner of the partitioned solve (block of the replica's coarse spaces, restriction on the
+    # owned rows, replicated grid hierarchy) with one rank: same answer and about the same iteration count as the
+    # single-GPU solver with the same grids; then the peer-memory kernels with this rank as its own only peer
+    from pelvistim_fem_b200 import partition
+    m = meshgen.synth_slab("S", interfaces_as_103=False)
+    ref = fo.solve_case(m, SIGMA5, [(102, 0.0)], [(101, 15.975)], recover=None)["phi"]
+    dm = dm_for(gpu_ctx, m)
+    dm.assemble(SIGMA5).bc_reset(1).neumann(101, 15.975).dirichlet(102, 0.0)
+    rowptr, col = dm.get_pattern()
+    blk = partition.local_block(rowptr, col, dm.get_values(0, True), dm.get_rhs(0), 0, 1)
+    dm.solve(precond=engine.PRECOND_JACOBI, rtol=1e-11)
+    it_jacobi = dm.last_stats["iterations"]
+    dm.solve(precond=engine.PRECOND_TWOLEVEL, coarse_nodes=300, coarse_levels=levels, rtol=1e-11)
+    it_single, k_single = dm.last_stats["iterations"], dm.last_stats["coarse_unknowns"]
+    ds = engine.DistSystem(gpu_ctx, blk)
+    ds.coarse_attach(dm, 0)
+    x = ds.solve(rtol=1e-11)
+    st = ds.last_stats
+    assert st["converged"] == 1 and st["precond"] == engine.PRECOND_TWOLEVEL and st["coarse_unknowns"] == k_single
+    assert rel(x, ref) < TOL_PHI
+    # single-reduction CG checks every 10 iterations: the count is the single-GPU one rounded up (+ a few for the recurrences)
+    assert st["iterations"] <= it_single + 20 and st["iterations"] * 3 < it_jacobi
+    x2 = ds.solve(rtol=1e-11, use_graph=0)
+    assert np.array_equal(x, x2)                                  # graph replay == direct launches
+    xj = ds.solve(rtol=1e-11, precond=engine.PRECOND_JACOBI)       # the attached system still solves with Jacobi alone
+    assert ds.last_stats["precond"] == engine.PRECOND_JACOBI and rel(xj, ref) < TOL_PHI
+    ds.close()
+    # peer-memory transport, one rank: mailboxes, exchange buffers and flags are this rank's own
+    engine.dist_init(gpu_ctx, None, 0, 1)
+    try:
+        dp = engine.DistSystem(gpu_ctx, blk)
+        dp.coarse_attach(dm, 0)
+        dp.p2p_connect([dp.p2p_export()], partition.halo_sources(blk, n=rowptr.shape[0] - 1))
+        for _ in range(2):      # the second solve starts on whatever parity the first left the exchange buffers in
+            xp = dp.solve(rtol=1e-11)
+            assert dp.last_stats["precond"] == engine.PRECOND_TWOLEVEL and abs(dp.last_stats["iterations"] - st["iterations"]) <= 10
+            assert rel(xp, x) < 1e-8
+        xp3 = dp.solve(rtol=1e-11, check_every=7)                   # odd request -> kept even internally
+        assert rel(xp3, ref) < TOL_PHI
+        dp.close()
+    finally:
+        engine.dist_finalize(gpu_ctx)
+    dm.close()
+
+
 def test_morton_row_order_forced(monkeypatch):
     # processing-order permutation of the streaming SpMV (auto-enabled only for incoherent numberings)
     monkeypatch.setenv("PTFEM_MORTON", "1")
