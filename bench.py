@@ -395,30 +395,33 @@ def main():
         if float(tmin[0].item()) < 1.0 or res is None:       # some rank failed
             part = {"error": err or "failed on another rank"}
         else:
-            t = t.tolist()
-            used = res["transport"]
-            with_coarse = bool(res["coarse"])
-            same_ms = res["single_gpu_auto_solve_ms"] if with_coarse else res["single_gpu_ms"]
-            same_it = res["single_gpu_auto_iterations"] if with_coarse else res["single_gpu_iterations"]
-            part = {"workload": f"synth_slab {args.size} with contact pads, one PCG solve row-partitioned over {world} GPUs, "
-                                + ("Jacobi + geometric coarse grids (restriction / prolongation on the owned rows, finest grid vector "
-                                   "summed over the ranks once per iteration, grid hierarchy replicated); " if with_coarse else "Jacobi; ")
-                                + ("peer-memory transport: halo rows pulled with direct NVLink loads, scalars and the coarse grid vector "
-                                   "reduced through exported buffers, no NCCL call in the iteration; single-reduction CG" if used == "p2p" else
-                                   "NCCL halo exchange + all-reduce per iteration, single-reduction CG"),
-                    "transport": used, "precond": "jacobi+coarse-grids" if with_coarse else "jacobi",
-                    "iterations": res["stats"]["iterations"], "solve_ms": t[1], "ms_per_iteration": t[1] / max(res["stats"]["iterations"], 1),
-                    "spmv_ms": t[2], "halo_ms": t[3], "allreduce_ms": t[4], "rows_per_rank": res["nloc"], "halo_rows": res["nhalo"],
-                    "single_gpu_same_precond_solve_ms": same_ms, "single_gpu_same_precond_iterations": same_it,
-                    "speedup_vs_1gpu": same_ms / t[1], "max_rel_err_vs_single_gpu": t[5],
-                    "single_gpu_jacobi_solve_ms": res["single_gpu_ms"], "single_gpu_jacobi_iterations": res["single_gpu_iterations"],
-                    "single_gpu_coarse_grid_solve_ms": res["single_gpu_auto_solve_ms"],
-                    "single_gpu_coarse_grid_setup_ms": res["single_gpu_auto_setup_ms"],
-                    "single_gpu_coarse_grid_iterations": res["single_gpu_auto_iterations"],
-                    "coarse_note": res["coarse_note"],
-                    "note": "speedup_vs_1gpu compares the same preconditioner on 1 and N GPUs, solve time only; the coarse-grid "
-                            "set-up (single_gpu_coarse_grid_setup_ms) runs replicated on every rank's copy of the mesh and is the "
-                            "same on 1 and N GPUs"}
+            try:
+                t = t.tolist()
+                used = res["transport"]
+                with_coarse = bool(res["coarse"])
+                same_ms = res["single_gpu_auto_solve_ms"] if with_coarse else res["single_gpu_ms"]
+                same_it = res["single_gpu_auto_iterations"] if with_coarse else res["single_gpu_iterations"]
+                part = {"workload": f"synth_slab {args.size} with contact pads, one PCG solve row-partitioned over {world} GPUs, "
+                                    + ("Jacobi + geometric coarse grids (restriction / prolongation on the owned rows, finest grid vector "
+                                       "summed over the ranks once per iteration, grid hierarchy replicated); " if with_coarse else "Jacobi; ")
+                                    + ("peer-memory transport: halo rows pulled with direct NVLink loads, scalars and the coarse grid vector "
+                                       "reduced through exported buffers, no NCCL call in the iteration; single-reduction CG" if used == "p2p" else
+                                       "NCCL halo exchange + all-reduce per iteration, single-reduction CG"),
+                        "transport": used, "precond": "jacobi+coarse-grids" if with_coarse else "jacobi",
+                        "iterations": res["stats"]["iterations"], "solve_ms": t[1], "ms_per_iteration": t[1] / max(res["stats"]["iterations"], 1),
+                        "spmv_ms": t[2], "halo_ms": t[3], "allreduce_ms": t[4], "rows_per_rank": res["nloc"], "halo_rows": res["nhalo"],
+                        "single_gpu_same_precond_solve_ms": same_ms, "single_gpu_same_precond_iterations": same_it,
+                        "speedup_vs_1gpu": same_ms / t[1], "max_rel_err_vs_single_gpu": t[5],
+                        "single_gpu_jacobi_solve_ms": res["single_gpu_ms"], "single_gpu_jacobi_iterations": res["single_gpu_iterations"],
+                        "single_gpu_coarse_grid_solve_ms": res["single_gpu_auto_solve_ms"],
+                        "single_gpu_coarse_grid_setup_ms": res["single_gpu_auto_setup_ms"],
+                        "single_gpu_coarse_grid_iterations": res["single_gpu_auto_iterations"],
+                        "coarse_note": res["coarse_note"],
+                        "note": "speedup_vs_1gpu compares the same preconditioner on 1 and N GPUs, solve time only; the coarse-grid "
+                                "set-up (single_gpu_coarse_grid_setup_ms) runs replicated on every rank's copy of the mesh and is the "
+                                "same on 1 and N GPUs"}
+            except Exception as e:  # noqa: BLE001 - reporting the extra must not cost the line either
+                part = {"error": f"{type(e).__name__}: {e}"}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
