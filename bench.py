@@ -408,7 +408,7 @@ def main():
                                        "reduced through exported buffers, no NCCL call in the iteration; single-reduction CG" if used == "p2p" else
                                        "NCCL halo exchange + all-reduce per iteration, single-reduction CG"),
                         "transport": used, "precond": "jacobi+coarse-grids" if with_coarse else "jacobi",
-                        "iterations": res["stats"]["iterations"], "solve_ms": t[1], "ms_per_iteration": t[1] / max(res["stats"]["iterations"], 1),
+                        "iterations": res["stats"]["iterations"], "solve_ms": t[1], "first_solve_ms_incl_graph_capture": res["first_solve_ms"], "ms_per_iteration": t[1] / max(res["stats"]["iterations"], 1),
                         "spmv_ms": t[2], "halo_ms": t[3], "allreduce_ms": t[4], "rows_per_rank": res["nloc"], "halo_rows": res["nhalo"],
                         "single_gpu_same_precond_solve_ms": same_ms, "single_gpu_same_precond_iterations": same_it,
                         "speedup_vs_1gpu": same_ms / t[1], "max_rel_err_vs_single_gpu": t[5],

@@ -462,8 +462,13 @@ __global__ void __launch_bounds__(kT) p2p_coarse_reduce_kernel(int64_t k, int pa
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * kT;
   for (int64_t I = (int64_t)blockIdx.x * kT + threadIdx.x; I < k; I += stride) {
+    // all loads first (a remote load is microseconds; one after the other they would add up), then the sum in rank order
+    double part[kMaxRanks];
+#pragma unroll
+    for (int q = 0; q < kMaxRanks; ++q) part[q] = q < pt.nranks ? ld_volatile_f64(pt.xch[q] + (size_t)par * pt.xstride + I) : 0.0;
     double v = 0.0;
-    for (int q = 0; q < pt.nranks; ++q) v += ld_volatile_f64(pt.xch[q] + (size_t)par * pt.xstride + I);
+#pragma unroll
+    for (int q = 0; q < kMaxRanks; ++q) v += part[q];   // + 0.0 for the unused slots changes nothing
     rc[I] = v;
     if (binv) yc[I] = v * __ldg(binv + I);
   }
