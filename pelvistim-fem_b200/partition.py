@@ -118,18 +118,22 @@ def local_spmv(blk: LocalBlock, u_full):
     return A @ u_full
 
 
-def cg_single_reduction(blk: LocalBlock, exchange, allreduce, rtol=1e-10, maxit=100000):
-    """Chronopoulos-Gear Jacobi-PCG on one rank's block.  ``exchange(u_owned) -> u_halo`` and
-    ``allreduce(vec3) -> vec3`` are the only communication.  Returns (x_owned, iterations, rel)."""
+def cg_single_reduction(blk: LocalBlock, exchange, allreduce, rtol=1e-10, maxit=100000, precond=None):
+    """Chronopoulos-Gear PCG on one rank's block.  ``exchange(u_owned) -> u_halo`` and ``allreduce(vec3) -> vec3`` are
+    the only communication of the iteration itself; ``precond(r_owned, dinv) -> u_owned`` replaces the Jacobi step
+    ``u = D^-1 r`` (it may communicate: the coarse-grid preconditioner sums its finest grid vector over the ranks, as
+    ``csrc/dist.cu`` does).  Returns (x_owned, iterations, rel)."""
     nloc = blk.nloc
     diag = np.ones(nloc)
     rows = np.repeat(np.arange(nloc), np.diff(blk.rowptr))
     on_diag = blk.col == rows
     diag[rows[on_diag]] = blk.val[on_diag]
     dinv = 1.0 / diag
+    if precond is None:
+        precond = lambda r_, dinv_: r_ * dinv_
     x = np.zeros(nloc)
     r = blk.b.copy()
-    u = r * dinv
+    u = precond(r, dinv)
     bn2 = allreduce(np.array([blk.b @ blk.b, 0.0, 0.0]))[0]
     w = local_spmv(blk, np.concatenate([u, exchange(u)]))
     g, d, rr = allreduce(np.array([r @ u, w @ u, r @ r]))
@@ -142,7 +146,7 @@ def cg_single_reduction(blk: LocalBlock, exchange, allreduce, rtol=1e-10, maxit=
         s = w + beta * s
         x += alpha * p
         r -= alpha * s
-        u = r * dinv
+        u = precond(r, dinv)
         w = local_spmv(blk, np.concatenate([u, exchange(u)]))
         g, d, rr = allreduce(np.array([r @ u, w @ u, r @ r]))
         beta = g / g_old if g_old > 0 else 0.0

@@ -113,3 +113,125 @@ def test_sweep_map_points_two_workers():
     assert [r["rank"] for r in out] == [k % 2 for k in range(7)]            # point i -> GPU i mod G
     with pytest.raises(RuntimeError, match="boom"):
         sweep.map_points(_failing_fn, [1, 2, 3, 4], gpus=2)
+
+
+# -- coarse-grid preconditioner of the partitioned solve (csrc/dist.cu: dist_coarse_add) -----------------------------
+# Restated with the oracle's interpolation matrices: every rank restricts its OWN rows to the finest grid, that grid
+# vector is summed over the ranks, the grid hierarchy above it is applied replicated (grid-to-grid transfers, exact
+# coarsest solve), and every rank interpolates back to its own rows.
+def _coarse_setup(coarse_nodes=36, extra_levels=1):
+    from oracle import coarse_oracle as cz
+    m, ref, rowptr, col, val, b = _system()
+    K = ref["K"].tocsr()
+    is_dir = np.zeros(m.nn, dtype=bool)
+    is_dir[np.unique(m.tris[m.bcid == 102])] = True
+    M = cz.CoarsePreconditioner(K, m.nodes, is_dir, coarse_nodes=coarse_nodes, extra_levels=extra_levels)
+    lo, hi = m.nodes.min(axis=0), m.nodes.max(axis=0)
+    base = cz.choose_grid(lo, hi, float(coarse_nodes))
+    # P_l: trilinear interpolation from grid l to the nodes of grid l-1 (cells halve from level to level)
+    P = [None]
+    for l in range(1, M.nlev):
+        nf = base * (1 << (M.nlev - l))
+        ext = np.where(hi - lo > 0.0, hi - lo, 1.0) * (1.0 + 1e-12)
+        ax = [lo[d] + ext[d] * np.arange(nf[d] + 1) / nf[d] for d in range(3)]
+        Z, Y, X = np.meshgrid(ax[2], ax[1], ax[0], indexing="ij")          # x fastest, as the grid nodes are numbered
+        pts = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+        P.append(cz.interpolation(pts, np.ones(pts.shape[0]), lo, hi, nf // 2))
+    return m, ref, (rowptr, col, val, b), K, M, P
+
+
+def _hierarchy(M, P, rc0):
+    """finest grid residual (summed over the ranks) -> finest grid correction carrying all levels (replicated part)."""
+    rc = [rc0]
+    for l in range(1, M.nlev):
+        rc.append(P[l].T @ rc[l - 1])
+    y = [(B @ r if B.ndim == 2 else B * r) for B, r in zip(M.B, rc)]
+    yt = y[-1]
+    for l in range(M.nlev - 2, -1, -1):
+        yt = y[l] + P[l + 1] @ yt
+    return yt
+
+
+def test_nested_grids_interpolate_exactly():
+    # what the CUDA code relies on when it touches the mesh only on the finest level: Z_l = Z_{l-1} P_l
+    m, ref, sysm, K, M, P = _coarse_setup()
+    assert M.nlev == 2
+    for l in range(1, M.nlev):
+        d = (M.Z[l] - M.Z[l - 1] @ P[l])
+        assert abs(d).max() < 1e-10            # weights are O(1); the box is widened by 1e-12 and planes snap at 1e-9
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3])
+def test_partitioned_coarse_preconditioner_equals_global(nranks):
+    m, ref, (rowptr, col, val, b), K, M, P = _coarse_setup()
+    bounds = partition.row_bounds(m.nn, nranks)
+    r = np.random.default_rng(3).standard_normal(m.nn)
+    parts = [M.Z[0][bounds[q]:bounds[q + 1]].T @ r[bounds[q]:bounds[q + 1]] for q in range(nranks)]
+    rc0 = np.sum(parts, axis=0)                                    # the one cross-rank sum of the iteration
+    assert np.abs(rc0 - M.Z[0].T @ r).max() < 1e-12 * np.abs(rc0).max()
+    yt = _hierarchy(M, P, rc0)
+    z = np.concatenate([M.dinv[bounds[q]:bounds[q + 1]] * r[bounds[q]:bounds[q + 1]] + M.Z[0][bounds[q]:bounds[q + 1]] @ yt
+                        for q in range(nranks)])
+    zg = M.apply(r)
+    assert np.abs(z - zg).max() < 1e-11 * np.abs(zg).max()
+
+
+def _gloo_coarse_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from oracle import coarse_oracle as cz
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    m, ref, (rowptr, col, val, b), K, M, P = _coarse_setup()      # replicated set-up, as on the GPUs
+    blk = partition.local_block(rowptr, col, val, b, rank, world)
+    Zloc = M.Z[0][blk.row0:blk.row0 + blk.nloc]
+
+    def allreduce(v):
+        t = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64).copy())
+        dist.all_reduce(t)
+        return t.numpy()
+
+    def exchange(u):
+        h = np.empty(blk.nhalo)
+        reqs, bufs = [], []
+        for k, qn in enumerate(blk.nbr_rank):
+            s = torch.from_numpy(np.ascontiguousarray(u[blk.send_idx[blk.send_ptr[k]:blk.send_ptr[k + 1]]]))
+            r = torch.empty(int(blk.recv_ptr[k + 1] - blk.recv_ptr[k]), dtype=torch.float64)
+            reqs.append(dist.isend(s, int(qn)))
+            reqs.append(dist.irecv(r, int(qn)))
+            bufs.append((k, r, s))
+        for rq in reqs:
+            rq.wait()
+        for k, r, _ in bufs:
+            h[blk.recv_ptr[k]:blk.recv_ptr[k + 1]] = r.numpy()
+        return h
+
+    def precond(r, dinv):
+        return dinv * r + Zloc @ _hierarchy(M, P, allreduce(Zloc.T @ r))
+
+    x, it, rel = partition.cg_single_reduction(blk, exchange, allreduce, rtol=1e-11, precond=precond)
+    _, it_jacobi, _ = partition.cg_single_reduction(blk, exchange, allreduce, rtol=1e-11)
+    _, it_serial = cz.pcg(K, ref["b"], M.apply, rtol=1e-11)
+    err = np.abs(x - ref["phi"][blk.row0:blk.row0 + blk.nloc]).max() / np.abs(ref["phi"]).max()
+    q.put((rank, it, it_jacobi, it_serial, rel, err))
+    dist.destroy_process_group()
+
+
+def test_two_process_gloo_solve_with_coarse_grids():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_coarse_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r[0] for r in res) == [0, 1]
+    for rank, it, it_jacobi, it_serial, rel, err in res:
+        assert rel <= 1e-11 and err < 1e-8
+        assert abs(it - it_serial) <= 2            # same preconditioner, same Krylov space: the partitioned count is the serial one
+        assert it * 4 < it_jacobi * 3                # a 36-node coarse grid on 2254 nodes: 101 vs 157 iterations
+    assert res[0][1] == res[1][1]
