@@ -5,9 +5,12 @@
 // partials of its (up to) eight cells in a fixed order; the Galerkin matrix is built the same way.  The only
 // atomics are the shared-memory accumulations inside one CTA of the Galerkin build (their order changes the
 // preconditioner in the last bits, never the solution the iteration converges to) and the rarely taken slow path.
+#include <cooperative_groups.h>
 #include <cub/cub.cuh>
 
 #include "coarse.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace ptfem {
 namespace {
@@ -329,6 +332,205 @@ __global__ void __launch_bounds__(256) coarse_dense_kernel(int kp, const double*
     dot = y * __ldcg(rc + (size_t)(I0 + r) * S + ss);
   }
   dot_by_sys<S>(dot, s_buf, dpart, cdot, ticket);
+}
+
+// ---- the grid hierarchy in ONE cooperative launch (PTFEM_COARSE_FUSED) ---------------------------------------------
+// node gather, grid restrictions, dense coarsest solve, prolongations and the per-level dots are six to eight small
+// dependent kernels per CG iteration; between them sit launch gaps and the ticket / last-CTA epilogues of the dots.
+// Here they are phases of one kernel separated by grid-wide barriers (cooperative groups).  Per element the arithmetic
+// is that of the separate kernels; the dots are summed per CTA and then over the CTAs in index order by CTA 0
+// (deterministic, but a different grouping than the separate kernels': the results agree to round-off, not bit for bit).
+struct ChainLevel {
+  CoarseGrid g;
+  int64_t k;
+  int kp, exact;
+  const double* binv;
+  double *rc, *yc, *yt;
+};
+struct ChainArgs {
+  int nlev, split, do_node, scaled0;
+  ChainLevel lev[kMaxCoarseLevels];
+  const double* part;   // restriction partials of level 0 (do_node)
+  double* dpart;        // [nlev][gridDim.x][S]
+  double* cdot;         // [nlev][16]
+};
+
+template <int S>
+__device__ __forceinline__ double chain_node_gather(const CoarseGrid& g, int split, const double* __restrict__ part, int64_t I, int s) {
+  double v = 0.0;
+  const int nx1 = g.n[0] + 1, ny1 = g.n[1] + 1;
+  const int ix = (int)(I % nx1), iy = (int)((I / nx1) % ny1), iz = (int)(I / ((int64_t)nx1 * ny1));
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int cx = ix - (a & 1), cy = iy - ((a >> 1) & 1), cz = iz - (a >> 2);
+    if (cx < 0 || cy < 0 || cz < 0 || cx >= g.n[0] || cy >= g.n[1] || cz >= g.n[2]) continue;
+    const int64_t c = cx + (int64_t)g.n[0] * (cy + (int64_t)g.n[1] * cz);
+    for (int sp = 0; sp < split; ++sp) v += __ldcg(part + (((size_t)c * split + sp) * 8 + a) * S + s);
+  }
+  return v;
+}
+template <int S>
+__device__ __forceinline__ double chain_restrict27(const CoarseGrid& gc, const double* __restrict__ rf, int64_t I, int s) {
+  double v = 0.0;
+  const int nx1 = gc.n[0] + 1, ny1 = gc.n[1] + 1;
+  const int ix = (int)(I % nx1), iy = (int)((I / nx1) % ny1), iz = (int)(I / ((int64_t)nx1 * ny1));
+  const int fx1 = 2 * gc.n[0] + 1, fy1 = 2 * gc.n[1] + 1, fz1 = 2 * gc.n[2] + 1;
+  for (int dz = -1; dz <= 1; ++dz) {
+    const int fz = 2 * iz + dz;
+    if (fz < 0 || fz >= fz1) continue;
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int fy = 2 * iy + dy;
+      if (fy < 0 || fy >= fy1) continue;
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int fx = 2 * ix + dx;
+        if (fx < 0 || fx >= fx1) continue;
+        const double w = (dx ? 0.5 : 1.0) * (dy ? 0.5 : 1.0) * (dz ? 0.5 : 1.0);
+        v = fma(w, __ldcg(rf + ((size_t)fx + (size_t)fx1 * (fy + (size_t)fy1 * fz)) * S + s), v);
+      }
+    }
+  }
+  return v;
+}
+template <int S>
+__device__ __forceinline__ double chain_prolong8(const CoarseGrid& gc, const double* __restrict__ ytc, double yf, int64_t F, int s) {
+  const int fx1 = 2 * gc.n[0] + 1, fy1 = 2 * gc.n[1] + 1;
+  const int nx1 = gc.n[0] + 1, ny1 = gc.n[1] + 1;
+  const int fx = (int)(F % fx1), fy = (int)((F / fx1) % fy1), fz = (int)(F / ((int64_t)fx1 * fy1));
+  double v = yf;
+  for (int az = 0; az <= (fz & 1); ++az)
+    for (int ay = 0; ay <= (fy & 1); ++ay)
+      for (int ax = 0; ax <= (fx & 1); ++ax) {
+        const double w = ((fx & 1) ? 0.5 : 1.0) * ((fy & 1) ? 0.5 : 1.0) * ((fz & 1) ? 0.5 : 1.0);
+        const size_t c = (size_t)(fx / 2 + ax) + (size_t)nx1 * ((fy / 2 + ay) + (size_t)ny1 * (fz / 2 + az));
+        v = fma(w, __ldcg(ytc + c * S + s), v);
+      }
+  return v;
+}
+
+template <int S>
+__global__ void __launch_bounds__(256) coarse_chain_kernel(ChainArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double s_buf[256];
+  __shared__ double s_part[8][kDenseRows][S];
+  const int s = threadIdx.x % S;   // 256 and the grid stride are multiples of S: a thread stays with one system
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+  double dot[kMaxCoarseLevels];
+#pragma unroll
+  for (int l = 0; l < kMaxCoarseLevels; ++l) dot[l] = 0.0;
+
+  // level 0: r_c from the restriction partials (or already there, summed over the ranks by the caller)
+  if (a.do_node || (!a.scaled0 && !a.lev[0].exact)) {
+    const ChainLevel& L = a.lev[0];
+    for (int64_t e = tid; e < L.k * S; e += nthr) {
+      const int64_t I = e / S;
+      const double v = a.do_node ? chain_node_gather<S>(L.g, a.split, a.part, I, s) : L.rc[e];
+      if (a.do_node) L.rc[e] = v;
+      if (!L.exact) {
+        const double y = v * __ldg(L.binv + I);
+        L.yc[e] = y;
+        dot[0] = fma(v, y, dot[0]);
+      }
+    }
+    grid.sync();
+  }
+  // coarser levels: r_c by 27-point restriction of the next finer grid
+#pragma unroll 1
+  for (int l = 1; l < a.nlev; ++l) {
+    const ChainLevel& L = a.lev[l];
+    const double* rf = a.lev[l - 1].rc;
+    double dl = 0.0;
+    for (int64_t e = tid; e < L.k * S; e += nthr) {
+      const int64_t I = e / S;
+      const double v = chain_restrict27<S>(L.g, rf, I, s);
+      L.rc[e] = v;
+      if (!L.exact) {
+        const double y = v * __ldg(L.binv + I);
+        L.yc[e] = y;
+        dl = fma(v, y, dl);
+      }
+    }
+    dot[l] = dl;
+    grid.sync();
+  }
+  // coarsest level: y_c = B r_c (dense); CTA takes groups of kDenseRows rows, warp w the w-th eighth of the columns
+  {
+    const ChainLevel& L = a.lev[a.nlev - 1];
+    constexpr int JPW = 32 / S;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int jj = lane / S, ls = lane % S;
+    const int chunk = L.kp / 8;
+    const int j0 = wid * chunk, j1 = j0 + chunk;
+    double dx = 0.0;
+    for (int I0 = blockIdx.x * kDenseRows; I0 < L.kp; I0 += gridDim.x * kDenseRows) {
+      double acc[kDenseRows];
+#pragma unroll
+      for (int r = 0; r < kDenseRows; ++r) acc[r] = 0.0;
+#pragma unroll 4
+      for (int J = j0 + jj; J < j1; J += JPW) {
+        const double v = __ldcg(L.rc + (size_t)J * S + ls);
+#pragma unroll
+        for (int r = 0; r < kDenseRows; ++r) acc[r] = fma(__ldg(L.binv + (size_t)(I0 + r) * L.kp + J), v, acc[r]);
+      }
+#pragma unroll
+      for (int r = 0; r < kDenseRows; ++r) {
+#pragma unroll
+        for (int o = S; o < 32; o <<= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+      }
+      if (lane < S) {
+#pragma unroll
+        for (int r = 0; r < kDenseRows; ++r) s_part[wid][r][lane] = acc[r];
+      }
+      __syncthreads();
+      if (threadIdx.x < kDenseRows * S) {
+        const int r = threadIdx.x / S, ss = threadIdx.x % S;
+        double y = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) y += s_part[w][r][ss];
+        L.yc[(size_t)(I0 + r) * S + ss] = y;
+        dx = fma(y, __ldcg(L.rc + (size_t)(I0 + r) * S + ss), dx);
+      }
+      __syncthreads();
+    }
+    dot[a.nlev - 1] = dx;
+  }
+  // per-level dots of this CTA (by system) -> dpart
+#pragma unroll 1
+  for (int l = 0; l < a.nlev; ++l) {
+    __syncthreads();
+    s_buf[threadIdx.x] = dot[l];
+    __syncthreads();
+    if (threadIdx.x < S) {
+      double tot = 0.0;
+      for (int k = threadIdx.x; k < (int)blockDim.x; k += S) tot += s_buf[k];
+      a.dpart[((size_t)l * gridDim.x + blockIdx.x) * S + threadIdx.x] = tot;
+    }
+  }
+  grid.sync();
+  // CTA 0: the sums over the CTAs, in order (thread = (CTA group g, system); then the groups in order)
+  if (blockIdx.x == 0) {
+    const int G = (int)blockDim.x / S, sys = threadIdx.x % S, g = threadIdx.x / S;
+#pragma unroll 1
+    for (int l = 0; l < a.nlev; ++l) {
+      double tot = 0.0;
+      for (unsigned int b = g; b < gridDim.x; b += G) tot += __ldcg(a.dpart + ((size_t)l * gridDim.x + b) * S + sys);
+      __syncthreads();
+      s_buf[threadIdx.x] = tot;
+      __syncthreads();
+      if (threadIdx.x < S) {
+        double t2 = 0.0;
+        for (int gg = 0; gg < G; ++gg) t2 += s_buf[gg * S + threadIdx.x];
+        a.cdot[l * 16 + threadIdx.x] = t2;
+      }
+    }
+  }
+  // coarsest -> finest grid: yt_l = y_l + P yt_{l+1}
+#pragma unroll 1
+  for (int l = a.nlev - 2; l >= 0; --l) {
+    const ChainLevel& L = a.lev[l];
+    const double* ytc = (l + 1 == a.nlev - 1) ? a.lev[l + 1].yc : a.lev[l + 1].yt;
+    for (int64_t e = tid; e < L.k * S; e += nthr) L.yt[e] = chain_prolong8<S>(a.lev[l + 1].g, ytc, L.yc[e], e / S, s);
+    if (l > 0) grid.sync();
+  }
 }
 
 // ---- Galerkin operator of the exact level ----------------------------------------------------------------------
@@ -693,6 +895,55 @@ void choose_grid(const ptfem_mesh* m, double target_nodes, CoarseGrid& g) {
   }
 }
 
+// grid of the cooperative chain kernel (all CTAs co-resident) and its per-CTA dot buffer; called outside graph capture
+template <int S>
+int chain_setup_t(ptfem_ctx* ctx, CoarseSpace& cs) {
+  int nb = 0;
+  PT_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, coarse_chain_kernel<S>, 256, 0));
+  if (nb > 4) nb = 4;
+  cs.chain_grid = nb > 0 ? nb * ctx->sm_count : 0;
+  if (cs.chain_grid > 0) PT_TRY(cs.chain_part.alloc((size_t)kMaxCoarseLevels * cs.chain_grid * 16));
+  return PTFEM_OK;
+}
+int chain_setup(ptfem_ctx* ctx, CoarseSpace& cs, int S) {
+  cs.chain_grid = 0;
+  if (!ctx->tune_coarse_fused) return PTFEM_OK;
+  switch (S) {
+    case 1: return chain_setup_t<1>(ctx, cs);
+    case 2: return chain_setup_t<2>(ctx, cs);
+    case 4: return chain_setup_t<4>(ctx, cs);
+    case 8: return chain_setup_t<8>(ctx, cs);
+    case 16: return chain_setup_t<16>(ctx, cs);
+  }
+  return PTFEM_OK;
+}
+template <int S>
+int chain_launch(ptfem_ctx* ctx, CoarseSpace& cs, bool do_node, bool scaled0) {
+  ChainArgs a;
+  a.nlev = cs.nlev;
+  a.split = cs.lev[0].split;
+  a.do_node = do_node ? 1 : 0;
+  a.scaled0 = scaled0 ? 1 : 0;
+  for (int l = 0; l < cs.nlev; ++l) {
+    CoarseLevel& L = cs.lev[l];
+    a.lev[l].g = L.g;
+    a.lev[l].k = L.k;
+    a.lev[l].kp = L.kp;
+    a.lev[l].exact = L.exact ? 1 : 0;
+    a.lev[l].binv = L.binv.p;
+    a.lev[l].rc = L.rc.p;
+    a.lev[l].yc = L.yc.p;
+    a.lev[l].yt = L.yt.p;
+  }
+  a.part = cs.lev[0].part.p;
+  a.dpart = cs.chain_part.p;
+  a.cdot = cs.cdot.p;
+  void* args[] = {&a};
+  PT_CK(cudaLaunchCooperativeKernel((const void*)coarse_chain_kernel<S>, dim3(cs.chain_grid), dim3(256), args, 0, ctx->stream));
+  ctx->launches++;
+  return PTFEM_OK;
+}
+
 template <int S>
 int apply_t(ptfem_ctx* ctx, CoarseSpace& cs, const double* r) {
   // mesh -> finest grid
@@ -708,6 +959,7 @@ int apply_t(ptfem_ctx* ctx, CoarseSpace& cs, const double* r) {
                                                                     r, L0.part.p);
     PT_LAUNCH_CHECK(ctx);
   }
+  if (cs.chain_grid > 0) return chain_launch<S>(ctx, cs, true, false);
   for (int l = 0; l < cs.nlev; ++l) {
     CoarseLevel& L = cs.lev[l];
     double* cdot = cs.cdot.p + (size_t)l * 16;
@@ -848,6 +1100,7 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
       PT_TRY(cs.ticket.alloc(4));
       PT_CK(cudaMemsetAsync(cs.ticket.p, 0, 4 * sizeof(unsigned int), ctx->stream));
     }
+    PT_TRY(chain_setup(ctx, cs, S));
     cs.S = S;
     rebuilt = true;
     cs.generation++;
@@ -970,6 +1223,7 @@ int coarse_attach_rows(ptfem_mesh* sys, ptfem_mesh* full, int64_t row0) {
   PT_TRY(cs.ticket.alloc(4));
   PT_CK(cudaMemsetAsync(cs.cdot.p, 0, (size_t)kMaxCoarseLevels * 16 * sizeof(double), ctx->stream));
   PT_CK(cudaMemsetAsync(cs.ticket.p, 0, 4 * sizeof(unsigned int), ctx->stream));
+  PT_TRY(chain_setup(ctx, cs, 1));
   PT_CK(cudaStreamSynchronize(ctx->stream));
   cs.S = 1;
   cs.geom_ok = true;
@@ -997,6 +1251,7 @@ int coarse_restrict_rows(ptfem_ctx* ctx, CoarseSpace& cs, const double* r, doubl
 
 // lev[0].rc holds the summed Z_0^T r (and, when scaled0, lev[0].yc = binv_0 r_c): the replicated grid hierarchy
 int coarse_grids_apply(ptfem_ctx* ctx, CoarseSpace& cs, bool scaled0) {
+  if (cs.chain_grid > 0) return chain_launch<1>(ctx, cs, false, scaled0);
   for (int l = 0; l < cs.nlev; ++l) {
     CoarseLevel& L = cs.lev[l];
     double* cdot = cs.cdot.p + (size_t)l * 16;

@@ -56,6 +56,8 @@ struct CoarseSpace {
   ptfem::DevBuf<double> ctab0;            // the same rows in the order of level 0's row list (restriction reads it in step with the list)
   ptfem::DevBuf<int32_t> flag;            // [0] non-positive pivot seen, [1] slow-path entries
   double setup_ms = 0.0;
+  int chain_grid = 0;                     // CTAs of the cooperative grid-hierarchy kernel (0: separate kernels)
+  ptfem::DevBuf<double> chain_part;       // its per-CTA dot partials [nlev][chain_grid][S]
 };
 
 __device__ __forceinline__ void coarse_locate(const CoarseGrid& g, const double* __restrict__ xyz, int64_t i, int (&c)[3],
