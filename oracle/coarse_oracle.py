@@ -2,7 +2,7 @@
 
 numpy/scipy restatement of the coarse-grid PCG preconditioner of ``pelvistim-fem_b200/csrc/coarse.cu``:
 
-    M^-1 r = D^-1 r + sum_l Z_l B_l Z_l^T r
+    M^-1 r = D^-1 r + w sum_l Z_l B_l Z_l^T r        (w = 2 / (levels + 1) unless ``PTFEM_COARSE_WEIGHT`` is set)
 
 ``Z_l``: trilinear interpolation from nested regular grids over the mesh bounding box to the mesh nodes (zero
 rows for Dirichlet nodes), ``B`` of the coarsest grid = exact inverse of the Galerkin matrix ``Z^T K Z``, ``B_l`` of
@@ -63,11 +63,16 @@ def interpolation(nodes, free, lo, hi, n):
 class CoarsePreconditioner:
     """M^-1 for the eliminated matrix K (Dirichlet rows = identity rows) of a mesh with nodes ``nodes``."""
 
-    def __init__(self, K, nodes, is_dirichlet, coarse_nodes=2000, extra_levels=-1):
+    def __init__(self, K, nodes, is_dirichlet, coarse_nodes=2000, extra_levels=-1, level_weight=None):
         lo, hi = nodes.min(axis=0), nodes.max(axis=0)
         base = choose_grid(lo, hi, float(coarse_nodes if coarse_nodes > 0 else 2000))
         self.nlev = level_count(nodes.shape[0], base, extra_levels)
         free = (~np.asarray(is_dirichlet, dtype=bool)).astype(np.float64)
+        # the additive levels overlap in what they correct: each is weighted by 2 / (levels + 1) against the Jacobi term
+        # (coarse.cu: level_weight(); measured optimum on the 3-level bench mesh, neutral for one level)
+        if level_weight is None:
+            level_weight = 2.0 / (self.nlev + 1)
+        self.level_weight = level_weight
         self.dinv = 1.0 / K.diagonal()
         self.Z, self.B = [], []
         for l in range(self.nlev):                      # level 0 = finest, last = coarsest (exact)
@@ -79,9 +84,9 @@ class CoarsePreconditioner:
                 Ed = E.toarray()
                 empty = ~(d > 0.0)
                 Ed[empty, empty] = 1.0
-                self.B.append(np.linalg.inv(Ed))
+                self.B.append(level_weight * np.linalg.inv(Ed))
             else:
-                self.B.append(np.where(d > 0.0, 1.0 / np.where(d > 0.0, d, 1.0), 0.0))
+                self.B.append(level_weight * np.where(d > 0.0, 1.0 / np.where(d > 0.0, d, 1.0), 0.0))
             self.Z.append(Z)
         self.coarse_unknowns = self.Z[-1].shape[1]
 

@@ -195,6 +195,10 @@ int ptfem_ctx_create(int device, ptfem_ctx** out) {
   if (const char* e = getenv("PTFEM_CTAS_PER_SM")) c->tune_ctas_per_sm = atoi(e);
   if (const char* e = getenv("PTFEM_RESTRICT_OCC")) c->tune_restrict_occ = atoi(e);
   if (const char* e = getenv("PTFEM_COARSE_FUSED")) c->tune_coarse_fused = atoi(e) != 0;
+  if (const char* e = getenv("PTFEM_COARSE_WEIGHT")) {
+    const double w = atof(e);
+    if (w > 0.0) c->tune_coarse_weight = w;
+  }
   if (const char* e = getenv("PTFEM_STREAM_CAP")) c->tune_stream_cap = atoi(e);
   if (const char* e = getenv("PTFEM_STREAM_ROWS")) c->tune_stream_rows = atoi(e);
   if (const char* e = getenv("PTFEM_STREAM_TPR")) c->tune_stream_tpr = atoi(e);

@@ -838,6 +838,11 @@ __global__ void coarse_table_split_kernel(int64_t nn, double* __restrict__ ctab,
   isdir[i] = cell < 0 ? 1 : 0;
   ctab[4 * i + 3] = __longlong_as_double(cell & ~kDirBit);
 }
+// level weight: B_l *= w (the additive levels overlap in what they correct)
+__global__ void coarse_weight_kernel(double* __restrict__ binv, int64_t n, double w) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) binv[i] *= w;
+}
 // y_c = binv * r_c on a diagonal-only level whose r_c was summed over the ranks by the caller
 __global__ void coarse_scale_kernel(int64_t k, const double* __restrict__ binv, const double* __restrict__ rc,
                                     double* __restrict__ yc) {
@@ -1113,6 +1118,10 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
     PT_TRY(cs.ctab0.alloc((size_t)m->nn * 4));
     gather_table_kernel<<<ceil_div(m->nn, 256), 256, 0, ctx->stream>>>(cs.ctab.p, cs.lev[0].rows.p, m->nn, cs.ctab0.p);
     PT_LAUNCH_CHECK(ctx);
+    // the additive levels overlap in what they correct (every level sees the smooth part of r): each is weighted by
+    // 2 / (levels + 1) against the Jacobi term - CPU study profiles/r01_precond_level_weights_L_cpu.txt: 71 -> 60 iterations
+    // on the 3-level bench mesh, 59 -> 56 with 2 levels, unchanged with one; PTFEM_COARSE_WEIGHT overrides
+    const double level_w = ctx->tune_coarse_weight > 0.0 ? ctx->tune_coarse_weight : 2.0 / (cs.nlev + 1);
     for (int l = 0; l < cs.nlev; ++l) {
       CoarseLevel& L = cs.lev[l];
       if (L.exact) {
@@ -1130,6 +1139,10 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
         galerkin_gather_kernel<<<ceil_div((int64_t)n2, 256), 256, 0, ctx->stream>>>(L.g, L.k, L.kp, blockE.p, L.binv.p);
         PT_LAUNCH_CHECK(ctx);
         PT_TRY(dense_inverse(ctx, L.binv.p, L.kp, cs.flag.p));
+        if (level_w != 1.0) {
+          coarse_weight_kernel<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(L.binv.p, (int64_t)n2, level_w);
+          PT_LAUNCH_CHECK(ctx);
+        }
       } else {
         const double* before = L.binv.p;
         PT_TRY(L.binv.alloc(L.k));
@@ -1142,6 +1155,10 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
         PT_LAUNCH_CHECK(ctx);
         galerkin_diag_node_kernel<<<ceil_div(L.k, 256), 256, 0, ctx->stream>>>(L.g, L.k, dpartc.p, L.binv.p);
         PT_LAUNCH_CHECK(ctx);
+        if (level_w != 1.0) {
+          coarse_weight_kernel<<<ceil_div(L.k, 256), 256, 0, ctx->stream>>>(L.binv.p, L.k, level_w);
+          PT_LAUNCH_CHECK(ctx);
+        }
         PT_CK(cudaStreamSynchronize(ctx->stream));
       }
     }
