@@ -261,3 +261,13 @@ def test_ctypes_structs_follow_the_header():
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         fields = [(m.group(2), ctype[m.group(1)]) for m in re.finditer(r"(int32_t|int64_t|double)\s+(\w+)\s*;", body)]
         assert fields == list(cls._fields_), name
+
+
+@pytest.mark.parametrize("step,fixture", [("step03_ankle_layers", "step03_params.yaml"), ("step04_pressure", "step04_params.yaml")])
+def test_driver_params_carry_the_reference_values(golden, step, fixture):
+    # drivers/<step>/params.yaml is written in this repo's own words; keys and values are the reference's
+    # (tests/golden/ holds the reference's file as committed there)
+    import pathlib
+    import yaml
+    ours = yaml.safe_load((pathlib.Path(__file__).resolve().parents[1] / "drivers" / step / "params.yaml").read_text())
+    assert ours == yaml.safe_load((golden / fixture).read_text())
