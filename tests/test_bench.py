@@ -20,7 +20,8 @@ def _run(*args):
 
 
 def test_reference_arm_line():
-    d = _run("--impl", "reference", "--size", "XS", "--steps", "2", "--warmup", "1")
+    d = _run("--impl", "reference", "--size", "XS", "--steps", "2", "--warmup", "1", "--no-direct-sample")
+    assert "direct_solver_sample" not in d
     assert BASE_KEYS <= set(d) and d["impl"] == "reference" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
@@ -35,6 +36,14 @@ def test_reference_arm_other_ranks_exit_quietly(monkeypatch):
     assert pr.returncode == 0 and pr.stdout.strip() == ""
 
 
+def test_direct_solver_sample_of_the_reference_arm():
+    # the reference's solver class (sparse direct) on a slab that factors in a blink here; the arm uses 48x36x30
+    sys.path.insert(0, str(ROOT))
+    import bench
+    d = bench.direct_solver_sample((12, 9, 8))
+    assert d["nodes"] > 500 and d["rel_residual"] < 1e-9 and d["fill_nnz"] > d["matrix_nnz"] and d["solves_per_s"] > 0
+
+
 @pytest.mark.gpu
 def test_gpu_arm_line():
     d = _run("--size", "S", "--steps", "2", "--warmup", "3", "--cpu-iters", "20")
@@ -45,5 +54,5 @@ def test_gpu_arm_line():
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] > 0
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
-    ref = _run("--impl", "reference", "--size", "S", "--steps", "1", "--warmup", "1")
+    ref = _run("--impl", "reference", "--size", "S", "--steps", "1", "--warmup", "1", "--no-direct-sample")
     assert ref["config"] == d["config"] and ref["metric"] == d["metric"] and ref["unit"] == d["unit"]
