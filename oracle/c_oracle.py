@@ -41,6 +41,15 @@ def lib():
         L.oc_spmv.argtypes = [i64, vp, vp, vp, vp, vp]
         L.oc_pcg.restype = C.c_int
         L.oc_pcg.argtypes = [i64, vp, vp, vp, vp, vp, dbl, C.c_int, C.POINTER(dbl)]
+        L.oc_coarse_locate.argtypes = [i64, vp, vp, vp, vp, vp, vp]
+        L.oc_galerkin_dense.restype = C.c_int
+        L.oc_galerkin_dense.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.oc_galerkin_diag.restype = C.c_int
+        L.oc_galerkin_diag.argtypes = [i64, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.oc_pcg_coarse.restype = C.c_int
+        L.oc_pcg_coarse.argtypes = [i64, vp, vp, vp, vp, vp, dbl, C.c_int, C.POINTER(dbl), C.c_int, vp, vp, vp, vp, vp, vp]
+        L.oc_recover_lumped.restype = C.c_int
+        L.oc_recover_lumped.argtypes = [i64, vp, vp, vp, vp, vp]
         _LIB = L
     return _LIB
 
@@ -55,6 +64,23 @@ def threads():
 
 def set_threads(n):
     lib().oc_set_threads(int(n))
+
+
+def host_cores():
+    """Cores this process may run on (the affinity mask, not ``os.cpu_count()``: containers are often pinned)."""
+    import os
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def use_all_cores():
+    """Pin the OpenMP thread count to every core the process may use.  ``torch.distributed.run`` exports
+    ``OMP_NUM_THREADS=1`` to its children, which would otherwise leave the oracle on one thread."""
+    n = host_cores()
+    set_threads(n)
+    return n
 
 
 class CSystem:
@@ -98,6 +124,8 @@ class CSystem:
         self.val = self.val_raw.copy()
         L.oc_dirichlet(nn, _p(self.rowptr), _p(isdir), _p(dval), _p(self.val), _p(self.b))
         self.isdir = isdir
+        self.nodes, self.tets, self.sigma_e = nodes, tets, sig
+        self.coarse = None
 
     def spmv(self, x, raw=False):
         x = np.ascontiguousarray(x, dtype=np.float64)
@@ -113,3 +141,68 @@ class CSystem:
         if it < 0:
             raise MemoryError("oc_pcg failed")
         return x, it, rel.value
+
+    # -- Jacobi + geometric coarse grids (restates coarse_oracle.py in C; same grid / level / weight rules) --------
+    def coarse_setup(self, coarse_nodes=2000, extra_levels=-1, level_weight=None):
+        """Grids, Galerkin operators and their inverses for :meth:`pcg_coarse`.  Returns the set-up dict."""
+        from . import coarse_oracle as cor
+        L = lib()
+        lo, hi = self.nodes.min(axis=0), self.nodes.max(axis=0)
+        base = cor.choose_grid(lo, hi, float(coarse_nodes if coarse_nodes > 0 else 2000))
+        nlev = cor.level_count(self.nn, base, extra_levels)
+        if level_weight is None:
+            level_weight = 2.0 / (nlev + 1)
+        ext = np.where(hi - lo > 0.0, hi - lo, 1.0)
+        ns, bdiag, node0_f, t_f, bdense = [], [], None, None, None
+        for l in range(nlev):                                  # 0 = finest ... nlev-1 = coarsest (exact)
+            n = (base * (1 << (nlev - 1 - l))).astype(np.int32)
+            inv_h = np.ascontiguousarray(n / (ext * (1.0 + 1e-12)), dtype=np.float64)
+            node0 = np.empty(self.nn, dtype=np.int32)
+            t = np.empty((self.nn, 3), dtype=np.float64)
+            lo_c = np.ascontiguousarray(lo, dtype=np.float64)
+            L.oc_coarse_locate(self.nn, _p(self.nodes), _p(lo_c), _p(inv_h), _p(n), _p(node0), _p(t))
+            k = int(np.prod(n + 1))
+            if l == nlev - 1:
+                E = np.empty((k, k), dtype=np.float64)
+                if L.oc_galerkin_dense(self.nn, _p(self.rowptr), _p(self.col), _p(self.val), _p(self.isdir), _p(node0), _p(t),
+                                       _p(n), _p(E)) != 0:
+                    raise MemoryError("oc_galerkin_dense failed")
+                d = E.diagonal().copy()
+                empty = ~(d > 0.0)
+                E[empty, empty] = 1.0
+                bdense = np.ascontiguousarray(level_weight * np.linalg.inv(E))
+            else:
+                d = np.empty(k, dtype=np.float64)
+                if L.oc_galerkin_diag(self.nn, _p(self.rowptr), _p(self.col), _p(self.val), _p(self.isdir), _p(node0), _p(t),
+                                      _p(n), _p(d)) != 0:
+                    raise MemoryError("oc_galerkin_diag failed")
+                bdiag.append(level_weight * np.where(d > 0.0, 1.0 / np.where(d > 0.0, d, 1.0), 0.0))
+            if l == 0:
+                node0_f, t_f = node0, t
+            ns.append(n)
+        self.coarse = dict(nlev=nlev, n=np.ascontiguousarray(np.stack(ns), dtype=np.int32), node0=node0_f, t=t_f,
+                           bdiag=np.ascontiguousarray(np.concatenate(bdiag)) if bdiag else np.zeros(1), bdense=bdense,
+                           coarse_unknowns=int(bdense.shape[0]), level_weight=level_weight)
+        return self.coarse
+
+    def pcg_coarse(self, rtol=1e-12, maxit=100000, x0=None):
+        """PCG with the Jacobi + coarse-grid preconditioner (call :meth:`coarse_setup` first)."""
+        if self.coarse is None:
+            self.coarse_setup()
+        c = self.coarse
+        x = np.zeros(self.nn, dtype=np.float64) if x0 is None else np.ascontiguousarray(x0, dtype=np.float64).copy()
+        rel = C.c_double()
+        it = lib().oc_pcg_coarse(self.nn, _p(self.rowptr), _p(self.col), _p(self.val), _p(self.b), _p(x), float(rtol), int(maxit),
+                                 C.byref(rel), int(c["nlev"]), _p(c["n"]), _p(c["node0"]), _p(c["t"]), _p(self.isdir),
+                                 _p(c["bdiag"]), _p(c["bdense"]))
+        if it < 0:
+            raise MemoryError("oc_pcg_coarse failed")
+        return x, it, rel.value
+
+    def recover_lumped(self, phi):
+        """Nodal ``volume current`` by the volume-weighted average (= fem_oracle ``method="lumped"``)."""
+        phi = np.ascontiguousarray(phi, dtype=np.float64)
+        J = np.empty((self.nn, 3), dtype=np.float64)
+        if lib().oc_recover_lumped(self.nn, _p(self.nodes), _p(self.tets), _p(self.sigma_e), _p(phi), _p(J)) != 0:
+            raise RuntimeError("oc_recover_lumped needs the pattern of this mesh (build the CSystem last)")
+        return J

@@ -92,12 +92,12 @@ def cell_fields(pts, tets, tris, phi, J):
     phic_b = phi[tris].mean(axis=1)
     acc = np.zeros(nn)
     cnt = np.zeros(nn)
-    for a in range(4):
-        np.add.at(acc, tets[:, a], phic_t)
-        np.add.at(cnt, tets[:, a], 1.0)
+    for a in range(4):          # bincount adds in input order, like np.add.at, but vectorised
+        acc += np.bincount(tets[:, a], weights=phic_t, minlength=nn)
+        cnt += np.bincount(tets[:, a], minlength=nn)
     for a in range(3):
-        np.add.at(acc, tris[:, a], phic_b)
-        np.add.at(cnt, tris[:, a], 1.0)
+        acc += np.bincount(tris[:, a], weights=phic_b, minlength=nn)
+        cnt += np.bincount(tris[:, a], minlength=nn)
     phis = acc / np.maximum(cnt, 1.0)                   # smoothed point values
     _, g = tet_geometry(pts, tets)
     grad_t = np.einsum("ei,eik->ek", phis[tets], g)

@@ -253,7 +253,7 @@ __global__ void dist_scalar_kernel(double* __restrict__ scal, int first) {
 // pull of iteration k, and this rank overwrites u (update k+1) only after the all-reduce completed.
 // Mailboxes are double-buffered by iteration parity.  Every wait is bounded; a timeout raises err in the mailbox.
 constexpr int kMaxRanks = 16;
-constexpr unsigned long long kSpinLimit = 1ull << 23;   // bounded waits: a few seconds, then err is raised
+constexpr unsigned long long kWaitDefaultNs = 20ull * 1000000000ull;   // bounded waits: wall-clock (globaltimer), then err is raised
 struct alignas(16) MailBox {
   double v[3];
   unsigned long long seq;
@@ -273,6 +273,7 @@ struct PeerTable {
   const double* u[kMaxRanks];  // neighbours' u vectors, indexed by rank (null when not a neighbour)
   const double* xch[kMaxRanks];// every rank's coarse exchange area [2][xstride] (behind its mailbox; null without coarse grids)
   int64_t xstride;
+  unsigned long long timeout_ns;   // bound of every cross-rank wait (PTFEM_P2P_TIMEOUT_MS, default 20 s)
   int32_t nbr_rank[kMaxRanks];
   int32_t nnbr, rank, nranks;
 };
@@ -293,13 +294,35 @@ __device__ __forceinline__ double ld_volatile_f64(const double* p) {
 __device__ __forceinline__ void st_volatile_f64(double* p, double v) {
   asm volatile("st.volatile.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
-// spin until *p >= want (bounded); returns false on timeout
-__device__ __forceinline__ bool wait_ge(const unsigned long long* p, unsigned long long want, unsigned long long* err) {
-  for (unsigned long long n = 0; n < kSpinLimit; ++n) {
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// Spin until *p >= want.  The bound is wall-clock time (a descheduled peer - two ranks time-sliced on one GPU, a busy
+// host - costs milliseconds, not a spin count).  On a timeout err is raised in the local mailbox AND pushed into every
+// peer's, and a wait that finds err already raised returns at once: after the first missed wait no rank spins again,
+// the host sees err with the next scalar read-back and abandons the solve (ptfem_dist_solve).
+__device__ __noinline__ bool wait_ge(const unsigned long long* p, unsigned long long want, const PeerTable& pt) {
+  if (ld_acquire_sys(p) >= want) return true;
+  Mail* me = pt.mail[pt.rank];
+  const unsigned long long t0 = globaltimer_ns();
+  for (unsigned long long n = 1;; ++n) {
     if (ld_acquire_sys(p) >= want) return true;
+    if ((n & 31) == 0) {
+      if (ld_volatile_u64(&me->err)) return false;
+      if (globaltimer_ns() - t0 > pt.timeout_ns) break;
+    }
     __nanosleep(64);
   }
-  atomicExch(err, 1ull);
+  atomicExch(&me->err, 1ull);
+  for (int q = 0; q < pt.nranks; ++q)
+    if (q != pt.rank) st_release_sys(&pt.mail[q]->err, 1ull);
   return false;
 }
 
@@ -321,7 +344,7 @@ __device__ void mailbox_allreduce(const double loc[3], const PeerTable& pt, doub
   double tot[3] = {0.0, 0.0, 0.0};
   for (int q = 0; q < pt.nranks; ++q) {
     MailBox* bx = &me->box[par][q];
-    if (!wait_ge(&bx->seq, seq, &me->err)) break;
+    if (!wait_ge(&bx->seq, seq, pt)) break;
     for (int c = 0; c < 3; ++c) tot[c] += ld_volatile_f64(&bx->v[c]);
   }
   if (bnorm) {
@@ -457,7 +480,7 @@ __global__ void __launch_bounds__(kT) p2p_coarse_reduce_kernel(int64_t k, int pa
   if (threadIdx.x == 0) {
     const unsigned long long seq = me->xred;   // bumped by the signal kernel just before this launch
     for (int q = 0; q < pt.nranks; ++q)
-      if (q != pt.rank && !wait_ge(&me->xready_from[q], seq, &me->err)) break;
+      if (q != pt.rank && !wait_ge(&me->xready_from[q], seq, pt)) break;
   }
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * kT;
@@ -482,7 +505,7 @@ __global__ void __launch_bounds__(kT) p2p_pull_kernel(int64_t nloc, const int32_
   const int64_t stride = (int64_t)gridDim.x * kT;
   for (int j = 0; j < pt.nnbr; ++j) {
     const int q = pt.nbr_rank[j];
-    if (threadIdx.x == 0) wait_ge(&me->ready_from[q], k, &me->err);
+    if (threadIdx.x == 0) wait_ge(&me->ready_from[q], k, pt);
     __syncthreads();
     const double* pu = pt.u[q];
     for (int64_t h = recv_ptr[j] + (int64_t)blockIdx.x * kT + threadIdx.x; h < recv_ptr[j + 1]; h += stride)
@@ -554,6 +577,7 @@ struct DistState {
   int32_t stream_rows = 0, stream_cap = 0;  // streaming SpMV tile geometry valid for any row range
   // peer-memory path
   bool p2p = false;
+  bool p2p_broken = false;     // a cross-rank wait timed out: sequence counters are out of step until the ranks reconnect
   DevBuf<Mail> mail;
   DevBuf<int32_t> halo_src, recv_ptr_dev;
   PeerTable pt{};
@@ -943,6 +967,9 @@ int ptfem_dist_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* x_loca
   double* h = ctx->h_pinned;
 
   const bool p2p = d.p2p;
+  if (p2p && d.p2p_broken)
+    return set_err(PTFEM_ERR_STATE, "peer-memory connection is out of step after a timed-out wait: build a new system and reconnect, "
+                                    "or use the NCCL transport");
   if (ctx->nranks > 1 && !p2p && !ctx->comm)
     return set_err(PTFEM_ERR_STATE, "neither an NCCL communicator (ptfem_dist_init) nor peer memory (ptfem_dist_p2p_connect) is set up");
   // first use of a peer connection / collective sets up NCCL channels (seconds): keep it out of the timing
@@ -977,9 +1004,20 @@ int ptfem_dist_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* x_loca
     PT_TRY(dist_reduce(m, d, 1));
   }
 
+  // scalars, and with them the mailbox's error flag: a timed-out wait ends the solve at the next read-back
+  unsigned long long* h_err = reinterpret_cast<unsigned long long*>(h + D_COUNT);
+  *h_err = 0;
   auto read_scal = [&]() -> int {
     PT_CK(cudaMemcpyAsync(h, d.scal.p, D_COUNT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (p2p) PT_CK(cudaMemcpyAsync(h_err, &d.mail.p->err, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     PT_CK(cudaStreamSynchronize(ctx->stream));
+    if (p2p && *h_err) {
+      d.p2p_broken = true;
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      return set_err(PTFEM_ERR_STATE, "peer-memory solve: a cross-rank wait timed out (on this rank or a peer); the connection is out "
+                                      "of step - reconnect (ptfem_dist_p2p_export / _connect on a new system) or use the NCCL transport");
+    }
     return PTFEM_OK;
   };
   PT_TRY(read_scal());
@@ -1058,16 +1096,7 @@ int ptfem_dist_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* x_loca
       cudaEventElapsedTime(&t_ar, e0, e1);
     }
   }
-  if (p2p) {
-    Mail hm;
-    PT_CK(cudaMemcpy(&hm, d.mail.p, sizeof(Mail), cudaMemcpyDeviceToHost));
-    if (hm.err) {
-      cudaMemset(&d.mail.p->err, 0, sizeof(unsigned long long));
-      cudaEventDestroy(e0);
-      cudaEventDestroy(e1);
-      return set_err(PTFEM_ERR_STATE, "peer-memory solve: a wait on another rank timed out (iteration %llu)", hm.iter);
-    }
-  }
+  if (p2p) PT_TRY(read_scal());   // a wait of the last chunk may have timed out after the last read-back
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   if (ms_spmv) *ms_spmv = t_spmv / reps;
@@ -1148,6 +1177,11 @@ int ptfem_dist_p2p_connect(ptfem_mesh* m, int32_t nranks, const void* all_handle
   pt.nranks = nranks;
   pt.nnbr = m->nnbr;
   pt.xstride = d.xstride;
+  pt.timeout_ns = kWaitDefaultNs;
+  if (const char* e = getenv("PTFEM_P2P_TIMEOUT_MS")) {
+    const double ms = atof(e);
+    if (ms > 0.0) pt.timeout_ns = (unsigned long long)(ms * 1e6);
+  }
   if (m->nnbr > kMaxRanks) return set_err(PTFEM_ERR_ARG, "too many neighbours");
   for (int k = 0; k < m->nnbr; ++k) pt.nbr_rank[k] = m->nbr_rank[k];
   const cudaIpcMemHandle_t* hs = reinterpret_cast<const cudaIpcMemHandle_t*>(all_handles);

@@ -61,26 +61,35 @@ def partitioned_solve(ctx, mesh, sigma_by_body, dirichlet, neumann, rank, world,
     ds = None
     if (world > 1 or force_p2p) and transport == "p2p":
         # peer memory needs CUDA IPC between the ranks' processes; every rank must agree on whether it works
-        ok = 1
+        # (every rank takes part in every collective below whatever failed locally: a rank that raised before a gather
+        #  would otherwise pair its next collective with the others' previous one)
+        p2p_error, exported = None, None
         try:
             engine.dist_init(ctx, None, rank, world)
             ds = make_system()
-            handles = [None] * world
-            dist.all_gather_object(handles, ds.p2p_export())
-            ds.p2p_connect(handles, partition.halo_sources(blk, n=rowptr.shape[0] - 1))
+            exported = ds.p2p_export()
         except engine.PtfemError as e:
-            ok = 0
             p2p_error = str(e)
+        handles = [None] * world
+        dist.all_gather_object(handles, exported)                 # None = that rank could not export
+        if p2p_error is None:
+            if all(h is not None for h in handles):
+                try:
+                    ds.p2p_connect(handles, partition.halo_sources(blk, n=rowptr.shape[0] - 1))
+                except engine.PtfemError as e:
+                    p2p_error = str(e)
+            else:
+                p2p_error = "export failed on another rank"
         flags = [None] * world
-        dist.all_gather_object(flags, ok)
-        if not all(flags):
+        dist.all_gather_object(flags, p2p_error)
+        if any(flags):
             if ds is not None:
                 ds.close()
                 ds = None
             engine.dist_finalize(ctx)
             used = "nccl"
             if rank == 0:
-                print(f"distsolve: peer-memory transport unavailable ({p2p_error if not ok else 'on another rank'}); using NCCL", flush=True)
+                print(f"distsolve: peer-memory transport unavailable ({[f for f in flags if f][0]}); using NCCL", flush=True)
         else:
             dist.barrier()
     if world > 1 and used == "nccl":
@@ -89,15 +98,48 @@ def partitioned_solve(ctx, mesh, sigma_by_body, dirichlet, neumann, rank, world,
         engine.dist_init(ctx, ids[0], rank, world)
     if ds is None:
         ds = make_system()
+
+    def timed_solves(ds):
+        """first solve: captures the CUDA graph of the iteration (and warms the peer mappings); the second one is reported.
+        Every rank reports success or failure of its own solves; the ranks then agree (a timed-out peer-memory wait is
+        pushed to every rank's mailbox, so all of them leave the solve within one read-back of the scalars)."""
+        err, x, first_ms, wall = None, None, None, None
+        try:
+            ds.solve(**opts)
+            first_ms = ds.last_stats["solve_ms"]
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            x = ds.solve(**opts)
+            wall = time.perf_counter() - t0
+        except engine.PtfemError as e:
+            if e.code == engine.ERR_NOCONV:
+                raise
+            err = str(e)
+        if world > 1:
+            flags = [None] * world
+            dist.all_gather_object(flags, err)
+            bad = [f for f in flags if f]
+            if bad:
+                err = err or f"on another rank: {bad[0]}"
+        return err, x, first_ms, wall
+
+    err, x, first_ms, wall = timed_solves(ds)
+    if err and used == "p2p" and world > 1:
+        # a peer stalled past the bounded wait: the peer-memory connection is out of step - start over on the NCCL transport
+        if rank == 0:
+            print(f"distsolve: peer-memory solve failed ({err}); retrying over NCCL", flush=True)
+        ds.close()
+        engine.dist_finalize(ctx)
+        used = "nccl"
+        ids = [engine.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        engine.dist_init(ctx, ids[0], rank, world)
+        ds = make_system()
+        err, x, first_ms, wall = timed_solves(ds)
     dm.close()
-    # first solve: captures the CUDA graph of the iteration (and warms the peer mappings); the second one is reported
-    ds.solve(**opts)
-    first_ms = ds.last_stats["solve_ms"]
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    x = ds.solve(**opts)
-    wall = time.perf_counter() - t0
+    if err:
+        raise engine.PtfemError(-3, err)
     out = dict(x_local=x, row0=blk.row0, nloc=blk.nloc, nhalo=blk.nhalo, stats=ds.last_stats, timings=ds.timings, wall_s=wall,
                transport=used, coarse=state["coarse"], coarse_note=state["note"], first_solve_ms=first_ms)
     if check:

@@ -49,8 +49,16 @@ def map_points(fn, points, gpus=1):
     out = [None] * len(points)
     got = 0
     err = None
+    import queue
     while got < len(points) and err is None:
-        i, res, e = q.get()
+        try:
+            i, res, e = q.get(timeout=2.0)
+        except queue.Empty:
+            # a worker killed by a CUDA abort or a segfault never reports: notice it instead of waiting forever
+            dead = [pr for pr in procs if not pr.is_alive() and pr.exitcode not in (0, None)]
+            if dead:
+                err = f"sweep worker pid {dead[0].pid} died with exit code {dead[0].exitcode}"
+            continue
         if e is not None:
             err = e
             break

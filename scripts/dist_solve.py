@@ -37,5 +37,7 @@ line = dict(rank=rank, world=world, size=size, transport=res["transport"], coars
             single_gpu_coarse_solve_ms=res["single_gpu_auto_solve_ms"], single_gpu_coarse_iterations=res["single_gpu_auto_iterations"],
             **res["timings"])
 print(json.dumps(line), flush=True)
+if os.environ.get("PTFEM_DUMP_X"):      # this rank's block of the solution, for the caller's own checks (tests compare with the oracle)
+    np.save(os.environ["PTFEM_DUMP_X"].format(rank=rank), res["x_local"])
 assert res["rel_err_vs_single"] < 1e-6, res["rel_err_vs_single"]
 dist.destroy_process_group()

@@ -199,3 +199,28 @@ def test_coarse_grid_preconditioner_restatement():
     # grid choice follows coarse.cu: >= 2 cells per axis, about the requested node count
     n = cz.choose_grid(np.zeros(3), np.array([0.08, 0.06, 0.0405]), 2000.0)
     assert (n >= 2).all() and 1500 <= np.prod(n + 1) <= 2600
+
+
+def test_c_oracle_coarse_grid_pcg_and_recovery_match_numpy_oracle():
+    # oracle/fem_c.c oc_pcg_coarse / oc_recover_lumped (what bench.py's CPU legs and the size-M/L GPU parity tests use)
+    # against the numpy oracle: direct solve, coarse_oracle.py iteration counts, lumped recovery
+    from oracle import coarse_oracle as cor
+    co.use_all_cores()
+    m = meshgen.synth_slab("S")
+    ref = fo.solve_case(m, SIGMA5, [(102, 0.0)], [(101, 15.975)], recover="lumped")
+    cs = co.CSystem(m, SIGMA5, [(102, 0.0)], [(101, 15.975)])
+    K = sp.csr_matrix((cs.val, cs.col, cs.rowptr), shape=(cs.nn, cs.nn))
+    for nodes, levels in ((300, 0), (120, 1)):
+        c = cs.coarse_setup(coarse_nodes=nodes, extra_levels=levels)
+        x, it, rel = cs.pcg_coarse(rtol=1e-12)
+        P = cor.CoarsePreconditioner(K, m.nodes, cs.isdir.astype(bool), coarse_nodes=nodes, extra_levels=levels)
+        xn, itn = cor.pcg(K, cs.b, P.apply, rtol=1e-12)
+        assert c["nlev"] == P.nlev == levels + 1 and c["coarse_unknowns"] == P.coarse_unknowns
+        assert abs(it - itn) <= 1 and rel <= 1e-12
+        assert np.abs(x - ref["phi"]).max() < 1e-9 * np.abs(ref["phi"]).max()
+    J = cs.recover_lumped(ref["phi"])
+    assert np.abs(J - ref["J"]).max() < 1e-12 * np.abs(ref["J"]).max()
+    # thread count is explicit: an exported OMP_NUM_THREADS=1 (torch.distributed.run does that) must not stick
+    co.set_threads(1)
+    assert co.threads() == 1
+    assert co.use_all_cores() == co.host_cores() == co.threads()
