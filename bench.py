@@ -67,13 +67,20 @@ def run_sweep_step(dm, mesh, confs, step, phi_out=None, J_out=None, sample_spmv=
     phi = dm.solve(to_host=phi_out is not None, out=phi_out, rtol=RTOL, sample_spmv=sample_spmv, spmv_variant=0, precond=PRECOND)
     stats = dm.last_stats
     Lz, t_skin = mesh.meta["Lz"], mesh.meta["t_skin"]
-    rows = []
+    # nodal currents of all configurations in two launches (read-back, if asked for, on the side stream), then all the
+    # metric reductions of the sweep in one batch: one pass over the mesh per kind, one device->host read-back
+    dm.recover_current_batch(RECOVER, to_host=J_out is not None, out=J_out, wait=False)
+    reqs = []
     for k, c in enumerate(confs):
-        dm.recover_current(k, RECOVER, to_host=J_out is not None, out=None if J_out is None else J_out[k], wait=J_out is None)
         fp = (c["center"][0], c["center"][1], c["r"], False)
-        pk = dm.metric_nodes(0, Lz - 0.2 * t_skin, sys=k)
-        ph = dm.metric_nodes(1, Lz - 1e-5, mode=1, footprints=[fp], scale_r=1.0, sys=k)
-        roi = dm.metric_roi([c["center"][0], c["center"][1], Lz - 0.010], 0.005, (1.0, 1.5, 2.0, 3.0), include_tris=False, sys=k)[0]
+        reqs.append(dict(kind="nodes", sys=k, field=0, zmin=Lz - 0.2 * t_skin))
+        reqs.append(dict(kind="nodes", sys=k, field=1, zmin=Lz - 1e-5, mode=1, footprints=[fp], scale_r=1.0))
+        reqs.append(dict(kind="roi", sys=k, cen=[c["center"][0], c["center"][1], Lz - 0.010], r0=0.005, mults=(1.0, 1.5, 2.0, 3.0),
+                         include_tris=False))
+    res = dm.metrics_batch(reqs)
+    rows = []
+    for k in range(len(confs)):
+        pk, ph, roi = res[3 * k], res[3 * k + 1], res[3 * k + 2][0]
         rows.append(dict(peak_J=pk["max"], V_active=ph["sum"] / max(ph["count"], 1), roi_mean_E=roi["sum_E"] / max(roi["n"], 1)))
     return rows, stats, phi
 
@@ -462,8 +469,12 @@ def main():
         ev0.record(stream)
         for s in range(args.steps):
             l2_flush()
-            rows, st, _ = run_sweep_step(dm, mesh, confs, args.warmup + s, sample_spmv=4)
-            spmv_ms.append(st["spmv_ms"]); iters.append(st["iterations"]); last_st = st
+            # the dominant kernel is timed live, with CUDA events on the solver's stream, inside the first two timed steps
+            # (4 extra launches each: sampling every step would only tax the number it explains)
+            rows, st, _ = run_sweep_step(dm, mesh, confs, args.warmup + s, sample_spmv=4 if s < 2 else 0)
+            if s < 2:
+                spmv_ms.append(st["spmv_ms"])
+            iters.append(st["iterations"]); last_st = st
         ev1.record(stream)
         ctx.sync(); torch.cuda.synchronize()
     launches = ctx.launches - launches0

@@ -68,8 +68,8 @@ typedef struct ptfem_solve_opts {
   int32_t use_graph;    /* capture check_every iterations in a CUDA graph */
   int32_t warm_start;   /* 0: start from phi = 0; 1: start from the solution already on the device */
   int32_t sample_spmv;  /* >0: after the solve, time this many launches of the solve's SpMV kernel (stats.spmv_ms) */
-  int32_t coarse_nodes; /* PTFEM_PRECOND_TWOLEVEL: unknowns of the coarsest (exactly inverted) grid, 0 = default (2000) */
-  int32_t coarse_levels;/* PTFEM_PRECOND_TWOLEVEL: extra finer diagonal-only grids (0..3), each halves the cell size;
+  int32_t coarse_nodes; /* PTFEM_PRECOND_TWOLEVEL: unknowns of the coarsest (exactly inverted) grid, 0 = default (300) */
+  int32_t coarse_levels;/* PTFEM_PRECOND_TWOLEVEL: extra finer diagonal-only grids (0..5), each halves the cell size;
                            -1 (default) = as many as keep >= 16 mesh nodes per cell of the finest grid */
 } ptfem_solve_opts;
 
@@ -188,6 +188,32 @@ int ptfem_sample_polyline(ptfem_mesh* m, int32_t sys, int64_t npts, const double
    the copy overlaps the metric reductions of this system and the element pass of the next one */
 int ptfem_recover_current_async(ptfem_mesh* m, int32_t sys, int32_t method, double* J /*[nn*3], pinned*/);
 int ptfem_current_get(ptfem_mesh* m, double* J /*[nn*3]*/);
+/* nodal currents of EVERY system of the last solve in two launches (lumped / average; L2 goes system by system):
+ * the sweep form of `Calculate Volume Current` (one ElmerSolver run per sweep point in the reference,
+ * run_sweep.py:301-341).  J, if not NULL, receives [nsys][nn][3]; wait = 0 (J in pinned memory) leaves the copy running
+ * on the side stream until the next ptfem_ctx_sync.  Afterwards the per-system metric calls and
+ * ptfem_recover_current(sys, same method) use these currents without recomputing them. */
+int ptfem_recover_current_batch(ptfem_mesh* m, int32_t method, double* J /*[nsys*nn*3] or NULL*/, int32_t wait);
+
+/* -- K12, batched: any number of the three reductions above, for any systems, in ONE pass over the mesh per kind and one
+ *    device->host read-back (a sweep asks for the same few metrics of every configuration). ---------------------------- */
+#define PTFEM_METRIC_NODES 0       /* ptfem_metric_nodes       -> out[0..3]  = {count, sum, max, min}             */
+#define PTFEM_METRIC_PAD_CURRENT 1 /* ptfem_metric_pad_current -> out[0..2]  = {I_signed, area, count}            */
+#define PTFEM_METRIC_ROI 2         /* ptfem_metric_roi         -> out[0..6*nmult-1]                               */
+#define PTFEM_METRIC_OUT_STRIDE 24
+typedef struct ptfem_metric_req {
+  int32_t kind, sys;
+  int32_t field, mode;      /* NODES */
+  double zmin, zmax;        /* NODES, PAD_CURRENT (zmin) */
+  double scale_r;           /* NODES, PAD_CURRENT */
+  ptfem_footprint fp[2];    /* NODES (nfp of them), PAD_CURRENT (fp[0]) */
+  int32_t nfp;
+  int32_t include_tris;     /* ROI */
+  double cen[3], r0, mult[4];
+  int32_t nmult, pad_;
+  double z0, z1;
+} ptfem_metric_req;
+int ptfem_metrics_batch(ptfem_mesh* m, int32_t nreq, const ptfem_metric_req* req, double* out /*[nreq][PTFEM_METRIC_OUT_STRIDE]*/);
 
 /* -- multi-GPU: row-partitioned single solve (config #5).  The caller passes an ncclUniqueId
  *    (128 bytes) obtained on rank 0 via ptfem_dist_unique_id and broadcast by the launcher. ---- */

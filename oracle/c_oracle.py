@@ -143,12 +143,12 @@ class CSystem:
         return x, it, rel.value
 
     # -- Jacobi + geometric coarse grids (restates coarse_oracle.py in C; same grid / level / weight rules) --------
-    def coarse_setup(self, coarse_nodes=2000, extra_levels=-1, level_weight=None):
+    def coarse_setup(self, coarse_nodes=300, extra_levels=-1, level_weight=None):
         """Grids, Galerkin operators and their inverses for :meth:`pcg_coarse`.  Returns the set-up dict."""
         from . import coarse_oracle as cor
         L = lib()
         lo, hi = self.nodes.min(axis=0), self.nodes.max(axis=0)
-        base = cor.choose_grid(lo, hi, float(coarse_nodes if coarse_nodes > 0 else 2000))
+        base = cor.choose_grid(lo, hi, float(coarse_nodes if coarse_nodes > 0 else 300))
         nlev = cor.level_count(self.nn, base, extra_levels)
         if level_weight is None:
             level_weight = 2.0 / (nlev + 1)

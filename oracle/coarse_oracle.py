@@ -36,7 +36,7 @@ def level_count(nn, base_cells, extra_levels):
     """Levels used: requested finer levels are dropped until >= 8 (requested) / 16 (automatic) nodes per finest cell."""
     cells = float(np.prod(base_cells))
     min_rows = 16.0 if extra_levels < 0 else 8.0
-    nlev = 4 if extra_levels < 0 else min(extra_levels, 3) + 1
+    nlev = 6 if extra_levels < 0 else min(extra_levels, 5) + 1
     while nlev > 1 and cells * 8.0 ** (nlev - 1) * min_rows > nn:
         nlev -= 1
     return nlev
@@ -63,9 +63,9 @@ def interpolation(nodes, free, lo, hi, n):
 class CoarsePreconditioner:
     """M^-1 for the eliminated matrix K (Dirichlet rows = identity rows) of a mesh with nodes ``nodes``."""
 
-    def __init__(self, K, nodes, is_dirichlet, coarse_nodes=2000, extra_levels=-1, level_weight=None):
+    def __init__(self, K, nodes, is_dirichlet, coarse_nodes=300, extra_levels=-1, level_weight=None):
         lo, hi = nodes.min(axis=0), nodes.max(axis=0)
-        base = choose_grid(lo, hi, float(coarse_nodes if coarse_nodes > 0 else 2000))
+        base = choose_grid(lo, hi, float(coarse_nodes if coarse_nodes > 0 else 300))
         self.nlev = level_count(nodes.shape[0], base, extra_levels)
         free = (~np.asarray(is_dirichlet, dtype=bool)).astype(np.float64)
         # the additive levels overlap in what they correct: each is weighted by 2 / (levels + 1) against the Jacobi term

@@ -462,12 +462,12 @@ static void grid_prolong_add(const int32_t* nc, const double* yf, const double* 
 int oc_pcg_coarse(int64_t nn, const int32_t* rowptr, const int32_t* col, const double* val, const double* b, double* x,
                   double rtol, int maxit, double* rel_out, int nlev, const int32_t* n, const int32_t* node0,
                   const double* t, const uint8_t* isdir, const double* bdiag, const double* bdense) {
-  if (nlev < 1 || nlev > 4) return -1;
+  if (nlev < 1 || nlev > 6) return -1;
   int nth = 1;
 #ifdef _OPENMP
   nth = omp_get_max_threads();
 #endif
-  int64_t kl[4], off[4];
+  int64_t kl[6], off[6];
   int64_t tot = 0;
   for (int l = 0; l < nlev; ++l) {
     kl[l] = (int64_t)(n[3 * l] + 1) * (n[3 * l + 1] + 1) * (n[3 * l + 2] + 1);

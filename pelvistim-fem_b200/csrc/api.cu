@@ -17,6 +17,9 @@ int ptfem_do_bc_neumann_tris(ptfem_mesh* m, int32_t rhs, int64_t n, const int32_
 int ptfem_apply_bc(ptfem_mesh* m, double* dinv_out, int* S_out);
 int ptfem_do_element_fields(ptfem_mesh* m, int sys);
 int ptfem_do_recover(ptfem_mesh* m, int sys, int method);
+int ptfem_do_recover_batch(ptfem_mesh* m, int method);
+int ptfem_do_metrics_batch(ptfem_mesh* m, int32_t nreq, const ptfem_metric_req* req, double* out);
+const double* ptfem_current_ptr(ptfem_mesh* m);
 int ptfem_do_metric_nodes(ptfem_mesh* m, int sys, int field, double zmin, double zmax, int mode, const ptfem_footprint* fp,
                           int nfp, double scale_r, double out[4]);
 int ptfem_do_metric_pad_current(ptfem_mesh* m, int sys, double zmin, const ptfem_footprint* fp, double scale_r, double out[3]);
@@ -149,7 +152,7 @@ int coarse_replica_prepare(ptfem_mesh* full) {
   // spaces prepared by an earlier solve of the replica on this matrix are taken as they are (the caller chose them)
   if (full->coarse && full->coarse->geom_ok && full->coarse->matrix_epoch == full->matrix_epoch) return PTFEM_OK;
   int rc = coarse_prepare(full, 0, -1, full->S);
-  if (rc == PTFEM_ERR_STATE) rc = coarse_prepare(full, 500, -1, full->S);
+  if (rc == PTFEM_ERR_STATE) rc = coarse_prepare(full, 80, -1, full->S);
   return rc;
 }
 }  // namespace ptfem
@@ -321,6 +324,7 @@ int ptfem_mesh_set_coords(ptfem_mesh* m, const double* xyz) {
   PT_TRY(device_bbox(m));
   if (m->coarse) m->coarse->geom_ok = false;
   m->has_geom = false;
+  m->has_tcen = false;
   if (m->has_pattern) PT_TRY(ptfem_build_geometry(m));
   m->nval = 0;  // values must be re-assembled
   m->bc_dirty = true;
@@ -456,7 +460,7 @@ int ptfem_solve_device(ptfem_mesh* m, const ptfem_solve_opts* opts, ptfem_solve_
     // a strongly graded mesh can leave coarse cells (nearly) empty and the Galerkin matrix singular: the automatic
     // choice then retries with a 4x coarser grid and finally settles for Jacobi; an explicit request reports the error
     if (rcp == PTFEM_ERR_STATE && automatic) {
-      const int nodes = (o.coarse_nodes > 0 ? o.coarse_nodes : 2000) / 4;
+      const int nodes = (o.coarse_nodes > 0 ? o.coarse_nodes : kDefaultCoarseNodes) / 4;
       rcp = coarse_prepare(m, nodes < 27 ? 27 : nodes, o.coarse_levels, m->S);
       if (rcp == PTFEM_ERR_STATE) {
         o.precond = PTFEM_PRECOND_JACOBI;
@@ -470,6 +474,8 @@ int ptfem_solve_device(ptfem_mesh* m, const ptfem_solve_opts* opts, ptfem_solve_
     }
   }
   m->J_sys = -1;
+  m->J_all_valid = false;
+  m->J_from_all = false;
   if (!o.warm_start) PT_CK(cudaMemsetAsync(m->phi.p, 0, (size_t)m->nn * m->S * sizeof(double), m->ctx->stream));
   int rc = pcg_solve(m->ctx, A, m->work, o, m->phi.p, stats);
   if (stats) {
@@ -527,6 +533,8 @@ int ptfem_phi_set(ptfem_mesh* m, int32_t sys, const double* phi) {
   PT_LAUNCH_CHECK(m->ctx);
   PT_CK(cudaStreamSynchronize(m->ctx->stream));
   m->J_sys = -1;
+  m->J_all_valid = false;
+  m->J_from_all = false;
   return PTFEM_OK;
 }
 
@@ -611,7 +619,7 @@ int ptfem_recover_current(ptfem_mesh* m, int32_t sys, int32_t method, double* J)
   PT_CK(cudaSetDevice(m->ctx->device));
   PT_TRY(ptfem_do_recover(m, sys, method));
   if (J) {
-    PT_CK(cudaMemcpyAsync(J, m->Jnode.p, (size_t)m->nn * 3 * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
+    PT_CK(cudaMemcpyAsync(J, ptfem_current_ptr(m), (size_t)m->nn * 3 * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
     PT_CK(cudaStreamSynchronize(m->ctx->stream));
   }
   return PTFEM_OK;
@@ -626,7 +634,7 @@ int ptfem_recover_current_async(ptfem_mesh* m, int32_t sys, int32_t method, doub
   // overwrites the device buffer, metric kernels of this system only read it and run concurrently
   PT_CK(cudaEventRecord(ctx->ev_j_ready, ctx->stream));
   PT_CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_j_ready, 0));
-  PT_CK(cudaMemcpyAsync(J, m->Jnode.p, (size_t)m->nn * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream2));
+  PT_CK(cudaMemcpyAsync(J, ptfem_current_ptr(m), (size_t)m->nn * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream2));
   PT_CK(cudaEventRecord(ctx->ev_j_copied, ctx->stream2));
   m->j_copy_pending = true;
   return PTFEM_OK;
@@ -634,11 +642,40 @@ int ptfem_recover_current_async(ptfem_mesh* m, int32_t sys, int32_t method, doub
 
 int ptfem_current_get(ptfem_mesh* m, double* J) {
   PT_ARG(m && J, "null pointer");
-  if (!m->Jnode.p || m->J_sys < 0) return set_err(PTFEM_ERR_STATE, "no recovered current on the device");
+  if (!ptfem_current_ptr(m) || m->J_sys < 0) return set_err(PTFEM_ERR_STATE, "no recovered current on the device");
   PT_CK(cudaSetDevice(m->ctx->device));
-  PT_CK(cudaMemcpyAsync(J, m->Jnode.p, (size_t)m->nn * 3 * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
+  PT_CK(cudaMemcpyAsync(J, ptfem_current_ptr(m), (size_t)m->nn * 3 * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
   PT_CK(cudaStreamSynchronize(m->ctx->stream));
   return PTFEM_OK;
+}
+
+int ptfem_recover_current_batch(ptfem_mesh* m, int32_t method, double* J, int32_t wait) {
+  PT_ARG(m, "null mesh");
+  ptfem_ctx* ctx = m->ctx;
+  PT_CK(cudaSetDevice(ctx->device));
+  PT_TRY(ptfem_do_recover_batch(m, method));
+  if (J) {
+    const size_t bytes = (size_t)m->nsys_user * m->nn * 3 * sizeof(double);
+    if (wait) {
+      PT_CK(cudaMemcpyAsync(J, m->Jall.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+      PT_CK(cudaStreamSynchronize(ctx->stream));
+    } else {
+      // read-back on the side stream; the caller's next ptfem_ctx_sync completes it, and the next recovery waits for it
+      PT_CK(cudaEventRecord(ctx->ev_j_ready, ctx->stream));
+      PT_CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_j_ready, 0));
+      PT_CK(cudaMemcpyAsync(J, m->Jall.p, bytes, cudaMemcpyDeviceToHost, ctx->stream2));
+      PT_CK(cudaEventRecord(ctx->ev_j_copied, ctx->stream2));
+      m->j_copy_pending = true;
+    }
+  }
+  return PTFEM_OK;
+}
+
+int ptfem_metrics_batch(ptfem_mesh* m, int32_t nreq, const ptfem_metric_req* req, double* out) {
+  PT_ARG(m && req && out, "null pointer");
+  PT_ARG(nreq >= 1 && nreq <= 256, "1..256 requests per batch");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  return ptfem_do_metrics_batch(m, nreq, req, out);
 }
 
 int ptfem_metric_nodes(ptfem_mesh* m, int32_t sys, int32_t field, double zmin, double zmax, int32_t mode,

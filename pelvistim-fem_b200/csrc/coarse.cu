@@ -1032,7 +1032,11 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
   if (m->nvalp != 1) return set_err(PTFEM_ERR_ARG, "the two-level preconditioner needs one shared matrix (multi-RHS), not %d", m->nval);
   if (!m->coarse) m->coarse = new CoarseSpace();
   CoarseSpace& cs = *m->coarse;
-  if (target_nodes <= 0) target_nodes = 2000;
+  // The iteration count is set by the FINEST grid; the exactly inverted one only has to be coarse enough for its O(k^3)
+  // inverse to cost nothing: 8x6x4 cells (315 unknowns) under three diagonal-only levels needs the same 60 iterations on the
+  // 20 M-tet slab as 16x12x8 (1989 unknowns) under two (CPU study, profiles/r02_coarse_grid_size_cpu.txt), and its inverse
+  // takes 0.1 ms instead of 6.4.
+  if (target_nodes <= 0) target_nodes = kDefaultCoarseNodes;
   if (extra_levels > kMaxCoarseLevels - 1) extra_levels = kMaxCoarseLevels - 1;
   struct Events {  // destroyed on every return path
     cudaEvent_t e0 = nullptr, e1 = nullptr;

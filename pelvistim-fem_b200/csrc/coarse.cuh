@@ -10,7 +10,8 @@
 #pragma once
 #include "common.cuh"
 
-constexpr int kMaxCoarseLevels = 4;
+constexpr int kMaxCoarseLevels = 6;
+constexpr int kDefaultCoarseNodes = 300;   // unknowns of the exactly inverted grid (see coarse_prepare)
 
 struct CoarseGrid {  // passed by value to kernels
   int n[3];          // cells per axis

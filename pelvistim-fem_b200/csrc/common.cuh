@@ -203,7 +203,15 @@ struct ptfem_mesh {
   ptfem::DevBuf<double> mval;     // [nnz] consistent mass values (L2 recovery)
   ptfem::DevBuf<double> mdinv, mrhs, mx; // mass-matrix Jacobi, rhs [nn][4], solution [nn][4]
   ptfem::DevBuf<double> phis;     // [nn] VTK-smoothed potential (ROI metric)
-  int J_sys = -1;                 // system whose nodal current is in Jnode
+  int J_sys = -1;                 // system whose nodal current is current (in Jnode, or a block of Jall when J_from_all)
+  ptfem::DevBuf<double> Jall;     // [nsys][nn][3] nodal currents of every system (ptfem_recover_current_batch)
+  ptfem::DevBuf<double> Jelem_all;// [nt][3][S] element currents of every system (scratch of the batched recovery)
+  bool J_all_valid = false;       // Jall holds the currents of the solution on the device
+  int J_all_method = -1;
+  bool J_from_all = false;        // the current system's nodal current is Jall + J_sys*nn*3
+  ptfem::DevBuf<float> tcen;      // [nt][4] tet centroids in single precision (prefilter of the ROI scans)
+  bool has_tcen = false;
+  ptfem::DevBuf<double> phis_all; // [nroi][nn] smoothed potentials of a metric batch
   bool j_copy_pending = false;    // an asynchronous device->host copy of Jnode may still be reading it
   int mass_iters = 0;
   ptfem::DevBuf<double> scratch_d;

@@ -529,6 +529,14 @@ static int wait_j_copy(ptfem_mesh* m) {
 
 int ptfem_do_recover(ptfem_mesh* m, int sys, int method) {
   ptfem_ctx* ctx = m->ctx;
+  if (m->J_all_valid && m->J_all_method == method) {   // already there (ptfem_recover_current_batch)
+    PT_TRY(check_sys(m, sys));
+    m->J_sys = sys;
+    m->J_from_all = true;
+    return PTFEM_OK;
+  }
+  m->J_all_valid = false;
+  m->J_from_all = false;
   PT_TRY(ptfem_do_element_fields(m, sys));
   PT_TRY(m->Jnode.alloc((size_t)m->nn * 3));
   const int grid = ceil_div(m->nn, 128);
@@ -579,8 +587,15 @@ int ptfem_do_recover(ptfem_mesh* m, int sys, int method) {
   return PTFEM_OK;
 }
 
+// nodal current of system sys on the device: a block of the batched recovery, or the single-system buffer
+static const double* j_of(ptfem_mesh* m, int sys) {
+  if (m->J_all_valid && m->Jall.p && sys >= 0 && sys < m->nsys_user) return m->Jall.p + (size_t)sys * m->nn * 3;
+  if (m->Jnode.p && m->J_sys == sys && !m->J_from_all) return m->Jnode.p;
+  return nullptr;
+}
+const double* ptfem_current_ptr(ptfem_mesh* m) { return m->J_sys >= 0 ? j_of(m, m->J_sys) : nullptr; }
 static int need_J(ptfem_mesh* m, int sys) {
-  if (!m->Jnode.p || m->J_sys != sys)
+  if (!j_of(m, sys))
     return set_err(PTFEM_ERR_STATE, "nodal current of system %d has not been recovered (ptfem_recover_current)", sys);
   return PTFEM_OK;
 }
@@ -596,7 +611,7 @@ int ptfem_do_metric_nodes(ptfem_mesh* m, int sys, int field, double zmin, double
   for (int k = 0; k < nfp; ++k) pk.f[k] = fp[k];
   const int grid = red_grid(ctx, m->nn);
   PT_TRY(need_partials(m, grid, 4));
-  metric_nodes_kernel<<<grid, kT, 0, ctx->stream>>>(m->xyz.p, m->nn, m->phi.p, m->S, sys, m->Jnode.p, field, zmin, zmax, mode,
+  metric_nodes_kernel<<<grid, kT, 0, ctx->stream>>>(m->xyz.p, m->nn, m->phi.p, m->S, sys, j_of(m, sys), field, zmin, zmax, mode,
                                                     pk, scale_r, m->scratch_d.p);
   PT_LAUNCH_CHECK(ctx);
   const int ops[4] = {0, 0, 1, 2};
@@ -609,7 +624,7 @@ int ptfem_do_metric_pad_current(ptfem_mesh* m, int sys, double zmin, const ptfem
   PT_TRY(need_J(m, sys));
   const int grid = red_grid(ctx, m->nb);
   PT_TRY(need_partials(m, grid, 3));
-  pad_current_kernel<<<grid, kT, 0, ctx->stream>>>(m->xyz.p, m->tris.p, m->nb, m->tri_area.p, m->Jnode.p, zmin, *fp, scale_r,
+  pad_current_kernel<<<grid, kT, 0, ctx->stream>>>(m->xyz.p, m->tris.p, m->nb, m->tri_area.p, j_of(m, sys), zmin, *fp, scale_r,
                                                    m->scratch_d.p);
   PT_LAUNCH_CHECK(ctx);
   const int ops[3] = {0, 0, 0};
@@ -641,7 +656,7 @@ int ptfem_do_metric_roi(ptfem_mesh* m, int sys, const double cen[3], double r0, 
   constexpr int NV = 6 * kMaxMult;
   PT_TRY(need_partials(m, grid, NV));
   roi_kernel<<<grid, kT, 0, ctx->stream>>>(m->xyz.p, m->tets.p, m->nt, m->tris.p, include_tris ? m->nb : 0, m->phis.p,
-                                           m->Jnode.p, a, m->scratch_d.p);
+                                           j_of(m, sys), a, m->scratch_d.p);
   PT_LAUNCH_CHECK(ctx);
   int ops[NV];
   for (int k = 0; k < NV; ++k) ops[k] = 0;
@@ -667,7 +682,7 @@ int ptfem_do_metric_jstats(ptfem_mesh* m, int sys, double shift, double out[3]) 
   PT_TRY(need_J(m, sys));
   const int grid = red_grid(ctx, m->nn);
   PT_TRY(need_partials(m, grid, 3));
-  jstats_kernel<<<grid, kT, 0, ctx->stream>>>(m->Jnode.p, m->nn, shift, m->scratch_d.p);
+  jstats_kernel<<<grid, kT, 0, ctx->stream>>>(j_of(m, sys), m->nn, shift, m->scratch_d.p);
   PT_LAUNCH_CHECK(ctx);
   const int ops[3] = {0, 0, 0};
   return finish_reduce(m, grid, 3, ops, out);
@@ -723,5 +738,499 @@ int ptfem_do_sample_polyline(ptfem_mesh* m, int sys, int64_t npts, const double*
   if (phi_out) PT_CK(cudaMemcpyAsync(phi_out, d_v.p, npts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (af_out) PT_CK(cudaMemcpyAsync(af_out, d_af.p, npts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   PT_CK(cudaStreamSynchronize(ctx->stream));
+  return PTFEM_OK;
+}
+
+// =====================================================================================================
+// Sweep forms: nodal currents of every system in two launches, and any number of metric reductions in one
+// pass per kind with a single read-back.  The reference runs one ElmerSolver + pyvista extraction per sweep
+// point (step02_electrodes/run_sweep.py:301-341, step03_ankle_layers/run_layered_sweep.py:1061-1062); here the
+// S configurations solved together are also post-processed together (vectors are [nn][S], system fastest).
+// =====================================================================================================
+namespace {
+
+// ---- K10/K11 batched: J_e of all S systems -> Je[nt][3][S]; LPT = S/2 lanes per tet (one 16-byte gather per node) ----
+template <int S>
+__global__ void __launch_bounds__(256) element_J_all_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ tets,
+                                                            int64_t nt, const double* __restrict__ phi,
+                                                            const uint8_t* __restrict__ regidx, const double* __restrict__ sigma,
+                                                            int VS, int nreg, double* __restrict__ Je) {
+  constexpr int LPT = S >= 2 ? S / 2 : 1;
+  constexpr int NV = S >= 2 ? 2 : 1;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t e = gid / LPT;
+  const int lane = (int)(gid % LPT);
+  if (e >= nt) return;
+  double g[4][3];
+  tet_grads(xyz, tets + e * 4, g);
+  double ex[NV], ey[NV], ez[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) ex[v] = ey[v] = ez[v] = 0.0;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const double* pp = phi + (int64_t)tets[e * 4 + a] * S + NV * lane;
+    double pv[NV];
+    if constexpr (NV == 2) {
+      const double2 t = *reinterpret_cast<const double2*>(pp);
+      pv[0] = t.x;
+      pv[1] = t.y;
+    } else {
+      pv[0] = pp[0];
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      ex[v] -= pv[v] * g[a][0];
+      ey[v] -= pv[v] * g[a][1];
+      ez[v] -= pv[v] * g[a][2];
+    }
+  }
+  const int r = regidx[e];
+  double sg[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) sg[v] = sigma[(size_t)(VS == 1 ? 0 : NV * lane + v) * nreg + r];
+  double* out = Je + (size_t)e * 3 * S + NV * lane;
+  if constexpr (NV == 2) {
+    *reinterpret_cast<double2*>(out) = make_double2(sg[0] * ex[0], sg[1] * ex[1]);
+    *reinterpret_cast<double2*>(out + S) = make_double2(sg[0] * ey[0], sg[1] * ey[1]);
+    *reinterpret_cast<double2*>(out + 2 * S) = make_double2(sg[0] * ez[0], sg[1] * ez[1]);
+  } else {
+    out[0] = sg[0] * ex[0];
+    out[S] = sg[0] * ey[0];
+    out[2 * S] = sg[0] * ez[0];
+  }
+}
+
+// node gather (sorted node -> tet lists: fixed order): Jall[sys][i][k] ; mode 1 lumped, 2 unweighted average
+template <int S>
+__global__ void __launch_bounds__(256) recover_gather_all_kernel(const int32_t* __restrict__ n2t_ptr, const int32_t* __restrict__ n2t,
+                                                                 const double* __restrict__ vol, const double* __restrict__ Je,
+                                                                 const double* __restrict__ mlump, int64_t nn, int mode, int nsys,
+                                                                 double* __restrict__ Jall) {
+  constexpr int LPN = S >= 2 ? S / 2 : 1;
+  constexpr int NV = S >= 2 ? 2 : 1;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = gid / LPN;
+  const int lane = (int)(gid % LPN);
+  if (i >= nn) return;
+  const int32_t b = n2t_ptr[i], e = n2t_ptr[i + 1];
+  double acc[3][NV];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[k][v] = 0.0;
+  for (int32_t q = b; q < e; ++q) {
+    const int64_t t = n2t[q];
+    const double w = mode == 2 ? 1.0 : 0.25 * vol[t];
+    const double* src = Je + (size_t)t * 3 * S + NV * lane;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if constexpr (NV == 2) {
+        const double2 jv = *reinterpret_cast<const double2*>(src + k * S);
+        acc[k][0] += w * jv.x;
+        acc[k][1] += w * jv.y;
+      } else {
+        acc[k][0] += w * src[k * S];
+      }
+    }
+  }
+  double d = mode == 1 ? mlump[i] : (double)(e - b);
+  d = d > 0.0 ? 1.0 / d : 0.0;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int sys = NV * lane + v;
+    if (sys >= nsys) continue;
+    double* out = Jall + ((size_t)sys * nn + i) * 3;
+    out[0] = acc[0][v] * d;
+    out[1] = acc[1][v] * d;
+    out[2] = acc[2][v] * d;
+  }
+}
+
+template <int S>
+int recover_batch_t(ptfem_mesh* m, int mode) {
+  ptfem_ctx* ctx = m->ctx;
+  constexpr int L = S >= 2 ? S / 2 : 1;
+  if (m->nt > 0) {
+    element_J_all_kernel<S><<<ceil_div(m->nt * L, 256), 256, 0, ctx->stream>>>(m->xyz.p, m->tets.p, m->nt, m->phi.p, m->regidx.p,
+                                                                               m->sigma_tab.p, m->nvalp, m->nreg, m->Jelem_all.p);
+    PT_LAUNCH_CHECK(ctx);
+  }
+  recover_gather_all_kernel<S><<<ceil_div(m->nn * L, 256), 256, 0, ctx->stream>>>(m->n2t_ptr.p, m->n2t.p, m->vol.p, m->Jelem_all.p,
+                                                                                  m->mlump.p, m->nn, mode, m->nsys_user, m->Jall.p);
+  PT_LAUNCH_CHECK(ctx);
+  return PTFEM_OK;
+}
+
+// ---- K12 batched -----------------------------------------------------------------------------------------
+// single-precision tet centroids: prefilter of the ROI scans (a cell within the margin is re-tested in double)
+__global__ void tet_centroid_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ tets, int64_t nt,
+                                    float4* __restrict__ cen) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nt) return;
+  double c[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int64_t n = tets[e * 4 + a];
+    c[0] += xyz[n * 3];
+    c[1] += xyz[n * 3 + 1];
+    c[2] += xyz[n * 3 + 2];
+  }
+  cen[e] = make_float4((float)(0.25 * c[0]), (float)(0.25 * c[1]), (float)(0.25 * c[2]), 0.f);
+}
+
+struct BatchReq {   // device copy of one request (+ where its inputs / partials live)
+  ptfem_metric_req r;
+  int32_t slot;     // index among the requests of its kind
+  int32_t pad_;
+};
+
+// blockIdx.y = request (of kind NODES); partial[(slot*gridDim.x + blockIdx.x)*4 ..]
+__global__ void __launch_bounds__(kT) metric_nodes_batch_kernel(const double* __restrict__ xyz, int64_t nn,
+                                                                const double* __restrict__ phi, int S,
+                                                                const double* __restrict__ Jall, const BatchReq* __restrict__ reqs,
+                                                                const int32_t* __restrict__ idx, double* __restrict__ partial) {
+  const BatchReq& q = reqs[idx[blockIdx.y]];
+  const ptfem_metric_req& r = q.r;
+  const double* Jn = Jall + (size_t)r.sys * nn * 3;
+  double v[4] = {0.0, 0.0, -INFINITY, INFINITY};
+  const int64_t stride = (int64_t)gridDim.x * kT;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < nn; i += stride) {
+    const double z = xyz[i * 3 + 2];
+    if (!(z > r.zmin)) continue;
+    if (r.zmax == r.zmax && !(z < r.zmax)) continue;
+    if (r.mode != 0) {
+      const double x = xyz[i * 3], y = xyz[i * 3 + 1];
+      bool inside = false;
+      for (int k = 0; k < r.nfp; ++k) inside = inside || in_footprint(x, y, r.fp[k], r.scale_r);
+      if ((r.mode == 1) != inside) continue;
+    }
+    double f;
+    if (r.field == 1) {
+      f = phi[i * S + r.sys];
+    } else {
+      const double jx = Jn[i * 3], jy = Jn[i * 3 + 1], jz = Jn[i * 3 + 2];
+      f = r.field == 0 ? sqrt(jx * jx + jy * jy + jz * jz) : (r.field == 2 ? fabs(jz) : jz);
+    }
+    v[0] += 1.0;
+    v[1] += f;
+    v[2] = fmax(v[2], f);
+    v[3] = fmin(v[3], f);
+  }
+  const int op[4] = {0, 0, 1, 2};
+  block_reduce_ops<4>(v, op, partial + (size_t)blockIdx.y * gridDim.x * 4);
+}
+
+__global__ void __launch_bounds__(kT) pad_current_batch_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ tris,
+                                                               int64_t nb, const double* __restrict__ tri_area, int64_t nn,
+                                                               const double* __restrict__ Jall, const BatchReq* __restrict__ reqs,
+                                                               const int32_t* __restrict__ idx, double* __restrict__ partial) {
+  const ptfem_metric_req& r = reqs[idx[blockIdx.y]].r;
+  const double* Jn = Jall + (size_t)r.sys * nn * 3;
+  double v[3] = {0.0, 0.0, 0.0};
+  const int64_t stride = (int64_t)gridDim.x * kT;
+  for (int64_t t = (int64_t)blockIdx.x * kT + threadIdx.x; t < nb; t += stride) {
+    const int64_t a = tris[t * 3], b = tris[t * 3 + 1], c = tris[t * 3 + 2];
+    const double cx = (xyz[a * 3] + xyz[b * 3] + xyz[c * 3]) / 3.0;
+    const double cy = (xyz[a * 3 + 1] + xyz[b * 3 + 1] + xyz[c * 3 + 1]) / 3.0;
+    const double cz = (xyz[a * 3 + 2] + xyz[b * 3 + 2] + xyz[c * 3 + 2]) / 3.0;
+    if (!(cz > r.zmin) || !in_footprint(cx, cy, r.fp[0], r.scale_r)) continue;
+    const double jz = (Jn[a * 3 + 2] + Jn[b * 3 + 2] + Jn[c * 3 + 2]) / 3.0;
+    v[0] += jz * tri_area[t];
+    v[1] += tri_area[t];
+    v[2] += 1.0;
+  }
+  const int op[3] = {0, 0, 0};
+  block_reduce_ops<3>(v, op, partial + (size_t)blockIdx.y * gridDim.x * 3);
+}
+
+// VTK point smoothing for every ROI request (blockIdx.y): phis[slot][i] for the nodes an in-ROI cell can use
+__global__ void smooth_phi_batch_kernel(const int32_t* __restrict__ n2t_ptr, const int32_t* __restrict__ n2t,
+                                        const int32_t* __restrict__ n2b_ptr, const int32_t* __restrict__ n2b,
+                                        const int32_t* __restrict__ tets, const int32_t* __restrict__ tris,
+                                        const double* __restrict__ phi, int S, int64_t nn, const double* __restrict__ xyz,
+                                        double h_max, const BatchReq* __restrict__ reqs, const int32_t* __restrict__ idx,
+                                        double* __restrict__ phis_all) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nn) return;
+  const ptfem_metric_req& r = reqs[idx[blockIdx.y]].r;
+  const double rad = r.r0 * r.mult[r.nmult - 1] + 1.01 * h_max;
+  const double dx = xyz[3 * i] - r.cen[0], dy = xyz[3 * i + 1] - r.cen[1], dz = xyz[3 * i + 2] - r.cen[2];
+  if (dx * dx + dy * dy + dz * dz > rad * rad) return;
+  const int sys = r.sys;
+  double acc = 0.0;
+  int cnt = 0;
+  for (int32_t k = n2t_ptr[i]; k < n2t_ptr[i + 1]; ++k) {
+    const int64_t t = n2t[k];
+    acc += (phi[(int64_t)tets[t * 4] * S + sys] + phi[(int64_t)tets[t * 4 + 1] * S + sys] +
+            phi[(int64_t)tets[t * 4 + 2] * S + sys] + phi[(int64_t)tets[t * 4 + 3] * S + sys]) / 4.0;
+    ++cnt;
+  }
+  if (r.include_tris) {
+    for (int32_t k = n2b_ptr[i]; k < n2b_ptr[i + 1]; ++k) {
+      const int64_t t = n2b[k];
+      acc += (phi[(int64_t)tris[t * 3] * S + sys] + phi[(int64_t)tris[t * 3 + 1] * S + sys] +
+              phi[(int64_t)tris[t * 3 + 2] * S + sys]) / 3.0;
+      ++cnt;
+    }
+  }
+  phis_all[(size_t)blockIdx.y * nn + i] = cnt > 0 ? acc / (double)cnt : 0.0;
+}
+
+// the per-cell part of roi_kernel for one cell known to be a candidate; adds to v[6*kMaxMult]
+__device__ __forceinline__ void roi_cell_accumulate(const double* __restrict__ xyz, const int32_t* __restrict__ tets, int64_t nt,
+                                                    const int32_t* __restrict__ tris, int64_t c, const double* __restrict__ phis,
+                                                    const double* __restrict__ Jn, const ptfem_metric_req& a, double (&v)[6 * kMaxMult]) {
+  double cx, cy, cz, jm, em;
+  const double rmax = a.r0 * a.mult[a.nmult - 1];
+  if (c < nt) {
+    const int32_t* t = tets + c * 4;
+    cx = cy = cz = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t n = t[k];
+      cx += xyz[n * 3]; cy += xyz[n * 3 + 1]; cz += xyz[n * 3 + 2];
+    }
+    cx *= 0.25; cy *= 0.25; cz *= 0.25;
+    const double dx = cx - a.cen[0], dy = cy - a.cen[1], dz = cz - a.cen[2];
+    if (!(sqrt(dx * dx + dy * dy + dz * dz) < rmax)) return;
+    double jx = 0.0, jy = 0.0, jz = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int64_t n = t[k];
+      jx += Jn[n * 3]; jy += Jn[n * 3 + 1]; jz += Jn[n * 3 + 2];
+    }
+    jx *= 0.25; jy *= 0.25; jz *= 0.25;
+    jm = sqrt(jx * jx + jy * jy + jz * jz);
+    double g[4][3];
+    tet_grads(xyz, t, g);
+    double ex = 0.0, ey = 0.0, ez = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double pv = phis[t[k]];
+      ex += pv * g[k][0]; ey += pv * g[k][1]; ez += pv * g[k][2];
+    }
+    em = sqrt(ex * ex + ey * ey + ez * ez);
+  } else {
+    const int32_t* t = tris + (c - nt) * 3;
+    const int64_t n0 = t[0], n1 = t[1], n2 = t[2];
+    cx = (xyz[n0 * 3] + xyz[n1 * 3] + xyz[n2 * 3]) / 3.0;
+    cy = (xyz[n0 * 3 + 1] + xyz[n1 * 3 + 1] + xyz[n2 * 3 + 1]) / 3.0;
+    cz = (xyz[n0 * 3 + 2] + xyz[n1 * 3 + 2] + xyz[n2 * 3 + 2]) / 3.0;
+    const double dx = cx - a.cen[0], dy = cy - a.cen[1], dz = cz - a.cen[2];
+    if (!(sqrt(dx * dx + dy * dy + dz * dz) < rmax)) return;
+    const double jx = (Jn[n0 * 3] + Jn[n1 * 3] + Jn[n2 * 3]) / 3.0;
+    const double jy = (Jn[n0 * 3 + 1] + Jn[n1 * 3 + 1] + Jn[n2 * 3 + 1]) / 3.0;
+    const double jz = (Jn[n0 * 3 + 2] + Jn[n1 * 3 + 2] + Jn[n2 * 3 + 2]) / 3.0;
+    jm = sqrt(jx * jx + jy * jy + jz * jz);
+    const double e1x = xyz[n1 * 3] - xyz[n0 * 3], e1y = xyz[n1 * 3 + 1] - xyz[n0 * 3 + 1], e1z = xyz[n1 * 3 + 2] - xyz[n0 * 3 + 2];
+    const double e2x = xyz[n2 * 3] - xyz[n0 * 3], e2y = xyz[n2 * 3 + 1] - xyz[n0 * 3 + 1], e2z = xyz[n2 * 3 + 2] - xyz[n0 * 3 + 2];
+    const double nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
+    double n2v = nx * nx + ny * ny + nz * nz;
+    n2v = n2v > 0.0 ? n2v : 1.0;
+    const double d1 = phis[n1] - phis[n0], d2 = phis[n2] - phis[n0];
+    const double ax = e2y * nz - e2z * ny, ay = e2z * nx - e2x * nz, az = e2x * ny - e2y * nx;
+    const double bx = ny * e1z - nz * e1y, by = nz * e1x - nx * e1z, bz = nx * e1y - ny * e1x;
+    const double ex = (d1 * ax + d2 * bx) / n2v, ey = (d1 * ay + d2 * by) / n2v, ez = (d1 * az + d2 * bz) / n2v;
+    em = sqrt(ex * ex + ey * ey + ez * ez);
+  }
+  const double dx = cx - a.cen[0], dy = cy - a.cen[1], dz = cz - a.cen[2];
+  const double dist = sqrt(dx * dx + dy * dy + dz * dz);
+#pragma unroll
+  for (int mi = 0; mi < kMaxMult; ++mi) {
+    if (mi < a.nmult && dist < a.r0 * a.mult[mi]) {
+      v[mi * 6 + 0] += 1.0;
+      v[mi * 6 + 1] += jm;
+      v[mi * 6 + 2] += em;
+      if (cz > a.z1) v[mi * 6 + 3] += 1.0;
+      else if (cz > a.z0) v[mi * 6 + 4] += 1.0;
+      else v[mi * 6 + 5] += 1.0;
+    }
+  }
+}
+
+// blockIdx.y = ROI request.  Tets are prefiltered by their single-precision centroid (16 bytes per tet instead of the
+// 4 node ids + 4 gathered coordinates), boundary triangles are tested directly.
+__global__ void __launch_bounds__(kT) roi_batch_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ tets, int64_t nt,
+                                                       const int32_t* __restrict__ tris, int64_t nb, const float4* __restrict__ tcen,
+                                                       int64_t nn, const double* __restrict__ phis_all, const double* __restrict__ Jall,
+                                                       const BatchReq* __restrict__ reqs, const int32_t* __restrict__ idx,
+                                                       double* __restrict__ partial) {
+  const ptfem_metric_req& a = reqs[idx[blockIdx.y]].r;
+  const double* phis = phis_all + (size_t)blockIdx.y * nn;
+  const double* Jn = Jall + (size_t)a.sys * nn * 3;
+  double v[6 * kMaxMult];
+#pragma unroll
+  for (int k = 0; k < 6 * kMaxMult; ++k) v[k] = 0.0;
+  const double rmax = a.r0 * a.mult[a.nmult - 1];
+  // margin of the float prefilter: a few ulps of the coordinates' magnitude
+  const float cxf = (float)a.cen[0], cyf = (float)a.cen[1], czf = (float)a.cen[2];
+  const float big = fmaxf(fmaxf(fabsf(cxf), fabsf(cyf)), fabsf(czf)) + (float)rmax;
+  const float rf = (float)rmax * 1.0001f + 64.f * 1.1920929e-7f * big;
+  const float rf2 = rf * rf;
+  const int64_t stride = (int64_t)gridDim.x * kT;
+  for (int64_t c = (int64_t)blockIdx.x * kT + threadIdx.x; c < nt; c += stride) {
+    const float4 q = __ldg(tcen + c);
+    const float dx = q.x - cxf, dy = q.y - cyf, dz = q.z - czf;
+    if (dx * dx + dy * dy + dz * dz > rf2) continue;
+    roi_cell_accumulate(xyz, tets, nt, tris, c, phis, Jn, a, v);
+  }
+  if (a.include_tris)
+    for (int64_t c = nt + (int64_t)blockIdx.x * kT + threadIdx.x; c < nt + nb; c += stride)
+      roi_cell_accumulate(xyz, tets, nt, tris, c, phis, Jn, a, v);
+  int op[6 * kMaxMult];
+#pragma unroll
+  for (int k = 0; k < 6 * kMaxMult; ++k) op[k] = 0;
+  block_reduce_ops<6 * kMaxMult>(v, op, partial + (size_t)blockIdx.y * gridDim.x * 6 * kMaxMult);
+}
+
+// one warp per (request, slot): fixed lane-strided order over the CTA partials, fixed shuffle tree
+__global__ void finalize_batch_kernel(const double* __restrict__ partial, int nblocks, int nv, int nreq_kind, uint32_t opmask2,
+                                      const int32_t* __restrict__ idx, double* __restrict__ out) {
+  const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (w >= nreq_kind * nv) return;
+  const int rq = w / nv, k = w % nv;
+  const int op = (int)((opmask2 >> (2 * (k < 16 ? k : 15))) & 3u);
+  const double* p = partial + (size_t)rq * nblocks * nv;
+  double a = op == 0 ? 0.0 : (op == 1 ? -INFINITY : INFINITY);
+  for (int b = lane; b < nblocks; b += 32) {
+    const double x = p[(size_t)b * nv + k];
+    a = op == 0 ? a + x : (op == 1 ? fmax(a, x) : fmin(a, x));
+  }
+  a = op == 0 ? warp_sum(a) : (op == 1 ? warp_max(a) : warp_min(a));
+  if (lane == 0) out[(size_t)idx[rq] * PTFEM_METRIC_OUT_STRIDE + k] = a;
+}
+
+}  // namespace
+
+int ptfem_do_recover_batch(ptfem_mesh* m, int method) {
+  PT_TRY(check_sys(m, 0));
+  if (method == PTFEM_RECOVER_L2) {
+    // consistent-mass projection needs a PCG solve per system: system by system into the blocks of Jall
+    PT_TRY(m->Jall.alloc((size_t)m->nsys_user * m->nn * 3));
+    PT_TRY(wait_j_copy(m));
+    for (int s = 0; s < m->nsys_user; ++s) {
+      m->J_all_valid = false;
+      PT_TRY(ptfem_do_recover(m, s, PTFEM_RECOVER_L2));
+      PT_CK(cudaMemcpyAsync(m->Jall.p + (size_t)s * m->nn * 3, m->Jnode.p, (size_t)m->nn * 3 * sizeof(double), cudaMemcpyDeviceToDevice,
+                            m->ctx->stream));
+    }
+  } else if (method == PTFEM_RECOVER_LUMPED || method == PTFEM_RECOVER_AVERAGE) {
+    if (m->nvalp != 1 && m->nvalp != m->S) return set_err(PTFEM_ERR_STATE, "value sets and systems out of step");
+    PT_TRY(m->Jall.alloc((size_t)m->nsys_user * m->nn * 3));
+    PT_TRY(m->Jelem_all.alloc((size_t)(m->nt > 0 ? m->nt : 1) * 3 * m->S));
+    PT_TRY(wait_j_copy(m));
+    const int mode = method == PTFEM_RECOVER_LUMPED ? 1 : 2;
+    switch (m->S) {
+      case 1: PT_TRY(recover_batch_t<1>(m, mode)); break;
+      case 2: PT_TRY(recover_batch_t<2>(m, mode)); break;
+      case 4: PT_TRY(recover_batch_t<4>(m, mode)); break;
+      case 8: PT_TRY(recover_batch_t<8>(m, mode)); break;
+      case 16: PT_TRY(recover_batch_t<16>(m, mode)); break;
+      default: return set_err(PTFEM_ERR_STATE, "unsupported system count %d", m->S);
+    }
+  } else {
+    return set_err(PTFEM_ERR_ARG, "unknown recovery method %d", method);
+  }
+  m->J_all_valid = true;
+  m->J_all_method = method;
+  m->J_sys = 0;
+  m->J_from_all = true;
+  return PTFEM_OK;
+}
+
+int ptfem_do_metrics_batch(ptfem_mesh* m, int32_t nreq, const ptfem_metric_req* req, double* out) {
+  ptfem_ctx* ctx = m->ctx;
+  PT_TRY(check_sys(m, 0));
+  std::vector<BatchReq> h(nreq);
+  std::vector<int32_t> idx[3];
+  bool need_j = false;
+  for (int q = 0; q < nreq; ++q) {
+    const ptfem_metric_req& r = req[q];
+    if (r.kind < 0 || r.kind > 2) return set_err(PTFEM_ERR_ARG, "request %d: unknown kind %d", q, r.kind);
+    PT_TRY(check_sys(m, r.sys));
+    if (r.kind == PTFEM_METRIC_NODES) {
+      if (r.field < 0 || r.field > 3 || r.mode < 0 || r.mode > 2) return set_err(PTFEM_ERR_ARG, "request %d: bad field / mode", q);
+      if (r.mode != 0 && (r.nfp < 1 || r.nfp > 2)) return set_err(PTFEM_ERR_ARG, "request %d: 1..2 footprints for mode 1/2", q);
+      need_j = need_j || r.field != 1;
+    } else if (r.kind == PTFEM_METRIC_ROI) {
+      if (r.nmult < 1 || r.nmult > kMaxMult) return set_err(PTFEM_ERR_ARG, "request %d: 1..4 radius multipliers", q);
+      for (int k = 1; k < r.nmult; ++k)
+        if (!(r.mult[k] >= r.mult[k - 1])) return set_err(PTFEM_ERR_ARG, "request %d: radius multipliers must be non-decreasing", q);
+      need_j = true;
+    } else {
+      need_j = true;
+    }
+    h[q].r = r;
+    h[q].slot = (int32_t)idx[r.kind].size();
+    h[q].pad_ = 0;
+    idx[r.kind].push_back(q);
+  }
+  if (need_j && !(m->J_all_valid && m->Jall.p))
+    return set_err(PTFEM_ERR_STATE, "ptfem_metrics_batch needs the nodal currents of every system (ptfem_recover_current_batch)");
+  const double* Jall = m->Jall.p;
+  if (!m->has_tcen && !idx[2].empty()) {
+    PT_TRY(m->tcen.alloc((size_t)(m->nt > 0 ? m->nt : 1) * 4));
+    if (m->nt > 0) {
+      tet_centroid_kernel<<<ceil_div(m->nt, 256), 256, 0, ctx->stream>>>(m->xyz.p, m->tets.p, m->nt, reinterpret_cast<float4*>(m->tcen.p));
+      PT_LAUNCH_CHECK(ctx);
+    }
+    m->has_tcen = true;
+  }
+  // device copies: requests, per-kind index lists, partials, results
+  DevBuf<BatchReq> d_req;
+  DevBuf<int32_t> d_idx;
+  PT_TRY(d_req.alloc(nreq));
+  PT_TRY(d_idx.alloc(nreq));
+  std::vector<int32_t> flat;
+  int off[3];
+  for (int k = 0; k < 3; ++k) {
+    off[k] = (int)flat.size();
+    flat.insert(flat.end(), idx[k].begin(), idx[k].end());
+  }
+  PT_CK(cudaMemcpyAsync(d_req.p, h.data(), sizeof(BatchReq) * nreq, cudaMemcpyHostToDevice, ctx->stream));
+  PT_CK(cudaMemcpyAsync(d_idx.p, flat.data(), sizeof(int32_t) * nreq, cudaMemcpyHostToDevice, ctx->stream));
+  const int gn = red_grid(ctx, m->nn), gb = red_grid(ctx, m->nb), gc = red_grid(ctx, m->nt + m->nb);
+  constexpr int NVR = 6 * kMaxMult;
+  const size_t np0 = idx[0].size() * (size_t)gn * 4, np1 = idx[1].size() * (size_t)gb * 3, np2 = idx[2].size() * (size_t)gc * NVR;
+  const size_t nres = (size_t)nreq * PTFEM_METRIC_OUT_STRIDE;
+  PT_TRY(m->scratch_d.alloc(np0 + np1 + np2 + nres + 64));
+  double* part0 = m->scratch_d.p;
+  double* part1 = part0 + np0;
+  double* part2 = part1 + np1;
+  double* res = part2 + np2;
+  PT_CK(cudaMemsetAsync(res, 0, nres * sizeof(double), ctx->stream));
+  if (!idx[0].empty()) {
+    metric_nodes_batch_kernel<<<dim3(gn, (unsigned)idx[0].size()), kT, 0, ctx->stream>>>(m->xyz.p, m->nn, m->phi.p, m->S, Jall, d_req.p,
+                                                                                       d_idx.p + off[0], part0);
+    PT_LAUNCH_CHECK(ctx);
+    finalize_batch_kernel<<<ceil_div((int64_t)idx[0].size() * 4 * 32, 256), 256, 0, ctx->stream>>>(part0, gn, 4, (int)idx[0].size(),
+                                                                                                    0u | (0u << 2) | (1u << 4) | (2u << 6),
+                                                                                                    d_idx.p + off[0], res);
+    PT_LAUNCH_CHECK(ctx);
+  }
+  if (!idx[1].empty()) {
+    pad_current_batch_kernel<<<dim3(gb, (unsigned)idx[1].size()), kT, 0, ctx->stream>>>(m->xyz.p, m->tris.p, m->nb, m->tri_area.p, m->nn,
+                                                                                      Jall, d_req.p, d_idx.p + off[1], part1);
+    PT_LAUNCH_CHECK(ctx);
+    finalize_batch_kernel<<<ceil_div((int64_t)idx[1].size() * 3 * 32, 256), 256, 0, ctx->stream>>>(part1, gb, 3, (int)idx[1].size(), 0u,
+                                                                                                    d_idx.p + off[1], res);
+    PT_LAUNCH_CHECK(ctx);
+  }
+  if (!idx[2].empty()) {
+    PT_TRY(m->phis_all.alloc(idx[2].size() * (size_t)m->nn));
+    smooth_phi_batch_kernel<<<dim3(ceil_div(m->nn, 128), (unsigned)idx[2].size()), 128, 0, ctx->stream>>>(
+        m->n2t_ptr.p, m->n2t.p, m->n2b_ptr.p, m->n2b.p, m->tets.p, m->tris.p, m->phi.p, m->S, m->nn, m->xyz.p, m->h_max, d_req.p,
+        d_idx.p + off[2], m->phis_all.p);
+    PT_LAUNCH_CHECK(ctx);
+    roi_batch_kernel<<<dim3(gc, (unsigned)idx[2].size()), kT, 0, ctx->stream>>>(m->xyz.p, m->tets.p, m->nt, m->tris.p, m->nb,
+                                                                                 reinterpret_cast<const float4*>(m->tcen.p), m->nn,
+                                                                                 m->phis_all.p, Jall, d_req.p, d_idx.p + off[2], part2);
+    PT_LAUNCH_CHECK(ctx);
+    finalize_batch_kernel<<<ceil_div((int64_t)idx[2].size() * NVR * 32, 256), 256, 0, ctx->stream>>>(part2, gc, NVR, (int)idx[2].size(), 0u,
+                                                                                                      d_idx.p + off[2], res);
+    PT_LAUNCH_CHECK(ctx);
+  }
+  PT_CK(cudaMemcpyAsync(out, res, nres * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  PT_CK(cudaStreamSynchronize(ctx->stream));   // (the request / index buffers go back to the allocator here)
   return PTFEM_OK;
 }

@@ -1160,24 +1160,38 @@ int pcg_iteration(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int 
   return PTFEM_OK;
 }
 
-// r = b - A x ; z ; p = z ; rho = r.z ; rr = r.r
+// (re)start, first half: r = b - A x (true residual; x_is_zero: r = b without the product), rr = r.r and - Jacobi and
+// coarse-grid preconditioners - the Jacobi part of r.z.  The host reads rr before it decides whether the second half runs.
+template <int S, int VS>
+int pcg_residual(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int precond, double* x, bool x_is_zero) {
+  const int grid = grid_for(ctx, (A.nn * A.S + 1) / 2, kThreads);
+  if (x_is_zero) {
+    PT_CK(cudaMemcpyAsync(w.r.p, A.b, (size_t)A.nn * S * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    PT_TRY((spmv_sv<S, VS>(ctx, A, variant, x, w.q.p, &w, false)));
+    residual_kernel<S><<<grid, kThreads, 0, ctx->stream>>>(A.nn, A.b, w.q.p, w.r.p);
+    PT_LAUNCH_CHECK(ctx);
+  }
+  if (precond == PTFEM_PRECOND_JACOBI || precond == PTFEM_PRECOND_TWOLEVEL) {
+    dots_kernel<S, VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.r.p, A.dinv, w.partial.p, w.scal.p,
+                                                           precond == PTFEM_PRECOND_JACOBI ? SC_RHO : SC_RHOL, SC_RR, 0, w.ticket.p);
+  } else {
+    dots_kernel<S, VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.r.p, nullptr, w.partial.p, w.scal.p, -1, SC_RR, 0,
+                                                           w.ticket.p);
+  }
+  PT_LAUNCH_CHECK(ctx);
+  return PTFEM_OK;
+}
+
+// (re)start, second half: z = M^-1 r ; p = z ; rho = r.z
 template <int S, int VS>
 int pcg_start(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int precond, int degree, double* x) {
   const int grid = grid_for(ctx, (A.nn * A.S + 1) / 2, kThreads);
-  PT_TRY((spmv_sv<S, VS>(ctx, A, variant, x, w.q.p, &w, false)));
-  residual_kernel<S><<<grid, kThreads, 0, ctx->stream>>>(A.nn, A.b, w.q.p, w.r.p);
-  PT_LAUNCH_CHECK(ctx);
   if (precond == PTFEM_PRECOND_JACOBI) {
-    dots_kernel<S, VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.r.p, A.dinv, w.partial.p, w.scal.p, SC_RHO, SC_RR,
-                                                           0, w.ticket.p);
-    PT_LAUNCH_CHECK(ctx);
     cg_pupdate_kernel<S, VS, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, nullptr, A.dinv, w.p.p, x, w.scal.p, 1);
     PT_LAUNCH_CHECK(ctx);
   } else if (precond == PTFEM_PRECOND_TWOLEVEL) {
     if constexpr (VS == 1) {
-      dots_kernel<S, 1><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.r.p, A.dinv, w.partial.p, w.scal.p, SC_RHOL, SC_RR, 0,
-                                                            w.ticket.p);
-      PT_LAUNCH_CHECK(ctx);
       PT_TRY(coarse_apply(ctx, *A.coarse, S, w.r.p));
       rho_finalize_kernel<<<1, 32, 0, ctx->stream>>>(w.scal.p, A.coarse->cdot.p, A.coarse->nlev, S);
       PT_LAUNCH_CHECK(ctx);
@@ -1187,7 +1201,7 @@ int pcg_start(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int prec
     }
   } else {
     PT_TRY((cheb_apply<S, VS>(ctx, A, w, variant, degree)));
-    dots_kernel<S, VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.z.p, nullptr, w.partial.p, w.scal.p, SC_RHO, SC_RR,
+    dots_kernel<S, VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.z.p, nullptr, w.partial.p, w.scal.p, SC_RHO, -1,
                                                            0, w.ticket.p);
     PT_LAUNCH_CHECK(ctx);
     cg_pupdate_kernel<S, VS, false><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.z.p, A.dinv, w.p.p, x, w.scal.p, 1);
@@ -1276,14 +1290,20 @@ int pcg_solve_t(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_o
     return worst;
   };
 
+  bool true_known = false;   // h[] holds the true residual of the x on the device
+  double true_w2 = 0.0;
   while (true) {
-    rc = pcg_start<S, VS>(ctx, A, w, variant, precond, degree, x);
+    // true residual first; the preconditioner application and the first direction only if the iteration goes on
+    const bool x_is_zero = restarts == 0 && !o.warm_start;
+    rc = pcg_residual<S, VS>(ctx, A, w, variant, precond, x, x_is_zero);
     if (rc) break;
-    spmv_calls += 1 + degree;
+    spmv_calls += x_is_zero ? 0 : 1;
     rc = read_scal();
     if (rc) break;
     double w2 = worst_rel2();
     rel = sqrt(w2);
+    true_known = true;
+    true_w2 = w2;
     if (w2 <= rtol2) {
       converged = true;
       break;
@@ -1293,6 +1313,10 @@ int pcg_solve_t(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_o
       break;
     }
     prev_true2 = w2;
+    rc = pcg_start<S, VS>(ctx, A, w, variant, precond, degree, x);
+    if (rc) break;
+    spmv_calls += degree;
+    true_known = false;
     // iterate in chunks of `check`
     bool chunk_conv = false;
     double chunk_w2 = w2;   // worst rel^2 at the start of the next chunk
@@ -1387,15 +1411,19 @@ int pcg_solve_t(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_o
   cudaEventDestroy(ev1);
   if (rc) return rc;
 
-  // final true residual
-  PT_TRY((spmv_sv<S, VS>(ctx, A, variant, x, w.q.p, &w, false)));
-  residual_kernel<S><<<grid, kThreads, 0, ctx->stream>>>(A.nn, A.b, w.q.p, w.r.p);
-  PT_LAUNCH_CHECK(ctx);
-  dots_kernel<S, VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.r.p, nullptr, w.partial.p, w.scal.p, -1, SC_RR, 0,
-                                                         w.ticket.p);
-  PT_LAUNCH_CHECK(ctx);
-  PT_TRY(read_scal());
-  const double true_rel = sqrt(worst_rel2());
+  // final true residual (already known when the loop ended on a restart's check: x has not moved since)
+  if (!true_known) {
+    PT_TRY((spmv_sv<S, VS>(ctx, A, variant, x, w.q.p, &w, false)));
+    residual_kernel<S><<<grid, kThreads, 0, ctx->stream>>>(A.nn, A.b, w.q.p, w.r.p);
+    PT_LAUNCH_CHECK(ctx);
+    dots_kernel<S, VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.r.p, nullptr, w.partial.p, w.scal.p, -1, SC_RR, 0,
+                                                           w.ticket.p);
+    PT_LAUNCH_CHECK(ctx);
+    PT_TRY(read_scal());
+    true_w2 = worst_rel2();
+    spmv_calls += 1;
+  }
+  const double true_rel = sqrt(true_w2);
   // optional: device time of the SpMV kernel this solve used (same variant, fused dot), for roofline reports
   double spmv_ms = 0.0;
   if (o.sample_spmv > 0) {
@@ -1420,7 +1448,7 @@ int pcg_solve_t(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_o
     st->iterations = it;
     st->converged = converged ? 1 : 0;
     st->nsys = S;
-    st->spmv_calls = spmv_calls + 1;
+    st->spmv_calls = spmv_calls;
     st->rel_residual = rel;
     st->true_rel_residual = true_rel;
     st->solve_ms = ms;

@@ -51,6 +51,17 @@ class Footprint(C.Structure):
     _fields_ = [("cx", C.c_double), ("cy", C.c_double), ("r", C.c_double), ("square", C.c_int32), ("pad_", C.c_int32)]
 
 
+class MetricReq(C.Structure):
+    """``ptfem_metric_req`` (include/ptfem.h): one reduction of a metric batch."""
+    _fields_ = [("kind", C.c_int32), ("sys", C.c_int32), ("field", C.c_int32), ("mode", C.c_int32),
+                ("zmin", C.c_double), ("zmax", C.c_double), ("scale_r", C.c_double), ("fp", Footprint * 2),
+                ("nfp", C.c_int32), ("include_tris", C.c_int32), ("cen", C.c_double * 3), ("r0", C.c_double),
+                ("mult", C.c_double * 4), ("nmult", C.c_int32), ("pad_", C.c_int32), ("z0", C.c_double), ("z1", C.c_double)]
+
+
+METRIC_NODES, METRIC_PAD_CURRENT, METRIC_ROI, METRIC_OUT_STRIDE = 0, 1, 2, 24
+
+
 def lib_path():
     return Path(os.environ.get("PTFEM_LIB", _LIB_PATH))
 
@@ -100,6 +111,8 @@ def load_library():
         "ptfem_recover_current": (C.c_int, [vp, i32, i32, vp]),
         "ptfem_recover_current_async": (C.c_int, [vp, i32, i32, vp]),
         "ptfem_current_get": (C.c_int, [vp, vp]),
+        "ptfem_recover_current_batch": (C.c_int, [vp, i32, vp, i32]),
+        "ptfem_metrics_batch": (C.c_int, [vp, i32, P(MetricReq), P(dbl)]),
         "ptfem_metric_nodes": (C.c_int, [vp, i32, i32, dbl, dbl, i32, vp, i32, dbl, P(dbl)]),
         "ptfem_metric_pad_current": (C.c_int, [vp, i32, dbl, P(Footprint), dbl, P(dbl)]),
         "ptfem_metric_roi": (C.c_int, [vp, i32, P(dbl), dbl, P(dbl), i32, dbl, dbl, i32, P(dbl)]),
@@ -373,7 +386,71 @@ class DeviceMesh:
             self._ck(self.lib.ptfem_recover_current(self._h, sys, _RECOVER[method], _ptr(J)))
         return J
 
+    def recover_current_batch(self, method="lumped", to_host=False, out=None, wait=True):
+        """Nodal currents of EVERY system of the last solve in two launches (``ptfem_recover_current_batch``).  Returns
+        J [nsys, nn, 3] when ``to_host``; ``wait=False`` (``out`` in pinned memory) leaves the read-back running on the side
+        stream until ``Context.sync()``.  Later per-system metric calls use these currents."""
+        J = None
+        if to_host:
+            J = out if out is not None else np.empty((self.nsys, self.nn, 3), dtype=np.float64)
+            if J.shape != (self.nsys, self.nn, 3) or J.dtype != np.float64 or not J.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous float64 array of shape [nsys, nn, 3]")
+            if not wait and out is None:
+                raise ValueError("wait=False needs a caller-owned (pinned) out array")
+        self._ck(self.lib.ptfem_recover_current_batch(self._h, _RECOVER[method], _ptr(J), 1 if wait else 0))
+        return J
+
     # -- K12 -------------------------------------------------------------------------
+    def metrics_batch(self, reqs):
+        """Any number of metric reductions in one pass per kind and ONE read-back (``ptfem_metrics_batch``).  ``reqs``: list of
+        dicts ``dict(kind="nodes", sys, field, zmin, zmax=nan, mode=0, footprints=(), scale_r=1.0)``,
+        ``dict(kind="pad_current", sys, zmin, footprint, scale_r=1.2)`` or
+        ``dict(kind="roi", sys, cen, r0, mults=(1, 1.5, 2, 3), z0=0, z1=0, include_tris=True)``; returns one result dict (or
+        list of dicts for "roi") per request, shaped like the single-request methods' results."""
+        n = len(reqs)
+        arr = (MetricReq * n)()
+        for q, r in zip(arr, reqs):
+            kind = r["kind"]
+            q.sys = int(r.get("sys", 0))
+            if kind == "nodes":
+                q.kind, q.field, q.mode = METRIC_NODES, int(r["field"]), int(r.get("mode", 0))
+                q.zmin, q.zmax, q.scale_r = float(r["zmin"]), float(r.get("zmax", float("nan"))), float(r.get("scale_r", 1.0))
+                fps = list(r.get("footprints", ()))
+                if len(fps) > 2:
+                    raise ValueError("at most 2 footprints per batched request")
+                for k, (cx, cy, rr, square) in enumerate(fps):
+                    q.fp[k] = Footprint(cx, cy, rr, 1 if square else 0, 0)
+                q.nfp = len(fps)
+            elif kind == "pad_current":
+                q.kind, q.zmin, q.scale_r = METRIC_PAD_CURRENT, float(r["zmin"]), float(r.get("scale_r", 1.2))
+                cx, cy, rr, square = r["footprint"]
+                q.fp[0] = Footprint(cx, cy, rr, 1 if square else 0, 0)
+                q.nfp = 1
+            elif kind == "roi":
+                mults = tuple(r.get("mults", (1.0, 1.5, 2.0, 3.0)))
+                q.kind, q.r0, q.nmult = METRIC_ROI, float(r["r0"]), len(mults)
+                for k in range(3):
+                    q.cen[k] = float(r["cen"][k])
+                for k, mval in enumerate(mults):
+                    q.mult[k] = float(mval)
+                q.z0, q.z1, q.include_tris = float(r.get("z0", 0.0)), float(r.get("z1", 0.0)), 1 if r.get("include_tris", True) else 0
+            else:
+                raise ValueError(f"unknown metric kind {kind!r}")
+        out = (C.c_double * (METRIC_OUT_STRIDE * n))()
+        self._ck(self.lib.ptfem_metrics_batch(self._h, n, arr, out))
+        res = []
+        for i, r in enumerate(reqs):
+            o = out[i * METRIC_OUT_STRIDE:(i + 1) * METRIC_OUT_STRIDE]
+            if r["kind"] == "nodes":
+                res.append(dict(count=int(o[0]), sum=o[1], max=o[2], min=o[3]))
+            elif r["kind"] == "pad_current":
+                res.append(dict(I_signed=o[0], area=o[1], count=int(o[2])))
+            else:
+                nm = len(tuple(r.get("mults", (1.0, 1.5, 2.0, 3.0))))
+                res.append([dict(n=int(o[6 * k]), sum_J=o[6 * k + 1], sum_E=o[6 * k + 2], n_above=int(o[6 * k + 3]),
+                                 n_mid=int(o[6 * k + 4]), n_below=int(o[6 * k + 5])) for k in range(nm)])
+        return res
+
     @staticmethod
     def _fps(fps):
         arr = (Footprint * max(1, len(fps)))()

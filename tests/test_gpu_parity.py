@@ -521,6 +521,67 @@ def test_large_mesh_properties(gpu_ctx):
     dm.close()
 
 
+# -- sweep forms: all systems' currents in two launches, all metrics in one batch == the per-system calls ----------------
+@pytest.mark.parametrize("mode", ["multi_rhs", "batched_matrices"])
+@pytest.mark.parametrize("method", ["lumped", "average", "l2"])
+def test_batched_recovery_and_metrics_match_per_system_calls(gpu_ctx, mode, method):
+    m = meshgen.synth_slab("S")
+    dm = dm_for(gpu_ctx, m)
+    if mode == "multi_rhs":
+        dm.assemble(SIGMA5).bc_reset(3)
+        for k in range(3):
+            dm.neumann(101, 15.975 * (1 + k), rhs=k)
+    else:
+        sigs = [{**SIGMA5, 4: sc, 5: sc} for sc in (5e-3, 1e-3, 2e-4)]
+        dm.assemble(sigs).bc_reset(1).neumann(101, 15.975)
+    dm.dirichlet(102, 0.0)
+    dm.solve(to_host=False, rtol=1e-11)
+    Lz, t_skin = m.meta["Lz"], m.meta["t_skin"]
+    e1 = (0.015, 0.045, 0.010, False)
+    cen = [0.015, 0.045, Lz - 0.010]
+    single, Js = [], []
+    for k in range(3):
+        Js.append(dm.recover_current(k, method))
+        single.append(dm.metric_nodes(0, Lz - 0.2 * t_skin, sys=k))
+        single.append(dm.metric_nodes(1, Lz - 1e-5, mode=1, footprints=[e1], scale_r=1.5, sys=k))
+        single.append(dm.metric_nodes(3, 0.0, zmax=Lz * 0.5, mode=2, footprints=[e1, (0.065, 0.045, 0.010, True)], sys=k))
+        single.append(dm.metric_pad_current(Lz - 1e-5, e1, 1.2, sys=k))
+        single.append(dm.metric_roi(cen, 0.005, (1.0, 1.5, 2.0, 3.0), z0=0.0335, z1=0.0385, include_tris=True, sys=k))
+        single.append(dm.metric_roi(cen, 0.0004, (1.0, 1.5), include_tris=False, sys=k))
+    dm.solve(to_host=False, rtol=1e-11)                      # invalidates the per-system current
+    Jb = dm.recover_current_batch(method, to_host=True)
+    assert Jb.shape == (3, m.nn, 3)
+    for k in range(3):
+        assert rel(Jb[k], Js[k]) < (1e-9 if method == "l2" else 1e-14)
+    reqs = []
+    for k in range(3):
+        reqs += [dict(kind="nodes", sys=k, field=0, zmin=Lz - 0.2 * t_skin),
+                 dict(kind="nodes", sys=k, field=1, zmin=Lz - 1e-5, mode=1, footprints=[e1], scale_r=1.5),
+                 dict(kind="nodes", sys=k, field=3, zmin=0.0, zmax=Lz * 0.5, mode=2, footprints=[e1, (0.065, 0.045, 0.010, True)]),
+                 dict(kind="pad_current", sys=k, zmin=Lz - 1e-5, footprint=e1, scale_r=1.2),
+                 dict(kind="roi", sys=k, cen=cen, r0=0.005, mults=(1.0, 1.5, 2.0, 3.0), z0=0.0335, z1=0.0385, include_tris=True),
+                 dict(kind="roi", sys=k, cen=cen, r0=0.0004, mults=(1.0, 1.5), include_tris=False)]
+    batch = dm.metrics_batch(reqs)
+    tol = 1e-8 if method == "l2" else 1e-12
+
+    def same(a, b):
+        if isinstance(a, list):
+            return len(a) == len(b) and all(same(x, y) for x, y in zip(a, b))
+        return a.keys() == b.keys() and all(abs(a[k] - b[k]) <= tol * max(abs(b[k]), 1e-300) or a[k] == b[k] for k in a)
+    assert len(batch) == len(single)
+    for i, (a, b) in enumerate(zip(batch, single)):
+        assert same(a, b), (i, a, b)
+    # the per-system calls after a batch use its currents (no recomputation) and agree as well
+    assert rel(dm.recover_current(1, method), Js[1]) < (1e-9 if method == "l2" else 1e-14)
+    assert same(dm.metric_pad_current(Lz - 1e-5, e1, 1.2, sys=2), single[2 * 6 + 3])
+    with pytest.raises(engine.PtfemError):
+        dm.metrics_batch([dict(kind="nodes", sys=7, field=0, zmin=0.0)])
+    dm.solve(to_host=False, rtol=1e-11)
+    with pytest.raises(engine.PtfemError):                     # currents are stale after a new solve
+        dm.metrics_batch([dict(kind="pad_current", sys=0, zmin=0.0, footprint=e1)])
+    dm.close()
+
+
 # -- parity at the sizes the bench measures, against the CPU oracle (C/OpenMP restatement, itself checked against the numpy
 #    oracle in tests/test_oracle.py): node potentials 1e-6, nodal currents 1e-4 --------------------------------------------
 _ORACLE_CACHE = {}
