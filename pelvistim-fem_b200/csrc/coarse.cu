@@ -19,41 +19,33 @@ constexpr int kGjNb = 32;     // pivot block of the Gauss-Jordan inverse
 constexpr int kGjTile = 64;   // update tile (kp is a multiple of it)
 
 // ---- grids ------------------------------------------------------------------------------------------------
-constexpr long long kDirBit = (long long)(1ull << 63);
-
 // table row = position of the mesh node in the coarsest grid (see CoarseSpace::ctab)
-__global__ void coarse_table_kernel(CoarseGrid g, const double* __restrict__ xyz, int64_t nn, double* __restrict__ ctab) {
+__global__ void coarse_table_kernel(CoarseGrid g, const double* __restrict__ xyz, int64_t nn, float4* __restrict__ ctab) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nn) return;
   int c[3];
   double t[3];
   coarse_locate(g, xyz, i, c, t);
-  ctab[4 * i] = t[0];
-  ctab[4 * i + 1] = t[1];
-  ctab[4 * i + 2] = t[2];
-  ctab[4 * i + 3] = __longlong_as_double((long long)c[0] | ((long long)c[1] << 21) | ((long long)c[2] << 42));
+  ctab[i] = coarse_row_pack(c, t, false);
 }
 // Dirichlet rows carry the sign bit: coarse_row() then reports them as outside every coarse space
-__global__ void coarse_table_flag_kernel(const uint8_t* __restrict__ isdir, int64_t nn, double* __restrict__ ctab) {
+__global__ void coarse_table_flag_kernel(const uint8_t* __restrict__ isdir, int64_t nn, float4* __restrict__ ctab) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nn) return;
-  const long long cell = __double_as_longlong(ctab[4 * i + 3]) & ~kDirBit;
-  ctab[4 * i + 3] = __longlong_as_double(isdir[i] ? (cell | kDirBit) : cell);
+  const unsigned int cell = __float_as_uint(ctab[i].w) & ~kCoarseDirBit;
+  ctab[i].w = __uint_as_float(isdir[i] ? (cell | kCoarseDirBit) : cell);
 }
 
 // table rows in the order of a row list
-__global__ void gather_table_kernel(const double* __restrict__ ctab, const int32_t* __restrict__ rows, int64_t nn,
-                                    double* __restrict__ out) {
+__global__ void gather_table_kernel(const float4* __restrict__ ctab, const int32_t* __restrict__ rows, int64_t nn,
+                                    float4* __restrict__ out) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nn) return;
-  const int64_t i = rows[p];
-  const double2 a = *reinterpret_cast<const double2*>(ctab + 4 * i), b = *reinterpret_cast<const double2*>(ctab + 4 * i + 2);
-  *reinterpret_cast<double2*>(out + 4 * p) = a;
-  *reinterpret_cast<double2*>(out + 4 * p + 2) = b;
+  out[p] = ctab[rows[p]];
 }
 
 // (called before the Dirichlet flags are set: every row has a cell)
-__global__ void cell_key_kernel(int n0, int n1, int shift, const double* __restrict__ ctab, int64_t nn, int32_t* __restrict__ key,
+__global__ void cell_key_kernel(int n0, int n1, int shift, const float4* __restrict__ ctab, int64_t nn, int32_t* __restrict__ key,
                                 int32_t* __restrict__ id) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nn) return;
@@ -78,7 +70,7 @@ __global__ void cell_ptr_kernel(const int32_t* __restrict__ key, int64_t nn, int
 // task's rows of w_corner(row) r[row][s]: registers and shuffles only, fixed order, no atomics.
 template <int S, bool OCC>
 __global__ void __launch_bounds__(256, OCC ? 4 : 2) restrict_cell_kernel(int64_t ntask, int split, int shift, const int32_t* __restrict__ cellptr,
-                                                            const int32_t* __restrict__ rows, const double* __restrict__ ctab0,
+                                                            const int32_t* __restrict__ rows, const float4* __restrict__ ctab0,
                                                             const double* __restrict__ r, double* __restrict__ part) {
   constexpr int NP = S >= 2 ? S / 2 : 1;  // lanes per row
   constexpr int NV = S >= 2 ? 2 : 1;      // systems per lane
@@ -539,7 +531,7 @@ __global__ void __launch_bounds__(256) coarse_chain_kernel(ChainArgs a) {
 // sum_i w_i(I) Y[i][slot].  Columns further away (mesh edge longer than a coarse cell) take the slow path.
 constexpr int kGalRows = 64;
 __global__ void __launch_bounds__(256) galerkin_cell_kernel(CoarseGrid g, const int32_t* __restrict__ cellptr,
-                                                            const int32_t* __restrict__ rows, const double* __restrict__ ctab,
+                                                            const int32_t* __restrict__ rows, const float4* __restrict__ ctab,
                                                             const int32_t* __restrict__ rowptr,
                                                             const int32_t* __restrict__ col, const double* __restrict__ val,
                                                             double* __restrict__ blockE /*[ncell][8][64]*/,
@@ -642,7 +634,7 @@ __global__ void __launch_bounds__(256) galerkin_gather_kernel(CoarseGrid g, int6
 // ---- Galerkin diagonal of a finer (BPX) level -----------------------------------------------------------------
 // diag_I = sum_i sum_j w_i(I) K_ij hat_I(x_j); CTA per cell, 4 lanes per row, per-cell partials [ncell][8]
 __global__ void __launch_bounds__(256) galerkin_diag_cell_kernel(int shift, int64_t ncell, const int32_t* __restrict__ cellptr,
-                                                                 const int32_t* __restrict__ rows, const double* __restrict__ ctab,
+                                                                 const int32_t* __restrict__ rows, const float4* __restrict__ ctab,
                                                                  const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                                  const double* __restrict__ val, double* __restrict__ dpartc) {
   __shared__ double s_red[8 * 256];
@@ -831,12 +823,12 @@ int dense_inverse(ptfem_ctx* ctx, double* A, int kp, int32_t* flag) {
 
 // ---- row-partitioned solve (dist.cu): table of a row block, level-0 scaling after the cross-rank sum -----------
 // splits the Dirichlet bit off a copied table (the row lists are built from cells, which Dirichlet rows keep)
-__global__ void coarse_table_split_kernel(int64_t nn, double* __restrict__ ctab, uint8_t* __restrict__ isdir) {
+__global__ void coarse_table_split_kernel(int64_t nn, float4* __restrict__ ctab, uint8_t* __restrict__ isdir) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nn) return;
-  const long long cell = __double_as_longlong(ctab[4 * i + 3]);
-  isdir[i] = cell < 0 ? 1 : 0;
-  ctab[4 * i + 3] = __longlong_as_double(cell & ~kDirBit);
+  const unsigned int cell = __float_as_uint(ctab[i].w);
+  isdir[i] = (cell & kCoarseDirBit) ? 1 : 0;
+  ctab[i].w = __uint_as_float(cell & ~kCoarseDirBit);
 }
 // level weight: B_l *= w (the additive levels overlap in what they correct)
 __global__ void coarse_weight_kernel(double* __restrict__ binv, int64_t n, double w) {
@@ -1061,7 +1053,9 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
     }
     CoarseGrid base;
     choose_grid(m, (double)target_nodes, base);
-    PT_TRY(cs.ctab.alloc((size_t)m->nn * 4));
+    if (base.n[0] > kCoarseMaxCells || base.n[1] > kCoarseMaxCells || base.n[2] > kCoarseMaxCells)
+      return set_err(PTFEM_ERR_ARG, "coarsest grid of %dx%dx%d cells: at most %d per axis", base.n[0], base.n[1], base.n[2], kCoarseMaxCells);
+    PT_TRY(cs.ctab.alloc((size_t)m->nn));
     coarse_table_kernel<<<ceil_div(m->nn, 256), 256, 0, ctx->stream>>>(base, m->xyz.p, m->nn, cs.ctab.p);
     PT_LAUNCH_CHECK(ctx);
     for (int l = 0; l < cs.nlev; ++l) {
@@ -1119,7 +1113,7 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
     PT_CK(cudaMemsetAsync(cs.flag.p, 0, 2 * sizeof(int32_t), ctx->stream));
     coarse_table_flag_kernel<<<ceil_div(m->nn, 256), 256, 0, ctx->stream>>>(m->isdir.p, m->nn, cs.ctab.p);
     PT_LAUNCH_CHECK(ctx);
-    PT_TRY(cs.ctab0.alloc((size_t)m->nn * 4));
+    PT_TRY(cs.ctab0.alloc((size_t)m->nn));
     gather_table_kernel<<<ceil_div(m->nn, 256), 256, 0, ctx->stream>>>(cs.ctab.p, cs.lev[0].rows.p, m->nn, cs.ctab0.p);
     PT_LAUNCH_CHECK(ctx);
     // the additive levels overlap in what they correct (every level sees the smooth part of r): each is weighted by
@@ -1201,8 +1195,8 @@ int coarse_attach_rows(ptfem_mesh* sys, ptfem_mesh* full, int64_t row0) {
   sys->coarse = new CoarseSpace();
   CoarseSpace& cs = *sys->coarse;
   cs.nlev = F.nlev;
-  PT_TRY(cs.ctab.alloc((size_t)nloc * 4));
-  PT_CK(cudaMemcpyAsync(cs.ctab.p, F.ctab.p + 4 * row0, (size_t)nloc * 4 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  PT_TRY(cs.ctab.alloc((size_t)nloc));
+  PT_CK(cudaMemcpyAsync(cs.ctab.p, F.ctab.p + row0, (size_t)nloc * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
   DevBuf<uint8_t> isdir;
   PT_TRY(isdir.alloc(nloc));
   coarse_table_split_kernel<<<ceil_div(nloc, 256), 256, 0, ctx->stream>>>(nloc, cs.ctab.p, isdir.p);
@@ -1236,7 +1230,7 @@ int coarse_attach_rows(ptfem_mesh* sys, ptfem_mesh* full, int64_t row0) {
   }
   coarse_table_flag_kernel<<<ceil_div(nloc, 256), 256, 0, ctx->stream>>>(isdir.p, nloc, cs.ctab.p);
   PT_LAUNCH_CHECK(ctx);
-  PT_TRY(cs.ctab0.alloc((size_t)nloc * 4));
+  PT_TRY(cs.ctab0.alloc((size_t)nloc));
   gather_table_kernel<<<ceil_div(nloc, 256), 256, 0, ctx->stream>>>(cs.ctab.p, cs.lev[0].rows.p, nloc, cs.ctab0.p);
   PT_LAUNCH_CHECK(ctx);
   PT_TRY(cs.dpart.alloc(maxgrid * 16));

@@ -23,7 +23,7 @@ struct CoarseDev {
   int nx1 = 1, ny1 = 1;         // grid nodes per axis (x, y) of the finest level
   int shift = 0;                // its cells are 2^shift smaller than the table's
   const double* y = nullptr;    // [k_0][S] sum over the levels, on the finest grid
-  const double* ctab = nullptr; // [nn][4] see CoarseSpace::ctab
+  const float4* ctab = nullptr; // [nn] see CoarseSpace::ctab
 };
 
 struct CoarseLevel {
@@ -51,10 +51,12 @@ struct CoarseSpace {
   ptfem::DevBuf<double> cdot;             // [nlev][16] r_c . y_c per level and system
   ptfem::DevBuf<double> dpart;            // per-CTA partials of those dots
   ptfem::DevBuf<unsigned int> ticket;
-  // per mesh row: position in the coarsest grid {t_x, t_y, t_z, packed cell (21 bits per axis) or -1 for a
-  // Dirichlet row}; finer levels derive theirs by doubling.  Rebuilt with the matrix (Dirichlet flags live here).
-  ptfem::DevBuf<double> ctab;
-  ptfem::DevBuf<double> ctab0;            // the same rows in the order of level 0's row list (restriction reads it in step with the list)
+  // per mesh row, 16 bytes: position in the coarsest grid {t_x, t_y, t_z as float, packed cell (10 bits per axis) with
+  // bit 31 set for a Dirichlet row}; finer levels derive theirs by doubling.  Single precision halves what restriction and
+  // prolongation read per row; every consumer (Galerkin operators, restriction, prolongation) decodes the SAME rounded
+  // coordinates, so Z is one matrix everywhere and M^-1 stays symmetric.  Rebuilt with the matrix (Dirichlet flags).
+  ptfem::DevBuf<float4> ctab;
+  ptfem::DevBuf<float4> ctab0;            // the same rows in the order of level 0's row list (restriction reads it in step with the list)
   ptfem::DevBuf<int32_t> flag;            // [0] non-positive pivot seen, [1] slow-path entries
   double setup_ms = 0.0;
   int chain_grid = 0;                     // CTAs of the cooperative grid-hierarchy kernel (0: separate kernels)
@@ -79,24 +81,29 @@ __device__ __forceinline__ void coarse_locate(const CoarseGrid& g, const double*
 // Split in load + decode so that callers can issue the loads of several rows before any of them is used; the decode
 // is branch-free (a Dirichlet row decodes to cell 0 and live = false).
 struct CoarseRaw {
-  double2 a, b;
+  float4 v;
 };
-__device__ __forceinline__ CoarseRaw coarse_row_load(const double* __restrict__ ctab, int64_t i) {
+constexpr unsigned int kCoarseDirBit = 0x80000000u;
+constexpr int kCoarseMaxCells = 1023;   // cells per axis of the coarsest grid that fit the packed entry
+__device__ __forceinline__ float4 coarse_row_pack(const int (&c)[3], const double (&t)[3], bool dirichlet) {
+  const unsigned int bits = (unsigned)c[0] | ((unsigned)c[1] << 10) | ((unsigned)c[2] << 20) | (dirichlet ? kCoarseDirBit : 0u);
+  return make_float4((float)t[0], (float)t[1], (float)t[2], __uint_as_float(bits));
+}
+__device__ __forceinline__ CoarseRaw coarse_row_load(const float4* __restrict__ ctab, int64_t i) {
   CoarseRaw r;
-  r.a = __ldg(reinterpret_cast<const double2*>(ctab + 4 * i));
-  r.b = __ldg(reinterpret_cast<const double2*>(ctab + 4 * i + 2));
+  r.v = __ldg(ctab + i);
   return r;
 }
 __device__ __forceinline__ bool coarse_row_decode(const CoarseRaw& r, int shift, int (&c)[3], double (&t)[3]) {
-  long long cell = __double_as_longlong(r.b.y);
-  const bool live = cell >= 0;
-  cell = live ? cell : 0;
-  c[0] = (int)(cell & 0x1fffff);
-  c[1] = (int)((cell >> 21) & 0x1fffff);
-  c[2] = (int)(cell >> 42);
-  t[0] = r.a.x;
-  t[1] = r.a.y;
-  t[2] = r.b.x;
+  unsigned int cell = __float_as_uint(r.v.w);
+  const bool live = !(cell & kCoarseDirBit);
+  cell = live ? cell : 0u;
+  c[0] = (int)(cell & 0x3ffu);
+  c[1] = (int)((cell >> 10) & 0x3ffu);
+  c[2] = (int)((cell >> 20) & 0x3ffu);
+  t[0] = (double)r.v.x;
+  t[1] = (double)r.v.y;
+  t[2] = (double)r.v.z;
   if (shift > 0) {
     const int f = 1 << shift;
 #pragma unroll
@@ -110,7 +117,7 @@ __device__ __forceinline__ bool coarse_row_decode(const CoarseRaw& r, int shift,
   }
   return live;
 }
-__device__ __forceinline__ bool coarse_row(const double* __restrict__ ctab, int64_t i, int shift, int (&c)[3], double (&t)[3]) {
+__device__ __forceinline__ bool coarse_row(const float4* __restrict__ ctab, int64_t i, int shift, int (&c)[3], double (&t)[3]) {
   return coarse_row_decode(coarse_row_load(ctab, i), shift, c, t);
 }
 // the eight trilinear weights from three subtractions and twelve products

@@ -111,6 +111,7 @@ struct ptfem_ctx {
   int tune_restrict_occ = 1;       // PTFEM_RESTRICT_OCC: 1 = register-capped restriction kernel (4 CTAs/SM, measured 7% faster solve), 0 = uncapped
   int tune_coarse_fused = 0;       // PTFEM_COARSE_FUSED: grid hierarchy of the coarse-grid preconditioner as one cooperative kernel
   double tune_coarse_weight = 0.0; // PTFEM_COARSE_WEIGHT: weight of the coarse-grid levels against the Jacobi term (0 = 2 / (levels + 1))
+  int tune_pupdate_np = 2;         // PTFEM_PUPDATE_NP: pairs per trip of the coarse-grid p-update (1: 4 CTAs/SM, 2: 2 CTAs/SM, all loads of both first)
   int tune_ctas_per_sm = 0;        // cap on resident CTAs per SM of the streaming SpMV (PTFEM_CTAS_PER_SM)
   std::unordered_map<const void*, size_t> func_smem;  // dynamic shared memory limit raised per kernel
   // NCCL (row-partitioned solves)

@@ -637,11 +637,12 @@ __global__ void rho_finalize_kernel(double* __restrict__ scal, const double* __r
   scal[SC_BETA * kMaxSys + s] = rho_old > 0.0 ? rho / rho_old : 0.0;
 }
 
-// p-update of the two-level preconditioner (one shared matrix): z = dinv r + Z y.  The table entry of the next trip is
-// loaded one trip ahead: the table -> grid node -> y chain is two dependent loads deep and ncu shows the kernel
-// waiting on exactly that chain (long-scoreboard stalls on the first use of the table entry).
-template <int S>
-__global__ void __launch_bounds__(kThreads, 3) cg_pupdate_coarse_kernel(int64_t nn, const double* __restrict__ r,
+// p-update of the two-level preconditioner (one shared matrix): z = dinv r + Z y ; x += alpha p ; p = z + beta p.
+// Two pairs per trip: the loads of both (five streamed 16-byte accesses and the table entry each) are issued before
+// either is used, and the eight grid-node gathers of both are independent - the kernel used to sit at 4.7 TB/s waiting
+// on the table -> grid node -> y chain with ~60 KB per SM in flight (ncu, round 1); the table entry is 16 bytes now.
+template <int S, int NP>
+__global__ void __launch_bounds__(kThreads, NP == 1 ? 4 : 2) cg_pupdate_coarse_kernel(int64_t nn, const double* __restrict__ r,
                                                                         const double* __restrict__ dinv, double* __restrict__ p,
                                                                         double* __restrict__ x, const double* __restrict__ scal,
                                                                         int first, CoarseDev cd) {
@@ -649,45 +650,53 @@ __global__ void __launch_bounds__(kThreads, 3) cg_pupdate_coarse_kernel(int64_t 
   const double b0 = first ? 0.0 : scal[SC_BETA * kMaxSys + fp.s0], b1 = first ? 0.0 : scal[SC_BETA * kMaxSys + fp.s1];
   const double a0 = first ? 0.0 : scal[SC_ALPHA * kMaxSys + fp.s0], a1 = first ? 0.0 : scal[SC_ALPHA * kMaxSys + fp.s1];
   constexpr int NR = S == 1 ? 2 : 1;  // mesh rows per pair
-  CoarseRaw raw[NR], nxt[NR];
-  if (fp.j0 < fp.npairs) {
+  for (int64_t j = fp.j0; j < fp.npairs; j += NP * fp.stride) {
+    const bool two = NP == 2 && j + fp.stride < fp.npairs;
+    const int64_t jj[2] = {j, two ? j + fp.stride : j};
+    CoarseRaw raw[NP][NR];
+    double2 zv[NP], d[NP], pv[NP], xv[NP];
 #pragma unroll
-    for (int k = 0; k < NR; ++k) raw[k] = coarse_row_load(cd.ctab, S == 1 ? 2 * fp.j0 + k : (2 * fp.j0) / S);
-  }
-  for (int64_t j = fp.j0; j < fp.npairs; j += fp.stride) {
-    const int64_t e = 2 * j;
-    const int64_t jn = j + fp.stride < fp.npairs ? j + fp.stride : j;
+    for (int u = 0; u < NP; ++u) {
+      const int64_t e = 2 * jj[u];
 #pragma unroll
-    for (int k = 0; k < NR; ++k) nxt[k] = coarse_row_load(cd.ctab, S == 1 ? 2 * jn + k : (2 * jn) / S);
-    double2 zv = __ldg(reinterpret_cast<const double2*>(r + e));
-    const double2 d = pair_weight<S, 1>(dinv, e);
-    double2 pv = make_double2(0.0, 0.0), xv = make_double2(0.0, 0.0);
-    if (!first) {
-      pv = *reinterpret_cast<const double2*>(p + e);
-      xv = *reinterpret_cast<const double2*>(x + e);
+      for (int k = 0; k < NR; ++k) raw[u][k] = coarse_row_load(cd.ctab, S == 1 ? e + k : e / S);
+      zv[u] = __ldg(reinterpret_cast<const double2*>(r + e));
+      d[u] = pair_weight<S, 1>(dinv, e);
+      pv[u] = make_double2(0.0, 0.0);
+      xv[u] = make_double2(0.0, 0.0);
+      if (!first) {
+        pv[u] = *reinterpret_cast<const double2*>(p + e);
+        xv[u] = *reinterpret_cast<const double2*>(x + e);
+      }
     }
-    double cz[2];
-    if constexpr (S == 1) {
-      double c0[1], c1[1];
-      coarse_prolong<1, 1>(cd, raw[0], 0, c0);
-      coarse_prolong<1, 1>(cd, raw[1], 0, c1);
-      cz[0] = c0[0];
-      cz[1] = c1[0];
-    } else {
-      coarse_prolong<S, 2>(cd, raw[0], fp.s0, cz);
-    }
-    zv.x = fma(zv.x, d.x, cz[0]);
-    zv.y = fma(zv.y, d.y, cz[1]);
-    if (!first) {
-      xv.x = fma(a0, pv.x, xv.x);
-      xv.y = fma(a1, pv.y, xv.y);
-      *reinterpret_cast<double2*>(x + e) = xv;
-      zv.x = fma(b0, pv.x, zv.x);
-      zv.y = fma(b1, pv.y, zv.y);
-    }
-    *reinterpret_cast<double2*>(p + e) = zv;
 #pragma unroll
-    for (int k = 0; k < NR; ++k) raw[k] = nxt[k];
+    for (int u = 0; u < NP; ++u) {
+      double cz[2];
+      if constexpr (S == 1) {
+        double c0[1], c1[1];
+        coarse_prolong<1, 1>(cd, raw[u][0], 0, c0);
+        coarse_prolong<1, 1>(cd, raw[u][1], 0, c1);
+        cz[0] = c0[0];
+        cz[1] = c1[0];
+      } else {
+        coarse_prolong<S, 2>(cd, raw[u][0], fp.s0, cz);
+      }
+      zv[u].x = fma(zv[u].x, d[u].x, cz[0]);
+      zv[u].y = fma(zv[u].y, d[u].y, cz[1]);
+    }
+#pragma unroll
+    for (int u = 0; u < NP; ++u) {
+      if (u == 1 && !two) break;
+      const int64_t e = 2 * jj[u];
+      if (!first) {
+        xv[u].x = fma(a0, pv[u].x, xv[u].x);
+        xv[u].y = fma(a1, pv[u].y, xv[u].y);
+        *reinterpret_cast<double2*>(x + e) = xv[u];
+        zv[u].x = fma(b0, pv[u].x, zv[u].x);
+        zv[u].y = fma(b1, pv[u].y, zv[u].y);
+      }
+      *reinterpret_cast<double2*>(p + e) = zv[u];
+    }
   }
   if (fp.has_tail) {
     const int64_t e = fp.tail;
@@ -1141,8 +1150,12 @@ int pcg_iteration(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int 
       PT_TRY(coarse_apply(ctx, *A.coarse, S, w.r.p));
       rho_finalize_kernel<<<1, 32, 0, ctx->stream>>>(w.scal.p, A.coarse->cdot.p, A.coarse->nlev, S);
       PT_LAUNCH_CHECK(ctx);
-      cg_pupdate_coarse_kernel<S><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
-                                                                      coarse_dev(*A.coarse));
+      if (ctx->tune_pupdate_np == 1)
+        cg_pupdate_coarse_kernel<S, 1><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
+                                                                           coarse_dev(*A.coarse));
+      else
+        cg_pupdate_coarse_kernel<S, 2><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
+                                                                           coarse_dev(*A.coarse));
       PT_LAUNCH_CHECK(ctx);
     }
   } else {
@@ -1195,8 +1208,8 @@ int pcg_start(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int prec
       PT_TRY(coarse_apply(ctx, *A.coarse, S, w.r.p));
       rho_finalize_kernel<<<1, 32, 0, ctx->stream>>>(w.scal.p, A.coarse->cdot.p, A.coarse->nlev, S);
       PT_LAUNCH_CHECK(ctx);
-      cg_pupdate_coarse_kernel<S><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 1,
-                                                                      coarse_dev(*A.coarse));
+      cg_pupdate_coarse_kernel<S, 1><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 1,
+                                                                         coarse_dev(*A.coarse));
       PT_LAUNCH_CHECK(ctx);
     }
   } else {
