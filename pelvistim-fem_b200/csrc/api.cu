@@ -198,7 +198,8 @@ int ptfem_ctx_create(int device, ptfem_ctx** out) {
   if (const char* e = getenv("PTFEM_CTAS_PER_SM")) c->tune_ctas_per_sm = atoi(e);
   if (const char* e = getenv("PTFEM_RESTRICT_OCC")) c->tune_restrict_occ = atoi(e);
   if (const char* e = getenv("PTFEM_COARSE_FUSED")) c->tune_coarse_fused = atoi(e) != 0;
-  if (const char* e = getenv("PTFEM_PUPDATE_NP")) c->tune_pupdate_np = atoi(e) == 1 ? 1 : 2;
+  if (const char* e = getenv("PTFEM_PUPDATE_NP")) c->tune_pupdate_np = atoi(e) == 2 ? 2 : 1;
+  if (const char* e = getenv("PTFEM_PUPDATE_OCC")) c->tune_pupdate_occ = atoi(e);
   if (const char* e = getenv("PTFEM_COARSE_WEIGHT")) {
     const double w = atof(e);
     if (w > 0.0) c->tune_coarse_weight = w;

@@ -206,6 +206,35 @@ __global__ void eliminate_kernel(const int32_t* __restrict__ rowptr, const int32
   if (i >= nn) return;
   const int32_t rb = rowptr[i], re = rowptr[i + 1], dg = diag[i];
   const bool di = isdir[i] != 0;
+  if (VS == 1 && !di) {
+    // one shared matrix (multi-RHS sweep): the row is walked ONCE - values, diagonal and whether any neighbour is a
+    // Dirichlet node; only rows next to an electrode (a fraction of a percent) then visit their Dirichlet neighbours per system
+    double d = 0.0;
+    bool any = false;
+    for (int32_t k = rb; k < re; ++k) {
+      const double v = val_raw[k];
+      const bool dj = isdir[col[k]] != 0;
+      any = any || dj;
+      val_bc[k] = dj ? 0.0 : v;
+      if (k == dg && !dj) d = v;
+    }
+    if (d == 0.0) {  // isolated node (no tets): identity row
+      d = 1.0;
+      val_bc[dg] = 1.0;
+    }
+    dinv[i] = 1.0 / d;
+    for (int s = 0; s < S; ++s) {
+      const int ds = (s < dirS) ? s : 0;
+      double acc = b_neu[i * dirS + ds];
+      if (any)
+        for (int32_t k = rb; k < re; ++k) {
+          const int32_t j = col[k];
+          if (isdir[j]) acc -= val_raw[k] * dirval[(int64_t)j * dirS + ds];
+        }
+      b[i * S + s] = acc;
+    }
+    return;
+  }
   for (int s = 0; s < S; ++s) {
     const int vs = (VS == 1) ? 0 : s;
     const int ds = (s < dirS) ? s : 0;

@@ -68,8 +68,8 @@ __global__ void cell_ptr_kernel(const int32_t* __restrict__ key, int64_t nn, int
 // ---- restriction: per-cell partials -------------------------------------------------------------------------
 // One warp per task = (cell, split index); lane = (row slot, system pair).  part[task][corner][s] = sum over the
 // task's rows of w_corner(row) r[row][s]: registers and shuffles only, fixed order, no atomics.
-template <int S, bool OCC>
-__global__ void __launch_bounds__(256, OCC ? 4 : 2) restrict_cell_kernel(int64_t ntask, int split, int shift, const int32_t* __restrict__ cellptr,
+template <int S, int OCC>
+__global__ void __launch_bounds__(256, OCC) restrict_cell_kernel(int64_t ntask, int split, int shift, const int32_t* __restrict__ cellptr,
                                                             const int32_t* __restrict__ rows, const float4* __restrict__ ctab0,
                                                             const double* __restrict__ r, double* __restrict__ part) {
   constexpr int NP = S >= 2 ? S / 2 : 1;  // lanes per row
@@ -534,18 +534,27 @@ __global__ void __launch_bounds__(256) galerkin_cell_kernel(CoarseGrid g, const 
                                                             const int32_t* __restrict__ rows, const float4* __restrict__ ctab,
                                                             const int32_t* __restrict__ rowptr,
                                                             const int32_t* __restrict__ col, const double* __restrict__ val,
-                                                            double* __restrict__ blockE /*[ncell][8][64]*/,
-                                                            double* __restrict__ E, int kp, int32_t* __restrict__ flag) {
+                                                            double* __restrict__ blockE /*[ncell][gsplit][8][64]*/,
+                                                            double* __restrict__ E, int kp, int32_t* __restrict__ flag, int gsplit) {
   __shared__ double Y[kGalRows][65];
   __shared__ double W[kGalRows][8];
-  const int64_t c = blockIdx.x;
+  // gsplit CTAs share a cell (contiguous pieces of its row list, whole chunks of kGalRows rows): the exactly inverted grid
+  // is small (a few hundred cells), one CTA per cell would leave most of the GPU idle
+  const int64_t c = blockIdx.x / gsplit;
+  const int sp = (int)(blockIdx.x % gsplit);
   int cc[3];
   cc[0] = (int)(c % g.n[0]);
   cc[1] = (int)((c / g.n[0]) % g.n[1]);
   cc[2] = (int)(c / ((int64_t)g.n[0] * g.n[1]));
   double acc[2] = {0.0, 0.0};
   const int rloc = threadIdx.x >> 2, l4 = threadIdx.x & 3;
-  const int32_t p0 = cellptr[c], p1 = cellptr[c + 1];
+  int32_t p0 = cellptr[c], p1 = cellptr[c + 1];
+  {
+    const int32_t chunks = (p1 - p0 + kGalRows - 1) / kGalRows, per = (chunks + gsplit - 1) / gsplit;
+    const int32_t q0 = p0 + sp * per * kGalRows, q1 = q0 + per * kGalRows;
+    p0 = q0 < p1 ? q0 : p1;
+    p1 = q1 < p1 ? q1 : p1;
+  }
   for (int32_t base = p0; base < p1; base += kGalRows) {
     for (int k = threadIdx.x; k < kGalRows * 65; k += 256) (&Y[0][0])[k] = 0.0;
     __syncthreads();
@@ -562,28 +571,47 @@ __global__ void __launch_bounds__(256) galerkin_cell_kernel(CoarseGrid g, const 
 #pragma unroll
       for (int a = 0; a < 8; ++a) W[rloc][a] = live ? coarse_weight(ti, a) : 0.0;
     }
+    // The four lanes of a row all walk the whole row, and lane z adds only the corners that fall into plane z of the
+    // 4x4x4 slot block: no two lanes ever touch the same slot, so plain read-modify-writes do (four lanes adding into
+    // the same 64 slots needed shared-memory atomics - 400 M of them, the whole cost of the first version).  Non-zeros
+    // are taken four at a time, all loads first: the col -> table chain is two dependent gathers deep.
     if (live) {
-      for (int32_t e = rowptr[i] + l4; e < rowptr[i + 1]; e += 4) {
-        const double v = val[e];
-        const int32_t j = col[e];
-        if (v == 0.0) continue;
-        int cj[3];
-        double tj[3];
-        if (!coarse_row(ctab, j, 0, cj, tj)) continue;
-        const int d0 = cj[0] - cc[0], d1 = cj[1] - cc[1], d2 = cj[2] - cc[2];
-        if (d0 >= -1 && d0 <= 1 && d1 >= -1 && d1 <= 1 && d2 >= -1 && d2 <= 1) {
+      const int32_t rb = rowptr[i], re = rowptr[i + 1];
+      for (int32_t e0 = rb; e0 < re; e0 += 4) {
+        double v4[4];
+        CoarseRaw r4[4];
 #pragma unroll
-          for (int a = 0; a < 8; ++a) {
-            const int slot = (d0 + (a & 1) + 1) + 4 * (d1 + ((a >> 1) & 1) + 1) + 16 * (d2 + (a >> 2) + 1);
-            atomicAdd(&Y[rloc][slot], v * coarse_weight(tj, a));
-          }
-        } else {
-          flag[1] = 1;
-          int ci[3] = {cc[0], cc[1], cc[2]};
-          for (int a = 0; a < 8; ++a) {
-            const double wi = coarse_weight(ti, a);
-            const int64_t I = coarse_node(g, ci, a);
-            for (int b = 0; b < 8; ++b) atomicAdd(E + (size_t)I * kp + coarse_node(g, cj, b), wi * v * coarse_weight(tj, b));
+        for (int u = 0; u < 4; ++u) {
+          const int32_t e = e0 + u < re ? e0 + u : re - 1;
+          v4[u] = e0 + u < re ? val[e] : 0.0;
+          r4[u] = coarse_row_load(ctab, col[e]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double v = v4[u];
+          if (v == 0.0) continue;
+          int cj[3];
+          double tj[3];
+          if (!coarse_row_decode(r4[u], 0, cj, tj)) continue;
+          const int d0 = cj[0] - cc[0], d1 = cj[1] - cc[1], d2 = cj[2] - cc[2];
+          if (d0 >= -1 && d0 <= 1 && d1 >= -1 && d1 <= 1 && d2 >= -1 && d2 <= 1) {
+            const int az = l4 - d2 - 1;   // corner layer of column j's cell that lies in this lane's plane
+            if (az == 0 || az == 1) {
+              const double wz = v * (az ? tj[2] : 1.0 - tj[2]);
+#pragma unroll
+              for (int a = 0; a < 4; ++a) {
+                const int slot = (d0 + (a & 1) + 1) + 4 * (d1 + (a >> 1) + 1) + 16 * l4;
+                Y[rloc][slot] += wz * ((a & 1) ? tj[0] : 1.0 - tj[0]) * ((a & 2) ? tj[1] : 1.0 - tj[1]);
+              }
+            }
+          } else if (l4 == 0) {
+            flag[1] = 1;
+            int ci[3] = {cc[0], cc[1], cc[2]};
+            for (int a = 0; a < 8; ++a) {
+              const double wi = coarse_weight(ti, a);
+              const int64_t I = coarse_node(g, ci, a);
+              for (int b2 = 0; b2 < 8; ++b2) atomicAdd(E + (size_t)I * kp + coarse_node(g, cj, b2), wi * v * coarse_weight(tj, b2));
+            }
           }
         }
       }
@@ -598,13 +626,13 @@ __global__ void __launch_bounds__(256) galerkin_cell_kernel(CoarseGrid g, const 
     }
     __syncthreads();
   }
-  blockE[(size_t)c * 512 + threadIdx.x] = acc[0];
-  blockE[(size_t)c * 512 + 256 + threadIdx.x] = acc[1];
+  blockE[(size_t)blockIdx.x * 512 + threadIdx.x] = acc[0];
+  blockE[(size_t)blockIdx.x * 512 + 256 + threadIdx.x] = acc[1];
 }
 
 // E[I][J] += sum over the cells around I of their block entry for (I, J); padding / empty nodes -> identity
 __global__ void __launch_bounds__(256) galerkin_gather_kernel(CoarseGrid g, int64_t k, int kp, const double* __restrict__ blockE,
-                                                              double* __restrict__ E) {
+                                                              double* __restrict__ E, int gsplit) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (int64_t)kp * kp) return;
   const int64_t I = e / kp, J = e % kp;
@@ -624,74 +652,100 @@ __global__ void __launch_bounds__(256) galerkin_gather_kernel(CoarseGrid g, int6
       const int sx = jx - cx + 1, sy = jy - cy + 1, sz = jz - cz + 1;
       if (sx < 0 || sx > 3 || sy < 0 || sy > 3 || sz < 0 || sz > 3) continue;
       const int64_t c = cx + (int64_t)g.n[0] * (cy + (int64_t)g.n[1] * cz);
-      v += blockE[(size_t)c * 512 + a * 64 + (sx + 4 * sy + 16 * sz)];
+      for (int sp = 0; sp < gsplit; ++sp) v += blockE[((size_t)c * gsplit + sp) * 512 + a * 64 + (sx + 4 * sy + 16 * sz)];
     }
   }
   if (I == J && !(v > 0.0)) v = 1.0;  // grid node without a free mesh node in its support
   E[e] = v;
 }
 
-// ---- Galerkin diagonal of a finer (BPX) level -----------------------------------------------------------------
-// diag_I = sum_i sum_j w_i(I) K_ij hat_I(x_j); CTA per cell, 4 lanes per row, per-cell partials [ncell][8]
-__global__ void __launch_bounds__(256) galerkin_diag_cell_kernel(int shift, int64_t ncell, const int32_t* __restrict__ cellptr,
-                                                                 const int32_t* __restrict__ rows, const float4* __restrict__ ctab,
-                                                                 const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                                                 const double* __restrict__ val, double* __restrict__ dpartc) {
-  __shared__ double s_red[8 * 256];
-  for (int64_t c = blockIdx.x; c < ncell; c += gridDim.x) {
-    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const int32_t p1 = cellptr[c + 1];
-    for (int32_t p = cellptr[c] + (threadIdx.x >> 2); p < p1; p += 64) {
-      const int32_t i = rows[p];
-      int ci[3];
-      double ti[3];
-      if (!coarse_row(ctab, i, shift, ci, ti)) continue;
-      double h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int32_t e = rowptr[i] + (threadIdx.x & 3); e < rowptr[i + 1]; e += 4) {
-        const double v = val[e];
-        const int32_t j = col[e];
-        if (v == 0.0) continue;
-        int cj[3];
-        double u[3];
-        if (!coarse_row(ctab, j, shift, cj, u)) continue;
+// ---- Galerkin diagonals of the finer (BPX) levels ---------------------------------------------------------------
+// All diagonal-only levels in ONE pass over the matrix: CTAs walk the cells of the FINEST grid (its row list); for every
+// row the levels are taken one after the other - the row's val / col / table entries are read from DRAM for the first
+// level and from L1 for the others.  dpartf[l][finest cell][8] = this finest cell's contribution to the eight corners of
+// the level-l cell that contains it; galerkin_diag_node_multi_kernel adds the children up.
+__global__ void __launch_bounds__(256) galerkin_diag_multi_kernel(int nb, int shift0, int64_t ncell, const int32_t* __restrict__ cellptr,
+                                                                  const int32_t* __restrict__ rows, const float4* __restrict__ ctab,
+                                                                  const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                                  const double* __restrict__ val, double* __restrict__ dpartf) {
+  // one WARP per finest cell (a few dozen rows): lane = (row slot, quarter of the row's non-zeros); the eight corner sums
+  // are reduced with shuffles - no shared memory, no block barrier (the block-wide reduction of the first version cost
+  // more than the arithmetic)
+  const int lane = threadIdx.x & 31, slot = lane >> 2, q4 = lane & 3;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t c = warp0; c < ncell; c += nwarp) {
+    const int32_t p0 = cellptr[c], p1 = cellptr[c + 1];
+    for (int l = 0; l < nb; ++l) {
+      const int shift = shift0 - l;   // level l's cells are 2^l larger than the finest's
+      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int32_t p = p0 + slot; p < p1; p += 8) {
+        const int32_t i = rows[p];
+        int ci[3];
+        double ti[3];
+        if (!coarse_row(ctab, i, shift, ci, ti)) continue;
+        double h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int32_t re = rowptr[i + 1];
+        for (int32_t e0 = rowptr[i] + q4; e0 < re; e0 += 16) {   // four non-zeros of this lane at a time, all loads first
+          double v4[4];
+          CoarseRaw r4[4];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) u[d] += (double)cj[d];
+          for (int t = 0; t < 4; ++t) {
+            const int32_t e = e0 + 4 * t;
+            v4[t] = e < re ? val[e] : 0.0;
+            r4[t] = coarse_row_load(ctab, col[e < re ? e : re - 1]);
+          }
 #pragma unroll
-        for (int a = 0; a < 8; ++a) {
-          const double hx = 1.0 - fabs(u[0] - (double)(ci[0] + (a & 1)));
-          const double hy = 1.0 - fabs(u[1] - (double)(ci[1] + ((a >> 1) & 1)));
-          const double hz = 1.0 - fabs(u[2] - (double)(ci[2] + (a >> 2)));
-          if (hx > 0.0 && hy > 0.0 && hz > 0.0) h[a] = fma(v, hx * hy * hz, h[a]);
+          for (int t = 0; t < 4; ++t) {
+            const double v = v4[t];
+            if (v == 0.0) continue;
+            int cj[3];
+            double u[3];
+            if (!coarse_row_decode(r4[t], shift, cj, u)) continue;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) u[d] += (double)cj[d];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+              const double hx = 1.0 - fabs(u[0] - (double)(ci[0] + (a & 1)));
+              const double hy = 1.0 - fabs(u[1] - (double)(ci[1] + ((a >> 1) & 1)));
+              const double hz = 1.0 - fabs(u[2] - (double)(ci[2] + (a >> 2)));
+              if (hx > 0.0 && hy > 0.0 && hz > 0.0) h[a] = fma(v, hx * hy * hz, h[a]);
+            }
+          }
         }
+#pragma unroll
+        for (int a = 0; a < 8; ++a) acc[a] = fma(coarse_weight(ti, a), h[a], acc[a]);
       }
 #pragma unroll
-      for (int a = 0; a < 8; ++a) acc[a] = fma(coarse_weight(ti, a), h[a], acc[a]);
-    }
+      for (int a = 0; a < 8; ++a) acc[a] = warp_sum(acc[a]);
+      if (lane == 0) {
 #pragma unroll
-    for (int a = 0; a < 8; ++a) s_red[a * 256 + threadIdx.x] = acc[a];
-    __syncthreads();
-    if (threadIdx.x < 8) {
-      double tot = 0.0;
-      for (int k = 0; k < 256; ++k) tot += s_red[threadIdx.x * 256 + k];
-      dpartc[(size_t)c * 8 + threadIdx.x] = tot;
+        for (int a = 0; a < 8; ++a) dpartf[((size_t)l * ncell + c) * 8 + a] = acc[a];
+      }
     }
-    __syncthreads();
   }
 }
-__global__ void galerkin_diag_node_kernel(CoarseGrid g, int64_t k, const double* __restrict__ dpartc, double* __restrict__ binv) {
-  const int64_t I = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per grid node of level l (cells 2^l = f times the finest's): binv[I] = 1 / sum over the (up to) eight cells around
+// I of the contributions of their f^3 finest children (lanes stride over the children, fixed shuffle tree: deterministic)
+__global__ void galerkin_diag_node_multi_kernel(CoarseGrid g, int64_t k, int f, int nf0, int nf1, const double* __restrict__ dpart_l,
+                                                double* __restrict__ binv) {
+  const int64_t I = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (I >= k) return;
   const int nx1 = g.n[0] + 1, ny1 = g.n[1] + 1;
   const int ix = (int)(I % nx1), iy = (int)((I / nx1) % ny1), iz = (int)(I / ((int64_t)nx1 * ny1));
   double v = 0.0;
-#pragma unroll
+  const int nch = f * f * f;
   for (int a = 0; a < 8; ++a) {
     const int cx = ix - (a & 1), cy = iy - ((a >> 1) & 1), cz = iz - (a >> 2);
     if (cx < 0 || cy < 0 || cz < 0 || cx >= g.n[0] || cy >= g.n[1] || cz >= g.n[2]) continue;
-    const int64_t c = cx + (int64_t)g.n[0] * (cy + (int64_t)g.n[1] * cz);
-    v += dpartc[(size_t)c * 8 + a];
+    for (int q = lane; q < nch; q += 32) {
+      const int qx = q % f, qy = (q / f) % f, qz = q / (f * f);
+      const int64_t cf = (int64_t)(cx * f + qx) + (int64_t)nf0 * ((cy * f + qy) + (int64_t)nf1 * (cz * f + qz));
+      v += dpart_l[(size_t)cf * 8 + a];
+    }
   }
-  binv[I] = v > 0.0 ? 1.0 / v : 0.0;
+  v = warp_sum(v);
+  if (lane == 0) binv[I] = v > 0.0 ? 1.0 / v : 0.0;
 }
 
 // ---- dense inverse: blocked Gauss-Jordan without pivoting (the matrix is SPD) ---------------------------------
@@ -843,11 +897,12 @@ __global__ void coarse_scale_kernel(int64_t k, const double* __restrict__ binv, 
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
-int build_level_geometry(ptfem_mesh* m, CoarseLevel& L) {
+int build_level_geometry(ptfem_mesh* m, CoarseLevel& L, bool lists = true) {
   ptfem_ctx* ctx = m->ctx;
   const int64_t nn = m->nn;
   L.ncell = (int64_t)L.g.n[0] * L.g.n[1] * L.g.n[2];
   L.k = (int64_t)(L.g.n[0] + 1) * (L.g.n[1] + 1) * (L.g.n[2] + 1);
+  if (!lists) return PTFEM_OK;   // only the finest level (restriction, diagonals) and the exact one (Galerkin matrix) walk row lists
   DevBuf<int32_t> key, key2, id;
   PT_TRY(key.alloc(nn));
   PT_TRY(key2.alloc(nn));
@@ -948,12 +1003,15 @@ int apply_t(ptfem_ctx* ctx, CoarseSpace& cs, const double* r) {
   {
     const int64_t ntask = L0.ncell * L0.split;
     const int grid = (int)std::min<int64_t>((ntask + 7) / 8, (int64_t)ctx->sm_count * 32);
-    if (ctx->tune_restrict_occ)
-      restrict_cell_kernel<S, true><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p, r,
-                                                                   L0.part.p);
+    if (ctx->tune_restrict_occ >= 6)
+      restrict_cell_kernel<S, 6><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p, r,
+                                                                L0.part.p);
+    else if (ctx->tune_restrict_occ >= 3)
+      restrict_cell_kernel<S, 4><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p, r,
+                                                                L0.part.p);
     else
-      restrict_cell_kernel<S, false><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p,
-                                                                    r, L0.part.p);
+      restrict_cell_kernel<S, 2><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p,
+                                                                r, L0.part.p);
     PT_LAUNCH_CHECK(ctx);
   }
   if (cs.chain_grid > 0) return chain_launch<S>(ctx, cs, true, false);
@@ -1068,7 +1126,7 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
         L.g.inv_h[d] = base.inv_h[d] * f;
       }
       L.exact = (l == cs.nlev - 1);
-      PT_TRY(build_level_geometry(m, L));
+      PT_TRY(build_level_geometry(m, L, l == 0 || L.exact));
       L.kp = L.exact ? (int)((L.k + kGjTile - 1) / kGjTile) * kGjTile : 0;
       // restriction tasks (one warp each) of at most ~96 rows
       L.split = 1;
@@ -1129,36 +1187,48 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
         if (L.binv.p != before) cs.generation++;
         PT_CK(cudaMemsetAsync(L.binv.p, 0, n2 * sizeof(double), ctx->stream));
         DevBuf<double> blockE;
-        PT_TRY(blockE.alloc((size_t)L.ncell * 512));
-        galerkin_cell_kernel<<<(unsigned)L.ncell, 256, 0, ctx->stream>>>(L.g, L.cellptr.p, L.rows.p, cs.ctab.p,
-                                                                          m->rowptr.p, m->col.p, m->val_bc.p, blockE.p, L.binv.p,
-                                                                          L.kp, cs.flag.p);
+        int gsplit = 1;   // CTAs per cell: about eight CTAs per SM in all, each with at least a few chunks of rows
+        while (L.ncell * gsplit < (int64_t)8 * ctx->sm_count && m->nn / (L.ncell * gsplit) > 4 * kGalRows && gsplit < 64) gsplit *= 2;
+        PT_TRY(blockE.alloc((size_t)L.ncell * gsplit * 512));
+        galerkin_cell_kernel<<<(unsigned)(L.ncell * gsplit), 256, 0, ctx->stream>>>(L.g, L.cellptr.p, L.rows.p, cs.ctab.p,
+                                                                                     m->rowptr.p, m->col.p, m->val_bc.p, blockE.p,
+                                                                                     L.binv.p, L.kp, cs.flag.p, gsplit);
         PT_LAUNCH_CHECK(ctx);
-        galerkin_gather_kernel<<<ceil_div((int64_t)n2, 256), 256, 0, ctx->stream>>>(L.g, L.k, L.kp, blockE.p, L.binv.p);
+        galerkin_gather_kernel<<<ceil_div((int64_t)n2, 256), 256, 0, ctx->stream>>>(L.g, L.k, L.kp, blockE.p, L.binv.p, gsplit);
         PT_LAUNCH_CHECK(ctx);
         PT_TRY(dense_inverse(ctx, L.binv.p, L.kp, cs.flag.p));
         if (level_w != 1.0) {
           coarse_weight_kernel<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(L.binv.p, (int64_t)n2, level_w);
           PT_LAUNCH_CHECK(ctx);
         }
-      } else {
-        const double* before = L.binv.p;
-        PT_TRY(L.binv.alloc(L.k));
-        if (L.binv.p != before) cs.generation++;
-        DevBuf<double> dpartc;
-        PT_TRY(dpartc.alloc((size_t)L.ncell * 8));
-        const int grid = (int)std::min<int64_t>(L.ncell, (int64_t)ctx->sm_count * 16);
-        galerkin_diag_cell_kernel<<<grid, 256, 0, ctx->stream>>>(L.shift, L.ncell, L.cellptr.p, L.rows.p, cs.ctab.p,
-                                                                 m->rowptr.p, m->col.p, m->val_bc.p, dpartc.p);
-        PT_LAUNCH_CHECK(ctx);
-        galerkin_diag_node_kernel<<<ceil_div(L.k, 256), 256, 0, ctx->stream>>>(L.g, L.k, dpartc.p, L.binv.p);
+      }
+    }
+    // diagonal-only levels (0 .. nlev-2): one pass over the matrix for all of them
+    if (cs.nlev > 1) {
+      const int nb = cs.nlev - 1;
+      CoarseLevel& L0 = cs.lev[0];
+      for (int l = 0; l < nb; ++l) {
+        const double* before = cs.lev[l].binv.p;
+        PT_TRY(cs.lev[l].binv.alloc(cs.lev[l].k));
+        if (cs.lev[l].binv.p != before) cs.generation++;
+      }
+      DevBuf<double> dpartf;
+      PT_TRY(dpartf.alloc((size_t)nb * L0.ncell * 8));
+      const int grid = (int)std::min<int64_t>((L0.ncell + 7) / 8, (int64_t)ctx->sm_count * 32);
+      galerkin_diag_multi_kernel<<<grid, 256, 0, ctx->stream>>>(nb, L0.shift, L0.ncell, L0.cellptr.p, L0.rows.p, cs.ctab.p, m->rowptr.p,
+                                                                m->col.p, m->val_bc.p, dpartf.p);
+      PT_LAUNCH_CHECK(ctx);
+      for (int l = 0; l < nb; ++l) {
+        CoarseLevel& L = cs.lev[l];
+        galerkin_diag_node_multi_kernel<<<ceil_div(L.k * 32, 256), 256, 0, ctx->stream>>>(L.g, L.k, 1 << l, L0.g.n[0], L0.g.n[1],
+                                                                                         dpartf.p + (size_t)l * L0.ncell * 8, L.binv.p);
         PT_LAUNCH_CHECK(ctx);
         if (level_w != 1.0) {
           coarse_weight_kernel<<<ceil_div(L.k, 256), 256, 0, ctx->stream>>>(L.binv.p, L.k, level_w);
           PT_LAUNCH_CHECK(ctx);
         }
-        PT_CK(cudaStreamSynchronize(ctx->stream));
       }
+      PT_CK(cudaStreamSynchronize(ctx->stream));   // dpartf goes back to the allocator
     }
     int32_t hflag[2] = {0, 0};
     PT_CK(cudaMemcpyAsync(hflag, cs.flag.p, sizeof hflag, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1254,7 +1324,7 @@ int coarse_restrict_rows(ptfem_ctx* ctx, CoarseSpace& cs, const double* r, doubl
   CoarseLevel& L0 = cs.lev[0];
   const int64_t ntask = L0.ncell * L0.split;
   const int grid = (int)std::min<int64_t>((ntask + 7) / 8, (int64_t)ctx->sm_count * 32);
-  restrict_cell_kernel<1, true><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p, r,
+  restrict_cell_kernel<1, 4><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p, r,
                                                                 L0.part.p);
   PT_LAUNCH_CHECK(ctx);
   const int ngrid = std::min(ceil_div(L0.k, 256), 4 * ctx->sm_count);

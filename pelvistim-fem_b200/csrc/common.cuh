@@ -108,10 +108,11 @@ struct ptfem_ctx {
   int tune_morton = -1;            // streaming SpMV walks rows along a Morton curve: -1 auto, 0 off, 1 on (PTFEM_MORTON)
   int tune_p2p_fused = 0;          // row-partitioned solve: SpMV loads halo entries from peer memory itself (PTFEM_P2P_FUSED)
   int tune_xprefetch = 0;          // streaming SpMV prefetches the leading edge of x into L2 (PTFEM_XPREFETCH)
-  int tune_restrict_occ = 1;       // PTFEM_RESTRICT_OCC: 1 = register-capped restriction kernel (4 CTAs/SM, measured 7% faster solve), 0 = uncapped
+  int tune_restrict_occ = 4;       // PTFEM_RESTRICT_OCC: resident CTAs per SM the restriction kernel is compiled for (2, 4, 6; 4 measured best in round 1)
   int tune_coarse_fused = 0;       // PTFEM_COARSE_FUSED: grid hierarchy of the coarse-grid preconditioner as one cooperative kernel
   double tune_coarse_weight = 0.0; // PTFEM_COARSE_WEIGHT: weight of the coarse-grid levels against the Jacobi term (0 = 2 / (levels + 1))
-  int tune_pupdate_np = 2;         // PTFEM_PUPDATE_NP: pairs per trip of the coarse-grid p-update (1: 4 CTAs/SM, 2: 2 CTAs/SM, all loads of both first)
+  int tune_pupdate_occ = 4;        // PTFEM_PUPDATE_OCC: resident CTAs per SM the one-pair p-update is compiled for (4, 5, 6)
+  int tune_pupdate_np = 1;         // PTFEM_PUPDATE_NP: pairs per trip of the coarse-grid p-update (1: 4 CTAs/SM, 2: 2 CTAs/SM, all loads of both first)
   int tune_ctas_per_sm = 0;        // cap on resident CTAs per SM of the streaming SpMV (PTFEM_CTAS_PER_SM)
   std::unordered_map<const void*, size_t> func_smem;  // dynamic shared memory limit raised per kernel
   // NCCL (row-partitioned solves)

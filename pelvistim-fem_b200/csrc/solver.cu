@@ -641,8 +641,8 @@ __global__ void rho_finalize_kernel(double* __restrict__ scal, const double* __r
 // Two pairs per trip: the loads of both (five streamed 16-byte accesses and the table entry each) are issued before
 // either is used, and the eight grid-node gathers of both are independent - the kernel used to sit at 4.7 TB/s waiting
 // on the table -> grid node -> y chain with ~60 KB per SM in flight (ncu, round 1); the table entry is 16 bytes now.
-template <int S, int NP>
-__global__ void __launch_bounds__(kThreads, NP == 1 ? 4 : 2) cg_pupdate_coarse_kernel(int64_t nn, const double* __restrict__ r,
+template <int S, int NP, int MINB = (NP == 1 ? 4 : 2)>
+__global__ void __launch_bounds__(kThreads, MINB) cg_pupdate_coarse_kernel(int64_t nn, const double* __restrict__ r,
                                                                         const double* __restrict__ dinv, double* __restrict__ p,
                                                                         double* __restrict__ x, const double* __restrict__ scal,
                                                                         int first, CoarseDev cd) {
@@ -1150,7 +1150,13 @@ int pcg_iteration(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int 
       PT_TRY(coarse_apply(ctx, *A.coarse, S, w.r.p));
       rho_finalize_kernel<<<1, 32, 0, ctx->stream>>>(w.scal.p, A.coarse->cdot.p, A.coarse->nlev, S);
       PT_LAUNCH_CHECK(ctx);
-      if (ctx->tune_pupdate_np == 1)
+      if (ctx->tune_pupdate_np == 1 && ctx->tune_pupdate_occ == 5)
+        cg_pupdate_coarse_kernel<S, 1, 5><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
+                                                                              coarse_dev(*A.coarse));
+      else if (ctx->tune_pupdate_np == 1 && ctx->tune_pupdate_occ == 6)
+        cg_pupdate_coarse_kernel<S, 1, 6><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
+                                                                              coarse_dev(*A.coarse));
+      else if (ctx->tune_pupdate_np == 1)
         cg_pupdate_coarse_kernel<S, 1><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
                                                                            coarse_dev(*A.coarse));
       else
