@@ -237,6 +237,13 @@ int ptfem_dist_solve(ptfem_mesh* sys, const ptfem_solve_opts* opts, double* x_lo
  * ptfem_dist_solve then preconditions with Jacobi + coarse grids for PTFEM_PRECOND_AUTO / _TWOLEVEL.
  * PTFEM_ERR_STATE: the Galerkin matrix is singular on this mesh (keep Jacobi). */
 int ptfem_dist_coarse_attach(ptfem_mesh* sys, ptfem_mesh* replica, int64_t row0);
+/* Sharded coarse exchange of the peer-memory transport: a contiguous block of rows reaches a slab of the finest grid only.
+ * _get returns this rank's {a0, b0, a1, b1} (finest-grid nodes [a0, b0) and level-1 nodes [a1, b1) its rows contribute to,
+ * known after ptfem_dist_coarse_attach); the launcher all-gathers them and hands every rank the whole table with _set, before
+ * ptfem_dist_p2p_connect.  Per iteration a rank then sums only the grid planes it shares with neighbouring slabs plus the
+ * level-1 vector, instead of every rank's whole finest-grid vector.  Without _set the exchange covers the whole grids. */
+int ptfem_dist_coarse_ranges_get(ptfem_mesh* sys, int64_t ranges4[4]);
+int ptfem_dist_coarse_ranges_set(ptfem_mesh* sys, int32_t nranks, const int64_t* all_ranges /*[nranks*4]*/);
 /* Peer-memory transport (NVLink P2P through CUDA IPC) instead of NCCL calls inside the iteration: every rank
  * exports two IPC handles (its vector and its mailbox, 2 x 64 bytes), the launcher all-gathers them, and each
  * rank connects.  halo_src[h] = index, in the owner's local numbering, of the row halo slot h mirrors.

@@ -1325,7 +1325,7 @@ int coarse_restrict_rows(ptfem_ctx* ctx, CoarseSpace& cs, const double* r, doubl
   const int64_t ntask = L0.ncell * L0.split;
   const int grid = (int)std::min<int64_t>((ntask + 7) / 8, (int64_t)ctx->sm_count * 32);
   restrict_cell_kernel<1, 4><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p, r,
-                                                                L0.part.p);
+                                                            L0.part.p);
   PT_LAUNCH_CHECK(ctx);
   const int ngrid = std::min(ceil_div(L0.k, 256), 4 * ctx->sm_count);
   coarse_node_kernel<1, false><<<ngrid, 256, 0, ctx->stream>>>(L0.g, L0.k, L0.split, L0.part.p, nullptr, rc_out, nullptr, nullptr,
@@ -1334,14 +1334,153 @@ int coarse_restrict_rows(ptfem_ctx* ctx, CoarseSpace& cs, const double* r, doubl
   return PTFEM_OK;
 }
 
-// lev[0].rc holds the summed Z_0^T r (and, when scaled0, lev[0].yc = binv_0 r_c): the replicated grid hierarchy
-int coarse_grids_apply(ptfem_ctx* ctx, CoarseSpace& cs, bool scaled0) {
-  if (cs.chain_grid > 0) return chain_launch<1>(ctx, cs, false, scaled0);
-  for (int l = 0; l < cs.nlev; ++l) {
+// ---- sharded form (peer-memory transport, >= 2 levels) -------------------------------------------------------------------
+// A contiguous block of mesh rows touches a slab of the finest grid only: nodes [a0, b0) of level 0, and through the 27-point
+// grid restriction nodes [a1, b1) of level 1.  The rank computes its partial sums on those ranges only -
+// out0[a0..b0) = this rank's part of Z_0^T r and out1[a1..b1) = P^T of that part (the restriction is linear, so the sum over
+// the ranks of these equals P^T of the summed level-0 vector) - and the cross-rank exchange carries a few grid planes of
+// level 0 (neighbouring slabs) plus the small level-1 vector instead of the whole finest grid.
+namespace {
+// the touched node range of a row list: min / max finest-grid node over the rows' cells
+__global__ void touched_range_kernel(int64_t nn, const float4* __restrict__ ctab, int shift, int nx1, int ny1, int nz1,
+                                     unsigned long long* __restrict__ out /*[0] = min, [1] = max*/) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nn) return;
+  int c[3];
+  double t[3];
+  const CoarseRaw raw = coarse_row_load(ctab, i);
+  CoarseRaw live = raw;
+  live.v.w = __uint_as_float(__float_as_uint(raw.v.w) & ~kCoarseDirBit);   // Dirichlet rows still sit in a cell
+  coarse_row_decode(live, shift, c, t);
+  (void)nz1;
+  const unsigned long long lo = (unsigned long long)c[0] + (unsigned long long)nx1 * (c[1] + (unsigned long long)ny1 * c[2]);
+  const unsigned long long hi = (unsigned long long)(c[0] + 1) + (unsigned long long)nx1 * ((c[1] + 1) + (unsigned long long)ny1 * (c[2] + 1));
+  atomicMin(out, lo);
+  atomicMax(out + 1, hi);
+}
+// rc[I] for finest nodes I in [I0, I1) from the restriction partials (as coarse_node_kernel, S = 1)
+__global__ void __launch_bounds__(256) coarse_node_range_kernel(CoarseGrid g, int64_t I0, int64_t I1, int split,
+                                                                const double* __restrict__ part, double* __restrict__ rc) {
+  const int64_t I = I0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (I >= I1) return;
+  double v = 0.0;
+  const int nx1 = g.n[0] + 1, ny1 = g.n[1] + 1;
+  const int ix = (int)(I % nx1), iy = (int)((I / nx1) % ny1), iz = (int)(I / ((int64_t)nx1 * ny1));
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int cx = ix - (a & 1), cy = iy - ((a >> 1) & 1), cz = iz - (a >> 2);
+    if (cx < 0 || cy < 0 || cz < 0 || cx >= g.n[0] || cy >= g.n[1] || cz >= g.n[2]) continue;
+    const int64_t c = cx + (int64_t)g.n[0] * (cy + (int64_t)g.n[1] * cz);
+    for (int sp = 0; sp < split; ++sp) v += __ldcg(part + (((size_t)c * split + sp) * 8 + a));
+  }
+  rc[I] = v;
+}
+// rc1[J] for level-1 nodes J in [J0, J1): 27-point restriction of rf, fine nodes outside [f0, f1) counting as zero
+__global__ void __launch_bounds__(256) grid_restrict_range_kernel(CoarseGrid gc, int64_t J0, int64_t J1, int64_t f0, int64_t f1,
+                                                                  const double* __restrict__ rf, double* __restrict__ rc) {
+  const int64_t I = J0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (I >= J1) return;
+  double v = 0.0;
+  const int nx1 = gc.n[0] + 1, ny1 = gc.n[1] + 1;
+  const int ix = (int)(I % nx1), iy = (int)((I / nx1) % ny1), iz = (int)(I / ((int64_t)nx1 * ny1));
+  const int fx1 = 2 * gc.n[0] + 1, fy1 = 2 * gc.n[1] + 1, fz1 = 2 * gc.n[2] + 1;
+  for (int dz = -1; dz <= 1; ++dz) {
+    const int fz = 2 * iz + dz;
+    if (fz < 0 || fz >= fz1) continue;
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int fy = 2 * iy + dy;
+      if (fy < 0 || fy >= fy1) continue;
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int fx = 2 * ix + dx;
+        if (fx < 0 || fx >= fx1) continue;
+        const int64_t F = (int64_t)fx + (int64_t)fx1 * (fy + (int64_t)fy1 * fz);
+        if (F < f0 || F >= f1) continue;
+        const double w = (dx ? 0.5 : 1.0) * (dy ? 0.5 : 1.0) * (dz ? 0.5 : 1.0);
+        v = fma(w, __ldcg(rf + F), v);
+      }
+    }
+  }
+  rc[I] = v;
+}
+// yt_f[F] = y_f[F] + (P yt_c)[F] for fine nodes F in [F0, F1)
+__global__ void __launch_bounds__(256) grid_prolong_range_kernel(CoarseGrid gc, int64_t F0, int64_t F1, const double* __restrict__ yf,
+                                                                 const double* __restrict__ ytc, double* __restrict__ ytf) {
+  const int64_t F = F0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (F >= F1) return;
+  const int fx1 = 2 * gc.n[0] + 1, fy1 = 2 * gc.n[1] + 1;
+  const int nx1 = gc.n[0] + 1, ny1 = gc.n[1] + 1;
+  const int fx = (int)(F % fx1), fy = (int)((F / fx1) % fy1), fz = (int)(F / ((int64_t)fx1 * fy1));
+  double v = yf[F];
+  for (int az = 0; az <= (fz & 1); ++az)
+    for (int ay = 0; ay <= (fy & 1); ++ay)
+      for (int ax = 0; ax <= (fx & 1); ++ax) {
+        const double w = ((fx & 1) ? 0.5 : 1.0) * ((fy & 1) ? 0.5 : 1.0) * ((fz & 1) ? 0.5 : 1.0);
+        const size_t c = (size_t)(fx / 2 + ax) + (size_t)nx1 * ((fy / 2 + ay) + (size_t)ny1 * (fz / 2 + az));
+        v = fma(w, __ldcg(ytc + c), v);
+      }
+  ytf[F] = v;
+}
+}  // namespace
+
+// ranges[4] = {a0, b0, a1, b1}: finest-grid nodes the rows of this system touch, and the level-1 nodes their restriction reaches
+int coarse_touched_ranges(ptfem_ctx* ctx, CoarseSpace& cs, int64_t nn, int64_t ranges[4]) {
+  CoarseLevel& L0 = cs.lev[0];
+  ranges[0] = 0; ranges[1] = L0.k; ranges[2] = 0; ranges[3] = cs.nlev > 1 ? cs.lev[1].k : 0;
+  if (cs.nlev < 2 || nn <= 0) return PTFEM_OK;
+  DevBuf<unsigned long long> mm;
+  PT_TRY(mm.alloc(2));
+  const unsigned long long init[2] = {~0ull, 0ull};
+  PT_CK(cudaMemcpyAsync(mm.p, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+  const int nx1 = L0.g.n[0] + 1, ny1 = L0.g.n[1] + 1, nz1 = L0.g.n[2] + 1;
+  touched_range_kernel<<<ceil_div(nn, 256), 256, 0, ctx->stream>>>(nn, cs.ctab.p, L0.shift, nx1, ny1, nz1, mm.p);
+  PT_LAUNCH_CHECK(ctx);
+  unsigned long long h[2];
+  PT_CK(cudaMemcpyAsync(h, mm.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  PT_CK(cudaStreamSynchronize(ctx->stream));
+  if (h[0] > h[1]) return PTFEM_OK;
+  // whole z-planes of the finest grid (node index = x + nx1 (y + ny1 z)); level 1: planes floor(zlo/2) .. ceil(zhi/2)
+  const int64_t plane0 = (int64_t)nx1 * ny1;
+  const int64_t zlo = (int64_t)h[0] / plane0, zhi = (int64_t)h[1] / plane0;
+  ranges[0] = zlo * plane0;
+  ranges[1] = std::min<int64_t>(L0.k, (zhi + 1) * plane0);
+  const CoarseLevel& L1 = cs.lev[1];
+  const int64_t plane1 = (int64_t)(L1.g.n[0] + 1) * (L1.g.n[1] + 1);
+  ranges[2] = (zlo / 2) * plane1;
+  ranges[3] = std::min<int64_t>(L1.k, ((zhi + 1) / 2 + 1) * plane1);
+  return PTFEM_OK;
+}
+
+// restriction of the owned rows on their ranges: out0[a0..b0) (level 0) and out1[a1..b1) (level 1), see above
+int coarse_restrict_rows_sharded(ptfem_ctx* ctx, CoarseSpace& cs, const double* r, const int64_t ranges[4], double* out0,
+                                 double* out1) {
+  CoarseLevel& L0 = cs.lev[0];
+  const int64_t ntask = L0.ncell * L0.split;
+  const int grid = (int)std::min<int64_t>((ntask + 7) / 8, (int64_t)ctx->sm_count * 32);
+  restrict_cell_kernel<1, 4><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p, r,
+                                                            L0.part.p);
+  PT_LAUNCH_CHECK(ctx);
+  if (ranges[1] > ranges[0]) {
+    coarse_node_range_kernel<<<ceil_div(ranges[1] - ranges[0], 256), 256, 0, ctx->stream>>>(L0.g, ranges[0], ranges[1], L0.split,
+                                                                                           L0.part.p, out0);
+    PT_LAUNCH_CHECK(ctx);
+  }
+  if (ranges[3] > ranges[2]) {
+    grid_restrict_range_kernel<<<ceil_div(ranges[3] - ranges[2], 256), 256, 0, ctx->stream>>>(cs.lev[1].g, ranges[2], ranges[3],
+                                                                                             ranges[0], ranges[1], out0, out1);
+    PT_LAUNCH_CHECK(ctx);
+  }
+  return PTFEM_OK;
+}
+
+// lev[start].rc holds the summed restriction of level `start` (and, when scaled, lev[start].yc = binv rc on a diagonal level):
+// the replicated grid hierarchy from that level up and back down to it (yt of level `start`, or yc when it is the last level)
+int coarse_grids_apply(ptfem_ctx* ctx, CoarseSpace& cs, bool scaled0, int start) {
+  if (cs.chain_grid > 0 && start == 0) return chain_launch<1>(ctx, cs, false, scaled0);
+  for (int l = start; l < cs.nlev; ++l) {
     CoarseLevel& L = cs.lev[l];
     double* cdot = cs.cdot.p + (size_t)l * 16;
     const int ngrid = std::min(ceil_div(L.k, 256), 4 * ctx->sm_count);
-    if (l == 0) {
+    if (l == start) {
       if (!L.exact && !scaled0) {
         coarse_scale_kernel<<<ceil_div(L.k, 256), 256, 0, ctx->stream>>>(L.k, L.binv.p, L.rc.p, L.yc.p);
         PT_LAUNCH_CHECK(ctx);
@@ -1361,12 +1500,22 @@ int coarse_grids_apply(ptfem_ctx* ctx, CoarseSpace& cs, bool scaled0) {
       PT_LAUNCH_CHECK(ctx);
     }
   }
-  for (int l = cs.nlev - 2; l >= 0; --l) {
+  for (int l = cs.nlev - 2; l >= start; --l) {
     CoarseLevel& L = cs.lev[l];
     const double* ytc = (l + 1 == cs.nlev - 1) ? cs.lev[l + 1].yc.p : cs.lev[l + 1].yt.p;
     grid_prolong_kernel<1><<<ceil_div(L.k, 256), 256, 0, ctx->stream>>>(cs.lev[l + 1].g, L.k, L.yc.p, ytc, L.yt.p);
     PT_LAUNCH_CHECK(ctx);
   }
+  return PTFEM_OK;
+}
+
+// yt_0 = y_0 + P yt_1 on the finest-grid nodes [a0, b0) only (the rows of this rank read nothing else)
+int coarse_prolong_finest_range(ptfem_ctx* ctx, CoarseSpace& cs, int64_t a0, int64_t b0) {
+  if (cs.nlev < 2 || b0 <= a0) return PTFEM_OK;
+  CoarseLevel& L0 = cs.lev[0];
+  const double* ytc = (cs.nlev == 2) ? cs.lev[1].yc.p : cs.lev[1].yt.p;
+  grid_prolong_range_kernel<<<ceil_div(b0 - a0, 256), 256, 0, ctx->stream>>>(cs.lev[1].g, a0, b0, L0.yc.p, ytc, L0.yt.p);
+  PT_LAUNCH_CHECK(ctx);
   return PTFEM_OK;
 }
 

@@ -178,5 +178,9 @@ void coarse_free(CoarseSpace* cs);
 int coarse_replica_prepare(ptfem_mesh* full);   // api.cu
 int coarse_attach_rows(ptfem_mesh* sys, ptfem_mesh* full, int64_t row0);
 int coarse_restrict_rows(ptfem_ctx* ctx, CoarseSpace& cs, const double* r, double* rc_out);
-int coarse_grids_apply(ptfem_ctx* ctx, CoarseSpace& cs, bool scaled0);
+int coarse_grids_apply(ptfem_ctx* ctx, CoarseSpace& cs, bool scaled0, int start = 0);
+// sharded form of the two above (peer-memory transport): see coarse.cu
+int coarse_touched_ranges(ptfem_ctx* ctx, CoarseSpace& cs, int64_t nn, int64_t ranges[4]);
+int coarse_restrict_rows_sharded(ptfem_ctx* ctx, CoarseSpace& cs, const double* r, const int64_t ranges[4], double* out0, double* out1);
+int coarse_prolong_finest_range(ptfem_ctx* ctx, CoarseSpace& cs, int64_t a0, int64_t b0);
 }  // namespace ptfem

@@ -263,7 +263,7 @@ struct Mail {
   unsigned long long err;                     // local: a bounded wait timed out
   unsigned long long nred;                    // local: reductions started (sequence number of the mailbox protocol)
   unsigned long long xred;                    // local: coarse-grid sums started (sequence number of the exchange buffers)
-  unsigned long long pad[4];
+  unsigned long long wait_ns[4];              // local: time spent in cross-rank waits: [0] halo flags, [1] scalar all-reduce, [2] grid exchange
   unsigned long long ready_from[kMaxRanks];   // ready_from[q] = k : rank q's u of iteration k is complete (pushed by q)
   unsigned long long xready_from[kMaxRanks];  // xready_from[q] = n : rank q's exchange buffer of coarse sum n is complete
   MailBox box[2][kMaxRanks];                  // box[k & 1][q] : rank q's partial sums of iteration k (pushed by q)
@@ -273,6 +273,8 @@ struct PeerTable {
   const double* u[kMaxRanks];  // neighbours' u vectors, indexed by rank (null when not a neighbour)
   const double* xch[kMaxRanks];// every rank's coarse exchange area [2][xstride] (behind its mailbox; null without coarse grids)
   int64_t xstride;
+  int64_t k0;                      // finest-grid unknowns: a rank's exchange buffer is [level-0 part | level-1 part]
+  int64_t range[kMaxRanks][4];     // per rank {a0, b0, a1, b1}: finest / level-1 grid nodes its rows reach (sharded coarse exchange)
   unsigned long long timeout_ns;   // bound of every cross-rank wait (PTFEM_P2P_TIMEOUT_MS, default 20 s)
   int32_t nbr_rank[kMaxRanks];
   int32_t nnbr, rank, nranks;
@@ -308,12 +310,15 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
 // host - costs milliseconds, not a spin count).  On a timeout err is raised in the local mailbox AND pushed into every
 // peer's, and a wait that finds err already raised returns at once: after the first missed wait no rank spins again,
 // the host sees err with the next scalar read-back and abandons the solve (ptfem_dist_solve).
-__device__ __noinline__ bool wait_ge(const unsigned long long* p, unsigned long long want, const PeerTable& pt) {
+__device__ __noinline__ bool wait_ge(const unsigned long long* p, unsigned long long want, const PeerTable& pt, int kind) {
   if (ld_acquire_sys(p) >= want) return true;
   Mail* me = pt.mail[pt.rank];
   const unsigned long long t0 = globaltimer_ns();
   for (unsigned long long n = 1;; ++n) {
-    if (ld_acquire_sys(p) >= want) return true;
+    if (ld_acquire_sys(p) >= want) {
+      me->wait_ns[kind] += globaltimer_ns() - t0;   // (one waiting thread per kernel: no race)
+      return true;
+    }
     if ((n & 31) == 0) {
       if (ld_volatile_u64(&me->err)) return false;
       if (globaltimer_ns() - t0 > pt.timeout_ns) break;
@@ -344,7 +349,7 @@ __device__ void mailbox_allreduce(const double loc[3], const PeerTable& pt, doub
   double tot[3] = {0.0, 0.0, 0.0};
   for (int q = 0; q < pt.nranks; ++q) {
     MailBox* bx = &me->box[par][q];
-    if (!wait_ge(&bx->seq, seq, pt)) break;
+    if (!wait_ge(&bx->seq, seq, pt, 1)) break;
     for (int c = 0; c < 3; ++c) tot[c] += ld_volatile_f64(&bx->v[c]);
   }
   if (bnorm) {
@@ -443,22 +448,64 @@ __global__ void __launch_bounds__(kT) p2p_update_kernel(int64_t n, int first, in
 }
 
 // ---- coarse grids in the partitioned solve -------------------------------------------------------------------
-// u += Z y on the owned rows (y = sum of all levels on the finest grid); signal: last CTA announces u (peer memory)
-__global__ void __launch_bounds__(kT) dist_zadd_kernel(int64_t n, CoarseDev cd, double* __restrict__ u, PeerTable pt, int signal,
-                                                       unsigned int* __restrict__ ticket) {
+// u += Z y on the owned rows (y = sum of all levels on the finest grid).  With `partial`: also the local sums r.u (u complete
+// now) and r.r - per-CTA partials added up in fixed order by the last CTA into scal_out[D_LOC_G], [D_LOC_RR] - so that the
+// iteration needs no separate pass over r, u, w for its dot products (w.u comes out of the SpMV's epilogue).  signal: the
+// last CTA then announces u to the neighbours (peer memory).
+__global__ void __launch_bounds__(kT) dist_zadd_kernel(int64_t n, CoarseDev cd, double* __restrict__ u, const double* __restrict__ r,
+                                                       PeerTable pt, int signal, unsigned int* __restrict__ ticket,
+                                                       double* __restrict__ partial, double* __restrict__ scal_out) {
+  __shared__ int s_last;
+  __shared__ double s_red[2 * (kT / 32)];
   const int64_t stride = (int64_t)gridDim.x * kT;
+  double g_acc = 0.0, rr_acc = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < n; i += stride) {
     double c0[1];
     coarse_prolong<1, 1>(cd, coarse_row_load(cd.ctab, i), 0, c0);
-    u[i] += c0[0];
+    const double ui = u[i] + c0[0];
+    u[i] = ui;
+    if (partial) {
+      const double ri = r[i];
+      g_acc = fma(ri, ui, g_acc);
+      rr_acc = fma(ri, ri, rr_acc);
+    }
   }
-  if (!signal) return;
-  __shared__ int s_last;
+  if (!signal && !partial) return;
+  if (partial) {
+    g_acc = warp_sum(g_acc);
+    rr_acc = warp_sum(rr_acc);
+    if ((threadIdx.x & 31) == 0) {
+      s_red[(threadIdx.x >> 5) * 2] = g_acc;
+      s_red[(threadIdx.x >> 5) * 2 + 1] = rr_acc;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      double a = 0.0;
+      for (int k = 0; k < kT / 32; ++k) a += s_red[k * 2 + threadIdx.x];
+      partial[(size_t)blockIdx.x * 2 + threadIdx.x] = a;
+    }
+  }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
   __syncthreads();
-  if (s_last && threadIdx.x == 0) signal_u_ready(pt);
+  if (!s_last) return;
+  __threadfence();
+  if (partial) {
+    __shared__ double s_part[kT];
+    const int c = threadIdx.x & 1, g = threadIdx.x >> 1;
+    double a = 0.0;
+    for (unsigned bk = g; bk < gridDim.x; bk += kT / 2) a += __ldcg(partial + (size_t)bk * 2 + c);
+    s_part[threadIdx.x] = a;
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      double t = 0.0;
+      for (int gg = 0; gg < kT / 2; ++gg) t += s_part[gg * 2 + threadIdx.x];
+      scal_out[D_LOC_G + threadIdx.x] = t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && signal) signal_u_ready(pt);
 }
 
 // one thread: this rank's exchange buffer of the next coarse sum is complete -> every other rank's mailbox
@@ -480,7 +527,7 @@ __global__ void __launch_bounds__(kT) p2p_coarse_reduce_kernel(int64_t k, int pa
   if (threadIdx.x == 0) {
     const unsigned long long seq = me->xred;   // bumped by the signal kernel just before this launch
     for (int q = 0; q < pt.nranks; ++q)
-      if (q != pt.rank && !wait_ge(&me->xready_from[q], seq, pt)) break;
+      if (q != pt.rank && !wait_ge(&me->xready_from[q], seq, pt, 2)) break;
   }
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * kT;
@@ -497,6 +544,47 @@ __global__ void __launch_bounds__(kT) p2p_coarse_reduce_kernel(int64_t k, int pa
   }
 }
 
+// Sharded form: this rank needs the level-0 sums on ITS nodes [a0, b0) only - contributions of the ranks whose slab
+// overlaps (in rank order: both sides of an overlap add the same numbers in the same order) - and the whole level-1
+// vector, to which every rank contributes the restriction of its own part on its own range.  Per rank the NVLink reads are a
+// few grid planes + the level-1 ranges instead of nranks whole finest-grid vectors.
+__global__ void __launch_bounds__(kT) p2p_coarse_reduce_sharded_kernel(int64_t k1, int par, const double* __restrict__ binv0,
+                                                                       const double* __restrict__ binv1, double* __restrict__ rc0,
+                                                                       double* __restrict__ yc0, double* __restrict__ rc1,
+                                                                       double* __restrict__ yc1, PeerTable pt) {
+  Mail* me = pt.mail[pt.rank];
+  if (threadIdx.x == 0) {
+    const unsigned long long seq = me->xred;   // bumped by the signal kernel just before this launch
+    for (int q = 0; q < pt.nranks; ++q)
+      if (q != pt.rank && !wait_ge(&me->xready_from[q], seq, pt, 2)) break;
+  }
+  __syncthreads();
+  const int64_t a0 = pt.range[pt.rank][0], n0 = pt.range[pt.rank][1] - a0;
+  const size_t base = (size_t)par * pt.xstride;
+  const int64_t stride = (int64_t)gridDim.x * kT;
+  for (int64_t e = (int64_t)blockIdx.x * kT + threadIdx.x; e < n0 + k1; e += stride) {
+    const bool lev1 = e >= n0;
+    const int64_t I = lev1 ? e - n0 : a0 + e;
+    const size_t off = base + (lev1 ? (size_t)pt.k0 : 0) + (size_t)I;
+    double part[kMaxRanks];
+#pragma unroll
+    for (int q = 0; q < kMaxRanks; ++q) {
+      const bool in = q < pt.nranks && I >= pt.range[q][lev1 ? 2 : 0] && I < pt.range[q][lev1 ? 3 : 1];
+      part[q] = in ? ld_volatile_f64(pt.xch[q] + off) : 0.0;
+    }
+    double v = 0.0;
+#pragma unroll
+    for (int q = 0; q < kMaxRanks; ++q) v += part[q];
+    if (lev1) {
+      rc1[I] = v;
+      if (binv1) yc1[I] = v * __ldg(binv1 + I);
+    } else {
+      rc0[I] = v;
+      yc0[I] = v * __ldg(binv0 + I);
+    }
+  }
+}
+
 // halo pull: slot h of neighbour j (recv_ptr ranges) = peer u[src[h]]
 __global__ void __launch_bounds__(kT) p2p_pull_kernel(int64_t nloc, const int32_t* __restrict__ recv_ptr,
                                                       const int32_t* __restrict__ src, double* __restrict__ u, PeerTable pt) {
@@ -505,7 +593,7 @@ __global__ void __launch_bounds__(kT) p2p_pull_kernel(int64_t nloc, const int32_
   const int64_t stride = (int64_t)gridDim.x * kT;
   for (int j = 0; j < pt.nnbr; ++j) {
     const int q = pt.nbr_rank[j];
-    if (threadIdx.x == 0) wait_ge(&me->ready_from[q], k, pt);
+    if (threadIdx.x == 0) wait_ge(&me->ready_from[q], k, pt, 0);
     __syncthreads();
     const double* pu = pt.u[q];
     for (int64_t h = recv_ptr[j] + (int64_t)blockIdx.x * kT + threadIdx.x; h < recv_ptr[j + 1]; h += stride)
@@ -596,6 +684,9 @@ struct DistState {
   int64_t xstride = 0;
   double* xch = nullptr;       // own exchange area [2][xstride] behind the mailbox (peer memory)
   unsigned long long xseq = 0; // coarse sums enqueued so far (host copy of Mail::xred)
+  bool sharded = false;        // coarse exchange by grid slab (>= 2 levels, peer memory): level-0 overlap planes + level-1 vector
+  int64_t ranges[4] = {0, 0, 0, 0};            // own {a0, b0, a1, b1}
+  std::vector<int64_t> all_ranges;             // every rank's, [nranks][4] (ptfem_dist_coarse_ranges_set; empty = whole grids)
 };
 
 }  // namespace
@@ -624,7 +715,7 @@ static int halo_exchange(ptfem_mesh* m, DistState& d, cudaStream_t st) {
   return PTFEM_OK;
 }
 
-static int spmv_rows(ptfem_mesh* m, DistState& d, int64_t r0, int64_t r1) {
+static int spmv_rows(ptfem_mesh* m, DistState& d, int64_t r0, int64_t r1, PcgWork* dot_work = nullptr) {
   if (r1 <= r0) return PTFEM_OK;
   LinSys A;
   A.nn = r1 - r0;
@@ -639,7 +730,7 @@ static int spmv_rows(ptfem_mesh* m, DistState& d, int64_t r0, int64_t r1) {
   A.stream_cap = d.stream_cap;
   // short ranges (the few boundary rows) are not worth a persistent launch
   const int variant = (d.stream_rows > 0 && r1 - r0 >= 16384) ? PTFEM_SPMV_STREAM : PTFEM_SPMV_VECTOR;
-  return spmv_launch(m->ctx, A, variant, d.u.p, d.w.p, nullptr, false);
+  return spmv_launch(m->ctx, A, variant, d.u.p, d.w.p, dot_work, dot_work != nullptr);   // dot_work: local w.u in the epilogue
 }
 
 // w = A u with the halo exchange of u overlapped with the interior rows
@@ -673,7 +764,21 @@ static int dist_coarse_add(ptfem_mesh* m, DistState& d) {
   ptfem_ctx* ctx = m->ctx;
   CoarseSpace& cs = *m->coarse;
   CoarseLevel& L0 = cs.lev[0];
-  if (d.p2p) {
+  if (d.p2p && d.sharded) {
+    const int par = (int)((d.xseq + 1) & 1);
+    double* mine = d.xch + (size_t)par * d.xstride;
+    PT_TRY(coarse_restrict_rows_sharded(ctx, cs, d.r.p, d.ranges, mine, mine + L0.k));
+    p2p_coarse_signal_kernel<<<1, 32, 0, ctx->stream>>>(d.pt);
+    PT_LAUNCH_CHECK(ctx);
+    d.xseq++;
+    CoarseLevel& L1 = cs.lev[1];
+    const int g = std::min(ceil_div(d.ranges[1] - d.ranges[0] + L1.k, kT), 2 * ctx->sm_count);
+    p2p_coarse_reduce_sharded_kernel<<<g, kT, 0, ctx->stream>>>(L1.k, par, L0.binv.p, L1.exact ? nullptr : L1.binv.p, L0.rc.p, L0.yc.p,
+                                                                L1.rc.p, L1.yc.p, d.pt);
+    PT_LAUNCH_CHECK(ctx);
+    PT_TRY(coarse_grids_apply(ctx, cs, !L1.exact, 1));
+    PT_TRY(coarse_prolong_finest_range(ctx, cs, d.ranges[0], d.ranges[1]));
+  } else if (d.p2p) {
     const int par = (int)((d.xseq + 1) & 1);
     PT_TRY(coarse_restrict_rows(ctx, cs, d.r.p, d.xch + (size_t)par * d.xstride));
     p2p_coarse_signal_kernel<<<1, 32, 0, ctx->stream>>>(d.pt);
@@ -691,7 +796,8 @@ static int dist_coarse_add(ptfem_mesh* m, DistState& d) {
     }
     PT_TRY(coarse_grids_apply(ctx, cs, false));
   }
-  dist_zadd_kernel<<<dist_grid(ctx, m->nloc), kT, 0, ctx->stream>>>(m->nloc, coarse_dev(cs), d.u.p, d.pt, d.p2p ? 1 : 0, d.ticket.p);
+  dist_zadd_kernel<<<dist_grid(ctx, m->nloc), kT, 0, ctx->stream>>>(m->nloc, coarse_dev(cs), d.u.p, d.r.p, d.pt, d.p2p ? 1 : 0,
+                                                                    d.ticket.p, d.p2p ? d.partial2.p : nullptr, d.scal.p);
   PT_LAUNCH_CHECK(ctx);
   return PTFEM_OK;
 }
@@ -715,9 +821,10 @@ static int p2p_matvec_reduce(ptfem_mesh* m, DistState& d, int first) {
     p2p_pull_kernel<<<g, kT, 0, ctx->stream>>>(m->nloc, d.recv_ptr_dev.p, d.halo_src.p, d.u.p, d.pt);
     PT_LAUNCH_CHECK(ctx);
   }
-  PT_TRY(spmv_rows(m, d, 0, m->nloc));
-  p2p_dots_kernel<<<dist_grid(ctx, m->nloc), kT, 0, ctx->stream>>>(m->nloc, d.r.p, d.u.p, d.w.p, d.partial.p, d.scal.p,
-                                                                   d.ticket.p, d.pt, first, 0);
+  // w = A u with the local w.u in the SpMV's epilogue; r.u and r.r were left by the kernel that completed u (update, or
+  // the coarse-grid interpolation): the all-reduce + Chronopoulos-Gear scalars are then one single-thread kernel
+  PT_TRY(spmv_rows(m, d, 0, m->nloc, &d.spmv_work));
+  p2p_reduce_kernel<<<1, 32, 0, ctx->stream>>>(d.scal.p, d.spmv_work.scal.p, d.pt, first);
   PT_LAUNCH_CHECK(ctx);
   return PTFEM_OK;
 }
@@ -979,6 +1086,7 @@ int ptfem_dist_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* x_loca
     PT_CK(cudaStreamSynchronize(ctx->stream));
     d.warmed = true;
   }
+  if (p2p) PT_CK(cudaMemsetAsync(d.mail.p->wait_ns, 0, sizeof(d.mail.p->wait_ns), ctx->stream));
   cudaEvent_t e0, e1;
   PT_CK(cudaEventCreate(&e0));
   PT_CK(cudaEventCreate(&e1));
@@ -1096,6 +1204,16 @@ int ptfem_dist_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* x_loca
       cudaEventElapsedTime(&t_ar, e0, e1);
     }
   }
+  if (p2p) {
+    // time the iteration spent waiting for other ranks (globaltimer inside the waiting kernels), per iteration: the peer-memory
+    // transport has no separate halo / all-reduce launches to time - what it has are these waits
+    unsigned long long wn[4] = {0, 0, 0, 0};
+    PT_CK(cudaMemcpyAsync(wn, d.mail.p->wait_ns, sizeof wn, cudaMemcpyDeviceToHost, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    const double per = 1e-6 / (double)(it > 0 ? it : 1);
+    t_halo = (float)(wn[0] * per) * reps;            // (reported as t / reps below)
+    t_ar = (float)((wn[1] + wn[2]) * per) * reps;
+  }
   if (p2p) PT_TRY(read_scal());   // a wait of the last chunk may have timed out after the last read-back
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
@@ -1133,8 +1251,37 @@ int ptfem_dist_coarse_attach(ptfem_mesh* m, ptfem_mesh* full, int64_t row0) {
   PT_TRY(coarse_attach_rows(m, full, row0));
   d.coarse = true;
   d.xk = m->coarse->lev[0].k;
+  // sharded exchange (>= 2 levels): the grid nodes this rank's rows reach; other ranks' ranges arrive through
+  // ptfem_dist_coarse_ranges_set (without them every rank is taken to reach the whole grids: correct, just not sharded)
+  d.sharded = m->coarse->nlev >= 2 && !m->coarse->lev[0].exact;
+  PT_TRY(coarse_touched_ranges(m->ctx, *m->coarse, m->nloc, d.ranges));
+  d.all_ranges.clear();
   if (d.graph) cudaGraphExecDestroy(d.graph);
   d.graph = nullptr;
+  return PTFEM_OK;
+}
+
+int ptfem_dist_coarse_ranges_get(ptfem_mesh* m, int64_t ranges4[4]) {
+  PT_ARG(m && m->is_dist && m->dist && ranges4, "not a distributed system");
+  DistState& d = *m->dist;
+  if (!d.coarse) return set_err(PTFEM_ERR_STATE, "ptfem_dist_coarse_attach has not been called");
+  for (int k = 0; k < 4; ++k) ranges4[k] = d.ranges[k];
+  return PTFEM_OK;
+}
+
+int ptfem_dist_coarse_ranges_set(ptfem_mesh* m, int32_t nranks, const int64_t* all_ranges) {
+  PT_ARG(m && m->is_dist && m->dist && all_ranges, "not a distributed system");
+  PT_ARG(nranks == m->ctx->nranks && nranks <= kMaxRanks, "rank count mismatch");
+  DistState& d = *m->dist;
+  if (!d.coarse) return set_err(PTFEM_ERR_STATE, "ptfem_dist_coarse_attach has not been called");
+  if (d.p2p) return set_err(PTFEM_ERR_STATE, "set the ranges before ptfem_dist_p2p_connect");
+  for (int q = 0; q < nranks; ++q) {
+    const int64_t* r = all_ranges + 4 * q;
+    if (r[0] < 0 || r[1] < r[0] || r[1] > d.xk || r[2] < 0 || r[3] < r[2]) return set_err(PTFEM_ERR_ARG, "bad range of rank %d", q);
+  }
+  for (int k = 0; k < 4; ++k)
+    if (all_ranges[4 * m->ctx->rank + k] != d.ranges[k]) return set_err(PTFEM_ERR_ARG, "own range differs from ptfem_dist_coarse_ranges_get");
+  d.all_ranges.assign(all_ranges, all_ranges + 4 * nranks);
   return PTFEM_OK;
 }
 
@@ -1146,7 +1293,7 @@ int ptfem_dist_p2p_export(ptfem_mesh* m, void* handles128) {
     // one allocation = one IPC handle: the coarse exchange area [2][xstride] lives behind the mailbox
     size_t nmail = 1;
     if (d.coarse) {
-      d.xstride = (d.xk + 15) & ~(int64_t)15;
+      d.xstride = (d.xk + (d.sharded ? m->coarse->lev[1].k : 0) + 15) & ~(int64_t)15;
       nmail += (2 * (size_t)d.xstride * sizeof(double) + sizeof(Mail) - 1) / sizeof(Mail);
     }
     PT_TRY(d.mail.alloc(nmail));
@@ -1177,6 +1324,17 @@ int ptfem_dist_p2p_connect(ptfem_mesh* m, int32_t nranks, const void* all_handle
   pt.nranks = nranks;
   pt.nnbr = m->nnbr;
   pt.xstride = d.xstride;
+  pt.k0 = d.xk;
+  for (int q = 0; q < kMaxRanks; ++q) {
+    const bool have = (int)d.all_ranges.size() == 4 * nranks && q < nranks;
+    pt.range[q][0] = have ? d.all_ranges[4 * q] : 0;
+    pt.range[q][1] = have ? d.all_ranges[4 * q + 1] : d.xk;
+    pt.range[q][2] = have ? d.all_ranges[4 * q + 2] : 0;
+    pt.range[q][3] = have ? d.all_ranges[4 * q + 3] : (d.sharded ? m->coarse->lev[1].k : 0);
+  }
+  if ((int)d.all_ranges.size() != 4 * nranks && d.sharded) {   // own ranges too: everybody reaches everything
+    d.ranges[0] = 0; d.ranges[1] = d.xk; d.ranges[2] = 0; d.ranges[3] = m->coarse->lev[1].k;
+  }
   pt.timeout_ns = kWaitDefaultNs;
   if (const char* e = getenv("PTFEM_P2P_TIMEOUT_MS")) {
     const double ms = atof(e);

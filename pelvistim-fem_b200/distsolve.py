@@ -67,7 +67,18 @@ def partitioned_solve(ctx, mesh, sigma_by_body, dirichlet, neumann, rank, world,
         try:
             engine.dist_init(ctx, None, rank, world)
             ds = make_system()
-            exported = ds.p2p_export()
+            my_ranges = ds.coarse_ranges().tolist() if state["coarse"] else None
+        except engine.PtfemError as e:
+            p2p_error = str(e)
+            my_ranges = None
+        # sharded coarse exchange: every rank learns which slab of the coarse grids every other rank's rows reach
+        all_ranges = [None] * world
+        dist.all_gather_object(all_ranges, my_ranges if p2p_error is None else None)
+        try:
+            if p2p_error is None:
+                if state["coarse"] and all(r is not None for r in all_ranges):
+                    ds.set_coarse_ranges(np.array(all_ranges, dtype=np.int64))
+                exported = ds.p2p_export()
         except engine.PtfemError as e:
             p2p_error = str(e)
         handles = [None] * world

@@ -126,6 +126,8 @@ def load_library():
         "ptfem_dist_system_create": (C.c_int, [vp, i64, i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, P(vp)]),
         "ptfem_dist_solve": (C.c_int, [vp, P(SolveOpts), vp, P(SolveStats), P(dbl), P(dbl), P(dbl)]),
         "ptfem_dist_coarse_attach": (C.c_int, [vp, vp, i64]),
+        "ptfem_dist_coarse_ranges_get": (C.c_int, [vp, vp]),
+        "ptfem_dist_coarse_ranges_set": (C.c_int, [vp, i32, vp]),
         "ptfem_dist_p2p_export": (C.c_int, [vp, vp]),
         "ptfem_dist_p2p_connect": (C.c_int, [vp, i32, vp, vp]),
     }
@@ -582,6 +584,17 @@ class DistSystem:
         and boundary conditions; rows ``[row0, row0 + nloc)`` of its coarse spaces are taken (``ptfem_dist_coarse_attach``).
         Call before :meth:`p2p_export`."""
         self.ctx._ck(self.lib.ptfem_dist_coarse_attach(self._h, replica._h, int(row0)))
+
+    def coarse_ranges(self):
+        """This rank's {a0, b0, a1, b1} of the sharded coarse exchange (``ptfem_dist_coarse_ranges_get``)."""
+        out = np.zeros(4, dtype=np.int64)
+        self.ctx._ck(self.lib.ptfem_dist_coarse_ranges_get(self._h, _ptr(out)))
+        return out
+
+    def set_coarse_ranges(self, all_ranges):
+        """Every rank's ranges, [nranks, 4] (all-gathered by the launcher), before :meth:`p2p_connect`."""
+        a = np.ascontiguousarray(all_ranges, dtype=np.int64)
+        self.ctx._ck(self.lib.ptfem_dist_coarse_ranges_set(self._h, a.shape[0], _ptr(a)))
 
     def p2p_export(self) -> bytes:
         buf = C.create_string_buffer(128)
