@@ -237,6 +237,19 @@ int ptfem_dist_solve(ptfem_mesh* sys, const ptfem_solve_opts* opts, double* x_lo
  * ptfem_dist_solve then preconditions with Jacobi + coarse grids for PTFEM_PRECOND_AUTO / _TWOLEVEL.
  * PTFEM_ERR_STATE: the Galerkin matrix is singular on this mesh (keep Jacobi). */
 int ptfem_dist_coarse_attach(ptfem_mesh* sys, ptfem_mesh* replica, int64_t row0);
+/* Distributed set-up (no rank holds the whole mesh): every rank creates a mesh of its OWNED nodes (global rows
+ * [row0, row0+nloc), first), the ghost nodes of the elements touching them and the nodes of boundary triangles touching
+ * those (partition.local_submesh), assembles and applies the boundary conditions on it - the owned rows of that matrix are
+ * complete, with columns already numbered [owned | halo] - and builds its block with ptfem_dist_system_create from them.
+ * ptfem_mesh_set_bbox gives the local mesh the bounding box of the WHOLE mesh and marks it as a part (a part may hold no
+ * Dirichlet node: call it before the first solve / value read-back).  Coarse grids: ptfem_dist_coarse_partial
+ * computes the Galerkin sums of the owned rows on grids chosen for nn_global nodes (sums == NULL: size query, *n doubles);
+ * the launcher adds the arrays of all ranks; ptfem_dist_coarse_finish inverts them (identical on every rank); then
+ * ptfem_dist_coarse_attach(sys, local_mesh, 0). */
+int ptfem_mesh_set_bbox(ptfem_mesh* m, const double* lo /*[3]*/, const double* hi /*[3]*/);
+int ptfem_dist_coarse_partial(ptfem_mesh* local_mesh, int64_t nrows_owned, int64_t nn_global, int32_t coarse_nodes,
+                              int32_t coarse_levels, int64_t* n, double* sums /*[cap] or NULL*/, int64_t cap);
+int ptfem_dist_coarse_finish(ptfem_mesh* local_mesh, const double* sums /*[n]*/, int64_t n);
 /* Sharded coarse exchange of the peer-memory transport: a contiguous block of rows reaches a slab of the finest grid only.
  * _get returns this rank's {a0, b0, a1, b1} (finest-grid nodes [a0, b0) and level-1 nodes [a1, b1) its rows contribute to,
  * known after ptfem_dist_coarse_attach); the launcher all-gathers them and hands every rank the whole table with _set, before

@@ -200,6 +200,7 @@ int ptfem_ctx_create(int device, ptfem_ctx** out) {
   if (const char* e = getenv("PTFEM_COARSE_FUSED")) c->tune_coarse_fused = atoi(e) != 0;
   if (const char* e = getenv("PTFEM_PUPDATE_NP")) c->tune_pupdate_np = atoi(e) == 2 ? 2 : 1;
   if (const char* e = getenv("PTFEM_PUPDATE_OCC")) c->tune_pupdate_occ = atoi(e);
+  if (const char* e = getenv("PTFEM_CHAIN_TAIL")) c->tune_chain_tail = atoi(e) != 0;
   if (const char* e = getenv("PTFEM_COARSE_WEIGHT")) {
     const double w = atof(e);
     if (w > 0.0) c->tune_coarse_weight = w;
@@ -331,6 +332,42 @@ int ptfem_mesh_set_coords(ptfem_mesh* m, const double* xyz) {
   m->nval = 0;  // values must be re-assembled
   m->bc_dirty = true;
   return PTFEM_OK;
+}
+
+int ptfem_mesh_set_bbox(ptfem_mesh* m, const double* lo, const double* hi) {
+  PT_ARG(m && lo && hi, "null pointer");
+  for (int d = 0; d < 3; ++d) {
+    PT_ARG(hi[d] >= lo[d], "empty bounding box");
+    m->bb_lo[d] = lo[d];
+    m->bb_hi[d] = hi[d];
+  }
+  if (m->coarse) m->coarse->geom_ok = false;
+  m->is_part = true;
+  return PTFEM_OK;
+}
+
+int ptfem_dist_coarse_partial(ptfem_mesh* m, int64_t nrows_owned, int64_t nn_global, int32_t coarse_nodes, int32_t coarse_levels,
+                              int64_t* n, double* sums, int64_t cap) {
+  PT_ARG(m && !m->is_dist && n, "needs the rank's local mesh");
+  PT_ARG(nrows_owned > 0 && nrows_owned <= m->nn && nn_global >= nrows_owned, "bad row counts");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  PT_TRY(prepare_systems(m));
+  if (m->nvalp != 1 || m->S != 1) return set_err(PTFEM_ERR_ARG, "the distributed set-up handles one matrix, one right-hand side");
+  if (!m->coarse || !m->coarse->partial_ready || m->coarse->row_limit != nrows_owned || m->coarse->nn_levels != nn_global) {
+    if (m->coarse) coarse_free(m->coarse);
+    m->coarse = new CoarseSpace();
+    m->coarse->row_limit = nrows_owned;
+    m->coarse->nn_levels = nn_global;
+    m->coarse->partial_mode = true;
+    PT_TRY(coarse_prepare(m, coarse_nodes, coarse_levels, 1));
+  }
+  return coarse_partial_sums(m, n, sums, cap);
+}
+
+int ptfem_dist_coarse_finish(ptfem_mesh* m, const double* sums, int64_t n) {
+  PT_ARG(m && !m->is_dist && sums, "needs the rank's local mesh and the summed Galerkin data");
+  PT_CK(cudaSetDevice(m->ctx->device));
+  return coarse_finish_sums(m, sums, n);
 }
 
 int ptfem_pattern(ptfem_mesh* m, int64_t* nnz) {

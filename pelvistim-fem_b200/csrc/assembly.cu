@@ -451,7 +451,7 @@ int ptfem_apply_bc(ptfem_mesh* m, double* dinv_out /*[nn][VS]*/, int* S_out) {
     int32_t h = 0;
     PT_CK(cudaMemcpyAsync(&h, flag.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     PT_CK(cudaStreamSynchronize(ctx->stream));
-    if (!h)
+    if (!h && !m->is_part)   // (one rank's part of a larger mesh may hold no electrode at all)
       return set_err(PTFEM_ERR_ARG, "no mesh node carries a Potential (Dirichlet) condition: the boundary ids given to "
                                     "ptfem_bc_dirichlet do not occur in the mesh, or none was set (pure Neumann problem is singular)");
   }

@@ -632,12 +632,12 @@ __global__ void __launch_bounds__(256) galerkin_cell_kernel(CoarseGrid g, const 
 
 // E[I][J] += sum over the cells around I of their block entry for (I, J); padding / empty nodes -> identity
 __global__ void __launch_bounds__(256) galerkin_gather_kernel(CoarseGrid g, int64_t k, int kp, const double* __restrict__ blockE,
-                                                              double* __restrict__ E, int gsplit) {
+                                                              double* __restrict__ E, int gsplit, int fix) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (int64_t)kp * kp) return;
   const int64_t I = e / kp, J = e % kp;
   if (I >= k || J >= k) {
-    E[e] = I == J ? 1.0 : 0.0;
+    E[e] = (I == J && fix) ? 1.0 : 0.0;
     return;
   }
   const int nx1 = g.n[0] + 1, ny1 = g.n[1] + 1;
@@ -655,8 +655,19 @@ __global__ void __launch_bounds__(256) galerkin_gather_kernel(CoarseGrid g, int6
       for (int sp = 0; sp < gsplit; ++sp) v += blockE[((size_t)c * gsplit + sp) * 512 + a * 64 + (sx + 4 * sy + 16 * sz)];
     }
   }
-  if (I == J && !(v > 0.0)) v = 1.0;  // grid node without a free mesh node in its support
+  if (fix && I == J && !(v > 0.0)) v = 1.0;  // grid node without a free mesh node in its support
   E[e] = v;
+}
+// the same fix applied to raw sums added up over the ranks (distributed set-up)
+__global__ void galerkin_fix_kernel(int64_t k, int kp, double* __restrict__ E) {
+  const int I = blockIdx.x * blockDim.x + threadIdx.x;
+  if (I >= kp) return;
+  const double v = E[(size_t)I * kp + I];
+  if (I >= k || !(v > 0.0)) E[(size_t)I * kp + I] = 1.0;
+}
+__global__ void diag_invert_kernel(int64_t k, double w, double* __restrict__ binv) {
+  const int64_t I = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (I < k) binv[I] = binv[I] > 0.0 ? w / binv[I] : 0.0;
 }
 
 // ---- Galerkin diagonals of the finer (BPX) levels ---------------------------------------------------------------
@@ -727,7 +738,7 @@ __global__ void __launch_bounds__(256) galerkin_diag_multi_kernel(int nb, int sh
 // one warp per grid node of level l (cells 2^l = f times the finest's): binv[I] = 1 / sum over the (up to) eight cells around
 // I of the contributions of their f^3 finest children (lanes stride over the children, fixed shuffle tree: deterministic)
 __global__ void galerkin_diag_node_multi_kernel(CoarseGrid g, int64_t k, int f, int nf0, int nf1, const double* __restrict__ dpart_l,
-                                                double* __restrict__ binv) {
+                                                double* __restrict__ binv, int invert) {
   const int64_t I = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (I >= k) return;
@@ -745,7 +756,7 @@ __global__ void galerkin_diag_node_multi_kernel(CoarseGrid g, int64_t k, int f, 
     }
   }
   v = warp_sum(v);
-  if (lane == 0) binv[I] = v > 0.0 ? 1.0 / v : 0.0;
+  if (lane == 0) binv[I] = invert ? (v > 0.0 ? 1.0 / v : 0.0) : v;
 }
 
 // ---- dense inverse: blocked Gauss-Jordan without pivoting (the matrix is SPD) ---------------------------------
@@ -899,7 +910,7 @@ __global__ void coarse_scale_kernel(int64_t k, const double* __restrict__ binv, 
 // ---- host side ------------------------------------------------------------------------------------------------
 int build_level_geometry(ptfem_mesh* m, CoarseLevel& L, bool lists = true) {
   ptfem_ctx* ctx = m->ctx;
-  const int64_t nn = m->nn;
+  const int64_t nn = (m->coarse && m->coarse->row_limit >= 0) ? m->coarse->row_limit : m->nn;   // rows that enter the lists
   L.ncell = (int64_t)L.g.n[0] * L.g.n[1] * L.g.n[2];
   L.k = (int64_t)(L.g.n[0] + 1) * (L.g.n[1] + 1) * (L.g.n[2] + 1);
   if (!lists) return PTFEM_OK;   // only the finest level (restriction, diagonals) and the exact one (Galerkin matrix) walk row lists
@@ -1107,7 +1118,8 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
       const double cells = (double)b0.n[0] * b0.n[1] * b0.n[2];
       const double min_rows = extra_levels < 0 ? 16.0 : 8.0;
       cs.nlev = extra_levels < 0 ? kMaxCoarseLevels : extra_levels + 1;
-      while (cs.nlev > 1 && cells * pow(8.0, cs.nlev - 1) * min_rows > (double)m->nn) --cs.nlev;
+      const double nn_rule = (double)(cs.nn_levels > 0 ? cs.nn_levels : m->nn);   // (distributed set-up: the WHOLE mesh's node count)
+      while (cs.nlev > 1 && cells * pow(8.0, cs.nlev - 1) * min_rows > nn_rule) --cs.nlev;
     }
     CoarseGrid base;
     choose_grid(m, (double)target_nodes, base);
@@ -1130,7 +1142,7 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
       L.kp = L.exact ? (int)((L.k + kGjTile - 1) / kGjTile) * kGjTile : 0;
       // restriction tasks (one warp each) of at most ~96 rows
       L.split = 1;
-      while (m->nn / (L.ncell * L.split) > 96 && L.split < 64) L.split *= 2;
+      while ((cs.nn_levels > 0 ? cs.nn_levels : m->nn) / (L.ncell * L.split) > 96 && L.split < 64) L.split *= 2;
     }
     cs.geom_ok = true;
     cs.req_nodes = target_nodes;
@@ -1171,8 +1183,9 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
     PT_CK(cudaMemsetAsync(cs.flag.p, 0, 2 * sizeof(int32_t), ctx->stream));
     coarse_table_flag_kernel<<<ceil_div(m->nn, 256), 256, 0, ctx->stream>>>(m->isdir.p, m->nn, cs.ctab.p);
     PT_LAUNCH_CHECK(ctx);
+    const int64_t nlist = cs.row_limit >= 0 ? cs.row_limit : m->nn;
     PT_TRY(cs.ctab0.alloc((size_t)m->nn));
-    gather_table_kernel<<<ceil_div(m->nn, 256), 256, 0, ctx->stream>>>(cs.ctab.p, cs.lev[0].rows.p, m->nn, cs.ctab0.p);
+    gather_table_kernel<<<ceil_div(nlist, 256), 256, 0, ctx->stream>>>(cs.ctab.p, cs.lev[0].rows.p, nlist, cs.ctab0.p);
     PT_LAUNCH_CHECK(ctx);
     // the additive levels overlap in what they correct (every level sees the smooth part of r): each is weighted by
     // 2 / (levels + 1) against the Jacobi term - CPU study profiles/r01_precond_level_weights_L_cpu.txt: 71 -> 60 iterations
@@ -1188,14 +1201,19 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
         PT_CK(cudaMemsetAsync(L.binv.p, 0, n2 * sizeof(double), ctx->stream));
         DevBuf<double> blockE;
         int gsplit = 1;   // CTAs per cell: about eight CTAs per SM in all, each with at least a few chunks of rows
-        while (L.ncell * gsplit < (int64_t)8 * ctx->sm_count && m->nn / (L.ncell * gsplit) > 4 * kGalRows && gsplit < 64) gsplit *= 2;
+        while (L.ncell * gsplit < (int64_t)8 * ctx->sm_count && nlist / (L.ncell * gsplit) > 4 * kGalRows && gsplit < 64) gsplit *= 2;
         PT_TRY(blockE.alloc((size_t)L.ncell * gsplit * 512));
         galerkin_cell_kernel<<<(unsigned)(L.ncell * gsplit), 256, 0, ctx->stream>>>(L.g, L.cellptr.p, L.rows.p, cs.ctab.p,
                                                                                      m->rowptr.p, m->col.p, m->val_bc.p, blockE.p,
                                                                                      L.binv.p, L.kp, cs.flag.p, gsplit);
         PT_LAUNCH_CHECK(ctx);
-        galerkin_gather_kernel<<<ceil_div((int64_t)n2, 256), 256, 0, ctx->stream>>>(L.g, L.k, L.kp, blockE.p, L.binv.p, gsplit);
+        galerkin_gather_kernel<<<ceil_div((int64_t)n2, 256), 256, 0, ctx->stream>>>(L.g, L.k, L.kp, blockE.p, L.binv.p, gsplit,
+                                                                                    cs.partial_mode ? 0 : 1);
         PT_LAUNCH_CHECK(ctx);
+        if (cs.partial_mode) {
+          PT_CK(cudaStreamSynchronize(ctx->stream));   // blockE goes back to the allocator
+          continue;
+        }
         PT_TRY(dense_inverse(ctx, L.binv.p, L.kp, cs.flag.p));
         if (level_w != 1.0) {
           coarse_weight_kernel<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(L.binv.p, (int64_t)n2, level_w);
@@ -1221,9 +1239,10 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
       for (int l = 0; l < nb; ++l) {
         CoarseLevel& L = cs.lev[l];
         galerkin_diag_node_multi_kernel<<<ceil_div(L.k * 32, 256), 256, 0, ctx->stream>>>(L.g, L.k, 1 << l, L0.g.n[0], L0.g.n[1],
-                                                                                         dpartf.p + (size_t)l * L0.ncell * 8, L.binv.p);
+                                                                                         dpartf.p + (size_t)l * L0.ncell * 8, L.binv.p,
+                                                                                         cs.partial_mode ? 0 : 1);
         PT_LAUNCH_CHECK(ctx);
-        if (level_w != 1.0) {
+        if (level_w != 1.0 && !cs.partial_mode) {
           coarse_weight_kernel<<<ceil_div(L.k, 256), 256, 0, ctx->stream>>>(L.binv.p, L.k, level_w);
           PT_LAUNCH_CHECK(ctx);
         }
@@ -1236,7 +1255,11 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
     if (hflag[0])
       return set_err(PTFEM_ERR_STATE, "coarse Galerkin matrix is singular or indefinite to working precision (grid %dx%dx%d too fine for this mesh?)",
                      cs.lev[cs.nlev - 1].g.n[0], cs.lev[cs.nlev - 1].g.n[1], cs.lev[cs.nlev - 1].g.n[2]);
-    cs.matrix_epoch = m->matrix_epoch;
+    if (cs.partial_mode) {
+      cs.partial_ready = true;   // raw sums of the owned rows; coarse_finish_sums completes them
+    } else {
+      cs.matrix_epoch = m->matrix_epoch;
+    }
     rebuilt = true;
   }
   PT_CK(cudaEventRecord(e1, ctx->stream));
@@ -1247,6 +1270,69 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
   return PTFEM_OK;
 }
 
+
+// ---- distributed set-up: Galerkin sums of the owned rows, added up over the ranks by the launcher ------------------------
+static int64_t partial_sum_count(const CoarseSpace& cs) {
+  int64_t n = 0;
+  for (int l = 0; l < cs.nlev; ++l) n += cs.lev[l].exact ? (int64_t)cs.lev[l].kp * cs.lev[l].kp : cs.lev[l].k;
+  return n;
+}
+int coarse_partial_sums(ptfem_mesh* m, int64_t* n_out, double* out_host, int64_t cap) {
+  if (!m->coarse || !m->coarse->partial_ready) return set_err(PTFEM_ERR_STATE, "the partial coarse set-up has not been run");
+  CoarseSpace& cs = *m->coarse;
+  const int64_t n = partial_sum_count(cs);
+  if (n_out) *n_out = n;
+  if (!out_host) return PTFEM_OK;
+  if (cap < n) return set_err(PTFEM_ERR_ARG, "buffer of %lld doubles, %lld needed", (long long)cap, (long long)n);
+  int64_t off = 0;
+  for (int l = cs.nlev - 1; l >= 0; --l) {   // exact level first, then levels 0 .. nlev-2
+    if (!cs.lev[l].exact) continue;
+    const int64_t c = (int64_t)cs.lev[l].kp * cs.lev[l].kp;
+    PT_CK(cudaMemcpyAsync(out_host + off, cs.lev[l].binv.p, c * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
+    off += c;
+  }
+  for (int l = 0; l < cs.nlev - 1; ++l) {
+    PT_CK(cudaMemcpyAsync(out_host + off, cs.lev[l].binv.p, cs.lev[l].k * sizeof(double), cudaMemcpyDeviceToHost, m->ctx->stream));
+    off += cs.lev[l].k;
+  }
+  PT_CK(cudaStreamSynchronize(m->ctx->stream));
+  return PTFEM_OK;
+}
+int coarse_finish_sums(ptfem_mesh* m, const double* sums_host, int64_t n) {
+  if (!m->coarse || !m->coarse->partial_ready) return set_err(PTFEM_ERR_STATE, "the partial coarse set-up has not been run");
+  ptfem_ctx* ctx = m->ctx;
+  CoarseSpace& cs = *m->coarse;
+  if (n != partial_sum_count(cs)) return set_err(PTFEM_ERR_ARG, "%lld sums given, %lld expected", (long long)n, (long long)partial_sum_count(cs));
+  const double level_w = ctx->tune_coarse_weight > 0.0 ? ctx->tune_coarse_weight : 2.0 / (cs.nlev + 1);
+  int64_t off = 0;
+  CoarseLevel& X = cs.lev[cs.nlev - 1];
+  const int64_t n2 = (int64_t)X.kp * X.kp;
+  PT_CK(cudaMemcpyAsync(X.binv.p, sums_host + off, n2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  off += n2;
+  galerkin_fix_kernel<<<ceil_div(X.kp, 256), 256, 0, ctx->stream>>>(X.k, X.kp, X.binv.p);
+  PT_LAUNCH_CHECK(ctx);
+  PT_CK(cudaMemsetAsync(cs.flag.p, 0, 2 * sizeof(int32_t), ctx->stream));
+  PT_TRY(dense_inverse(ctx, X.binv.p, X.kp, cs.flag.p));
+  if (level_w != 1.0) {
+    coarse_weight_kernel<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(X.binv.p, n2, level_w);
+    PT_LAUNCH_CHECK(ctx);
+  }
+  for (int l = 0; l < cs.nlev - 1; ++l) {
+    CoarseLevel& L = cs.lev[l];
+    PT_CK(cudaMemcpyAsync(L.binv.p, sums_host + off, L.k * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    off += L.k;
+    diag_invert_kernel<<<ceil_div(L.k, 256), 256, 0, ctx->stream>>>(L.k, level_w, L.binv.p);
+    PT_LAUNCH_CHECK(ctx);
+  }
+  int32_t hflag[2] = {0, 0};
+  PT_CK(cudaMemcpyAsync(hflag, cs.flag.p, sizeof hflag, cudaMemcpyDeviceToHost, ctx->stream));
+  PT_CK(cudaStreamSynchronize(ctx->stream));
+  if (hflag[0]) return set_err(PTFEM_ERR_STATE, "coarse Galerkin matrix is singular or indefinite to working precision");
+  cs.matrix_epoch = m->matrix_epoch;
+  cs.partial_mode = false;   // the spaces now hold the operators of the whole matrix
+  cs.generation++;
+  return PTFEM_OK;
+}
 
 // ---- row-partitioned solve ------------------------------------------------------------------------------------
 // The ranks of a partitioned solve each hold a replica of the mesh (they assembled it, as in a sweep) and a block of
@@ -1472,10 +1558,70 @@ int coarse_restrict_rows_sharded(ptfem_ctx* ctx, CoarseSpace& cs, const double* 
   return PTFEM_OK;
 }
 
+// The grid hierarchy above level `start` as ONE block of 1024 threads (row-partitioned solve, one right-hand side): with the
+// finest level sharded over the ranks, what is left replicated are a few thousand grid nodes - five dependent kernels of
+// ~6 us launch-to-launch each did a few microseconds of work.  Phases are separated by block barriers.
+namespace {
+__global__ void __launch_bounds__(1024) coarse_chain_tail_kernel(ChainArgs a, int start) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  for (int l = start + 1; l < a.nlev; ++l) {
+    const ChainLevel& L = a.lev[l];
+    const double* rf = a.lev[l - 1].rc;
+    for (int64_t I = tid; I < L.k; I += nth) {
+      const double v = chain_restrict27<1>(L.g, rf, I, 0);
+      L.rc[I] = v;
+      if (!L.exact) L.yc[I] = v * L.binv[I];
+    }
+    __syncthreads();
+  }
+  {  // exact level: y = B r, one warp per row
+    const ChainLevel& L = a.lev[a.nlev - 1];
+    const int lane = tid & 31, wid = tid >> 5, nw = nth >> 5;
+    for (int I = wid; I < L.kp; I += nw) {
+      double acc = 0.0;
+      for (int J = lane; J < L.kp; J += 32) acc = fma(L.binv[(size_t)I * L.kp + J], L.rc[J], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) L.yc[I] = acc;
+    }
+    __syncthreads();
+  }
+  for (int l = a.nlev - 2; l >= start; --l) {
+    const ChainLevel& L = a.lev[l];
+    const double* ytc = (l + 1 == a.nlev - 1) ? a.lev[l + 1].yc : a.lev[l + 1].yt;
+    for (int64_t F = tid; F < L.k; F += nth) L.yt[F] = chain_prolong8<1>(a.lev[l + 1].g, ytc, L.yc[F], F, 0);
+    __syncthreads();
+  }
+}
+}  // namespace
+
 // lev[start].rc holds the summed restriction of level `start` (and, when scaled, lev[start].yc = binv rc on a diagonal level):
 // the replicated grid hierarchy from that level up and back down to it (yt of level `start`, or yc when it is the last level)
 int coarse_grids_apply(ptfem_ctx* ctx, CoarseSpace& cs, bool scaled0, int start) {
   if (cs.chain_grid > 0 && start == 0) return chain_launch<1>(ctx, cs, false, scaled0);
+  if (start >= 1 && (scaled0 || cs.lev[start].exact) && cs.lev[start].k <= 65536 && ctx->tune_chain_tail) {
+    ChainArgs a;
+    a.nlev = cs.nlev;
+    a.split = 1;
+    a.do_node = 0;
+    a.scaled0 = 1;
+    for (int l = 0; l < cs.nlev; ++l) {
+      CoarseLevel& L = cs.lev[l];
+      a.lev[l].g = L.g;
+      a.lev[l].k = L.k;
+      a.lev[l].kp = L.kp;
+      a.lev[l].exact = L.exact ? 1 : 0;
+      a.lev[l].binv = L.binv.p;
+      a.lev[l].rc = L.rc.p;
+      a.lev[l].yc = L.yc.p;
+      a.lev[l].yt = L.yt.p;
+    }
+    a.part = nullptr;
+    a.dpart = nullptr;
+    a.cdot = nullptr;
+    coarse_chain_tail_kernel<<<1, 1024, 0, ctx->stream>>>(a, start);
+    PT_LAUNCH_CHECK(ctx);
+    return PTFEM_OK;
+  }
   for (int l = start; l < cs.nlev; ++l) {
     CoarseLevel& L = cs.lev[l];
     double* cdot = cs.cdot.p + (size_t)l * 16;

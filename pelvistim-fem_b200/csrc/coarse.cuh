@@ -59,6 +59,11 @@ struct CoarseSpace {
   ptfem::DevBuf<float4> ctab0;            // the same rows in the order of level 0's row list (restriction reads it in step with the list)
   ptfem::DevBuf<int32_t> flag;            // [0] non-positive pivot seen, [1] slow-path entries
   double setup_ms = 0.0;
+  // distributed set-up (a rank's local mesh = owned rows first, then ghost nodes): only the first row_limit rows own
+  // Galerkin contributions and enter the row lists; nn_levels = node count of the WHOLE mesh (level rule); partial_mode:
+  // coarse_prepare stops at the raw Galerkin sums, which the ranks add up before coarse_finish_sums inverts them
+  int64_t row_limit = -1, nn_levels = -1;
+  bool partial_mode = false, partial_ready = false;
   int chain_grid = 0;                     // CTAs of the cooperative grid-hierarchy kernel (0: separate kernels)
   ptfem::DevBuf<double> chain_part;       // its per-CTA dot partials [nlev][chain_grid][S]
 };
@@ -169,6 +174,10 @@ namespace ptfem {
 // operators (matrix changed).  target_nodes: unknowns of the exact level (0 = default); extra_levels: finer
 // diagonal-only levels (each halves the cell size).
 int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S);
+// distributed set-up: raw Galerkin sums of the owned rows [kp*kp | k_0 | k_1 | ...] (size query with out == nullptr), and the
+// inversion once the launcher has summed them over the ranks
+int coarse_partial_sums(ptfem_mesh* m, int64_t* n_out, double* out_host, int64_t cap);
+int coarse_finish_sums(ptfem_mesh* m, const double* sums_host, int64_t n);
 // y_c = B_l Z_l^T r for every level; leaves r_c.y_c per level/system in cs.cdot
 int coarse_apply(ptfem_ctx* ctx, CoarseSpace& cs, int S, const double* r);
 CoarseDev coarse_dev(const CoarseSpace& cs);

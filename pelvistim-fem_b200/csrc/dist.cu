@@ -316,7 +316,7 @@ __device__ __noinline__ bool wait_ge(const unsigned long long* p, unsigned long 
   const unsigned long long t0 = globaltimer_ns();
   for (unsigned long long n = 1;; ++n) {
     if (ld_acquire_sys(p) >= want) {
-      me->wait_ns[kind] += globaltimer_ns() - t0;   // (one waiting thread per kernel: no race)
+      if (kind >= 0) me->wait_ns[kind] += globaltimer_ns() - t0;   // (accounted by one thread per kernel - CTA 0's: no race)
       return true;
     }
     if ((n & 31) == 0) {
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(kT) p2p_coarse_reduce_kernel(int64_t k, int pa
   if (threadIdx.x == 0) {
     const unsigned long long seq = me->xred;   // bumped by the signal kernel just before this launch
     for (int q = 0; q < pt.nranks; ++q)
-      if (q != pt.rank && !wait_ge(&me->xready_from[q], seq, pt, 2)) break;
+      if (q != pt.rank && !wait_ge(&me->xready_from[q], seq, pt, blockIdx.x == 0 ? 2 : -1)) break;
   }
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * kT;
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(kT) p2p_coarse_reduce_sharded_kernel(int64_t k
   if (threadIdx.x == 0) {
     const unsigned long long seq = me->xred;   // bumped by the signal kernel just before this launch
     for (int q = 0; q < pt.nranks; ++q)
-      if (q != pt.rank && !wait_ge(&me->xready_from[q], seq, pt, 2)) break;
+      if (q != pt.rank && !wait_ge(&me->xready_from[q], seq, pt, blockIdx.x == 0 ? 2 : -1)) break;
   }
   __syncthreads();
   const int64_t a0 = pt.range[pt.rank][0], n0 = pt.range[pt.rank][1] - a0;
@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(kT) p2p_pull_kernel(int64_t nloc, const int32_
   const int64_t stride = (int64_t)gridDim.x * kT;
   for (int j = 0; j < pt.nnbr; ++j) {
     const int q = pt.nbr_rank[j];
-    if (threadIdx.x == 0) wait_ge(&me->ready_from[q], k, pt, 0);
+    if (threadIdx.x == 0) wait_ge(&me->ready_from[q], k, pt, blockIdx.x == 0 ? 0 : -1);
     __syncthreads();
     const double* pu = pt.u[q];
     for (int64_t h = recv_ptr[j] + (int64_t)blockIdx.x * kT + threadIdx.x; h < recv_ptr[j + 1]; h += stride)

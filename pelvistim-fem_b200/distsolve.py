@@ -11,16 +11,48 @@ import numpy as np
 from . import engine, partition
 
 
+def _allreduce(arr, op="sum"):
+    """Element-wise reduction of a float64 numpy array over the ranks of the default process group (NCCL: through the
+    GPU; gloo: on the host); every rank gets the same result."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return arr
+    t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64))
+    on_gpu = dist.get_backend() == "nccl"
+    if on_gpu:
+        t = t.cuda()
+    dist.all_reduce(t, op={"sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX}[op])
+    return t.cpu().numpy() if on_gpu else t.numpy()
+
+
 def partitioned_solve(ctx, mesh, sigma_by_body, dirichlet, neumann, rank, world, check=True, transport="p2p", coarse=True,
-                      force_p2p=False, **opts):
+                      force_p2p=False, distributed=False, **opts):
     """Returns dict(x_local, row0, stats, timings, nloc, nhalo, rel_err_vs_single).
 
-    ``coarse``: precondition with Jacobi + geometric coarse grids (taken from this rank's replica of the mesh; the finest
-    grid vector is summed over the ranks once per iteration) when the mesh is large enough for the single-GPU solver to
-    choose them too (>= 100 k nodes); Jacobi otherwise.  ``force_p2p``: use the peer-memory kernels even with one rank
-    (tests)."""
+    ``coarse``: precondition with Jacobi + geometric coarse grids (the finest grid vector is summed over the ranks once per
+    iteration) when the mesh is large enough for the single-GPU solver to choose them too (>= 100 k nodes); Jacobi otherwise.
+    ``force_p2p``: use the peer-memory kernels even with one rank (tests).
+
+    ``distributed=False``: every rank assembles a replica of the whole mesh on its GPU and cuts its row block out of it (the
+    mesh must fit one GPU; with ``check`` the single-GPU solve of the replica is timed beside the partitioned one).
+    ``distributed=True``: no GPU ever holds the whole mesh - each rank uploads its owned nodes and the elements touching
+    them (``partition.local_submesh``), assembles that, and the coarse-grid operators are built from per-rank Galerkin
+    sums added up over the ranks (owner-computes with ghost elements)."""
     import torch.distributed as dist
-    dm = ctx.mesh(mesh.nodes, mesh.tets, mesh.region, mesh.tris, mesh.bcid)
+    lm = None
+    if distributed:
+        check = False
+        lm = partition.local_submesh(mesh, rank, world)
+        dm = ctx.mesh(lm.nodes, lm.tets, lm.region, lm.tris, lm.bcid)
+        nn_global = lm.nn_global
+        # bounding box of the WHOLE mesh (coarse grids are laid over it); also marks the local mesh as a part of a larger one
+        own = lm.nodes[:lm.nloc]
+        bb_lo, bb_hi = _allreduce(own.min(axis=0), "min"), _allreduce(own.max(axis=0), "max")
+        dm.set_bbox(bb_lo, bb_hi)
+    else:
+        dm = ctx.mesh(mesh.nodes, mesh.tets, mesh.region, mesh.tris, mesh.bcid)
+        nn_global = mesh.nn
     dm.assemble(sigma_by_body).bc_reset(1)
     for bid, g in neumann:
         dm.neumann(bid, g)
@@ -40,9 +72,37 @@ def partitioned_solve(ctx, mesh, sigma_by_body, dirichlet, neumann, rank, world,
         setup_ms = dm.last_stats["setup_ms"]
         dm.solve(to_host=False, rtol=opts.get("rtol", 1e-10), precond=engine.PRECOND_AUTO)
         single_auto_stats = dict(dm.last_stats, setup_ms=setup_ms)
-    blk = partition.local_block(rowptr, col, val, b, rank, world)
-    want_coarse = bool(coarse) and mesh.nn >= 100000
+    if distributed:
+        blk = partition.block_from_local(lm, rowptr, col, val, b)
+    else:
+        blk = partition.local_block(rowptr, col, val, b, rank, world)
+    del rowptr, col, val, b
+    want_coarse = bool(coarse) and nn_global >= 100000
     state = dict(coarse=False, note=None)
+    attach_row0 = 0 if distributed else blk.row0
+    if distributed and want_coarse:
+        # coarse-grid operators of the WHOLE matrix from per-rank sums: grids over the global bounding box, Galerkin sums of
+        # the owned rows, one all-reduce of ~1 MB, the same inversion on every rank (every rank takes part in every collective)
+        sums, err = None, None
+        try:
+            sums = dm.coarse_partial(lm.nloc, nn_global)
+        except engine.PtfemError as e:
+            err = str(e)
+        sizes = [None] * world
+        dist.all_gather_object(sizes, None if sums is None else int(sums.size))
+        if all(z is not None for z in sizes) and len(set(sizes)) == 1:
+            sums = _allreduce(sums, "sum")
+            try:
+                dm.coarse_finish(sums)
+            except engine.PtfemError as e:
+                err = str(e)
+        else:
+            err = err or "the ranks disagree on the coarse grids"
+        errs = [None] * world
+        dist.all_gather_object(errs, err)
+        if any(errs):
+            want_coarse = False
+            state["note"] = f"coarse grids not built ({[e for e in errs if e][0]}); Jacobi"
 
     def make_system():
         """This rank's block; with the coarse grids attached when asked for and possible (every rank decides alike: the
@@ -51,7 +111,7 @@ def partitioned_solve(ctx, mesh, sigma_by_body, dirichlet, neumann, rank, world,
         state["coarse"] = False
         if want_coarse:
             try:
-                sysm.coarse_attach(dm, blk.row0)
+                sysm.coarse_attach(dm, attach_row0)
                 state["coarse"] = True
             except engine.PtfemError as e:
                 state["note"] = f"coarse grids not attached ({e}); Jacobi"
@@ -86,7 +146,7 @@ def partitioned_solve(ctx, mesh, sigma_by_body, dirichlet, neumann, rank, world,
         if p2p_error is None:
             if all(h is not None for h in handles):
                 try:
-                    ds.p2p_connect(handles, partition.halo_sources(blk, n=rowptr.shape[0] - 1))
+                    ds.p2p_connect(handles, partition.halo_sources(blk, n=nn_global))
                 except engine.PtfemError as e:
                     p2p_error = str(e)
             else:
@@ -135,6 +195,13 @@ def partitioned_solve(ctx, mesh, sigma_by_body, dirichlet, neumann, rank, world,
                 err = err or f"on another rank: {bad[0]}"
         return err, x, first_ms, wall
 
+    mem_gb = None
+    try:   # device memory in use on this rank with the local mesh, its matrix and the block all resident (peak of the set-up)
+        import torch
+        free_b, total_b = torch.cuda.mem_get_info(ctx.device)
+        mem_gb = (total_b - free_b) / 2 ** 30
+    except Exception:  # noqa: BLE001 - reporting only
+        pass
     err, x, first_ms, wall = timed_solves(ds)
     if err and used == "p2p" and world > 1:
         # a peer stalled past the bounded wait: the peer-memory connection is out of step - start over on the NCCL transport
@@ -152,7 +219,8 @@ def partitioned_solve(ctx, mesh, sigma_by_body, dirichlet, neumann, rank, world,
     if err:
         raise engine.PtfemError(-3, err)
     out = dict(x_local=x, row0=blk.row0, nloc=blk.nloc, nhalo=blk.nhalo, stats=ds.last_stats, timings=ds.timings, wall_s=wall,
-               transport=used, coarse=state["coarse"], coarse_note=state["note"], first_solve_ms=first_ms)
+               transport=used, coarse=state["coarse"], coarse_note=state["note"], first_solve_ms=first_ms, distributed=bool(distributed),
+               device_mem_gb=mem_gb, local_nodes=(lm.nn if lm is not None else mesh.nn), local_tets=(lm.tets.shape[0] if lm is not None else mesh.nt))
     if check:
         ref = phi_single[blk.row0:blk.row0 + blk.nloc]
         out["rel_err_vs_single"] = float(np.abs(x - ref).max() / max(np.abs(phi_single).max(), 1e-300))

@@ -126,6 +126,9 @@ def load_library():
         "ptfem_dist_system_create": (C.c_int, [vp, i64, i64, vp, vp, vp, vp, i32, vp, vp, vp, vp, P(vp)]),
         "ptfem_dist_solve": (C.c_int, [vp, P(SolveOpts), vp, P(SolveStats), P(dbl), P(dbl), P(dbl)]),
         "ptfem_dist_coarse_attach": (C.c_int, [vp, vp, i64]),
+        "ptfem_mesh_set_bbox": (C.c_int, [vp, vp, vp]),
+        "ptfem_dist_coarse_partial": (C.c_int, [vp, i64, i64, i32, i32, P(i64), vp, i64]),
+        "ptfem_dist_coarse_finish": (C.c_int, [vp, vp, i64]),
         "ptfem_dist_coarse_ranges_get": (C.c_int, [vp, vp]),
         "ptfem_dist_coarse_ranges_set": (C.c_int, [vp, i32, vp]),
         "ptfem_dist_p2p_export": (C.c_int, [vp, vp]),
@@ -264,6 +267,25 @@ class DeviceMesh:
         out = np.empty((self.nt, 16), dtype=np.int32)
         self._ck(self.lib.ptfem_e2nnz_get(self._h, _ptr(out)))
         return out
+
+    def set_bbox(self, lo, hi):
+        """Bounding box the coarse grids are laid over (distributed set-up: the WHOLE mesh's box on a rank's local mesh)."""
+        lo, hi = _f64(lo), _f64(hi)
+        self._ck(self.lib.ptfem_mesh_set_bbox(self._h, _ptr(lo), _ptr(hi)))
+
+    def coarse_partial(self, nrows_owned, nn_global, coarse_nodes=0, coarse_levels=-1):
+        """Raw Galerkin sums of the owned rows of this (local) mesh, to be added up over the ranks."""
+        n = C.c_int64()
+        self._ck(self.lib.ptfem_dist_coarse_partial(self._h, int(nrows_owned), int(nn_global), coarse_nodes, coarse_levels,
+                                                    C.byref(n), None, 0))
+        out = np.empty(n.value, dtype=np.float64)
+        self._ck(self.lib.ptfem_dist_coarse_partial(self._h, int(nrows_owned), int(nn_global), coarse_nodes, coarse_levels,
+                                                    C.byref(n), _ptr(out), out.size))
+        return out
+
+    def coarse_finish(self, sums):
+        sums = _f64(sums)
+        self._ck(self.lib.ptfem_dist_coarse_finish(self._h, _ptr(sums), sums.size))
 
     def set_coords(self, nodes):
         nodes = _f64(nodes)

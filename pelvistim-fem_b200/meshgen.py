@@ -589,6 +589,7 @@ SYNTH_SIZES = {
     "S": (32, 24, 16),
     "M": (96, 72, 60),
     "L": (192, 144, 120),
+    "XL": (288, 216, 180),     # 67 M tets, 11.3 M nodes: the row-partitioned solve with a distributed set-up
 }
 
 

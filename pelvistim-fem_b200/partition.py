@@ -68,6 +68,81 @@ def local_block(rowptr, col, val, b, rank, nranks, bounds=None) -> LocalBlock:
                       np.ascontiguousarray(b[r0:r1], dtype=np.float64), halo, nbr, send_ptr, send_idx, recv_ptr)
 
 
+@dataclass
+class LocalMesh:
+    """One rank's part of a mesh for the distributed set-up: the owned nodes (global rows ``[row0, row0 + nloc)``, first),
+    the ghost nodes of the elements that touch them (``halo_global``, ascending global id = grouped by owner) and, last, the
+    remaining nodes of boundary triangles that touch any of those (``extra_global``: they only carry Dirichlet flags for
+    the ghosts and end up as isolated rows).  Every tet with at least one owned node is here, so the owned ROWS of the
+    stiffness matrix assembled on this mesh are complete, with columns already numbered [owned | halo]."""
+    rank: int
+    nranks: int
+    row0: int
+    nloc: int
+    nn_global: int
+    nodes: np.ndarray
+    tets: np.ndarray
+    region: np.ndarray
+    tris: np.ndarray
+    bcid: np.ndarray
+    halo_global: np.ndarray
+    extra_global: np.ndarray
+
+    @property
+    def nn(self):
+        return self.nodes.shape[0]
+
+
+def local_submesh(mesh, rank, nranks, bounds=None) -> LocalMesh:
+    """Owner-computes sub-mesh of ``rank`` (assembly with ghost elements)."""
+    nn = mesh.nodes.shape[0]
+    bounds = row_bounds(nn, nranks) if bounds is None else np.asarray(bounds, dtype=np.int64)
+    r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+    nloc = r1 - r0
+    t = mesh.tets
+    sel = ((t >= r0) & (t < r1)).any(axis=1)
+    lt = t[sel]
+    ghosts = np.unique(lt[(lt < r0) | (lt >= r1)]).astype(np.int64)
+    inloc = np.zeros(nn, dtype=bool)
+    inloc[r0:r1] = True
+    inloc[ghosts] = True
+    tsel = inloc[mesh.tris].any(axis=1) if mesh.tris.shape[0] else np.zeros(0, dtype=bool)
+    ltri = mesh.tris[tsel]
+    extra = np.unique(ltri[~inloc[ltri]]).astype(np.int64) if ltri.size else np.zeros(0, dtype=np.int64)
+    g2l = np.full(nn, -1, dtype=np.int32)
+    g2l[r0:r1] = np.arange(nloc, dtype=np.int32)
+    g2l[ghosts] = nloc + np.arange(ghosts.size, dtype=np.int32)
+    g2l[extra] = nloc + ghosts.size + np.arange(extra.size, dtype=np.int32)
+    nodes = np.ascontiguousarray(np.concatenate([mesh.nodes[r0:r1], mesh.nodes[ghosts], mesh.nodes[extra]], axis=0))
+    return LocalMesh(rank, nranks, r0, nloc, nn, nodes, np.ascontiguousarray(g2l[lt]), np.ascontiguousarray(mesh.region[sel]),
+                     np.ascontiguousarray(g2l[ltri]).reshape(-1, 3), np.ascontiguousarray(mesh.bcid[tsel]), ghosts, extra)
+
+
+def block_from_local(lm: LocalMesh, rowptr, col, val, b, bounds=None) -> LocalBlock:
+    """The rank's block of the row-partitioned system out of the matrix assembled on its :class:`LocalMesh`: rows
+    ``[0, nloc)``, whose columns are already local ([0, nloc) owned, then the halo in ascending global order)."""
+    bounds = row_bounds(lm.nn_global, lm.nranks) if bounds is None else np.asarray(bounds, dtype=np.int64)
+    nloc, nh = lm.nloc, int(lm.halo_global.size)
+    k1 = int(rowptr[nloc])
+    lrowptr = np.ascontiguousarray(rowptr[:nloc + 1], dtype=np.int32)
+    c = col[:k1].astype(np.int64)
+    if c.size and int(c.max()) >= nloc + nh:
+        raise ValueError("an owned row refers to a node outside [owned | halo]: the sub-mesh misses an element")
+    owner = np.searchsorted(bounds, lm.halo_global, side="right") - 1
+    nbr = np.unique(owner).astype(np.int32)
+    recv_ptr = np.concatenate([[0], np.cumsum([(owner == q).sum() for q in nbr])]).astype(np.int32)
+    rows = np.repeat(np.arange(nloc, dtype=np.int64), np.diff(lrowptr))
+    col_owner = np.full(c.shape, lm.rank, dtype=np.int64)
+    ish = c >= nloc
+    col_owner[ish] = owner[c[ish] - nloc]
+    send = [np.unique(rows[col_owner == q]).astype(np.int32) for q in nbr]
+    send_ptr = np.concatenate([[0], np.cumsum([s_.size for s_ in send])]).astype(np.int32)
+    send_idx = np.concatenate(send).astype(np.int32) if send else np.zeros(0, np.int32)
+    return LocalBlock(lm.rank, lm.nranks, lm.row0, nloc, nh, lrowptr, np.ascontiguousarray(col[:k1], dtype=np.int32),
+                      np.ascontiguousarray(val[:k1], dtype=np.float64), np.ascontiguousarray(b[:nloc], dtype=np.float64),
+                      lm.halo_global, nbr, send_ptr, send_idx, recv_ptr)
+
+
 class SerialComm:
     """All ranks in one process (tests): exchange/allreduce over a list of blocks."""
 

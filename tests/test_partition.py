@@ -235,3 +235,46 @@ def test_two_process_gloo_solve_with_coarse_grids():
         assert abs(it - it_serial) <= 2            # same preconditioner, same Krylov space: the partitioned count is the serial one
         assert it * 4 < it_jacobi * 3                # a 36-node coarse grid on 2254 nodes: 101 vs 157 iterations
     assert res[0][1] == res[1][1]
+
+
+def test_local_submesh_gives_complete_owned_rows():
+    # distributed set-up (owner-computes with ghost elements): the matrix assembled on a rank's sub-mesh has
+    # complete owned rows with columns already numbered [owned | halo], and the blocks of all ranks fit together
+    import scipy.sparse as sp
+    from oracle import fem_oracle as fo
+    from pelvistim_fem_b200 import meshgen
+    m = meshgen.synth_slab("XS")
+    sig = {1: 0.35, 2: 0.04, 3: 0.001, 4: 0.005, 5: 0.005}
+    ref = fo.solve_case(m, sig, [(102, 0.0)], [(101, 15.975)], recover=None)
+    K, b = ref["K"].tocsr(), ref["b"]
+
+    def on_pattern(A, nodes, tets):
+        """A's values on the FULL P1 pattern (explicit zeros where the elimination left none): what the device stores."""
+        rp, cc = fo.csr_pattern(nodes.shape[0], tets)
+        rows = np.repeat(np.arange(nodes.shape[0]), np.diff(rp))
+        return rp, cc, np.asarray(A[rows, cc]).ravel()
+
+    grp, gcc, gval = on_pattern(K, m.nodes, m.tets)
+    for world in (2, 3):
+        blocks = []
+        for r in range(world):
+            lm = partition.local_submesh(m, r, world)
+            assert lm.nloc == partition.row_bounds(m.nn, world)[r + 1] - lm.row0 and lm.nn == lm.nloc + lm.halo_global.size + lm.extra_global.size
+            Kl = fo.assemble_stiffness(lm.nodes, lm.tets, lm.region, sig).tocsr()
+            isd, dv = fo.dirichlet_nodes(lm.tris, lm.bcid, [(102, 0.0)], lm.nn)
+            bl = fo.neumann_rhs(lm.nodes, lm.tris, lm.bcid, [(101, 15.975)])
+            Kl, bl = fo.apply_dirichlet_symmetric(Kl, bl, isd, dv)
+            rp, cc, val = on_pattern(Kl.tocsr(), lm.nodes, lm.tets)
+            blk = partition.block_from_local(lm, rp, cc, val, bl)
+            want = partition.local_block(grp, gcc, gval, b, r, world)
+            assert np.array_equal(blk.rowptr, want.rowptr) and np.array_equal(blk.halo_global, want.halo_global)
+            # same rows (the sub-mesh numbers its halo after the owned nodes, so the order of the columns inside a row differs)
+            A1 = sp.csr_matrix((blk.val, blk.col, blk.rowptr), shape=(blk.nloc, blk.nloc + blk.nhalo))
+            A2 = sp.csr_matrix((want.val, want.col, want.rowptr), shape=(blk.nloc, blk.nloc + blk.nhalo))
+            assert abs(A1 - A2).max() < 1e-15 * np.abs(want.val).max() and np.abs(blk.b - want.b).max() < 1e-18
+            P1 = sp.csr_matrix((np.ones(blk.col.size), blk.col, blk.rowptr), shape=A1.shape)
+            P2 = sp.csr_matrix((np.ones(want.col.size), want.col, want.rowptr), shape=A1.shape)
+            assert (P1 != P2).nnz == 0                                  # identical pattern, explicit zeros included
+            assert np.array_equal(blk.nbr_rank, want.nbr_rank) and np.array_equal(blk.send_idx, want.send_idx) and np.array_equal(blk.recv_ptr, want.recv_ptr)
+            blocks.append(blk)
+        assert partition.check_consistency(blocks)
