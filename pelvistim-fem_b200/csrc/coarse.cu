@@ -1463,9 +1463,10 @@ __global__ void __launch_bounds__(256) coarse_node_range_kernel(CoarseGrid g, in
 }
 // rc1[J] for level-1 nodes J in [J0, J1): 27-point restriction of rf, fine nodes outside [f0, f1) counting as zero
 __global__ void __launch_bounds__(256) grid_restrict_range_kernel(CoarseGrid gc, int64_t J0, int64_t J1, int64_t f0, int64_t f1,
-                                                                  const double* __restrict__ rf, double* __restrict__ rc) {
+                                                                  const double* __restrict__ rf, double* __restrict__ rc,
+                                                                  CoarseSignal sig) {
   const int64_t I = J0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (I >= J1) return;
+  if (I < J1) {
   double v = 0.0;
   const int nx1 = gc.n[0] + 1, ny1 = gc.n[1] + 1;
   const int ix = (int)(I % nx1), iy = (int)((I / nx1) % ny1), iz = (int)(I / ((int64_t)nx1 * ny1));
@@ -1487,6 +1488,20 @@ __global__ void __launch_bounds__(256) grid_restrict_range_kernel(CoarseGrid gc,
     }
   }
   rc[I] = v;
+  }
+  if (sig.n <= 0 && !sig.seq) return;
+  // last CTA: both parts of the exchange buffer are complete -> tell every other rank (release at system scope)
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicInc(sig.ticket, gridDim.x - 1) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned long long seq = *sig.seq + 1;
+    *sig.seq = seq;
+    for (int q = 0; q < sig.n; ++q) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(sig.peer_flag[q]), "l"(seq) : "memory");
+  }
 }
 // yt_f[F] = y_f[F] + (P yt_c)[F] for fine nodes F in [F0, F1)
 __global__ void __launch_bounds__(256) grid_prolong_range_kernel(CoarseGrid gc, int64_t F0, int64_t F1, const double* __restrict__ yf,
@@ -1538,7 +1553,7 @@ int coarse_touched_ranges(ptfem_ctx* ctx, CoarseSpace& cs, int64_t nn, int64_t r
 
 // restriction of the owned rows on their ranges: out0[a0..b0) (level 0) and out1[a1..b1) (level 1), see above
 int coarse_restrict_rows_sharded(ptfem_ctx* ctx, CoarseSpace& cs, const double* r, const int64_t ranges[4], double* out0,
-                                 double* out1) {
+                                 double* out1, const CoarseSignal& sig) {
   CoarseLevel& L0 = cs.lev[0];
   const int64_t ntask = L0.ncell * L0.split;
   const int grid = (int)std::min<int64_t>((ntask + 7) / 8, (int64_t)ctx->sm_count * 32);
@@ -1550,19 +1565,21 @@ int coarse_restrict_rows_sharded(ptfem_ctx* ctx, CoarseSpace& cs, const double* 
                                                                                            L0.part.p, out0);
     PT_LAUNCH_CHECK(ctx);
   }
-  if (ranges[3] > ranges[2]) {
-    grid_restrict_range_kernel<<<ceil_div(ranges[3] - ranges[2], 256), 256, 0, ctx->stream>>>(cs.lev[1].g, ranges[2], ranges[3],
-                                                                                             ranges[0], ranges[1], out0, out1);
-    PT_LAUNCH_CHECK(ctx);
-  }
+  // (launched even for an empty range: its last CTA raises the "buffer complete" signal)
+  const int64_t n1 = ranges[3] > ranges[2] ? ranges[3] - ranges[2] : 0;
+  grid_restrict_range_kernel<<<std::max(1, ceil_div(n1, 256)), 256, 0, ctx->stream>>>(cs.lev[1].g, ranges[2], ranges[2] + n1, ranges[0],
+                                                                                      ranges[1], out0, out1, sig);
+  PT_LAUNCH_CHECK(ctx);
   return PTFEM_OK;
 }
 
-// The grid hierarchy above level `start` as ONE block of 1024 threads (row-partitioned solve, one right-hand side): with the
-// finest level sharded over the ranks, what is left replicated are a few thousand grid nodes - five dependent kernels of
-// ~6 us launch-to-launch each did a few microseconds of work.  Phases are separated by block barriers.
+// The grid levels above `start` (a few thousand nodes in all) as ONE block of 1024 threads (row-partitioned solve, one
+// right-hand side): restrictions up from level `start`, the dense coarsest solve, prolongations back down to level `down_to`;
+// phases separated by block barriers.  Four dependent kernels of ~6 us launch-to-launch each did a few microseconds of
+// work here.  Level `start` itself (18 k nodes on the 20 M-tet slab) is prolonged by the ordinary multi-CTA kernel: one block
+// for it as well was measured slower (0.34 vs 0.27 ms per iteration on 2 GPUs).
 namespace {
-__global__ void __launch_bounds__(1024) coarse_chain_tail_kernel(ChainArgs a, int start) {
+__global__ void __launch_bounds__(1024) coarse_chain_tail_kernel(ChainArgs a, int start, int down_to) {
   const int tid = threadIdx.x, nth = blockDim.x;
   for (int l = start + 1; l < a.nlev; ++l) {
     const ChainLevel& L = a.lev[l];
@@ -1585,7 +1602,7 @@ __global__ void __launch_bounds__(1024) coarse_chain_tail_kernel(ChainArgs a, in
     }
     __syncthreads();
   }
-  for (int l = a.nlev - 2; l >= start; --l) {
+  for (int l = a.nlev - 2; l >= down_to; --l) {
     const ChainLevel& L = a.lev[l];
     const double* ytc = (l + 1 == a.nlev - 1) ? a.lev[l + 1].yc : a.lev[l + 1].yt;
     for (int64_t F = tid; F < L.k; F += nth) L.yt[F] = chain_prolong8<1>(a.lev[l + 1].g, ytc, L.yc[F], F, 0);
@@ -1598,7 +1615,7 @@ __global__ void __launch_bounds__(1024) coarse_chain_tail_kernel(ChainArgs a, in
 // the replicated grid hierarchy from that level up and back down to it (yt of level `start`, or yc when it is the last level)
 int coarse_grids_apply(ptfem_ctx* ctx, CoarseSpace& cs, bool scaled0, int start) {
   if (cs.chain_grid > 0 && start == 0) return chain_launch<1>(ctx, cs, false, scaled0);
-  if (start >= 1 && (scaled0 || cs.lev[start].exact) && cs.lev[start].k <= 65536 && ctx->tune_chain_tail) {
+  if (start >= 1 && start + 1 < cs.nlev && scaled0 && cs.lev[start + 1].k <= 8192 && ctx->tune_chain_tail) {
     ChainArgs a;
     a.nlev = cs.nlev;
     a.split = 1;
@@ -1618,7 +1635,11 @@ int coarse_grids_apply(ptfem_ctx* ctx, CoarseSpace& cs, bool scaled0, int start)
     a.part = nullptr;
     a.dpart = nullptr;
     a.cdot = nullptr;
-    coarse_chain_tail_kernel<<<1, 1024, 0, ctx->stream>>>(a, start);
+    coarse_chain_tail_kernel<<<1, 1024, 0, ctx->stream>>>(a, start, start + 1);
+    PT_LAUNCH_CHECK(ctx);
+    CoarseLevel& L = cs.lev[start];
+    const double* ytc = (start + 1 == cs.nlev - 1) ? cs.lev[start + 1].yc.p : cs.lev[start + 1].yt.p;
+    grid_prolong_kernel<1><<<ceil_div(L.k, 256), 256, 0, ctx->stream>>>(cs.lev[start + 1].g, L.k, L.yc.p, ytc, L.yt.p);
     PT_LAUNCH_CHECK(ctx);
     return PTFEM_OK;
   }

@@ -169,6 +169,15 @@ __device__ __forceinline__ void coarse_prolong(const CoarseDev& cd, const Coarse
   for (int k = 0; k < NS; ++k) out[k] = acc[k] * live;
 }
 
+// "this rank's exchange buffer is complete" signal of the sharded coarse exchange, raised by the last CTA of the kernel that
+// completes the buffer (dist.cu fills it in; n == 0: no signal)
+struct CoarseSignal {
+  unsigned long long* seq = nullptr;          // local sequence counter (Mail::xred), bumped by one
+  unsigned long long* peer_flag[16] = {};     // xready_from[this rank] in every other rank's mailbox
+  int n = 0;
+  unsigned int* ticket = nullptr;
+};
+
 namespace ptfem {
 // (re)builds what is stale: grids + sorted row lists (mesh coordinates / requested size changed) and the Galerkin
 // operators (matrix changed).  target_nodes: unknowns of the exact level (0 = default); extra_levels: finer
@@ -190,6 +199,7 @@ int coarse_restrict_rows(ptfem_ctx* ctx, CoarseSpace& cs, const double* r, doubl
 int coarse_grids_apply(ptfem_ctx* ctx, CoarseSpace& cs, bool scaled0, int start = 0);
 // sharded form of the two above (peer-memory transport): see coarse.cu
 int coarse_touched_ranges(ptfem_ctx* ctx, CoarseSpace& cs, int64_t nn, int64_t ranges[4]);
-int coarse_restrict_rows_sharded(ptfem_ctx* ctx, CoarseSpace& cs, const double* r, const int64_t ranges[4], double* out0, double* out1);
+int coarse_restrict_rows_sharded(ptfem_ctx* ctx, CoarseSpace& cs, const double* r, const int64_t ranges[4], double* out0, double* out1,
+                                 const CoarseSignal& sig);
 int coarse_prolong_finest_range(ptfem_ctx* ctx, CoarseSpace& cs, int64_t a0, int64_t b0);
 }  // namespace ptfem

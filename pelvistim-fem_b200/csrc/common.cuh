@@ -111,7 +111,7 @@ struct ptfem_ctx {
   int tune_restrict_occ = 4;       // PTFEM_RESTRICT_OCC: resident CTAs per SM the restriction kernel is compiled for (2, 4, 6; 4 measured best in round 1)
   int tune_coarse_fused = 0;       // PTFEM_COARSE_FUSED: grid hierarchy of the coarse-grid preconditioner as one cooperative kernel
   double tune_coarse_weight = 0.0; // PTFEM_COARSE_WEIGHT: weight of the coarse-grid levels against the Jacobi term (0 = 2 / (levels + 1))
-  int tune_chain_tail = 1;         // PTFEM_CHAIN_TAIL: partitioned solve runs the replicated small grid levels as one block (0: separate kernels)
+  int tune_chain_tail = 0;         // PTFEM_CHAIN_TAIL: partitioned solve runs the replicated smallest grid levels as one block (measured slower: off)
   int tune_pupdate_occ = 4;        // PTFEM_PUPDATE_OCC: resident CTAs per SM the one-pair p-update is compiled for (4, 5, 6)
   int tune_pupdate_np = 1;         // PTFEM_PUPDATE_NP: pairs per trip of the coarse-grid p-update (1: 4 CTAs/SM, 2: 2 CTAs/SM, all loads of both first)
   int tune_ctas_per_sm = 0;        // cap on resident CTAs per SM of the streaming SpMV (PTFEM_CTAS_PER_SM)

@@ -654,7 +654,7 @@ int dist_grid(ptfem_ctx* ctx, int64_t n) {
 
 struct DistState {
   DevBuf<double> x, r, u, w, p, s, scal, partial;
-  DevBuf<unsigned int> ticket;
+  DevBuf<unsigned int> ticket, ticket2;
   DevBuf<int32_t> recv_dummy;
   cudaEvent_t ev_u = nullptr, ev_halo = nullptr;
   cudaGraphExec_t graph = nullptr;
@@ -767,9 +767,13 @@ static int dist_coarse_add(ptfem_mesh* m, DistState& d) {
   if (d.p2p && d.sharded) {
     const int par = (int)((d.xseq + 1) & 1);
     double* mine = d.xch + (size_t)par * d.xstride;
-    PT_TRY(coarse_restrict_rows_sharded(ctx, cs, d.r.p, d.ranges, mine, mine + L0.k));
-    p2p_coarse_signal_kernel<<<1, 32, 0, ctx->stream>>>(d.pt);
-    PT_LAUNCH_CHECK(ctx);
+    // the last CTA of the restriction to level 1 raises "buffer complete" in every other rank's mailbox (no separate launch)
+    CoarseSignal sig;
+    sig.seq = &d.mail.p->xred;
+    sig.ticket = d.ticket2.p;
+    for (int q = 0; q < d.pt.nranks; ++q)
+      if (q != d.pt.rank) sig.peer_flag[sig.n++] = &d.pt.mail[q]->xready_from[d.pt.rank];
+    PT_TRY(coarse_restrict_rows_sharded(ctx, cs, d.r.p, d.ranges, mine, mine + L0.k, sig));
     d.xseq++;
     CoarseLevel& L1 = cs.lev[1];
     const int g = std::min(ceil_div(d.ranges[1] - d.ranges[0] + L1.k, kT), 2 * ctx->sm_count);
@@ -986,6 +990,8 @@ int ptfem_dist_system_create(ptfem_ctx* ctx, int64_t nloc, int64_t nhalo, const 
     PT_TRY(d.partial.alloc((size_t)ctx->sm_count * 4 * 3));
     PT_TRY(d.ticket.alloc(1));
     PT_CK(cudaMemsetAsync(d.ticket.p, 0, sizeof(unsigned int), ctx->stream));
+    PT_TRY(d.ticket2.alloc(1));
+    PT_CK(cudaMemsetAsync(d.ticket2.p, 0, sizeof(unsigned int), ctx->stream));
     PT_CK(cudaMemsetAsync(d.u.p, 0, nv * sizeof(double), ctx->stream));
     PT_CK(cudaMemsetAsync(d.scal.p, 0, D_COUNT * sizeof(double), ctx->stream));
     PT_CK(cudaEventCreateWithFlags(&d.ev_u, cudaEventDisableTiming));
