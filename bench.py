@@ -64,8 +64,10 @@ def run_sweep_step(dm, mesh, confs, step, phi_out=None, J_out=None, sample_spmv=
     for k, c in enumerate(confs):
         dm.neumann_tris(c["tris"], I_INJECT / c["area"], rhs=k)
     dm.dirichlet(102, 0.0)
-    phi = dm.solve(to_host=phi_out is not None, out=phi_out, rtol=RTOL, sample_spmv=sample_spmv, spmv_variant=0, precond=PRECOND)
+    phi = dm.solve(to_host=False, rtol=RTOL, sample_spmv=sample_spmv, spmv_variant=0, precond=PRECOND)
     stats = dm.last_stats
+    if phi_out is not None:     # read-back on the side stream, overlapping the recovery / metrics below (valid after a sync)
+        phi = dm.get_phi_all_async(phi_out)
     Lz, t_skin = mesh.meta["Lz"], mesh.meta["t_skin"]
     # nodal currents of all configurations in two launches (read-back, if asked for, on the side stream), then all the
     # metric reductions of the sweep in one batch: one pass over the mesh per kind, one device->host read-back
@@ -507,18 +509,36 @@ def main():
         h2d = sum(a.nbytes for a in h.values()) + sum(c["tris"].nbytes for c in confs)
         d2h = phi_out.nbytes + J_out.nbytes
 
+        # double-buffered outputs: the device->host copies of step k (side stream) overlap the upload and pattern build of
+        # step k+1; the mesh of step k is released (which waits for its copies) once step k+1's pattern is built
+        outs = [(phi_out, J_out), (torch.empty((args.nconf, mesh.nn), dtype=torch.float64).pin_memory().numpy(),
+                                   torch.empty((args.nconf, mesh.nn, 3), dtype=torch.float64).pin_memory().numpy())]
+        state = {"prev": None}
+
         def e2e_step(s):
             d = ctx.mesh(h["nodes"], h["tets"], h["region"], h["tris"], h["bcid"])
-            r, _, _ = run_sweep_step(d, mesh, confs, s, phi_out=phi_out, J_out=J_out)
-            d.close()
+            d.pattern()
+            if state["prev"] is not None:
+                state["prev"].close()
+            po, jo = outs[s % 2]
+            r, _, _ = run_sweep_step(d, mesh, confs, s, phi_out=po, J_out=jo)
+            state["prev"] = d
             return r
-        e2e_step(0)
+
+        def e2e_drain():
+            if state["prev"] is not None:
+                state["prev"].close()       # waits for the last step's copies
+                state["prev"] = None
+        for s in range(3):          # untimed: the allocator's cache ends up holding the blocks of two meshes (two are alive at a time)
+            e2e_step(s)
+        e2e_drain()
         ctx.sync(); torch.cuda.synchronize(); barrier()
-        n_e2e = max(1, min(args.steps, 3))
+        n_e2e = max(1, min(args.steps, 5))
         ev0.record(stream)
         for s in range(n_e2e):
             l2_flush()
             e2e_step(100 + s)
+        e2e_drain()
         ev1.record(stream)
         ctx.sync(); torch.cuda.synchronize()
         t_e2e = ev0.elapsed_time(ev1) * 1e-3

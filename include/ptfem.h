@@ -141,6 +141,9 @@ int ptfem_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* phi, ptfem_
 int ptfem_solve_device(ptfem_mesh* m, const ptfem_solve_opts* opts, ptfem_solve_stats* stats);
 int ptfem_phi_get(ptfem_mesh* m, int32_t sys, double* phi /*[nn]*/);
 int ptfem_phi_set(ptfem_mesh* m, int32_t sys, const double* phi /*[nn]*/);
+/* every system's potential, [nsys][nn], copied on the side stream and NOT waited for: phi (pinned host memory) is valid after
+ * the next ptfem_ctx_sync (or ptfem_mesh_destroy); the copy overlaps the post-processing the caller enqueues next */
+int ptfem_phi_get_all_async(ptfem_mesh* m, double* phi /*[nsys*nn], pinned*/);
 
 /* y = A x with the assembled matrix of system sys (with_bc selects the eliminated matrix) */
 int ptfem_spmv(ptfem_mesh* m, int32_t sys, int32_t with_bc, int32_t variant, const double* x, double* y);

@@ -191,6 +191,7 @@ int ptfem_ctx_create(int device, ptfem_ctx** out) {
   PT_CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
   PT_CK(cudaEventCreateWithFlags(&c->ev_j_ready, cudaEventDisableTiming));
   PT_CK(cudaEventCreateWithFlags(&c->ev_j_copied, cudaEventDisableTiming));
+  PT_CK(cudaEventCreateWithFlags(&c->ev_phi_ready, cudaEventDisableTiming));
   if (const char* e = getenv("PTFEM_INTERLEAVE")) c->tune_interleave = atoi(e) != 0;
   if (const char* e = getenv("PTFEM_MORTON")) c->tune_morton = atoi(e);
   if (const char* e = getenv("PTFEM_P2P_FUSED")) c->tune_p2p_fused = atoi(e) != 0;
@@ -222,6 +223,7 @@ int ptfem_ctx_destroy(ptfem_ctx* ctx) {
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->ev_j_ready) cudaEventDestroy(ctx->ev_j_ready);
   if (ctx->ev_j_copied) cudaEventDestroy(ctx->ev_j_copied);
+  if (ctx->ev_phi_ready) cudaEventDestroy(ctx->ev_phi_ready);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   delete ctx;
@@ -544,6 +546,25 @@ int ptfem_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* phi, ptfem_
   PT_CK(cudaStreamSynchronize(ctx->stream));
   g_err = keep;
   return rc;
+}
+
+int ptfem_phi_get_all_async(ptfem_mesh* m, double* phi) {
+  PT_ARG(m && phi, "null pointer");
+  if (!m->phi.p || m->S < 1) return set_err(PTFEM_ERR_STATE, "no solution on the device");
+  ptfem_ctx* ctx = m->ctx;
+  PT_CK(cudaSetDevice(ctx->device));
+  const double* src = m->phi.p;
+  if (m->S != 1) {   // [nn][S] -> [nsys][nn] on the device, then one copy
+    PT_TRY(m->scratch_phi.alloc((size_t)m->nn * m->nsys_user));
+    transpose_out_kernel<<<ceil_div(m->nn, 256), 256, 0, ctx->stream>>>(m->phi.p, m->nn, m->S, m->nsys_user, m->scratch_phi.p);
+    PT_LAUNCH_CHECK(ctx);
+    src = m->scratch_phi.p;
+  }
+  // read-back on the side stream: it overlaps whatever the caller enqueues next (current recovery, metrics, the next mesh)
+  PT_CK(cudaEventRecord(ctx->ev_phi_ready, ctx->stream));
+  PT_CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_phi_ready, 0));
+  PT_CK(cudaMemcpyAsync(phi, src, (size_t)m->nn * m->nsys_user * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream2));
+  return PTFEM_OK;
 }
 
 int ptfem_phi_get(ptfem_mesh* m, int32_t sys, double* phi) {

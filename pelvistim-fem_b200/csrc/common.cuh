@@ -97,6 +97,7 @@ struct ptfem_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // copies / halo
   int64_t launches = 0;
+  cudaEvent_t ev_phi_ready = nullptr;
   cudaEvent_t ev_j_ready = nullptr, ev_j_copied = nullptr;  // asynchronous read-back of the nodal current (stream2)
   double* h_pinned = nullptr;  // small pinned scratch (scalars)
   size_t h_pinned_n = 0;
@@ -217,6 +218,7 @@ struct ptfem_mesh {
   ptfem::DevBuf<double> phis_all; // [nroi][nn] smoothed potentials of a metric batch
   bool j_copy_pending = false;    // an asynchronous device->host copy of Jnode may still be reading it
   int mass_iters = 0;
+  ptfem::DevBuf<double> scratch_phi;  // [nsys][nn] staging of ptfem_phi_get_all_async (scratch_d is reused by the metric kernels)
   ptfem::DevBuf<double> scratch_d;
   ptfem::DevBuf<int32_t> scratch_i;
   PcgWork work;

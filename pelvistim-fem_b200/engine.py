@@ -105,6 +105,7 @@ def load_library():
         "ptfem_solve_device": (C.c_int, [vp, P(SolveOpts), P(SolveStats)]),
         "ptfem_phi_get": (C.c_int, [vp, i32, vp]),
         "ptfem_phi_set": (C.c_int, [vp, i32, vp]),
+        "ptfem_phi_get_all_async": (C.c_int, [vp, vp]),
         "ptfem_spmv": (C.c_int, [vp, i32, i32, i32, vp, vp]),
         "ptfem_spmv_bench": (C.c_int, [vp, i32, i32, P(dbl)]),
         "ptfem_element_fields": (C.c_int, [vp, i32, vp, vp]),
@@ -374,6 +375,13 @@ class DeviceMesh:
     def get_phi(self, sys=0):
         out = np.empty(self.nn, dtype=np.float64)
         self._ck(self.lib.ptfem_phi_get(self._h, sys, _ptr(out)))
+        return out
+
+    def get_phi_all_async(self, out):
+        """All potentials [nsys, nn] into ``out`` (pinned) on the side stream; valid after ``Context.sync()`` / ``close()``."""
+        if out.shape != (self.nsys, self.nn) or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 array of shape [nsys, nn]")
+        self._ck(self.lib.ptfem_phi_get_all_async(self._h, _ptr(out)))
         return out
 
     def set_phi(self, phi, sys=0):

@@ -26,15 +26,13 @@ for rep in range(3):
         d.neumann_tris(c["tris"], bench.I_INJECT / c["area"], rhs=k)
     d.dirichlet(102, 0.0); t = tic("bc", t)
     d.solve(to_host=True, out=phi_out, rtol=bench.RTOL); t = tic("solve+d2h_phi", t)
-    T["recover+d2h_J x8"] = 0.0; T["metrics x8"] = 0.0
+    d.recover_current_batch(bench.RECOVER, to_host=True, out=J_out, wait=False); t = tic("recover_batch+d2h_J", t)
+    reqs = []
     for k, c in enumerate(confs):
-        t = time.perf_counter()
-        d.recover_current(k, bench.RECOVER, to_host=True, out=J_out[k]); ctx.sync()
-        T["recover+d2h_J x8"] += time.perf_counter() - t; t = time.perf_counter()
         fp = (c["center"][0], c["center"][1], c["r"], False)
-        d.metric_nodes(0, 0.0397, sys=k); d.metric_nodes(1, 0.04 - 1e-5, mode=1, footprints=[fp], sys=k)
-        d.metric_roi([c["center"][0], c["center"][1], 0.03], 0.005, (1.0, 1.5, 2.0, 3.0), include_tris=False, sys=k)
-        ctx.sync(); T["metrics x8"] += time.perf_counter() - t
+        reqs += [dict(kind="nodes", sys=k, field=0, zmin=0.0397), dict(kind="nodes", sys=k, field=1, zmin=0.04 - 1e-5, mode=1, footprints=[fp]),
+                 dict(kind="roi", sys=k, cen=[c["center"][0], c["center"][1], 0.03], r0=0.005, include_tris=False)]
+    d.metrics_batch(reqs); t = tic("metrics_batch", t)
     t = time.perf_counter()
     d.close(); t = tic("close", t)
     print({k: round(v, 4) for k, v in T.items()}, "iters", d.last_stats["iterations"], "solve_ms", round(d.last_stats["solve_ms"], 1), flush=True)

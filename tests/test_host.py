@@ -271,3 +271,55 @@ def test_driver_params_carry_the_reference_values(golden, step, fixture):
     import yaml
     ours = yaml.safe_load((pathlib.Path(__file__).resolve().parents[1] / "drivers" / step / "params.yaml").read_text())
     assert ours == yaml.safe_load((golden / fixture).read_text())
+
+
+def test_vtu_bytes_follow_the_vtk_xml_appended_raw_layout(tmp_path):
+    # An independent, byte-level reading of the file along the VTK XML file-format rules (VTK File Formats, "XML File Formats":
+    # UnstructuredGrid piece; DataArray format="appended" offset=N counts bytes after the '_' that opens <AppendedData
+    # encoding="raw">; every block = one header_type (UInt64, little endian) byte count followed by that many raw bytes) - not
+    # through vtu.read_vtu.  It is what vtkXMLUnstructuredGridReader does with results/case_t0001.vtu
+    # (consumers: step03_ankle_layers/plot_layered_results.py:88-93, smoke_test.py:88-123).
+    import re
+    import struct
+    import xml.etree.ElementTree as ET
+    from pelvistim_fem_b200 import meshgen, vtu
+    m = meshgen.box_mesh(nx=3, ny=2, nz=2)
+    phi = np.linspace(0.0, 1.0, m.nn)
+    J = np.stack([phi, 2 * phi, -phi], axis=1)
+    gid = np.concatenate([m.region, m.bcid]).astype(np.int32)
+    f = tmp_path / "case_t0001.vtu"
+    vtu.write_vtu(f, m.nodes, m.tets, m.tris, {"potential": phi, "volume current": J}, {"GeometryIds": gid})
+    raw = f.read_bytes()
+    cut = raw.index(b'<AppendedData encoding="raw">')
+    us = raw.index(b"_", cut) + 1                                   # first byte of the appended data
+    tail = raw.rindex(b"</AppendedData>")
+    root = ET.fromstring(raw[:cut] + b"</VTKFile>")                 # the XML part alone is well formed
+    assert root.tag == "VTKFile" and root.attrib["type"] == "UnstructuredGrid" and root.attrib["byte_order"] == "LittleEndian"
+    assert root.attrib["header_type"] == "UInt64"
+    piece = root.find("UnstructuredGrid/Piece")
+    npts, ncells = int(piece.attrib["NumberOfPoints"]), int(piece.attrib["NumberOfCells"])
+    assert npts == m.nn and ncells == m.nt + m.nb
+    size = {"Float64": 8, "Float32": 4, "Int32": 4, "Int64": 8, "UInt8": 1}
+    np_t = {"Float64": "<f8", "Float32": "<f4", "Int32": "<i4", "Int64": "<i8", "UInt8": "u1"}
+    arrays, end = {}, 0
+    for sec, ntup in (("PointData", npts), ("CellData", ncells), ("Points", npts), ("Cells", None)):
+        for da in piece.find(sec).findall("DataArray"):
+            assert da.attrib["format"] == "appended"
+            off, t, nc = int(da.attrib["offset"]), da.attrib["type"], int(da.attrib.get("NumberOfComponents", "1"))
+            assert off == end, "blocks are laid out back to back in document order"
+            (nbytes,) = struct.unpack_from("<Q", raw, us + off)
+            if ntup is not None:
+                assert nbytes == ntup * nc * size[t], (sec, da.attrib.get("Name"))
+            a = np.frombuffer(raw, dtype=np_t[t], count=nbytes // size[t], offset=us + off + 8)
+            arrays[(sec, da.attrib.get("Name"))] = a.reshape(-1, nc) if nc > 1 else a
+            end = off + 8 + nbytes
+    assert us + end <= tail and raw[us + end:tail].strip() == b""    # nothing but white space after the last block
+    assert piece.find("Points/DataArray").attrib["NumberOfComponents"] == "3"
+    conn, offs, types = arrays[("Cells", "connectivity")], arrays[("Cells", "offsets")], arrays[("Cells", "types")]
+    assert types.dtype == np.uint8 and offs.shape[0] == types.shape[0] == ncells
+    assert np.all(np.diff(np.concatenate([[0], offs])) == np.where(types == 10, 4, 3)) and offs[-1] == conn.shape[0]
+    assert np.all(types[:m.nt] == 10) and np.all(types[m.nt:] == 5)            # tets first, then the boundary triangles
+    assert conn.min() >= 0 and conn.max() < npts
+    assert np.array_equal(arrays[("Points", None)], m.nodes) and np.array_equal(arrays[("PointData", "potential")], phi)
+    assert np.array_equal(arrays[("PointData", "volume current")], J) and np.array_equal(arrays[("CellData", "GeometryIds")], gid)
+    assert np.array_equal(conn[:4 * m.nt].reshape(-1, 4), m.tets) and np.array_equal(conn[4 * m.nt:].reshape(-1, 3), m.tris)
