@@ -60,20 +60,24 @@ def build_mesh(p, t_fat, elec_r, run_dir, coarse=False):
     lc_elec = mm.get("lc_electrode_mm", elec_r * 300) * 1e-3 * scale
     lc_bulk = mm.get("lc_global_mm", 3.0) * 1e-3 * scale
     t_muscle = Lz - ls["t_skin"] - t_fat
+    bn = p.get("bone", {})
+    bone = None
+    if bn.get("enabled", False):   # optional bone block inside the muscle (params.yaml `bone:`; not in the reference's model)
+        bone = dict(x=[v * 1e-3 for v in bn["x_mm"]], y=[v * 1e-3 for v in bn["y_mm"]], z=[v * 1e-3 for v in bn["z_mm"]])
     n_m = max(3, int(round(t_muscle / lc_bulk)))
     n_f = max(2, int(round(t_fat / lc_elec)))
     mesh = meshgen.layered_slab_mesh(Lx, Ly, Lz, ls["t_skin"], t_fat, t_contact or 0.0005, active_xy, return_xy, elec_r,
                                      shape, n_muscle=n_m, n_fat=n_f, n_skin=2, n_contact=1, h_bulk=lc_bulk,
-                                     h_elec=lc_elec, contact_enabled=contact, snap_rim=True)
+                                     h_elec=lc_elec, contact_enabled=contact, snap_rim=True, bone=bone)
     # same per-case files as the reference: mesh.msh (gmsh.write, :342-343) then the ElmerGrid 14 2 conversion (:1077)
-    names = {(3, 1): "muscle", (3, 2): "fat", (3, 3): "skin", (3, 4): "contact_active", (3, 5): "contact_return",
+    names = {(3, 1): "muscle", (3, 2): "fat", (3, 3): "skin", (3, 4): "contact_active", (3, 5): "contact_return", (3, 6): "bone",
              (2, 101): "active", (2, 102): "return", (2, 103): "other"}
     gmsh_io.write_msh(run_dir / "mesh.msh", mesh, names)
     elmer_io.write_elmer_mesh(run_dir / "elmer_mesh", mesh)
     z_top = Lz + t_contact
     body_info = dict(contact_enabled=contact, z_skin_top=Lz, z_elec_top=z_top, z_e1_skin=Lz, z_e2_skin=Lz,
                      z_e1_elec_top=z_top, z_e2_elec_top=z_top, c1_body_id=4 if contact else None,
-                     c2_body_id=5 if contact else None, elec_shape=shape)
+                     c2_body_id=5 if contact else None, elec_shape=shape, bone=mesh.meta.get("bone"))
     e1 = np.array([float(active_xy[0]), float(active_xy[1]), z_top])
     e2 = np.array([float(return_xy[0]), float(return_xy[1]), z_top])
     return mesh, e1, e2, body_info
@@ -90,7 +94,7 @@ def write_sif(run_dir, e1_id, e2_id, p, elec_r, body_info, sigma_skin_override=N
         c2_body=body_info.get("c2_body_id") or 5, mode=st.get("control_mode", "voltage"),
         injected_current_mA=st.get("injected_current_mA", 5.0), elec_r=elec_r, shape=body_info.get("elec_shape", "circle"),
         elec_area_mesh=elec_area_mesh, tol=sv.get("tolerance", 1e-8), lin_solver=sv.get("linear_solver", "UMFPACK"),
-        dialect=dialect)
+        dialect=dialect, sigma_bone=(c.get("sigma_bone", 0.02) if body_info.get("bone") else None))
     if warning:
         print(f"    WARNING: {warning}")
     (Path(run_dir) / "case.sif").write_text(sif.serialize(secs))
@@ -138,16 +142,41 @@ def case_label(t_fat, elec_r):
     return f"tfat{int(t_fat*1000):04d}um_r{int(elec_r*1000):04d}um"
 
 
-def run_case(p, t_fat, elec_r, coarse=False, sigma_skin_override=None, ctx=None, results_dir=None, quiet=False):
-    """One sweep point, end to end (the loop body of ``run_layered_sweep.py:1061-1124``)."""
+def displace_fat_thickness(mesh, p, t_fat_ref, t_fat):
+    """The mesh built for fat thickness ``t_fat_ref`` with its nodes moved so that the fat layer is ``t_fat`` thick - same
+    topology, piecewise-linear map of z: the muscle block is stretched, the fat layer squeezed, skin and pads stay put.
+    (The reference re-meshes every point, ``run_layered_sweep.py:1061-1062``; on fixed topology the CSR pattern, the
+    element -> non-zero map and the device mesh are built once per electrode size.)"""
+    Lz, t_skin = p["geometry"]["Lz"], p["layers"]["t_skin"]
+    z_fs = Lz - t_skin
+    z_ref, z_new = z_fs - t_fat_ref, z_fs - t_fat
+    if z_new <= 1e-4:
+        raise ValueError(f"t_muscle = {z_new*1000:.2f} mm <= 0.1 mm - reduce t_fat + t_skin or increase Lz")
+    nodes = mesh.nodes.copy()
+    z = nodes[:, 2]
+    nodes[:, 2] = np.where(z <= z_ref, z * (z_new / z_ref), np.where(z <= z_fs, z_new + (z - z_ref) * (t_fat / t_fat_ref), z))
+    return type(mesh)(nodes, mesh.tets, mesh.region, mesh.tris, mesh.bcid)
+
+
+def run_case(p, t_fat, elec_r, coarse=False, sigma_skin_override=None, ctx=None, results_dir=None, quiet=False, prebuilt=None,
+             dmesh=None):
+    """One sweep point, end to end (the loop body of ``run_layered_sweep.py:1061-1124``).  ``prebuilt`` =
+    ``(mesh, e1_pos, e2_pos, body_info)`` and ``dmesh`` (a device mesh of the same topology whose coordinates have been set
+    to ``mesh.nodes``): the fixed-topology sweep, which re-uses pattern and device mesh instead of re-meshing."""
     say = (lambda *a, **k: None) if quiet else print
     results_dir = Path(results_dir) if results_dir else RESULTS_DIR
     sigma_skin = sigma_skin_override if sigma_skin_override is not None else p["conductivities"]["sigma_skin"]
     label = case_label(t_fat, elec_r)
     run_dir = results_dir / label
     say(f"\n[{label}]  t_fat={t_fat*1000:.1f}mm  r={elec_r*1000:.1f}mm  sigma_skin={sigma_skin}")
-    say("  meshing ...")
-    mesh, e1_pos, e2_pos, body_info = build_mesh(p, t_fat, elec_r, run_dir, coarse=coarse)
+    if prebuilt is None:
+        say("  meshing ...")
+        mesh, e1_pos, e2_pos, body_info = build_mesh(p, t_fat, elec_r, run_dir, coarse=coarse)
+    else:
+        say("  mesh: fixed topology, nodes displaced ...")
+        mesh, e1_pos, e2_pos, body_info = prebuilt
+        run_dir.mkdir(parents=True, exist_ok=True)
+        elmer_io.write_elmer_mesh(run_dir / "elmer_mesh", mesh)
     say(f"    {mesh.nn} nodes")
     say("  detecting electrode BCs + computing mesh areas ...")
     e1_id, e2_id, A_act, A_ret = pipeline.detect_elec_bc_ids(mesh, e1_pos, e2_pos, e1_pos[2], e2_pos[2])
@@ -159,7 +188,7 @@ def run_case(p, t_fat, elec_r, coarse=False, sigma_skin_override=None, ctx=None,
     pipeline.save_bc_debug_report(run_dir, label, e1_id, e2_id, A_act, A_ret, jn_used, p, body_info)
     (run_dir / "results").mkdir(exist_ok=True)
     say("  solver (GPU engine) ...")
-    case = pipeline.run_elmer_solver(run_dir, ctx=ctx, mesh=mesh,
+    case = pipeline.run_elmer_solver(run_dir, ctx=ctx, mesh=mesh, dmesh=dmesh,
                                      recover=p.get("solver", {}).get("current_recovery", pipeline.DEFAULT_RECOVER))
     say("  extracting metrics ...")
     res = pipeline.extract_layered(case, p, t_fat, elec_r, e1_pos, e2_pos, body_info, sigma_skin_used=sigma_skin,
@@ -167,7 +196,8 @@ def run_case(p, t_fat, elec_r, coarse=False, sigma_skin_override=None, ctx=None,
                                    e2_id=e2_id, warn=say)
     af_peak, af_path = save_activating_function(case, p, e1_pos, body_info, run_dir)
     say(f"    activating function along the nerve fibre: peak {af_peak:.4e} V/m² → {af_path.name}")
-    case.close()
+    if dmesh is None:
+        case.close()
     say(f"    peak_J_no_elec={res['peak_J_skin_no_elec']:.4f}  roi_mean_E={res['roi_mean_E']:.4f}  "
         f"efficiency={res['efficiency']:.4e}  flux_err={res['flux_err']:.3e}")
     if res.get("control_mode") == "current":
@@ -199,6 +229,30 @@ def run_sweep(p, t_fat_list, elec_r_list, coarse=False, sigma_skin_override=None
     return sweep.map_points(_point, points, gpus=gpus)
 
 
+def run_sweep_fixed_topology(p, t_fat_list, elec_r_list, coarse=False, sigma_skin_override=None, ctx=None, results_dir=None):
+    """The same sweep with the fat thickness as a NODE DISPLACEMENT: per electrode size one mesh (built for the thickest fat
+    layer of the sweep, so no layer is stretched thin), one device mesh and one CSR pattern; every thickness moves the nodes
+    (``ptfem_mesh_set_coords``), re-assembles and solves.  Rows come back in the reference's order (thickness outer loop)."""
+    ctx = ctx or sweep.worker_context()
+    results_dir = Path(results_dir) if results_dir else RESULTS_DIR
+    results_dir.mkdir(exist_ok=True)
+    t_ref = max(t_fat_list)
+    rows = {}
+    for r_mm in elec_r_list:
+        elec_r = r_mm * 1e-3
+        ref_dir = results_dir / f"_topology_r{int(r_mm):04d}um"
+        mesh_ref, e1, e2, body_info = build_mesh(p, t_ref, elec_r, ref_dir, coarse=coarse)
+        dm = ctx.mesh(mesh_ref.nodes, mesh_ref.tets, mesh_ref.region, mesh_ref.tris, mesh_ref.bcid)
+        dm.pattern()
+        for t_fat in t_fat_list:
+            mesh_k = displace_fat_thickness(mesh_ref, p, t_ref, t_fat)
+            dm.set_coords(mesh_k.nodes)
+            rows[(t_fat, r_mm)] = run_case(p, t_fat, elec_r, coarse, sigma_skin_override, ctx=ctx, results_dir=results_dir,
+                                           prebuilt=(mesh_k, e1, e2, body_info), dmesh=dm)
+        dm.close()
+    return [rows[(t_fat, r_mm)] for t_fat in t_fat_list for r_mm in elec_r_list]
+
+
 def save_results(all_results, results_dir=None):
     if not all_results:
         return
@@ -218,6 +272,9 @@ def main(argv=None):
     ap = argparse.ArgumentParser(description="Ankle layered slab sweep")
     ap.add_argument("--smoke", action="store_true", help="Single coarse case for quick pipeline check")
     ap.add_argument("--gpus", type=int, default=1, help="shard sweep points over this many GPUs")
+    ap.add_argument("--fixed-topology", action="store_true",
+                    help="fat thickness as node displacement on one mesh per electrode size (pattern and device mesh built once) "
+                         "instead of re-meshing every point")
     args = ap.parse_args(argv)
     p = load_params()
     pl = _pl(p)
@@ -230,7 +287,10 @@ def main(argv=None):
         r_list = pl.get("electrode_r_mm_list", pl.get("size_list", [5, 10, 15]))
         print(f"=== FULL SWEEP: {len(t_fat_list)} fat thicknesses × {len(r_list)} electrode sizes = "
               f"{len(t_fat_list)*len(r_list)} cases ===")
-    results = run_sweep(p, t_fat_list, r_list, coarse=args.smoke, gpus=args.gpus)
+    if args.fixed_topology:
+        results = run_sweep_fixed_topology(p, t_fat_list, r_list, coarse=args.smoke)
+    else:
+        results = run_sweep(p, t_fat_list, r_list, coarse=args.smoke, gpus=args.gpus)
     save_results(results)
     print(f"\n  {len(results)} case(s) computed → results/summary.csv, results/summary.json")
     return results

@@ -381,7 +381,7 @@ def layered_slab_mesh(Lx=0.080, Ly=0.060, Lz=0.040, t_skin=0.0015, t_fat=0.005, 
                       active_xy=(0.015, 0.045), return_xy=(0.065, 0.045), elec_r=0.010, shape="circle",
                       xs=None, ys=None, n_muscle=12, n_fat=3, n_skin=2, n_contact=1,
                       h_bulk=0.003, h_elec=0.0015, jitter=0.0, seed=0,
-                      interfaces_as_103=True, with_parents=True, contact_enabled=True, snap_rim=False):
+                      interfaces_as_103=True, with_parents=True, contact_enabled=True, snap_rim=False, bone=None):
     """Layered slab: muscle (body 1) / fat (2) / skin (3) + two contact pads
     (4 active, 5 return) sitting ON TOP of the skin.
 
@@ -393,6 +393,10 @@ def layered_slab_mesh(Lx=0.080, Ly=0.060, Lz=0.040, t_skin=0.0015, t_fat=0.005, 
     including the internal layer interfaces (``other_s``, ``:297,308``) when
     ``interfaces_as_103``.  Without contact (``contact_enabled=False``) the
     electrode patches lie on the skin top face.
+
+    ``bone``: optional ``dict(x=(x0, x1), y=(y0, y1), z=(z0, z1))`` - a block of body 6 (bone; BASELINE.json north_star
+    "skin/fat/muscle/bone layers"; the reference's slab only names the bone faces, ``params.yaml:9-10,18``) cut out of the
+    muscle.  Its faces are snapped onto the nearest grid planes; the extents actually meshed are in ``meta["bone"]``.
     """
     t_muscle = Lz - t_skin - t_fat
     if t_muscle <= 1e-4:
@@ -429,6 +433,20 @@ def layered_slab_mesh(Lx=0.080, Ly=0.060, Lz=0.040, t_skin=0.0015, t_fat=0.005, 
         raise ValueError("electrode footprints overlap")
     # hex body ids
     body = np.where(hk < k_fat, 1, np.where(hk < k_skin, 2, 3)).astype(np.int32)
+    bone_meta = None
+    if bone is not None:
+        def snap(lines, lo, hi, kmax):
+            a = int(np.argmin(np.abs(lines[:kmax + 1] - lo)))
+            b = int(np.argmin(np.abs(lines[:kmax + 1] - hi)))
+            if b <= a:
+                raise ValueError("bone block is thinner than one cell of this mesh")
+            return a, b
+        ia, ib = snap(xs, bone["x"][0], bone["x"][1], nxn - 1)
+        ja, jb = snap(ys, bone["y"][0], bone["y"][1], nyn - 1)
+        ka, kb = snap(zs, bone["z"][0], bone["z"][1], k_fat)          # bone lies inside the muscle block
+        inb = (hi >= ia) & (hi < ib) & (hj >= ja) & (hj < jb) & (hk >= ka) & (hk < kb)
+        body = np.where(inb, 6, body).astype(np.int32)
+        bone_meta = dict(x=(float(xs[ia]), float(xs[ib])), y=(float(ys[ja]), float(ys[jb])), z=(float(zs[ka]), float(zs[kb])))
     keep = np.ones(hk.shape, dtype=bool)
     if nc:
         in_pad = hk >= k_top
@@ -497,6 +515,7 @@ def layered_slab_mesh(Lx=0.080, Ly=0.060, Lz=0.040, t_skin=0.0015, t_fat=0.005, 
                              t_contact=t_contact if nc else 0.0, elec_r=elec_r, shape=shape,
                              active_xy=tuple(active_xy), return_xy=tuple(return_xy),
                              z_elec_top=z_elec_top, contact_enabled=bool(nc),
+                             bone=bone_meta,
                              area_active=float(ca[m1].sum()), area_return=float(ca[m2].sum()),
                              grid=(nxn, nyn, nzn)))
     if with_parents:

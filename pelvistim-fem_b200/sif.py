@@ -136,13 +136,15 @@ def electrode_area_analytic(elec_r, shape):
 
 def layered_case(e1_id, e2_id, sigma_muscle, sigma_fat, sigma_skin, sigma_contact, contact=True,
                  c1_body=4, c2_body=5, mode="current", injected_current_mA=5.0, elec_r=0.010,
-                 shape="circle", elec_area_mesh=None, tol=1e-8, lin_solver="UMFPACK", dialect="step03"):
+                 shape="circle", elec_area_mesh=None, tol=1e-8, lin_solver="UMFPACK", dialect="step03",
+                 sigma_bone=None, bone_body=6):
     """Layered-slab case (``run_layered_sweep.py:507-633``; step04 variant
     ``run_pressure_sweep.py:297-432`` selected with ``dialect='step04'``).
 
     Returns ``(sections, jn_used, warning)``; ``jn_used`` = I / A (A = mesh area of the
     active electrode when given, else the analytic footprint area), ``None`` in
-    voltage mode."""
+    voltage mode.  ``sigma_bone``: adds a bone body (mesh body ``bone_body``) with its own material after the
+    reference's bodies / materials (not in the reference's SIFs, which are reproduced byte for byte without it)."""
     secs = [_header(), _simulation(3), _constants(), _equation(),
             _solver_current(tol=tol, method=lin_solver), _solver_output()]
     for i, (name, mat) in enumerate((("muscle", 1), ("fat", 2), ("skin", 3)), start=1):
@@ -153,6 +155,9 @@ def layered_case(e1_id, e2_id, sigma_muscle, sigma_fat, sigma_skin, sigma_contac
                     .add("Equation", 1).add("Material", 4))
         secs.append(Section("Body", 5).add("Name", '"contact_return"').add("Target Bodies(1)", c2_body)
                     .add("Equation", 1).add("Material", 4))
+    if sigma_bone is not None:
+        secs.append(Section("Body", 6 if contact else 4).add("Name", '"bone"').add("Target Bodies(1)", bone_body)
+                    .add("Equation", 1).add("Material", 5 if contact else 4))
     m1 = Section("Material", 1).add("Name", '"muscle"').add("Electric Conductivity", sigma_muscle)
     if dialect == "step03":
         m1.lead = "! PLACEHOLDER conductivities — replace with measured values"
@@ -163,6 +168,8 @@ def layered_case(e1_id, e2_id, sigma_muscle, sigma_fat, sigma_skin, sigma_contac
                 else "pressure-dependent — PLACEHOLDER")
         secs.append(Section("Material", 4).add("Name", '"contact"')
                     .add("Electric Conductivity", sigma_contact, comment=note, gap=3))
+    if sigma_bone is not None:
+        secs.append(Section("Material", 5 if contact else 4).add("Name", '"bone"').add("Electric Conductivity", sigma_bone))
     jn_used = None
     warning = None
     bc1 = Section("Boundary Condition", 1).add("Name", '"active_electrode"').add(f"Target Boundaries = {e1_id}")

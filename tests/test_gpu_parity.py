@@ -881,6 +881,56 @@ def test_step03_driver_reproduces_reference_table(gpu_ctx, golden, tmp_path, mon
         assert (tmp_path / label / f).exists(), f                      # per-case layout of README.md:67-86
 
 
+def test_step03_smoke_test_script():
+    # the reference's own acceptance script for step03 (step03_ankle_layers/smoke_test.py:81-188), as a drop-in beside the driver
+    import os, subprocess, sys
+    from pathlib import Path
+    d = Path(__file__).resolve().parents[1] / "drivers" / "step03_ankle_layers"
+    pr = subprocess.run([sys.executable, "smoke_test.py"], cwd=d, capture_output=True, text=True, timeout=600)
+    assert pr.returncode == 0, pr.stdout[-3000:] + pr.stderr[-2000:]
+    assert "All checks passed" in pr.stdout and "FAIL" not in pr.stdout
+    assert pr.stdout.count("PASS") >= 11                      # 10 field / table checks + the summary line (current mode: + compliance)
+
+
+def test_bone_layer_series_circuit_exact_on_gpu(gpu_ctx):
+    # bone body (region 6) through the C-ABI: the analytic series-circuit answer (tests/test_oracle.py states it)
+    from test_oracle import _bone_layer_case
+    m, sig, phi_exact, Jz = _bone_layer_case()
+    dm = dm_for(gpu_ctx, m)
+    dm.assemble(sig).bc_reset(1).dirichlet(201, 1.0).dirichlet(202, 0.0)
+    phi = dm.solve(rtol=1e-13)[0]
+    assert np.abs(phi - phi_exact(m.nodes[:, 2])).max() < 1e-9
+    J = dm.recover_current(0, "lumped")
+    assert np.abs(J[:, 2] - Jz).max() < 1e-7 * abs(Jz) and np.abs(J[:, :2]).max() < 1e-7 * abs(Jz)
+    dm.close()
+
+
+def test_step03_fat_thickness_as_node_displacement(gpu_ctx, tmp_path, monkeypatch):
+    # the fat-thickness axis of step03 on FIXED topology (one pattern / device mesh per electrode size, nodes
+    # displaced) against the re-meshed sweep: same columns, physical agreement to discretisation accuracy, and the displaced
+    # geometry is exactly the requested one (layer interfaces where params say)
+    import run_layered_sweep as s3
+    monkeypatch.setattr(s3, "RESULTS_DIR", tmp_path)
+    monkeypatch.setattr(s3.sweep, "worker_context", lambda: gpu_ctx)
+    p = s3.load_params()
+    t_list, r_list = [0.003, 0.008], [10]
+    fixed = s3.run_sweep_fixed_topology(p, t_list, r_list, ctx=gpu_ctx, results_dir=tmp_path / "fixed")
+    remesh = [s3.run_case(p, t, 0.010, ctx=gpu_ctx, results_dir=tmp_path / "remesh", quiet=True) for t in t_list]
+    assert [list(r.keys()) for r in fixed] == [list(r.keys()) for r in remesh]
+    for a, b in zip(fixed, remesh):
+        assert a["t_fat_mm"] == b["t_fat_mm"] and a["dist_fat_muscle_mm"] == b["dist_fat_muscle_mm"]
+        assert a["elec_area_mesh_cm2"] == b["elec_area_mesh_cm2"] and a["jn_used"] == b["jn_used"]     # same footprint mesh
+        for k, tol in (("compliance_V", 0.03), ("total_current_A", 0.03), ("roi_mean_J", 0.12), ("roi_mean_E", 0.12)):
+            assert abs(a[k] - b[k]) <= tol * abs(b[k]), (a["t_fat_mm"], k, a[k], b[k])
+    # thinner fat -> the nerve depth sees more current (both ways of building the mesh agree on the trend)
+    assert fixed[0]["roi_mean_J"] > fixed[1]["roi_mean_J"] and remesh[0]["roi_mean_J"] > remesh[1]["roi_mean_J"]
+    from pelvistim_fem_b200 import elmer_io
+    m3 = elmer_io.read_elmer_mesh(tmp_path / "fixed" / s3.case_label(0.003, 0.010) / "elmer_mesh")
+    zs = np.unique(np.round(m3.nodes[:, 2], 9))
+    Lz, t_skin = p["geometry"]["Lz"], p["layers"]["t_skin"]
+    assert np.any(np.abs(zs - (Lz - t_skin - 0.003)) < 1e-9) and np.any(np.abs(zs - (Lz - t_skin)) < 1e-9)
+
+
 # last in the file: it depends on how the box schedules two processes on one GPU
 @pytest.mark.parametrize("setup", ["replica", "distributed"])
 def test_row_partitioned_two_ranks_on_one_gpu(tmp_path, setup):

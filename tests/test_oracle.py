@@ -224,3 +224,37 @@ def test_c_oracle_coarse_grid_pcg_and_recovery_match_numpy_oracle():
     co.set_threads(1)
     assert co.threads() == 1
     assert co.use_all_cores() == co.host_cores() == co.threads()
+
+
+def _bone_layer_case():
+    """Layered slab whose bone block is a FULL layer inside the muscle, 1 V across top and bottom faces: a 1-D series
+    circuit with a known answer that linear tets reproduce exactly (interfaces lie on mesh planes)."""
+    m = meshgen.layered_slab_mesh(bone=dict(x=(0, 0.08), y=(0, 0.06), z=(0.010, 0.020)), contact_enabled=False,
+                                  h_bulk=0.006, h_elec=0.004, n_muscle=10)
+    zt = m.nodes[m.tris][:, :, 2]
+    bc = np.where(np.all(np.abs(zt - 0.040) < 1e-12, axis=1), 201, np.where(np.all(np.abs(zt) < 1e-12, axis=1), 202, 103)).astype(np.int32)
+    m = meshgen.TetMesh(m.nodes, m.tets, m.region, m.tris, bc, meta=m.meta)
+    sig = {1: 0.35, 2: 0.04, 3: 0.001, 6: 0.02}
+    zb0, zb1 = m.meta["bone"]["z"]
+    z_mf, z_fs, Lz = 0.040 - 0.0015 - 0.005, 0.040 - 0.0015, 0.040
+    layers = [(0.0, zb0, sig[1]), (zb0, zb1, sig[6]), (zb1, z_mf, sig[1]), (z_mf, z_fs, sig[2]), (z_fs, Lz, sig[3])]
+    R = sum((b - a) / s for a, b, s in layers)
+    Jz = -1.0 / R                                  # 1 V on top, 0 V at the bottom: current flows down
+
+    def phi_exact(z):
+        out = np.zeros_like(z)
+        acc = 0.0
+        for a, b, s in layers:
+            out = np.where(z > a, acc + (np.minimum(z, b) - a) / s / R, out)
+            acc += (b - a) / s / R
+        return out
+    return m, sig, phi_exact, Jz
+
+
+def test_bone_layer_series_circuit_exact():
+    # the bone body (region 6): analytic two-(five-)material known answer, exact for P1
+    m, sig, phi_exact, Jz = _bone_layer_case()
+    assert 6 in np.unique(m.region)
+    r = fo.solve_case(m, sig, [(201, 1.0), (202, 0.0)], [], recover="lumped")
+    assert np.abs(r["phi"] - phi_exact(m.nodes[:, 2])).max() < 1e-11
+    assert np.abs(r["J"][:, 2] - Jz).max() < 1e-9 * abs(Jz) and np.abs(r["J"][:, :2]).max() < 1e-9 * abs(Jz)
