@@ -111,6 +111,13 @@ int make_linsys(ptfem_mesh* m, LinSys& A) {
   A.b = m->b.p;
   A.stream_rows = m->stream_rows;
   A.stream_cap = m->stream_cap;
+  if (m->has_qcopy && m->nvalp == 1 && m->qval.p) {
+    A.qrowptr = m->qrowptr.p;
+    A.qcol = m->qcol.p;
+    A.qval = m->qval.p;
+    A.q_rows = m->q_rows;
+    A.q_cap = m->q_cap;
+  }
   if (m->has_rowperm && m->nvalp == 1 && m->pval.p) {
     A.rowid = m->rowid.p;
     A.prowptr = m->prowptr.p;
@@ -132,6 +139,11 @@ int prepare_systems(ptfem_mesh* m) {
       PT_CK(cudaMemsetAsync(m->phi.p, 0, (size_t)m->nn * S * sizeof(double), m->ctx->stream));
     }
     m->nsys_user = std::max(m->nval, m->nrhs);
+    if (m->has_qcopy && m->nvalp == 1) {     // even-padded copy of the eliminated matrix for the multi-RHS streaming kernel
+      PT_TRY(m->qval.alloc(m->qnnz + 8));
+      PT_CK(cudaMemsetAsync(m->qval.p + m->qnnz, 0, 8 * sizeof(double), m->ctx->stream));
+      PT_TRY(pad_values(m->ctx, m->nn, m->rowptr.p, m->qrowptr.p, m->val_bc.p, m->qval.p));
+    }
     if (m->has_rowperm && m->nvalp == 1) {   // the streaming kernel's private copy of the eliminated matrix
       PT_TRY(m->pval.alloc(m->nnz + 8));
       PT_CK(cudaMemsetAsync(m->pval.p + m->nnz, 0, 8 * sizeof(double), m->ctx->stream));
@@ -202,6 +214,7 @@ int ptfem_ctx_create(int device, ptfem_ctx** out) {
   if (const char* e = getenv("PTFEM_PUPDATE_NP")) c->tune_pupdate_np = atoi(e) == 2 ? 2 : 1;
   if (const char* e = getenv("PTFEM_PUPDATE_OCC")) c->tune_pupdate_occ = atoi(e);
   if (const char* e = getenv("PTFEM_CHAIN_TAIL")) c->tune_chain_tail = atoi(e) != 0;
+  if (const char* e = getenv("PTFEM_SPMM_PAIR")) c->tune_pair = atoi(e) != 0;
   if (const char* e = getenv("PTFEM_COARSE_WEIGHT")) {
     const double w = atof(e);
     if (w > 0.0) c->tune_coarse_weight = w;

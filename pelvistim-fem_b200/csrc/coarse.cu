@@ -127,18 +127,50 @@ __global__ void __launch_bounds__(256, OCC) restrict_cell_kernel(int64_t ntask, 
           for (int v = 0; v < NV; ++v) acc[a][v] = fma(wgt[a], vb[v], acc[a][v]);
       }
     }
+    // Sum over the row slots (lanes with the same system pair).  Butterfly with halving: at every step a lane hands half of
+    // its remaining sums to its partner and receives the partner's half of the others, so 8*NV sums over 32/NP slots cost
+    // 8*NV - (what is left per lane) shuffles instead of 8*NV per step (14 instead of 48 for S = 8: the shuffles were
+    // half of this kernel's LSU wavefronts), and the sums end up spread over the lanes, which then store in parallel.
+    constexpr int NVAL = 8 * NV;
+    double v[NVAL];
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
-      for (int v = 0; v < NV; ++v) {
+      for (int q = 0; q < NV; ++q) v[a * NV + q] = acc[a][q];
+    int base = 0;        // v[i] of this lane is sum number base + i
+    bool owner = true;   // false for the duplicates left by steps taken after a lane is down to one sum
+    {
+      int n = NVAL;
 #pragma unroll
-        for (int o = NP; o < 32; o <<= 1) acc[a][v] += __shfl_xor_sync(0xffffffffu, acc[a][v], o);
+      for (int o = NP; o < 32; o <<= 1) {
+        const bool up = (lane & o) != 0;
+        if (n > 1) {
+#pragma unroll
+          for (int i = 0; i < NVAL / 2; ++i) {
+            if (i < n / 2) {
+              const double send = up ? v[i] : v[i + n / 2];
+              const double keep = up ? v[i + n / 2] : v[i];
+              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+          }
+          base += up ? n / 2 : 0;
+          n /= 2;
+        } else {
+          v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+          owner = owner && !up;
+        }
       }
-    if (slot == 0) {
+      if (owner) {
+        if (n >= 2 && NV == 2) {   // pairs (sum 2j, 2j+1) = corner j, both systems of this lane: one 16-byte store each
 #pragma unroll
-      for (int a = 0; a < 8; ++a)
+          for (int i = 0; i < NVAL; i += 2)
+            if (i < n) *reinterpret_cast<double2*>(part + ((size_t)w * 8 + (base + i) / 2) * S + 2 * pr) = make_double2(v[i], v[i + 1]);
+        } else {
 #pragma unroll
-        for (int v = 0; v < NV; ++v) part[((size_t)w * 8 + a) * S + NV * pr + v] = acc[a][v];
+          for (int i = 0; i < NVAL; ++i)
+            if (i < n) part[((size_t)w * 8 + (base + i) / NV) * S + NV * pr + (base + i) % NV] = v[i];
+        }
+      }
     }
   }
 }

@@ -112,6 +112,7 @@ struct ptfem_ctx {
   int tune_restrict_occ = 4;       // PTFEM_RESTRICT_OCC: resident CTAs per SM the restriction kernel is compiled for (2, 4, 6; 4 measured best in round 1)
   int tune_coarse_fused = 0;       // PTFEM_COARSE_FUSED: grid hierarchy of the coarse-grid preconditioner as one cooperative kernel
   double tune_coarse_weight = 0.0; // PTFEM_COARSE_WEIGHT: weight of the coarse-grid levels against the Jacobi term (0 = 2 / (levels + 1))
+  int tune_pair = 0;               // PTFEM_SPMM_PAIR: multi-RHS streaming SpMM reads two non-zeros per shared-memory access (even-padded copy); measured slower (0.335 vs 0.289 ms): off
   int tune_chain_tail = 0;         // PTFEM_CHAIN_TAIL: partitioned solve runs the replicated smallest grid levels as one block (measured slower: off)
   int tune_pupdate_occ = 4;        // PTFEM_PUPDATE_OCC: resident CTAs per SM the one-pair p-update is compiled for (4, 5, 6)
   int tune_pupdate_np = 1;         // PTFEM_PUPDATE_NP: pairs per trip of the coarse-grid p-update (1: 4 CTAs/SM, 2: 2 CTAs/SM, all loads of both first)
@@ -167,6 +168,13 @@ struct ptfem_mesh {
   double row_coherence = 1.0;     // fraction of rows whose columns are the previous row's shifted by one
   ptfem::DevBuf<int32_t> rowid, prowptr, pcol;
   ptfem::DevBuf<double> pval;     // [nnz] values of val_bc in processing order (single matrix only)
+  // multi-RHS streaming SpMM: copy of the matrix with every row padded to an EVEN length (pad: value 0, column = the row's
+  // own), so that a lane takes two non-zeros per shared-memory access (one 16-byte load of values, one 8-byte load of columns)
+  bool has_qcopy = false;
+  int64_t qnnz = 0;
+  ptfem::DevBuf<int32_t> qrowptr, qcol;
+  ptfem::DevBuf<double> qval;
+  int32_t q_rows = 0, q_cap = 0;  // its tile geometry
   double bb_lo[3] = {0, 0, 0}, bb_hi[3] = {0, 0, 0};
   int32_t stream_rows = 0;        // rows per tile of the streaming SpMV (0 = not usable on this pattern)
   int32_t stream_cap = 0;         // staged entries per tile

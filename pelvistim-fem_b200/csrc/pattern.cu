@@ -172,6 +172,19 @@ __global__ void perm_row_len(const int32_t* __restrict__ rowptr, const int32_t* 
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j < nn) len[j] = rowptr[rowid[j] + 1] - rowptr[rowid[j]];
 }
+// even-padded copy: row lengths rounded up to even; the pad entry points at the row's own column
+__global__ void pad_row_len(const int32_t* __restrict__ rowptr, int64_t nn, int32_t* __restrict__ len) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nn) len[i] = (rowptr[i + 1] - rowptr[i] + 1) & ~1;
+}
+__global__ void pad_copy_col(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ qrowptr,
+                             int64_t nn, int32_t* __restrict__ qcol) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nn) return;
+  const int32_t src = rowptr[i], n = rowptr[i + 1] - src, dst = qrowptr[i], nq = qrowptr[i + 1] - dst;
+  for (int32_t t = 0; t < n; ++t) qcol[dst + t] = col[src + t];
+  for (int32_t t = n; t < nq; ++t) qcol[dst + t] = (int32_t)i;
+}
 // pcol[prowptr[j] + t] = col[rowptr[rowid[j]] + t]
 __global__ void perm_copy_col(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                               const int32_t* __restrict__ rowid, const int32_t* __restrict__ prowptr, int64_t nn,
@@ -361,6 +374,37 @@ int ptfem_build_pattern(ptfem_mesh* m) {
         m->stream_cap = ctx->tune_stream_cap > 0 ? cap_max : ((mx + 31) & ~31);
         if (m->stream_cap < 256) m->stream_cap = 256;
       }
+    }
+  }
+  // even-padded copy for the multi-RHS streaming SpMM (natural row order only; the Morton copy keeps its own path)
+  m->has_qcopy = false;
+  if (!m->has_rowperm && m->stream_rows > 0 && ctx->tune_pair && nn >= 4096) {
+    DevBuf<int32_t> qlen;
+    PT_TRY(qlen.alloc(nn + 1));
+    PT_TRY(m->qrowptr.alloc(nn + 1));
+    pad_row_len<<<ceil_div(nn, 256), 256, 0, ctx->stream>>>(m->rowptr.p, nn, qlen.p);
+    PT_LAUNCH_CHECK(ctx);
+    int64_t tot = 0;
+    PT_TRY(exclusive_scan_i32(ctx, qlen.p, m->qrowptr.p, nn, &tot));
+    m->qnnz = tot;
+    PT_TRY(m->qcol.alloc(tot + 8));
+    PT_CK(cudaMemsetAsync(m->qcol.p + tot, 0, 8 * sizeof(int32_t), ctx->stream));
+    pad_copy_col<<<ceil_div(nn, 256), 256, 0, ctx->stream>>>(m->rowptr.p, m->col.p, m->qrowptr.p, nn, m->qcol.p);
+    PT_LAUNCH_CHECK(ctx);
+    // tile geometry of the padded copy (same rows per tile, a slightly larger stage)
+    DevBuf<int32_t> mt;
+    PT_TRY(mt.alloc(1));
+    PT_TRY(fill_i32(ctx, mt.p, 0, 1));
+    const int R = m->stream_rows;
+    max_tile_nnz<<<ceil_div((nn + R - 1) / R, 256), 256, 0, ctx->stream>>>(m->qrowptr.p, nn, R, mt.p);
+    PT_LAUNCH_CHECK(ctx);
+    int32_t mx = 0;
+    PT_CK(cudaMemcpyAsync(&mx, mt.p, sizeof mx, cudaMemcpyDeviceToHost, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    if (mx <= ptfem_stream_cap_max()) {
+      m->q_rows = R;
+      m->q_cap = std::max(256, (mx + 31) & ~31);
+      m->has_qcopy = true;
     }
   }
   DevBuf<int32_t> mrl;

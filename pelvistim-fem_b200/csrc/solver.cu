@@ -391,7 +391,7 @@ __host__ __device__ inline size_t stream_smem_bytes(int stages, int cap) { retur
 // interleave = 1: CTAs sweep the matrix together as one moving front (tile j of CTA b is b + j*grid).
 // LPR lanes share a row: for S == 1 they split the row's non-zeros (TPR), for S >= 2 each of the S/2
 // lanes owns two systems (one 16-byte access per lane, 8*S contiguous bytes per row and non-zero).
-template <int S, int STAGES, int TPR, bool DOT, bool PEER = false>
+template <int S, int STAGES, int TPR, bool DOT, bool PEER = false, bool PAIR = false>
 __global__ void __launch_bounds__(kStreamThreads*(S == 1 ? TPR : S / 2))
     spmv_stream_kernel(int64_t nn, int64_t row0, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                        const double* __restrict__ val, int32_t R, int32_t cap, int32_t ntiles, int32_t tiles_per_cta,
@@ -512,7 +512,21 @@ __global__ void __launch_bounds__(kStreamThreads*(S == 1 ? TPR : S / 2))
         acc.x = fma(a, xv.x, acc.x);
         acc.y = fma(a, xv.y, acc.y);
       };
-      if constexpr (TPR == 2) {
+      if constexpr (PAIR) {
+        // even-padded rows: two non-zeros per trip from ONE 16-byte shared load of values and ONE 8-byte load of columns
+        // (half the shared-memory wavefronts of the one-at-a-time loop; the LSU data pipe is this kernel's bound)
+#pragma unroll 2
+        for (int32_t k = b - a0; k < e - a0; k += 2) {
+          const double2 a2 = *reinterpret_cast<const double2*>(sv + k);
+          const int2 c2 = *reinterpret_cast<const int2*>(sc + k);
+          const double2 x0 = ldg_f64x2_hint(x + (int64_t)c2.x * S + 2 * lane, pol_keep);
+          const double2 x1 = ldg_f64x2_hint(x + (int64_t)c2.y * S + 2 * lane, pol_keep);
+          acc.x = fma(a2.x, x0.x, acc.x);
+          acc.y = fma(a2.x, x0.y, acc.y);
+          acc.x = fma(a2.y, x1.x, acc.x);
+          acc.y = fma(a2.y, x1.y, acc.y);
+        }
+      } else if constexpr (TPR == 2) {
 #pragma unroll 8
         for (int32_t k = b - a0; k < e - a0; ++k) body(k);
       } else if constexpr (TPR == 4) {
@@ -972,14 +986,23 @@ int launch_vector(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y, P
   return PTFEM_OK;
 }
 
-template <int S, int STAGES, int TPR, bool DOT, bool PEER = false>
-int launch_stream_t(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y, PcgWork* w) {
+template <int S, int STAGES, int TPR, bool DOT, bool PEER = false, bool PAIR = false>
+int launch_stream_t(ptfem_ctx* ctx, const LinSys& A0, const double* x, double* y, PcgWork* w) {
+  LinSys A = A0;
+  if constexpr (PAIR) {   // the even-padded copy and its tile geometry stand in for the matrix
+    A.rowptr = A0.qrowptr;
+    A.col = A0.qcol;
+    A.val = A0.qval;
+    A.stream_rows = A0.q_rows;
+    A.stream_cap = A0.q_cap;
+    A.rowid = nullptr;
+  }
   const size_t smem = stream_smem_bytes(STAGES, A.stream_cap);
   {
-    const void* fn = reinterpret_cast<const void*>(&spmv_stream_kernel<S, STAGES, TPR, DOT, PEER>);
+    const void* fn = reinterpret_cast<const void*>(&spmv_stream_kernel<S, STAGES, TPR, DOT, PEER, PAIR>);
     auto it = ctx->func_smem.find(fn);
     if (it == ctx->func_smem.end() || it->second < smem) {
-      PT_CK(cudaFuncSetAttribute(spmv_stream_kernel<S, STAGES, TPR, DOT, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PT_CK(cudaFuncSetAttribute(spmv_stream_kernel<S, STAGES, TPR, DOT, PEER, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       ctx->func_smem[fn] = smem;
     }
   }
@@ -997,7 +1020,7 @@ int launch_stream_t(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y,
   const int64_t per_cta = (ntiles + grid - 1) / grid;
   if (!ctx->tune_interleave) grid = (ntiles + per_cta - 1) / per_cta;
   const bool perm = A.rowid != nullptr && A.row0 == 0;
-  spmv_stream_kernel<S, STAGES, TPR, DOT, PEER><<<(int)grid, threads, smem, ctx->stream>>>(
+  spmv_stream_kernel<S, STAGES, TPR, DOT, PEER, PAIR><<<(int)grid, threads, smem, ctx->stream>>>(
       A.nn, A.row0, perm ? A.prowptr : A.rowptr, perm ? A.pcol : A.col, perm ? A.pval : A.val, A.stream_rows, A.stream_cap,
       (int32_t)ntiles, (int32_t)per_cta, ctx->tune_interleave, perm ? 0 : ctx->tune_xprefetch, perm ? A.rowid : nullptr, x, y,
       w ? w->partial.p : nullptr, w ? w->scal.p : nullptr, w ? w->ticket.p : nullptr, A.peer);
@@ -1016,6 +1039,7 @@ int launch_stream(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y, P
     if (stages >= 3) return tpr == 2 ? launch_stream_t<1, 3, 2, DOT>(ctx, A, x, y, w) : launch_stream_t<1, 3, 1, DOT>(ctx, A, x, y, w);
     return tpr == 2 ? launch_stream_t<1, 2, 2, DOT>(ctx, A, x, y, w) : launch_stream_t<1, 2, 1, DOT>(ctx, A, x, y, w);
   } else {
+    if (A.qval && A.row0 == 0 && !A.rowid && tpr != 2 && tpr != 4) return launch_stream_t<S, 2, 1, DOT, false, true>(ctx, A, x, y, w);
     if (tpr == 2) return launch_stream_t<S, 2, 2, DOT>(ctx, A, x, y, w);
     if (tpr == 4) return launch_stream_t<S, 2, 4, DOT>(ctx, A, x, y, w);
     return launch_stream_t<S, 2, 1, DOT>(ctx, A, x, y, w);
@@ -1060,6 +1084,17 @@ __global__ void permute_values_kernel(int64_t nn, const int32_t* __restrict__ ro
 }
 }  // namespace
 
+namespace {
+__global__ void pad_values_kernel(int64_t nn, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ qrowptr,
+                                  const double* __restrict__ val, double* __restrict__ qval) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;   // 8 lanes per row
+  const int lane = threadIdx.x & 7;
+  if (i >= nn) return;
+  const int32_t src = rowptr[i], n = rowptr[i + 1] - src, dst = qrowptr[i], nq = qrowptr[i + 1] - dst;
+  for (int32_t t = lane; t < nq; t += 8) qval[dst + t] = t < n ? val[src + t] : 0.0;
+}
+}  // namespace
+
 int ptfem_stream_cap_max() { return kStreamCapMax; }
 int ptfem_stream_rows_default() { return kStreamRowsDefault; }
 int ptfem_stream_threads() { return kStreamThreads; }
@@ -1076,6 +1111,12 @@ int resolve_variant(const LinSys& A, int variant) {
 int permute_values(ptfem_ctx* ctx, int64_t nn, const int32_t* rowptr, const int32_t* rowid, const int32_t* prowptr,
                    const double* val, double* pval) {
   permute_values_kernel<<<ceil_div(nn * 8, 256), 256, 0, ctx->stream>>>(nn, rowptr, rowid, prowptr, val, pval);
+  PT_LAUNCH_CHECK(ctx);
+  return PTFEM_OK;
+}
+
+int pad_values(ptfem_ctx* ctx, int64_t nn, const int32_t* rowptr, const int32_t* qrowptr, const double* val, double* qval) {
+  pad_values_kernel<<<ceil_div(nn * 8, 256), 256, 0, ctx->stream>>>(nn, rowptr, qrowptr, val, qval);
   PT_LAUNCH_CHECK(ctx);
   return PTFEM_OK;
 }

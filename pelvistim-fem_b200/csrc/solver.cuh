@@ -30,6 +30,11 @@ struct LinSys {
   const int32_t* prowptr = nullptr;
   const int32_t* pcol = nullptr;
   const double* pval = nullptr;
+  // optional even-padded copy for the multi-RHS streaming kernel (natural row order)
+  const int32_t* qrowptr = nullptr;
+  const int32_t* qcol = nullptr;
+  const double* qval = nullptr;
+  int32_t q_rows = 0, q_cap = 0;
   // peer-memory gathers (row-partitioned solve, S == 1): columns >= peer.nloc are not local; entry c is read
   // through peer.halo[c - nloc] (a pointer into a neighbour GPU's vector) after the neighbours' ready flags
   // (peer.flags, local memory) have reached *peer.wait
@@ -54,4 +59,6 @@ int resolve_variant(const LinSys& A, int variant);
 // pval = val gathered into processing order (one matrix): pval[prowptr[j]+t] = val[rowptr[rowid[j]]+t]
 int permute_values(ptfem_ctx* ctx, int64_t nn, const int32_t* rowptr, const int32_t* rowid, const int32_t* prowptr,
                    const double* val, double* pval);
+// qval = val with every row padded to even length (pad value 0)
+int pad_values(ptfem_ctx* ctx, int64_t nn, const int32_t* rowptr, const int32_t* qrowptr, const double* val, double* qval);
 }  // namespace ptfem

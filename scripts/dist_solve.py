@@ -41,7 +41,8 @@ line = dict(rank=rank, world=world, size=size, transport=res["transport"], coars
 if not distributed:
     line.update(rel_err_vs_single=res["rel_err_vs_single"], single_gpu_ms=res["single_gpu_ms"], single_gpu_iterations=res["single_gpu_iterations"],
                 single_gpu_coarse_solve_ms=res["single_gpu_auto_solve_ms"], single_gpu_coarse_iterations=res["single_gpu_auto_iterations"])
-print(json.dumps(line), flush=True)
+sys.stdout.flush()
+os.write(1, (json.dumps(line) + "\n").encode())     # one write: lines of different ranks do not interleave in the launcher's pipe
 if os.environ.get("PTFEM_DUMP_X"):      # this rank's block of the solution, for the caller's own checks (tests compare with the oracle)
     np.save(os.environ["PTFEM_DUMP_X"].format(rank=rank), res["x_local"])
 assert distributed or res["rel_err_vs_single"] < 1e-6, res["rel_err_vs_single"]
