@@ -16,7 +16,7 @@ import numpy as np
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import _common  # noqa: F401,E402
-from pelvistim_fem_b200 import elmer_io, gmsh_io, meshgen, pipeline, sif  # noqa: E402
+from pelvistim_fem_b200 import elmer_io, gmsh_io, meshgen, pipeline, sif, sizefield_mesher  # noqa: E402
 
 Lx, Ly, Lz = 0.15, 0.15, 0.05
 SEP = 0.06
@@ -30,10 +30,16 @@ e1_pos = np.array([Lx / 2 - SEP / 2, Ly / 2])
 e2_pos = np.array([Lx / 2 + SEP / 2, Ly / 2])
 
 
-def build_mesh(shape, r, run_dir, coarse=False):
+def build_mesh(shape, r, run_dir, coarse=False, mesher="kuhn"):
+    """``mesher``: "kuhn" (structured, default) or "graded" (size-field mesh of the reference's kind,
+    ``sizefield_mesher.electrode_box_graded``: mean |J| over the top-face nodes within 2-5 % of the reference's PNG titles for
+    r >= 10 mm against 13-20 %, but +34 % at r = 5 mm and square-corner peaks +22-27 % - oracle study, scripts/study/tables_cpu2.py)."""
     run_dir.mkdir(parents=True, exist_ok=True)
     s = 2.0 if coarse else 1.0
-    m = meshgen.electrode_box_mesh(Lx, Ly, Lz, e1_pos, e2_pos, r, shape, h_elec=s * r / 3.5, h_bulk=s * min(4 * r, 0.012), snap_rim=True)
+    if mesher == "graded":
+        m = sizefield_mesher.electrode_box_graded(Lx, Ly, Lz, e1_pos, e2_pos, r, shape, lc_elec=s * r / 3.5, lc_bulk=s * min(4 * r, 0.012))
+    else:
+        m = meshgen.electrode_box_mesh(Lx, Ly, Lz, e1_pos, e2_pos, r, shape, h_elec=s * r / 3.5, h_bulk=s * min(4 * r, 0.012), snap_rim=True)
     gmsh_io.write_msh(run_dir / "mesh.msh", m, {(3, 1): "tissue", (2, 101): "active", (2, 102): "return", (2, 103): "other"})
     elmer_io.write_elmer_mesh(run_dir / "elmer_mesh", m)
     return m, (np.pi * r * r if shape == "circle" else (2 * r) ** 2)
@@ -51,6 +57,7 @@ def write_sif(run_dir, e1_id, e2_id):
 def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--smoke", action="store_true", help="one coarse case")
+    ap.add_argument("--mesher", choices=("kuhn", "graded"), default="kuhn")
     args = ap.parse_args(argv)
     RESULTS.mkdir(exist_ok=True)
     cases = [("circle", 0.010)] if args.smoke else [(s, r) for s in SHAPES for r in RADII]
@@ -60,7 +67,7 @@ def main(argv=None):
         run_dir = RESULTS / label
         print(f"\n[{label}]")
         print("  building mesh...")
-        mesh, area = build_mesh(shape, r, run_dir, coarse=args.smoke)
+        mesh, area = build_mesh(shape, r, run_dir, coarse=args.smoke, mesher=args.mesher)
         print("  detecting electrode boundary IDs...")
         e1_id, e2_id = detect_elec_bc_ids(mesh)
         print(f"    active BC={e1_id}, return BC={e2_id}")

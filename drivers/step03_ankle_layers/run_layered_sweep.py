@@ -20,11 +20,12 @@ import yaml
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import _common  # noqa: F401,E402
-from pelvistim_fem_b200 import elmer_io, gmsh_io, meshgen, pipeline, sif, sweep  # noqa: E402
+from pelvistim_fem_b200 import elmer_io, gmsh_io, meshgen, pipeline, sif, sizefield_mesher, sweep  # noqa: E402
 
 HERE = Path(__file__).resolve().parent
 RESULTS_DIR = HERE / "results"
 PARAMS_FILE = HERE / "params.yaml"
+_PLANS = {}          # 2-D triangulations of the graded mesher, by pad geometry
 
 
 def load_params(path=PARAMS_FILE):
@@ -67,11 +68,25 @@ def build_mesh(p, t_fat, elec_r, run_dir, coarse=False):
     # (the rim of the footprint is snapped onto the circle on the production meshes only: on the doubled spacing of the smoke
     #  case the snapped rim elements are distorted enough to cost accuracy - pad-current mismatch 5.1 % against 4.3 % unsnapped,
     #  3.0 % against 4.1 % at full resolution; oracle study)
-    n_m = max(3, int(round(t_muscle / lc_bulk)))
-    n_f = max(2, int(round(t_fat / lc_elec)))
-    mesh = meshgen.layered_slab_mesh(Lx, Ly, Lz, ls["t_skin"], t_fat, t_contact or 0.0005, active_xy, return_xy, elec_r,
-                                     shape, n_muscle=n_m, n_fat=n_f, n_skin=2, n_contact=1, h_bulk=lc_bulk,
-                                     h_elec=lc_elec, contact_enabled=contact, snap_rim=not coarse, bone=bone)
+    mesher = mm.get("mesher", "graded")
+    if mesher == "graded":
+        # size-field mesh of the reference's kind (Distance/Threshold law, polygonal pad rim, run_layered_sweep.py:311-323);
+        # the 2-D triangulation depends on the pad size only and is kept between sweep points
+        key = (Lx, Ly, tuple(active_xy), tuple(return_xy), elec_r, shape, lc_elec, lc_bulk)
+        mesh = sizefield_mesher.layered_slab_graded(
+            Lx, Ly, Lz, ls["t_skin"], t_fat, t_contact or 0.0005, active_xy, return_xy, elec_r, shape, lc_elec=lc_elec,
+            lc_bulk=lc_bulk, n_skin=mm.get("n_skin"), n_fat=mm.get("n_fat"), n_contact=mm.get("n_contact", 1),
+            contact_enabled=contact, bone=bone, z_size_factor=float(mm.get("z_size_factor", 1.25)),
+            plan=_PLANS.get(key))
+        _PLANS[key] = mesh.meta["plan"]
+    elif mesher == "kuhn":
+        n_m = max(3, int(round(t_muscle / lc_bulk)))
+        n_f = max(2, int(round(t_fat / lc_elec)))
+        mesh = meshgen.layered_slab_mesh(Lx, Ly, Lz, ls["t_skin"], t_fat, t_contact or 0.0005, active_xy, return_xy, elec_r,
+                                         shape, n_muscle=n_m, n_fat=n_f, n_skin=2, n_contact=1, h_bulk=lc_bulk,
+                                         h_elec=lc_elec, contact_enabled=contact, snap_rim=not coarse, bone=bone)
+    else:
+        raise ValueError(f"mesh.mesher: {mesher!r} (graded | kuhn)")
     # same per-case files as the reference: mesh.msh (gmsh.write, :342-343) then the ElmerGrid 14 2 conversion (:1077)
     names = {(3, 1): "muscle", (3, 2): "fat", (3, 3): "skin", (3, 4): "contact_active", (3, 5): "contact_return", (3, 6): "bone",
              (2, 101): "active", (2, 102): "return", (2, 103): "other"}

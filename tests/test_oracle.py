@@ -113,8 +113,9 @@ def test_metrics_hand_cases():
 
 
 def test_layered_oracle_vs_golden_table(golden):
-    # step03 summary row (t_fat 5 mm, r 10 mm): mesh-dependent golden; the built-in mesh must agree
-    # to discretisation accuracy on the mesh-insensitive columns (few %)
+    # step03 summary row (t_fat 5 mm, r 10 mm) on the size-field mesh: the pad rim is the polygon Gmsh's 1-D mesh of the circle
+    # gives, so the mesh area and the imposed current density equal the reference's to every printed digit; the potential-
+    # driven columns agree to discretisation accuracy, the pad-rim peak - set by the element layout at the rim - to a few %
     import run_layered_sweep as s3
     import tempfile
     from pathlib import Path
@@ -124,22 +125,45 @@ def test_layered_oracle_vs_golden_table(golden):
         mesh, e1, e2, bi = s3.build_mesh(p, 0.005, 0.010, Path(d) / "c", coarse=False)
         e1id, e2id, Aa, Ar = pipeline.detect_elec_bc_ids(mesh, e1, e2, e1[2], e2[2])
         jn = s3.write_sif(Path(d) / "c", e1id, e2id, p, 0.010, bi, elec_area_mesh=Aa)
-        prob = sif.problem_from_sif((Path(d) / "c" / "case.sif").read_text())
+        text = (Path(d) / "c" / "case.sif").read_text()
+        prob = sif.problem_from_sif(text)
     assert (e1id, e2id) == (101, 102)
-    ref = fo.solve_case(mesh, prob.sigma_by_body, prob.dirichlet, prob.neumann, recover="l2")
+    # the whole case.sif - Current Density line with the mesh area in its comment included - is the reference's file
+    assert text == (golden / "step03_tfat0005um_r0010um_case.sif").read_text()
+    ref = fo.solve_case(mesh, prob.sigma_by_body, prob.dirichlet, prob.neumann, recover="lumped")
     row = mo.layered_row(mesh.nodes, mesh.tets, mesh.tris, ref["phi"], ref["J"], p, 0.005, 0.010, e1, e2, bi, jn_used=jn,
                          elec_area_mesh=Aa, return_area_mesh=Ar, e1_id=e1id, e2_id=e2id)
     gold = [r for r in json.load(open(golden / "step03_summary.json")) if r["t_fat_mm"] == 5.0 and r["elec_r_mm"] == 10.0][0]
     assert list(row.keys()) == list(gold.keys())                       # 36 columns, same order
-    for k, tol in (("compliance_V", 0.02), ("roi_mean_J", 0.04), ("roi_mean_E", 0.06), ("elec_area_mesh_cm2", 0.002)):
+    for k, tol in (("compliance_V", 0.005), ("roi_mean_J", 0.04), ("peak_J_skin_with_elec", 0.06), ("roi_mean_E", 0.15),
+                   ("total_current_A", 0.04)):
         assert abs(row[k] - gold[k]) / abs(gold[k]) < tol, (k, row[k], gold[k])
     for k in ("elec_shape", "contact_enabled", "control_mode", "roi_layer", "roi_center_z_mm", "dist_fat_muscle_mm",
-              "active_boundary_id_used", "return_boundary_id_used", "elec_area_cm2", "t_fat_mm", "elec_r_mm"):
+              "active_boundary_id_used", "return_boundary_id_used", "elec_area_cm2", "t_fat_mm", "elec_r_mm",
+              "elec_area_mesh_cm2", "return_area_mesh_cm2", "jn_used"):
         assert row[k] == gold[k], k
     # weak-form KCL is exact even though the nodal-J pad integral is not (run_layered_sweep.py README note)
     react = ref["K_raw"] @ ref["phi"] - ref["b_neumann"]
     I_in = prob.neumann[0][1] * Aa            # the SIF holds Jn with 7 significant digits
     assert abs(react[np.unique(mesh.tris[mesh.bcid == 102])].sum() + I_in) < 1e-12
+
+
+def test_graded_mesher_reproduces_reference_mesh_areas(golden):
+    # the polygon areas of the three pad sizes (tangent pads included) equal the reference's mesh areas, 4 printed digits
+    from pelvistim_fem_b200 import sizefield_mesher as sm, meshgen as mg
+    rows = json.load(open(golden / "step03_summary.json"))
+    for r_mm in (5.0, 10.0, 15.0):
+        gold = [r for r in rows if r["elec_r_mm"] == r_mm][0]
+        m = sm.layered_slab_graded(elec_r=r_mm * 1e-3, t_fat=0.005)
+        assert round(m.meta["area_active"] * 1e4, 4) == gold["elec_area_mesh_cm2"]
+        assert round(m.meta["area_return"] * 1e4, 4) == gold["return_area_mesh_cm2"]
+        assert (m.tri_parent >= 0).all() and (mg.tet_volumes(m.nodes, m.tets) > 0).all()
+        ext, _ = mg.external_faces(m.tets)                 # closed surface: every external face is a tagged triangle
+        key = lambda a: set(map(tuple, np.sort(a, axis=1).tolist()))
+        assert key(ext) <= key(m.tris)
+        vol = 0.08 * 0.06 * 0.04 + (m.meta["area_active"] + m.meta["area_return"]) * 0.0005
+        assert abs(mg.tet_volumes(m.nodes, m.tets).sum() - vol) < 1e-12 * vol * 1e3
+        assert m.meta["triangulation"]["mean_quality"] > 0.95
 
 
 def test_step04_series_law_from_golden(golden):
