@@ -426,6 +426,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — this engine has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa_cpus = engine.bind_host_to_gpu(local_rank)   # before any host buffer of the sweep exists (pinned staging, mesh arrays)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -548,7 +549,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             t_e2e = float(t.item())
         e2e = {"value": world * args.nconf * n_e2e / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "steps": n_e2e}
+               "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
+               "host_cpus_bound_to_gpu_numa_node": None if numa_cpus is None else len(numa_cpus)}
 
     # ---- N > 1 extra: the same mesh as ONE row-partitioned solve over all ranks (config #5, strong scaling) -------
     part = None

@@ -90,6 +90,9 @@ typedef struct ptfem_solve_stats {
 const char* ptfem_last_error(void);
 int ptfem_version(void);
 int ptfem_device_count(int* n);
+/* PCI bus id of a device ("0000:1b:00.0", NUL-terminated, len >= 16): lets the host bind its threads and pinned staging
+ * buffers to the NUMA node the GPU hangs off before it allocates them (engine.bind_host_to_gpu) */
+int ptfem_device_pci_bus_id(int device, char* out, int len);
 
 /* -- context: one per GPU ------------------------------------------------------------------ */
 int ptfem_ctx_create(int device, ptfem_ctx** out);

@@ -184,6 +184,13 @@ int ptfem_device_count(int* n) {
   return PTFEM_OK;
 }
 
+int ptfem_device_pci_bus_id(int device, char* out, int len) {
+  PT_ARG(out && len >= 16, "buffer of at least 16 bytes needed");
+  out[0] = 0;
+  PT_CK(cudaDeviceGetPCIBusId(out, len, device));
+  return PTFEM_OK;
+}
+
 int ptfem_ctx_create(int device, ptfem_ctx** out) {
   PT_ARG(out, "null pointer");
   *out = nullptr;

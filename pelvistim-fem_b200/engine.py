@@ -82,6 +82,7 @@ def load_library():
         "ptfem_last_error": (C.c_char_p, []),
         "ptfem_version": (C.c_int, []),
         "ptfem_device_count": (C.c_int, [P(C.c_int)]),
+        "ptfem_device_pci_bus_id": (C.c_int, [C.c_int, C.c_char_p, C.c_int]),
         "ptfem_ctx_create": (C.c_int, [C.c_int, P(vp)]),
         "ptfem_ctx_destroy": (C.c_int, [vp]),
         "ptfem_ctx_sync": (C.c_int, [vp]),
@@ -164,6 +165,44 @@ def _f64(a):
 
 def _i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_host_to_gpu(device=0):
+    """Restrict the calling process to the CPUs of the NUMA node the GPU is attached to (``/sys/bus/pci/devices/<bus id>/
+    local_cpulist``), so that the host buffers it allocates afterwards - pinned staging for the mesh upload and the phi / J
+    read-back above all - are first touched on that node and the copies do not cross the socket interconnect.  One process
+    per GPU makes this matter: eight ranks stream 1.3 GB per sweep step each.  Returns the CPU set applied, or None when the
+    topology is not exposed (single-node hosts, containers without sysfs) or the set would be empty."""
+    import os
+    L = load_library()
+    buf = C.create_string_buffer(32)
+    if L.ptfem_device_pci_bus_id(int(device), buf, 32) != 0:
+        return None
+    bus = buf.value.decode().lower()
+    try:
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            local = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+    except (OSError, ValueError, AttributeError):
+        return None
+    cpus = local & allowed
+    if not cpus or cpus == allowed:
+        return None
+    try:
+        os.sched_setaffinity(0, cpus)
+    except OSError:
+        return None
+    return sorted(cpus)
 
 
 class Context:

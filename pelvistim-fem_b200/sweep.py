@@ -30,6 +30,8 @@ def assign(n_points, n_gpus):
 def _worker(rank, fn, points, idx, out_q):
     _WORKER["rank"] = rank
     try:
+        from .engine import bind_host_to_gpu
+        bind_host_to_gpu(rank)                # host buffers of this worker live on its GPU's NUMA node
         for i in idx:
             out_q.put((i, fn(points[i]), None))
     except BaseException as e:  # noqa: BLE001 - reported to the parent, which raises
