@@ -135,13 +135,14 @@ def test_layered_oracle_vs_golden_table(golden):
                          elec_area_mesh=Aa, return_area_mesh=Ar, e1_id=e1id, e2_id=e2id)
     gold = [r for r in json.load(open(golden / "step03_summary.json")) if r["t_fat_mm"] == 5.0 and r["elec_r_mm"] == 10.0][0]
     assert list(row.keys()) == list(gold.keys())                       # 36 columns, same order
-    for k, tol in (("compliance_V", 0.005), ("roi_mean_J", 0.04), ("peak_J_skin_with_elec", 0.06), ("roi_mean_E", 0.15),
-                   ("total_current_A", 0.04)):
+    for k, tol in (("compliance_V", 0.012), ("roi_mean_J", 0.04), ("peak_J_skin_with_elec", 0.05), ("roi_mean_E", 0.15),
+                   ("total_current_A", 0.002), ("I_return_A", 0.02)):
         assert abs(row[k] - gold[k]) / abs(gold[k]) < tol, (k, row[k], gold[k])
     for k in ("elec_shape", "contact_enabled", "control_mode", "roi_layer", "roi_center_z_mm", "dist_fat_muscle_mm",
               "active_boundary_id_used", "return_boundary_id_used", "elec_area_cm2", "t_fat_mm", "elec_r_mm",
               "elec_area_mesh_cm2", "return_area_mesh_cm2", "jn_used"):
         assert row[k] == gold[k], k
+    assert row["flux_err"] < 0.03                                      # reference 0.0088
     # weak-form KCL is exact even though the nodal-J pad integral is not (run_layered_sweep.py README note)
     react = ref["K_raw"] @ ref["phi"] - ref["b_neumann"]
     I_in = prob.neumann[0][1] * Aa            # the SIF holds Jn with 7 significant digits
