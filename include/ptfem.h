@@ -115,6 +115,10 @@ int ptfem_mesh_set_coords(ptfem_mesh* m, const double* xyz /*[nn*3]*/);
 
 /* -- K1: CSR pattern + element->nnz map (Elmer's matrix-structure creation). Idempotent. ----- */
 int ptfem_pattern(ptfem_mesh* m, int64_t* nnz);
+/* plan of the window SpMM (multi-RHS product out of shared-memory x windows) built with the pattern: info[0] = 1 if the numbering
+ * allowed one (else the streaming kernel serves every product), [1] tiles, [2] largest window (vector rows), [3] largest tile blob
+ * (bytes), [4] / [5] detected line length / plane size of the numbering; *rows_per_row = window rows staged per matrix row */
+int ptfem_window_plan_info(ptfem_mesh* m, int64_t info[6], double* rows_per_row);
 int ptfem_pattern_get(ptfem_mesh* m, int32_t* rowptr /*[nn+1]*/, int32_t* col /*[nnz]*/);
 int ptfem_e2nnz_get(ptfem_mesh* m, int32_t* e2nnz /*[nt*16]*/);
 

@@ -118,6 +118,7 @@ int make_linsys(ptfem_mesh* m, LinSys& A) {
     A.q_rows = m->q_rows;
     A.q_cap = m->q_cap;
   }
+  if (m->win.valid && m->nvalp == 1) A.win = &m->win;
   if (m->has_rowperm && m->nvalp == 1 && m->pval.p) {
     A.rowid = m->rowid.p;
     A.prowptr = m->prowptr.p;
@@ -144,6 +145,7 @@ int prepare_systems(ptfem_mesh* m) {
       PT_CK(cudaMemsetAsync(m->qval.p + m->qnnz, 0, 8 * sizeof(double), m->ctx->stream));
       PT_TRY(pad_values(m->ctx, m->nn, m->rowptr.p, m->qrowptr.p, m->val_bc.p, m->qval.p));
     }
+    if (m->win.valid && m->nvalp == 1) PT_TRY(window_refresh_values(m, m->val_bc.p));   // the window SpMM's blobs
     if (m->has_rowperm && m->nvalp == 1) {   // the streaming kernel's private copy of the eliminated matrix
       PT_TRY(m->pval.alloc(m->nnz + 8));
       PT_CK(cudaMemsetAsync(m->pval.p + m->nnz, 0, 8 * sizeof(double), m->ctx->stream));
@@ -226,6 +228,9 @@ int ptfem_ctx_create(int device, ptfem_ctx** out) {
     const double w = atof(e);
     if (w > 0.0) c->tune_coarse_weight = w;
   }
+  if (const char* e = getenv("PTFEM_SPMM_WINDOW")) c->tune_window = atoi(e);
+  if (const char* e = getenv("PTFEM_WINDOW_BX")) c->tune_window_bx = atoi(e);
+  if (const char* e = getenv("PTFEM_WINDOW_CTAS")) c->tune_window_ctas = atoi(e);
   if (const char* e = getenv("PTFEM_STREAM_CAP")) c->tune_stream_cap = atoi(e);
   if (const char* e = getenv("PTFEM_STREAM_ROWS")) c->tune_stream_rows = atoi(e);
   if (const char* e = getenv("PTFEM_STREAM_TPR")) c->tune_stream_tpr = atoi(e);
@@ -390,6 +395,19 @@ int ptfem_dist_coarse_finish(ptfem_mesh* m, const double* sums, int64_t n) {
   PT_ARG(m && !m->is_dist && sums, "needs the rank's local mesh and the summed Galerkin data");
   PT_CK(cudaSetDevice(m->ctx->device));
   return coarse_finish_sums(m, sums, n);
+}
+
+int ptfem_window_plan_info(ptfem_mesh* m, int64_t info[6], double* rows_per_row) {
+  PT_ARG(m && info && rows_per_row, "null pointer");
+  if (!m->has_pattern) return set_err(PTFEM_ERR_STATE, "ptfem_pattern has not been called");
+  info[0] = m->win.valid ? 1 : 0;
+  info[1] = m->win.ntiles;
+  info[2] = m->win.wmax;
+  info[3] = m->win.capblob;
+  info[4] = m->win.grid_a;
+  info[5] = m->win.grid_b;
+  *rows_per_row = m->win.window_rows_per_row;
+  return PTFEM_OK;
 }
 
 int ptfem_pattern(ptfem_mesh* m, int64_t* nnz) {

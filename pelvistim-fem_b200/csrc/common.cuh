@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/ptfem.h"
+#include "window.cuh"
 
 namespace ptfem {
 
@@ -116,6 +117,9 @@ struct ptfem_ctx {
   int tune_chain_tail = 0;         // PTFEM_CHAIN_TAIL: partitioned solve runs the replicated smallest grid levels as one block (measured slower: off)
   int tune_pupdate_occ = 4;        // PTFEM_PUPDATE_OCC: resident CTAs per SM the one-pair p-update is compiled for (4, 5, 6)
   int tune_pupdate_np = 1;         // PTFEM_PUPDATE_NP: pairs per trip of the coarse-grid p-update (1: 4 CTAs/SM, 2: 2 CTAs/SM, all loads of both first)
+  int tune_window = 1;             // PTFEM_SPMM_WINDOW: multi-RHS SpMM out of shared-memory x windows where the numbering allows a plan (window.cu); 0 = streaming kernel
+  int tune_window_bx = 0;          // PTFEM_WINDOW_BX: rows of a brick along a line (0 = 16)
+  int tune_window_ctas = 0;        // PTFEM_WINDOW_CTAS: resident CTAs per SM of the window SpMM (0 = as many as fit, at most 4)
   int tune_ctas_per_sm = 0;        // cap on resident CTAs per SM of the streaming SpMV (PTFEM_CTAS_PER_SM)
   std::unordered_map<const void*, size_t> func_smem;  // dynamic shared memory limit raised per kernel
   // NCCL (row-partitioned solves)
@@ -175,6 +179,13 @@ struct ptfem_mesh {
   ptfem::DevBuf<int32_t> qrowptr, qcol;
   ptfem::DevBuf<double> qval;
   int32_t q_rows = 0, q_cap = 0;  // its tile geometry
+  // window SpMM (window.cuh): plan + the buffers it points into
+  WindowPlan win;
+  ptfem::DevBuf<WinTile> win_tiles;
+  ptfem::DevBuf<WinRange> win_ranges;
+  ptfem::DevBuf<unsigned char> win_blob;
+  ptfem::DevBuf<int32_t> win_rowid;   // brick order: processing position -> mesh row
+  ptfem::DevBuf<int32_t> win_rowtile, win_trow0;   // tile of a processing row; first processing row of a tile
   double bb_lo[3] = {0, 0, 0}, bb_hi[3] = {0, 0, 0};
   int32_t stream_rows = 0;        // rows per tile of the streaming SpMV (0 = not usable on this pattern)
   int32_t stream_cap = 0;         // staged entries per tile
@@ -247,6 +258,9 @@ namespace ptfem {
 int exclusive_scan_i32(ptfem_ctx* ctx, const int32_t* in, int32_t* out, int64_t n, int64_t* total);
 int fill_i32(ptfem_ctx* ctx, int32_t* p, int32_t v, int64_t n);
 int fill_f64(ptfem_ctx* ctx, double* p, double v, int64_t n);
+// window.cu: plan of the window SpMM for this pattern (m->win.valid says whether there is one), and its values
+int window_plan_build(ptfem_mesh* m);
+int window_refresh_values(ptfem_mesh* m, const double* val);
 }  // namespace ptfem
 
 #define PT_LAUNCH_CHECK(ctx)                                                                     \

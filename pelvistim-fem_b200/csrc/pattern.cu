@@ -414,6 +414,7 @@ int ptfem_build_pattern(ptfem_mesh* m) {
   PT_LAUNCH_CHECK(ctx);
   PT_CK(cudaMemcpyAsync(&m->max_row, mrl.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   PT_CK(cudaStreamSynchronize(ctx->stream));
+  PT_TRY(window_plan_build(m));    // multi-RHS SpMM out of shared-memory x windows, where the numbering allows it
   m->has_pattern = true;
   return PTFEM_OK;
 }

@@ -356,6 +356,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
   uint32_t done;
   do {
@@ -1046,9 +1049,160 @@ int launch_stream(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y, P
   }
 }
 
+
+// ---- K8b: window SpMM (multi-RHS, one matrix) ---------------------------------------------------------------------
+// Plan in window.cuh / window.cu.  CTA = 64*S/2 consumer threads (S/2 lanes per row, two systems per lane, one row of the
+// tile per lane group) + one producer warp.  The producer brings tile j+STAGES-1 into shared memory while the consumers
+// multiply tile j: lane 0 copies the blob, the lanes share the x ranges (cp.async.bulk, completion on the stage's "full"
+// mbarrier); a stage is handed back through its "empty" mbarrier (one arrival per consumer warp).  Consumers touch global
+// memory only to store y.  Tiles are dealt to the CTAs as one moving front (tile b + j*grid), as in the streaming kernel.
+template <int S>
+constexpr int win_consumers() { return kWinRows * (S / 2); }
+__host__ __device__ inline size_t win_stage_bytes(int S, int capblob, int wmax) { return (size_t)capblob + (((size_t)wmax * S * 8 + 127) & ~(size_t)127); }
+
+template <int S, int STAGES, bool DOT>
+__global__ void __launch_bounds__(kWinRows*(S / 2) + 32)
+    spmm_window_kernel(int32_t ntiles, const WinTile* __restrict__ tiles, const WinRange* __restrict__ ranges,
+                       const unsigned char* __restrict__ blob, int32_t capblob, int32_t wmax, const double* __restrict__ x,
+                       double* __restrict__ y, double* __restrict__ partial, double* __restrict__ scal,
+                       unsigned int* __restrict__ ticket) {
+  constexpr int LPR = S / 2, NC = kWinRows * LPR;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t s_full[STAGES], s_empty[STAGES];
+  const size_t stage_bytes = win_stage_bytes(S, capblob, wmax);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], NC / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int nloc = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  double dot[1][2] = {{0.0, 0.0}};
+  if (tid >= NC) {
+    const int lane = tid - NC;
+    const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
+    for (int j = 0; j < nloc; ++j) {
+      const int st = j % STAGES;
+      if (j >= STAGES) mbar_wait(&s_empty[st], (uint32_t)(((j / STAGES) - 1) & 1));
+      const int64_t t = (int64_t)blockIdx.x + (int64_t)j * gridDim.x;
+      const WinTile ti = tiles[t];
+      unsigned char* sb = smem_raw + (size_t)st * stage_bytes;
+      double* xs = reinterpret_cast<double*>(sb + capblob);
+      if (lane == 0) {
+        mbar_expect_tx(&s_full[st], (uint32_t)ti.blob_bytes + (uint32_t)ti.wrows * (uint32_t)(S * 8));
+        bulk_g2s(sb, blob + ti.blob_off, (uint32_t)ti.blob_bytes, &s_full[st], pol_stream);
+      }
+      __syncwarp();
+      if (lane < ti.nranges) {
+        const WinRange r = ranges[t * kWinMaxRanges + lane];
+        bulk_g2s(xs + (size_t)r.woff * S, x + (size_t)r.xstart * S, (uint32_t)r.nrows * (uint32_t)(S * 8), &s_full[st], pol_keep);
+      }
+    }
+  } else {
+    const int lane = tid % LPR, rr = tid / LPR;
+    for (int j = 0; j < nloc; ++j) {
+      const int st = j % STAGES;
+      const WinTile ti = tiles[(int64_t)blockIdx.x + (int64_t)j * gridDim.x];
+      const unsigned char* sb = smem_raw + (size_t)st * stage_bytes;
+      const double* vs = reinterpret_cast<const double*>(sb);
+      const int32_t* rid = reinterpret_cast<const int32_t*>(sb + (size_t)ti.nnzp * 8);
+      const uint16_t* roff = reinterpret_cast<const uint16_t*>(sb + (size_t)ti.nnzp * 8 + (size_t)((ti.nrows + 3) & ~3) * 4);
+      const uint16_t* ldiag = roff + ((ti.nrows + 1 + 7) & ~7);
+      const uint16_t* ls = ldiag + ((ti.nrows + 7) & ~7);
+      const double* xs = reinterpret_cast<const double*>(sb + capblob);
+      mbar_wait(&s_full[st], (uint32_t)((j / STAGES) & 1));
+      if (rr < ti.nrows) {
+        const int b = roff[rr], e = roff[rr + 1];
+        double2 acc = make_double2(0.0, 0.0);
+#pragma unroll 4
+        for (int k = b; k < e; ++k) {
+          const double a = vs[k];
+          const double2 xv = *reinterpret_cast<const double2*>(xs + (int)ls[k] * S + 2 * lane);
+          acc.x = fma(a, xv.x, acc.x);
+          acc.y = fma(a, xv.y, acc.y);
+        }
+        *reinterpret_cast<double2*>(y + (int64_t)rid[rr] * S + 2 * lane) = acc;
+        if constexpr (DOT) {
+          const double2 xr = *reinterpret_cast<const double2*>(xs + (int)ldiag[rr] * S + 2 * lane);
+          dot[0][0] = fma(acc.x, xr.x, dot[0][0]);
+          dot[0][1] = fma(acc.y, xr.y, dot[0][1]);
+        }
+      }
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&s_empty[st]);
+    }
+  }
+  if constexpr (DOT) {
+    __syncthreads();   // every tile consumed, no copy in flight: the stage memory is free for the reduction
+    double* s_red = reinterpret_cast<double*>(smem_raw);
+    block_sum_by_sys<S, 1>(dot, s_red, partial);
+    if (is_last_block(ticket)) {
+      const double pq = sum_partials<S>(partial, gridDim.x, s_red);
+      if (tid < S) {
+        const double rho = scal[SC_RHO * kMaxSys + tid];
+        scal[SC_PQ * kMaxSys + tid] = pq;
+        scal[SC_ALPHA * kMaxSys + tid] = pq > 0.0 ? rho / pq : 0.0;
+      }
+    }
+  }
+}
+
+// resident CTAs per SM the plan allows at S right-hand sides (0: the window kernel is not used)
+template <int S>
+int window_ctas_per_sm(const ptfem_ctx* ctx, const WindowPlan& P) {
+  const size_t smem = 2 * win_stage_bytes(S, P.capblob, P.wmax);
+  if (smem < (size_t)2 * (win_consumers<S>() + 32) * 8) return 0;       // the reduction borrows the stage memory
+  int per = (int)((size_t)(227 * 1024) / (smem + 1024 + 64));
+  const int by_threads = 2048 / (win_consumers<S>() + 32);
+  if (per > by_threads) per = by_threads;
+  if (per > 4) per = 4;
+  if (ctx->tune_window_ctas > 0 && ctx->tune_window_ctas < per) per = ctx->tune_window_ctas;
+  return per;
+}
+
+template <int S, bool DOT>
+int launch_window(ptfem_ctx* ctx, const LinSys& A, const double* x, double* y, PcgWork* w) {
+  const WindowPlan& P = *A.win;
+  const int per = window_ctas_per_sm<S>(ctx, P);
+  const size_t smem = 2 * win_stage_bytes(S, P.capblob, P.wmax);
+  {
+    const void* fn = reinterpret_cast<const void*>(&spmm_window_kernel<S, 2, DOT>);
+    auto it = ctx->func_smem.find(fn);
+    if (it == ctx->func_smem.end() || it->second < smem) {
+      PT_CK(cudaFuncSetAttribute(spmm_window_kernel<S, 2, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ctx->func_smem[fn] = smem;
+    }
+  }
+  int64_t grid = (int64_t)ctx->sm_count * per;
+  if (grid > P.ntiles) grid = P.ntiles;
+  spmm_window_kernel<S, 2, DOT><<<(int)grid, win_consumers<S>() + 32, smem, ctx->stream>>>(
+      (int32_t)P.ntiles, P.tiles, P.ranges, P.blob, P.capblob, P.wmax, x, y, w ? w->partial.p : nullptr, w ? w->scal.p : nullptr,
+      w ? w->ticket.p : nullptr);
+  PT_LAUNCH_CHECK(ctx);
+  return PTFEM_OK;
+}
+
+// the window kernel serves whole-matrix products of one matrix on 4, 8 or 16 right-hand sides, when at least two CTAs fit an SM
+template <int S>
+bool use_window(const ptfem_ctx* ctx, const LinSys& A) {
+  if constexpr (S == 4 || S == 8 || S == 16) {
+    return A.win && A.win->valid && A.row0 == 0 && A.peer.nloc == 0 && !A.rowid && A.win->ntiles < 2147483647LL &&
+           window_ctas_per_sm<S>(ctx, *A.win) >= 2;
+  }
+  return false;
+}
+
 template <int S, int VS>
 int spmv_sv(ptfem_ctx* ctx, const LinSys& A, int variant, const double* x, double* y, PcgWork* w, bool dot) {
   if constexpr (VS == 1) {
+    if constexpr (S == 4 || S == 8 || S == 16) {
+      if ((variant == PTFEM_SPMV_STREAM || variant == PTFEM_SPMV_STREAM1) && use_window<S>(ctx, A))
+        return dot ? launch_window<S, true>(ctx, A, x, y, w) : launch_window<S, false>(ctx, A, x, y, w);
+    }
     if (variant == PTFEM_SPMV_STREAM || variant == PTFEM_SPMV_STREAM1) {
       const int stages = variant == PTFEM_SPMV_STREAM ? ctx->tune_stream_stages : ctx->tune_stream_stages + 1;
       return dot ? launch_stream<S, true>(ctx, A, x, y, w, stages, ctx->tune_stream_tpr)

@@ -39,6 +39,8 @@ struct LinSys {
   // through peer.halo[c - nloc] (a pointer into a neighbour GPU's vector) after the neighbours' ready flags
   // (peer.flags, local memory) have reached *peer.wait
   PeerGather peer;
+  // window SpMM plan (values already refreshed from val), or nullptr
+  const WindowPlan* win = nullptr;
   // two-level preconditioner (PTFEM_PRECOND_TWOLEVEL): prepared coarse spaces + what their kernels read
   CoarseSpace* coarse = nullptr;
   int64_t row0 = 0;              // the system is rows [row0, row0+nn) of the arrays (row-range SpMV)

@@ -1,0 +1,377 @@
+// window.cu — builds the plan of the window SpMM (window.cuh) from the CSR pattern, and refreshes its values.
+//
+// Tiles: the rows in "brick order", cut into runs of 64.  Brick order needs no geometry: when the numbering is that of a
+// structured grid (row r and r-1 adjacent along lines of a rows, lines stacked in planes of b rows) a brick is 16 x 2 x 2
+// nodes - four runs of 16 consecutive rows - and its window 14 ranges of ~18 consecutive vector rows (3.8 window rows per
+// row; 2.3-3.0 for fatter bricks, but more and shorter ranges, which the copy engine likes less: measured,
+// profiles/r02_proto_window2.txt).  a and b are read off the matrix; the window of every tile is computed from its actual
+// columns, so a wrong guess costs speed, never correctness, and a plan whose windows come out too large is dropped
+// (the streaming kernel then runs as before).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+#include "window.cuh"
+
+namespace ptfem {
+namespace {
+
+__device__ __forceinline__ bool has_edge(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t r, int64_t c) {
+  int32_t lo = rowptr[r], hi = rowptr[r + 1];
+  while (lo < hi) {
+    const int32_t mid = (lo + hi) >> 1;
+    const int32_t v = col[mid];
+    if (v == c) return true;
+    if (v < c) lo = mid + 1; else hi = mid;
+  }
+  return false;
+}
+
+// smallest r in [step, limit) with r % step == 0 and no matrix entry (r, r - step)
+__global__ void first_break_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t limit, int64_t step,
+                                   unsigned long long* __restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1;
+  const int64_t r = k * step;
+  if (r >= limit) return;
+  if (!has_edge(rowptr, col, r, r - step)) atomicMin(out, (unsigned long long)r);
+}
+
+// key = brick * 64 + position inside the brick.  Every axis is cut into ceil(n / width) parts of nearly equal size (no sliver
+// bricks at the far faces), so a brick has at most bx*by*bz = 64 rows and is one tile.
+__global__ void brick_keys_kernel(int64_t nn, int64_t a, int64_t b, int bx, int by, int bz, int64_t nz, unsigned long long* __restrict__ key,
+                                  int32_t* __restrict__ id) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nn) return;
+  const int64_t ny = b / a;
+  const int64_t z = r / b, rem = r % b, y = rem / a, x = rem % a;
+  const int64_t nxb = (a + bx - 1) / bx, nyb = (ny + by - 1) / by, nzb = (nz + bz - 1) / bz;
+  const int64_t xb = x * nxb / a, yb = y * nyb / ny, zb = z * nzb / nz;
+  const int64_t x0 = (xb * a + nxb - 1) / nxb, y0 = (yb * ny + nyb - 1) / nyb, z0 = (zb * nz + nzb - 1) / nzb;
+  const int64_t brick = (zb * nyb + yb) * nxb + xb;
+  const int64_t local = ((z - z0) * by + (y - y0)) * bx + (x - x0);
+  key[r] = (unsigned long long)(brick * (int64_t)kWinRows + local);
+  id[r] = (int32_t)r;
+}
+
+// tile starts in the sorted order: a new brick begins
+__global__ void tile_flags_kernel(int64_t nn, const unsigned long long* __restrict__ key, int32_t* __restrict__ flag) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nn) return;
+  flag[j] = (j == 0 || key[j] / kWinRows != key[j - 1] / kWinRows) ? 1 : 0;
+}
+// rowtile[j] = tile of processing row j (inclusive count of starts - 1); trow0[tile] = its first processing row
+__global__ void tile_rows_kernel(int64_t nn, const int32_t* __restrict__ flag, const int32_t* __restrict__ excl, int32_t* __restrict__ rowtile,
+                                 int32_t* __restrict__ trow0, int64_t ntiles) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nn) return;
+  const int32_t t = excl[j] + flag[j] - 1;
+  rowtile[j] = t;
+  if (flag[j]) trow0[t] = (int32_t)j;
+  if (j == 0) trow0[ntiles] = (int32_t)nn;
+}
+
+// blob size of every tile, in units of 16 bytes
+__global__ void tile_units_kernel(int64_t ntiles, const int32_t* __restrict__ trow0, const int32_t* __restrict__ rowptr,
+                                  const int32_t* __restrict__ rowid, int32_t* __restrict__ units) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  const int64_t r0 = trow0[t];
+  const int R = trow0[t + 1] - trow0[t];
+  int nnz = 0;
+  for (int rr = 0; rr < R; ++rr) {
+    const int32_t g = rowid[r0 + rr];
+    nnz += rowptr[g + 1] - rowptr[g];
+  }
+  units[t] = win_blob_bytes(R, (nnz + 7) & ~7) / 16;
+}
+
+constexpr int kPlanThreads = 256;
+constexpr int kMaxSpanWords = 8192;      // the columns of one tile span at most 256 k vector rows
+
+// one CTA per tile: bitmap of the tile's columns over [cmin, cmax] -> ranges (runs of set bits), window index of a column =
+// number of set bits below it; writes the tile record, its ranges and the index sections of its blob
+__global__ void __launch_bounds__(kPlanThreads)
+    build_tiles_kernel(const int32_t* __restrict__ trow0, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                       const int32_t* __restrict__ rowid, const int32_t* __restrict__ unit_off, WinTile* __restrict__ tiles,
+                       WinRange* __restrict__ ranges, unsigned char* __restrict__ blob, int32_t* __restrict__ stats /*[4]: fail, wmax, rmax, bmax*/,
+                       unsigned long long* __restrict__ wsum) {
+  extern __shared__ uint32_t s_dyn[];
+  uint32_t* bits = s_dyn;                     // [kMaxSpanWords]
+  uint32_t* wpre = s_dyn + kMaxSpanWords;     // [kMaxSpanWords] set bits below word w
+  __shared__ int32_t s_rid[kWinRows], s_off[kWinRows + 1];
+  __shared__ int32_t s_min, s_max;
+  __shared__ uint32_t s_cnt[kPlanThreads], s_starts[kPlanThreads];
+  const int tid = threadIdx.x;
+  const int64_t t = blockIdx.x;
+  const int64_t r0 = trow0[t];
+  const int R = trow0[t + 1] - trow0[t];
+  if (tid == 0) { s_min = 2147483647; s_max = -1; }
+  __syncthreads();
+  if (tid < R) {
+    const int32_t g = rowid[r0 + tid];
+    s_rid[tid] = g;
+    const int32_t b = rowptr[g], e = rowptr[g + 1];
+    s_off[tid + 1] = e - b;
+    if (e > b) { atomicMin(&s_min, col[b]); atomicMax(&s_max, col[e - 1]); }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    s_off[0] = 0;
+    for (int rr = 0; rr < R; ++rr) s_off[rr + 1] += s_off[rr];
+  }
+  __syncthreads();
+  const int nnz = s_off[R];
+  const int nnzp = (nnz + 7) & ~7;
+  const int64_t cmin = s_min, span = (int64_t)s_max - s_min + 1;
+  const int nwords = (int)((span + 31) >> 5);
+  if (nnz == 0 || nwords > kMaxSpanWords || nnz > 65528) {
+    if (tid == 0) atomicExch(&stats[0], 1);
+    return;
+  }
+  for (int w = tid; w < nwords; w += kPlanThreads) bits[w] = 0u;
+  __syncthreads();
+  // 4 lanes per row set the bits
+  for (int rr = tid >> 2; rr < R; rr += kPlanThreads / 4) {
+    const int32_t b = rowptr[s_rid[rr]];
+    const int n = s_off[rr + 1] - s_off[rr];
+    for (int k = tid & 3; k < n; k += 4) {
+      const int64_t c = col[b + k] - cmin;
+      atomicOr(&bits[c >> 5], 1u << (c & 31));
+    }
+  }
+  __syncthreads();
+  // per-thread chunk of words: set bits and run starts, then exclusive scans over the 256 chunks
+  const int chunk = (nwords + kPlanThreads - 1) / kPlanThreads;
+  const int w0 = min(nwords, tid * chunk), w1 = min(nwords, w0 + chunk);
+  uint32_t cnt = 0, starts = 0;
+  for (int w = w0; w < w1; ++w) {
+    const uint32_t v = bits[w];
+    const uint32_t prev = w > 0 ? bits[w - 1] >> 31 : 0u;
+    cnt += __popc(v);
+    starts += __popc(v & ~((v << 1) | prev));
+  }
+  s_cnt[tid] = cnt;
+  s_starts[tid] = starts;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t a = 0, b = 0;
+    for (int i = 0; i < kPlanThreads; ++i) {
+      const uint32_t c = s_cnt[i], s = s_starts[i];
+      s_cnt[i] = a; s_starts[i] = b;
+      a += c; b += s;
+    }
+    s_min = (int32_t)a;     // window rows
+    s_max = (int32_t)b;     // ranges
+  }
+  __syncthreads();
+  const int wrows = s_min, nranges = s_max;
+  if (nranges > kWinMaxRanges || wrows > 65535) {
+    if (tid == 0) atomicExch(&stats[0], 1);
+    return;
+  }
+  {
+    uint32_t pre = s_cnt[tid], ridx = s_starts[tid];
+    for (int w = w0; w < w1; ++w) {
+      const uint32_t v = bits[w];
+      const uint32_t prev = w > 0 ? bits[w - 1] >> 31 : 0u;
+      wpre[w] = pre;
+      uint32_t st = v & ~((v << 1) | prev);
+      while (st) {
+        const int bit = __ffs(st) - 1;
+        st &= st - 1;
+        WinRange rg;
+        rg.xstart = (int32_t)(cmin + ((int64_t)w << 5) + bit);
+        rg.woff = (int32_t)(pre + __popc(v & ((1u << bit) - 1u)));
+        rg.nrows = 0;      // filled below from the next range's offset
+        rg.pad = 0;
+        ranges[t * kWinMaxRanges + ridx] = rg;
+        ++ridx;
+      }
+      pre += __popc(v);
+    }
+  }
+  __syncthreads();
+  __threadfence_block();
+  if (tid < nranges) {
+    WinRange* rg = ranges + t * kWinMaxRanges;
+    const int next = tid + 1 < nranges ? rg[tid + 1].woff : wrows;
+    rg[tid].nrows = next - rg[tid].woff;
+  }
+  // blob index sections
+  const int64_t boff = (int64_t)unit_off[t] * 16;
+  const int bbytes = win_blob_bytes(R, nnzp);
+  unsigned char* p = blob + boff;
+  int32_t* brid = reinterpret_cast<int32_t*>(p + (size_t)nnzp * 8);
+  uint16_t* broff = reinterpret_cast<uint16_t*>(p + (size_t)nnzp * 8 + (size_t)((R + 3) & ~3) * 4);
+  uint16_t* bdiag = broff + ((R + 1 + 7) & ~7);
+  uint16_t* blcol = bdiag + ((R + 7) & ~7);
+  auto local_of = [&](int64_t c) {
+    const int64_t d = c - cmin;
+    const uint32_t v = bits[d >> 5];
+    return (uint16_t)(wpre[d >> 5] + __popc(v & ((1u << (d & 31)) - 1u)));
+  };
+  if (tid <= R) broff[tid] = (uint16_t)s_off[tid];
+  if (tid < R) { brid[tid] = s_rid[tid]; bdiag[tid] = local_of(s_rid[tid]); }
+  for (int rr = tid >> 2; rr < R; rr += kPlanThreads / 4) {
+    const int32_t b = rowptr[s_rid[rr]];
+    const int o = s_off[rr], n = s_off[rr + 1] - o;
+    for (int k = tid & 3; k < n; k += 4) blcol[o + k] = local_of(col[b + k]);
+  }
+  if (tid == 0) {
+    WinTile ti;
+    ti.blob_off = boff; ti.blob_bytes = bbytes; ti.nrows = R; ti.nnzp = nnzp; ti.nranges = nranges; ti.wrows = wrows; ti.pad = 0;
+    tiles[t] = ti;
+    atomicMax(&stats[1], wrows);
+    atomicMax(&stats[2], nranges);
+    atomicMax(&stats[3], bbytes);
+    atomicAdd(wsum, (unsigned long long)wrows);
+  }
+}
+
+// values of the (eliminated) matrix into the blobs: 8 lanes per tile row
+__global__ void window_values_kernel(int64_t nn, const int32_t* __restrict__ rowptr, const double* __restrict__ val,
+                                     const int32_t* __restrict__ rowtile, const int32_t* __restrict__ trow0,
+                                     const WinTile* __restrict__ tiles, unsigned char* __restrict__ blob) {
+  const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;   // processing-order row
+  const int lane = threadIdx.x & 7;
+  if (j >= nn) return;
+  const int32_t t = rowtile[j];
+  const WinTile ti = tiles[t];
+  const int rr = (int)(j - trow0[t]);
+  unsigned char* p = blob + ti.blob_off;
+  const int32_t* brid = reinterpret_cast<const int32_t*>(p + (size_t)ti.nnzp * 8);
+  const uint16_t* broff = reinterpret_cast<const uint16_t*>(p + (size_t)ti.nnzp * 8 + (size_t)((ti.nrows + 3) & ~3) * 4);
+  double* bval = reinterpret_cast<double*>(p);
+  const int32_t src = rowptr[brid[rr]];
+  const int o = broff[rr], n = broff[rr + 1] - o;
+  for (int k = lane; k < n; k += 8) bval[o + k] = val[src + k];
+}
+
+}  // namespace
+
+int window_plan_build(ptfem_mesh* m) {
+  ptfem_ctx* ctx = m->ctx;
+  const int64_t nn = m->nn;
+  m->win = WindowPlan();
+  if (!ctx->tune_window || nn < 65536 || nn > 2000000000LL || m->has_rowperm) return PTFEM_OK;
+  // structure of the numbering: line length a, plane size b
+  DevBuf<unsigned long long> brk;
+  PT_TRY(brk.alloc(1));
+  auto first_break = [&](int64_t step, int64_t limit, int64_t* out) -> int {
+    const unsigned long long none = ~0ull;
+    PT_CK(cudaMemcpyAsync(brk.p, &none, sizeof none, cudaMemcpyHostToDevice, ctx->stream));
+    const int64_t n = (limit + step - 1) / step;
+    first_break_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(m->rowptr.p, m->col.p, limit, step, brk.p);
+    PT_LAUNCH_CHECK(ctx);
+    unsigned long long h = 0;
+    PT_CK(cudaMemcpyAsync(&h, brk.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    PT_CK(cudaStreamSynchronize(ctx->stream));
+    *out = h == none ? 0 : (int64_t)h;
+    return PTFEM_OK;
+  };
+  int64_t a = 0, b = 0;
+  PT_TRY(first_break(1, std::min<int64_t>(nn, 1 << 22), &a));
+  if (a < 8) return PTFEM_OK;                       // no lines of consecutive rows: the window of a tile would be scattered
+  PT_TRY(first_break(a, nn, &b));
+  if (b < 2 * a || b % a != 0) b = 0;
+  m->win.grid_a = (int32_t)std::min<int64_t>(a, 2147483647);
+  m->win.grid_b = (int32_t)std::min<int64_t>(b, 2147483647);
+  // brick order; one tile per brick
+  PT_TRY(m->win_rowid.alloc(nn));
+  PT_TRY(m->win_rowtile.alloc(nn));
+  int64_t ntiles = 0;
+  {
+    DevBuf<unsigned long long> key, key2;
+    DevBuf<int32_t> id, flag, excl;
+    PT_TRY(key.alloc(nn));
+    PT_TRY(key2.alloc(nn));
+    PT_TRY(id.alloc(nn));
+    const int bx = ctx->tune_window_bx > 0 ? ctx->tune_window_bx : 16;
+    int by = 2, bz = 2;
+    int64_t bb = b;
+    if (b == 0) { bb = a * ((nn + a - 1) / a); by = 4; bz = 1; }     // lines only: bricks of one "plane"
+    if (bx * by * bz != kWinRows) { by = kWinRows / bx / bz; if (by < 1) by = 1; }
+    if (bx * by * bz > kWinRows) return PTFEM_OK;
+    const int64_t nz = (nn + bb - 1) / bb;
+    brick_keys_kernel<<<ceil_div(nn, 256), 256, 0, ctx->stream>>>(nn, a, bb, bx, by, bz, nz, key.p, id.p);
+    PT_LAUNCH_CHECK(ctx);
+    const unsigned long long kmax = (unsigned long long)(((a + bx - 1) / bx) * ((bb / a + by - 1) / by) * ((nz + bz - 1) / bz)) * kWinRows;
+    int bits = 1;
+    while (bits < 64 && (1ull << bits) <= kmax) ++bits;
+    size_t tmp_bytes = 0;
+    PT_CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key.p, key2.p, id.p, m->win_rowid.p, (int)nn, 0, bits, ctx->stream));
+    DevBuf<uint8_t> tmp;
+    PT_TRY(tmp.alloc(tmp_bytes));
+    PT_CK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, key.p, key2.p, id.p, m->win_rowid.p, (int)nn, 0, bits, ctx->stream));
+    ctx->launches += 2;
+    PT_TRY(flag.alloc(nn + 1));
+    PT_TRY(excl.alloc(nn + 1));
+    tile_flags_kernel<<<ceil_div(nn, 256), 256, 0, ctx->stream>>>(nn, key2.p, flag.p);
+    PT_LAUNCH_CHECK(ctx);
+    PT_TRY(exclusive_scan_i32(ctx, flag.p, excl.p, nn, &ntiles));
+    PT_TRY(m->win_trow0.alloc(ntiles + 1));
+    tile_rows_kernel<<<ceil_div(nn, 256), 256, 0, ctx->stream>>>(nn, flag.p, excl.p, m->win_rowtile.p, m->win_trow0.p, ntiles);
+    PT_LAUNCH_CHECK(ctx);
+  }
+  // blob offsets
+  DevBuf<int32_t> units, unit_off;
+  PT_TRY(units.alloc(ntiles + 1));
+  PT_TRY(unit_off.alloc(ntiles + 1));
+  tile_units_kernel<<<ceil_div(ntiles, 128), 128, 0, ctx->stream>>>(ntiles, m->win_trow0.p, m->rowptr.p, m->win_rowid.p, units.p);
+  PT_LAUNCH_CHECK(ctx);
+  int64_t total_units = 0;
+  PT_TRY(exclusive_scan_i32(ctx, units.p, unit_off.p, ntiles, &total_units));
+  const int64_t blob_bytes = total_units * 16;
+  PT_TRY(m->win_tiles.alloc(ntiles));
+  PT_TRY(m->win_ranges.alloc(ntiles * kWinMaxRanges));
+  PT_TRY(m->win_blob.alloc(blob_bytes + 256));
+  PT_CK(cudaMemsetAsync(m->win_blob.p, 0, blob_bytes + 256, ctx->stream));
+  DevBuf<int32_t> stats;
+  DevBuf<unsigned long long> wsum;
+  PT_TRY(stats.alloc(4));
+  PT_TRY(wsum.alloc(1));
+  PT_TRY(fill_i32(ctx, stats.p, 0, 4));
+  PT_CK(cudaMemsetAsync(wsum.p, 0, sizeof(unsigned long long), ctx->stream));
+  const size_t dyn = (size_t)kMaxSpanWords * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PT_CK(cudaFuncSetAttribute(build_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    attr_set = true;
+  }
+  build_tiles_kernel<<<(unsigned)ntiles, kPlanThreads, dyn, ctx->stream>>>(m->win_trow0.p, m->rowptr.p, m->col.p, m->win_rowid.p, unit_off.p,
+                                                                          m->win_tiles.p, m->win_ranges.p, m->win_blob.p, stats.p, wsum.p);
+  PT_LAUNCH_CHECK(ctx);
+  int32_t h[4] = {0, 0, 0, 0};
+  unsigned long long hw = 0;
+  PT_CK(cudaMemcpyAsync(h, stats.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  PT_CK(cudaMemcpyAsync(&hw, wsum.p, sizeof hw, cudaMemcpyDeviceToHost, ctx->stream));
+  PT_CK(cudaStreamSynchronize(ctx->stream));
+  const double wpr = (double)hw / (double)nn;
+  // a window worth having: it fits two stages of four CTAs per SM at 8 right-hand sides and re-reads x less than the
+  // streaming kernel's L1 misses do
+  const bool ok = h[0] == 0 && h[1] > 0 && h[1] <= 640 && wpr <= 6.0;
+  if (!ok) {
+    m->win_tiles.release(); m->win_ranges.release(); m->win_blob.release(); m->win_rowid.release();
+    m->win_rowtile.release(); m->win_trow0.release();
+    return PTFEM_OK;
+  }
+  m->win.valid = true;
+  m->win.ntiles = ntiles;
+  m->win.wmax = h[1];
+  m->win.capblob = (h[3] + 127) & ~127;
+  m->win.window_rows_per_row = wpr;
+  m->win.tiles = m->win_tiles.p;
+  m->win.ranges = m->win_ranges.p;
+  m->win.blob = m->win_blob.p;
+  m->win.blob_bytes = blob_bytes;
+  return PTFEM_OK;
+}
+
+int window_refresh_values(ptfem_mesh* m, const double* val) {
+  if (!m->win.valid) return PTFEM_OK;
+  window_values_kernel<<<ceil_div(m->nn * 8, 256), 256, 0, m->ctx->stream>>>(m->nn, m->rowptr.p, val, m->win_rowtile.p, m->win_trow0.p,
+                                                                                 m->win.tiles, m->win.blob);
+  PT_LAUNCH_CHECK(m->ctx);
+  return PTFEM_OK;
+}
+
+}  // namespace ptfem

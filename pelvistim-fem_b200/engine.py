@@ -92,6 +92,7 @@ def load_library():
         "ptfem_mesh_destroy": (C.c_int, [vp]),
         "ptfem_mesh_set_coords": (C.c_int, [vp, vp]),
         "ptfem_pattern": (C.c_int, [vp, P(i64)]),
+        "ptfem_window_plan_info": (C.c_int, [vp, P(i64), P(dbl)]),
         "ptfem_pattern_get": (C.c_int, [vp, vp, vp]),
         "ptfem_e2nnz_get": (C.c_int, [vp, vp]),
         "ptfem_assemble": (C.c_int, [vp, i32, vp, vp, i32]),
@@ -294,6 +295,14 @@ class DeviceMesh:
         self._ck(self.lib.ptfem_pattern(self._h, C.byref(n)))
         self.nnz = n.value
         return self.nnz
+
+    def window_plan(self):
+        """Plan of the window SpMM for this pattern: dict(valid, tiles, wmax, capblob, line, plane, rows_per_row)."""
+        info = (C.c_int64 * 6)()
+        rpr = C.c_double()
+        self._ck(self.lib.ptfem_window_plan_info(self._h, info, C.byref(rpr)))
+        return dict(valid=bool(info[0]), tiles=int(info[1]), wmax=int(info[2]), capblob=int(info[3]), line=int(info[4]),
+                    plane=int(info[5]), rows_per_row=rpr.value)
 
     def get_pattern(self):
         nnz = self.pattern()

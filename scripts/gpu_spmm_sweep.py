@@ -12,13 +12,14 @@ configs = [dict(MORTON=0), dict(MORTON=1), dict(MORTON=1, STREAM_ROWS=32), dict(
 if len(sys.argv) > 2:
     configs = [eval("dict(" + a + ")") for a in sys.argv[2:]]
 for c in configs:
-    for k in ("XPREFETCH", "STREAM_ROWS", "INTERLEAVE", "STREAM_STAGES", "MORTON", "STREAM_CAP", "CTAS_PER_SM"):
+    for k in ("XPREFETCH", "STREAM_ROWS", "INTERLEAVE", "STREAM_STAGES", "MORTON", "STREAM_CAP", "CTAS_PER_SM", "SPMM_WINDOW", "WINDOW_BX", "WINDOW_CTAS"):
         os.environ.pop("PTFEM_" + k, None)
     for k, v in c.items():
         os.environ["PTFEM_" + k] = str(v)
     ctx = engine.Context(0)
     dm = ctx.mesh(mesh.nodes, mesh.tets, mesh.region, mesh.tris, mesh.bcid)
     nnz = dm.pattern()
+    print('window plan', dm.window_plan(), flush=True)
     dm.assemble(bench.SIGMA); dm.bc_reset(8)
     for k, cf in enumerate(confs):
         dm.neumann_tris(cf["tris"], bench.I_INJECT / cf["area"], rhs=k)

@@ -644,6 +644,54 @@ def test_size_L_matches_cpu_oracle(gpu_ctx):
     del _ORACLE_CACHE["L"]
 
 
+# -- window SpMM (multi-RHS product out of shared-memory x windows): same answers as the streaming kernel and as the oracle ----
+@pytest.mark.parametrize("nrhs", [4, 8, 16])
+def test_window_spmm_matches_streaming_kernel_and_oracle(monkeypatch, nrhs):
+    m, phi_o, _ = _c_oracle_solution("M")
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("PTFEM_SPMM_WINDOW", flag)
+        ctx = engine.Context(0)
+        dm = dm_for(ctx, m)
+        dm.pattern()
+        plan = dm.window_plan()
+        assert plan["valid"] == (flag == "1")
+        if plan["valid"]:          # the slab's structured numbering is recognised: lines of nx rows, planes of nx*ny
+            nx, ny, _ = m.meta["grid"] if "grid" in m.meta else (plan["line"], plan["plane"] // plan["line"], 0)
+            assert plan["line"] == nx and plan["plane"] == nx * ny and plan["rows_per_row"] < 4.5 and plan["wmax"] <= 400
+        dm.assemble(SIGMA5).bc_reset(nrhs)
+        for k in range(nrhs):
+            dm.neumann(101, 15.975 * (1.0 + 0.25 * k), rhs=k)
+        dm.dirichlet(102, 0.0)
+        phi = dm.solve(rtol=1e-11, precond=engine.PRECOND_TWOLEVEL)
+        out[flag] = (phi.copy(), dm.last_stats["iterations"])
+        assert dm.last_stats["converged"] == 1
+        for k in range(nrhs):
+            assert rel(phi[k], phi_o * (1.0 + 0.25 * k)) < TOL_PHI, (flag, k)
+        dm.close()
+        ctx.close()
+    assert abs(out["1"][1] - out["0"][1]) <= 1                    # same Krylov iteration, summation order aside
+    assert rel(out["1"][0], out["0"][0]) < 1e-9
+
+
+def test_window_plan_is_dropped_where_the_numbering_has_no_lines(gpu_ctx):
+    # shuffled numbering (the Morton copy serves it) and an unstructured Delaunay mesh: no plan, the streaming / vector kernels run
+    m = meshgen.synth_slab("M")
+    perm = np.random.default_rng(5).permutation(m.nn)
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(m.nn)
+    ms = meshgen.TetMesh(m.nodes[perm], inv[m.tets].astype(np.int32), m.region, inv[m.tris].astype(np.int32), m.bcid)
+    dm = dm_for(gpu_ctx, ms)
+    dm.pattern()
+    assert not dm.window_plan()["valid"]
+    dm.close()
+    md = meshgen.delaunay_box_mesh(npts=70000, seed=1)
+    dm = dm_for(gpu_ctx, md)
+    dm.pattern()
+    assert not dm.window_plan()["valid"]
+    dm.close()
+
+
 # -- the drop-in boundary itself: `ElmerSolver case.sif` in a case directory -----------------------------------------
 def test_elmersolver_shim_subprocess(tmp_path):
     import subprocess, sys
