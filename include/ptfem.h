@@ -108,6 +108,12 @@ int ptfem_ctx_stream(ptfem_ctx* ctx, void** stream);
 int ptfem_mesh_create(ptfem_ctx* ctx, int64_t nn, const double* xyz /*[nn*3]*/, int64_t nt,
                       const int32_t* tets /*[nt*4]*/, const int32_t* region /*[nt]*/, int64_t nb,
                       const int32_t* tris /*[nb*3]*/, const int32_t* bcid /*[nb]*/, ptfem_mesh** out);
+/* same, but returns as soon as the copies are queued on an upload stream: the host arrays (pinned memory, or the call
+ * degenerates to a blocking copy) must stay untouched until ptfem_pattern(), which waits for the upload and validates the
+ * indices.  Lets a sweep upload the mesh of point k+1 while point k is being solved. */
+int ptfem_mesh_create_async(ptfem_ctx* ctx, int64_t nn, const double* xyz /*[nn*3]*/, int64_t nt,
+                            const int32_t* tets /*[nt*4]*/, const int32_t* region /*[nt]*/, int64_t nb,
+                            const int32_t* tris /*[nb*3]*/, const int32_t* bcid /*[nb]*/, ptfem_mesh** out);
 int ptfem_mesh_destroy(ptfem_mesh* m);
 /* geometry change on fixed topology (node displacement; reference example:
  * run_layered_sweep.py:329-340): keeps the pattern, recomputes element geometry factors. */

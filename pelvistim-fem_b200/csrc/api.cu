@@ -210,6 +210,7 @@ int ptfem_ctx_create(int device, ptfem_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   PT_CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   PT_CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  PT_CK(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
   PT_CK(cudaEventCreateWithFlags(&c->ev_j_ready, cudaEventDisableTiming));
   PT_CK(cudaEventCreateWithFlags(&c->ev_j_copied, cudaEventDisableTiming));
   PT_CK(cudaEventCreateWithFlags(&c->ev_phi_ready, cudaEventDisableTiming));
@@ -250,6 +251,7 @@ int ptfem_ctx_destroy(ptfem_ctx* ctx) {
   if (ctx->ev_j_copied) cudaEventDestroy(ctx->ev_j_copied);
   if (ctx->ev_phi_ready) cudaEventDestroy(ctx->ev_phi_ready);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+  if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   delete ctx;
   dev_cache_flush();
@@ -276,8 +278,31 @@ int ptfem_ctx_stream(ptfem_ctx* ctx, void** stream) {
   return PTFEM_OK;
 }
 
-int ptfem_mesh_create(ptfem_ctx* ctx, int64_t nn, const double* xyz, int64_t nt, const int32_t* tets, const int32_t* region,
-                      int64_t nb, const int32_t* tris, const int32_t* bcid, ptfem_mesh** out) {
+namespace {
+// device-side validation of the uploaded index arrays + bounding box; ends an asynchronous upload
+int mesh_finish_upload(ptfem_mesh* m) {
+  if (!m->upload_pending) return PTFEM_OK;
+  ptfem_ctx* ctx = m->ctx;
+  m->upload_pending = false;
+  PT_CK(cudaStreamWaitEvent(ctx->stream, m->ev_upload, 0));
+  // (a host pass over 80 M indices cost more than the upload itself)
+  DevBuf<unsigned long long> bad;
+  PT_TRY(bad.alloc(2));
+  PT_CK(cudaMemsetAsync(bad.p, 0xff, 2 * sizeof(unsigned long long), ctx->stream));
+  if (m->nt > 0) index_check_kernel<<<ceil_div(m->nt * 4, 256), 256, 0, ctx->stream>>>(m->tets.p, m->nt * 4, m->nn, bad.p);
+  if (m->nb > 0) index_check_kernel<<<ceil_div(m->nb * 3, 256), 256, 0, ctx->stream>>>(m->tris.p, m->nb * 3, m->nn, bad.p + 1);
+  ctx->launches += (m->nt > 0) + (m->nb > 0);
+  unsigned long long hb[2];
+  PT_CK(cudaMemcpyAsync(hb, bad.p, sizeof hb, cudaMemcpyDeviceToHost, ctx->stream));
+  PT_CK(cudaStreamSynchronize(ctx->stream));
+  if (hb[0] != ~0ull) return set_err(PTFEM_ERR_ARG, "tet %llu refers to a node outside 0..%lld", hb[0] / 4, (long long)m->nn - 1);
+  if (hb[1] != ~0ull) return set_err(PTFEM_ERR_ARG, "boundary triangle %llu refers to a node outside 0..%lld", hb[1] / 3, (long long)m->nn - 1);
+  return device_bbox(m);
+}
+}  // namespace
+
+int ptfem_mesh_create_async(ptfem_ctx* ctx, int64_t nn, const double* xyz, int64_t nt, const int32_t* tets, const int32_t* region,
+                            int64_t nb, const int32_t* tris, const int32_t* bcid, ptfem_mesh** out) {
   PT_ARG(ctx && out, "null pointer");
   *out = nullptr;
   PT_ARG(nn > 0 && nt >= 0 && nb >= 0, "negative or zero sizes");
@@ -290,46 +315,41 @@ int ptfem_mesh_create(ptfem_ctx* ctx, int64_t nn, const double* xyz, int64_t nt,
   m->nt = nt;
   m->nb = nb;
   int rc = PTFEM_OK;
+  if (cudaEventCreateWithFlags(&m->ev_upload, cudaEventDisableTiming) != cudaSuccess) rc = set_err(PTFEM_ERR_CUDA, "event creation failed");
   auto up = [&](auto& buf, const auto* src, size_t count) {
     if (rc) return;
     rc = buf.alloc(count);
     if (rc || count == 0) return;
-    cudaError_t e = cudaMemcpyAsync(buf.p, src, count * sizeof(*src), cudaMemcpyHostToDevice, ctx->stream);
+    cudaError_t e = cudaMemcpyAsync(buf.p, src, count * sizeof(*src), cudaMemcpyHostToDevice, ctx->stream3);
     if (e != cudaSuccess) rc = set_err(PTFEM_ERR_CUDA, "mesh upload: %s", cudaGetErrorString(e));
   };
+  up(m->tets, tets, (size_t)nt * 4);       // what the pattern needs first
   up(m->xyz, xyz, (size_t)nn * 3);
-  up(m->tets, tets, (size_t)nt * 4);
   up(m->region, region, (size_t)nt);
   up(m->tris, tris, (size_t)nb * 3);
   up(m->bcid, bcid, (size_t)nb);
-  if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = set_err(PTFEM_ERR_CUDA, "mesh upload failed");
-  // validation and bounding box on the device (a host pass over 80 M indices cost more than the upload itself)
-  if (!rc) {
-    DevBuf<unsigned long long> bad;
-    rc = bad.alloc(2);
-    if (!rc && cudaMemsetAsync(bad.p, 0xff, 2 * sizeof(unsigned long long), ctx->stream) != cudaSuccess)
-      rc = set_err(PTFEM_ERR_CUDA, "mesh validation failed");
-    if (!rc) {
-      if (nt > 0) index_check_kernel<<<ceil_div(nt * 4, 256), 256, 0, ctx->stream>>>(m->tets.p, nt * 4, nn, bad.p);
-      if (nb > 0) index_check_kernel<<<ceil_div(nb * 3, 256), 256, 0, ctx->stream>>>(m->tris.p, nb * 3, nn, bad.p + 1);
-      ctx->launches += (nt > 0) + (nb > 0);
-      unsigned long long hb[2];
-      if (cudaMemcpyAsync(hb, bad.p, sizeof hb, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-          cudaStreamSynchronize(ctx->stream) != cudaSuccess)
-        rc = set_err(PTFEM_ERR_CUDA, "mesh validation failed: %s", cudaGetErrorString(cudaGetLastError()));
-      else if (hb[0] != ~0ull)
-        rc = set_err(PTFEM_ERR_ARG, "tet %llu refers to node %d (nn = %lld)", hb[0] / 4, tets[hb[0]], (long long)nn);
-      else if (hb[1] != ~0ull)
-        rc = set_err(PTFEM_ERR_ARG, "boundary triangle %llu refers to node %d", hb[1] / 3, tris[hb[1]]);
-    }
-  }
-  if (!rc) rc = device_bbox(m);
+  if (!rc && cudaEventRecord(m->ev_upload, ctx->stream3) != cudaSuccess) rc = set_err(PTFEM_ERR_CUDA, "mesh upload failed");
   if (rc) {
+    cudaStreamSynchronize(ctx->stream3);
+    if (m->ev_upload) cudaEventDestroy(m->ev_upload);
     delete m;
     return rc;
   }
+  m->upload_pending = true;
   *out = m;
   return PTFEM_OK;
+}
+
+int ptfem_mesh_create(ptfem_ctx* ctx, int64_t nn, const double* xyz, int64_t nt, const int32_t* tets, const int32_t* region,
+                      int64_t nb, const int32_t* tris, const int32_t* bcid, ptfem_mesh** out) {
+  PT_TRY(ptfem_mesh_create_async(ctx, nn, xyz, nt, tets, region, nb, tris, bcid, out));
+  PT_CK(cudaStreamSynchronize(ctx->stream3));       // the host arrays are the caller's again
+  const int rc = mesh_finish_upload(*out);
+  if (rc) {
+    ptfem_mesh_destroy(*out);
+    *out = nullptr;
+  }
+  return rc;
 }
 
 int ptfem_mesh_destroy(ptfem_mesh* m) {
@@ -337,6 +357,8 @@ int ptfem_mesh_destroy(ptfem_mesh* m) {
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
   cudaStreamSynchronize(m->ctx->stream2);
+  if (m->upload_pending) cudaStreamSynchronize(m->ctx->stream3);
+  if (m->ev_upload) cudaEventDestroy(m->ev_upload);
   pcg_work_drop_graph(m->work);
   pcg_work_drop_graph(m->work3);
   ptfem_dist_mesh_release(m);
@@ -349,6 +371,7 @@ int ptfem_mesh_destroy(ptfem_mesh* m) {
 int ptfem_mesh_set_coords(ptfem_mesh* m, const double* xyz) {
   PT_ARG(m && xyz, "null pointer");
   PT_CK(cudaSetDevice(m->ctx->device));
+  PT_TRY(mesh_finish_upload(m));
   PT_CK(cudaMemcpyAsync(m->xyz.p, xyz, (size_t)m->nn * 3 * sizeof(double), cudaMemcpyHostToDevice, m->ctx->stream));
   PT_CK(cudaStreamSynchronize(m->ctx->stream));
   PT_TRY(device_bbox(m));
@@ -413,6 +436,7 @@ int ptfem_window_plan_info(ptfem_mesh* m, int64_t info[6], double* rows_per_row)
 int ptfem_pattern(ptfem_mesh* m, int64_t* nnz) {
   PT_ARG(m, "null mesh");
   PT_CK(cudaSetDevice(m->ctx->device));
+  PT_TRY(mesh_finish_upload(m));
   if (!m->has_pattern) PT_TRY(ptfem_build_pattern(m));
   if (!m->has_geom) PT_TRY(ptfem_build_geometry(m));
   if (nnz) *nnz = m->nnz;

@@ -97,6 +97,7 @@ struct ptfem_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // copies / halo
+  cudaStream_t stream3 = nullptr;  // mesh uploads (host -> device), so they overlap both the kernels and the read-backs
   int64_t launches = 0;
   cudaEvent_t ev_phi_ready = nullptr;
   cudaEvent_t ev_j_ready = nullptr, ev_j_copied = nullptr;  // asynchronous read-back of the nodal current (stream2)
@@ -152,6 +153,8 @@ struct PcgWork {
 
 struct ptfem_mesh {
   ptfem_ctx* ctx = nullptr;
+  bool upload_pending = false;    // ptfem_mesh_create_async: arrays still arriving on stream3, validation and bounding box still to do
+  cudaEvent_t ev_upload = nullptr;
   int64_t nn = 0, nt = 0, nb = 0, nnz = 0;
   // mesh
   ptfem::DevBuf<double> xyz;     // [nn][3]

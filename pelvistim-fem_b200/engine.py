@@ -89,6 +89,7 @@ def load_library():
         "ptfem_ctx_launch_count": (C.c_int, [vp, P(i64)]),
         "ptfem_ctx_stream": (C.c_int, [vp, P(vp)]),
         "ptfem_mesh_create": (C.c_int, [vp, i64, vp, i64, vp, vp, i64, vp, vp, P(vp)]),
+        "ptfem_mesh_create_async": (C.c_int, [vp, i64, vp, i64, vp, vp, i64, vp, vp, P(vp)]),
         "ptfem_mesh_destroy": (C.c_int, [vp]),
         "ptfem_mesh_set_coords": (C.c_int, [vp, vp]),
         "ptfem_pattern": (C.c_int, [vp, P(i64)]),
@@ -236,8 +237,8 @@ class Context:
         self._ck(self.lib.ptfem_ctx_stream(self._h, C.byref(s)))
         return s.value or 0
 
-    def mesh(self, nodes, tets, region, tris, bcid):
-        return DeviceMesh(self, nodes, tets, region, tris, bcid)
+    def mesh(self, nodes, tets, region, tris, bcid, prefetch=False):
+        return DeviceMesh(self, nodes, tets, region, tris, bcid, prefetch=prefetch)
 
     def close(self):
         if self._h is not None:
@@ -261,7 +262,9 @@ class DeviceMesh:
     """A mesh resident on the GPU together with its pattern, matrices, right-hand sides and
     solution (``ptfem_mesh``)."""
 
-    def __init__(self, ctx: Context, nodes, tets, region, tris, bcid):
+    def __init__(self, ctx: Context, nodes, tets, region, tris, bcid, prefetch=False):
+        """``prefetch=True``: the upload is only queued (``ptfem_mesh_create_async``) - give pinned arrays and leave them
+        alone until ``pattern()``; a sweep uses it to send the mesh of its next point while the current one is being solved."""
         self.ctx = ctx
         self.lib = ctx.lib
         nodes, tets, region = _f64(nodes), _i32(tets), _i32(region)
@@ -269,8 +272,9 @@ class DeviceMesh:
         self.nn, self.nt, self.nb = nodes.shape[0], tets.shape[0], tris.shape[0]
         h = C.c_void_p()
         self._h = None
-        self._ck(self.lib.ptfem_mesh_create(ctx._h, self.nn, _ptr(nodes), self.nt, _ptr(tets), _ptr(region),
-                                            self.nb, _ptr(tris), _ptr(bcid), C.byref(h)))
+        create = self.lib.ptfem_mesh_create_async if prefetch else self.lib.ptfem_mesh_create
+        self._ck(create(ctx._h, self.nn, _ptr(nodes), self.nt, _ptr(tets), _ptr(region), self.nb, _ptr(tris), _ptr(bcid), C.byref(h)))
+        self._host = (nodes, tets, region, tris, bcid) if prefetch else None     # alive until the upload has been waited for
         self._h = h
         self.nnz = None
         self.nsys = 1
@@ -293,6 +297,7 @@ class DeviceMesh:
     def pattern(self):
         n = C.c_int64()
         self._ck(self.lib.ptfem_pattern(self._h, C.byref(n)))
+        self._host = None
         self.nnz = n.value
         return self.nnz
 

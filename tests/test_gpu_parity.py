@@ -644,6 +644,29 @@ def test_size_L_matches_cpu_oracle(gpu_ctx):
     del _ORACLE_CACHE["L"]
 
 
+def test_prefetched_mesh_upload_matches_blocking_upload(gpu_ctx):
+    # ptfem_mesh_create_async: the upload is queued on its own stream and waited for (and validated) by ptfem_pattern
+    import torch
+    m = meshgen.synth_slab("S")
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    hn, ht, hr, hb, hi = pin(m.nodes), pin(m.tets), pin(m.region), pin(m.tris), pin(m.bcid)
+    d0 = gpu_ctx.mesh(m.nodes, m.tets, m.region, m.tris, m.bcid)
+    d1 = gpu_ctx.mesh(hn, ht, hr, hb, hi, prefetch=True)
+    d2 = gpu_ctx.mesh(hn, ht, hr, hb, hi, prefetch=True)          # two uploads in flight behind each other
+    assert d0.pattern() == d1.pattern() == d2.pattern()
+    p0, p1 = d0.get_pattern(), d2.get_pattern()
+    assert np.array_equal(p0[0], p1[0]) and np.array_equal(p0[1], p1[1])
+    for d in (d0, d1):
+        d.assemble(SIGMA5).bc_reset(1).neumann(101, 15.975).dirichlet(102, 0.0)
+    assert np.array_equal(d0.solve(rtol=1e-12)[0], d1.solve(rtol=1e-12)[0])
+    bad = ht.copy(); bad[5, 2] = m.nn + 3
+    d3 = gpu_ctx.mesh(hn, pin(bad), hr, hb, hi, prefetch=True)
+    with pytest.raises(engine.PtfemError):                          # a bad index surfaces where the upload is waited for
+        d3.pattern()
+    for d in (d0, d1, d2, d3):
+        d.close()
+
+
 # -- window SpMM (multi-RHS product out of shared-memory x windows): same answers as the streaming kernel and as the oracle ----
 @pytest.mark.parametrize("nrhs", [4, 8, 16])
 def test_window_spmm_matches_streaming_kernel_and_oracle(monkeypatch, nrhs):
