@@ -462,6 +462,7 @@ def main():
     # ---- device-resident throughput -------------------------------------------------------------------
     dm = ctx.mesh(mesh.nodes, mesh.tets, mesh.region, mesh.tris, mesh.bcid)
     nnz = dm.pattern()
+    win_plan = dm.window_plan()
     for s in range(args.warmup):
         run_sweep_step(dm, mesh, confs, s)
     ctx.sync(); torch.cuda.synchronize(); barrier()
@@ -641,12 +642,17 @@ def main():
     traffic = ncu_traffic()
     alg1 = 12 * nnz + 20 * mesh.nn
     spmv1_gbs = alg1 / (spmv1_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": f"spmv_stream_kernel<S={S}> (multi-RHS CSR SpMV with fused p.Ap)", "achieved": achieved,
+    windowed = win_plan["valid"] and S in (4, 8, 16)
+    kernel = (f"spmm_window_kernel<S={S}> (multi-RHS CSR product out of shared-memory x windows, fused p.Ap)" if windowed
+              else f"spmv_stream_kernel<S={S}> (multi-RHS CSR SpMV with fused p.Ap)")
+    tkey = "spmm_window_bytes_per_launch" if windowed else "spmm_bytes_per_launch"
+    roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": t_spmv * 1e3,
                 "share_of_step": statistics.mean(iters) * t_spmv * args.steps / t_dev,
-                "traffic": None if traffic is None else traffic.get("spmm_bytes_per_launch"),
-                "frac_of_nominal_8TBs": achieved / 8000.0}
+                "traffic": None if traffic is None else traffic.get(tkey),
+                "traffic_source": None if traffic is None else traffic.get("source"),
+                "frac_of_nominal_8TBs": achieved / 8000.0, "window_plan": win_plan}
     line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, mesh, nnz),

@@ -37,38 +37,68 @@ __global__ void fill_incidence(const int32_t* __restrict__ elems, int64_t ne, co
   }
 }
 
-// insertion sort of each (short) list: thread per list
-__global__ void sort_lists(const int32_t* __restrict__ ptr, int32_t* __restrict__ list, int64_t n) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int32_t b = ptr[i], e = ptr[i + 1];
-  for (int32_t k = b + 1; k < e; ++k) {
-    int32_t v = list[k];
-    int32_t j = k - 1;
-    while (j >= b && list[j] > v) {
-      list[j + 1] = list[j];
-      --j;
+// insertion sort of each (short) list: thread per list.  The lists of a block are one contiguous span of the array: it is
+// brought into shared memory with coalesced loads, every thread sorts its own segment there, and the span goes back the
+// same way (a span that does not fit is sorted in place in global memory, as before).
+constexpr int kSortThreads = 128;
+constexpr int kSortSpan = 8192;      // entries of shared memory per block (64 per list on average)
+__global__ void __launch_bounds__(kSortThreads) sort_lists(const int32_t* __restrict__ ptr, int32_t* __restrict__ list, int64_t n) {
+  __shared__ int32_t s_span[kSortSpan];
+  const int64_t i0 = (int64_t)blockIdx.x * kSortThreads;
+  const int64_t i1 = min(n, i0 + kSortThreads);
+  const int64_t i = i0 + threadIdx.x;
+  const int32_t base = ptr[i0], top = ptr[i1];
+  const bool fits = top - base <= kSortSpan;
+  int32_t* buf = list;
+  int32_t off = 0;
+  if (fits) {
+    for (int32_t k = threadIdx.x; k < top - base; k += kSortThreads) s_span[k] = list[base + k];
+    __syncthreads();
+    buf = s_span;
+    off = base;
+  }
+  if (i < n) {
+    const int32_t b = ptr[i] - off, e = ptr[i + 1] - off;
+    for (int32_t k = b + 1; k < e; ++k) {
+      const int32_t v = buf[k];
+      int32_t j = k - 1;
+      while (j >= b && buf[j] > v) {
+        buf[j + 1] = buf[j];
+        --j;
+      }
+      buf[j + 1] = v;
     }
-    list[j + 1] = v;
+  }
+  if (fits) {
+    __syncthreads();
+    for (int32_t k = threadIdx.x; k < top - base; k += kSortThreads) list[base + k] = s_span[k];
   }
 }
 
 // ---- rows: sorted unique neighbour list of every node ------------------------------------------
 // scratch region of node i: [4*n2t_ptr[i] + i, 4*n2t_ptr[i+1] + i + 1)  (room for 4*cnt + 1 entries)
-__global__ void row_unique(const int32_t* __restrict__ tets, const int32_t* __restrict__ n2t_ptr,
-                           const int32_t* __restrict__ n2t, int64_t nn, int32_t* __restrict__ scratch,
-                           int32_t* __restrict__ rowlen) {
+constexpr int kUniqThreads = 64;
+constexpr int kUniqPitch = 129;     // odd: the threads' private segments start in different banks; room for 32 tets per node
+__global__ void __launch_bounds__(kUniqThreads)
+    row_unique(const int32_t* __restrict__ tets, const int32_t* __restrict__ n2t_ptr, const int32_t* __restrict__ n2t, int64_t nn,
+               int32_t* __restrict__ scratch, int32_t* __restrict__ rowlen) {
+  __shared__ int32_t s_row[kUniqThreads * kUniqPitch];
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nn) return;
   const int32_t tb = n2t_ptr[i], te = n2t_ptr[i + 1];
-  int32_t* row = scratch + ((int64_t)4 * tb + i);
+  int32_t* out = scratch + ((int64_t)4 * tb + i);
+  // the sorted insertion works in shared memory when the node's 4*cnt + 1 candidates fit there, else in the scratch itself
+  const bool in_smem = 4 * (te - tb) + 1 <= kUniqPitch;
+  int32_t* row = in_smem ? s_row + threadIdx.x * kUniqPitch : out;
   int32_t u = 1;
   row[0] = (int32_t)i;  // the diagonal is always present
   for (int32_t t = tb; t < te; ++t) {
     const int32_t e = n2t[t];
+    const int4 v = *reinterpret_cast<const int4*>(tets + (int64_t)e * 4);
+    const int32_t nd[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-      const int32_t c = tets[(int64_t)e * 4 + a];
+      const int32_t c = nd[a];
       // lower bound in row[0..u)
       int32_t lo = 0, hi = u;
       while (lo < hi) {
@@ -81,6 +111,8 @@ __global__ void row_unique(const int32_t* __restrict__ tets, const int32_t* __re
       ++u;
     }
   }
+  if (in_smem)
+    for (int32_t k = 0; k < u; ++k) out[k] = row[k];
   rowlen[i] = u;
 }
 
@@ -232,7 +264,7 @@ int build_incidence(ptfem_ctx* ctx, const int32_t* elems, int64_t ne, int64_t nn
     PT_TRY(fill_i32(ctx, cursor.p, 0, nn + 1));
     fill_incidence<NV><<<ceil_div(ne, 256), 256, 0, ctx->stream>>>(elems, ne, ptr.p, cursor.p, list.p);
     PT_LAUNCH_CHECK(ctx);
-    sort_lists<<<ceil_div(nn, 128), 128, 0, ctx->stream>>>(ptr.p, list.p, nn);
+    sort_lists<<<ceil_div(nn, kSortThreads), kSortThreads, 0, ctx->stream>>>(ptr.p, list.p, nn);
     PT_LAUNCH_CHECK(ctx);
   }
   PT_CK(cudaStreamSynchronize(ctx->stream));  // cursor goes out of scope
@@ -257,7 +289,7 @@ int ptfem_build_pattern(ptfem_mesh* m) {
   PT_TRY(scratch.alloc((size_t)16 * nt + nn + 1));
   PT_TRY(rowlen.alloc(nn + 1));
   PT_TRY(m->rowptr.alloc(nn + 1));
-  row_unique<<<ceil_div(nn, 128), 128, 0, ctx->stream>>>(m->tets.p, m->n2t_ptr.p, m->n2t.p, nn, scratch.p, rowlen.p);
+  row_unique<<<ceil_div(nn, kUniqThreads), kUniqThreads, 0, ctx->stream>>>(m->tets.p, m->n2t_ptr.p, m->n2t.p, nn, scratch.p, rowlen.p);
   PT_LAUNCH_CHECK(ctx);
   int64_t nnz = 0;
   PT_TRY(exclusive_scan_i32(ctx, rowlen.p, m->rowptr.p, nn, &nnz));
@@ -291,7 +323,7 @@ int ptfem_build_pattern(ptfem_mesh* m) {
     PT_TRY(fill_i32(ctx, cursor.p, 0, nnz + 1));
     fill_contrib<<<ceil_div(nt * 16, 256), 256, 0, ctx->stream>>>(m->e2nnz.p, nt * 16, m->gptr.p, cursor.p, m->gsrc.p);
     PT_LAUNCH_CHECK(ctx);
-    sort_lists<<<ceil_div(nnz, 128), 128, 0, ctx->stream>>>(m->gptr.p, m->gsrc.p, nnz);
+    sort_lists<<<ceil_div(nnz, kSortThreads), kSortThreads, 0, ctx->stream>>>(m->gptr.p, m->gsrc.p, nnz);
     PT_LAUNCH_CHECK(ctx);
     PT_CK(cudaStreamSynchronize(ctx->stream));
   }
