@@ -406,6 +406,7 @@ def main():
                     help="reference arm: skip the sparse direct solve (the reference's solver class) on a small slab")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-pipelines", type=int, default=2, help="sweep pipelines (host thread + context) per GPU of the end-to-end leg")
     ap.add_argument("--no-partitioned", action="store_true", help="N > 1: skip the row-partitioned single-solve extra")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="transport of the row-partitioned solve")
     ap.add_argument("--partitioned-precond", default="auto", choices=["auto", "jacobi"],
@@ -511,40 +512,48 @@ def main():
         h2d = sum(a.nbytes for a in h.values()) + sum(c["tris"].nbytes for c in confs)
         d2h = phi_out.nbytes + J_out.nbytes
 
-        # double-buffered outputs: the device->host copies of step k (side stream) overlap the upload and pattern build of
-        # step k+1; the mesh of step k is released (which waits for its copies) once step k+1's pattern is built
-        outs = [(phi_out, J_out), (torch.empty((args.nconf, mesh.nn), dtype=torch.float64).pin_memory().numpy(),
-                                   torch.empty((args.nconf, mesh.nn, 3), dtype=torch.float64).pin_memory().numpy())]
-        state = {"prev": None, "next": None}
+        # Two sweep pipelines on the GPU (sweep.map_points_pipelined: a host thread + Context each), steps dealt alternately.
+        # Inside a pipeline: the mesh of its next step is queued for upload while the current one is solved, outputs are
+        # double-buffered so the device->host copies of step k overlap the pattern build of step k+2, and the mesh of step k is
+        # released (which waits for its copies) once the next pattern is built.  Across pipelines the GPU overlaps one's
+        # latency-bound phases (upload, pattern, host gaps) with the other's bandwidth-bound solve.
+        from pelvistim_fem_b200 import sweep as sweep_mod
+        P = max(1, args.e2e_pipelines)
+        new_out = lambda: (torch.empty((args.nconf, mesh.nn), dtype=torch.float64).pin_memory().numpy(),
+                           torch.empty((args.nconf, mesh.nn, 3), dtype=torch.float64).pin_memory().numpy())
+        pipe_outs = [[(phi_out, J_out) if k == 0 else new_out(), new_out()] for k in range(P)]
 
-        def e2e_step(s, last=False):
-            # this step's mesh was queued for upload while the previous step was being solved; the next step's is queued now
-            d = state["next"] or ctx.mesh(h["nodes"], h["tets"], h["region"], h["tris"], h["bcid"], prefetch=True)
+        def e2e_point(pctx, st, pt):
+            s, last = pt
+            d = st.get("next") or pctx.mesh(h["nodes"], h["tets"], h["region"], h["tris"], h["bcid"], prefetch=True)
             d.pattern()
-            state["next"] = None if last else ctx.mesh(h["nodes"], h["tets"], h["region"], h["tris"], h["bcid"], prefetch=True)
-            if state["prev"] is not None:
-                state["prev"].close()
-            po, jo = outs[s % 2]
+            st["next"] = None if last else pctx.mesh(h["nodes"], h["tets"], h["region"], h["tris"], h["bcid"], prefetch=True)
+            if st.get("prev") is not None:
+                st["prev"].close()
+            st["n"] = st.get("n", 0) + 1
+            po, jo = pipe_outs[st["pipeline"]][st["n"] % 2]
             r, _, _ = run_sweep_step(d, mesh, confs, s, phi_out=po, J_out=jo)
-            state["prev"] = d
+            st["prev"] = d
             return r
 
-        def e2e_drain():
-            if state["prev"] is not None:
-                state["prev"].close()       # waits for the last step's copies
-                state["prev"] = None
-        for s in range(3):          # untimed: the allocator's cache ends up holding the blocks of the meshes alive at a time
-            e2e_step(s, last=s == 2)
-        e2e_drain()
+        def e2e_finish(pctx, st):
+            if st.get("prev") is not None:
+                st["prev"].close()       # waits for the last step's copies
+                st["prev"] = None
+
+        pool = sweep_mod.PipelinePool(local_rank, P)
+
+        def e2e_run(first, n):          # steps first .. first+n-1; a pipeline's last step does not prefetch
+            pts = [(first + k, k + P >= n) for k in range(n)]
+            return pool.map(e2e_point, pts, finish=e2e_finish)
+        e2e_run(0, 3 * P)               # untimed: the allocator's cache ends up holding the blocks of the meshes alive at a time
         ctx.sync(); torch.cuda.synchronize(); barrier()
-        n_e2e = max(1, min(args.steps, 5))
+        n_e2e = max(P, min(args.steps, 12))
         ev0.record(stream)
-        for s in range(n_e2e):      # every upload that is consumed is inside the timed region: the first is not overlapped
-            l2_flush()
-            e2e_step(100 + s, last=s == n_e2e - 1)
-        e2e_drain()
+        e2e_run(100, n_e2e)             # every upload that is consumed is inside the timed region
         ev1.record(stream)
         ctx.sync(); torch.cuda.synchronize()
+        pool.close()
         t_e2e = ev0.elapsed_time(ev1) * 1e-3
         barrier()
         if dist is not None:
@@ -553,7 +562,7 @@ def main():
             t_e2e = float(t.item())
         e2e = {"value": world * args.nconf * n_e2e / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
-               "host_cpus_bound_to_gpu_numa_node": None if numa_cpus is None else len(numa_cpus)}
+               "pipelines_per_gpu": P, "host_cpus_bound_to_gpu_numa_node": None if numa_cpus is None else len(numa_cpus)}
 
     # ---- N > 1 extra: the same mesh as ONE row-partitioned solve over all ranks (config #5, strong scaling) -------
     part = None

@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -23,14 +24,17 @@ int set_err(int code, const char* fmt, ...) {
 
 // ---- caching device allocator ---------------------------------------------------------------------
 // One cache per process, keyed by device.  Blocks are only reused after the owning buffer was released
-// on the host, and every kernel that touched a buffer was launched on the context's stream before that
-// release; callers synchronise that stream before dropping buffers that may still be in use
-// (ptfem_mesh_destroy does), so a recycled block is never in flight.
+// on the host, and every kernel that touched a buffer was launched on the releasing thread's context stream
+// before that release, so a block handed back to the SAME host thread is reused in stream order.  A block
+// released by another host thread (sweep pipelines: one thread and one context each) may still be in flight
+// on that thread's stream and is never handed out; it returns to the driver when the cache is flushed
+// (allocation failure, context destruction), which synchronises the device.
 namespace {
 struct CacheBlock {
   void* p;
   size_t bytes;
   int device;
+  std::thread::id owner;      // host thread that released it last
 };
 std::mutex g_cache_mu;
 std::multimap<size_t, CacheBlock> g_free;                 // by size
@@ -41,10 +45,11 @@ int dev_alloc(void** out, size_t bytes) {
   int dev = 0;
   cudaGetDevice(&dev);
   bytes = (bytes + 511) & ~(size_t)511;
+  const std::thread::id me = std::this_thread::get_id();
   {
     std::lock_guard<std::mutex> lk(g_cache_mu);
     for (auto it = g_free.lower_bound(bytes); it != g_free.end() && it->first <= bytes + bytes / 4 + 4096; ++it) {
-      if (it->second.device == dev) {
+      if (it->second.device == dev && it->second.owner == me) {
         CacheBlock b = it->second;
         g_free.erase(it);
         g_live[b.p] = b;
@@ -65,7 +70,7 @@ int dev_alloc(void** out, size_t bytes) {
     return set_err(PTFEM_ERR_CUDA, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
   }
   std::lock_guard<std::mutex> lk(g_cache_mu);
-  g_live[p] = CacheBlock{p, bytes, dev};
+  g_live[p] = CacheBlock{p, bytes, dev, std::this_thread::get_id()};
   *out = p;
   return PTFEM_OK;
 }
@@ -75,6 +80,7 @@ void dev_free(void* p) {
   std::lock_guard<std::mutex> lk(g_cache_mu);
   auto it = g_live.find(p);
   if (it == g_live.end()) return;
+  it->second.owner = std::this_thread::get_id();
   g_free.emplace(it->second.bytes, it->second);
   g_live.erase(it);
 }

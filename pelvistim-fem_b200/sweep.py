@@ -73,3 +73,78 @@ def map_points(fn, points, gpus=1):
     if err is not None:
         raise RuntimeError(err)
     return out
+
+
+class PipelinePool:
+    """``pipelines`` host threads of THIS process, each owning a ``Context`` (its own streams) on the same GPU and a private
+    ``state`` dict, kept alive between calls (the device allocator caches blocks per host thread).  Sweep points are
+    independent (``run_layered_sweep.py:1061-1062``), so while one pipeline is in the latency-bound part of its point (mesh
+    upload, pattern build, Python between calls) the other keeps the memory system busy with its solve: the GPU sees the
+    union of both streams."""
+
+    def __init__(self, device=0, pipelines=2):
+        import queue
+        import threading
+        self.pipelines = max(1, int(pipelines))
+        self.device = device
+        self._jobs = [queue.Queue() for _ in range(self.pipelines)]
+        self._done = queue.Queue()
+        self._threads = [threading.Thread(target=self._run, args=(k,), name=f"ptfem-pipeline-{k}", daemon=True)
+                         for k in range(self.pipelines)]
+        for t in self._threads:
+            t.start()
+
+    def _run(self, k):
+        from .engine import Context
+        ctx, state = None, {"pipeline": k}
+        while True:
+            job = self._jobs[k].get()
+            if job is None:
+                break
+            fn, items, finish, out = job
+            err = None
+            try:
+                if ctx is None:
+                    ctx = Context(self.device)
+                for i, pt in items:
+                    out[i] = fn(ctx, state, pt)
+                if finish is not None:
+                    finish(ctx, state)
+                ctx.sync()
+            except BaseException as e:  # noqa: BLE001 - re-raised in the caller's thread
+                err = e
+            self._done.put(err)
+        if ctx is not None:
+            ctx.close()
+        self._done.put(None)
+
+    def map(self, fn, points, finish=None):
+        """``[fn(ctx, state, pt) for pt in points]``, point i on pipeline i mod P; ``finish(ctx, state)`` runs in every
+        pipeline's thread after its last point (drain outstanding copies)."""
+        points = list(points)
+        out = [None] * len(points)
+        for k in range(self.pipelines):
+            self._jobs[k].put((fn, [(i, points[i]) for i in range(k, len(points), self.pipelines)], finish, out))
+        errs = [self._done.get() for _ in range(self.pipelines)]
+        for e in errs:
+            if e is not None:
+                raise e
+        return out
+
+    def close(self):
+        for q in self._jobs:
+            q.put(None)
+        for _ in self._threads:
+            self._done.get()
+        for t in self._threads:
+            t.join()
+        self._threads = []
+
+
+def map_points_pipelined(fn, points, device=0, pipelines=2, finish=None):
+    """One-shot form of ``PipelinePool.map``."""
+    pool = PipelinePool(device, pipelines)
+    try:
+        return pool.map(fn, points, finish)
+    finally:
+        pool.close()
