@@ -553,7 +553,7 @@ int ptfem_solve_device(ptfem_mesh* m, const ptfem_solve_opts* opts, ptfem_solve_
   PT_ARG(o.precond >= PTFEM_PRECOND_AUTO && o.precond <= PTFEM_PRECOND_TWOLEVEL, "unknown preconditioner");
   PT_TRY(prepare_systems(m));
   const bool automatic = o.precond == PTFEM_PRECOND_AUTO;
-  if (automatic) o.precond = (m->nvalp == 1 && m->nn >= 100000) ? PTFEM_PRECOND_TWOLEVEL : PTFEM_PRECOND_JACOBI;
+  if (automatic) o.precond = m->nn >= 100000 ? PTFEM_PRECOND_TWOLEVEL : PTFEM_PRECOND_JACOBI;   // shared and batched matrices alike
   LinSys A;
   make_linsys(m, A);
   double setup_ms = 0.0;

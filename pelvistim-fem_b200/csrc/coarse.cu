@@ -220,7 +220,7 @@ __device__ __forceinline__ void dot_by_sys(double v, double* s_buf /*[blockDim]*
 // grid node I gathers the partials of the cells around it (fixed order).  DIAG: y = r_c * binv, dot.
 template <int S, bool DIAG>
 __global__ void __launch_bounds__(256) coarse_node_kernel(CoarseGrid g, int64_t k, int split, const double* __restrict__ part,
-                                                          const double* __restrict__ binv, double* __restrict__ rc,
+                                                          const double* __restrict__ binv, int64_t bstride, double* __restrict__ rc,
                                                           double* __restrict__ yc, double* __restrict__ dpart,
                                                           double* __restrict__ cdot, unsigned int* ticket) {
   __shared__ double s_buf[256];
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256) coarse_node_kernel(CoarseGrid g, int64_t 
     }
     rc[I * S + s] = v;
     if (DIAG) {
-      const double y = v * __ldg(binv + I);
+      const double y = v * __ldg(binv + (size_t)s * bstride + I);   // bstride > 0: every system has its own operator
       yc[I * S + s] = y;
       dot = fma(v, y, dot);
     }
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(256) coarse_node_kernel(CoarseGrid g, int64_t 
 // r_c[I] = sum_f P[f][I] r_f[f] (27 fine nodes around 2I);  DIAG: y = binv r_c and the level's dot
 template <int S, bool DIAG>
 __global__ void __launch_bounds__(256) grid_restrict_kernel(CoarseGrid gc, int64_t k, const double* __restrict__ rf,
-                                                            const double* __restrict__ binv, double* __restrict__ rc,
+                                                            const double* __restrict__ binv, int64_t bstride, double* __restrict__ rc,
                                                             double* __restrict__ yc, double* __restrict__ dpart,
                                                             double* __restrict__ cdot, unsigned int* ticket) {
   __shared__ double s_buf[256];
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(256) grid_restrict_kernel(CoarseGrid gc, int64
     }
     rc[I * S + s] = v;
     if (DIAG) {
-      const double y = v * __ldg(binv + I);
+      const double y = v * __ldg(binv + (size_t)s * bstride + I);
       yc[I * S + s] = y;
       dot = fma(v, y, dot);
     }
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(256) grid_prolong_kernel(CoarseGrid gc, int64_
 // lane = (column within a group of 32/S, system), so the r_c loads of a warp are one contiguous 256-byte run.
 constexpr int kDenseRows = 4;
 template <int S>
-__global__ void __launch_bounds__(256) coarse_dense_kernel(int kp, const double* __restrict__ binv, const double* __restrict__ rc,
+__global__ void __launch_bounds__(256) coarse_dense_kernel(int kp, const double* __restrict__ binv0, int64_t bstride, const double* __restrict__ rc,
                                                            double* __restrict__ yc, double* __restrict__ dpart,
                                                            double* __restrict__ cdot, unsigned int* ticket) {
   __shared__ double s_buf[256];
@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(256) coarse_dense_kernel(int kp, const double*
   constexpr int JPW = 32 / S;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int jj = lane / S, s = lane % S;
+  const double* binv = binv0 + (size_t)s * bstride;     // bstride > 0: the inverse of this lane's system
   const int I0 = blockIdx.x * kDenseRows;
   const int chunk = kp / 8;  // kp is a multiple of 64
   const int j0 = wid * chunk, j1 = j0 + chunk;
@@ -928,6 +929,11 @@ __global__ void coarse_table_split_kernel(int64_t nn, float4* __restrict__ ctab,
   ctab[i].w = __uint_as_float(cell & ~kCoarseDirBit);
 }
 // level weight: B_l *= w (the additive levels overlap in what they correct)
+// out[k] = val[k][sys] of the interleaved value sets
+__global__ void gather_value_set_kernel(const double* __restrict__ val, int64_t nnz, int VS, int sys, double* __restrict__ out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < nnz) out[k] = val[k * VS + sys];
+}
 __global__ void coarse_weight_kernel(double* __restrict__ binv, int64_t n, double w) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) binv[i] *= w;
@@ -1002,7 +1008,7 @@ int chain_setup_t(ptfem_ctx* ctx, CoarseSpace& cs) {
 }
 int chain_setup(ptfem_ctx* ctx, CoarseSpace& cs, int S) {
   cs.chain_grid = 0;
-  if (!ctx->tune_coarse_fused) return PTFEM_OK;
+  if (!ctx->tune_coarse_fused || cs.VS > 1) return PTFEM_OK;
   switch (S) {
     case 1: return chain_setup_t<1>(ctx, cs);
     case 2: return chain_setup_t<2>(ctx, cs);
@@ -1062,24 +1068,26 @@ int apply_t(ptfem_ctx* ctx, CoarseSpace& cs, const double* r) {
     CoarseLevel& L = cs.lev[l];
     double* cdot = cs.cdot.p + (size_t)l * 16;
     const int ngrid = std::min(ceil_div(L.k * S, 256), 4 * ctx->sm_count);
+    // one operator per system (batched matrices): system s reads binv + s * bs
+    const int64_t bs = cs.VS > 1 ? (L.exact ? (int64_t)L.kp * L.kp : L.k) : 0;
     if (l == 0) {
       if (L.exact)
-        coarse_node_kernel<S, false><<<ngrid, 256, 0, ctx->stream>>>(L.g, L.k, L.split, L.part.p, nullptr, L.rc.p, L.yc.p, cs.dpart.p,
+        coarse_node_kernel<S, false><<<ngrid, 256, 0, ctx->stream>>>(L.g, L.k, L.split, L.part.p, nullptr, 0, L.rc.p, L.yc.p, cs.dpart.p,
                                                                      cdot, cs.ticket.p);
       else
-        coarse_node_kernel<S, true><<<ngrid, 256, 0, ctx->stream>>>(L.g, L.k, L.split, L.part.p, L.binv.p, L.rc.p, L.yc.p, cs.dpart.p,
+        coarse_node_kernel<S, true><<<ngrid, 256, 0, ctx->stream>>>(L.g, L.k, L.split, L.part.p, L.binv.p, bs, L.rc.p, L.yc.p, cs.dpart.p,
                                                                     cdot, cs.ticket.p);
     } else {
       if (L.exact)
-        grid_restrict_kernel<S, false><<<ngrid, 256, 0, ctx->stream>>>(L.g, L.k, cs.lev[l - 1].rc.p, nullptr, L.rc.p, L.yc.p,
+        grid_restrict_kernel<S, false><<<ngrid, 256, 0, ctx->stream>>>(L.g, L.k, cs.lev[l - 1].rc.p, nullptr, 0, L.rc.p, L.yc.p,
                                                                        cs.dpart.p, cdot, cs.ticket.p);
       else
-        grid_restrict_kernel<S, true><<<ngrid, 256, 0, ctx->stream>>>(L.g, L.k, cs.lev[l - 1].rc.p, L.binv.p, L.rc.p, L.yc.p,
+        grid_restrict_kernel<S, true><<<ngrid, 256, 0, ctx->stream>>>(L.g, L.k, cs.lev[l - 1].rc.p, L.binv.p, bs, L.rc.p, L.yc.p,
                                                                       cs.dpart.p, cdot, cs.ticket.p);
     }
     PT_LAUNCH_CHECK(ctx);
     if (L.exact) {
-      coarse_dense_kernel<S><<<L.kp / kDenseRows, 256, 0, ctx->stream>>>(L.kp, L.binv.p, L.rc.p, L.yc.p, cs.dpart.p, cdot,
+      coarse_dense_kernel<S><<<L.kp / kDenseRows, 256, 0, ctx->stream>>>(L.kp, L.binv.p, bs, L.rc.p, L.yc.p, cs.dpart.p, cdot,
                                                                         cs.ticket.p);
       PT_LAUNCH_CHECK(ctx);
     }
@@ -1122,9 +1130,16 @@ void coarse_free(CoarseSpace* cs) { delete cs; }
 
 int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
   ptfem_ctx* ctx = m->ctx;
-  if (m->nvalp != 1) return set_err(PTFEM_ERR_ARG, "the two-level preconditioner needs one shared matrix (multi-RHS), not %d", m->nval);
   if (!m->coarse) m->coarse = new CoarseSpace();
   CoarseSpace& cs = *m->coarse;
+  // batched matrices (nvalp value sets on one pattern, one per system): the grids, Z and the row lists are shared, every
+  // system gets its own Galerkin operators (stored one after the other), built by the same kernels from its value set
+  const int VS = m->nvalp > 1 ? m->nvalp : 1;
+  if (VS > 1 && VS != S) return set_err(PTFEM_ERR_ARG, "batched matrices: %d value sets but %d systems", VS, S);
+  if (VS > 1 && (cs.partial_mode || cs.row_limit >= 0))
+    return set_err(PTFEM_ERR_ARG, "the distributed coarse set-up takes one matrix");
+  const bool vs_changed = cs.VS != VS;
+  cs.VS = VS;
   // The iteration count is set by the FINEST grid; the exactly inverted one only has to be coarse enough for its O(k^3)
   // inverse to cost nothing: 8x6x4 cells (315 unknowns) under three diagonal-only levels needs the same 60 iterations on the
   // 20 M-tet slab as 16x12x8 (1989 unknowns) under two (CPU study, profiles/r02_coarse_grid_size_cpu.txt), and its inverse
@@ -1210,7 +1225,8 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
     rebuilt = true;
     cs.generation++;
   }
-  if (cs.matrix_epoch != m->matrix_epoch) {
+  if (cs.matrix_epoch != m->matrix_epoch || vs_changed) {
+    if (vs_changed) cs.generation++;
     PT_TRY(cs.flag.alloc(2));
     PT_CK(cudaMemsetAsync(cs.flag.p, 0, 2 * sizeof(int32_t), ctx->stream));
     coarse_table_flag_kernel<<<ceil_div(m->nn, 256), 256, 0, ctx->stream>>>(m->isdir.p, m->nn, cs.ctab.p);
@@ -1223,32 +1239,44 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
     // 2 / (levels + 1) against the Jacobi term - CPU study profiles/r01_precond_level_weights_L_cpu.txt: 71 -> 60 iterations
     // on the 3-level bench mesh, 59 -> 56 with 2 levels, unchanged with one; PTFEM_COARSE_WEIGHT overrides
     const double level_w = ctx->tune_coarse_weight > 0.0 ? ctx->tune_coarse_weight : 2.0 / (cs.nlev + 1);
+    DevBuf<double> valset;          // value set of one system, gathered out of the interleaved [nnz][VS] array
+    if (VS > 1) PT_TRY(valset.alloc(m->nnz + 8));
+    for (int l = 0; l < cs.nlev; ++l) {
+      CoarseLevel& L = cs.lev[l];
+      const size_t want = (L.exact ? (size_t)L.kp * L.kp : (size_t)L.k) * VS;
+      const double* before = L.binv.p;
+      PT_TRY(L.binv.alloc(want));
+      if (L.binv.p != before) cs.generation++;
+    }
+    for (int sys = 0; sys < VS; ++sys) {
+    const double* val = m->val_bc.p;
+    if (VS > 1) {
+      gather_value_set_kernel<<<ceil_div(m->nnz, 256), 256, 0, ctx->stream>>>(m->val_bc.p, m->nnz, VS, sys, valset.p);
+      PT_LAUNCH_CHECK(ctx);
+      val = valset.p;
+    }
     for (int l = 0; l < cs.nlev; ++l) {
       CoarseLevel& L = cs.lev[l];
       if (L.exact) {
         const size_t n2 = (size_t)L.kp * L.kp;
-        const double* before = L.binv.p;
-        PT_TRY(L.binv.alloc(n2));
-        if (L.binv.p != before) cs.generation++;
-        PT_CK(cudaMemsetAsync(L.binv.p, 0, n2 * sizeof(double), ctx->stream));
+        double* binv = L.binv.p + (size_t)sys * n2;
+        PT_CK(cudaMemsetAsync(binv, 0, n2 * sizeof(double), ctx->stream));
         DevBuf<double> blockE;
         int gsplit = 1;   // CTAs per cell: about eight CTAs per SM in all, each with at least a few chunks of rows
         while (L.ncell * gsplit < (int64_t)8 * ctx->sm_count && nlist / (L.ncell * gsplit) > 4 * kGalRows && gsplit < 64) gsplit *= 2;
         PT_TRY(blockE.alloc((size_t)L.ncell * gsplit * 512));
         galerkin_cell_kernel<<<(unsigned)(L.ncell * gsplit), 256, 0, ctx->stream>>>(L.g, L.cellptr.p, L.rows.p, cs.ctab.p,
-                                                                                     m->rowptr.p, m->col.p, m->val_bc.p, blockE.p,
-                                                                                     L.binv.p, L.kp, cs.flag.p, gsplit);
+                                                                                     m->rowptr.p, m->col.p, val, blockE.p,
+                                                                                     binv, L.kp, cs.flag.p, gsplit);
         PT_LAUNCH_CHECK(ctx);
-        galerkin_gather_kernel<<<ceil_div((int64_t)n2, 256), 256, 0, ctx->stream>>>(L.g, L.k, L.kp, blockE.p, L.binv.p, gsplit,
+        galerkin_gather_kernel<<<ceil_div((int64_t)n2, 256), 256, 0, ctx->stream>>>(L.g, L.k, L.kp, blockE.p, binv, gsplit,
                                                                                     cs.partial_mode ? 0 : 1);
         PT_LAUNCH_CHECK(ctx);
-        if (cs.partial_mode) {
-          PT_CK(cudaStreamSynchronize(ctx->stream));   // blockE goes back to the allocator
-          continue;
-        }
-        PT_TRY(dense_inverse(ctx, L.binv.p, L.kp, cs.flag.p));
+        PT_CK(cudaStreamSynchronize(ctx->stream));   // blockE goes back to the allocator
+        if (cs.partial_mode) continue;
+        PT_TRY(dense_inverse(ctx, binv, L.kp, cs.flag.p));
         if (level_w != 1.0) {
-          coarse_weight_kernel<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(L.binv.p, (int64_t)n2, level_w);
+          coarse_weight_kernel<<<4 * ctx->sm_count, 256, 0, ctx->stream>>>(binv, (int64_t)n2, level_w);
           PT_LAUNCH_CHECK(ctx);
         }
       }
@@ -1257,30 +1285,27 @@ int coarse_prepare(ptfem_mesh* m, int target_nodes, int extra_levels, int S) {
     if (cs.nlev > 1) {
       const int nb = cs.nlev - 1;
       CoarseLevel& L0 = cs.lev[0];
-      for (int l = 0; l < nb; ++l) {
-        const double* before = cs.lev[l].binv.p;
-        PT_TRY(cs.lev[l].binv.alloc(cs.lev[l].k));
-        if (cs.lev[l].binv.p != before) cs.generation++;
-      }
       DevBuf<double> dpartf;
       PT_TRY(dpartf.alloc((size_t)nb * L0.ncell * 8));
       const int grid = (int)std::min<int64_t>((L0.ncell + 7) / 8, (int64_t)ctx->sm_count * 32);
       galerkin_diag_multi_kernel<<<grid, 256, 0, ctx->stream>>>(nb, L0.shift, L0.ncell, L0.cellptr.p, L0.rows.p, cs.ctab.p, m->rowptr.p,
-                                                                m->col.p, m->val_bc.p, dpartf.p);
+                                                                m->col.p, val, dpartf.p);
       PT_LAUNCH_CHECK(ctx);
       for (int l = 0; l < nb; ++l) {
         CoarseLevel& L = cs.lev[l];
+        double* binv = L.binv.p + (size_t)sys * L.k;
         galerkin_diag_node_multi_kernel<<<ceil_div(L.k * 32, 256), 256, 0, ctx->stream>>>(L.g, L.k, 1 << l, L0.g.n[0], L0.g.n[1],
-                                                                                         dpartf.p + (size_t)l * L0.ncell * 8, L.binv.p,
+                                                                                         dpartf.p + (size_t)l * L0.ncell * 8, binv,
                                                                                          cs.partial_mode ? 0 : 1);
         PT_LAUNCH_CHECK(ctx);
         if (level_w != 1.0 && !cs.partial_mode) {
-          coarse_weight_kernel<<<ceil_div(L.k, 256), 256, 0, ctx->stream>>>(L.binv.p, L.k, level_w);
+          coarse_weight_kernel<<<ceil_div(L.k, 256), 256, 0, ctx->stream>>>(binv, L.k, level_w);
           PT_LAUNCH_CHECK(ctx);
         }
       }
       PT_CK(cudaStreamSynchronize(ctx->stream));   // dpartf goes back to the allocator
     }
+    }   // systems
     int32_t hflag[2] = {0, 0};
     PT_CK(cudaMemcpyAsync(hflag, cs.flag.p, sizeof hflag, cudaMemcpyDeviceToHost, ctx->stream));
     PT_CK(cudaStreamSynchronize(ctx->stream));
@@ -1446,7 +1471,7 @@ int coarse_restrict_rows(ptfem_ctx* ctx, CoarseSpace& cs, const double* r, doubl
                                                             L0.part.p);
   PT_LAUNCH_CHECK(ctx);
   const int ngrid = std::min(ceil_div(L0.k, 256), 4 * ctx->sm_count);
-  coarse_node_kernel<1, false><<<ngrid, 256, 0, ctx->stream>>>(L0.g, L0.k, L0.split, L0.part.p, nullptr, rc_out, nullptr, nullptr,
+  coarse_node_kernel<1, false><<<ngrid, 256, 0, ctx->stream>>>(L0.g, L0.k, L0.split, L0.part.p, nullptr, 0, rc_out, nullptr, nullptr,
                                                                nullptr, nullptr);
   PT_LAUNCH_CHECK(ctx);
   return PTFEM_OK;
@@ -1686,15 +1711,15 @@ int coarse_grids_apply(ptfem_ctx* ctx, CoarseSpace& cs, bool scaled0, int start)
       }
     } else {
       if (L.exact)
-        grid_restrict_kernel<1, false><<<ngrid, 256, 0, ctx->stream>>>(L.g, L.k, cs.lev[l - 1].rc.p, nullptr, L.rc.p, L.yc.p,
+        grid_restrict_kernel<1, false><<<ngrid, 256, 0, ctx->stream>>>(L.g, L.k, cs.lev[l - 1].rc.p, nullptr, 0, L.rc.p, L.yc.p,
                                                                        cs.dpart.p, cdot, cs.ticket.p);
       else
-        grid_restrict_kernel<1, true><<<ngrid, 256, 0, ctx->stream>>>(L.g, L.k, cs.lev[l - 1].rc.p, L.binv.p, L.rc.p, L.yc.p,
+        grid_restrict_kernel<1, true><<<ngrid, 256, 0, ctx->stream>>>(L.g, L.k, cs.lev[l - 1].rc.p, L.binv.p, 0, L.rc.p, L.yc.p,
                                                                       cs.dpart.p, cdot, cs.ticket.p);
       PT_LAUNCH_CHECK(ctx);
     }
     if (L.exact) {
-      coarse_dense_kernel<1><<<L.kp / kDenseRows, 256, 0, ctx->stream>>>(L.kp, L.binv.p, L.rc.p, L.yc.p, cs.dpart.p, cdot,
+      coarse_dense_kernel<1><<<L.kp / kDenseRows, 256, 0, ctx->stream>>>(L.kp, L.binv.p, 0, L.rc.p, L.yc.p, cs.dpart.p, cdot,
                                                                         cs.ticket.p);
       PT_LAUNCH_CHECK(ctx);
     }

@@ -47,6 +47,7 @@ struct CoarseSpace {
   int64_t matrix_epoch = -1;  // ptfem_mesh::matrix_epoch the Galerkin operators were built for
   int64_t generation = 0;     // bumped whenever buffers or grids change (CUDA-graph key)
   int S = 0;
+  int VS = 1;                 // Galerkin operators per level: 1 (one matrix) or S (batched matrices, stored one after the other)
   int req_nodes = 0, req_levels = 0;
   ptfem::DevBuf<double> cdot;             // [nlev][16] r_c . y_c per level and system
   ptfem::DevBuf<double> dpart;            // per-CTA partials of those dots

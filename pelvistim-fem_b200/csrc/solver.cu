@@ -658,7 +658,7 @@ __global__ void rho_finalize_kernel(double* __restrict__ scal, const double* __r
 // Two pairs per trip: the loads of both (five streamed 16-byte accesses and the table entry each) are issued before
 // either is used, and the eight grid-node gathers of both are independent - the kernel used to sit at 4.7 TB/s waiting
 // on the table -> grid node -> y chain with ~60 KB per SM in flight (ncu, round 1); the table entry is 16 bytes now.
-template <int S, int NP, int MINB = (NP == 1 ? 4 : 2)>
+template <int S, int NP, int MINB = (NP == 1 ? 4 : 2), int VS = 1>
 __global__ void __launch_bounds__(kThreads, MINB) cg_pupdate_coarse_kernel(int64_t nn, const double* __restrict__ r,
                                                                         const double* __restrict__ dinv, double* __restrict__ p,
                                                                         double* __restrict__ x, const double* __restrict__ scal,
@@ -678,7 +678,7 @@ __global__ void __launch_bounds__(kThreads, MINB) cg_pupdate_coarse_kernel(int64
 #pragma unroll
       for (int k = 0; k < NR; ++k) raw[u][k] = coarse_row_load(cd.ctab, S == 1 ? e + k : e / S);
       zv[u] = __ldg(reinterpret_cast<const double2*>(r + e));
-      d[u] = pair_weight<S, 1>(dinv, e);
+      d[u] = pair_weight<S, VS>(dinv, e);
       pv[u] = make_double2(0.0, 0.0);
       xv[u] = make_double2(0.0, 0.0);
       if (!first) {
@@ -1338,27 +1338,28 @@ int pcg_iteration(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int 
     cg_pupdate_kernel<S, VS, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, nullptr, A.dinv, w.p.p, x, w.scal.p, 0);
     PT_LAUNCH_CHECK(ctx);
   } else if (precond == PTFEM_PRECOND_TWOLEVEL) {
-    if constexpr (VS == 1) {
-      cg_update_kernel<S, 1, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.q.p, A.dinv, w.r.p, w.partial.p, w.scal.p,
-                                                                       w.ticket.p, 1);
-      PT_LAUNCH_CHECK(ctx);
-      PT_TRY(coarse_apply(ctx, *A.coarse, S, w.r.p));
-      rho_finalize_kernel<<<1, 32, 0, ctx->stream>>>(w.scal.p, A.coarse->cdot.p, A.coarse->nlev, S);
-      PT_LAUNCH_CHECK(ctx);
-      if (ctx->tune_pupdate_np == 1 && ctx->tune_pupdate_occ == 5)
-        cg_pupdate_coarse_kernel<S, 1, 5><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
-                                                                              coarse_dev(*A.coarse));
-      else if (ctx->tune_pupdate_np == 1 && ctx->tune_pupdate_occ == 6)
-        cg_pupdate_coarse_kernel<S, 1, 6><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
-                                                                              coarse_dev(*A.coarse));
-      else if (ctx->tune_pupdate_np == 1)
-        cg_pupdate_coarse_kernel<S, 1><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
-                                                                           coarse_dev(*A.coarse));
-      else
-        cg_pupdate_coarse_kernel<S, 2><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
-                                                                           coarse_dev(*A.coarse));
-      PT_LAUNCH_CHECK(ctx);
-    }
+    cg_update_kernel<S, VS, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.q.p, A.dinv, w.r.p, w.partial.p, w.scal.p,
+                                                                      w.ticket.p, 1);
+    PT_LAUNCH_CHECK(ctx);
+    PT_TRY(coarse_apply(ctx, *A.coarse, S, w.r.p));
+    rho_finalize_kernel<<<1, 32, 0, ctx->stream>>>(w.scal.p, A.coarse->cdot.p, A.coarse->nlev, S);
+    PT_LAUNCH_CHECK(ctx);
+    if constexpr (VS != 1) {    // batched matrices: one inverse diagonal per system
+      cg_pupdate_coarse_kernel<S, 1, 4, VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
+                                                                                coarse_dev(*A.coarse));
+    } else if (ctx->tune_pupdate_np == 1 && ctx->tune_pupdate_occ == 5)
+      cg_pupdate_coarse_kernel<S, 1, 5><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
+                                                                            coarse_dev(*A.coarse));
+    else if (ctx->tune_pupdate_np == 1 && ctx->tune_pupdate_occ == 6)
+      cg_pupdate_coarse_kernel<S, 1, 6><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
+                                                                            coarse_dev(*A.coarse));
+    else if (ctx->tune_pupdate_np == 1)
+      cg_pupdate_coarse_kernel<S, 1><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
+                                                                         coarse_dev(*A.coarse));
+    else
+      cg_pupdate_coarse_kernel<S, 2><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
+                                                                         coarse_dev(*A.coarse));
+    PT_LAUNCH_CHECK(ctx);
   } else {
     cg_update_kernel<S, VS, false><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.q.p, A.dinv, w.r.p, w.partial.p, w.scal.p,
                                                                        w.ticket.p, 0);
@@ -1405,14 +1406,12 @@ int pcg_start(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int prec
     cg_pupdate_kernel<S, VS, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, nullptr, A.dinv, w.p.p, x, w.scal.p, 1);
     PT_LAUNCH_CHECK(ctx);
   } else if (precond == PTFEM_PRECOND_TWOLEVEL) {
-    if constexpr (VS == 1) {
-      PT_TRY(coarse_apply(ctx, *A.coarse, S, w.r.p));
-      rho_finalize_kernel<<<1, 32, 0, ctx->stream>>>(w.scal.p, A.coarse->cdot.p, A.coarse->nlev, S);
-      PT_LAUNCH_CHECK(ctx);
-      cg_pupdate_coarse_kernel<S, 1><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 1,
-                                                                         coarse_dev(*A.coarse));
-      PT_LAUNCH_CHECK(ctx);
-    }
+    PT_TRY(coarse_apply(ctx, *A.coarse, S, w.r.p));
+    rho_finalize_kernel<<<1, 32, 0, ctx->stream>>>(w.scal.p, A.coarse->cdot.p, A.coarse->nlev, S);
+    PT_LAUNCH_CHECK(ctx);
+    cg_pupdate_coarse_kernel<S, 1, 4, VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 1,
+                                                                              coarse_dev(*A.coarse));
+    PT_LAUNCH_CHECK(ctx);
   } else {
     PT_TRY((cheb_apply<S, VS>(ctx, A, w, variant, degree)));
     dots_kernel<S, VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, w.z.p, nullptr, w.partial.p, w.scal.p, SC_RHO, -1,
@@ -1433,8 +1432,8 @@ int pcg_solve_t(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_o
   const int check = o.check_every > 0 ? o.check_every : (precond == PTFEM_PRECOND_TWOLEVEL ? 10 : 50);
   double* h = ctx->h_pinned;  // >= SC_COUNT*kMaxSys doubles
   int spmv_calls = 0;
-  if (precond == PTFEM_PRECOND_TWOLEVEL && (VS != 1 || !A.coarse))
-    return set_err(PTFEM_ERR_STATE, "two-level preconditioner: coarse spaces not prepared (needs one shared matrix)");
+  if (precond == PTFEM_PRECOND_TWOLEVEL && (!A.coarse || A.coarse->VS != VS))
+    return set_err(PTFEM_ERR_STATE, "two-level preconditioner: coarse spaces not prepared for this system");
 
   if (precond == PTFEM_PRECOND_CHEBYSHEV) {
     const size_t n = (size_t)A.nn * S;

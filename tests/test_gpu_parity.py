@@ -381,15 +381,60 @@ def test_twolevel_too_fine_grid_is_reported(gpu_ctx):
     dm.close()
 
 
-def test_twolevel_needs_shared_matrix_and_auto_choice(gpu_ctx):
-    m = meshgen.synth_slab("XS")
+def test_twolevel_batched_matrices_small_mesh_and_auto_choice(gpu_ctx):
+    # batched matrices (one value set per system, step04's levels): every system gets its own Galerkin operators on the shared
+    # grids - same answers as the direct solve, iteration count of the slowest system as the restatement predicts
+    from oracle import coarse_oracle as cz
+    m = meshgen.synth_slab("S", interfaces_as_103=False)
     dm = dm_for(gpu_ctx, m)
-    sigs = [{**SIGMA5, 4: s, 5: s} for s in (5e-3, 0.5)]
+    sig_c = (5e-5, 5e-3, 0.5)
+    sigs = [{**SIGMA5, 4: s, 5: s} for s in sig_c]
     dm.assemble(sigs).bc_reset(1).neumann(101, 15.975).dirichlet(102, 0.0)
-    with pytest.raises(engine.PtfemError):
-        dm.solve(precond=engine.PRECOND_TWOLEVEL)
-    dm.solve(precond=engine.PRECOND_AUTO)                       # batched matrices / small mesh -> Jacobi
+    dm.solve(precond=engine.PRECOND_AUTO)                       # small mesh -> Jacobi
     assert dm.last_stats["precond"] == engine.PRECOND_JACOBI and dm.last_stats["converged"] == 1
+    it_j = dm.last_stats["iterations"]
+    phi = dm.solve(precond=engine.PRECOND_TWOLEVEL, coarse_nodes=300, coarse_levels=1, check_every=1, use_graph=0, rtol=1e-10)
+    st = dm.last_stats
+    assert st["converged"] == 1 and st["precond"] == engine.PRECOND_TWOLEVEL and st["iterations"] * 3 < it_j
+    its = []
+    for k, sg in enumerate(sigs):
+        ref = fo.solve_case(m, sg, [(102, 0.0)], [(101, 15.975)], recover=None)
+        assert rel(phi[k], ref["phi"]) < TOL_PHI, k
+        K_raw = fo.assemble_stiffness(m.nodes, m.tets, m.region, sg)
+        is_dir, val = fo.dirichlet_nodes(m.tris, m.bcid, [(102, 0.0)], m.nn)
+        K, b = fo.apply_dirichlet_symmetric(K_raw, fo.neumann_rhs(m.nodes, m.tris, m.bcid, [(101, 15.975)]), is_dir, val)
+        M = cz.CoarsePreconditioner(K.tocsr(), m.nodes, is_dir, coarse_nodes=300, extra_levels=1)
+        its.append(cz.pcg(K.tocsr(), b, M.apply, rtol=1e-10)[1])
+    assert abs(st["iterations"] - max(its)) <= 2, (st["iterations"], its)     # the batch runs until its slowest system is done
+    # the same matrices one at a time give the same potentials (shared operators path)
+    for k, sg in enumerate(sigs):
+        dm.assemble(sg).bc_reset(1).neumann(101, 15.975).dirichlet(102, 0.0)
+        one = dm.solve(precond=engine.PRECOND_TWOLEVEL, coarse_nodes=300, coarse_levels=1, rtol=1e-10)[0]
+        assert rel(phi[k], one) < 1e-7, k
+    dm.close()
+
+
+def test_twolevel_batched_matrices_step04_levels_on_size_M(gpu_ctx, golden):
+    # the 15 contact conductivities of the reference's pressure sweep (run_pressure_sweep.py:709-738) as ONE batched solve on
+    # the 2.5 M-tet slab: the automatic choice is the coarse-grid preconditioner, every level agrees with the C oracle
+    import yaml
+    from oracle import c_oracle as co
+    co.use_all_cores()
+    levels = yaml.safe_load((golden / "step04_params.yaml").read_text())["pressure_sweep"]["sigma_contact_Spm"]
+    m = meshgen.synth_slab("M")
+    dm = dm_for(gpu_ctx, m)
+    sigs = [{**SIGMA5, 4: s, 5: s} for s in levels]
+    dm.assemble(sigs).bc_reset(1).neumann(101, 15.975015).dirichlet(102, 0.0)
+    phi = dm.solve(rtol=1e-11)
+    st = dm.last_stats
+    assert st["precond"] == engine.PRECOND_TWOLEVEL and st["converged"] == 1 and phi.shape == (15, m.nn)
+    it_batch = st["iterations"]
+    for k in (0, 7, 14):
+        cs = co.CSystem(m, sigs[k], [(102, 0.0)], [(101, 15.975015)])
+        phi_o, it_o, relres = cs.pcg_coarse(rtol=1e-13, maxit=100000)
+        assert relres <= 1e-13 and rel(phi[k], phi_o) < TOL_PHI, k
+    dm.solve(rtol=1e-11, precond=engine.PRECOND_JACOBI, raise_on_noconv=False, maxit=20000)
+    assert dm.last_stats["iterations"] > 8 * it_batch                # what the batch cost before: Jacobi on every level
     dm.close()
 
 
