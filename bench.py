@@ -406,7 +406,10 @@ def main():
                     help="reference arm: skip the sparse direct solve (the reference's solver class) on a small slab")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-pipelines", type=int, default=2, help="sweep pipelines (host thread + context) per GPU of the end-to-end leg")
+    ap.add_argument("--e2e-pipelines", type=int, default=0,
+                    help="sweep pipelines (host thread + context) per GPU of the end-to-end leg; 0 = 2 on one GPU, 1 per GPU under torchrun "
+                         "(measured on L: 98.4 vs 91.2 solves/s with 2 vs 1 pipelines at N = 1, 171 vs 180 at N = 2: the ranks' pipelines "
+                         "then compete for the host's PCIe path)")
     ap.add_argument("--no-partitioned", action="store_true", help="N > 1: skip the row-partitioned single-solve extra")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="transport of the row-partitioned solve")
     ap.add_argument("--partitioned-precond", default="auto", choices=["auto", "jacobi"],
@@ -427,7 +430,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — this engine has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
-    numa_cpus = engine.bind_host_to_gpu(local_rank)   # before any host buffer of the sweep exists (pinned staging, mesh arrays)
+    numa_info = {}
+    numa_cpus = engine.bind_host_to_gpu(local_rank, numa_info)   # before any host buffer of the sweep exists (pinned staging, mesh arrays)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -518,7 +522,7 @@ def main():
         # released (which waits for its copies) once the next pattern is built.  Across pipelines the GPU overlaps one's
         # latency-bound phases (upload, pattern, host gaps) with the other's bandwidth-bound solve.
         from pelvistim_fem_b200 import sweep as sweep_mod
-        P = max(1, args.e2e_pipelines)
+        P = args.e2e_pipelines if args.e2e_pipelines > 0 else (2 if world == 1 else 1)
         new_out = lambda: (torch.empty((args.nconf, mesh.nn), dtype=torch.float64).pin_memory().numpy(),
                            torch.empty((args.nconf, mesh.nn, 3), dtype=torch.float64).pin_memory().numpy())
         pipe_outs = [[(phi_out, J_out) if k == 0 else new_out(), new_out()] for k in range(P)]
@@ -562,7 +566,8 @@ def main():
             t_e2e = float(t.item())
         e2e = {"value": world * args.nconf * n_e2e / t_e2e, "unit": "solves/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
-               "pipelines_per_gpu": P, "host_cpus_bound_to_gpu_numa_node": None if numa_cpus is None else len(numa_cpus)}
+               "pipelines_per_gpu": P, "host_cpus_bound_to_gpu_numa_node": None if numa_cpus is None else len(numa_cpus),
+               "numa": numa_info}
 
     # ---- N > 1 extra: the same mesh as ONE row-partitioned solve over all ranks (config #5, strong scaling) -------
     part = None

@@ -179,30 +179,38 @@ def _parse_cpulist(text):
     return cpus
 
 
-def bind_host_to_gpu(device=0):
+def bind_host_to_gpu(device=0, info=None):
     """Restrict the calling process to the CPUs of the NUMA node the GPU is attached to (``/sys/bus/pci/devices/<bus id>/
     local_cpulist``), so that the host buffers it allocates afterwards - pinned staging for the mesh upload and the phi / J
     read-back above all - are first touched on that node and the copies do not cross the socket interconnect.  One process
     per GPU makes this matter: eight ranks stream 1.3 GB per sweep step each.  Returns the CPU set applied, or None when the
-    topology is not exposed (single-node hosts, containers without sysfs) or the set would be empty."""
+    topology is not exposed (single-node hosts, containers without sysfs) or the set would be empty or change nothing.
+    ``info``: optional dict that receives what was found (bus id, local CPUs, allowed CPUs)."""
     import os
+    info = info if info is not None else {}
     L = load_library()
     buf = C.create_string_buffer(32)
     if L.ptfem_device_pci_bus_id(int(device), buf, 32) != 0:
+        info["why"] = "no PCI bus id"
         return None
     bus = buf.value.decode().lower()
+    info["bus"] = bus
     try:
         with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
             local = _parse_cpulist(f.read())
         allowed = os.sched_getaffinity(0)
-    except (OSError, ValueError, AttributeError):
+    except (OSError, ValueError, AttributeError) as e:
+        info["why"] = f"topology not readable: {type(e).__name__}"
         return None
+    info["local_cpus"], info["allowed_cpus"] = len(local), len(allowed)
     cpus = local & allowed
     if not cpus or cpus == allowed:
+        info["why"] = "GPU-local CPUs are all the process may use already" if cpus else "no GPU-local CPU allowed"
         return None
     try:
         os.sched_setaffinity(0, cpus)
-    except OSError:
+    except OSError as e:
+        info["why"] = f"sched_setaffinity: {e}"
         return None
     return sorted(cpus)
 
