@@ -489,10 +489,12 @@ def main():
     launches = ctx.launches - launches0
     t_dev = ev0.elapsed_time(ev1) * 1e-3
     barrier()
+    rank_ms = None
     if dist is not None:
-        t = torch.tensor([t_dev], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_dev = float(t.item())
+        tl = [torch.zeros(1, device="cuda", dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(tl, torch.tensor([t_dev], device="cuda", dtype=torch.float64))
+        rank_ms = [round(float(v.item()) / args.steps * 1e3, 3) for v in tl]      # per rank, for the spread; the line uses the max
+        t_dev = max(float(v.item()) for v in tl)
     value = world * args.nconf * args.steps / t_dev
     # single right-hand-side streaming SpMV of the CG (the north-star roofline kernel), timed alone
     dm.bc_reset(1); dm.neumann_tris(confs[0]["tris"], I_INJECT / confs[0]["area"]); dm.dirichlet(102, 0.0)
@@ -681,6 +683,8 @@ def main():
                              "ms_per_launch": spmv1_ms, "algorithmic_bytes_per_launch": alg1,
                              "traffic": None if traffic is None else traffic.get("spmv_bytes_per_launch")},
             "sample_metrics": rows[0] if rows else None}
+    if rank_ms is not None:
+        line["ms_per_step_by_rank"] = rank_ms
     if e2e is not None:
         line["e2e"] = e2e
     if part is not None:
