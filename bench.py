@@ -491,10 +491,17 @@ def main():
     barrier()
     rank_ms = None
     if dist is not None:
-        tl = [torch.zeros(1, device="cuda", dtype=torch.float64) for _ in range(world)]
-        dist.all_gather(tl, torch.tensor([t_dev], device="cuda", dtype=torch.float64))
-        rank_ms = [round(float(v.item()) / args.steps * 1e3, 3) for v in tl]      # per rank, for the spread; the line uses the max
-        t_dev = max(float(v.item()) for v in tl)
+        tl = [torch.zeros(4, device="cuda", dtype=torch.float64) for _ in range(world)]
+        cl = clocks.summary()
+        dist.all_gather(tl, torch.tensor([t_dev, last_st["solve_ms"], cl.get("sm_mhz") or 0.0, statistics.mean(iters)], device="cuda",
+                                         dtype=torch.float64))
+        # per rank, for the spread (the line uses the max): step time, PCG solve time of the last step, SM clock under load, PCG
+        # iterations per step - every rank sweeps its OWN electrode positions (sweep_definition(..., rank)), and positions that need
+        # one more 10-iteration chunk make that rank's steps ~7 ms longer: the spread is the workload's, not the machine's
+        rank_ms = {"ms_per_step": [round(float(v[0].item()) / args.steps * 1e3, 2) for v in tl],
+                   "solve_ms": [round(float(v[1].item()), 2) for v in tl], "sm_mhz": [float(v[2].item()) for v in tl],
+                   "pcg_iterations": [round(float(v[3].item()), 1) for v in tl]}
+        t_dev = max(float(v[0].item()) for v in tl)
     value = world * args.nconf * args.steps / t_dev
     # single right-hand-side streaming SpMV of the CG (the north-star roofline kernel), timed alone
     dm.bc_reset(1); dm.neumann_tris(confs[0]["tris"], I_INJECT / confs[0]["area"]); dm.dirichlet(102, 0.0)
@@ -684,7 +691,7 @@ def main():
                              "traffic": None if traffic is None else traffic.get("spmv_bytes_per_launch")},
             "sample_metrics": rows[0] if rows else None}
     if rank_ms is not None:
-        line["ms_per_step_by_rank"] = rank_ms
+        line["by_rank"] = rank_ms
     if e2e is not None:
         line["e2e"] = e2e
     if part is not None:
