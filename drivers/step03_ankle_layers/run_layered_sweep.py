@@ -230,7 +230,7 @@ def _point(args):
                     quiet=sweep.worker_rank() is not None)
 
 
-def run_sweep(p, t_fat_list, elec_r_list, coarse=False, sigma_skin_override=None, gpus=1):
+def run_sweep(p, t_fat_list, elec_r_list, coarse=False, sigma_skin_override=None, gpus=1, pipelines=1):
     RESULTS_DIR.mkdir(exist_ok=True)
     st = _stim(p)
     mode = st.get("control_mode", "voltage")
@@ -244,6 +244,11 @@ def run_sweep(p, t_fat_list, elec_r_list, coarse=False, sigma_skin_override=None
         print("  V_active = 1.0 V  |  V_return = 0 V  (Dirichlet BCs)")
     print(f"{'='*60}\n")
     points = [(p, t_fat, r * 1e-3, coarse, sigma_skin_override, str(RESULTS_DIR)) for t_fat in t_fat_list for r in elec_r_list]
+    if pipelines > 1 and gpus <= 1:
+        # several sweep pipelines on the one GPU (a host thread + context each): one point's meshing / file writing / upload
+        # overlaps another's solve; rows come back in sweep order
+        return sweep.map_points_pipelined(lambda ctx, state, a: run_case(a[0], a[1], a[2], a[3], a[4], ctx=ctx, results_dir=a[5], quiet=True),
+                                          points, device=0, pipelines=pipelines)
     return sweep.map_points(_point, points, gpus=gpus)
 
 
@@ -290,6 +295,7 @@ def main(argv=None):
     ap = argparse.ArgumentParser(description="Ankle layered slab sweep")
     ap.add_argument("--smoke", action="store_true", help="Single coarse case for quick pipeline check")
     ap.add_argument("--gpus", type=int, default=1, help="shard sweep points over this many GPUs")
+    ap.add_argument("--pipelines", type=int, default=1, help="sweep pipelines (host thread + GPU context each) on one GPU")
     ap.add_argument("--fixed-topology", action="store_true",
                     help="fat thickness as node displacement on one mesh per electrode size (pattern and device mesh built once) "
                          "instead of re-meshing every point")
@@ -308,7 +314,7 @@ def main(argv=None):
     if args.fixed_topology:
         results = run_sweep_fixed_topology(p, t_fat_list, r_list, coarse=args.smoke)
     else:
-        results = run_sweep(p, t_fat_list, r_list, coarse=args.smoke, gpus=args.gpus)
+        results = run_sweep(p, t_fat_list, r_list, coarse=args.smoke, gpus=args.gpus, pipelines=args.pipelines)
     save_results(results)
     print(f"\n  {len(results)} case(s) computed → results/summary.csv, results/summary.json")
     return results

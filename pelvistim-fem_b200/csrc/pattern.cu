@@ -40,8 +40,8 @@ __global__ void fill_incidence(const int32_t* __restrict__ elems, int64_t ne, co
 // insertion sort of each (short) list: thread per list.  The lists of a block are one contiguous span of the array: it is
 // brought into shared memory with coalesced loads, every thread sorts its own segment there, and the span goes back the
 // same way (a span that does not fit is sorted in place in global memory, as before).
-constexpr int kSortThreads = 128;
-constexpr int kSortSpan = 8192;      // entries of shared memory per block (64 per list on average)
+constexpr int kSortThreads = 256;
+constexpr int kSortSpan = 12032;     // entries of shared memory per block (47 per list on average)
 __global__ void __launch_bounds__(kSortThreads) sort_lists(const int32_t* __restrict__ ptr, int32_t* __restrict__ list, int64_t n) {
   __shared__ int32_t s_span[kSortSpan];
   const int64_t i0 = (int64_t)blockIdx.x * kSortThreads;

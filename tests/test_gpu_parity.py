@@ -1003,6 +1003,24 @@ def test_step03_driver_reproduces_reference_table(gpu_ctx, golden, tmp_path, mon
         assert (tmp_path / label / f).exists(), f                      # per-case layout of README.md:67-86
 
 
+def test_step03_sweep_pipelines_give_the_same_rows(gpu_ctx, tmp_path, monkeypatch):
+    # two sweep pipelines on one GPU (sweep.PipelinePool: a host thread and a context each): same rows, same order
+    import run_layered_sweep as s3
+    monkeypatch.setattr(s3, "RESULTS_DIR", tmp_path)
+    monkeypatch.setattr(s3.sweep, "worker_context", lambda: gpu_ctx)
+    p = s3.load_params()
+    seq = s3.run_sweep(p, [0.003, 0.005], [5, 10], coarse=True)
+    par = s3.run_sweep(p, [0.003, 0.005], [5, 10], coarse=True, pipelines=2)
+    assert len(seq) == len(par) == 4
+    for a, b in zip(seq, par):
+        assert list(a.keys()) == list(b.keys())
+        for k in a:
+            if isinstance(a[k], float):
+                assert abs(a[k] - b[k]) <= 1e-6 * max(abs(a[k]), 1e-12), k
+            else:
+                assert a[k] == b[k], k
+
+
 def test_step03_smoke_test_script():
     # the reference's own acceptance script for step03 (step03_ankle_layers/smoke_test.py:81-188), as a drop-in beside the driver
     import os, subprocess, sys
