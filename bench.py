@@ -636,6 +636,7 @@ def main():
                         "transport": used, "precond": "jacobi+coarse-grids" if with_coarse else "jacobi",
                         "iterations": res["stats"]["iterations"], "solve_ms": t[1], "first_solve_ms_incl_graph_capture": res["first_solve_ms"], "ms_per_iteration": t[1] / max(res["stats"]["iterations"], 1),
                         "spmv_ms": t[2], "halo_ms": t[3], "allreduce_ms": t[4], "rows_per_rank": res["nloc"], "halo_rows": res["nhalo"],
+                        "true_rel_residual": res.get("true_rel_residual"), "recurrence_rel_residual": res["stats"].get("recurrence_rel_residual"),
                         "single_gpu_same_precond_solve_ms": same_ms, "single_gpu_same_precond_iterations": same_it,
                         "speedup_vs_1gpu": same_ms / t[1], "max_rel_err_vs_single_gpu": t[5],
                         "rel_err_phi_vs_cpu_oracle": part_err_cpu, "cpu_oracle": part_cpu_note,

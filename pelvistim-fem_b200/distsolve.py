@@ -27,12 +27,14 @@ def _allreduce(arr, op="sum"):
 
 
 def partitioned_solve(ctx, mesh, sigma_by_body, dirichlet, neumann, rank, world, check=True, transport="p2p", coarse=True,
-                      force_p2p=False, distributed=False, **opts):
+                      force_p2p=False, distributed=False, true_residual=True, **opts):
     """Returns dict(x_local, row0, stats, timings, nloc, nhalo, rel_err_vs_single).
 
     ``coarse``: precondition with Jacobi + geometric coarse grids (the finest grid vector is summed over the ranks once per
     iteration) when the mesh is large enough for the single-GPU solver to choose them too (>= 100 k nodes); Jacobi otherwise.
     ``force_p2p``: use the peer-memory kernels even with one rank (tests).
+    ``true_residual``: recompute ||b - A x|| / ||b|| of the returned solution on the host from all ranks' rows
+    (``true_rel_residual`` in the result and in ``stats``; the device loop converges on the recurrence residual).
 
     ``distributed=False``: every rank assembles a replica of the whole mesh on its GPU and cuts its row block out of it (the
     mesh must fit one GPU; with ``check`` the single-GPU solve of the replica is timed beside the partitioned one).
@@ -221,6 +223,17 @@ def partitioned_solve(ctx, mesh, sigma_by_body, dirichlet, neumann, rank, world,
     out = dict(x_local=x, row0=blk.row0, nloc=blk.nloc, nhalo=blk.nhalo, stats=ds.last_stats, timings=ds.timings, wall_s=wall,
                transport=used, coarse=state["coarse"], coarse_note=state["note"], first_solve_ms=first_ms, distributed=bool(distributed),
                device_mem_gb=mem_gb, local_nodes=(lm.nn if lm is not None else mesh.nn), local_tets=(lm.tets.shape[0] if lm is not None else mesh.nt))
+    if true_residual:
+        # ||b - A x|| / ||b|| of what came back, recomputed on the host from every rank's rows (the device solver reports the
+        # recurrence residual of the Chronopoulos-Gear iteration, which can drift from the true one on ill-conditioned systems)
+        xg = np.zeros(nn_global)
+        xg[blk.row0:blk.row0 + blk.nloc] = x
+        xg = _allreduce(xg, "sum")
+        u = np.concatenate([xg[blk.row0:blk.row0 + blk.nloc], xg[np.asarray(blk.halo_global, dtype=np.int64)]])
+        r = blk.b - partition.local_spmv(blk, u)
+        sums = _allreduce(np.array([float(r @ r), float(blk.b @ blk.b)]), "sum")
+        out["true_rel_residual"] = float(np.sqrt(sums[0] / max(sums[1], 1e-300)))
+        out["stats"] = dict(out["stats"], true_rel_residual=out["true_rel_residual"], recurrence_rel_residual=out["stats"].get("rel_residual"))
     if check:
         ref = phi_single[blk.row0:blk.row0 + blk.nloc]
         out["rel_err_vs_single"] = float(np.abs(x - ref).max() / max(np.abs(phi_single).max(), 1e-300))

@@ -37,7 +37,8 @@ line = dict(rank=rank, world=world, size=size, transport=res["transport"], coars
             nloc=res["nloc"], nhalo=res["nhalo"], iterations=res["stats"]["iterations"],
             solve_ms=res["stats"]["solve_ms"], first_solve_ms=res["first_solve_ms"], ms_per_iter=res["stats"]["solve_ms"] / max(res["stats"]["iterations"], 1),
             distributed=res["distributed"], device_mem_gb=res["device_mem_gb"], local_nodes=res["local_nodes"], local_tets=res["local_tets"],
-            mesh_nodes=mesh.nn, mesh_tets=mesh.nt, **res["timings"])
+            mesh_nodes=mesh.nn, mesh_tets=mesh.nt, true_rel_residual=res.get("true_rel_residual"),
+            recurrence_rel_residual=res["stats"].get("recurrence_rel_residual"), **res["timings"])
 if not distributed:
     line.update(rel_err_vs_single=res["rel_err_vs_single"], single_gpu_ms=res["single_gpu_ms"], single_gpu_iterations=res["single_gpu_iterations"],
                 single_gpu_coarse_solve_ms=res["single_gpu_auto_solve_ms"], single_gpu_coarse_iterations=res["single_gpu_auto_iterations"])

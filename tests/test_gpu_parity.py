@@ -1097,6 +1097,8 @@ def test_row_partitioned_two_ranks_on_one_gpu(tmp_path, setup):
     assert sorted(d["rank"] for d in lines) == [0, 1]
     for d in lines:
         assert d["transport"] == "p2p" and d["coarse"] is True and d["nhalo"] > 0
+        # the TRUE residual of the returned solution (recomputed on the host from both ranks' rows), not the recurrence's
+        assert d["true_rel_residual"] is not None and d["true_rel_residual"] < 5e-10, d["true_rel_residual"]
         if setup == "replica":
             assert d["rel_err_vs_single"] < TOL_PHI                       # vs the single-GPU solve of the whole system
             assert d["iterations"] * 5 < d["single_gpu_iterations"]       # coarse grids at work (Jacobi needs ~1000)
