@@ -41,38 +41,54 @@ __global__ void fill_incidence(const int32_t* __restrict__ elems, int64_t ne, co
 // brought into shared memory with coalesced loads, every thread sorts its own segment there, and the span goes back the
 // same way (a span that does not fit is sorted in place in global memory, as before).
 constexpr int kSortThreads = 256;
-constexpr int kSortSpan = 12032;     // entries of shared memory per block (47 per list on average)
-__global__ void __launch_bounds__(kSortThreads) sort_lists(const int32_t* __restrict__ ptr, int32_t* __restrict__ list, int64_t n) {
-  __shared__ int32_t s_span[kSortSpan];
+constexpr int kSortSpanMax = 12032;  // entries of shared memory a block may get (47 per list on average)
+__global__ void __launch_bounds__(kSortThreads) sort_lists(const int32_t* __restrict__ ptr, int32_t* __restrict__ list, int64_t n, int span) {
+  extern __shared__ int32_t s_span[];    // [span]: sized by the caller to about twice the block's average share, so short
+                                         // lists leave room for many resident blocks
+  __shared__ int s_changed;
   const int64_t i0 = (int64_t)blockIdx.x * kSortThreads;
   const int64_t i1 = min(n, i0 + kSortThreads);
   const int64_t i = i0 + threadIdx.x;
   const int32_t base = ptr[i0], top = ptr[i1];
-  const bool fits = top - base <= kSortSpan;
+  const bool fits = top - base <= span;
   int32_t* buf = list;
   int32_t off = 0;
+  if (threadIdx.x == 0) s_changed = 0;
   if (fits) {
     for (int32_t k = threadIdx.x; k < top - base; k += kSortThreads) s_span[k] = list[base + k];
-    __syncthreads();
     buf = s_span;
     off = base;
   }
+  __syncthreads();
   if (i < n) {
     const int32_t b = ptr[i] - off, e = ptr[i + 1] - off;
+    bool changed = false;
     for (int32_t k = b + 1; k < e; ++k) {
       const int32_t v = buf[k];
       int32_t j = k - 1;
       while (j >= b && buf[j] > v) {
         buf[j + 1] = buf[j];
         --j;
+        changed = true;
       }
       buf[j + 1] = v;
     }
+    if (changed) s_changed = 1;
   }
   if (fits) {
     __syncthreads();
-    for (int32_t k = threadIdx.x; k < top - base; k += kSortThreads) list[base + k] = s_span[k];
+    if (s_changed)     // lists that arrived in order (most do) are not written back
+      for (int32_t k = threadIdx.x; k < top - base; k += kSortThreads) list[base + k] = s_span[k];
   }
+}
+// launch with a span of about twice the average share of a block
+static int launch_sort_lists(ptfem_ctx* ctx, const int32_t* ptr, int32_t* list, int64_t n, int64_t total) {
+  if (n <= 0) return PTFEM_OK;
+  int64_t span = 2 * ((total * kSortThreads + n - 1) / n) + 256;
+  if (span > kSortSpanMax) span = kSortSpanMax;
+  sort_lists<<<ceil_div(n, kSortThreads), kSortThreads, (size_t)span * sizeof(int32_t), ctx->stream>>>(ptr, list, n, (int)span);
+  PT_LAUNCH_CHECK(ctx);
+  return PTFEM_OK;
 }
 
 // ---- rows: sorted unique neighbour list of every node ------------------------------------------
@@ -132,7 +148,7 @@ __global__ void row_copy(const int32_t* __restrict__ n2t_ptr, const int32_t* __r
 
 // ---- element -> nnz map ---------------------------------------------------------------------------
 __global__ void build_e2nnz(const int32_t* __restrict__ tets, int64_t nt, const int32_t* __restrict__ rowptr,
-                            const int32_t* __restrict__ col, int32_t* __restrict__ e2nnz) {
+                            const int32_t* __restrict__ col, int32_t* __restrict__ e2nnz, int32_t* __restrict__ gcount) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (tet, local row)
   if (t >= nt * 4) return;
   const int64_t e = t >> 2;
@@ -148,13 +164,8 @@ __global__ void build_e2nnz(const int32_t* __restrict__ tets, int64_t nt, const 
       if (col[mid] < target) lo = mid + 1; else hi = mid;
     }
     e2nnz[e * 16 + a * 4 + c] = lo;
+    atomicAdd(&gcount[lo], 1);      // contributions per non-zero (counting only: the order is fixed by the sort below)
   }
-}
-
-__global__ void count_contrib(const int32_t* __restrict__ e2nnz, int64_t n, int32_t* __restrict__ cnt) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  atomicAdd(&cnt[e2nnz[i]], 1);
 }
 
 __global__ void fill_contrib(const int32_t* __restrict__ e2nnz, int64_t n, const int32_t* __restrict__ gptr,
@@ -264,8 +275,7 @@ int build_incidence(ptfem_ctx* ctx, const int32_t* elems, int64_t ne, int64_t nn
     PT_TRY(fill_i32(ctx, cursor.p, 0, nn + 1));
     fill_incidence<NV><<<ceil_div(ne, 256), 256, 0, ctx->stream>>>(elems, ne, ptr.p, cursor.p, list.p);
     PT_LAUNCH_CHECK(ctx);
-    sort_lists<<<ceil_div(nn, kSortThreads), kSortThreads, 0, ctx->stream>>>(ptr.p, list.p, nn);
-    PT_LAUNCH_CHECK(ctx);
+    PT_TRY(launch_sort_lists(ctx, ptr.p, list.p, nn, total));
   }
   PT_CK(cudaStreamSynchronize(ctx->stream));  // cursor goes out of scope
   return PTFEM_OK;
@@ -302,14 +312,10 @@ int ptfem_build_pattern(ptfem_mesh* m) {
 
   // element -> nnz and its inverse (nnz -> sorted list of tet*16+ij)
   PT_TRY(m->e2nnz.alloc((size_t)16 * nt));
-  if (nt > 0) {
-    build_e2nnz<<<ceil_div(nt * 4, 256), 256, 0, ctx->stream>>>(m->tets.p, nt, m->rowptr.p, m->col.p, m->e2nnz.p);
-    PT_LAUNCH_CHECK(ctx);
-  }
   PT_TRY(m->gptr.alloc(nnz + 1));
   PT_TRY(fill_i32(ctx, m->gptr.p, 0, nnz + 1));
   if (nt > 0) {
-    count_contrib<<<ceil_div(nt * 16, 256), 256, 0, ctx->stream>>>(m->e2nnz.p, nt * 16, m->gptr.p);
+    build_e2nnz<<<ceil_div(nt * 4, 256), 256, 0, ctx->stream>>>(m->tets.p, nt, m->rowptr.p, m->col.p, m->e2nnz.p, m->gptr.p);
     PT_LAUNCH_CHECK(ctx);
   }
   int64_t total = 0;
@@ -323,8 +329,7 @@ int ptfem_build_pattern(ptfem_mesh* m) {
     PT_TRY(fill_i32(ctx, cursor.p, 0, nnz + 1));
     fill_contrib<<<ceil_div(nt * 16, 256), 256, 0, ctx->stream>>>(m->e2nnz.p, nt * 16, m->gptr.p, cursor.p, m->gsrc.p);
     PT_LAUNCH_CHECK(ctx);
-    sort_lists<<<ceil_div(nnz, kSortThreads), kSortThreads, 0, ctx->stream>>>(m->gptr.p, m->gsrc.p, nnz);
-    PT_LAUNCH_CHECK(ctx);
+    PT_TRY(launch_sort_lists(ctx, m->gptr.p, m->gsrc.p, nnz, total));
     PT_CK(cudaStreamSynchronize(ctx->stream));
   }
 
