@@ -1067,6 +1067,7 @@ int apply_t(ptfem_ctx* ctx, CoarseSpace& cs, const double* r) {
   for (int l = 0; l < cs.nlev; ++l) {
     CoarseLevel& L = cs.lev[l];
     double* cdot = cs.cdot.p + (size_t)l * 16;
+    // (24 CTAs per SM for the finest level's gather, one element per thread, measured slower: 0.813 vs 0.780 ms per iteration)
     const int ngrid = std::min(ceil_div(L.k * S, 256), 4 * ctx->sm_count);
     // one operator per system (batched matrices): system s reads binv + s * bs
     const int64_t bs = cs.VS > 1 ? (L.exact ? (int64_t)L.kp * L.kp : L.k) : 0;
