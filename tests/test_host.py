@@ -323,3 +323,75 @@ def test_vtu_bytes_follow_the_vtk_xml_appended_raw_layout(tmp_path):
     assert np.array_equal(arrays[("Points", None)], m.nodes) and np.array_equal(arrays[("PointData", "potential")], phi)
     assert np.array_equal(arrays[("PointData", "volume current")], J) and np.array_equal(arrays[("CellData", "GeometryIds")], gid)
     assert np.array_equal(conn[:4 * m.nt].reshape(-1, 4), m.tets) and np.array_equal(conn[4 * m.nt:].reshape(-1, 3), m.tris)
+
+
+# -- sweep pipelines (host threads + contexts on one GPU): host logic with a stand-in for the device context ----------------
+class _FakeContext:
+    made = []
+
+    def __init__(self, device):
+        self.device, self.closed, self.synced = device, False, 0
+        _FakeContext.made.append(self)
+
+    def sync(self):
+        self.synced += 1
+
+    def close(self):
+        self.closed = True
+
+
+def test_pipeline_pool_order_state_finish_and_errors(monkeypatch):
+    import threading
+    monkeypatch.setattr(engine, "Context", _FakeContext)
+    _FakeContext.made = []
+    pool = sweep.PipelinePool(device=3, pipelines=2)
+    seen = []
+
+    def fn(ctx, state, pt):
+        state["count"] = state.get("count", 0) + 1
+        seen.append((state["pipeline"], pt, threading.current_thread().name))
+        return (pt, ctx.device, state["pipeline"])
+
+    finished = []
+    out = pool.map(fn, range(7), finish=lambda ctx, st: finished.append((st["pipeline"], st["count"])))
+    assert [o[0] for o in out] == list(range(7)) and all(o[1] == 3 for o in out)       # results in point order
+    assert [o[2] for o in out] == [0, 1, 0, 1, 0, 1, 0]                                # point i -> pipeline i mod P
+    assert sorted(finished) == [(0, 4), (1, 3)]                                        # finish once per pipeline, private state
+    per = {k: [p for q, p, _ in seen if q == k] for k in (0, 1)}
+    assert per[0] == [0, 2, 4, 6] and per[1] == [1, 3, 5]                              # each pipeline keeps its own order
+    out2 = pool.map(fn, range(3))                                                      # threads, contexts and state persist
+    assert len(_FakeContext.made) == 2 and [o[0] for o in out2] == [0, 1, 2]
+    assert sorted(n for _, _, n in seen if n.startswith("ptfem-pipeline"))[0] == "ptfem-pipeline-0"
+
+    def boom(ctx, state, pt):
+        if pt == 1:
+            raise ValueError("point 1 failed")
+        return pt
+    with pytest.raises(ValueError, match="point 1 failed"):
+        pool.map(boom, range(4))
+    assert pool.map(fn, [5])[0][0] == 5                                                # the pool survives a failed map
+    pool.close()
+    assert all(c.closed for c in _FakeContext.made)
+    assert sweep.map_points_pipelined(lambda c, s, p: p * 2, [1, 2, 3], pipelines=2) == [2, 4, 6]
+
+
+def test_cpulist_parser_and_numa_binding_without_topology():
+    assert engine._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert engine._parse_cpulist("") == set()
+
+
+def test_graded_electrode_box_mesh_is_closed_and_tagged():
+    # step02 geometry on the size-field mesher: polygonal patches of the right area, every external face tagged, parents found
+    from pelvistim_fem_b200 import sizefield_mesher as sm
+    r = 0.010
+    m = sm.electrode_box_graded(0.15, 0.15, 0.05, (0.045, 0.075), (0.105, 0.075), r, "circle")
+    n = round(2 * np.pi * r / (r / 3.5))
+    poly = 0.5 * n * r * r * np.sin(2 * np.pi / n)
+    assert abs(m.meta["area_active"] - poly) < 1e-12 and abs(m.meta["area_return"] - poly) < 1e-12
+    ext, _ = meshgen.external_faces(m.tets)
+    key = lambda a: set(map(tuple, np.sort(a, axis=1).tolist()))
+    assert key(ext) == key(m.tris) and (m.tri_parent >= 0).all()
+    assert abs(meshgen.tet_volumes(m.nodes, m.tets).sum() - 0.15 * 0.15 * 0.05) < 1e-12
+    assert set(np.unique(m.bcid)) == {101, 102, 103}
+    sq = sm.electrode_box_graded(0.15, 0.15, 0.05, (0.045, 0.075), (0.105, 0.075), r, "square")
+    assert abs(sq.meta["area_active"] - (2 * r) ** 2) < 1e-12                          # square patches are exact
