@@ -332,10 +332,13 @@ int window_plan_build(ptfem_mesh* m) {
   PT_TRY(fill_i32(ctx, stats.p, 0, 4));
   PT_CK(cudaMemsetAsync(wsum.p, 0, sizeof(unsigned long long), ctx->stream));
   const size_t dyn = (size_t)kMaxSpanWords * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PT_CK(cudaFuncSetAttribute(build_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    attr_set = true;
+  {   // (function attributes are per device: remembered per context, like the solver's kernels)
+    const void* fn = reinterpret_cast<const void*>(&build_tiles_kernel);
+    auto it = ctx->func_smem.find(fn);
+    if (it == ctx->func_smem.end() || it->second < dyn) {
+      PT_CK(cudaFuncSetAttribute(build_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+      ctx->func_smem[fn] = dyn;
+    }
   }
   build_tiles_kernel<<<(unsigned)ntiles, kPlanThreads, dyn, ctx->stream>>>(m->win_trow0.p, m->rowptr.p, m->col.p, m->win_rowid.p, unit_off.p,
                                                                           m->win_tiles.p, m->win_ranges.p, m->win_blob.p, stats.p, wsum.p);
