@@ -229,6 +229,7 @@ int ptfem_ctx_create(int device, ptfem_ctx** out) {
     const double w = atof(e);
     if (w > 0.0) c->tune_coarse_weight = w;
   }
+  if (const char* e = getenv("PTFEM_FUSE_UPDATE")) c->tune_fuse_update = atoi(e);
   if (const char* e = getenv("PTFEM_SPMM_WINDOW")) c->tune_window = atoi(e);
   if (const char* e = getenv("PTFEM_WINDOW_BX")) c->tune_window_bx = atoi(e);
   if (const char* e = getenv("PTFEM_WINDOW_CTAS")) c->tune_window_ctas = atoi(e);

@@ -65,19 +65,53 @@ __global__ void cell_ptr_kernel(const int32_t* __restrict__ key, int64_t nn, int
   for (int64_t c = lo + 1; c <= hi; ++c) cellptr[c] = (int32_t)p;
 }
 
+// last CTA of the grid (ticket) — same protocol as solver.cu
+__device__ __forceinline__ bool last_block(unsigned int* ticket) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicInc(ticket, gridDim.x - 1);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
 // ---- restriction: per-cell partials -------------------------------------------------------------------------
 // One warp per task = (cell, split index); lane = (row slot, system pair).  part[task][corner][s] = sum over the
 // task's rows of w_corner(row) r[row][s]: registers and shuffles only, fixed order, no atomics.
-template <int S, int OCC>
+// FUSE: the CG residual update rides along - r[row] -= alpha q[row] is applied to every row as it is gathered (each mesh row
+// sits in exactly one task), written back, and r.D^-1 r / r.r are accumulated; the separate pass of cg_update_kernel over
+// r, q and the inverse diagonal is gone (one launch and one read of r less per iteration).  fu.* are only read when FUSE.
+struct FusedUpdate {
+  const double* q = nullptr;        // [nn][S]
+  const double* dinv = nullptr;     // [nn] (one shared matrix)
+  const double* alpha = nullptr;    // [S] device scalars
+  double* r = nullptr;              // [nn][S] updated in place
+  double* partial = nullptr;        // [grid][2][S]
+  unsigned int* ticket = nullptr;
+  double* out_rz = nullptr;         // [S] r.D^-1 r (Jacobi part of rho)
+  double* out_rr = nullptr;         // [S]
+};
+template <int S, int OCC, bool FUSE = false>
 __global__ void __launch_bounds__(256, OCC) restrict_cell_kernel(int64_t ntask, int split, int shift, const int32_t* __restrict__ cellptr,
                                                             const int32_t* __restrict__ rows, const float4* __restrict__ ctab0,
-                                                            const double* __restrict__ r, double* __restrict__ part) {
+                                                            const double* __restrict__ r, double* __restrict__ part, FusedUpdate fu) {
   constexpr int NP = S >= 2 ? S / 2 : 1;  // lanes per row
   constexpr int NV = S >= 2 ? 2 : 1;      // systems per lane
   constexpr int RPW = 32 / NP;            // rows per warp trip
   const int lane = threadIdx.x & 31;
   const int pr = lane % NP, slot = lane / NP;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  double alpha[NV], dz[NV], dr[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    alpha[v] = FUSE ? fu.alpha[NV * pr + v] : 0.0;
+    dz[v] = 0.0;
+    dr[v] = 0.0;
+  }
   for (int64_t w = warp0; w < ntask; w += nwarp) {
     const int64_t c = w / split;
     const int sp = (int)(w % split);
@@ -93,7 +127,19 @@ __global__ void __launch_bounds__(256, OCC) restrict_cell_kernel(int64_t ntask, 
       const int32_t ia = __ldg(rows + p), ib = pb < p1 ? __ldg(rows + pb) : -1;
       const CoarseRaw ra = coarse_row_load(ctab0, p), rb = coarse_row_load(ctab0, pb < p1 ? pb : p);
       double va[NV], vb[NV];
-      if constexpr (NV == 2) {
+      if constexpr (FUSE) {          // r is rewritten by this kernel: plain loads, through the writable pointer
+        if constexpr (NV == 2) {
+          const double2 x = *reinterpret_cast<const double2*>(fu.r + (size_t)ia * S + 2 * pr);
+          va[0] = x.x;
+          va[1] = x.y;
+          const double2 y = ib >= 0 ? *reinterpret_cast<const double2*>(fu.r + (size_t)ib * S + 2 * pr) : make_double2(0.0, 0.0);
+          vb[0] = y.x;
+          vb[1] = y.y;
+        } else {
+          va[0] = fu.r[ia];
+          vb[0] = ib >= 0 ? fu.r[ib] : 0.0;
+        }
+      } else if constexpr (NV == 2) {
         const double2 x = __ldg(reinterpret_cast<const double2*>(r + (size_t)ia * S + 2 * pr));
         va[0] = x.x;
         va[1] = x.y;
@@ -103,6 +149,37 @@ __global__ void __launch_bounds__(256, OCC) restrict_cell_kernel(int64_t ntask, 
       } else {
         va[0] = __ldg(r + ia);
         vb[0] = ib >= 0 ? __ldg(r + ib) : 0.0;
+      }
+      if constexpr (FUSE) {
+        double qa[NV], qb[NV];
+        if constexpr (NV == 2) {
+          const double2 x = __ldg(reinterpret_cast<const double2*>(fu.q + (size_t)ia * S + 2 * pr));
+          qa[0] = x.x;
+          qa[1] = x.y;
+          const double2 y = ib >= 0 ? __ldg(reinterpret_cast<const double2*>(fu.q + (size_t)ib * S + 2 * pr)) : make_double2(0.0, 0.0);
+          qb[0] = y.x;
+          qb[1] = y.y;
+        } else {
+          qa[0] = __ldg(fu.q + ia);
+          qb[0] = ib >= 0 ? __ldg(fu.q + ib) : 0.0;
+        }
+        const double da = __ldg(fu.dinv + ia), db = ib >= 0 ? __ldg(fu.dinv + ib) : 0.0;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          va[v] = fma(-alpha[v], qa[v], va[v]);
+          vb[v] = fma(-alpha[v], qb[v], vb[v]);
+          dz[v] = fma(va[v] * da, va[v], dz[v]);
+          dr[v] = fma(va[v], va[v], dr[v]);
+          dz[v] = fma(vb[v] * db, vb[v], dz[v]);
+          dr[v] = fma(vb[v], vb[v], dr[v]);
+        }
+        if constexpr (NV == 2) {
+          *reinterpret_cast<double2*>(fu.r + (size_t)ia * S + 2 * pr) = make_double2(va[0], va[1]);
+          if (ib >= 0) *reinterpret_cast<double2*>(fu.r + (size_t)ib * S + 2 * pr) = make_double2(vb[0], vb[1]);
+        } else {
+          fu.r[ia] = va[0];
+          if (ib >= 0) fu.r[ib] = vb[0];
+        }
       }
       int cc[3];
       double t[3], wgt[8];
@@ -173,20 +250,39 @@ __global__ void __launch_bounds__(256, OCC) restrict_cell_kernel(int64_t ntask, 
       }
     }
   }
-}
-
-// last CTA of the grid (ticket) — same protocol as solver.cu
-__device__ __forceinline__ bool last_block(unsigned int* ticket) {
-  __shared__ int s_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int t = atomicInc(ticket, gridDim.x - 1);
-    s_last = (t == gridDim.x - 1);
+  if constexpr (FUSE) {
+    // r.D^-1 r and r.r per system: slot 2*tid + v of the block belongs to system (2*tid + v) mod S (NV == 2) / system 0; fixed
+    // order inside the block, the last block adds the blocks up in order
+    __shared__ double s_red[2][NV * 256];
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      s_red[0][NV * tid + v] = dz[v];
+      s_red[1][NV * tid + v] = dr[v];
+    }
+    __syncthreads();
+    if (tid < 2 * S) {
+      const int qn = tid / S, sys = tid % S;
+      double t = 0.0;
+      for (int k = sys; k < NV * 256; k += S) t += s_red[qn][k];
+      fu.partial[(size_t)blockIdx.x * 2 * S + tid] = t;
+    }
+    if (last_block(fu.ticket)) {
+      // thread t: slot t % 2S of blocks t / 2S, t / 2S + G, ...; then the G group sums in order
+      constexpr int G = 256 / (2 * S);
+      const int k = tid % (2 * S), g = tid / (2 * S);
+      double t = 0.0;
+      for (unsigned int b = g; b < gridDim.x; b += G) t += __ldcg(fu.partial + (size_t)b * 2 * S + k);
+      __syncthreads();
+      s_red[0][tid] = t;
+      __syncthreads();
+      if (tid < 2 * S) {
+        double tot = 0.0;
+        for (int gg = 0; gg < G; ++gg) tot += s_red[0][gg * 2 * S + tid];
+        if (tid < S) fu.out_rz[tid] = tot; else fu.out_rr[tid - S] = tot;
+      }
+    }
   }
-  __syncthreads();
-  if (s_last) __threadfence();
-  return s_last != 0;
 }
 
 // CTA sum per system of one value per thread whose system is threadIdx.x % S; result -> dpart[blockIdx.x][S];
@@ -1046,21 +1142,28 @@ int chain_launch(ptfem_ctx* ctx, CoarseSpace& cs, bool do_node, bool scaled0) {
 }
 
 template <int S>
-int apply_t(ptfem_ctx* ctx, CoarseSpace& cs, const double* r) {
+int apply_t(ptfem_ctx* ctx, CoarseSpace& cs, const double* r, const FusedUpdate* fu = nullptr) {
   // mesh -> finest grid
   CoarseLevel& L0 = cs.lev[0];
   {
     const int64_t ntask = L0.ncell * L0.split;
+    if (fu) {
+      // with the CG residual update fused in (r is rewritten): the grid stays within the CG workspace's partial sums
+      const int grid = (int)std::min<int64_t>((ntask + 7) / 8, (int64_t)ctx->sm_count * 8);
+      restrict_cell_kernel<S, 3, true><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p, r,
+                                                                      L0.part.p, *fu);
+    } else {
     const int grid = (int)std::min<int64_t>((ntask + 7) / 8, (int64_t)ctx->sm_count * 32);
     if (ctx->tune_restrict_occ >= 6)
       restrict_cell_kernel<S, 6><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p, r,
-                                                                L0.part.p);
+                                                                L0.part.p, FusedUpdate());
     else if (ctx->tune_restrict_occ >= 3)
       restrict_cell_kernel<S, 4><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p, r,
-                                                                L0.part.p);
+                                                                L0.part.p, FusedUpdate());
     else
       restrict_cell_kernel<S, 2><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p,
-                                                                r, L0.part.p);
+                                                                r, L0.part.p, FusedUpdate());
+    }
     PT_LAUNCH_CHECK(ctx);
   }
   if (cs.chain_grid > 0) return chain_launch<S>(ctx, cs, true, false);
@@ -1112,6 +1215,21 @@ int coarse_apply(ptfem_ctx* ctx, CoarseSpace& cs, int S, const double* r) {
     case 4: return apply_t<4>(ctx, cs, r);
     case 8: return apply_t<8>(ctx, cs, r);
     case 16: return apply_t<16>(ctx, cs, r);
+  }
+  return set_err(PTFEM_ERR_ARG, "unsupported system count %d", S);
+}
+
+int coarse_apply_fused_update(ptfem_ctx* ctx, CoarseSpace& cs, int S, double* r, const double* q, const double* dinv, const double* alpha,
+                              double* partial, unsigned int* ticket, double* out_rz, double* out_rr) {
+  if (cs.VS != 1 || cs.row_limit >= 0) return set_err(PTFEM_ERR_STATE, "the fused residual update takes one shared matrix and every row");
+  FusedUpdate fu;
+  fu.q = q; fu.dinv = dinv; fu.alpha = alpha; fu.r = r; fu.partial = partial; fu.ticket = ticket; fu.out_rz = out_rz; fu.out_rr = out_rr;
+  switch (S) {
+    case 1: return apply_t<1>(ctx, cs, r, &fu);
+    case 2: return apply_t<2>(ctx, cs, r, &fu);
+    case 4: return apply_t<4>(ctx, cs, r, &fu);
+    case 8: return apply_t<8>(ctx, cs, r, &fu);
+    case 16: return apply_t<16>(ctx, cs, r, &fu);
   }
   return set_err(PTFEM_ERR_ARG, "unsupported system count %d", S);
 }
@@ -1469,7 +1587,7 @@ int coarse_restrict_rows(ptfem_ctx* ctx, CoarseSpace& cs, const double* r, doubl
   const int64_t ntask = L0.ncell * L0.split;
   const int grid = (int)std::min<int64_t>((ntask + 7) / 8, (int64_t)ctx->sm_count * 32);
   restrict_cell_kernel<1, 4><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p, r,
-                                                            L0.part.p);
+                                                            L0.part.p, FusedUpdate());
   PT_LAUNCH_CHECK(ctx);
   const int ngrid = std::min(ceil_div(L0.k, 256), 4 * ctx->sm_count);
   coarse_node_kernel<1, false><<<ngrid, 256, 0, ctx->stream>>>(L0.g, L0.k, L0.split, L0.part.p, nullptr, 0, rc_out, nullptr, nullptr,
@@ -1616,7 +1734,7 @@ int coarse_restrict_rows_sharded(ptfem_ctx* ctx, CoarseSpace& cs, const double* 
   const int64_t ntask = L0.ncell * L0.split;
   const int grid = (int)std::min<int64_t>((ntask + 7) / 8, (int64_t)ctx->sm_count * 32);
   restrict_cell_kernel<1, 4><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p, r,
-                                                            L0.part.p);
+                                                            L0.part.p, FusedUpdate());
   PT_LAUNCH_CHECK(ctx);
   if (ranges[1] > ranges[0]) {
     coarse_node_range_kernel<<<ceil_div(ranges[1] - ranges[0], 256), 256, 0, ctx->stream>>>(L0.g, ranges[0], ranges[1], L0.split,

@@ -118,6 +118,7 @@ struct ptfem_ctx {
   int tune_chain_tail = 0;         // PTFEM_CHAIN_TAIL: partitioned solve runs the replicated smallest grid levels as one block (measured slower: off)
   int tune_pupdate_occ = 4;        // PTFEM_PUPDATE_OCC: resident CTAs per SM the one-pair p-update is compiled for (4, 5, 6)
   int tune_pupdate_np = 1;         // PTFEM_PUPDATE_NP: pairs per trip of the coarse-grid p-update (1: 4 CTAs/SM, 2: 2 CTAs/SM, all loads of both first)
+  int tune_fuse_update = 1;        // PTFEM_FUSE_UPDATE: CG residual update inside the restriction's gather (coarse-grid PCG, one matrix)
   int tune_window = 1;             // PTFEM_SPMM_WINDOW: multi-RHS SpMM out of shared-memory x windows where the numbering allows a plan (window.cu); 0 = streaming kernel
   int tune_window_bx = 0;          // PTFEM_WINDOW_BX: rows of a brick along a line (0 = 16)
   int tune_window_ctas = 0;        // PTFEM_WINDOW_CTAS: resident CTAs per SM of the window SpMM (0 = as many as fit, at most 4)

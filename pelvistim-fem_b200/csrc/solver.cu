@@ -1338,10 +1338,21 @@ int pcg_iteration(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int 
     cg_pupdate_kernel<S, VS, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, nullptr, A.dinv, w.p.p, x, w.scal.p, 0);
     PT_LAUNCH_CHECK(ctx);
   } else if (precond == PTFEM_PRECOND_TWOLEVEL) {
-    cg_update_kernel<S, VS, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.q.p, A.dinv, w.r.p, w.partial.p, w.scal.p,
-                                                                      w.ticket.p, 1);
-    PT_LAUNCH_CHECK(ctx);
-    PT_TRY(coarse_apply(ctx, *A.coarse, S, w.r.p));
+    bool fused = false;
+    if constexpr (VS == 1) {
+      if (ctx->tune_fuse_update && A.coarse->row_limit < 0 && A.coarse->chain_grid == 0) {
+        // r -= alpha q inside the restriction's gather (one pass over r instead of two)
+        PT_TRY(coarse_apply_fused_update(ctx, *A.coarse, S, w.r.p, w.q.p, A.dinv, w.scal.p + SC_ALPHA * kMaxSys, w.partial.p, w.ticket.p,
+                                         w.scal.p + SC_RHOL * kMaxSys, w.scal.p + SC_RR * kMaxSys));
+        fused = true;
+      }
+    }
+    if (!fused) {
+      cg_update_kernel<S, VS, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.q.p, A.dinv, w.r.p, w.partial.p, w.scal.p,
+                                                                        w.ticket.p, 1);
+      PT_LAUNCH_CHECK(ctx);
+      PT_TRY(coarse_apply(ctx, *A.coarse, S, w.r.p));
+    }
     rho_finalize_kernel<<<1, 32, 0, ctx->stream>>>(w.scal.p, A.coarse->cdot.p, A.coarse->nlev, S);
     PT_LAUNCH_CHECK(ctx);
     if constexpr (VS != 1) {    // batched matrices: one inverse diagonal per system

@@ -12,7 +12,7 @@ configs = [dict(MORTON=0), dict(MORTON=1), dict(MORTON=1, STREAM_ROWS=32), dict(
 if len(sys.argv) > 2:
     configs = [eval("dict(" + a + ")") for a in sys.argv[2:]]
 for c in configs:
-    for k in ("XPREFETCH", "STREAM_ROWS", "INTERLEAVE", "STREAM_STAGES", "MORTON", "STREAM_CAP", "CTAS_PER_SM", "SPMM_WINDOW", "WINDOW_BX", "WINDOW_CTAS"):
+    for k in ("XPREFETCH", "STREAM_ROWS", "INTERLEAVE", "STREAM_STAGES", "MORTON", "STREAM_CAP", "CTAS_PER_SM", "SPMM_WINDOW", "WINDOW_BX", "WINDOW_CTAS", "FUSE_UPDATE"):
         os.environ.pop("PTFEM_" + k, None)
     for k, v in c.items():
         os.environ["PTFEM_" + k] = str(v)
