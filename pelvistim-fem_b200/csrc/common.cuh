@@ -237,6 +237,8 @@ struct ptfem_mesh {
   int J_all_method = -1;
   bool J_from_all = false;        // the current system's nodal current is Jall + J_sys*nn*3
   ptfem::DevBuf<float> tcen;      // [nt][4] tet centroids in single precision (prefilter of the ROI scans)
+  ptfem::DevBuf<double> nchunk;   // [ceil(nn/128)][4] bounding sphere of every run of 128 consecutive nodes (ROI smoothing)
+  ptfem::DevBuf<float> tchunk;    // [ceil(nt/256)][4] bounding sphere (centre, radius) of every run of 256 consecutive centroids
   bool has_tcen = false;
   ptfem::DevBuf<double> phis_all; // [nroi][nn] smoothed potentials of a metric batch
   bool j_copy_pending = false;    // an asynchronous device->host copy of Jnode may still be reading it

@@ -878,6 +878,33 @@ __global__ void tet_centroid_kernel(const double* __restrict__ xyz, const int32_
   cen[e] = make_float4((float)(0.25 * c[0]), (float)(0.25 * c[1]), (float)(0.25 * c[2]), 0.f);
 }
 
+// bounding sphere of every run of kT consecutive tet centroids (one block per run): an ROI scan tests the run first and skips it
+// whole - on meshes whose tets are stored in spatial order (structured, extruded, anything a mesher emits region by region) a 5 mm
+// ROI touches a few hundred of the 77 k runs of the 20 M-tet slab, so a request reads ~1 MB instead of the 316 MB centroid array
+__global__ void __launch_bounds__(kT) tet_chunk_kernel(const float4* __restrict__ cen, int64_t nt, float4* __restrict__ chunk) {
+  __shared__ float s_a[kT], s_b[kT], s_c[kT];
+  const int tid = threadIdx.x;
+  const int64_t e = (int64_t)blockIdx.x * kT + tid;
+  const int n = (int)min((int64_t)kT, nt - (int64_t)blockIdx.x * kT);
+  const float4 q = e < nt ? cen[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+  s_a[tid] = q.x; s_b[tid] = q.y; s_c[tid] = q.z;
+  __syncthreads();
+  for (int o = kT / 2; o > 0; o >>= 1) {
+    if (tid < o) { s_a[tid] += s_a[tid + o]; s_b[tid] += s_b[tid + o]; s_c[tid] += s_c[tid + o]; }
+    __syncthreads();
+  }
+  const float cx = s_a[0] / n, cy = s_b[0] / n, cz = s_c[0] / n;
+  __syncthreads();
+  const float dx = q.x - cx, dy = q.y - cy, dz = q.z - cz;
+  s_a[tid] = e < nt ? sqrtf(dx * dx + dy * dy + dz * dz) : 0.f;
+  __syncthreads();
+  for (int o = kT / 2; o > 0; o >>= 1) {
+    if (tid < o) s_a[tid] = fmaxf(s_a[tid], s_a[tid + o]);
+    __syncthreads();
+  }
+  if (tid == 0) chunk[blockIdx.x] = make_float4(cx, cy, cz, s_a[0] * 1.0001f + 1e-30f);
+}
+
 struct BatchReq {   // device copy of one request (+ where its inputs / partials live)
   ptfem_metric_req r;
   int32_t slot;     // index among the requests of its kind
@@ -944,16 +971,49 @@ __global__ void __launch_bounds__(kT) pad_current_batch_kernel(const double* __r
 }
 
 // VTK point smoothing for every ROI request (blockIdx.y): phis[slot][i] for the nodes an in-ROI cell can use
+// bounding sphere (double precision) of every run of 128 consecutive nodes - one block of the smoothing kernel - so that blocks far
+// from the ROI leave after one 32-byte read instead of reading their nodes' coordinates
+__global__ void __launch_bounds__(128) node_chunk_kernel(const double* __restrict__ xyz, int64_t nn, double* __restrict__ chunk) {
+  __shared__ double s_a[128], s_b[128], s_c[128];
+  const int tid = threadIdx.x;
+  const int64_t i = (int64_t)blockIdx.x * 128 + tid;
+  const int n = (int)min((int64_t)128, nn - (int64_t)blockIdx.x * 128);
+  const double x = i < nn ? xyz[3 * i] : 0.0, y = i < nn ? xyz[3 * i + 1] : 0.0, z = i < nn ? xyz[3 * i + 2] : 0.0;
+  s_a[tid] = x; s_b[tid] = y; s_c[tid] = z;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (tid < o) { s_a[tid] += s_a[tid + o]; s_b[tid] += s_b[tid + o]; s_c[tid] += s_c[tid + o]; }
+    __syncthreads();
+  }
+  const double cx = s_a[0] / n, cy = s_b[0] / n, cz = s_c[0] / n;
+  __syncthreads();
+  s_a[tid] = i < nn ? sqrt((x - cx) * (x - cx) + (y - cy) * (y - cy) + (z - cz) * (z - cz)) : 0.0;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (tid < o) s_a[tid] = fmax(s_a[tid], s_a[tid + o]);
+    __syncthreads();
+  }
+  if (tid == 0) {
+    chunk[4 * (size_t)blockIdx.x] = cx; chunk[4 * (size_t)blockIdx.x + 1] = cy; chunk[4 * (size_t)blockIdx.x + 2] = cz;
+    chunk[4 * (size_t)blockIdx.x + 3] = s_a[0] * (1.0 + 1e-12);
+  }
+}
+
 __global__ void smooth_phi_batch_kernel(const int32_t* __restrict__ n2t_ptr, const int32_t* __restrict__ n2t,
                                         const int32_t* __restrict__ n2b_ptr, const int32_t* __restrict__ n2b,
                                         const int32_t* __restrict__ tets, const int32_t* __restrict__ tris,
                                         const double* __restrict__ phi, int S, int64_t nn, const double* __restrict__ xyz,
                                         double h_max, const BatchReq* __restrict__ reqs, const int32_t* __restrict__ idx,
-                                        double* __restrict__ phis_all) {
+                                        const double* __restrict__ nchunk, double* __restrict__ phis_all) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nn) return;
   const ptfem_metric_req& r = reqs[idx[blockIdx.y]].r;
   const double rad = r.r0 * r.mult[r.nmult - 1] + 1.01 * h_max;
+  {   // the block's nodes (blockDim.x == 128 consecutive ones) all lie outside: nothing to do
+    const double ex = nchunk[4 * (size_t)blockIdx.x] - r.cen[0], ey = nchunk[4 * (size_t)blockIdx.x + 1] - r.cen[1],
+                 ez = nchunk[4 * (size_t)blockIdx.x + 2] - r.cen[2], lim = (rad + nchunk[4 * (size_t)blockIdx.x + 3]) * (1.0 + 1e-12);
+    if (ex * ex + ey * ey + ez * ez > lim * lim) return;
+  }
   const double dx = xyz[3 * i] - r.cen[0], dy = xyz[3 * i + 1] - r.cen[1], dz = xyz[3 * i + 2] - r.cen[2];
   if (dx * dx + dy * dy + dz * dz > rad * rad) return;
   const int sys = r.sys;
@@ -1052,7 +1112,7 @@ __device__ __forceinline__ void roi_cell_accumulate(const double* __restrict__ x
 // 4 node ids + 4 gathered coordinates), boundary triangles are tested directly.
 __global__ void __launch_bounds__(kT) roi_batch_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ tets, int64_t nt,
                                                        const int32_t* __restrict__ tris, int64_t nb, const float4* __restrict__ tcen,
-                                                       int64_t nn, const double* __restrict__ phis_all, const double* __restrict__ Jall,
+                                                       const float4* __restrict__ tchunk, int64_t nn, const double* __restrict__ phis_all, const double* __restrict__ Jall,
                                                        const BatchReq* __restrict__ reqs, const int32_t* __restrict__ idx,
                                                        double* __restrict__ partial) {
   const ptfem_metric_req& a = reqs[idx[blockIdx.y]].r;
@@ -1068,7 +1128,14 @@ __global__ void __launch_bounds__(kT) roi_batch_kernel(const double* __restrict_
   const float rf = (float)rmax * 1.0001f + 64.f * 1.1920929e-7f * big;
   const float rf2 = rf * rf;
   const int64_t stride = (int64_t)gridDim.x * kT;
-  for (int64_t c = (int64_t)blockIdx.x * kT + threadIdx.x; c < nt; c += stride) {
+  const int64_t nchunk = (nt + kT - 1) / kT;
+  for (int64_t ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {      // thread t of the block owns tet ch * kT + t
+    const float4 sp = __ldg(tchunk + ch);
+    const float ex = sp.x - cxf, ey = sp.y - cyf, ez = sp.z - czf;
+    const float lim = (rf + sp.w) * 1.00001f;
+    if (ex * ex + ey * ey + ez * ez > lim * lim) continue;            // the whole run lies outside (same answer in every thread)
+    const int64_t c = ch * kT + threadIdx.x;
+    if (c >= nt) continue;
     const float4 q = __ldg(tcen + c);
     const float dx = q.x - cxf, dy = q.y - cyf, dz = q.z - czf;
     if (dx * dx + dy * dy + dz * dz > rf2) continue;
@@ -1174,6 +1241,15 @@ int ptfem_do_metrics_batch(ptfem_mesh* m, int32_t nreq, const ptfem_metric_req* 
       tet_centroid_kernel<<<ceil_div(m->nt, 256), 256, 0, ctx->stream>>>(m->xyz.p, m->tets.p, m->nt, reinterpret_cast<float4*>(m->tcen.p));
       PT_LAUNCH_CHECK(ctx);
     }
+    PT_TRY(m->tchunk.alloc((size_t)(ceil_div(m->nt, kT) > 0 ? ceil_div(m->nt, kT) : 1) * 4));
+    if (m->nt > 0) {
+      tet_chunk_kernel<<<ceil_div(m->nt, kT), kT, 0, ctx->stream>>>(reinterpret_cast<const float4*>(m->tcen.p), m->nt,
+                                                                    reinterpret_cast<float4*>(m->tchunk.p));
+      PT_LAUNCH_CHECK(ctx);
+    }
+    PT_TRY(m->nchunk.alloc((size_t)ceil_div(m->nn, 128) * 4));
+    node_chunk_kernel<<<ceil_div(m->nn, 128), 128, 0, ctx->stream>>>(m->xyz.p, m->nn, m->nchunk.p);
+    PT_LAUNCH_CHECK(ctx);
     m->has_tcen = true;
   }
   // device copies: requests, per-kind index lists, partials, results
@@ -1220,10 +1296,11 @@ int ptfem_do_metrics_batch(ptfem_mesh* m, int32_t nreq, const ptfem_metric_req* 
     PT_TRY(m->phis_all.alloc(idx[2].size() * (size_t)m->nn));
     smooth_phi_batch_kernel<<<dim3(ceil_div(m->nn, 128), (unsigned)idx[2].size()), 128, 0, ctx->stream>>>(
         m->n2t_ptr.p, m->n2t.p, m->n2b_ptr.p, m->n2b.p, m->tets.p, m->tris.p, m->phi.p, m->S, m->nn, m->xyz.p, m->h_max, d_req.p,
-        d_idx.p + off[2], m->phis_all.p);
+        d_idx.p + off[2], m->nchunk.p, m->phis_all.p);
     PT_LAUNCH_CHECK(ctx);
     roi_batch_kernel<<<dim3(gc, (unsigned)idx[2].size()), kT, 0, ctx->stream>>>(m->xyz.p, m->tets.p, m->nt, m->tris.p, m->nb,
-                                                                                 reinterpret_cast<const float4*>(m->tcen.p), m->nn,
+                                                                                 reinterpret_cast<const float4*>(m->tcen.p),
+                                                                                 reinterpret_cast<const float4*>(m->tchunk.p), m->nn,
                                                                                  m->phis_all.p, Jall, d_req.p, d_idx.p + off[2], part2);
     PT_LAUNCH_CHECK(ctx);
     finalize_batch_kernel<<<ceil_div((int64_t)idx[2].size() * NVR * 32, 256), 256, 0, ctx->stream>>>(part2, gc, NVR, (int)idx[2].size(), 0u,
