@@ -75,7 +75,8 @@ typedef struct ptfem_solve_opts {
 
 typedef struct ptfem_solve_stats {
   int32_t iterations;   /* CG iterations executed (same for every system of the batch) */
-  int32_t converged;    /* 1 if every system met rtol */
+  int32_t converged;    /* 1 if every system met rtol; 2 if the solve was accepted at the attainable accuracy instead (true residual
+                           stopped falling under residual replacement, still <= 1e-8 but above rtol: see true_rel_residual); 0 otherwise */
   int32_t nsys;         /* systems solved at once */
   int32_t spmv_calls;   /* sparse matrix-vector products launched (all systems count as one) */
   double rel_residual;  /* max over systems of recurrence ||r|| / ||b|| at exit */

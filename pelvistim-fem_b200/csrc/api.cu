@@ -211,6 +211,9 @@ int ptfem_ctx_create(int device, ptfem_ctx** out) {
   PT_CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   PT_CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
   PT_CK(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+  PT_CK(cudaStreamCreateWithFlags(&c->stream_x, cudaStreamNonBlocking));
+  PT_CK(cudaEventCreateWithFlags(&c->ev_xfork, cudaEventDisableTiming));
+  PT_CK(cudaEventCreateWithFlags(&c->ev_xjoin, cudaEventDisableTiming));
   PT_CK(cudaEventCreateWithFlags(&c->ev_j_ready, cudaEventDisableTiming));
   PT_CK(cudaEventCreateWithFlags(&c->ev_j_copied, cudaEventDisableTiming));
   PT_CK(cudaEventCreateWithFlags(&c->ev_phi_ready, cudaEventDisableTiming));
@@ -230,6 +233,8 @@ int ptfem_ctx_create(int device, ptfem_ctx** out) {
     if (w > 0.0) c->tune_coarse_weight = w;
   }
   if (const char* e = getenv("PTFEM_FUSE_UPDATE")) c->tune_fuse_update = atoi(e);
+  if (const char* e = getenv("PTFEM_SPLIT_X")) c->tune_split_x = atoi(e);
+  if (const char* e = getenv("PTFEM_SPLIT_X_CTAS")) c->tune_split_x_ctas = atoi(e);
   if (const char* e = getenv("PTFEM_SPMM_WINDOW")) c->tune_window = atoi(e);
   if (const char* e = getenv("PTFEM_WINDOW_BX")) c->tune_window_bx = atoi(e);
   if (const char* e = getenv("PTFEM_WINDOW_CTAS")) c->tune_window_ctas = atoi(e);
@@ -253,6 +258,9 @@ int ptfem_ctx_destroy(ptfem_ctx* ctx) {
   if (ctx->ev_phi_ready) cudaEventDestroy(ctx->ev_phi_ready);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
+  if (ctx->stream_x) cudaStreamDestroy(ctx->stream_x);
+  if (ctx->ev_xfork) cudaEventDestroy(ctx->ev_xfork);
+  if (ctx->ev_xjoin) cudaEventDestroy(ctx->ev_xjoin);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   delete ctx;
   dev_cache_flush();

@@ -1142,7 +1142,7 @@ int chain_launch(ptfem_ctx* ctx, CoarseSpace& cs, bool do_node, bool scaled0) {
 }
 
 template <int S>
-int apply_t(ptfem_ctx* ctx, CoarseSpace& cs, const double* r, const FusedUpdate* fu = nullptr) {
+int apply_t(ptfem_ctx* ctx, CoarseSpace& cs, const double* r, const FusedUpdate* fu = nullptr, cudaEvent_t after_restrict = nullptr) {
   // mesh -> finest grid
   CoarseLevel& L0 = cs.lev[0];
   {
@@ -1166,6 +1166,7 @@ int apply_t(ptfem_ctx* ctx, CoarseSpace& cs, const double* r, const FusedUpdate*
     }
     PT_LAUNCH_CHECK(ctx);
   }
+  if (after_restrict) PT_CK(cudaEventRecord(after_restrict, ctx->stream));
   if (cs.chain_grid > 0) return chain_launch<S>(ctx, cs, true, false);
   for (int l = 0; l < cs.nlev; ++l) {
     CoarseLevel& L = cs.lev[l];
@@ -1220,16 +1221,16 @@ int coarse_apply(ptfem_ctx* ctx, CoarseSpace& cs, int S, const double* r) {
 }
 
 int coarse_apply_fused_update(ptfem_ctx* ctx, CoarseSpace& cs, int S, double* r, const double* q, const double* dinv, const double* alpha,
-                              double* partial, unsigned int* ticket, double* out_rz, double* out_rr) {
+                              double* partial, unsigned int* ticket, double* out_rz, double* out_rr, cudaEvent_t after_restrict) {
   if (cs.VS != 1 || cs.row_limit >= 0) return set_err(PTFEM_ERR_STATE, "the fused residual update takes one shared matrix and every row");
   FusedUpdate fu;
   fu.q = q; fu.dinv = dinv; fu.alpha = alpha; fu.r = r; fu.partial = partial; fu.ticket = ticket; fu.out_rz = out_rz; fu.out_rr = out_rr;
   switch (S) {
-    case 1: return apply_t<1>(ctx, cs, r, &fu);
-    case 2: return apply_t<2>(ctx, cs, r, &fu);
-    case 4: return apply_t<4>(ctx, cs, r, &fu);
-    case 8: return apply_t<8>(ctx, cs, r, &fu);
-    case 16: return apply_t<16>(ctx, cs, r, &fu);
+    case 1: return apply_t<1>(ctx, cs, r, &fu, after_restrict);
+    case 2: return apply_t<2>(ctx, cs, r, &fu, after_restrict);
+    case 4: return apply_t<4>(ctx, cs, r, &fu, after_restrict);
+    case 8: return apply_t<8>(ctx, cs, r, &fu, after_restrict);
+    case 16: return apply_t<16>(ctx, cs, r, &fu, after_restrict);
   }
   return set_err(PTFEM_ERR_ARG, "unsupported system count %d", S);
 }

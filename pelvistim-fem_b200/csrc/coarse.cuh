@@ -191,9 +191,10 @@ int coarse_finish_sums(ptfem_mesh* m, const double* sums_host, int64_t n);
 // y_c = B_l Z_l^T r for every level; leaves r_c.y_c per level/system in cs.cdot
 int coarse_apply(ptfem_ctx* ctx, CoarseSpace& cs, int S, const double* r);
 // the same with the CG residual update fused into the restriction: r -= alpha q on every row as it is gathered, r.D^-1 r -> out_rz,
-// r.r -> out_rr (device scalars [S]); partial: >= 8 * SMs * 2 * S doubles, ticket: a zeroed counter
+// r.r -> out_rr (device scalars [S]); partial: >= 8 * SMs * 2 * S doubles, ticket: a zeroed counter; after_restrict (optional) is
+// recorded between the restriction and the grid hierarchy (fork point of work that may run beside the small grid kernels)
 int coarse_apply_fused_update(ptfem_ctx* ctx, CoarseSpace& cs, int S, double* r, const double* q, const double* dinv, const double* alpha,
-                              double* partial, unsigned int* ticket, double* out_rz, double* out_rr);
+                              double* partial, unsigned int* ticket, double* out_rz, double* out_rr, cudaEvent_t after_restrict = nullptr);
 CoarseDev coarse_dev(const CoarseSpace& cs);
 void coarse_free(CoarseSpace* cs);
 // row-partitioned solve (dist.cu): coarse spaces of a row block [row0, row0 + sys->nn) taken from the rank's replica

@@ -98,6 +98,8 @@ struct ptfem_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // copies / halo
   cudaStream_t stream3 = nullptr;  // mesh uploads (host -> device), so they overlap both the kernels and the read-backs
+  cudaStream_t stream_x = nullptr; // coarse-grid PCG: x += alpha p beside the grid hierarchy (PTFEM_SPLIT_X), forked and joined by events
+  cudaEvent_t ev_xfork = nullptr, ev_xjoin = nullptr;
   int64_t launches = 0;
   cudaEvent_t ev_phi_ready = nullptr;
   cudaEvent_t ev_j_ready = nullptr, ev_j_copied = nullptr;  // asynchronous read-back of the nodal current (stream2)
@@ -119,6 +121,8 @@ struct ptfem_ctx {
   int tune_pupdate_occ = 4;        // PTFEM_PUPDATE_OCC: resident CTAs per SM the one-pair p-update is compiled for (4, 5, 6)
   int tune_pupdate_np = 1;         // PTFEM_PUPDATE_NP: pairs per trip of the coarse-grid p-update (1: 4 CTAs/SM, 2: 2 CTAs/SM, all loads of both first)
   int tune_fuse_update = 1;        // PTFEM_FUSE_UPDATE: CG residual update inside the restriction's gather (coarse-grid PCG, one matrix)
+  int tune_split_x = 0;            // PTFEM_SPLIT_X: coarse-grid PCG updates x on a side stream while the grid hierarchy runs (1: forked after the product, 2: after the restriction); the p-update then leaves x alone
+  int tune_split_x_ctas = 0;       // PTFEM_SPLIT_X_CTAS: resident CTAs per SM of the side-stream x-update (0 = 2)
   int tune_window = 1;             // PTFEM_SPMM_WINDOW: multi-RHS SpMM out of shared-memory x windows where the numbering allows a plan (window.cu); 0 = streaming kernel
   int tune_window_bx = 0;          // PTFEM_WINDOW_BX: rows of a brick along a line (0 = 16)
   int tune_window_ctas = 0;        // PTFEM_WINDOW_CTAS: resident CTAs per SM of the window SpMM (0 = as many as fit, at most 4)

@@ -658,7 +658,8 @@ __global__ void rho_finalize_kernel(double* __restrict__ scal, const double* __r
 // Two pairs per trip: the loads of both (five streamed 16-byte accesses and the table entry each) are issued before
 // either is used, and the eight grid-node gathers of both are independent - the kernel used to sit at 4.7 TB/s waiting
 // on the table -> grid node -> y chain with ~60 KB per SM in flight (ncu, round 1); the table entry is 16 bytes now.
-template <int S, int NP, int MINB = (NP == 1 ? 4 : 2), int VS = 1>
+// NOX: x is updated elsewhere (cg_xupdate_kernel on the side stream, PTFEM_SPLIT_X): the kernel neither reads nor writes it.
+template <int S, int NP, int MINB = (NP == 1 ? 4 : 2), int VS = 1, bool NOX = false>
 __global__ void __launch_bounds__(kThreads, MINB) cg_pupdate_coarse_kernel(int64_t nn, const double* __restrict__ r,
                                                                         const double* __restrict__ dinv, double* __restrict__ p,
                                                                         double* __restrict__ x, const double* __restrict__ scal,
@@ -683,7 +684,7 @@ __global__ void __launch_bounds__(kThreads, MINB) cg_pupdate_coarse_kernel(int64
       xv[u] = make_double2(0.0, 0.0);
       if (!first) {
         pv[u] = *reinterpret_cast<const double2*>(p + e);
-        xv[u] = *reinterpret_cast<const double2*>(x + e);
+        if constexpr (!NOX) xv[u] = *reinterpret_cast<const double2*>(x + e);
       }
     }
 #pragma unroll
@@ -706,9 +707,11 @@ __global__ void __launch_bounds__(kThreads, MINB) cg_pupdate_coarse_kernel(int64
       if (u == 1 && !two) break;
       const int64_t e = 2 * jj[u];
       if (!first) {
-        xv[u].x = fma(a0, pv[u].x, xv[u].x);
-        xv[u].y = fma(a1, pv[u].y, xv[u].y);
-        *reinterpret_cast<double2*>(x + e) = xv[u];
+        if constexpr (!NOX) {
+          xv[u].x = fma(a0, pv[u].x, xv[u].x);
+          xv[u].y = fma(a1, pv[u].y, xv[u].y);
+          *reinterpret_cast<double2*>(x + e) = xv[u];
+        }
         zv[u].x = fma(b0, pv[u].x, zv[u].x);
         zv[u].y = fma(b1, pv[u].y, zv[u].y);
       }
@@ -723,10 +726,45 @@ __global__ void __launch_bounds__(kThreads, MINB) cg_pupdate_coarse_kernel(int64
     if (first) {
       p[e] = z;
     } else {
-      x[e] = fma(a0, p[e], x[e]);
+      if constexpr (!NOX) x[e] = fma(a0, p[e], x[e]);
       p[e] = fma(b0, p[e], z);
     }
   }
+}
+
+// x += alpha p alone (PTFEM_SPLIT_X): pure streaming, launched on the side stream while the main stream runs the restriction
+// and the small dependent kernels of the grid hierarchy; the p-update (NOX) waits for it because it overwrites p.
+template <int S>
+__global__ void __launch_bounds__(kThreads) cg_xupdate_kernel(int64_t nn, const double* __restrict__ p, double* __restrict__ x,
+                                                              const double* __restrict__ scal) {
+  // few resident CTAs (the grid is a fraction of what the SMs hold, so the small grid kernels find room beside it):
+  // four independent pairs per trip keep enough bytes in flight
+  const FlatPairs<S> fp(nn);
+  const double a0 = scal[SC_ALPHA * kMaxSys + fp.s0], a1 = scal[SC_ALPHA * kMaxSys + fp.s1];
+  constexpr int U = 4;
+  int64_t j = fp.j0;
+  for (; j + (U - 1) * fp.stride < fp.npairs; j += U * fp.stride) {
+    double2 pv[U], xv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      pv[u] = __ldg(reinterpret_cast<const double2*>(p + 2 * (j + u * fp.stride)));
+      xv[u] = *reinterpret_cast<const double2*>(x + 2 * (j + u * fp.stride));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      xv[u].x = fma(a0, pv[u].x, xv[u].x);
+      xv[u].y = fma(a1, pv[u].y, xv[u].y);
+      *reinterpret_cast<double2*>(x + 2 * (j + u * fp.stride)) = xv[u];
+    }
+  }
+  for (; j < fp.npairs; j += fp.stride) {
+    const double2 p0 = __ldg(reinterpret_cast<const double2*>(p + 2 * j));
+    double2 x0 = *reinterpret_cast<const double2*>(x + 2 * j);
+    x0.x = fma(a0, p0.x, x0.x);
+    x0.y = fma(a1, p0.y, x0.y);
+    *reinterpret_cast<double2*>(x + 2 * j) = x0;
+  }
+  if (fp.has_tail) x[fp.tail] = fma(a0, p[fp.tail], x[fp.tail]);
 }
 
 // x += alpha p_old ; p = z + beta p_old   with z = dinv * r (JAC) or z given.   first: p = z only.
@@ -1339,12 +1377,22 @@ int pcg_iteration(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int 
     PT_LAUNCH_CHECK(ctx);
   } else if (precond == PTFEM_PRECOND_TWOLEVEL) {
     bool fused = false;
+    int split_x = 0;   // x += alpha p on the side stream, beside the restriction (1) or the grid hierarchy only (2)
     if constexpr (VS == 1) {
       if (ctx->tune_fuse_update && A.coarse->row_limit < 0 && A.coarse->chain_grid == 0) {
+        split_x = ctx->tune_split_x == 1 || ctx->tune_split_x == 2 ? ctx->tune_split_x : 0;
+        if (split_x == 1) PT_CK(cudaEventRecord(ctx->ev_xfork, ctx->stream));
         // r -= alpha q inside the restriction's gather (one pass over r instead of two)
         PT_TRY(coarse_apply_fused_update(ctx, *A.coarse, S, w.r.p, w.q.p, A.dinv, w.scal.p + SC_ALPHA * kMaxSys, w.partial.p, w.ticket.p,
-                                         w.scal.p + SC_RHOL * kMaxSys, w.scal.p + SC_RR * kMaxSys));
+                                         w.scal.p + SC_RHOL * kMaxSys, w.scal.p + SC_RR * kMaxSys, split_x == 2 ? ctx->ev_xfork : nullptr));
         fused = true;
+        if (split_x) {
+          PT_CK(cudaStreamWaitEvent(ctx->stream_x, ctx->ev_xfork, 0));
+          const int xgrid = std::min(grid, ctx->sm_count * (ctx->tune_split_x_ctas > 0 ? ctx->tune_split_x_ctas : 2));
+          cg_xupdate_kernel<S><<<xgrid, kThreads, 0, ctx->stream_x>>>(A.nn, w.p.p, x, w.scal.p);
+          PT_LAUNCH_CHECK(ctx);
+          PT_CK(cudaEventRecord(ctx->ev_xjoin, ctx->stream_x));
+        }
       }
     }
     if (!fused) {
@@ -1355,10 +1403,17 @@ int pcg_iteration(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int 
     }
     rho_finalize_kernel<<<1, 32, 0, ctx->stream>>>(w.scal.p, A.coarse->cdot.p, A.coarse->nlev, S);
     PT_LAUNCH_CHECK(ctx);
+    if (split_x) PT_CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_xjoin, 0));
     if constexpr (VS != 1) {    // batched matrices: one inverse diagonal per system
       cg_pupdate_coarse_kernel<S, 1, 4, VS><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
                                                                                 coarse_dev(*A.coarse));
-    } else if (ctx->tune_pupdate_np == 1 && ctx->tune_pupdate_occ == 5)
+    } else if (split_x && ctx->tune_pupdate_occ >= 6)
+      cg_pupdate_coarse_kernel<S, 1, 6, 1, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
+                                                                                    coarse_dev(*A.coarse));
+    else if (split_x)
+      cg_pupdate_coarse_kernel<S, 1, 4, 1, true><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
+                                                                                    coarse_dev(*A.coarse));
+    else if (ctx->tune_pupdate_np == 1 && ctx->tune_pupdate_occ == 5)
       cg_pupdate_coarse_kernel<S, 1, 5><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
                                                                             coarse_dev(*A.coarse));
     else if (ctx->tune_pupdate_np == 1 && ctx->tune_pupdate_occ == 6)
@@ -1667,10 +1722,14 @@ int pcg_solve_t(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_o
   }
   // attainable accuracy: the true residual stopped improving under residual replacement (round-off floor of
   // ||A|| ||x|| eps / ||b||); accepted when it is still small in absolute terms
-  if (!converged && stagnated && true_rel <= 1e-8) converged = true;
+  bool relaxed = false;   // accepted above rtol (surfaced as converged = 2, not silently as 1)
+  if (!converged && stagnated && true_rel <= 1e-8) {
+    converged = true;
+    relaxed = true_rel > o.rtol;
+  }
   if (st) {
     st->iterations = it;
-    st->converged = converged ? 1 : 0;
+    st->converged = converged ? (relaxed ? 2 : 1) : 0;
     st->nsys = S;
     st->spmv_calls = spmv_calls;
     st->rel_residual = rel;
