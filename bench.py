@@ -684,6 +684,8 @@ def main():
             "pcg": {"precond": {0: "jacobi", 1: "chebyshev", 2: "jacobi+coarse-grids"}[last_st["precond"]],
                     "iterations": statistics.mean(iters), "solve_ms": last_st["solve_ms"], "setup_ms": last_st["setup_ms"],
                     "coarse_unknowns": last_st["coarse_unknowns"], "jacobi_iterations": jacobi_iters, "jacobi_solve_ms": jacobi_ms,
+                    # 1 = every system met rtol on the true residual b - A x, 2 = accepted at the attainable accuracy (<= 1e-8)
+                    "rtol": RTOL, "converged": last_st["converged"], "true_rel_residual": last_st["true_rel_residual"],
                     # the same step if the GPU arm ran the CPU arm's algorithm (plain Jacobi-PCG), for a like-for-like ratio
                     "value_with_jacobi_only": world * args.nconf / ((t_dev / args.steps) - (last_st["solve_ms"] + last_st["setup_ms"] - jacobi_ms) * 1e-3)},
             "roofline": roofline,
