@@ -233,6 +233,9 @@ int ptfem_ctx_create(int device, ptfem_ctx** out) {
     if (w > 0.0) c->tune_coarse_weight = w;
   }
   if (const char* e = getenv("PTFEM_FUSE_UPDATE")) c->tune_fuse_update = atoi(e);
+  if (const char* e = getenv("PTFEM_FUSE_OCC")) c->tune_fuse_occ = atoi(e);
+  if (const char* e = getenv("PTFEM_FUSE_GRID")) c->tune_fuse_grid = atoi(e);
+  if (const char* e = getenv("PTFEM_FUSE_PREFETCH")) c->tune_fuse_prefetch = atoi(e);
   if (const char* e = getenv("PTFEM_SPLIT_X")) c->tune_split_x = atoi(e);
   if (const char* e = getenv("PTFEM_SPLIT_X_CTAS")) c->tune_split_x_ctas = atoi(e);
   if (const char* e = getenv("PTFEM_SPMM_WINDOW")) c->tune_window = atoi(e);

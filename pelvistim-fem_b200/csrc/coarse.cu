@@ -94,7 +94,9 @@ struct FusedUpdate {
   unsigned int* ticket = nullptr;
   double* out_rz = nullptr;         // [S] r.D^-1 r (Jacobi part of rho)
   double* out_rr = nullptr;         // [S]
+  int prefetch = 0;                 // the next trip's rows of r, q, dinv are asked into L2 as soon as their indices are known
 };
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 template <int S, int OCC, bool FUSE = false>
 __global__ void __launch_bounds__(256, OCC) restrict_cell_kernel(int64_t ntask, int split, int shift, const int32_t* __restrict__ cellptr,
                                                             const int32_t* __restrict__ rows, const float4* __restrict__ ctab0,
@@ -121,10 +123,33 @@ __global__ void __launch_bounds__(256, OCC) restrict_cell_kernel(int64_t ntask, 
 #pragma unroll
       for (int v = 0; v < NV; ++v) acc[a][v] = 0.0;
     const int32_t p1 = cellptr[c + 1];
-    for (int32_t p = cellptr[c] + sp * RPW + slot; p < p1; p += 2 * split * RPW) {
+    // the row indices of the NEXT trip are loaded before this trip's values are used: one dependent latency (index -> value) less
+    // per trip after the first (the kernel is latency-bound: ncu r03, SM 26 %, DRAM 41 %, occupancy 34 % with the update fused in)
+    const int32_t pfirst = cellptr[c] + sp * RPW + slot;
+    int32_t nia = pfirst < p1 ? __ldg(rows + pfirst) : -1, nib = pfirst + split * RPW < p1 ? __ldg(rows + pfirst + split * RPW) : -1;
+    for (int32_t p = pfirst; p < p1; p += 2 * split * RPW) {
       // two rows per trip so that both index -> value chains are in flight together
       const int32_t pb = p + split * RPW;
-      const int32_t ia = __ldg(rows + p), ib = pb < p1 ? __ldg(rows + pb) : -1;
+      const int32_t ia = nia, ib = nib;
+      {
+        const int32_t pn = p + 2 * split * RPW, pnb = pn + split * RPW;
+        nia = pn < p1 ? __ldg(rows + pn) : -1;
+        nib = pnb < p1 ? __ldg(rows + pnb) : -1;
+      }
+      if constexpr (FUSE) {
+        if (fu.prefetch && ia >= 0) {    // (the indices of this trip arrived one trip ago: these are the next trip's)
+          if (nia >= 0) {
+            prefetch_l2(fu.r + (size_t)nia * S + NV * pr);
+            prefetch_l2(fu.q + (size_t)nia * S + NV * pr);
+            if (pr == 0) prefetch_l2(fu.dinv + nia);
+          }
+          if (nib >= 0) {
+            prefetch_l2(fu.r + (size_t)nib * S + NV * pr);
+            prefetch_l2(fu.q + (size_t)nib * S + NV * pr);
+            if (pr == 0) prefetch_l2(fu.dinv + nib);
+          }
+        }
+      }
       const CoarseRaw ra = coarse_row_load(ctab0, p), rb = coarse_row_load(ctab0, pb < p1 ? pb : p);
       double va[NV], vb[NV];
       if constexpr (FUSE) {          // r is rewritten by this kernel: plain loads, through the writable pointer
@@ -1149,9 +1174,16 @@ int apply_t(ptfem_ctx* ctx, CoarseSpace& cs, const double* r, const FusedUpdate*
     const int64_t ntask = L0.ncell * L0.split;
     if (fu) {
       // with the CG residual update fused in (r is rewritten): the grid stays within the CG workspace's partial sums
-      const int grid = (int)std::min<int64_t>((ntask + 7) / 8, (int64_t)ctx->sm_count * 8);
-      restrict_cell_kernel<S, 3, true><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p, r,
-                                                                      L0.part.p, *fu);
+      // whole waves of the resident CTAs (3 or 4 per SM): the grid used to be 8 per SM = 2.67 waves of 3
+      const int occ = ctx->tune_fuse_occ == 4 ? 4 : 3;
+      const int per_sm = ctx->tune_fuse_grid > 0 ? std::min(ctx->tune_fuse_grid, 8) : 2 * occ > 8 ? occ : 2 * occ;
+      const int grid = (int)std::min<int64_t>((ntask + 7) / 8, (int64_t)ctx->sm_count * per_sm);
+      if (occ == 4)
+        restrict_cell_kernel<S, 4, true><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p, r,
+                                                                        L0.part.p, *fu);
+      else
+        restrict_cell_kernel<S, 3, true><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p, r,
+                                                                        L0.part.p, *fu);
     } else {
     const int grid = (int)std::min<int64_t>((ntask + 7) / 8, (int64_t)ctx->sm_count * 32);
     if (ctx->tune_restrict_occ >= 6)
@@ -1225,6 +1257,7 @@ int coarse_apply_fused_update(ptfem_ctx* ctx, CoarseSpace& cs, int S, double* r,
   if (cs.VS != 1 || cs.row_limit >= 0) return set_err(PTFEM_ERR_STATE, "the fused residual update takes one shared matrix and every row");
   FusedUpdate fu;
   fu.q = q; fu.dinv = dinv; fu.alpha = alpha; fu.r = r; fu.partial = partial; fu.ticket = ticket; fu.out_rz = out_rz; fu.out_rr = out_rr;
+  fu.prefetch = ctx->tune_fuse_prefetch;
   switch (S) {
     case 1: return apply_t<1>(ctx, cs, r, &fu, after_restrict);
     case 2: return apply_t<2>(ctx, cs, r, &fu, after_restrict);
