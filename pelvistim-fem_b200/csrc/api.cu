@@ -226,6 +226,7 @@ int ptfem_ctx_create(int device, ptfem_ctx** out) {
   if (const char* e = getenv("PTFEM_COARSE_FUSED")) c->tune_coarse_fused = atoi(e) != 0;
   if (const char* e = getenv("PTFEM_PUPDATE_NP")) c->tune_pupdate_np = atoi(e) == 2 ? 2 : 1;
   if (const char* e = getenv("PTFEM_PUPDATE_OCC")) c->tune_pupdate_occ = atoi(e);
+  if (const char* e = getenv("PTFEM_PUPDATE_GRID")) c->tune_pupdate_grid = atoi(e);
   if (const char* e = getenv("PTFEM_CHAIN_TAIL")) c->tune_chain_tail = atoi(e) != 0;
   if (const char* e = getenv("PTFEM_SPMM_PAIR")) c->tune_pair = atoi(e) != 0;
   if (const char* e = getenv("PTFEM_COARSE_WEIGHT")) {

@@ -229,6 +229,18 @@ __global__ void __launch_bounds__(256, OCC) restrict_cell_kernel(int64_t ntask, 
           for (int v = 0; v < NV; ++v) acc[a][v] = fma(wgt[a], vb[v], acc[a][v]);
       }
     }
+    if constexpr (FUSE) {
+      // the next task's row list and table entries (consecutive in list order) are asked into L2 before the butterfly: its first
+      // trip then waits for L2, not DRAM, on the index -> value chain
+      if (fu.prefetch >= 2 && w + nwarp < ntask) {
+        const int64_t c2 = (w + nwarp) / split;
+        const int32_t q0 = __ldg(cellptr + c2) + lane;
+        if (q0 < __ldg(cellptr + c2 + 1)) {     // (never past the lists)
+          prefetch_l2(rows + q0);
+          prefetch_l2(ctab0 + q0);
+        }
+      }
+    }
     // Sum over the row slots (lanes with the same system pair).  Butterfly with halving: at every step a lane hands half of
     // its remaining sums to its partner and receives the partner's half of the others, so 8*NV sums over 32/NP slots cost
     // 8*NV - (what is left per lane) shuffles instead of 8*NV per step (14 instead of 48 for S = 8: the shuffles were
@@ -1174,9 +1186,11 @@ int apply_t(ptfem_ctx* ctx, CoarseSpace& cs, const double* r, const FusedUpdate*
     const int64_t ntask = L0.ncell * L0.split;
     if (fu) {
       // with the CG residual update fused in (r is rewritten): the grid stays within the CG workspace's partial sums
-      // whole waves of the resident CTAs (3 or 4 per SM): the grid used to be 8 per SM = 2.67 waves of 3
+      // ONE wave of the resident CTAs (3 per SM, 80 registers): the grid used to be 8 per SM = 2.67 waves.  Measured on L / 8 RHS
+      // (profiles/r03_fused_restrict_knobs.txt, ms per PCG iteration): 3 per SM 0.696, 6: 0.715, 8: 0.729, 4: 0.772; compiled for
+      // 4 CTAs per SM (64 registers, spills) 0.739-0.784; L2 prefetch of the next trip's rows / the next task's lists: no gain
       const int occ = ctx->tune_fuse_occ == 4 ? 4 : 3;
-      const int per_sm = ctx->tune_fuse_grid > 0 ? std::min(ctx->tune_fuse_grid, 8) : 2 * occ > 8 ? occ : 2 * occ;
+      const int per_sm = ctx->tune_fuse_grid > 0 ? std::min(ctx->tune_fuse_grid, 8) : occ;
       const int grid = (int)std::min<int64_t>((ntask + 7) / 8, (int64_t)ctx->sm_count * per_sm);
       if (occ == 4)
         restrict_cell_kernel<S, 4, true><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p, r,

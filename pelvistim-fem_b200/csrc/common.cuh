@@ -119,10 +119,11 @@ struct ptfem_ctx {
   int tune_pair = 0;               // PTFEM_SPMM_PAIR: multi-RHS streaming SpMM reads two non-zeros per shared-memory access (even-padded copy); measured slower (0.335 vs 0.289 ms): off
   int tune_chain_tail = 0;         // PTFEM_CHAIN_TAIL: partitioned solve runs the replicated smallest grid levels as one block (measured slower: off)
   int tune_pupdate_occ = 4;        // PTFEM_PUPDATE_OCC: resident CTAs per SM the one-pair p-update is compiled for (4, 5, 6)
+  int tune_pupdate_grid = 0;       // PTFEM_PUPDATE_GRID: CTAs per SM of the coarse-grid p-update's grid (0 = 8, two waves of the 4 resident)
   int tune_pupdate_np = 1;         // PTFEM_PUPDATE_NP: pairs per trip of the coarse-grid p-update (1: 4 CTAs/SM, 2: 2 CTAs/SM, all loads of both first)
   int tune_fuse_update = 1;        // PTFEM_FUSE_UPDATE: CG residual update inside the restriction's gather (coarse-grid PCG, one matrix)
   int tune_fuse_occ = 3;           // PTFEM_FUSE_OCC: resident CTAs per SM the fused update + restriction is compiled for (3: 80 registers, 4: 64)
-  int tune_fuse_grid = 0;          // PTFEM_FUSE_GRID: its CTAs per SM (0 = two waves of the resident CTAs, at most 8: the CG partial sums hold 8 per SM)
+  int tune_fuse_grid = 0;          // PTFEM_FUSE_GRID: its CTAs per SM (0 = one wave of the resident CTAs; at most 8: the CG partial sums hold 8 per SM)
   int tune_fuse_prefetch = 0;      // PTFEM_FUSE_PREFETCH: the fused update + restriction asks the next trip's rows of r, q, dinv into L2 when their indices arrive
   int tune_split_x = 0;            // PTFEM_SPLIT_X: coarse-grid PCG updates x on a side stream while the grid hierarchy runs (1: forked after the product, 2: after the restriction); the p-update then leaves x alone
   int tune_split_x_ctas = 0;       // PTFEM_SPLIT_X_CTAS: resident CTAs per SM of the side-stream x-update (0 = 2)

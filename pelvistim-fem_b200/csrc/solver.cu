@@ -1420,8 +1420,8 @@ int pcg_iteration(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, int variant, int 
       cg_pupdate_coarse_kernel<S, 1, 6><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
                                                                             coarse_dev(*A.coarse));
     else if (ctx->tune_pupdate_np == 1)
-      cg_pupdate_coarse_kernel<S, 1><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
-                                                                         coarse_dev(*A.coarse));
+      cg_pupdate_coarse_kernel<S, 1><<<ctx->tune_pupdate_grid > 0 ? std::min(grid, ctx->sm_count * ctx->tune_pupdate_grid) : grid, kThreads, 0,
+                                       ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0, coarse_dev(*A.coarse));
     else
       cg_pupdate_coarse_kernel<S, 2><<<grid, kThreads, 0, ctx->stream>>>(A.nn, w.r.p, A.dinv, w.p.p, x, w.scal.p, 0,
                                                                          coarse_dev(*A.coarse));
