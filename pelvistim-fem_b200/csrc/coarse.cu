@@ -79,6 +79,59 @@ __device__ __forceinline__ bool last_block(unsigned int* ticket) {
   return s_last != 0;
 }
 
+// Sum of a task's 8 * NV per-lane accumulators over the row slots and store of the task's partials (shared by the restriction kernels).
+template <int S>
+__device__ __forceinline__ void restrict_reduce_store(const double (&acc)[8][S >= 2 ? 2 : 1], int lane, int pr, int64_t w,
+                                                      double* __restrict__ part) {
+  constexpr int NP = S >= 2 ? S / 2 : 1;
+  constexpr int NV = S >= 2 ? 2 : 1;
+  // Sum over the row slots (lanes with the same system pair).  Butterfly with halving: at every step a lane hands half of
+  // its remaining sums to its partner and receives the partner's half of the others, so 8*NV sums over 32/NP slots cost
+  // 8*NV - (what is left per lane) shuffles instead of 8*NV per step (14 instead of 48 for S = 8: the shuffles were
+  // half of this kernel's LSU wavefronts), and the sums end up spread over the lanes, which then store in parallel.
+  constexpr int NVAL = 8 * NV;
+  double v[NVAL];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int q = 0; q < NV; ++q) v[a * NV + q] = acc[a][q];
+  int base = 0;        // v[i] of this lane is sum number base + i
+  bool owner = true;   // false for the duplicates left by steps taken after a lane is down to one sum
+  {
+    int n = NVAL;
+#pragma unroll
+    for (int o = NP; o < 32; o <<= 1) {
+      const bool up = (lane & o) != 0;
+      if (n > 1) {
+#pragma unroll
+        for (int i = 0; i < NVAL / 2; ++i) {
+          if (i < n / 2) {
+            const double send = up ? v[i] : v[i + n / 2];
+            const double keep = up ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+          }
+        }
+        base += up ? n / 2 : 0;
+        n /= 2;
+      } else {
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+        owner = owner && !up;
+      }
+    }
+    if (owner) {
+      if (n >= 2 && NV == 2) {   // pairs (sum 2j, 2j+1) = corner j, both systems of this lane: one 16-byte store each
+#pragma unroll
+        for (int i = 0; i < NVAL; i += 2)
+          if (i < n) *reinterpret_cast<double2*>(part + ((size_t)w * 8 + (base + i) / 2) * S + 2 * pr) = make_double2(v[i], v[i + 1]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < NVAL; ++i)
+          if (i < n) part[((size_t)w * 8 + (base + i) / NV) * S + NV * pr + (base + i) % NV] = v[i];
+      }
+    }
+  }
+}
+
 // ---- restriction: per-cell partials -------------------------------------------------------------------------
 // One warp per task = (cell, split index); lane = (row slot, system pair).  part[task][corner][s] = sum over the
 // task's rows of w_corner(row) r[row][s]: registers and shuffles only, fixed order, no atomics.
@@ -241,51 +294,7 @@ __global__ void __launch_bounds__(256, OCC) restrict_cell_kernel(int64_t ntask, 
         }
       }
     }
-    // Sum over the row slots (lanes with the same system pair).  Butterfly with halving: at every step a lane hands half of
-    // its remaining sums to its partner and receives the partner's half of the others, so 8*NV sums over 32/NP slots cost
-    // 8*NV - (what is left per lane) shuffles instead of 8*NV per step (14 instead of 48 for S = 8: the shuffles were
-    // half of this kernel's LSU wavefronts), and the sums end up spread over the lanes, which then store in parallel.
-    constexpr int NVAL = 8 * NV;
-    double v[NVAL];
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-      for (int q = 0; q < NV; ++q) v[a * NV + q] = acc[a][q];
-    int base = 0;        // v[i] of this lane is sum number base + i
-    bool owner = true;   // false for the duplicates left by steps taken after a lane is down to one sum
-    {
-      int n = NVAL;
-#pragma unroll
-      for (int o = NP; o < 32; o <<= 1) {
-        const bool up = (lane & o) != 0;
-        if (n > 1) {
-#pragma unroll
-          for (int i = 0; i < NVAL / 2; ++i) {
-            if (i < n / 2) {
-              const double send = up ? v[i] : v[i + n / 2];
-              const double keep = up ? v[i + n / 2] : v[i];
-              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-            }
-          }
-          base += up ? n / 2 : 0;
-          n /= 2;
-        } else {
-          v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
-          owner = owner && !up;
-        }
-      }
-      if (owner) {
-        if (n >= 2 && NV == 2) {   // pairs (sum 2j, 2j+1) = corner j, both systems of this lane: one 16-byte store each
-#pragma unroll
-          for (int i = 0; i < NVAL; i += 2)
-            if (i < n) *reinterpret_cast<double2*>(part + ((size_t)w * 8 + (base + i) / 2) * S + 2 * pr) = make_double2(v[i], v[i + 1]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < NVAL; ++i)
-            if (i < n) part[((size_t)w * 8 + (base + i) / NV) * S + NV * pr + (base + i) % NV] = v[i];
-        }
-      }
-    }
+    restrict_reduce_store<S>(acc, lane, pr, w, part);
   }
   if constexpr (FUSE) {
     // r.D^-1 r and r.r per system: slot 2*tid + v of the block belongs to system (2*tid + v) mod S (NV == 2) / system 0; fixed
@@ -306,6 +315,219 @@ __global__ void __launch_bounds__(256, OCC) restrict_cell_kernel(int64_t ntask, 
     }
     if (last_block(fu.ticket)) {
       // thread t: slot t % 2S of blocks t / 2S, t / 2S + G, ...; then the G group sums in order
+      constexpr int G = 256 / (2 * S);
+      const int k = tid % (2 * S), g = tid / (2 * S);
+      double t = 0.0;
+      for (unsigned int b = g; b < gridDim.x; b += G) t += __ldcg(fu.partial + (size_t)b * 2 * S + k);
+      __syncthreads();
+      s_red[0][tid] = t;
+      __syncthreads();
+      if (tid < 2 * S) {
+        double tot = 0.0;
+        for (int gg = 0; gg < G; ++gg) tot += s_red[0][gg * 2 * S + tid];
+        if (tid < S) fu.out_rz[tid] = tot; else fu.out_rr[tid - S] = tot;
+      }
+    }
+  }
+}
+
+// ---- the fused update + restriction as a software pipeline (PTFEM_FUSE_PIPE) ---------------------------------------------
+// The kernel above is latency-bound (ncu r03: 67 % long-scoreboard stalls, SM 26 %, DRAM 41 %, 24 warps per SM at 80 registers):
+// a warp loads a trip's indices, waits, loads the rows, waits, computes, and only then starts the next trip.  Here every warp
+// owns a CONTIGUOUS run of tasks (its cell pointers sit in shared memory, so where a later trip starts costs no global load),
+// the row indices are fetched two trips ahead into registers, and the rows of r, q, the table entries and the inverse
+// diagonal of the NEXT trip are on their way into a shared-memory stage (cp.async, one group per trip, two stages) while the
+// current trip is decoded, accumulated and - at the end of a task - reduced and stored.  Same per-lane order of sums as above,
+// so the partials are bit-identical; r.D^-1 r and r.r group their per-thread sums by the contiguous runs.
+__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int S>
+struct PipeStage {   // one warp, one trip: two rows per lane group
+  static constexpr int RPW = 32 / (S / 2);
+  double2 ra[32], rb[32], qa[32], qb[32];
+  float4 ta[RPW], tb[RPW];
+  double da[RPW], db[RPW];
+};
+constexpr int kPipeTasks = 32;   // tasks per cached run of list ranges (two entries per task and warp)
+template <int S>
+constexpr size_t pipe_smem_bytes() { return 8 * (2 * sizeof(PipeStage<S>) + 64 * sizeof(int32_t)); }
+
+template <int S>
+__global__ void __launch_bounds__(256, 3) restrict_fused_pipe_kernel(int64_t ntask, int split, int shift, const int32_t* __restrict__ cellptr,
+                                                                    const int32_t* __restrict__ rows, const float4* __restrict__ ctab0,
+                                                                    double* __restrict__ part, FusedUpdate fu, int strided) {
+  static_assert(S >= 2, "two systems per lane");
+  constexpr int NP = S / 2, NV = 2, RPW = 32 / NP;
+  extern __shared__ __align__(16) unsigned char pipe_smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int pr = lane % NP, slot = lane / NP;
+  PipeStage<S>* stage = reinterpret_cast<PipeStage<S>*>(pipe_smem) + 2 * wid;
+  int32_t* cache = reinterpret_cast<int32_t*>(pipe_smem + 8 * 2 * sizeof(PipeStage<S>)) + 64 * wid;
+  const int64_t gw = (int64_t)blockIdx.x * 8 + wid, nw = (int64_t)gridDim.x * 8;
+  // the warp's k-th task: a contiguous run (strided == 0) or every nw-th task (neighbouring warps in neighbouring cells at a time)
+  const int64_t n_mine = strided ? (ntask > gw ? (ntask - gw + nw - 1) / nw : 0) : ntask / nw + (gw < ntask % nw ? 1 : 0);
+  const int64_t first = strided ? gw : ntask / nw * gw + min(gw, ntask % nw), step = strided ? nw : 1;
+  const int64_t t_begin = 0, t_end = n_mine;
+  const int stride = 2 * split * RPW, boff = split * RPW;
+  double alpha[NV], dz[NV], dr[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    alpha[v] = fu.alpha[NV * pr + v];
+    dz[v] = 0.0;
+    dr[v] = 0.0;
+  }
+  for (int64_t run0 = t_begin; run0 < t_end; run0 += kPipeTasks) {
+    const int tend = (int)min((int64_t)kPipeTasks, t_end - run0);   // tasks of this run, numbered from 0
+    __syncwarp();
+    if (lane < tend) {   // list range of the run's tasks: [cell start + split index * RPW, cell end)
+      const int64_t w = first + (run0 + lane) * step, c = w / split;
+      cache[2 * lane] = __ldg(cellptr + c) + (int)(w - c * split) * RPW;
+      cache[2 * lane + 1] = __ldg(cellptr + c + 1);
+    }
+    __syncwarp();
+    // a trip: task t, first list position `base` of its rows a (rows b follow at base + boff), end of the task's cell p1
+    auto task_desc = [&](int t, int32_t& base, int32_t& p1) {
+      base = cache[2 * t];
+      p1 = cache[2 * t + 1];
+    };
+    auto advance = [&](int& t, int32_t& base, int32_t& p1) {
+      base += stride;
+      if (base >= p1 && ++t < tend) task_desc(t, base, p1);
+    };
+    auto load_idx = [&](int t, int32_t base, int32_t p1, int32_t& ia, int32_t& ib) {
+      const int32_t pa = base + slot, pb = pa + boff;
+      ia = (t < tend && pa < p1) ? __ldg(rows + pa) : -1;
+      ib = (t < tend && pb < p1) ? __ldg(rows + pb) : -1;
+    };
+    auto issue = [&](PipeStage<S>& st, int32_t base, int32_t ia, int32_t ib) {
+      if (ia >= 0) {
+        cp_async16(&st.ra[lane], fu.r + (size_t)ia * S + 2 * pr);
+        cp_async16(&st.qa[lane], fu.q + (size_t)ia * S + 2 * pr);
+        if (pr == 0) {
+          cp_async16(&st.ta[slot], ctab0 + base + slot);
+          cp_async8(&st.da[slot], fu.dinv + ia);
+        }
+      }
+      if (ib >= 0) {
+        cp_async16(&st.rb[lane], fu.r + (size_t)ib * S + 2 * pr);
+        cp_async16(&st.qb[lane], fu.q + (size_t)ib * S + 2 * pr);
+        if (pr == 0) {
+          cp_async16(&st.tb[slot], ctab0 + base + boff + slot);
+          cp_async8(&st.db[slot], fu.dinv + ib);
+        }
+      }
+      cp_async_commit();
+    };
+    int t0 = 0, t1, t2;
+    int32_t b0, e0, b1, e1, b2, e2, ia0, ib0, ia1, ib1, ia2, ib2;
+    task_desc(t0, b0, e0);
+    load_idx(t0, b0, e0, ia0, ib0);
+    t1 = t0; b1 = b0; e1 = e0;
+    advance(t1, b1, e1);
+    load_idx(t1, b1, e1, ia1, ib1);
+    t2 = t1; b2 = b1; e2 = e1;
+    if (t2 < tend) advance(t2, b2, e2);
+    issue(stage[0], b0, ia0, ib0);
+    int s = 0;
+    double acc[8][NV];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int v = 0; v < NV; ++v) acc[a][v] = 0.0;
+    while (t0 < tend) {
+      issue(stage[s ^ 1], b1, ia1, ib1);          // next trip's rows on their way (an empty group past the end)
+      load_idx(t2, b2, e2, ia2, ib2);             // indices two trips ahead
+      cp_async_wait<1>();                         // this trip's group has landed
+      __syncwarp();                               // (table entry and inverse diagonal were fetched by the lane group's first lane)
+      const PipeStage<S>& st = stage[s];
+      int cc[3];
+      double t[3], wgt[8];
+      if (ia0 >= 0) {
+        const double2 rv = st.ra[lane], qv = st.qa[lane];
+        const double d = st.da[slot];
+        CoarseRaw raw;
+        raw.v = st.ta[slot];
+        double va[NV];
+        va[0] = fma(-alpha[0], qv.x, rv.x);
+        va[1] = fma(-alpha[1], qv.y, rv.y);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          dz[v] = fma(va[v] * d, va[v], dz[v]);
+          dr[v] = fma(va[v], va[v], dr[v]);
+        }
+        *reinterpret_cast<double2*>(fu.r + (size_t)ia0 * S + 2 * pr) = make_double2(va[0], va[1]);
+        const double live = coarse_row_decode(raw, shift, cc, t) ? 1.0 : 0.0;
+        coarse_weights(t, wgt);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) va[v] *= live;
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+          for (int v = 0; v < NV; ++v) acc[a][v] = fma(wgt[a], va[v], acc[a][v]);
+      }
+      if (ib0 >= 0) {
+        const double2 rv = st.rb[lane], qv = st.qb[lane];
+        const double d = st.db[slot];
+        CoarseRaw raw;
+        raw.v = st.tb[slot];
+        double vb[NV];
+        vb[0] = fma(-alpha[0], qv.x, rv.x);
+        vb[1] = fma(-alpha[1], qv.y, rv.y);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          dz[v] = fma(vb[v] * d, vb[v], dz[v]);
+          dr[v] = fma(vb[v], vb[v], dr[v]);
+        }
+        *reinterpret_cast<double2*>(fu.r + (size_t)ib0 * S + 2 * pr) = make_double2(vb[0], vb[1]);
+        const double live = coarse_row_decode(raw, shift, cc, t) ? 1.0 : 0.0;
+        coarse_weights(t, wgt);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) vb[v] *= live;
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+          for (int v = 0; v < NV; ++v) acc[a][v] = fma(wgt[a], vb[v], acc[a][v]);
+      }
+      if (b0 + stride >= e0) {                    // last trip of task t0 (a task without rows still stores its zeros)
+        restrict_reduce_store<S>(acc, lane, pr, first + (run0 + t0) * step, part);
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+          for (int v = 0; v < NV; ++v) acc[a][v] = 0.0;
+      }
+      __syncwarp();                               // every lane is done with stage s before the next trip but one refills it
+      t0 = t1; b0 = b1; e0 = e1; ia0 = ia1; ib0 = ib1;
+      t1 = t2; b1 = b2; e1 = e2; ia1 = ia2; ib1 = ib2;
+      if (t2 < tend) advance(t2, b2, e2);
+      s ^= 1;
+    }
+    cp_async_wait<0>();
+  }
+  {
+    // r.D^-1 r and r.r per system, as in restrict_cell_kernel<S, OCC, true>
+    __shared__ double s_red[2][NV * 256];
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      s_red[0][NV * tid + v] = dz[v];
+      s_red[1][NV * tid + v] = dr[v];
+    }
+    __syncthreads();
+    if (tid < 2 * S) {
+      const int qn = tid / S, sys = tid % S;
+      double t = 0.0;
+      for (int k = sys; k < NV * 256; k += S) t += s_red[qn][k];
+      fu.partial[(size_t)blockIdx.x * 2 * S + tid] = t;
+    }
+    if (last_block(fu.ticket)) {
       constexpr int G = 256 / (2 * S);
       const int k = tid % (2 * S), g = tid / (2 * S);
       double t = 0.0;
@@ -1192,7 +1414,24 @@ int apply_t(ptfem_ctx* ctx, CoarseSpace& cs, const double* r, const FusedUpdate*
       const int occ = ctx->tune_fuse_occ == 4 ? 4 : 3;
       const int per_sm = ctx->tune_fuse_grid > 0 ? std::min(ctx->tune_fuse_grid, 8) : occ;
       const int grid = (int)std::min<int64_t>((ntask + 7) / 8, (int64_t)ctx->sm_count * per_sm);
-      if (occ == 4)
+      bool piped = false;
+      if constexpr (S >= 2) {
+        if (ctx->tune_fuse_pipe) {
+          constexpr size_t smem = pipe_smem_bytes<S>();
+          const void* fn = reinterpret_cast<const void*>(&restrict_fused_pipe_kernel<S>);
+          auto it = ctx->func_smem.find(fn);
+          if (it == ctx->func_smem.end()) {
+            PT_CK(cudaFuncSetAttribute(restrict_fused_pipe_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctx->func_smem[fn] = smem;
+          }
+          const int pgrid = (int)std::min<int64_t>((ntask + 7) / 8, (int64_t)ctx->sm_count * (ctx->tune_fuse_grid > 0 ? std::min(ctx->tune_fuse_grid, 8) : 3));
+          restrict_fused_pipe_kernel<S><<<pgrid, 256, smem, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p,
+                                                                          L0.part.p, *fu, ctx->tune_fuse_pipe == 2 ? 1 : 0);
+          piped = true;
+        }
+      }
+      if (piped) {
+      } else if (occ == 4)
         restrict_cell_kernel<S, 4, true><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p, r,
                                                                         L0.part.p, *fu);
       else

@@ -313,6 +313,37 @@ def test_twolevel_preconditioner_matches_oracle(gpu_ctx, nrhs, levels):
     dm.close()
 
 
+@pytest.mark.parametrize("knobs", [{"PTFEM_FUSE_PIPE": "1"}, {"PTFEM_FUSE_PIPE": "2"}, {"PTFEM_FUSE_UPDATE": "0"},
+                                   {"PTFEM_FUSE_PREFETCH": "2", "PTFEM_FUSE_GRID": "8"}, {"PTFEM_SPLIT_X": "1"}, {"PTFEM_SPLIT_X": "2"}])
+def test_twolevel_kernel_variants_behind_knobs_give_the_same_solution(monkeypatch, knobs):
+    # the measured-and-kept-off variants of the coarse-grid PCG iteration (cp.async pipeline of the fused update + restriction with
+    # contiguous / strided task runs, unfused update, L2 prefetch, x-update on a side stream) solve the same systems: same answer
+    # as the oracle and the same Krylov iteration as the default kernels, summation order aside
+    m = meshgen.synth_slab("S", interfaces_as_103=False)
+    ref = fo.solve_case(m, SIGMA5, [(102, 0.0)], [(101, 10.0)], recover=None)["phi"]
+    out = {}
+    for name, env in (("default", {}), ("variant", knobs)):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ctx = engine.Context(0)
+        for nrhs in (3, 8):                         # padded to 4 and 8 interleaved systems
+            dm = dm_for(ctx, m)
+            dm.assemble(SIGMA5).bc_reset(nrhs)
+            for k in range(nrhs):
+                dm.neumann(101, 10.0 + k, rhs=k)
+            dm.dirichlet(102, 0.0)
+            phi = dm.solve(precond=engine.PRECOND_TWOLEVEL, coarse_nodes=300, coarse_levels=1)
+            assert dm.last_stats["converged"] == 1
+            for k in range(nrhs):
+                assert rel(phi[k], ref * (10.0 + k) / 10.0) < TOL_PHI, (name, nrhs, k)
+            out[name, nrhs] = (phi.copy(), dm.last_stats["iterations"])
+            dm.close()
+        ctx.close()
+    for nrhs in (3, 8):
+        assert abs(out["default", nrhs][1] - out["variant", nrhs][1]) <= 1
+        assert rel(out["variant", nrhs][0], out["default", nrhs][0]) < 1e-8
+
+
 @pytest.mark.parametrize("levels", [0, 1])
 def test_twolevel_iteration_count_matches_restatement(gpu_ctx, levels):
     # the preconditioner does not change the answer, so the way to check that the device builds the SAME operator as
