@@ -1093,9 +1093,17 @@ int ptfem_dist_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* x_loca
     d.warmed = true;
   }
   if (p2p) PT_CK(cudaMemsetAsync(d.mail.p->wait_ns, 0, sizeof(d.mail.p->wait_ns), ctx->stream));
-  cudaEvent_t e0, e1;
-  PT_CK(cudaEventCreate(&e0));
-  PT_CK(cudaEventCreate(&e1));
+  // the timing events go with the scope: every early return below (a failed launch, a timed-out wait, divergence) releases them
+  struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair() {
+      if (a) cudaEventDestroy(a);
+      if (b) cudaEventDestroy(b);
+    }
+  } evp;
+  PT_CK(cudaEventCreate(&evp.a));
+  PT_CK(cudaEventCreate(&evp.b));
+  const cudaEvent_t e0 = evp.a, e1 = evp.b;
   PT_CK(cudaEventRecord(e0, ctx->stream));
   if (p2p) {
     // ||b||^2 through the mailboxes, then iteration 0 (x = 0, r = b, u = D^-1 r, w = A u, first scalars)
@@ -1127,8 +1135,6 @@ int ptfem_dist_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* x_loca
     PT_CK(cudaStreamSynchronize(ctx->stream));
     if (p2p && *h_err) {
       d.p2p_broken = true;
-      cudaEventDestroy(e0);
-      cudaEventDestroy(e1);
       return set_err(PTFEM_ERR_STATE, "peer-memory solve: a cross-rank wait timed out (on this rank or a peer); the connection is out "
                                       "of step - reconnect (ptfem_dist_p2p_export / _connect on a new system) or use the NCCL transport");
     }
@@ -1156,8 +1162,11 @@ int ptfem_dist_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* x_loca
         ctx->launches = l0;
         d.xseq = x0;            // captured, not run
         d.graph_coarse = d.use_coarse;
-        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
-        if (rc) return rc;
+        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);   // always: an error above must not leave the stream capturing
+        if (rc) {
+          if (g) cudaGraphDestroy(g);
+          return rc;
+        }
         if (ce != cudaSuccess) return set_err(PTFEM_ERR_CUDA, "graph capture of the distributed iteration failed: %s", cudaGetErrorString(ce));
         ce = cudaGraphInstantiate(&d.graph, g, 0);
         cudaGraphDestroy(g);
@@ -1221,8 +1230,6 @@ int ptfem_dist_solve(ptfem_mesh* m, const ptfem_solve_opts* opts, double* x_loca
     t_ar = (float)((wn[1] + wn[2]) * per) * reps;
   }
   if (p2p) PT_TRY(read_scal());   // a wait of the last chunk may have timed out after the last read-back
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   if (ms_spmv) *ms_spmv = t_spmv / reps;
   if (ms_halo) *ms_halo = t_halo / reps;
   if (ms_allreduce) *ms_allreduce = t_ar / reps;

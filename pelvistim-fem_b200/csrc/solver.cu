@@ -1537,9 +1537,17 @@ int pcg_solve_t(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_o
                                                          w.ticket.p);
   PT_LAUNCH_CHECK(ctx);
 
-  cudaEvent_t ev0, ev1;
-  PT_CK(cudaEventCreate(&ev0));
-  PT_CK(cudaEventCreate(&ev1));
+  // the timing events go with the scope (an early return on a CUDA error below releases them)
+  struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair() {
+      if (a) cudaEventDestroy(a);
+      if (b) cudaEventDestroy(b);
+    }
+  } evp;
+  PT_CK(cudaEventCreate(&evp.a));
+  PT_CK(cudaEventCreate(&evp.b));
+  const cudaEvent_t ev0 = evp.a, ev1 = evp.b;
   PT_CK(cudaEventRecord(ev0, ctx->stream));
 
   const double rtol2 = o.rtol * o.rtol;
@@ -1686,8 +1694,6 @@ int pcg_solve_t(ptfem_ctx* ctx, const LinSys& A, PcgWork& w, const ptfem_solve_o
   cudaEventSynchronize(ev1);
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ev0, ev1);
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
   if (rc) return rc;
 
   // final true residual (already known when the loop ended on a restart's check: x has not moved since)
