@@ -238,6 +238,7 @@ int ptfem_ctx_create(int device, ptfem_ctx** out) {
   if (const char* e = getenv("PTFEM_FUSE_GRID")) c->tune_fuse_grid = atoi(e);
   if (const char* e = getenv("PTFEM_FUSE_PREFETCH")) c->tune_fuse_prefetch = atoi(e);
   if (const char* e = getenv("PTFEM_FUSE_PIPE")) c->tune_fuse_pipe = atoi(e);
+  if (const char* e = getenv("PTFEM_RESTRICT_GRID")) c->tune_restrict_grid = atoi(e);
   if (const char* e = getenv("PTFEM_SPLIT_X")) c->tune_split_x = atoi(e);
   if (const char* e = getenv("PTFEM_SPLIT_X_CTAS")) c->tune_split_x_ctas = atoi(e);
   if (const char* e = getenv("PTFEM_SPMM_WINDOW")) c->tune_window = atoi(e);

@@ -1438,7 +1438,7 @@ int apply_t(ptfem_ctx* ctx, CoarseSpace& cs, const double* r, const FusedUpdate*
         restrict_cell_kernel<S, 3, true><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p, r,
                                                                         L0.part.p, *fu);
     } else {
-    const int grid = (int)std::min<int64_t>((ntask + 7) / 8, (int64_t)ctx->sm_count * 32);
+    const int grid = (int)std::min<int64_t>((ntask + 7) / 8, (int64_t)ctx->sm_count * (ctx->tune_restrict_grid > 0 ? ctx->tune_restrict_grid : 32));
     if (ctx->tune_restrict_occ >= 6)
       restrict_cell_kernel<S, 6><<<grid, 256, 0, ctx->stream>>>(ntask, L0.split, L0.shift, L0.cellptr.p, L0.rows.p, cs.ctab0.p, r,
                                                                 L0.part.p, FusedUpdate());

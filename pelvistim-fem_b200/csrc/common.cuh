@@ -124,6 +124,7 @@ struct ptfem_ctx {
   int tune_fuse_update = 1;        // PTFEM_FUSE_UPDATE: CG residual update inside the restriction's gather (coarse-grid PCG, one matrix)
   int tune_fuse_occ = 3;           // PTFEM_FUSE_OCC: resident CTAs per SM the fused update + restriction is compiled for (3: 80 registers, 4: 64)
   int tune_fuse_grid = 0;          // PTFEM_FUSE_GRID: its CTAs per SM (0 = one wave of the resident CTAs; at most 8: the CG partial sums hold 8 per SM)
+  int tune_restrict_grid = 0;      // PTFEM_RESTRICT_GRID: CTAs per SM of the plain restriction's grid (0 = 32: eight waves of the 4 resident)
   int tune_fuse_pipe = 0;          // PTFEM_FUSE_PIPE: the fused update + restriction as a cp.async software pipeline (contiguous task runs per warp, next trip's rows in flight)
   int tune_fuse_prefetch = 0;      // PTFEM_FUSE_PREFETCH: the fused update + restriction asks the next trip's rows of r, q, dinv into L2 when their indices arrive
   int tune_split_x = 0;            // PTFEM_SPLIT_X: coarse-grid PCG updates x on a side stream while the grid hierarchy runs (1: forked after the product, 2: after the restriction); the p-update then leaves x alone
