@@ -107,7 +107,8 @@ def _read_v4(sec):
             for ln in L[i:i + cnt]:
                 f = ln.split()
                 nph = int(f[7])
-                phys[dim][int(f[0])] = [int(v) for v in f[8:8 + nph]]
+                # (a negative physical tag only says the entity enters the group with reversed orientation)
+                phys[dim][int(f[0])] = [abs(int(v)) for v in f[8:8 + nph]]
             i += cnt
     L = sec["Nodes"]
     nblocks, nn = int(L[0].split()[0]), int(L[0].split()[1])

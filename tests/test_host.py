@@ -2,6 +2,7 @@
 and VTU I/O, boundary-id detection, labels, sweep sharding, and the C-ABI library surface."""
 import ctypes
 import re
+from pathlib import Path
 
 import numpy as np
 import pytest
@@ -213,6 +214,106 @@ def test_msh41_reader(tmp_path):
     assert np.allclose(m.nodes[4], [1, 1, 1])                 # node tag 9 -> compact index 4
     assert (meshgen.tet_volumes(m.nodes, m.tets) > 0).all()
     assert m.tri_parent.tolist() == [0]
+
+
+def _write_msh41_the_way_gmsh_lays_it_out(path, m, names):
+    """MSH 4.1 ASCII with everything a file written by ``gmsh.write`` after an OpenCASCADE fragment carries and the hand-typed
+    sample above does not: point and curve entities (with their own line layouts) ahead of the surfaces, one surface / volume
+    entity per physical group plus an untagged surface, a NEGATIVE physical tag (reversed orientation), node blocks classified
+    by entity with parametric coordinates on curves and surfaces (extra u / u v columns), node tags numbered entity by entity
+    (not in the order the elements use them), and point / line element blocks that a 3-D conversion drops."""
+    rng = np.random.default_rng(5)
+    bcs, regs = sorted(set(m.bcid.tolist())), sorted(set(m.region.tolist()))
+    lo, hi = m.nodes.min(axis=0), m.nodes.max(axis=0)
+    bb = " ".join(f"{v:.16g}" for v in (*lo, *hi))
+    surf_ent = {b: 10 + k for k, b in enumerate(bcs)}
+    vol_ent = {r: 1 + k for k, r in enumerate(regs)}
+    L = ["$MeshFormat", "4.1 0 8", "$EndMeshFormat", "$PhysicalNames", str(len(bcs) + len(regs))]
+    L += [f'2 {b} "{names.get(b, "b%d" % b)}"' for b in bcs] + [f'3 {r} "body{r}"' for r in regs] + ["$EndPhysicalNames"]
+    L += ["$Entities", f"2 1 {len(bcs) + 1} {len(regs)}",
+          f"1 {lo[0]:.16g} {lo[1]:.16g} {lo[2]:.16g} 0", f"2 {hi[0]:.16g} {hi[1]:.16g} {hi[2]:.16g} 0",
+          f"1 {bb} 0 2 1 -2"]
+    for k, b in enumerate(bcs):
+        L.append(f"{surf_ent[b]} {bb} 1 {-b if k == 0 else b} 1 1")
+    L.append(f"99 {bb} 0 1 1")                                     # a surface without a physical group
+    for r in regs:
+        L.append(f"{vol_ent[r]} {bb} 1 {r} {len(bcs)} " + " ".join(str(surf_ent[b]) for b in bcs))
+    L.append("$EndEntities")
+    # classify nodes: first node -> point entity 1, next three -> curve 1, nodes of boundary triangles -> their surface, rest -> volume
+    owner = np.full(m.nn, -1)
+    kind = {}
+    owner[0], kind[0] = 0, (0, 1)
+    for i in (1, 2, 3):
+        owner[i], kind[i] = 1, (1, 1)
+    for t, b in zip(m.tris, m.bcid):
+        for i in t:
+            if owner[i] < 0:
+                owner[i], kind[i] = 2, (2, surf_ent[int(b)])
+    first_tet = {}
+    for e, t in enumerate(m.tets):
+        for i in t:
+            first_tet.setdefault(int(i), e)
+    for i in range(m.nn):
+        if owner[i] < 0:
+            owner[i], kind[i] = 3, (3, vol_ent[int(m.region[first_tet[i]])])
+    blocks = {}
+    for i in range(m.nn):
+        blocks.setdefault(kind[i], []).append(i)
+    tag = np.zeros(m.nn, dtype=np.int64)
+    nxt = 1
+    node_lines = []
+    for key in sorted(blocks):
+        ids = blocks[key]
+        dim = key[0]
+        par = 1 if dim in (1, 2) else 0
+        node_lines.append(f"{dim} {key[1]} {par} {len(ids)}")
+        for i in ids:
+            tag[i] = nxt
+            nxt += 1
+        node_lines += [str(tag[i]) for i in ids]
+        for i in ids:
+            x = " ".join(f"{v:.17g}" for v in m.nodes[i])
+            node_lines.append(x + ("" if not par else " " + " ".join(f"{v:.6g}" for v in rng.random(dim))))
+    L += ["$Nodes", f"{len(blocks)} {m.nn} 1 {m.nn}"] + node_lines + ["$EndNodes"]
+    eb, et = [], 1
+    eb.append("0 1 15 1"); eb.append(f"{et} {tag[0]}"); et += 1                               # a point element
+    eb.append("1 1 1 2"); eb += [f"{et} {tag[1]} {tag[2]}", f"{et + 1} {tag[2]} {tag[3]}"]; et += 2   # two line elements
+    for b in bcs:
+        sel = np.nonzero(m.bcid == b)[0]
+        eb.append(f"2 {surf_ent[b]} 2 {len(sel)}")
+        for k in sel:
+            eb.append(f"{et} " + " ".join(str(tag[i]) for i in m.tris[k])); et += 1
+    eb.append("2 99 2 1"); eb.append(f"{et} " + " ".join(str(tag[i]) for i in m.tris[0])); et += 1   # triangle on the untagged surface
+    for r in regs:
+        sel = np.nonzero(m.region == r)[0]
+        eb.append(f"3 {vol_ent[r]} 4 {len(sel)}")
+        for k in sel:
+            eb.append(f"{et} " + " ".join(str(tag[i]) for i in m.tets[k])); et += 1
+    nblk = 2 + len(bcs) + 1 + len(regs)
+    L += ["$Elements", f"{nblk} {et - 1} 1 {et - 1}"] + eb + ["$EndElements"]
+    Path(path).write_text("\n".join(L) + "\n")
+
+
+def test_msh41_reader_on_a_file_laid_out_as_gmsh_writes_it(tmp_path):
+    from pelvistim_fem_b200 import gmsh_io
+    m = meshgen.synth_slab("XS")
+    _write_msh41_the_way_gmsh_lays_it_out(tmp_path / "mesh.msh", m, {101: "active", 102: "return", 103: "interfaces"})
+    r = gmsh_io.read_msh(tmp_path / "mesh.msh")
+    assert (r.nn, r.nt, r.nb) == (m.nn, m.nt, m.nb)                # untagged triangle, point and line elements dropped
+    assert sorted(set(r.bcid.tolist())) == sorted(set(m.bcid.tolist()))          # named groups keep their ids, sign dropped
+    assert np.array_equal(np.sort(r.nodes.view([("", r.nodes.dtype)] * 3), axis=0), np.sort(m.nodes.view([("", m.nodes.dtype)] * 3), axis=0))
+    vol = lambda q: {int(k): float(meshgen.tet_volumes(q.nodes, q.tets)[q.region == k].sum()) for k in set(q.region.tolist())}
+    va, vb = vol(m), vol(r)
+    assert va.keys() == vb.keys() and all(abs(va[k] - vb[k]) <= 1e-12 * abs(va[k]) for k in va)
+    area = lambda q: {int(k): float(0.5 * np.linalg.norm(np.cross(q.nodes[q.tris[q.bcid == k]][:, 1] - q.nodes[q.tris[q.bcid == k]][:, 0],
+                                                                   q.nodes[q.tris[q.bcid == k]][:, 2] - q.nodes[q.tris[q.bcid == k]][:, 0]), axis=1).sum())
+                      for k in set(q.bcid.tolist())}
+    aa, ab = area(m), area(r)
+    assert aa.keys() == ab.keys() and all(abs(aa[k] - ab[k]) <= 1e-12 * abs(aa[k]) for k in aa)
+    assert (meshgen.tet_volumes(r.nodes, r.tets) > 0).all() and (r.tri_parent >= 0).all()
+    # and the conversion the reference runs on it gives the same Elmer mesh as from the 2.2 file of the same mesh
+    out = gmsh_io.elmergrid_14_2(tmp_path / "mesh.msh", tmp_path / "elmer_mesh")
+    assert (tmp_path / "elmer_mesh" / "mesh.header").exists() and out.nt == m.nt
 
 
 def test_msh22_roundtrip_and_elmergrid_shim(tmp_path):
