@@ -344,6 +344,34 @@ def test_twolevel_kernel_variants_behind_knobs_give_the_same_solution(monkeypatc
         assert rel(out["variant", nrhs][0], out["default", nrhs][0]) < 1e-8
 
 
+def test_restriction_with_several_tasks_per_cell(monkeypatch):
+    # few, large cells (size M with the exactly inverted grid only: ~190 cells of ~2000 rows) make the restriction share a cell
+    # among several warps (split > 1); fused, unfused and pipelined kernels against the Jacobi solve (scripts/gpu_split_check.py)
+    m = meshgen.synth_slab("M")
+    ref, its = None, []
+    for env in ({}, {"PTFEM_FUSE_UPDATE": "0"}, {"PTFEM_FUSE_PIPE": "2"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ctx = engine.Context(0)
+        dm = dm_for(ctx, m)
+        dm.assemble(SIGMA5).bc_reset(3)
+        for k in range(3):
+            dm.neumann(101, 10.0 + k, rhs=k)
+        dm.dirichlet(102, 0.0)
+        if ref is None:
+            ref = dm.solve(precond=engine.PRECOND_JACOBI, rtol=1e-11).copy()
+        phi = dm.solve(precond=engine.PRECOND_TWOLEVEL, coarse_nodes=300, coarse_levels=0, rtol=1e-11)
+        assert _met_or_attained(dm.last_stats, 1e-11)
+        its.append(dm.last_stats["iterations"])
+        for k in range(3):
+            assert rel(phi[k], ref[k]) < 1e-7, (env, k)
+        dm.close()
+        ctx.close()
+        for k in env:
+            monkeypatch.delenv(k)
+    assert max(its) - min(its) <= 1
+
+
 @pytest.mark.parametrize("levels", [0, 1])
 def test_twolevel_iteration_count_matches_restatement(gpu_ctx, levels):
     # the preconditioner does not change the answer, so the way to check that the device builds the SAME operator as
