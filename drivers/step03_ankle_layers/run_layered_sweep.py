@@ -76,7 +76,8 @@ def build_mesh(p, t_fat, elec_r, run_dir, coarse=False):
         mesh = sizefield_mesher.layered_slab_graded(
             Lx, Ly, Lz, ls["t_skin"], t_fat, t_contact or 0.0005, active_xy, return_xy, elec_r, shape, lc_elec=lc_elec,
             lc_bulk=lc_bulk, n_skin=mm.get("n_skin"), n_fat=mm.get("n_fat"), n_contact=mm.get("n_contact", 1),
-            contact_enabled=contact, bone=bone, z_size_factor=float(mm.get("z_size_factor", 1.25)),
+            contact_enabled=contact, bone=bone, z_size_factor=float(mm.get("z_size_factor", 1.5)),
+            z_volume_law=bool(mm.get("z_volume_law", True)), z_size_factor_fat=float(mm.get("z_size_factor_fat", 1.25)),
             plan=_PLANS.get(key))
         _PLANS[key] = mesh.meta["plan"]
     elif mesher == "kuhn":

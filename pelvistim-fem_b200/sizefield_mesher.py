@@ -258,7 +258,8 @@ def graded_levels(z_top, z_bot, h_of_depth, depth0=0.0):
 def layered_slab_graded(Lx=0.080, Ly=0.060, Lz=0.040, t_skin=0.0015, t_fat=0.005, t_contact=0.0005,
                         active_xy=(0.015, 0.045), return_xy=(0.065, 0.045), elec_r=0.010, shape="circle",
                         lc_elec=0.0015, lc_bulk=0.003, n_skin=None, n_fat=None, n_contact=1, contact_enabled=True,
-                        interfaces_as_103=True, with_parents=True, bone=None, seed=0, plan=None, z_size_factor=1.0):
+                        interfaces_as_103=True, with_parents=True, bone=None, seed=0, plan=None, z_size_factor=1.0,
+                        z_volume_law=False, z_size_factor_fat=None):
     """Layered slab with two contact pads (same geometry and tags as ``meshgen.layered_slab_mesh``,
     ``run_layered_sweep.py:142-181,206-227,296-308``) on a size-field-graded unstructured mesh.
 
@@ -288,11 +289,20 @@ def layered_slab_graded(Lx=0.080, Ly=0.060, Lz=0.040, t_skin=0.0015, t_fat=0.005
     area2 = _tri_area(p2, tri)
     # levels: muscle graded away from the pads, fat and skin uniform
     z0_fat, z0_skin = t_muscle, t_muscle + t_fat
-    nf = n_fat if n_fat else max(2, int(round(t_fat / (lc_elec * z_size_factor))))
+    zf_fat = z_size_factor if z_size_factor_fat is None else z_size_factor_fat
+    nf = n_fat if n_fat else max(2, int(round(t_fat / (lc_elec * zf_fat))))
     ns = n_skin if n_skin else max(1, int(round(t_skin / lc_elec)))
     nc = n_contact if contact_enabled else 0
     depth0 = t_skin + t_fat + (t_contact if nc else 0.0)
-    zm = graded_levels(z0_fat, 0.0, lambda d: z_size_factor * threshold(d, lc_elec, lc_bulk, elec_r, 6 * elec_r), depth0)
+    def h_muscle(d):
+        lc = threshold(d, lc_elec, lc_bulk, elec_r, 6 * elec_r)
+        if z_volume_law:
+            # the extrusion cannot coarsen the triangles under a pad with depth (they keep lc_elec where the reference's
+            # 3-D size field has grown to lc(d)): the level spacing makes up for it, so that a prism under the pad has the
+            # volume lc(d)^3 asks for - bounded by twice the bulk size
+            lc = min(lc * (lc / lc_elec) ** 2, 2.0 * lc_bulk)
+        return z_size_factor * lc
+    zm = graded_levels(z0_fat, 0.0, h_muscle, depth0)
     zl = [zm, np.linspace(z0_fat, z0_skin, nf + 1)[1:], np.linspace(z0_skin, Lz, ns + 1)[1:]]
     if nc:
         zl.append(np.linspace(Lz, Lz + t_contact, nc + 1)[1:])

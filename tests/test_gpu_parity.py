@@ -1021,9 +1021,10 @@ def test_step04_driver_reproduces_reference_table(gpu_ctx, golden, tmp_path):
         assert r["pressure_label"] == g["pressure_label"] and r["sigma_contact_Spm"] == g["sigma_contact_Spm"]
         assert r["jn_used_A_m2"] == g["jn_used_A_m2"]                 # the rim polygon has the reference's area: 3.1299 cm2
         # size-field mesh: potential-driven columns to a fraction of a %, the pad-rim peaks (up to +98 % on the structured mesh
-        # of round 1) within 16 %; the nodal-J pad integrals and the smoothed ROI field stay mesh-layout dependent
+        # of round 1) within 16 %; the count-weighted ROI field within 6 % since the level spacing follows the reference's
+        # cell density in the ROI (-12 % before; the same rows through the CPU oracle: profiles/r03_tables_cpu_oracle.txt)
         for k, tol in (("compliance_V", 0.015), ("contact_impedance_ohm", 0.015), ("I_active_A", 0.003), ("I_return_A", 0.025),
-                       ("roi_mean_J", 0.04), ("roi_mean_E", 0.14), ("peak_J_skin_with_elec", 0.15), ("peak_J_skin_no_elec", 0.17)):
+                       ("roi_mean_J", 0.04), ("roi_mean_E", 0.08), ("peak_J_skin_with_elec", 0.15), ("peak_J_skin_no_elec", 0.17)):
             assert abs(r[k] - g[k]) / abs(g[k]) < tol, (r["pressure_label"], k, r[k], g[k])
         assert r["flux_err"] < 0.03                                   # the judge's bar of round 1 (reference: 0.000 .. 0.010)
         assert r["exceeded_compliance"] == g["exceeded_compliance"] and r["exceeds_charge_limit"] == g["exceeds_charge_limit"]
@@ -1060,7 +1061,8 @@ def test_step03_driver_reproduces_reference_table(gpu_ctx, golden, tmp_path, mon
     for r, g in zip(rows, gold):
         assert list(r.keys()) == list(g.keys()) and (r["t_fat_mm"], r["elec_r_mm"]) == (g["t_fat_mm"], g["elec_r_mm"])
         assert r["elec_area_mesh_cm2"] == g["elec_area_mesh_cm2"] and r["jn_used"] == g["jn_used"]   # same rim polygons
-        for k, tol in (("compliance_V", 0.015), ("total_current_A", 0.02), ("I_return_A", 0.08), ("roi_mean_J", 0.07),
+        for k, tol in (("compliance_V", 0.015), ("total_current_A", 0.02), ("I_return_A", 0.08), ("roi_mean_J", 0.075),
+                       ("roi_mean_E", 0.11),    # +-6 % on eight rows, +9.8 % where the fat / muscle interface cuts the ROI centre under the 5 mm pad
                        ("peak_J_skin_with_elec", 0.05), ("peak_J_skin_no_elec", 0.25), ("roi_center_z_mm", 1e-12),
                        ("dist_fat_muscle_mm", 1e-12)):
             assert abs(r[k] - g[k]) <= tol * abs(g[k]), (r["t_fat_mm"], r["elec_r_mm"], k, r[k], g[k])
